@@ -1,0 +1,32 @@
+# Builds libbgn_b200.so (sm_100a only) and the CPU-side test / oracle helpers.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+LIMBS     := 3 5 9 17 33
+SRC       := bgn_b200/csrc
+OBJ       := build
+HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h) include/bgn_b200.h
+OBJS      := $(OBJ)/api.o $(foreach l,$(LIMBS),$(OBJ)/inst_a_$(l).o $(OBJ)/inst_b_$(l).o)
+LIB       := bgn_b200/libbgn_b200.so
+
+all: $(LIB)
+
+$(OBJ)/inst_a_%.o: $(SRC)/inst_a.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DBGN_L=$* -c $< -o $@ 2> $(OBJ)/inst_a_$*.log || (tail -30 $(OBJ)/inst_a_$*.log; false)
+
+$(OBJ)/inst_b_%.o: $(SRC)/inst_b.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DBGN_L=$* -c $< -o $@ 2> $(OBJ)/inst_b_$*.log || (tail -30 $(OBJ)/inst_b_$*.log; false)
+
+$(OBJ)/api.o: $(SRC)/api.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/api.log || (tail -30 $(OBJ)/api.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+clean:
+	rm -rf $(OBJ) $(LIB)
+
+.PHONY: all clean

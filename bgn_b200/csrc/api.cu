@@ -1,0 +1,1210 @@
+// api.cu -- C-ABI (include/bgn_b200.h), context management and host-side
+// orchestration of the kernels in kernels.cuh.  No CPU arithmetic fallback: the
+// host only computes the handful of Montgomery constants a key needs (shifts,
+// adds and compares on small big-integers) and drives the device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bgn_b200.h"
+#include "ops.h"
+
+// ---------------------------------------------------------------- host bigint
+namespace {
+typedef std::vector<uint32_t> Big;  // little-endian limbs, fixed length per use
+
+Big big_from_be(const uint8_t* b, size_t len, size_t limbs) {
+  Big r(limbs, 0);
+  for (size_t i = 0; i < len; i++) {
+    size_t pos = len - 1 - i;  // byte significance
+    if (pos / 4 < limbs) r[pos / 4] |= (uint32_t)b[i] << (8 * (pos % 4));
+  }
+  return r;
+}
+int big_bits(const Big& a) {
+  for (int i = (int)a.size() - 1; i >= 0; i--)
+    if (a[i]) return 32 * i + 32 - __builtin_clz(a[i]);
+  return 0;
+}
+int big_cmp(const Big& a, const Big& b) {
+  for (int i = (int)a.size() - 1; i >= 0; i--)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+uint32_t big_add(Big& r, const Big& a, const Big& b) {
+  uint64_t c = 0;
+  for (size_t i = 0; i < r.size(); i++) {
+    c += (uint64_t)a[i] + b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return (uint32_t)c;
+}
+void big_sub(Big& r, const Big& a, const Big& b) {
+  int64_t c = 0;
+  for (size_t i = 0; i < r.size(); i++) {
+    c += (int64_t)a[i] - b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+}
+// r = 2a mod p (a < p)
+void big_dbl_mod(Big& a, const Big& p) {
+  Big t(a.size());
+  uint32_t carry = big_add(t, a, a);
+  if (carry || big_cmp(t, p) >= 0) big_sub(t, t, p);
+  a = t;
+}
+// signed-digit (NAF) expansion, most significant digit first
+std::vector<int8_t> big_naf(Big n) {
+  std::vector<int8_t> d;
+  n.push_back(0);
+  auto is_zero = [&]() {
+    for (uint32_t w : n)
+      if (w) return false;
+    return true;
+  };
+  while (!is_zero()) {
+    int8_t z = 0;
+    if (n[0] & 1) {
+      z = (int8_t)(2 - (int)(n[0] & 3));
+      // n -= z
+      if (z > 0) {
+        uint64_t i = 0;
+        while (n[i] == 0) n[i++] = 0xffffffffu;
+        n[i] -= 1;
+      } else {
+        size_t i = 0;
+        while (++n[i] == 0) i++;
+      }
+    }
+    d.push_back(z);
+    for (size_t i = 0; i + 1 < n.size(); i++) n[i] = (n[i] >> 1) | (n[i + 1] << 31);
+    n.back() >>= 1;
+  }
+  std::reverse(d.begin(), d.end());
+  return d;
+}
+
+const int kSupportedL[] = {3, 5, 9, 17, 33};
+
+std::mutex g_mu;                         // serialises device work of this library in the process
+std::map<int, const bgn_ctx*> g_active;  // device -> context whose constants are resident
+}  // namespace
+
+// ---------------------------------------------------------------- context
+struct KTime {
+  double ms = 0;
+  uint64_t launches = 0;
+};
+
+struct bgn_ctx {
+  int device = 0;
+  int L = 0, B = 0, nbytes = 0;
+  const LOpsA* A = nullptr;
+  const LOpsB* Bo = nullptr;
+  FieldConsts fc;
+  PairConsts pc;
+  cudaStream_t stream = nullptr;
+  // generators (affine Montgomery, SoA with N = 1) and window tables
+  uint32_t *dPx = nullptr, *dPy = nullptr, *dQx = nullptr, *dQy = nullptr;
+  uint8_t *dPinf = nullptr, *dQinf = nullptr;
+  uint32_t *tabP = nullptr, *tabQ = nullptr;
+  // decryption
+  bool has_secret = false;
+  uint32_t *bs_elems = nullptr, *bs_slots = nullptr, *bs_ginv = nullptr;
+  uint32_t bs_S = 0, bs_hmask = 0, bs_giant = 0;
+  uint64_t bs_mmax = 0;
+  // workspace arena (grow-only)
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+  // instrumentation
+  bool timing = false;
+  std::map<std::string, KTime> ktimes;
+  struct Pending {
+    std::string name;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  uint64_t total_launches = 0;
+  std::string err;
+};
+
+namespace {
+
+struct CudaErr {
+  std::string msg;
+};
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaErr{std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)}; \
+  } while (0)
+struct ArgErr {
+  std::string msg;
+};
+
+void activate(bgn_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  auto it = g_active.find(c->device);
+  if (it == g_active.end() || it->second != c) {
+    CK(c->A->upload(&c->fc, &c->pc, c->stream));
+    CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    g_active[c->device] = c;
+  }
+}
+void reupload_pc(bgn_ctx* c) {
+  CK(c->A->upload(&c->fc, &c->pc, c->stream));
+  CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+}
+
+// ---- arena
+void arena_reset(bgn_ctx* c) { c->arena_off = 0; }
+void arena_reserve(bgn_ctx* c, size_t bytes) {
+  if (bytes <= c->arena_cap) return;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->arena) CK(cudaFree(c->arena));
+  c->arena = nullptr;
+  c->arena_cap = 0;
+  size_t cap = bytes + bytes / 8 + (1 << 20);
+  CK(cudaMalloc(&c->arena, cap));
+  c->arena_cap = cap;
+}
+template <typename T>
+T* arena_get(bgn_ctx* c, size_t n) {
+  size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+  if (c->arena_off + bytes > c->arena_cap) throw CudaErr{"internal: arena overflow"};
+  T* p = reinterpret_cast<T*>(c->arena + c->arena_off);
+  c->arena_off += bytes;
+  return p;
+}
+size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---- instrumented launch
+struct Timer {
+  bgn_ctx* c;
+  bool on;
+  cudaEvent_t a = nullptr, b = nullptr;
+  std::string name;
+  Timer(bgn_ctx* c_, const char* name_) : c(c_), on(c_->timing), name(name_) {
+    c->total_launches++;
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->ev_pool.empty()) {
+        e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+      } else {
+        CK(cudaEventCreate(&e));
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    CK(cudaEventRecord(a, c->stream));
+  }
+  void done() {
+    CK(cudaGetLastError());
+    if (!on) return;
+    CK(cudaEventRecord(b, c->stream));
+    c->pending.push_back({name, a, b});
+  }
+};
+void finish(bgn_ctx* c) {
+  CK(cudaStreamSynchronize(c->stream));
+  for (auto& p : c->pending) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, p.a, p.b));
+    KTime& k = c->ktimes[p.name];
+    k.ms += ms;
+    k.launches++;
+    c->ev_pool.push_back(p.a);
+    c->ev_pool.push_back(p.b);
+  }
+  c->pending.clear();
+}
+
+LaunchCfg cfg(bgn_ctx* c, size_t grid, unsigned block, size_t smem = 0) {
+  return LaunchCfg{(unsigned)grid, block, smem, c->stream};
+}
+unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ---- device arrays
+struct G1Arr {
+  uint32_t *x = nullptr, *y = nullptr;
+  uint8_t* inf = nullptr;
+  size_t N = 0;
+};
+struct JacArr {
+  uint32_t *X = nullptr, *Y = nullptr, *Z = nullptr;
+  size_t N = 0;
+};
+struct GtArr {
+  uint32_t *re = nullptr, *im = nullptr;
+  size_t N = 0;
+};
+size_t g1_bytes(bgn_ctx* c, size_t n) { return 2 * pad256(n * c->L * 4) + pad256(n); }
+size_t jac_bytes(bgn_ctx* c, size_t n) { return 3 * pad256(n * c->L * 4); }
+size_t gt_bytes(bgn_ctx* c, size_t n) { return 2 * pad256(n * c->L * 4); }
+size_t io_bytes(bgn_ctx* c, size_t n) { return pad256(n * 2 * c->B); }
+
+G1Arr g1_alloc(bgn_ctx* c, size_t n) {
+  G1Arr a;
+  a.N = n;
+  a.x = arena_get<uint32_t>(c, n * c->L);
+  a.y = arena_get<uint32_t>(c, n * c->L);
+  a.inf = arena_get<uint8_t>(c, n);
+  return a;
+}
+JacArr jac_alloc(bgn_ctx* c, size_t n) {
+  JacArr a;
+  a.N = n;
+  a.X = arena_get<uint32_t>(c, n * c->L);
+  a.Y = arena_get<uint32_t>(c, n * c->L);
+  a.Z = arena_get<uint32_t>(c, n * c->L);
+  return a;
+}
+GtArr gt_alloc(bgn_ctx* c, size_t n) {
+  GtArr a;
+  a.N = n;
+  a.re = arena_get<uint32_t>(c, n * c->L);
+  a.im = arena_get<uint32_t>(c, n * c->L);
+  return a;
+}
+
+// stage a caller buffer on the device (no copy if it already is a device pointer)
+const uint8_t* stage_in(bgn_ctx* c, const void* p, size_t bytes) {
+  if (bytes == 0) return nullptr;
+  if (is_device_ptr(p)) return static_cast<const uint8_t*>(p);
+  uint8_t* d = arena_get<uint8_t>(c, bytes);
+  CK(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream));
+  return d;
+}
+struct OutBuf {
+  uint8_t* dev;
+  void* host;  // null when the caller gave a device pointer
+  size_t bytes;
+};
+OutBuf stage_out(bgn_ctx* c, void* p, size_t bytes) {
+  OutBuf o{nullptr, nullptr, bytes};
+  if (bytes == 0) return o;
+  if (is_device_ptr(p)) {
+    o.dev = static_cast<uint8_t*>(p);
+  } else {
+    o.dev = arena_get<uint8_t>(c, bytes);
+    o.host = p;
+  }
+  return o;
+}
+void commit_out(bgn_ctx* c, const OutBuf& o) {
+  if (o.host && o.bytes) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// ---- kernel wrappers
+void g1_from_bytes(bgn_ctx* c, const uint8_t* d_in, size_t count, const G1Arr& a) {
+  if (!count) return;
+  Timer t(c, "k_g1_from_bytes");
+  c->Bo->g1_from_bytes(cfg(c, nblk(count, 128), 128, 0), d_in, c->B, count, a.x, a.y, a.inf, a.N);
+  t.done();
+}
+void g1_to_bytes(bgn_ctx* c, const G1Arr& a, size_t count, uint8_t* d_out) {
+  if (!count) return;
+  Timer t(c, "k_g1_to_bytes");
+  c->Bo->g1_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.x, a.y, a.inf, a.N, count, d_out, c->B);
+  t.done();
+}
+void gt_from_bytes(bgn_ctx* c, const uint8_t* d_in, size_t count, const GtArr& a) {
+  if (!count) return;
+  Timer t(c, "k_fp2_from_bytes");
+  c->A->fp2_from_bytes(cfg(c, nblk(count, 128), 128, 0), d_in, c->B, count, a.re, a.im, a.N);
+  t.done();
+}
+void gt_to_bytes(bgn_ctx* c, const GtArr& a, size_t count, uint8_t* d_out) {
+  if (!count) return;
+  Timer t(c, "k_fp2_to_bytes");
+  c->A->fp2_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.re, a.im, a.N, count, d_out, c->B);
+  t.done();
+}
+
+// Jacobian -> affine; output either SoA (G1Arr) or AoS table
+void normalize(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, uint32_t* ox, uint32_t* oy,
+               size_t estride, size_t lstride, uint8_t* inf) {
+  if (!count) return;
+  NormArgs a;
+  a.X = j.X;
+  a.Y = j.Y;
+  a.Z = j.Z;
+  a.scratch = scratch;
+  a.count = count;
+  a.N = j.N;
+  size_t G = (count + 63) / 64;
+  if (G < 4096) G = std::min<size_t>(count, 4096);  // small batches: favour parallelism over shared inversions
+  a.G = (int)G;
+  a.ox = ox;
+  a.oy = oy;
+  a.o_estride = estride;
+  a.o_lstride = lstride;
+  a.inf = inf;
+  Timer t(c, "k_normalize");
+  c->Bo->normalize(cfg(c, nblk(G, 128), 128, 0), a);
+  t.done();
+}
+void normalize_soa(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, const G1Arr& o) {
+  normalize(c, j, count, scratch, o.x, o.y, 1, o.N, o.inf);
+}
+
+// the Miller team kernel; dM <= dE
+void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
+                const GtArr& out) {
+  if (!count) return;
+  size_t per_thread = (size_t)BGN_MILLER_NSLOT * c->L * 4 + 2;
+  int TS = dE;
+  size_t budget2 = 113000, budget1 = 227 * 1024 - 1024;
+  int nt_max = (int)std::min<size_t>(144, budget2 / per_thread);
+  int teams = nt_max / TS;
+  if (teams == 0) {
+    nt_max = (int)std::min<size_t>(160, budget1 / per_thread);
+    teams = nt_max / TS;
+  }
+  if (teams == 0) throw ArgErr{"polynomial has too many coefficients for one thread block"};
+  if (TS == 1) teams = std::min(teams, 128);
+  int nt = teams * TS;
+  size_t smem = per_thread * nt + 16;
+  MillerArgs a;
+  a.Mx = M.x;
+  a.My = M.y;
+  a.Minf = M.inf;
+  a.NM = (int)M.N;
+  a.Ex = E.x;
+  a.Ey = E.y;
+  a.Einf = E.inf;
+  a.NE = (int)E.N;
+  a.e_bcast = e_bcast;
+  a.out_re = out.re;
+  a.out_im = out.im;
+  a.NOUT = (int)out.N;
+  a.dM = dM;
+  a.dE = dE;
+  a.out_slots = out_slots;
+  a.count = (int)count;
+  a.teams_per_block = teams;
+  Timer t(c, "k_miller");
+  CK(c->A->miller_set_smem(smem));
+  c->A->miller(cfg(c, nblk(count, teams), nt, smem), a);
+  t.done();
+}
+
+void check_count(size_t count) {
+  if (count > ((size_t)1 << 27)) throw ArgErr{"batch too large (max 2^27 elements per call)"};
+}
+
+// builds a 255-entry-per-window table for the base point (bx, by) (device, Montgomery, N = 1)
+void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* tab) {
+  size_t nent = (size_t)nwin * 255;
+  arena_reset(c);
+  arena_reserve(c, jac_bytes(c, nwin) + g1_bytes(c, nwin) + jac_bytes(c, nent) + 2 * pad256(nent * c->L * 4) + 4096);
+  JacArr jb = jac_alloc(c, nwin);
+  G1Arr ab = g1_alloc(c, nwin);
+  JacArr je = jac_alloc(c, nent);
+  uint32_t* scratch = arena_get<uint32_t>(c, nent * c->L);
+  {
+    Timer t(c, "k_tab_bases");
+    c->Bo->tab_bases(cfg(c, 1, 32, 0), bx, by, nwin, jb.X, jb.Y, jb.Z, jb.N);
+    t.done();
+  }
+  normalize_soa(c, jb, nwin, scratch, ab);
+  {
+    Timer t(c, "k_tab_fill");
+    c->Bo->tab_fill(cfg(c, nblk(nwin, 32), 32, 0), ab.x, ab.y, ab.inf, ab.N, nwin, je.X, je.Y, je.Z, je.N);
+    t.done();
+  }
+  normalize(c, je, nent, scratch, tab, tab + c->L, 2 * (size_t)c->L, 1, nullptr);
+  finish(c);
+}
+
+template <typename Fn>
+int guarded(bgn_ctx* c, Fn fn) {
+  if (!c) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  try {
+    activate(c);
+    arena_reset(c);
+    fn();
+    finish(c);
+    return BGN_OK;
+  } catch (const CudaErr& e) {
+    c->err = e.msg;
+    cudaGetLastError();
+    c->pending.clear();
+    return BGN_E_CUDA;
+  } catch (const ArgErr& e) {
+    c->err = e.msg;
+    return BGN_E_BADARG;
+  } catch (const std::bad_alloc&) {
+    c->err = "host allocation failed";
+    return BGN_E_NOMEM;
+  }
+}
+
+}  // namespace
+
+// ================================================================== C-ABI
+extern "C" {
+
+int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
+  if (!prm || !out || !prm->p_be || !prm->n_be || !prm->P_bytes || !prm->Q_bytes || prm->l == 0) return BGN_E_BADARG;
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  bgn_ctx* c = nullptr;
+  try {
+    c = new bgn_ctx();
+    c->device = device;
+    Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
+    int pbits = big_bits(p0);
+    if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
+    int L = 0;
+    for (int cand : kSupportedL)
+      if (32 * cand >= pbits + 7) {
+        L = cand;
+        break;
+      }
+    if (!L) throw ArgErr{"field too large (max 1049-bit p)"};
+    c->L = L;
+    switch (L) {
+#define BGN_PICK(n)          \
+  case n:                    \
+    c->A = bgn_opsA_##n();   \
+    c->Bo = bgn_opsB_##n();  \
+    break;
+      BGN_PICK(3) BGN_PICK(5) BGN_PICK(9) BGN_PICK(17) BGN_PICK(33)
+#undef BGN_PICK
+    }
+    c->B = (pbits + 7) / 8;
+    Big p(p0.begin(), p0.begin() + L);
+    Big n = big_from_be(prm->n_be, prm->n_len, BGN_MAXL);
+    int nbits = big_bits(n);
+    if (nbits < 16 || !(n[0] & 1) || nbits > pbits) throw ArgErr{"bad group order n"};
+    c->nbytes = (nbits + 7) / 8;
+    // p + 1 == l * n  (type a1)
+    {
+      Big acc(BGN_MAXL + 2, 0);
+      uint64_t carry = 0;
+      uint64_t l_lo = prm->l & 0xffffffffu, l_hi = prm->l >> 32;
+      // acc = n * l (schoolbook with two 32-bit digits)
+      for (int i = 0; i < BGN_MAXL; i++) {
+        unsigned __int128 t = (unsigned __int128)n[i] * l_lo + acc[i] + carry;
+        acc[i] = (uint32_t)t;
+        carry = (uint64_t)(t >> 32);
+      }
+      acc[BGN_MAXL] = (uint32_t)carry;
+      carry = 0;
+      for (int i = 0; i < BGN_MAXL; i++) {
+        unsigned __int128 t = (unsigned __int128)n[i] * l_hi + acc[i + 1] + carry;
+        acc[i + 1] = (uint32_t)t;
+        carry = (uint64_t)(t >> 32);
+      }
+      Big pp(BGN_MAXL + 2, 0);
+      for (int i = 0; i < BGN_MAXL; i++) pp[i] = p0[i];
+      size_t i = 0;
+      while (++pp[i] == 0) i++;  // p + 1
+      if (pp != acc) throw ArgErr{"parameters are not type a1: p + 1 != l * n"};
+    }
+    memset(&c->fc, 0, sizeof(c->fc));
+    memset(&c->pc, 0, sizeof(c->pc));
+    for (int i = 0; i < L; i++) c->fc.p[i] = p[i];
+    Big p2(L);
+    big_add(p2, p, p);
+    for (int i = 0; i < L; i++) c->fc.p2[i] = p2[i];
+    Big x(L, 0);
+    x[0] = 1;
+    for (int i = 0; i < 32 * L; i++) big_dbl_mod(x, p);
+    for (int i = 0; i < L; i++) c->fc.one[i] = x[i];
+    for (int i = 0; i < 32 * L; i++) big_dbl_mod(x, p);
+    for (int i = 0; i < L; i++) c->fc.r2[i] = x[i];
+    uint32_t inv = p[0];
+    for (int i = 0; i < 5; i++) inv *= 2 - p[0] * inv;
+    c->fc.np0 = (uint32_t)(0u - inv);
+    c->pc.l = prm->l;
+    std::vector<int8_t> naf = big_naf(Big(n.begin(), n.begin() + (nbits + 31) / 32));
+    if (naf.size() > BGN_MAX_NAF) throw ArgErr{"group order too large"};
+    c->pc.naf_len = (int)naf.size();
+    for (size_t i = 0; i < naf.size(); i++) c->pc.naf[i] = naf[i];
+
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_active.erase(device);
+    activate(c);
+    // generators
+    size_t lw = (size_t)L * 4;
+    CK(cudaMalloc(&c->dPx, 4 * lw));
+    c->dPy = c->dPx + L;
+    c->dQx = c->dPx + 2 * L;
+    c->dQy = c->dPx + 3 * L;
+    CK(cudaMalloc(&c->dPinf, 2));
+    c->dQinf = c->dPinf + 1;
+    arena_reset(c);
+    arena_reserve(c, 4 * io_bytes(c, 1) + 4096);
+    {
+      uint8_t* dp = arena_get<uint8_t>(c, 2 * c->B);
+      uint8_t* dq = arena_get<uint8_t>(c, 2 * c->B);
+      CK(cudaMemcpyAsync(dp, prm->P_bytes, 2 * c->B, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(dq, prm->Q_bytes, 2 * c->B, cudaMemcpyHostToDevice, c->stream));
+      G1Arr aP{c->dPx, c->dPy, c->dPinf, 1}, aQ{c->dQx, c->dQy, c->dQinf, 1};
+      g1_from_bytes(c, dp, 1, aP);
+      g1_from_bytes(c, dq, 1, aQ);
+      finish(c);
+      uint8_t flags[2];
+      CK(cudaMemcpy(flags, c->dPinf, 2, cudaMemcpyDeviceToHost));
+      if (flags[0] || flags[1]) throw ArgErr{"generator P or Q is not a point on the curve"};
+    }
+    size_t tabP_words = (size_t)8 * 255 * 2 * L, tabQ_words = (size_t)c->nbytes * 255 * 2 * L;
+    CK(cudaMalloc(&c->tabP, tabP_words * 4));
+    CK(cudaMalloc(&c->tabQ, tabQ_words * 4));
+    build_table(c, c->dPx, c->dPy, 8, c->tabP);
+    build_table(c, c->dQx, c->dQy, c->nbytes, c->tabQ);
+    *out = c;
+    return BGN_OK;
+  } catch (const CudaErr& e) {
+    fprintf(stderr, "bgn_ctx_create: %s\n", e.msg.c_str());
+    cudaGetLastError();
+    delete c;
+    return BGN_E_CUDA;
+  } catch (const ArgErr& e) {
+    fprintf(stderr, "bgn_ctx_create: %s\n", e.msg.c_str());
+    delete c;
+    return BGN_E_BADARG;
+  } catch (const std::bad_alloc&) {
+    delete c;
+    return BGN_E_NOMEM;
+  }
+}
+
+void bgn_ctx_destroy(bgn_ctx* c) {
+  if (!c) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  auto it = g_active.find(c->device);
+  if (it != g_active.end() && it->second == c) g_active.erase(it);
+  cudaFree(c->dPx);
+  cudaFree(c->dPinf);
+  cudaFree(c->tabP);
+  cudaFree(c->tabQ);
+  cudaFree(c->bs_elems);
+  cudaFree(c->bs_slots);
+  cudaFree(c->bs_ginv);
+  cudaFree(c->arena);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* bgn_last_error(const bgn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bgn_ctx_info(const bgn_ctx* c, int* limbs, int* coord_bytes, int* scalar_bytes) {
+  if (!c) return BGN_E_BADARG;
+  if (limbs) *limbs = c->L;
+  if (coord_bytes) *coord_bytes = c->B;
+  if (scalar_bytes) *scalar_bytes = c->nbytes;
+  return BGN_OK;
+}
+
+int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!x || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    arena_reserve(c, pad256(count * 8) + pad256(count * c->nbytes) + jac_bytes(c, count) + g1_bytes(c, count) +
+                         pad256(count * c->L * 4) + io_bytes(c, count) + 4096);
+    const int64_t* dx = reinterpret_cast<const int64_t*>(stage_in(c, x, count * 8));
+    const uint8_t* dr = r_be ? stage_in(c, r_be, count * c->nbytes) : nullptr;
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    JacArr j = jac_alloc(c, count);
+    G1Arr a = g1_alloc(c, count);
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    EncArgs ea;
+    ea.x = dx;
+    ea.r_be = dr;
+    ea.rbytes = c->nbytes;
+    ea.tabP = c->tabP;
+    ea.tabQ = c->tabQ;
+    ea.X = j.X;
+    ea.Y = j.Y;
+    ea.Z = j.Z;
+    ea.count = count;
+    ea.N = count;
+    {
+      Timer t(c, "k_encrypt");
+      c->Bo->encrypt(cfg(c, nblk(count, 128), 128, 0), ea);
+      t.done();
+    }
+    normalize_soa(c, j, count, scratch, a);
+    g1_to_bytes(c, a, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+static int g1_binop(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, int subtract,
+                    int neg_only) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if ((!neg_only && !a) || !b || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    arena_reserve(c, 3 * io_bytes(c, count) + 3 * g1_bytes(c, count) + jac_bytes(c, count) + pad256(count * c->L * 4) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    G1Arr A, Bv = g1_alloc(c, count), R = g1_alloc(c, count);
+    if (!neg_only) {
+      const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+      A = g1_alloc(c, count);
+      g1_from_bytes(c, da, count, A);
+    } else {
+      A = g1_alloc(c, 1);
+      CK(cudaMemsetAsync(A.inf, 1, 1, c->stream));  // O
+    }
+    const uint8_t* db = stage_in(c, b, count * 2 * c->B);
+    g1_from_bytes(c, db, count, Bv);
+    JacArr j = jac_alloc(c, count);
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    G1AddArgs ga;
+    ga.x1 = A.x;
+    ga.y1 = A.y;
+    ga.inf1 = A.inf;
+    ga.N1 = A.N;
+    ga.x2 = Bv.x;
+    ga.y2 = Bv.y;
+    ga.inf2 = Bv.inf;
+    ga.N2 = Bv.N;
+    ga.bcast1 = neg_only;
+    ga.subtract = subtract;
+    ga.X = j.X;
+    ga.Y = j.Y;
+    ga.Z = j.Z;
+    ga.count = count;
+    ga.N = j.N;
+    {
+      Timer t(c, "k_g1_add");
+      c->Bo->g1_add(cfg(c, nblk(count, 128), 128, 0), ga);
+      t.done();
+    }
+    normalize_soa(c, j, count, scratch, R);
+    g1_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+int bgn_g1_add_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return g1_binop(c, a, b, count, out, 0, 0);
+}
+int bgn_g1_sub_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return g1_binop(c, a, b, count, out, 1, 0);
+}
+int bgn_g1_neg_batch(bgn_ctx* c, const uint8_t* a, size_t count, uint8_t* out) {
+  return g1_binop(c, nullptr, a, count, out, 1, 1);
+}
+
+int bgn_g1_mulconst_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* k_be, size_t kbytes, size_t count,
+                          uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !k_be || !out || !kbytes || kbytes > 4096) throw ArgErr{"bad argument"};
+    check_count(count);
+    arena_reserve(c, 2 * io_bytes(c, count) + pad256(count * kbytes) + 2 * g1_bytes(c, count) + jac_bytes(c, count) +
+                         pad256(count * c->L * 4) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+    const uint8_t* dk = stage_in(c, k_be, count * kbytes);
+    G1Arr A = g1_alloc(c, count), R = g1_alloc(c, count);
+    g1_from_bytes(c, da, count, A);
+    JacArr j = jac_alloc(c, count);
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    G1MulArgs ma;
+    ma.x = A.x;
+    ma.y = A.y;
+    ma.inf = A.inf;
+    ma.Nin = A.N;
+    ma.k_be = dk;
+    ma.kbytes = (int)kbytes;
+    ma.X = j.X;
+    ma.Y = j.Y;
+    ma.Z = j.Z;
+    ma.count = count;
+    ma.N = j.N;
+    {
+      Timer t(c, "k_g1_mulvar");
+      c->Bo->g1_mulvar(cfg(c, nblk(count, 128), 128, 0), ma);
+      t.done();
+    }
+    normalize_soa(c, j, count, scratch, R);
+    g1_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+static int gt_binop(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, int conj_b) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !b || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    arena_reserve(c, 3 * io_bytes(c, count) + 3 * gt_bytes(c, count) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+    const uint8_t* db = stage_in(c, b, count * 2 * c->B);
+    GtArr A = gt_alloc(c, count), Bv = gt_alloc(c, count), R = gt_alloc(c, count);
+    gt_from_bytes(c, da, count, A);
+    gt_from_bytes(c, db, count, Bv);
+    GtBinArgs ga;
+    ga.are = A.re;
+    ga.aim = A.im;
+    ga.Na = A.N;
+    ga.bre = Bv.re;
+    ga.bim = Bv.im;
+    ga.Nb = Bv.N;
+    ga.conj_b = conj_b;
+    ga.ore = R.re;
+    ga.oim = R.im;
+    ga.count = count;
+    ga.N = R.N;
+    {
+      Timer t(c, "k_gt_mul");
+      c->A->gt_mul(cfg(c, nblk(count, 128), 128, 0), ga);
+      t.done();
+    }
+    gt_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+int bgn_gt_mul_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return gt_binop(c, a, b, count, out, 0);
+}
+int bgn_gt_div_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return gt_binop(c, a, b, count, out, 1);
+}
+
+static int gt_pow_impl(bgn_ctx* c, const uint8_t* a, const uint8_t* k_be, size_t kbytes, size_t count, uint8_t* out,
+                       int mode /*0 var, 1 secret, 2 inverse*/) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !out) throw ArgErr{"null buffer"};
+    if (mode == 0 && (!k_be || !kbytes || kbytes > 4096)) throw ArgErr{"bad exponent buffer"};
+    if (mode == 1 && !c->has_secret) throw ArgErr{"secret key not set"};
+    check_count(count);
+    arena_reserve(c, 2 * io_bytes(c, count) + pad256(count * (kbytes + 1)) + 2 * gt_bytes(c, count) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+    GtArr A = gt_alloc(c, count), R = gt_alloc(c, count);
+    gt_from_bytes(c, da, count, A);
+    GtPowArgs pa;
+    pa.re = A.re;
+    pa.im = A.im;
+    pa.Nin = A.N;
+    pa.e_be = nullptr;
+    pa.ebytes = 0;
+    pa.mode = mode;
+    if (mode == 0) {
+      pa.e_be = stage_in(c, k_be, count * kbytes);
+      pa.ebytes = (int)kbytes;
+    }
+    pa.ore = R.re;
+    pa.oim = R.im;
+    pa.count = count;
+    pa.N = R.N;
+    {
+      Timer t(c, "k_gt_pow");
+      c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
+      t.done();
+    }
+    gt_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+int bgn_gt_pow_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* k_be, size_t kbytes, size_t count, uint8_t* out) {
+  return gt_pow_impl(c, a, k_be, kbytes, count, out, 0);
+}
+int bgn_gt_pow_secret_batch(bgn_ctx* c, const uint8_t* in, size_t count, uint8_t* out) {
+  return gt_pow_impl(c, in, nullptr, 0, count, out, 1);
+}
+int bgn_gt_inv_batch(bgn_ctx* c, const uint8_t* a, size_t count, uint8_t* out) {
+  return gt_pow_impl(c, a, nullptr, 0, count, out, 2);
+}
+
+static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  arena_reserve(c, 3 * io_bytes(c, count) + 2 * g1_bytes(c, count) + gt_bytes(c, count) + 8192);
+  OutBuf ob = stage_out(c, out, count * 2 * c->B);
+  const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+  G1Arr A = g1_alloc(c, count);
+  g1_from_bytes(c, da, count, A);
+  GtArr R = gt_alloc(c, count);
+  if (b) {
+    const uint8_t* db = stage_in(c, b, count * 2 * c->B);
+    G1Arr Bv = g1_alloc(c, count);
+    g1_from_bytes(c, db, count, Bv);
+    run_miller(c, A, 1, Bv, 1, 0, count, 1, R);
+  } else {
+    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+    run_miller(c, A, 1, Pv, 1, 1, count, 1, R);
+  }
+  gt_to_bytes(c, R, count, ob.dev);
+  commit_out(c, ob);
+}
+int bgn_pair_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !b || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    pair_common(c, a, b, count, out);
+  });
+}
+int bgn_make_l2_batch(bgn_ctx* c, const uint8_t* a, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    pair_common(c, a, nullptr, count, out);
+  });
+}
+
+int bgn_multpoly_batch(bgn_ctx* c, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                       uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!c1 || !c2 || !out || !d1 || !d2 || d1 > 128 || d2 > 128) throw ArgErr{"bad argument"};
+    check_count(count * (d1 + d2));
+    size_t n1 = count * d1, n2 = count * d2, no = count * (d1 + d2);
+    arena_reserve(c, io_bytes(c, n1) + io_bytes(c, n2) + io_bytes(c, no) + g1_bytes(c, n1) + g1_bytes(c, n2) +
+                         gt_bytes(c, no) + 8192);
+    OutBuf ob = stage_out(c, out, no * 2 * c->B);
+    const uint8_t* da = stage_in(c, c1, n1 * 2 * c->B);
+    const uint8_t* db = stage_in(c, c2, n2 * 2 * c->B);
+    G1Arr A = g1_alloc(c, n1), Bv = g1_alloc(c, n2);
+    g1_from_bytes(c, da, n1, A);
+    g1_from_bytes(c, db, n2, Bv);
+    GtArr R = gt_alloc(c, no);
+    // the pairing is symmetric: the shorter polynomial supplies the Miller points
+    if (d1 <= d2)
+      run_miller(c, A, (int)d1, Bv, (int)d2, 0, count, (int)(d1 + d2), R);
+    else
+      run_miller(c, Bv, (int)d2, A, (int)d1, 0, count, (int)(d1 + d2), R);
+    gt_to_bytes(c, R, no, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+// product tree over terms; leaves `ncoeff` elements in the returned array
+static GtArr reduce_tree(bgn_ctx* c, GtArr cur, size_t nterms, size_t ncoeff) {
+  while (nterms > 1) {
+    size_t G = (nterms + 15) / 16;
+    if (nterms <= 64) G = 1;
+    GtArr nxt = gt_alloc(c, G * ncoeff);
+    Timer t(c, "k_gt_reduce");
+    c->A->gt_reduce(cfg(c, nblk(G * ncoeff, 128), 128, 0), cur.re, cur.im, cur.N, nterms, (int)ncoeff, (int)G, nxt.re, nxt.im, nxt.N);
+    t.done();
+    cur = nxt;
+    nterms = G;
+  }
+  return cur;
+}
+
+int bgn_l2_sum_reduce(bgn_ctx* c, const uint8_t* in, size_t nterms, size_t ncoeff, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!ncoeff) return;
+    if (!out || (nterms && !in) || ncoeff > (1u << 20)) throw ArgErr{"bad argument"};
+    check_count(nterms * ncoeff + ncoeff);
+    size_t n = nterms * ncoeff;
+    arena_reserve(c, io_bytes(c, n) + io_bytes(c, ncoeff) + 3 * gt_bytes(c, n + ncoeff) + 65536);
+    OutBuf ob = stage_out(c, out, ncoeff * 2 * c->B);
+    GtArr R;
+    if (nterms == 0) {
+      R = gt_alloc(c, ncoeff);
+      Timer t(c, "k_gt_reduce");
+      c->A->gt_reduce(cfg(c, nblk(ncoeff, 128), 128, 0), R.re, R.im, R.N, 0, (int)ncoeff, 1, R.re, R.im, R.N);
+      t.done();
+    } else {
+      const uint8_t* di = stage_in(c, in, n * 2 * c->B);
+      GtArr A = gt_alloc(c, n);
+      gt_from_bytes(c, di, n, A);
+      R = reduce_tree(c, A, nterms, ncoeff);
+    }
+    gt_to_bytes(c, R, ncoeff, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t msg_space, uint32_t baby_steps) {
+  return guarded(c, [&] {
+    if (!q1_be || !q1_len || q1_len > 4 * (BGN_MAX_EXPW - 1) || msg_space == 0 || msg_space > ((uint64_t)1 << 50))
+      throw ArgErr{"bad secret key / message space"};
+    Big q = big_from_be(q1_be, q1_len, BGN_MAX_EXPW);
+    int qb = big_bits(q);
+    if (qb == 0) throw ArgErr{"q1 is zero"};
+    for (int i = 0; i < BGN_MAX_EXPW; i++) c->pc.exp[i] = q[i];
+    c->pc.exp_bits = qb;
+    reupload_pc(c);
+    c->has_secret = false;
+    // bound = ceil(sqrt(T)) exactly as gsbs.go:60 (float64 sqrt of an int64)
+    uint64_t bound = (uint64_t)ceil(sqrt((double)(int64_t)msg_space));
+    uint64_t mmax = bound * bound + bound + 2;  // i <= bound, table value j+1 <= bound+2 (gsbs.go:44, 77-98)
+    uint64_t S = baby_steps ? baby_steps : std::min<uint64_t>(mmax, (uint64_t)1 << 21);
+    if (S < 1) S = 1;
+    if (S > ((uint64_t)1 << 24)) throw ArgErr{"baby_steps too large"};
+    uint64_t hs = 1;
+    while (hs < 2 * S) hs <<= 1;
+    cudaFree(c->bs_elems);
+    cudaFree(c->bs_slots);
+    cudaFree(c->bs_ginv);
+    c->bs_elems = c->bs_slots = c->bs_ginv = nullptr;
+    CK(cudaMalloc(&c->bs_elems, S * 2 * c->L * 4));
+    CK(cudaMalloc(&c->bs_slots, hs * 4));
+    CK(cudaMalloc(&c->bs_ginv, 4 * (size_t)c->L * 4));
+    CK(cudaMemsetAsync(c->bs_slots, 0, hs * 4, c->stream));
+    // gsk = e(P,P)^q1   (bgn.go:198-199)
+    arena_reserve(c, 4 * gt_bytes(c, 1) + 8192);
+    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+    GtArr e = gt_alloc(c, 1), gsk = gt_alloc(c, 1), gs = gt_alloc(c, 1);
+    run_miller(c, Pv, 1, Pv, 1, 0, 1, 1, e);
+    GtPowArgs pa;
+    pa.re = e.re;
+    pa.im = e.im;
+    pa.Nin = 1;
+    pa.e_be = nullptr;
+    pa.ebytes = 0;
+    pa.mode = 1;
+    pa.ore = gsk.re;
+    pa.oim = gsk.im;
+    pa.count = 1;
+    pa.N = 1;
+    {
+      Timer t(c, "k_gt_pow");
+      c->A->gt_pow(cfg(c, 1, 32, 0), pa);
+      t.done();
+    }
+    // generator in AoS for the table kernels: bs_ginv[0..2L) temporarily holds gsk, then gen^-S
+    uint32_t* gen_aos = c->bs_ginv + 2 * c->L;
+    CK(cudaMemcpyAsync(gen_aos, gsk.re, c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(gen_aos + c->L, gsk.im, c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    BsgsBuildArgs ba;
+    ba.gen = gen_aos;
+    ba.elems = c->bs_elems;
+    ba.slots = c->bs_slots;
+    ba.hmask = (uint32_t)(hs - 1);
+    ba.S = (uint32_t)S;
+    ba.chunk = 64;
+    size_t nthreads = (S + ba.chunk - 1) / ba.chunk;
+    {
+      Timer t(c, "k_bsgs_build");
+      c->A->bsgs_build(cfg(c, nblk(nthreads, 128), 128, 0), ba);
+      t.done();
+    }
+    // ginv = conj(gsk^S): exponent S as 4 big-endian bytes
+    uint8_t sbe[4] = {(uint8_t)(S >> 24), (uint8_t)(S >> 16), (uint8_t)(S >> 8), (uint8_t)S};
+    uint8_t* dsbe = arena_get<uint8_t>(c, 4);
+    CK(cudaMemcpyAsync(dsbe, sbe, 4, cudaMemcpyHostToDevice, c->stream));
+    pa.re = gsk.re;
+    pa.im = gsk.im;
+    pa.e_be = dsbe;
+    pa.ebytes = 4;
+    pa.mode = 3;  // variable exponent, conjugated result
+    pa.ore = gs.re;
+    pa.oim = gs.im;
+    {
+      Timer t(c, "k_gt_pow");
+      c->A->gt_pow(cfg(c, 1, 32, 0), pa);
+      t.done();
+    }
+    CK(cudaMemcpyAsync(c->bs_ginv, gs.re, c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->bs_ginv + c->L, gs.im, c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->bs_S = (uint32_t)S;
+    c->bs_hmask = (uint32_t)(hs - 1);
+    c->bs_mmax = mmax;
+    c->bs_giant = (uint32_t)((mmax + S - 1) / S);
+    c->has_secret = true;
+  });
+}
+
+int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status) {
+  if (c && !c->has_secret) {
+    c->err = "DL tables not computed!";
+    return BGN_E_NOTSETUP;
+  }
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!in || !out || !status) throw ArgErr{"null buffer"};
+    check_count(count);
+    arena_reserve(c, io_bytes(c, count) + g1_bytes(c, count) + 3 * gt_bytes(c, count) + pad256(count * 8) +
+                         pad256(count) + 8192);
+    const uint8_t* di = stage_in(c, in, count * 2 * c->B);
+    OutBuf oo = stage_out(c, out, count * 8);
+    OutBuf os = stage_out(c, status, count);
+    GtArr A = gt_alloc(c, count), R = gt_alloc(c, count);
+    if (is_l2) {
+      gt_from_bytes(c, di, count, A);
+    } else {
+      // level 1: e(C, P)^q1 = e(P,P)^(q1 m); same m as the reference's G1 table search (bgn.go:222-223)
+      G1Arr C1 = g1_alloc(c, count);
+      g1_from_bytes(c, di, count, C1);
+      G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+      run_miller(c, C1, 1, Pv, 1, 1, count, 1, A);
+    }
+    GtPowArgs pa;
+    pa.re = A.re;
+    pa.im = A.im;
+    pa.Nin = A.N;
+    pa.e_be = nullptr;
+    pa.ebytes = 0;
+    pa.mode = 1;
+    pa.ore = R.re;
+    pa.oim = R.im;
+    pa.count = count;
+    pa.N = R.N;
+    {
+      Timer t(c, "k_gt_pow");
+      c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
+      t.done();
+    }
+    BsgsLookupArgs la;
+    la.re = R.re;
+    la.im = R.im;
+    la.Nin = R.N;
+    la.count = count;
+    la.elems = c->bs_elems;
+    la.slots = c->bs_slots;
+    la.hmask = c->bs_hmask;
+    la.S = c->bs_S;
+    la.ginv = c->bs_ginv;
+    la.giant_steps = c->bs_giant;
+    la.mmax = c->bs_mmax;
+    la.out = reinterpret_cast<int64_t*>(oo.dev);
+    la.status = os.dev;
+    {
+      Timer t(c, "k_bsgs_lookup");
+      c->A->bsgs_lookup(cfg(c, nblk(count, 128), 128, 0), la);
+      t.done();
+    }
+    commit_out(c, oo);
+    commit_out(c, os);
+  });
+}
+
+// ---------------------------------------------------------------- instrumentation
+int bgn_timing_enable(bgn_ctx* c, int on) {
+  if (!c) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  c->timing = on != 0;
+  return BGN_OK;
+}
+int bgn_timing_reset(bgn_ctx* c) {
+  if (!c) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  c->ktimes.clear();
+  c->total_launches = 0;
+  return BGN_OK;
+}
+int bgn_timing_get(bgn_ctx* c, const char* prefix, double* ms_total, uint64_t* launches) {
+  if (!c || !prefix) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  double ms = 0;
+  uint64_t n = 0;
+  size_t pl = strlen(prefix);
+  for (auto& kv : c->ktimes)
+    if (kv.first.compare(0, pl, prefix) == 0) {
+      ms += kv.second.ms;
+      n += kv.second.launches;
+    }
+  if (pl == 0) n = c->total_launches;
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  return BGN_OK;
+}
+
+int bgn_bench_mulmod(bgn_ctx* c, int ilp, int iters, int blocks, int threads, float* ms) {
+  return guarded(c, [&] {
+    if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 128) throw ArgErr{"bad argument"};
+    size_t N = (size_t)blocks * threads;
+    arena_reserve(c, pad256(N * c->L * 4) + 4096);
+    uint32_t* io = arena_get<uint32_t>(c, N * c->L);
+    CK(cudaMemsetAsync(io, 0x5a, N * c->L * 4, c->stream));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    auto launch = [&](int it) {
+      c->total_launches++;
+      if (ilp != 1 && ilp != 2) throw ArgErr{"ilp must be 1 or 2"};
+      c->A->mulmod_bench(cfg(c, blocks, threads, 0), ilp, io, N, it);
+    };
+    launch(4);  // warm-up
+    CK(cudaEventRecord(a, c->stream));
+    launch(iters);
+    CK(cudaEventRecord(b, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    CK(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  });
+}
+
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) r[i] = a + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        // 8 independent 64-bit accumulators, one IMAD.WIDE.U32 each
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(r[2 * k]), "+r"(r[2 * k + 1])
+                     : "r"(a), "r"(b));
+      }
+    }
+  }
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) o ^= r[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = o;
+}
+
+int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread) {
+  if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (cudaSetDevice(device) != cudaSuccess) return BGN_E_CUDA;
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return BGN_E_CUDA;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k_imad_peak<<<blocks, threads>>>(d, 16, 12345u);
+  cudaEventRecord(a);
+  k_imad_peak<<<blocks, threads>>>(d, iters, 12345u);
+  cudaEventRecord(b);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaEventElapsedTime(ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (instr_per_thread) *instr_per_thread = (double)iters * 64.0;
+  return e == cudaSuccess ? BGN_OK : BGN_E_CUDA;
+}
+
+}  // extern "C"

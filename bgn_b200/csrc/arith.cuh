@@ -1,0 +1,268 @@
+// arith.cuh -- multi-limb Montgomery arithmetic over the type-A1 field F_p
+// (p = l*n - 1) on 32-bit limbs, written for sm_100a.
+//
+// Replaces libpbc montfp.c / GMP mpn_* ("native #2/#3");
+// nothing here is derived from their sources.  One 32x32->64 product is one
+// IMAD.WIDE.U32[.X] issue slot: every (mad.lo.cc, madc.hi.cc) pair below lands
+// on an aligned 64-bit register pair so ptxas fuses it, and carries travel in
+// predicate registers so independent chains interleave (checked with
+// cuobjdump -sass; see DESIGN.md "K1").
+//
+// Representation: L limbs, little-endian limb order, Montgomery form with
+// R = 2^(32L).  Values are kept in the redundant range [0, 2p) ("lazy" form);
+// fp_canon() brings them to [0, p).  Requires 32L >= bits(p) + 3.
+//
+// When BGN_HOSTSIM is defined the same code compiles as plain C++ with the
+// carry flag emulated in software.  That build exists ONLY for the CPU-side
+// unit tests of the device logic (tests/hostsim); the shipped library never
+// contains it.
+#pragma once
+#include <stdint.h>
+#include "types.h"
+
+#ifdef BGN_HOSTSIM
+#define BGN_DEV inline
+#define BGN_DEVNI
+#define BGN_CONST static
+#define BGN_UNROLL
+namespace bgnsim {
+static thread_local uint32_t cc = 0;
+}
+BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+}
+BGN_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)hi << 32) | lo);
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+  bgnsim::cc = (uint32_t)(t >> 64);
+}
+BGN_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)hi << 32) | lo) + bgnsim::cc;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+  bgnsim::cc = (uint32_t)(t >> 64);
+}
+BGN_DEV void madc_wide_cc3(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)chi << 32) | clo) + bgnsim::cc;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+  bgnsim::cc = (uint32_t)(t >> 64);
+}
+BGN_DEV void add_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b;
+  r = (uint32_t)t;
+  bgnsim::cc = (uint32_t)(t >> 32);
+}
+BGN_DEV void addc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b + bgnsim::cc;
+  r = (uint32_t)t;
+  bgnsim::cc = (uint32_t)(t >> 32);
+}
+BGN_DEV void addc(uint32_t& r, uint32_t a, uint32_t b) {
+  r = a + b + bgnsim::cc;
+}
+BGN_DEV void sub_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b;
+  r = (uint32_t)t;
+  bgnsim::cc = (uint32_t)((t >> 32) & 1);  // PTX ISA: CC.CF = borrow-out
+}
+BGN_DEV void subc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b - bgnsim::cc;
+  r = (uint32_t)t;
+  bgnsim::cc = (uint32_t)((t >> 32) & 1);
+}
+BGN_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) {
+  r = a - b - bgnsim::cc;
+}
+#else
+#define BGN_DEV __device__ __forceinline__
+#define BGN_DEVNI __device__ __noinline__
+#define BGN_CONST __constant__
+#define BGN_UNROLL _Pragma("unroll")
+BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+BGN_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+BGN_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+BGN_DEV void madc_wide_cc3(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+               : "=&r"(lo), "=r"(hi)
+               : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+BGN_DEV void add_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+BGN_DEV void addc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+BGN_DEV void addc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+BGN_DEV void sub_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+BGN_DEV void subc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+BGN_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// Field constants.  One key is active per device at a time; the host uploads
+// these before launching (api.cu: ctx_activate).  Limb counts up to 33
+// (1024-bit keys) -- arrays are padded to BGN_MAXL.
+// ---------------------------------------------------------------------------
+BGN_CONST FieldConsts c_fc;
+
+// ---------------------------------------------------------------------------
+// Register-level primitives.  All loops have compile-time bounds.
+// ---------------------------------------------------------------------------
+template <int L>
+struct Fp {
+  static constexpr int W = 2 * ((L + 2) / 2);  // accumulator registers per parity array
+  static constexpr int KE = (L + 1) / 2;       // even-index limbs of an operand
+  static constexpr int KO = L / 2;             // odd-index limbs
+
+  // one CIOS row: acc += a*s (then caller reduces).  X is the array aligned at
+  // limb 0, Y sits one limb higher; on entry (not FIRST) Y is the previous
+  // row's X whose limb 0 is zero and whose limb 1 is the pending carry limb.
+  template <bool FIRST>
+  BGN_DEV static void row(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t (&a)[L], uint32_t s,
+                          const uint32_t* __restrict__ pm, uint32_t np0) {
+    if (FIRST) {
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) mul_wide(Y[2 * k], Y[2 * k + 1], a[2 * k + 1], s);
+      Y[W - 2] = 0;
+      Y[W - 1] = 0;
+      BGN_UNROLL
+      for (int k = 0; k < KE; k++) mul_wide(X[2 * k], X[2 * k + 1], a[2 * k], s);
+      if (2 * KE < W) {
+        X[W - 2] = 0;
+        X[W - 1] = 0;
+      }
+    } else {
+      add_cc(X[0], X[0], Y[1]);
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) madc_wide_cc3(Y[2 * k], Y[2 * k + 1], a[2 * k + 1], s, Y[2 * k + 2], Y[2 * k + 3]);
+      addc(Y[W - 2], 0, 0);
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], a[0], s);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a[2 * k], s);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+    uint32_t m = X[0] * np0;
+    mad_wide_cc(Y[0], Y[1], pm[1], m);
+    BGN_UNROLL
+    for (int k = 1; k < KO; k++) madc_wide_cc(Y[2 * k], Y[2 * k + 1], pm[2 * k + 1], m);
+    addc(Y[W - 2], Y[W - 2], 0);
+    mad_wide_cc(X[0], X[1], pm[0], m);
+    BGN_UNROLL
+    for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], pm[2 * k], m);
+    if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+  }
+
+  // r = a*b/R mod p, r in [0,2p) for a,b in [0,2p).  2L^2+L products.
+  BGN_DEV static void mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t X[W], Y[W];
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row<true>(X, Y, a, b[0], pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      row<false>(Y, X, a, b[i], pm, np0);
+      row<false>(X, Y, a, b[i + 1], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row<false>(Y, X, a, b[L - 1], pm, np0);
+      merge(r, X, Y);  // last row had (aligned=Y, other=X): after shift X is aligned
+    } else {
+      merge(r, Y, X);
+    }
+  }
+
+  // after the final row with roles (X=aligned, Y=offset): result = Y + (X >> 32)
+  BGN_DEV static void merge(uint32_t (&r)[L], const uint32_t (&A)[W], const uint32_t (&B)[W]) {
+    add_cc(r[0], A[0], B[1]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(r[j], A[j], B[j + 1]);
+    addc(r[L - 1], A[L - 1], B[L]);
+  }
+
+  BGN_DEV static void sqr(uint32_t (&r)[L], const uint32_t (&a)[L]) { mul(r, a, a); }
+
+  // r = a + b, kept in [0,2p)
+  BGN_DEV static void add(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t t[L], u[L];
+    add_cc(t[0], a[0], b[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(t[j], a[j], b[j]);
+    addc(t[L - 1], a[L - 1], b[L - 1]);
+    uint32_t bw = sub_p2(u, t);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) r[j] = bw ? t[j] : u[j];
+  }
+
+  // u = t - 2p; returns all-ones when the subtraction borrowed (t < 2p)
+  BGN_DEV static uint32_t sub_p2(uint32_t (&u)[L], const uint32_t (&t)[L]) {
+    uint32_t bw;
+    sub_cc(u[0], t[0], c_fc.p2[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L; j++) subc_cc(u[j], t[j], c_fc.p2[j]);
+    subc(bw, 0, 0);  // 0 - 0 - CF: all-ones mask on borrow
+    return bw;
+  }
+
+  // r = a - b, kept in [0,2p)
+  BGN_DEV static void sub(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t t[L], mask;
+    sub_cc(t[0], a[0], b[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L; j++) subc_cc(t[j], a[j], b[j]);
+    subc(mask, 0, 0);  // borrow -> add 2p
+    add_cc(r[0], t[0], c_fc.p2[0] & mask);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(r[j], t[j], c_fc.p2[j] & mask);
+    addc(r[L - 1], t[L - 1], c_fc.p2[L - 1] & mask);
+  }
+
+  // canonical representative in [0,p) of a value in [0,2p]
+  BGN_DEV static void canon(uint32_t (&r)[L], const uint32_t (&a)[L]) {
+    uint32_t t[L], u[L], bw;
+    sub_cc(t[0], a[0], c_fc.p[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L; j++) subc_cc(t[j], a[j], c_fc.p[j]);
+    subc(bw, 0, 0);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) u[j] = bw ? a[j] : t[j];
+    // a may equal 2p exactly only for inputs outside the invariant; one more pass is cheap and exact
+    sub_cc(t[0], u[0], c_fc.p[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L; j++) subc_cc(t[j], u[j], c_fc.p[j]);
+    subc(bw, 0, 0);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) r[j] = bw ? u[j] : t[j];
+  }
+
+  BGN_DEV static bool is_zero_raw(const uint32_t (&a)[L]) {
+    uint32_t o = 0;
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) o |= a[j];
+    return o == 0;
+  }
+  BGN_DEV static bool eq_raw(const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t o = 0;
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) o |= a[j] ^ b[j];
+    return o == 0;
+  }
+};

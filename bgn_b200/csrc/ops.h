@@ -1,0 +1,56 @@
+// ops.h -- per-limb-count launcher tables.  Each supported limb count L is
+// compiled in its own translation units (inst_a.cu: pairing / GT kernels,
+// inst_b.cu: G1, (de)serialisation and BSGS kernels) so the build parallelises;
+// every unit owns a copy of the __constant__ key material and exports `upload`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "types.h"
+
+struct LaunchCfg {
+  unsigned grid, block;
+  size_t smem;
+  cudaStream_t stream;
+};
+
+struct LOpsA {
+  int L;
+  cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
+  cudaError_t (*miller_set_smem)(size_t smem);
+  void (*miller)(LaunchCfg, const MillerArgs&);
+  void (*gt_mul)(LaunchCfg, const GtBinArgs&);
+  void (*gt_pow)(LaunchCfg, const GtPowArgs&);
+  void (*gt_reduce)(LaunchCfg, const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms, int ncoeff, int G,
+                    uint32_t* ore, uint32_t* oim, size_t N);
+  void (*fp2_from_bytes)(LaunchCfg, const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N);
+  void (*fp2_to_bytes)(LaunchCfg, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B);
+  void (*bsgs_build)(LaunchCfg, const BsgsBuildArgs&);
+  void (*bsgs_lookup)(LaunchCfg, const BsgsLookupArgs&);
+  void (*mulmod_bench)(LaunchCfg, int ilp, uint32_t* io, size_t N, int iters);
+};
+
+struct LOpsB {
+  int L;
+  cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
+  void (*g1_from_bytes)(LaunchCfg, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf,
+                        size_t N);
+  void (*g1_to_bytes)(LaunchCfg, const uint32_t* x, const uint32_t* y, const uint8_t* inf, size_t N, size_t count,
+                      uint8_t* out, int B);
+  void (*encrypt)(LaunchCfg, const EncArgs&);
+  void (*normalize)(LaunchCfg, const NormArgs&);
+  void (*g1_add)(LaunchCfg, const G1AddArgs&);
+  void (*g1_mulvar)(LaunchCfg, const G1MulArgs&);
+  void (*tab_bases)(LaunchCfg, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                    size_t N);
+  void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
+                   uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
+};
+
+#define BGN_DECL_OPS(L)               \
+  extern "C" const LOpsA* bgn_opsA_##L(); \
+  extern "C" const LOpsB* bgn_opsB_##L();
+BGN_DECL_OPS(3)
+BGN_DECL_OPS(5)
+BGN_DECL_OPS(9)
+BGN_DECL_OPS(17)
+BGN_DECL_OPS(33)

@@ -1,0 +1,127 @@
+// types.h -- plain structs shared by the host orchestration (api.cpp) and the
+// per-limb-count kernel translation units (inst.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#define BGN_MAXL 34
+struct FieldConsts {
+  uint32_t p[BGN_MAXL];    // modulus
+  uint32_t p2[BGN_MAXL];   // 2p
+  uint32_t one[BGN_MAXL];  // R mod p   (Montgomery 1)
+  uint32_t r2[BGN_MAXL];   // R^2 mod p (to-Montgomery factor)
+  uint32_t np0;            // -p^{-1} mod 2^32
+  uint32_t pad[3];
+};
+
+#define BGN_MAX_NAF 1100
+#define BGN_MAX_EXPW 34
+struct PairConsts {
+  uint64_t l;                    // cofactor, p + 1 = l*n
+  int32_t naf_len;               // number of signed digits of n (MSB first, naf[0] == 1)
+  int32_t exp_bits;              // bit length of the fixed GT exponent (secret q1)
+  uint32_t exp[BGN_MAX_EXPW];    // fixed exponent, little-endian words
+  int8_t naf[BGN_MAX_NAF];
+};
+
+#define BGN_MILLER_NSLOT 12  // shared-memory F_p slots per thread of the Miller team kernel
+struct MillerArgs {
+  const uint32_t* Mx;  // Miller-side points, Montgomery SoA [L][NM], index unit*dM + i
+  const uint32_t* My;
+  const uint8_t* Minf;  // 1 = point at infinity
+  const uint32_t* Ex;   // evaluation-side points, SoA [L][NE], index unit*dE + k
+  const uint32_t* Ey;
+  const uint8_t* Einf;
+  uint32_t* out_re;  // GT out, Montgomery SoA [L][NOUT], index unit*out_slots + j
+  uint32_t* out_im;
+  int NM, NE, NOUT;
+  int e_bcast;      // evaluation side is ONE polynomial shared by all units (makeL2: B = P)
+  int dM, dE;       // dM <= dE; team size TS = dE
+  int out_slots;    // slots written per unit (dM+dE for MultPoly: last one is the identity; 1 for Pair)
+  int count;        // units
+  int teams_per_block;
+};
+
+struct EncArgs {
+  const int64_t* x;       // plaintext scalars (signed, |x| < 2^63)
+  const uint8_t* r_be;    // randomness, big-endian, rbytes each (may be null: r = 0)
+  int rbytes;
+  const uint32_t* tabP;   // 8 windows
+  const uint32_t* tabQ;   // rbytes windows
+  uint32_t *X, *Y, *Z;    // Jacobian out, SoA [L][N]
+  size_t count, N;
+};
+
+struct NormArgs {
+  const uint32_t *X, *Y, *Z;  // SoA [L][N]
+  uint32_t* scratch;          // SoA [L][N] prefix products
+  size_t count, N;
+  int G;                      // number of worker threads
+  uint32_t* ox;               // out x: element e, limb j at ox[e*o_estride + j*o_lstride]
+  uint32_t* oy;
+  size_t o_estride, o_lstride;
+  uint8_t* inf;               // out flags (may be null)
+};
+
+struct G1AddArgs {
+  const uint32_t *x1, *y1;
+  const uint8_t* inf1;
+  const uint32_t *x2, *y2;
+  const uint8_t* inf2;
+  size_t N1, N2;
+  int bcast1;   // operand 1 is a single element (Neg: O - c)
+  int subtract;
+  uint32_t *X, *Y, *Z;
+  size_t count, N;
+};
+
+struct G1MulArgs {
+  const uint32_t *x, *y;
+  const uint8_t* inf;
+  size_t Nin;
+  const uint8_t* k_be;
+  int kbytes;
+  uint32_t *X, *Y, *Z;
+  size_t count, N;
+};
+
+struct GtBinArgs {
+  const uint32_t *are, *aim, *bre, *bim;
+  size_t Na, Nb;
+  int conj_b;  // division of unitary elements: a * conj(b)   (bgn.go:397)
+  uint32_t *ore, *oim;
+  size_t count, N;
+};
+
+struct GtPowArgs {
+  const uint32_t *re, *im;
+  size_t Nin;
+  const uint8_t* e_be;  // per-element exponents (modes 0 and 3)
+  int ebytes;
+  int mode;             // 0: a^e[i]; 1: a^q1 (c_pc.exp); 2: conj(a) = a^-1 (unitary); 3: conj(a^e[i])
+  uint32_t *ore, *oim;
+  size_t count, N;
+};
+
+struct BsgsBuildArgs {
+  const uint32_t* gen;   // generator gsk, AoS [2L] Montgomery
+  uint32_t* elems;       // [S][2L]
+  uint32_t* slots;
+  uint32_t hmask;
+  uint32_t S;
+  int chunk;             // baby steps per thread
+};
+
+struct BsgsLookupArgs {
+  const uint32_t *re, *im;  // csk = C^q1, SoA [L][Nin]
+  size_t Nin, count;
+  const uint32_t* elems;
+  const uint32_t* slots;
+  uint32_t hmask;
+  uint32_t S;
+  const uint32_t* ginv;     // gen^(-S), AoS [2L]
+  uint32_t giant_steps;     // ceil(Mmax / S)
+  uint64_t mmax;            // largest |m| the reference's table/loop bounds can return
+  int64_t* out;
+  uint8_t* status;          // 0 ok, 1 out of bounds (gsbs.go:105)
+};

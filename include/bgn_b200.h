@@ -1,0 +1,137 @@
+/* bgn_b200.h -- C-ABI of the B200-native batched BGN engine.
+ *
+ * This is the drop-in boundary for the arithmetic the reference (sachaservan/bgn)
+ * obtains, one element at a time, from github.com/Nik-U/pbc (cgo -> libpbc -> GMP).
+ * Each entry point names the reference code it replaces (file:line in the
+ * reference tree).  Everything crossing the boundary is a plain pointer + size:
+ *
+ *   - group elements travel in PBC element_to_bytes format: G1 = x||y, GT = re||im,
+ *     each coordinate big-endian, fixed width B = ceil(bits(p)/8) bytes
+ *     (bgn_ctx_info reports B).  The point at infinity is all-zero bytes.
+ *   - scalars are big-endian byte strings of a caller-stated fixed width.
+ *   - every data pointer may be a HOST pointer or a CUDA DEVICE pointer on the
+ *     context's device (detected with cudaPointerGetAttributes); host buffers are
+ *     copied in/out inside the call.
+ *   - the caller owns all buffers; the library keeps no caller pointer after return.
+ *   - all functions return 0 on success or a negative bgn_status; none throws or aborts.
+ *   - a context is thread-compatible: calls are serialised internally and are
+ *     synchronous (they return after the device work has finished).
+ *
+ * Homomorphic operations implement the reference's Deterministic=true behaviour
+ * (bgn_test.go:13); re-randomisation is done by the caller with bgn_encrypt_batch
+ * of zero plus an add (DESIGN.md "non-deterministic mode").
+ */
+#ifndef BGN_B200_H
+#define BGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bgn_ctx bgn_ctx;
+
+typedef enum {
+  BGN_OK = 0,
+  BGN_E_BADARG = -1,    /* programmer error; the reference panics (bgn.go:67-73, 87-89, 389) */
+  BGN_E_CUDA = -2,      /* CUDA runtime failure; see bgn_last_error */
+  BGN_E_NOTSETUP = -3,  /* decrypt before bgn_ctx_set_secret: "DL tables not computed!" (gsbs.go:56-58) */
+  BGN_E_NOMEM = -4,
+  BGN_E_UNSUPPORTED = -5
+} bgn_status;
+
+/* Public parameters: what PublicKey{P, Q, N, PairingParams} carries (bgn.go:28-41).
+ * p, n: big-endian magnitudes of the PBC "type a1" parameters (bgn.go:93-94);
+ * l: the cofactor the reference parses out of the param string (bgn.go:583-593);
+ * P, Q: Element.Bytes() of the generators (bgn.go:605-607), 2*B bytes each. */
+typedef struct {
+  const uint8_t* p_be;
+  size_t p_len;
+  const uint8_t* n_be;
+  size_t n_len;
+  uint64_t l;
+  const uint8_t* P_bytes;
+  const uint8_t* Q_bytes;
+} bgn_params;
+
+/* pbc.NewPairingFromString + G1.SetBytes (bgn.go:640-653): validates the
+ * parameters, uploads Montgomery constants, builds the fixed-base window tables
+ * for P and Q on the device.  device = CUDA ordinal. */
+int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out);
+void bgn_ctx_destroy(bgn_ctx* ctx);
+const char* bgn_last_error(const bgn_ctx* ctx);
+
+/* limbs: 32-bit limbs of the field; coord_bytes: B; scalar_bytes: ceil(bits(n)/8). */
+int bgn_ctx_info(const bgn_ctx* ctx, int* limbs, int* coord_bytes, int* scalar_bytes);
+
+/* SetupDecryption / ComputeDecryptionPreprocessing (bgn.go:142-149, 195-201) +
+ * PrecomputeTables (gsbs.go:41-51): q1 = SecretKey.Key, msg_space = PublicKey.MsgSpace.
+ * Builds gsk = e(P,P)^q1 and the baby-step table as a device hash table.
+ * baby_steps = 0 lets the library choose (it may hold more baby steps than the
+ * reference's ceil(sqrt(T))+2; the set of decryptable values is kept identical). */
+int bgn_ctx_set_secret(bgn_ctx* ctx, const uint8_t* q1_be, size_t q1_len, uint64_t msg_space, uint32_t baby_steps);
+
+/* EncryptWithRandomness over a batch (bgn.go:340-353; the negative branch of
+ * EncryptPoly, poly.go:17-21, is x < 0):  out[i] = x[i]*P + r[i]*Q.
+ * r_be: count scalars of scalar_bytes each, or NULL for EncryptDeterministic
+ * (bgn.go:325-331).  out: count G1 elements. */
+int bgn_encrypt_batch(bgn_ctx* ctx, const int64_t* x, const uint8_t* r_be, size_t count, uint8_t* out);
+
+/* Add / Sub / Neg on level-1 ciphertexts (bgn.go:482, 419, 436-439). */
+int bgn_g1_add_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_g1_sub_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_g1_neg_batch(bgn_ctx* ctx, const uint8_t* a, size_t count, uint8_t* out);
+/* MultConst on level 1 (bgn.go:258): out[i] = k[i]*a[i]; k_be: count scalars of kbytes each. */
+int bgn_g1_mulconst_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* k_be, size_t kbytes, size_t count,
+                          uint8_t* out);
+
+/* Add / Sub / Neg / MultConst on level-2 ciphertexts (bgn.go:460, 397, 277). */
+int bgn_gt_mul_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_gt_div_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_gt_inv_batch(bgn_ctx* ctx, const uint8_t* a, size_t count, uint8_t* out);
+int bgn_gt_pow_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* k_be, size_t kbytes, size_t count, uint8_t* out);
+
+/* Mult (bgn.go:294-314): out[i] = e(a[i], b[i]).  makeL2 (bgn.go:316-321): e(a[i], P). */
+int bgn_pair_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_make_l2_batch(bgn_ctx* ctx, const uint8_t* a, size_t count, uint8_t* out);
+
+/* MultPoly (poly.go:123-156) over a batch of `count` polynomial pairs:
+ * c1: count*d1 G1 elements (coefficient-major per polynomial), c2: count*d2.
+ * out: count*(d1+d2) GT elements, out[u][j] = prod_{i+k=j} e(c1[u][i], c2[u][k]);
+ * the last slot of each polynomial is the GT identity, as in the reference. */
+int bgn_multpoly_batch(bgn_ctx* ctx, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                       uint8_t* out);
+
+/* L2 sum of `nterms` polynomials of `ncoeff` slots each (AddPoly folded, poly.go:191-204
+ * -> bgn.go:460): out[c] = prod_t in[t*ncoeff + c].  One GPU's share of an encrypted
+ * inner product; partial results from several GPUs are folded with the same call. */
+int bgn_l2_sum_reduce(bgn_ctx* ctx, const uint8_t* in, size_t nterms, size_t ncoeff, uint8_t* out);
+
+/* csk = C^q1 (bgn.go:223), level 2 only: count GT in, count GT out. */
+int bgn_gt_pow_secret_batch(bgn_ctx* ctx, const uint8_t* in, size_t count, uint8_t* out);
+
+/* decrypt (bgn.go:218-250) + recoverMessage (bgn.go:357-372) + getDL (gsbs.go:54-106),
+ * including the negate-and-retry path.  status[i]: 0 ok, 1 "cannot find discrete
+ * log; out of bounds" (gsbs.go:105), in which case out[i] = 0 (DecryptFailSafe). */
+int bgn_decrypt_batch(bgn_ctx* ctx, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status);
+
+/* ---- instrumentation (bench.py) ---- */
+/* When enabled, every kernel launch is bracketed by CUDA events on the context's
+ * stream; bgn_timing_get returns the accumulated device time and launch count of
+ * kernels whose name starts with `prefix` ("" = all) since the last reset. */
+int bgn_timing_enable(bgn_ctx* ctx, int on);
+int bgn_timing_reset(bgn_ctx* ctx);
+int bgn_timing_get(bgn_ctx* ctx, const char* prefix, double* ms_total, uint64_t* launches);
+/* Register-resident Montgomery-product microbenchmark: blocks*threads threads,
+ * `iters` dependent products on each of `ilp` (1, 2 or 4) chains; returns device ms. */
+int bgn_bench_mulmod(bgn_ctx* ctx, int ilp, int iters, int blocks, int threads, float* ms);
+/* Peak rate of the 32x32+64 multiply-add instruction (IMAD.WIDE.U32) on `device`:
+ * blocks*threads threads issue iters*64 independent-chain instructions each. */
+int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGN_B200_H */

@@ -1,0 +1,88 @@
+// hostsim.cpp -- CPU execution of the *device* programs (bgn_b200/csrc/*.cuh
+// compiled with BGN_HOSTSIM: carry flag, atomics and the thread grid emulated
+// in software).  TEST INFRASTRUCTURE ONLY: it lets the CPU test-suite check the
+// kernels' per-thread logic against the oracle without a GPU.  It is never
+// linked into libbgn_b200.so and nothing in bgn_b200/ can reach it.
+#define BGN_HOSTSIM 1
+#include <vector>
+
+#include "../../bgn_b200/csrc/kernels.cuh"
+
+namespace {
+template <int L>
+void sim_miller(const MillerArgs& a, int nblocks, int nt) {
+  std::vector<uint32_t> smem((size_t)BGN_MILLER_NSLOT * L * nt + nt);
+  for (int b = 0; b < nblocks; b++) {
+    std::vector<MillerTeam<L>> T;
+    T.reserve(nt);
+    for (int tid = 0; tid < nt; tid++) T.emplace_back(a, smem.data(), tid, b, nt);
+    for (auto& t : T) t.init();
+    int n = c_pc.naf_len;
+    for (int idx = 1; idx < n; idx++) {
+      for (auto& t : T) t.phaseA(MOP_DBL, idx == 1);
+      for (auto& t : T) t.phaseB();
+      int d = c_pc.naf[idx];
+      if (d != 0 && idx != n - 1) {
+        for (auto& t : T) t.phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
+        for (auto& t : T) t.phaseB();
+      }
+    }
+    for (auto& t : T) t.finalize();
+  }
+}
+}  // namespace
+
+#define FOR_L(L, ...)                          \
+  switch (L) {                                 \
+    case 3: { constexpr int LL = 3; __VA_ARGS__; } break;   \
+    case 5: { constexpr int LL = 5; __VA_ARGS__; } break;   \
+    case 17: { constexpr int LL = 17; __VA_ARGS__; } break; \
+    default: return -1;                        \
+  }                                            \
+  return 0;
+
+extern "C" {
+void hs_set_consts(const FieldConsts* fc, const PairConsts* pc) {
+  c_fc = *fc;
+  c_pc = *pc;
+}
+int hs_miller(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller<LL>(*a, nblocks, nt)) }
+int hs_encrypt(int L, const EncArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) encrypt_body<LL>(*a, e)) }
+int hs_normalize(int L, const NormArgs* a) { FOR_L(L, for (size_t g = 0; g < (size_t)a->G; g++) normalize_body<LL>(*a, g)) }
+int hs_g1_add(int L, const G1AddArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) g1_add_body<LL>(*a, e)) }
+int hs_g1_mulvar(int L, const G1MulArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) g1_mulvar_body<LL>(*a, e)) }
+int hs_gt_mul(int L, const GtBinArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_mul_body<LL>(*a, e)) }
+int hs_gt_pow(int L, const GtPowArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_pow_body<LL>(*a, e)) }
+int hs_gt_reduce(int L, const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms, int ncoeff, int G,
+                 uint32_t* ore, uint32_t* oim, size_t N) {
+  FOR_L(L, for (size_t id = 0; id < (size_t)G * ncoeff; id++)
+               gt_reduce_body<LL>(re, im, Nin, nterms, ncoeff, G, ore, oim, N, id))
+}
+int hs_bsgs_build(int L, const BsgsBuildArgs* a) {
+  FOR_L(L, for (size_t g = 0; g * a->chunk < a->S; g++) bsgs_build_body<LL>(*a, g))
+}
+int hs_bsgs_lookup(int L, const BsgsLookupArgs* a) {
+  FOR_L(L, for (size_t e = 0; e < a->count; e++) bsgs_lookup_body<LL>(*a, e))
+}
+int hs_tab_bases(int L, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
+  FOR_L(L, tab_bases_body<LL>(bx, by, nwin, X, Y, Z, N, 0))
+}
+int hs_tab_fill(int L, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, uint32_t* X,
+                uint32_t* Y, uint32_t* Z, size_t N) {
+  FOR_L(L, for (int w = 0; w < nwin; w++) tab_fill_body<LL>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, w))
+}
+int hs_g1_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf, size_t N) {
+  FOR_L(L, for (size_t e = 0; e < count; e++) g1_from_bytes_body<LL>(in, B, count, x, y, inf, N, e))
+}
+int hs_g1_to_bytes(int L, const uint32_t* x, const uint32_t* y, const uint8_t* inf, size_t N, size_t count, uint8_t* out,
+                   int B) {
+  FOR_L(L, for (size_t e = 0; e < count; e++) g1_to_bytes_body<LL>(x, y, inf, N, count, out, B, e))
+}
+int hs_fp2_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N) {
+  FOR_L(L, for (size_t e = 0; e < count; e++) fp2_from_bytes_body<LL>(in, B, count, re, im, N, e))
+}
+int hs_fp2_to_bytes(int L, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B) {
+  FOR_L(L, for (size_t e = 0; e < count; e++) fp2_to_bytes_body<LL>(re, im, N, count, out, B, e))
+}
+int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv(mkv(r, 1), mkvc(a, 1))) }
+}

@@ -1,0 +1,375 @@
+"""ctypes driver for tests/hostsim/libhostsim.so: runs the device programs of
+bgn_b200/csrc on the CPU (carry flag / grid emulated) so their logic can be
+checked against the oracle without a GPU.  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+MAXL, MAX_NAF, MAX_EXPW, NSLOT = 34, 1100, 34, 12
+SUPPORTED_L = (3, 5, 17)  # limb counts instantiated in hostsim.cpp
+PRODUCT_L = (3, 5, 9, 17, 33)  # limb counts the CUDA library instantiates
+
+u32p = C.POINTER(C.c_uint32)
+u8p = C.POINTER(C.c_uint8)
+
+
+class FieldConsts(C.Structure):
+    _fields_ = [("p", C.c_uint32 * MAXL), ("p2", C.c_uint32 * MAXL), ("one", C.c_uint32 * MAXL),
+                ("r2", C.c_uint32 * MAXL), ("np0", C.c_uint32), ("pad", C.c_uint32 * 3)]
+
+
+class PairConsts(C.Structure):
+    _fields_ = [("l", C.c_uint64), ("naf_len", C.c_int32), ("exp_bits", C.c_int32),
+                ("exp", C.c_uint32 * MAX_EXPW), ("naf", C.c_int8 * MAX_NAF)]
+
+
+class MillerArgs(C.Structure):
+    _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
+                ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
+                ("e_bcast", C.c_int), ("dM", C.c_int), ("dE", C.c_int), ("out_slots", C.c_int), ("count", C.c_int),
+                ("teams_per_block", C.c_int)]
+
+
+class EncArgs(C.Structure):
+    _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p),
+                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [("X", u32p), ("Y", u32p), ("Z", u32p), ("scratch", u32p), ("count", C.c_size_t), ("N", C.c_size_t),
+                ("G", C.c_int), ("ox", u32p), ("oy", u32p), ("o_estride", C.c_size_t), ("o_lstride", C.c_size_t),
+                ("inf", u8p)]
+
+
+class G1AddArgs(C.Structure):
+    _fields_ = [("x1", u32p), ("y1", u32p), ("inf1", u8p), ("x2", u32p), ("y2", u32p), ("inf2", u8p),
+                ("N1", C.c_size_t), ("N2", C.c_size_t), ("bcast1", C.c_int), ("subtract", C.c_int),
+                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+
+
+class G1MulArgs(C.Structure):
+    _fields_ = [("x", u32p), ("y", u32p), ("inf", u8p), ("Nin", C.c_size_t), ("k_be", u8p), ("kbytes", C.c_int),
+                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+
+
+class GtBinArgs(C.Structure):
+    _fields_ = [("are", u32p), ("aim", u32p), ("bre", u32p), ("bim", u32p), ("Na", C.c_size_t), ("Nb", C.c_size_t),
+                ("conj_b", C.c_int), ("ore", u32p), ("oim", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+
+
+class GtPowArgs(C.Structure):
+    _fields_ = [("re", u32p), ("im", u32p), ("Nin", C.c_size_t), ("e_be", u8p), ("ebytes", C.c_int), ("mode", C.c_int),
+                ("ore", u32p), ("oim", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+
+
+class BsgsBuildArgs(C.Structure):
+    _fields_ = [("gen", u32p), ("elems", u32p), ("slots", u32p), ("hmask", C.c_uint32), ("S", C.c_uint32),
+                ("chunk", C.c_int)]
+
+
+class BsgsLookupArgs(C.Structure):
+    _fields_ = [("re", u32p), ("im", u32p), ("Nin", C.c_size_t), ("count", C.c_size_t), ("elems", u32p),
+                ("slots", u32p), ("hmask", C.c_uint32), ("S", C.c_uint32), ("ginv", u32p), ("giant_steps", C.c_uint32),
+                ("mmax", C.c_uint64), ("out", C.POINTER(C.c_int64)), ("status", u8p)]
+
+
+_lib = None
+
+
+def build() -> str:
+    """(Re)build libhostsim.so when a device header is newer than it."""
+    so = os.path.join(HERE, "libhostsim.so")
+    src = os.path.join(HERE, "hostsim.cpp")
+    csrc = os.path.join(ROOT, "bgn_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def P32(a: np.ndarray):
+    return a.ctypes.data_as(u32p)
+
+
+def P8(a: np.ndarray):
+    return a.ctypes.data_as(u8p)
+
+
+def naf_digits(n: int) -> List[int]:
+    d = []
+    while n:
+        z = 0
+        if n & 1:
+            z = 2 - (n & 3)
+            n -= z
+        d.append(z)
+        n >>= 1
+    return d[::-1]
+
+
+def pick_L(p: int) -> int:
+    for L in PRODUCT_L:
+        if 32 * L >= p.bit_length() + 7:
+            return L
+    raise ValueError("p too large")
+
+
+class Sim:
+    """Orchestrates the simulated kernels the way api.cu does on the GPU."""
+
+    def __init__(self, par, P, Q, q1: Optional[int] = None):
+        self.par = par
+        self.p = par.p
+        self.L = pick_L(par.p)
+        assert self.L in SUPPORTED_L, "hostsim only instantiates L in %r" % (SUPPORTED_L,)
+        self.R = 1 << (32 * self.L)
+        self.Rinv = pow(self.R, -1, self.p)
+        self.B = par.coord_bytes
+        self.nbytes = (par.n.bit_length() + 7) // 8
+        fc = FieldConsts()
+        for name, v in (("p", self.p), ("p2", 2 * self.p), ("one", self.R % self.p), ("r2", self.R * self.R % self.p)):
+            arr = getattr(fc, name)
+            for i in range(MAXL):
+                arr[i] = (v >> (32 * i)) & 0xFFFFFFFF
+        fc.np0 = (-pow(self.p, -1, 1 << 32)) % (1 << 32)
+        pc = PairConsts()
+        pc.l = par.l
+        naf = naf_digits(par.n)
+        pc.naf_len = len(naf)
+        for i, z in enumerate(naf):
+            pc.naf[i] = z
+        if q1 is not None:
+            pc.exp_bits = q1.bit_length()
+            for i in range(MAX_EXPW):
+                pc.exp[i] = (q1 >> (32 * i)) & 0xFFFFFFFF
+        self.fc, self.pc = fc, pc
+        self.P, self.Q = P, Q
+        self.activate()
+
+    def activate(self):
+        lib().hs_set_consts(C.byref(self.fc), C.byref(self.pc))
+
+    # ---- conversions between Python integers and Montgomery SoA
+    def soa(self, vals: Sequence[int], mont: bool = True) -> np.ndarray:
+        n = max(1, len(vals))
+        a = np.zeros((self.L, n), dtype=np.uint32)
+        for e, v in enumerate(vals):
+            if mont:
+                v = v * self.R % self.p
+            for j in range(self.L):
+                a[j, e] = (v >> (32 * j)) & 0xFFFFFFFF
+        return a
+
+    def unsoa(self, a: np.ndarray, count: int, mont: bool = True) -> List[int]:
+        out = []
+        for e in range(count):
+            v = 0
+            for j in range(self.L):
+                v |= int(a[j, e]) << (32 * j)
+            out.append(v * self.Rinv % self.p if mont else v)
+        return out
+
+    def g1_arrays(self, pts):
+        x = self.soa([0 if P is None else P[0] for P in pts])
+        y = self.soa([0 if P is None else P[1] for P in pts])
+        inf = np.array([1 if P is None else 0 for P in pts] or [0], dtype=np.uint8)
+        return x, y, inf
+
+    # ---- kernels
+    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2):
+        Mx, My, Mi = self.g1_arrays(M)
+        Ex, Ey, Ei = self.g1_arrays(E)
+        nout = count * out_slots
+        ore = np.zeros((self.L, nout), dtype=np.uint32)
+        oim = np.zeros((self.L, nout), dtype=np.uint32)
+        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), Mx.shape[1],
+                       Ex.shape[1], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block)
+        nt = teams_per_block * dE + 1  # one idle thread: exercises the inactive path
+        nblocks = (count + teams_per_block - 1) // teams_per_block
+        assert lib().hs_miller(self.L, C.byref(a), nblocks, nt) == 0
+        return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
+
+    def multpoly(self, c1, d1, c2, d2, count):
+        if d1 <= d2:
+            return self.miller(c1, d1, c2, d2, count, d1 + d2)
+        return self.miller(c2, d2, c1, d1, count, d1 + d2)
+
+    def pair(self, A, Bp):
+        return self.miller(A, 1, Bp, 1, len(A), 1, teams_per_block=3)
+
+    def normalize(self, X, Y, Z, count, G=None):
+        N = X.shape[1]
+        scratch = np.zeros_like(X)
+        ox = np.zeros_like(X)
+        oy = np.zeros_like(X)
+        inf = np.zeros(max(1, count), dtype=np.uint8)
+        G = G or max(1, min(count, 3))
+        a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), count, N, G, P32(ox), P32(oy), 1, N, P8(inf))
+        assert lib().hs_normalize(self.L, C.byref(a)) == 0
+        xs, ys = self.unsoa(ox, count), self.unsoa(oy, count)
+        return [None if inf[e] else (xs[e], ys[e]) for e in range(count)]
+
+    def build_table(self, base, nwin):
+        L = self.L
+        bx, by = self.soa([base[0]]), self.soa([base[1]])
+        X = np.zeros((L, nwin), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        assert lib().hs_tab_bases(L, P32(bx), P32(by), nwin, P32(X), P32(Y), P32(Z), nwin) == 0
+        bases = self.normalize(X, Y, Z, nwin)
+        ax, ay, ainf = self.g1_arrays(bases)
+        nent = nwin * 255
+        X = np.zeros((L, nent), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        assert lib().hs_tab_fill(L, P32(ax), P32(ay), P8(ainf), nwin, nwin, P32(X), P32(Y), P32(Z), nent) == 0
+        tab = np.zeros(nent * 2 * L, dtype=np.uint32)
+        scratch = np.zeros_like(X)
+        a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), nent, nent, 7, P32(tab), P32(tab[L:]), 2 * L, 1, None)
+        assert lib().hs_normalize(L, C.byref(a)) == 0
+        return tab
+
+    def encrypt(self, xs, rs, tabP, tabQ):
+        count = len(xs)
+        x = np.array(xs, dtype=np.int64)
+        X = np.zeros((self.L, count), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        if rs is None:
+            rbuf, rp = None, None
+        else:
+            rbuf = np.frombuffer(b"".join(int(r).to_bytes(self.nbytes, "big") for r in rs), dtype=np.uint8).copy()
+            rp = P8(rbuf)
+        a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)), rp, self.nbytes, P32(tabP), P32(tabQ), P32(X), P32(Y),
+                    P32(Z), count, count)
+        assert lib().hs_encrypt(self.L, C.byref(a)) == 0
+        return self.normalize(X, Y, Z, count)
+
+    def g1_add(self, A, Bp, subtract=False, bcast1=False):
+        count = len(Bp)
+        x1, y1, i1 = self.g1_arrays(A)
+        x2, y2, i2 = self.g1_arrays(Bp)
+        X = np.zeros((self.L, count), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        a = G1AddArgs(P32(x1), P32(y1), P8(i1), P32(x2), P32(y2), P8(i2), x1.shape[1], x2.shape[1],
+                      1 if bcast1 else 0, 1 if subtract else 0, P32(X), P32(Y), P32(Z), count, count)
+        assert lib().hs_g1_add(self.L, C.byref(a)) == 0
+        return self.normalize(X, Y, Z, count)
+
+    def g1_mulvar(self, A, ks, kbytes):
+        count = len(A)
+        x, y, inf = self.g1_arrays(A)
+        kb = np.frombuffer(b"".join(int(k).to_bytes(kbytes, "big") for k in ks), dtype=np.uint8).copy()
+        X = np.zeros((self.L, count), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        a = G1MulArgs(P32(x), P32(y), P8(inf), x.shape[1], P8(kb), kbytes, P32(X), P32(Y), P32(Z), count, count)
+        assert lib().hs_g1_mulvar(self.L, C.byref(a)) == 0
+        return self.normalize(X, Y, Z, count)
+
+    def gt_arrays(self, vals):
+        return self.soa([v[0] for v in vals]), self.soa([v[1] for v in vals])
+
+    def gt_mul(self, A, Bv, conj_b=False):
+        count = len(A)
+        are, aim = self.gt_arrays(A)
+        bre, bim = self.gt_arrays(Bv)
+        ore, oim = np.zeros_like(are), np.zeros_like(are)
+        a = GtBinArgs(P32(are), P32(aim), P32(bre), P32(bim), count, count, 1 if conj_b else 0, P32(ore), P32(oim),
+                      count, count)
+        assert lib().hs_gt_mul(self.L, C.byref(a)) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
+
+    def gt_pow(self, A, mode, exps=None, ebytes=0):
+        count = len(A)
+        are, aim = self.gt_arrays(A)
+        ore, oim = np.zeros_like(are), np.zeros_like(are)
+        eb, ep = None, None
+        if exps is not None:
+            eb = np.frombuffer(b"".join(int(k).to_bytes(ebytes, "big") for k in exps), dtype=np.uint8).copy()
+            ep = P8(eb)
+        a = GtPowArgs(P32(are), P32(aim), count, ep, ebytes, mode, P32(ore), P32(oim), count, count)
+        assert lib().hs_gt_pow(self.L, C.byref(a)) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
+
+    def gt_reduce(self, vals, nterms, ncoeff, G):
+        re, im = self.gt_arrays(vals)
+        ore = np.zeros((self.L, G * ncoeff), dtype=np.uint32)
+        oim = np.zeros_like(ore)
+        assert lib().hs_gt_reduce(self.L, P32(re), P32(im), re.shape[1], nterms, ncoeff, G, P32(ore), P32(oim),
+                                  G * ncoeff) == 0
+        return list(zip(self.unsoa(ore, G * ncoeff), self.unsoa(oim, G * ncoeff)))
+
+    def bsgs_setup(self, gsk: Tuple[int, int], msg_space: int, S: Optional[int] = None):
+        import math
+        L, p = self.L, self.p
+        bound = int(math.ceil(math.sqrt(float(msg_space))))
+        self.mmax = bound * bound + bound + 2
+        S = S or self.mmax
+        hs = 1
+        while hs < 2 * S:
+            hs <<= 1
+        gen = np.concatenate([self.soa([gsk[0]])[:, 0], self.soa([gsk[1]])[:, 0]]).astype(np.uint32)
+        self.bs_elems = np.zeros(S * 2 * L, dtype=np.uint32)
+        self.bs_slots = np.zeros(hs, dtype=np.uint32)
+        a = BsgsBuildArgs(P32(gen), P32(self.bs_elems), P32(self.bs_slots), hs - 1, S, 7)
+        assert lib().hs_bsgs_build(L, C.byref(a)) == 0
+        from oracle import bgn_oracle as O
+        gi = O.fp2_conj(O.fp2_pow(gsk, S, p), p)
+        self.bs_ginv = np.concatenate([self.soa([gi[0]])[:, 0], self.soa([gi[1]])[:, 0]]).astype(np.uint32)
+        self.bs_S, self.bs_hmask = S, hs - 1
+        self.bs_giant = (self.mmax + S - 1) // S
+
+    def bsgs_lookup(self, csk):
+        count = len(csk)
+        re, im = self.gt_arrays(csk)
+        out = np.zeros(count, dtype=np.int64)
+        status = np.zeros(count, dtype=np.uint8)
+        a = BsgsLookupArgs(P32(re), P32(im), count, count, P32(self.bs_elems), P32(self.bs_slots), self.bs_hmask,
+                           self.bs_S, P32(self.bs_ginv), self.bs_giant, self.mmax,
+                           out.ctypes.data_as(C.POINTER(C.c_int64)), P8(status))
+        assert lib().hs_bsgs_lookup(self.L, C.byref(a)) == 0
+        return list(out), list(status)
+
+    # ---- byte formats
+    def g1_from_bytes(self, data: bytes, count: int):
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        x = np.zeros((self.L, count), dtype=np.uint32)
+        y = np.zeros_like(x)
+        inf = np.zeros(count, dtype=np.uint8)
+        assert lib().hs_g1_from_bytes(self.L, P8(buf), self.B, count, P32(x), P32(y), P8(inf), count) == 0
+        xs, ys = self.unsoa(x, count), self.unsoa(y, count)
+        return [None if inf[e] else (xs[e], ys[e]) for e in range(count)]
+
+    def g1_to_bytes(self, pts) -> bytes:
+        count = len(pts)
+        x, y, inf = self.g1_arrays(pts)
+        out = np.zeros(count * 2 * self.B, dtype=np.uint8)
+        assert lib().hs_g1_to_bytes(self.L, P32(x), P32(y), P8(inf), x.shape[1], count, P8(out), self.B) == 0
+        return out.tobytes()
+
+    def gt_roundtrip_bytes(self, vals) -> bytes:
+        count = len(vals)
+        re, im = self.gt_arrays(vals)
+        out = np.zeros(count * 2 * self.B, dtype=np.uint8)
+        assert lib().hs_fp2_to_bytes(self.L, P32(re), P32(im), count, count, P8(out), self.B) == 0
+        re2, im2 = np.zeros_like(re), np.zeros_like(im)
+        assert lib().hs_fp2_from_bytes(self.L, P8(out), self.B, count, P32(re2), P32(im2), count) == 0
+        back = list(zip(self.unsoa(re2, count), self.unsoa(im2, count)))
+        assert back == [(v[0] % self.p, v[1] % self.p) for v in vals]
+        return out.tobytes()
