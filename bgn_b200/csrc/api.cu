@@ -135,6 +135,8 @@ struct bgn_ctx {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> ev_pool;
   uint64_t total_launches = 0;
+  cudaEvent_t call_a = nullptr, call_b = nullptr;  // bracket the device work of the last C-ABI call
+  double last_call_ms = 0;
   std::string err;
 };
 
@@ -450,8 +452,21 @@ int guarded(bgn_ctx* c, Fn fn) {
   try {
     activate(c);
     arena_reset(c);
+    if (c->timing) {
+      if (!c->call_a) {
+        CK(cudaEventCreate(&c->call_a));
+        CK(cudaEventCreate(&c->call_b));
+      }
+      CK(cudaEventRecord(c->call_a, c->stream));
+    }
     fn();
+    if (c->timing) CK(cudaEventRecord(c->call_b, c->stream));
     finish(c);
+    if (c->timing) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, c->call_a, c->call_b));
+      c->last_call_ms = ms;
+    }
     return BGN_OK;
   } catch (const CudaErr& e) {
     c->err = e.msg;
@@ -616,6 +631,8 @@ void bgn_ctx_destroy(bgn_ctx* c) {
   cudaFree(c->bs_ginv);
   cudaFree(c->arena);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->call_a) cudaEventDestroy(c->call_a);
+  if (c->call_b) cudaEventDestroy(c->call_b);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1132,6 +1149,13 @@ int bgn_timing_get(bgn_ctx* c, const char* prefix, double* ms_total, uint64_t* l
   if (pl == 0) n = c->total_launches;
   if (ms_total) *ms_total = ms;
   if (launches) *launches = n;
+  return BGN_OK;
+}
+
+int bgn_timing_last_call(bgn_ctx* c, double* ms) {
+  if (!c || !ms) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  *ms = c->last_call_ms;
   return BGN_OK;
 }
 

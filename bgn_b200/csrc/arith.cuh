@@ -27,6 +27,7 @@
 #define BGN_UNROLL
 namespace bgnsim {
 static thread_local uint32_t cc = 0;
+static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
 }
 BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t t = (uint64_t)a * b;
@@ -174,6 +175,9 @@ struct Fp {
   // r = a*b/R mod p, r in [0,2p) for a,b in [0,2p).  2L^2+L products.
   BGN_DEV static void mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
     uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    bgnsim::nmul++;
+#endif
     const uint32_t* pm = c_fc.p;
     const uint32_t np0 = c_fc.np0;
     row<true>(X, Y, a, b[0], pm, np0);

@@ -1,0 +1,237 @@
+"""Thin object wrapper around the C-ABI context (include/bgn_b200.h).
+
+Buffers may be `bytes`/`bytearray`, numpy uint8 arrays (host) or torch uint8
+tensors (host, pinned host, or CUDA on the context's device).  Results are
+returned as numpy arrays unless an input was a CUDA tensor, in which case the
+result is a CUDA tensor too (nothing crosses PCIe in that case).  All compute
+happens inside libbgn_b200.so on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+
+
+class BgnError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__("bgn_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _as_buf(x):
+    """-> (address, nbytes, keepalive, is_cuda)"""
+    if x is None:
+        return None, 0, None, False
+    if _is_torch(x):
+        assert x.is_contiguous(), "tensor must be contiguous"
+        return x.data_ptr(), x.numel() * x.element_size(), x, x.is_cuda
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(x, dtype=np.uint8)
+        return a.ctypes.data, a.nbytes, (a, x), False
+    a = np.ascontiguousarray(x)
+    return a.ctypes.data, a.nbytes, a, False
+
+
+class Engine:
+    """One BGN key resident on one GPU (bgn_ctx)."""
+
+    def __init__(self, p: int, n: int, l: int, P_bytes: bytes, Q_bytes: bytes, device: int = 0):
+        self._lib = _cabi.load()
+        self._ctx = C.c_void_p()
+        pb = p.to_bytes((p.bit_length() + 7) // 8, "big")
+        nb = n.to_bytes((n.bit_length() + 7) // 8, "big")
+        prm = _cabi.bgn_params(pb, len(pb), nb, len(nb), l, bytes(P_bytes), bytes(Q_bytes))
+        st = self._lib.bgn_ctx_create(C.byref(prm), device, C.byref(self._ctx))
+        if st != 0:
+            self._ctx = C.c_void_p()
+            raise BgnError(st, "bgn_ctx_create failed (see stderr)")
+        L, B, nbytes = C.c_int(), C.c_int(), C.c_int()
+        self._lib.bgn_ctx_info(self._ctx, C.byref(L), C.byref(B), C.byref(nbytes))
+        self.limbs, self.coord_bytes, self.scalar_bytes = L.value, B.value, nbytes.value
+        self.elem_bytes = 2 * B.value
+        self.device = device
+        self.p, self.n, self.l = p, n, l
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.bgn_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, st: int):
+        if st != 0:
+            raise BgnError(st, self._lib.bgn_last_error(self._ctx).decode())
+
+    def _out(self, nbytes: int, cuda: bool, out=None):
+        if out is not None:
+            return out
+        if cuda:
+            import torch
+            return torch.empty(nbytes, dtype=torch.uint8, device="cuda:%d" % self.device)
+        return np.empty(nbytes, dtype=np.uint8)
+
+    def _count(self, nbytes: int) -> int:
+        assert nbytes % self.elem_bytes == 0, "buffer is not a whole number of elements"
+        return nbytes // self.elem_bytes
+
+    def _binop(self, fn, a, b, out=None):
+        pa, na, ka, ca = _as_buf(a)
+        pb, nb_, kb, cb = _as_buf(b)
+        assert na == nb_
+        count = self._count(na)
+        o = self._out(na, ca or cb, out)
+        po = _as_buf(o)[0]
+        self._check(fn(self._ctx, pa, pb, count, po))
+        return o
+
+    def _unop(self, fn, a, out=None):
+        pa, na, ka, ca = _as_buf(a)
+        count = self._count(na)
+        o = self._out(na, ca, out)
+        self._check(fn(self._ctx, pa, count, _as_buf(o)[0]))
+        return o
+
+    def scalars_be(self, ks: Sequence[int], width: Optional[int] = None) -> np.ndarray:
+        width = width or self.scalar_bytes
+        return np.frombuffer(b"".join(int(k).to_bytes(width, "big") for k in ks), dtype=np.uint8).copy()
+
+    # ------------------------------------------------------------------ C-ABI calls
+    def set_secret(self, q1: int, msg_space: int, baby_steps: int = 0):
+        qb = q1.to_bytes((q1.bit_length() + 7) // 8, "big")
+        self._check(self._lib.bgn_ctx_set_secret(self._ctx, qb, len(qb), msg_space, baby_steps))
+
+    def encrypt_batch(self, x, r_be=None, out=None):
+        """x: int64 array/tensor; r_be: count*scalar_bytes big-endian randomness or None."""
+        if not _is_torch(x):
+            x = np.ascontiguousarray(x, dtype=np.int64)
+        px, nx, kx, cx = _as_buf(x)
+        count = nx // 8
+        pr, nr, kr, cr = _as_buf(r_be)
+        if r_be is not None:
+            assert nr == count * self.scalar_bytes
+        o = self._out(count * self.elem_bytes, cx or cr, out)
+        self._check(self._lib.bgn_encrypt_batch(self._ctx, px, pr, count, _as_buf(o)[0]))
+        return o
+
+    def g1_add_batch(self, a, b, out=None):
+        return self._binop(self._lib.bgn_g1_add_batch, a, b, out)
+
+    def g1_sub_batch(self, a, b, out=None):
+        return self._binop(self._lib.bgn_g1_sub_batch, a, b, out)
+
+    def g1_neg_batch(self, a, out=None):
+        return self._unop(self._lib.bgn_g1_neg_batch, a, out)
+
+    def g1_mulconst_batch(self, a, k_be, kbytes: int, out=None):
+        pa, na, ka, ca = _as_buf(a)
+        pk_, nk, kk, ck = _as_buf(k_be)
+        count = self._count(na)
+        assert nk == count * kbytes
+        o = self._out(na, ca, out)
+        self._check(self._lib.bgn_g1_mulconst_batch(self._ctx, pa, pk_, kbytes, count, _as_buf(o)[0]))
+        return o
+
+    def gt_mul_batch(self, a, b, out=None):
+        return self._binop(self._lib.bgn_gt_mul_batch, a, b, out)
+
+    def gt_div_batch(self, a, b, out=None):
+        return self._binop(self._lib.bgn_gt_div_batch, a, b, out)
+
+    def gt_inv_batch(self, a, out=None):
+        return self._unop(self._lib.bgn_gt_inv_batch, a, out)
+
+    def gt_pow_batch(self, a, k_be, kbytes: int, out=None):
+        pa, na, ka, ca = _as_buf(a)
+        pk_, nk, kk, ck = _as_buf(k_be)
+        count = self._count(na)
+        assert nk == count * kbytes
+        o = self._out(na, ca, out)
+        self._check(self._lib.bgn_gt_pow_batch(self._ctx, pa, pk_, kbytes, count, _as_buf(o)[0]))
+        return o
+
+    def pair_batch(self, a, b, out=None):
+        return self._binop(self._lib.bgn_pair_batch, a, b, out)
+
+    def make_l2_batch(self, a, out=None):
+        return self._unop(self._lib.bgn_make_l2_batch, a, out)
+
+    def multpoly_batch(self, c1, d1: int, c2, d2: int, count: int, out=None):
+        p1, n1, k1, cu1 = _as_buf(c1)
+        p2, n2, k2, cu2 = _as_buf(c2)
+        assert n1 == count * d1 * self.elem_bytes and n2 == count * d2 * self.elem_bytes
+        o = self._out(count * (d1 + d2) * self.elem_bytes, cu1 or cu2, out)
+        self._check(self._lib.bgn_multpoly_batch(self._ctx, p1, d1, p2, d2, count, _as_buf(o)[0]))
+        return o
+
+    def l2_sum_reduce(self, terms, nterms: int, ncoeff: int, out=None):
+        pt, nt, kt, ct = _as_buf(terms)
+        assert nt == nterms * ncoeff * self.elem_bytes
+        o = self._out(ncoeff * self.elem_bytes, ct, out)
+        self._check(self._lib.bgn_l2_sum_reduce(self._ctx, pt, nterms, ncoeff, _as_buf(o)[0]))
+        return o
+
+    def gt_pow_secret_batch(self, a, out=None):
+        return self._unop(self._lib.bgn_gt_pow_secret_batch, a, out)
+
+    def decrypt_batch(self, cts, is_l2: bool):
+        """-> (int64 values, uint8 status); status 1 = 'cannot find discrete log; out of bounds'."""
+        pc, nc, kc, cc = _as_buf(cts)
+        count = self._count(nc)
+        if cc:
+            import torch
+            dev = "cuda:%d" % self.device
+            vals = torch.empty(count, dtype=torch.int64, device=dev)
+            status = torch.empty(count, dtype=torch.uint8, device=dev)
+        else:
+            vals = np.empty(count, dtype=np.int64)
+            status = np.empty(count, dtype=np.uint8)
+        self._check(self._lib.bgn_decrypt_batch(self._ctx, pc, 1 if is_l2 else 0, count, _as_buf(vals)[0],
+                                                _as_buf(status)[0]))
+        return vals, status
+
+    # ------------------------------------------------------------------ instrumentation
+    def timing_enable(self, on: bool = True):
+        self._check(self._lib.bgn_timing_enable(self._ctx, 1 if on else 0))
+
+    def timing_reset(self):
+        self._check(self._lib.bgn_timing_reset(self._ctx))
+
+    def timing_get(self, prefix: str = ""):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self._lib.bgn_timing_get(self._ctx, prefix.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def timing_last_call(self) -> float:
+        """device ms of the last call (copy-in .. copy-out) on the context's stream"""
+        ms = C.c_double()
+        self._check(self._lib.bgn_timing_last_call(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def bench_mulmod(self, ilp: int, iters: int, blocks: int, threads: int) -> float:
+        ms = C.c_float()
+        self._check(self._lib.bgn_bench_mulmod(self._ctx, ilp, iters, blocks, threads, C.byref(ms)))
+        return ms.value
+
+
+def bench_imad_peak(device: int, iters: int, blocks: int, threads: int):
+    """-> (ms, IMAD.WIDE instructions per thread)"""
+    lib = _cabi.load()
+    ms, ipt = C.c_float(), C.c_double()
+    st = lib.bgn_bench_imad_peak(device, iters, blocks, threads, C.byref(ms), C.byref(ipt))
+    if st != 0:
+        raise BgnError(st, "bgn_bench_imad_peak failed")
+    return ms.value, ipt.value

@@ -1,0 +1,73 @@
+"""Work model of the kernels: how many F_p Montgomery products (modmuls) the
+schedules in bgn_b200/csrc actually execute, and how many 32x32->64 products
+(IMAD.WIDE issue slots) that is.  bench.py's roofline numbers come from here;
+tests/test_hostsim.py checks these formulas against a counter in the CPU
+simulation of the device code, and DESIGN.md states them.
+
+Units:  1 modmul on L limbs = 2*L*L + L products.
+"""
+from __future__ import annotations
+
+from typing import List
+
+
+def products_per_modmul(L: int) -> int:
+    return 2 * L * L + L
+
+
+def pick_limbs(p: int) -> int:
+    for L in (3, 5, 9, 17, 33):
+        if 32 * L >= p.bit_length() + 7:
+            return L
+    raise ValueError("field too large")
+
+
+def naf_digits(n: int) -> List[int]:
+    d = []
+    while n:
+        z = 0
+        if n & 1:
+            z = 2 - (n & 3)
+            n -= z
+        d.append(z)
+        n >>= 1
+    return d[::-1]
+
+
+def fermat_inv_modmuls(p: int, L: int) -> int:
+    """F<L>::inv: 4-bit fixed window over p-2 (field.cuh)."""
+    e = p - 2
+    cnt = 14  # table a^2..a^15
+    started = False
+    for w in range(8 * L - 1, -1, -1):
+        d = (e >> (4 * w)) & 15
+        if started:
+            cnt += 4
+        if d:
+            if started:
+                cnt += 1
+            started = True
+    return cnt
+
+
+def final_exp_modmuls(p: int, l: int, L: int) -> int:
+    """GT<L>::final_exp: conj(f)^2/N(f) then ^l (pairing.cuh)."""
+    return 5 + fermat_inv_modmuls(p, L) + 2 * (l.bit_length() - 1) + 3 * (bin(l).count("1") - 1)
+
+
+def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
+    """One unit of k_miller (dM Miller points x dE evaluation points, dM <= dE; all points finite):
+    dbl_line 12, madd_line 13, line_mul 5, sqr2 2 per output slot."""
+    L = pick_limbs(p)
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    nslots = dM + dE - 1
+    per_dbl = dM * 12 + dM * dE * 5
+    per_add = dM * 13 + dM * dE * 5
+    return D * per_dbl + (D - 1) * nslots * 2 + A * per_add + nslots * final_exp_modmuls(p, l, L)
+
+
+def canonical_pairing_modmuls(n: int, l: int) -> int:
+    """PBC-like unshared schedule, one full pairing."""
+    return 23 * n.bit_length() + 18 * bin(n).count("1") - 70 + 4 + 3 + 2 * l.bit_length() + 3 * bin(l).count("1") + 1

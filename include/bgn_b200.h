@@ -124,6 +124,9 @@ int bgn_decrypt_batch(bgn_ctx* ctx, const uint8_t* in, int is_l2, size_t count, 
 int bgn_timing_enable(bgn_ctx* ctx, int on);
 int bgn_timing_reset(bgn_ctx* ctx);
 int bgn_timing_get(bgn_ctx* ctx, const char* prefix, double* ms_total, uint64_t* launches);
+/* Device time of the last C-ABI call on this context, first copy-in to last copy-out
+ * (CUDA events on the context's stream); valid while timing is enabled. */
+int bgn_timing_last_call(bgn_ctx* ctx, double* ms);
 /* Register-resident Montgomery-product microbenchmark: blocks*threads threads,
  * `iters` dependent products on each of `ilp` (1, 2 or 4) chains; returns device ms. */
 int bgn_bench_mulmod(bgn_ctx* ctx, int ilp, int iters, int blocks, int threads, float* ms);

@@ -84,5 +84,10 @@ int hs_fp2_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* r
 int hs_fp2_to_bytes(int L, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B) {
   FOR_L(L, for (size_t e = 0; e < count; e++) fp2_to_bytes_body<LL>(re, im, N, count, out, B, e))
 }
+uint64_t hs_mul_count(int reset) {
+  uint64_t v = bgnsim::nmul;
+  if (reset) bgnsim::nmul = 0;
+  return v;
+}
 int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv(mkv(r, 1), mkvc(a, 1))) }
 }

@@ -1,0 +1,304 @@
+"""GPU parity: the CUDA path, called through the C-ABI (ctypes -> libbgn_b200.so),
+against (i) the committed golden vectors and (ii) the oracle on seeded inputs.
+Bit-exact: every comparison is on serialised bytes / integers."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, unhex
+
+pytestmark = pytest.mark.gpu
+
+_engines = {}
+
+
+def engine_for(g):
+    from bgn_b200 import Engine
+    kb = g["key_bits"]
+    if kb not in _engines:
+        e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+        e.set_secret(int(g["q1"], 16), g["msg_space"])
+        _engines[kb] = e
+    return _engines[kb]
+
+
+def buf(xs):
+    return np.frombuffer(unhex(xs), dtype=np.uint8)
+
+
+def scal(e, hexes, width):
+    return e.scalars_be([int(h, 16) for h in hexes], width)
+
+
+def test_ctx_info(golden):
+    e = engine_for(golden)
+    assert e.coord_bytes == golden["coord_bytes"]
+    assert e.scalar_bytes == (int(golden["n"], 16).bit_length() + 7) // 8
+    assert 32 * e.limbs >= int(golden["p"], 16).bit_length() + 3
+
+
+def test_encrypt(golden):
+    e, v = engine_for(golden), golden["encrypt"]
+    out = e.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(e, v["r"], e.scalar_bytes))
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_encrypt_deterministic(golden):
+    """r_be = NULL is EncryptDeterministic (bgn.go:325-331) == randomness 0."""
+    e = engine_for(golden)
+    xs = np.array([0, 1, 2, -1, 1021], dtype=np.int64)
+    a = e.encrypt_batch(xs, None)
+    b = e.encrypt_batch(xs, e.scalars_be([0] * len(xs)))
+    assert a.tobytes() == b.tobytes()
+    assert a[: e.elem_bytes].tobytes() == bytes(e.elem_bytes)  # x = 0 -> O -> all-zero bytes
+
+
+@pytest.mark.parametrize("op", ["g1_add", "g1_sub"])
+def test_g1_binop(golden, op):
+    e, v = engine_for(golden), golden[op]
+    out = getattr(e, op + "_batch")(buf(v["a"]), buf(v["b"]))
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_g1_neg(golden):
+    e, v = engine_for(golden), golden["g1_neg"]
+    assert e.g1_neg_batch(buf(v["a"])).tobytes() == unhex(v["out"])
+
+
+def test_g1_mulconst(golden):
+    e, v = engine_for(golden), golden["g1_mulconst"]
+    out = e.g1_mulconst_batch(buf(v["a"]), scal(e, v["k"], v["kbytes"]), v["kbytes"])
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_pair(golden):
+    e, v = engine_for(golden), golden["pair"]
+    assert e.pair_batch(buf(v["a"]), buf(v["b"])).tobytes() == unhex(v["out"])
+    # symmetric pairing
+    assert e.pair_batch(buf(v["b"]), buf(v["a"])).tobytes() == unhex(v["out"])
+
+
+def test_make_l2(golden):
+    e, v = engine_for(golden), golden["make_l2"]
+    assert e.make_l2_batch(buf(v["a"])).tobytes() == unhex(v["out"])
+
+
+@pytest.mark.parametrize("op", ["gt_mul", "gt_div"])
+def test_gt_binop(golden, op):
+    e, v = engine_for(golden), golden[op]
+    assert getattr(e, op + "_batch")(buf(v["a"]), buf(v["b"])).tobytes() == unhex(v["out"])
+
+
+def test_gt_inv(golden):
+    e, v = engine_for(golden), golden["gt_inv"]
+    assert e.gt_inv_batch(buf(v["a"])).tobytes() == unhex(v["out"])
+
+
+def test_gt_pow(golden):
+    e, v = engine_for(golden), golden["gt_pow"]
+    out = e.gt_pow_batch(buf(v["a"]), scal(e, v["k"], v["kbytes"]), v["kbytes"])
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_multpoly(golden):
+    e, v = engine_for(golden), golden["multpoly"]
+    out = e.multpoly_batch(buf(v["c1"]), v["d1"], buf(v["c2"]), v["d2"], 1)
+    assert out.tobytes() == unhex(v["out"])
+    # swapped operands: the product is commutative
+    out = e.multpoly_batch(buf(v["c2"]), v["d2"], buf(v["c1"]), v["d1"], 1)
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_multpoly_batch_of_copies(golden):
+    """ragged block occupancy: 37 units of the same product must all equal the golden one."""
+    e, v = engine_for(golden), golden["multpoly"]
+    cnt = 37
+    out = e.multpoly_batch(np.tile(buf(v["c1"]), cnt), v["d1"], np.tile(buf(v["c2"]), cnt), v["d2"], cnt)
+    assert out.tobytes() == unhex(v["out"]) * cnt
+
+
+def test_l2_sum(golden):
+    e, v = engine_for(golden), golden["l2_sum"]
+    assert e.l2_sum_reduce(buf(v["in"]), v["nterms"], v["ncoeff"]).tobytes() == unhex(v["out"])
+
+
+def test_l2_sum_large_tree(golden):
+    """multi-pass tree: 1000 copies of term set -> product = golden^(1000) per coefficient."""
+    e, v = engine_for(golden), golden["l2_sum"]
+    reps = 200
+    got = e.l2_sum_reduce(np.tile(buf(v["in"]), reps), v["nterms"] * reps, v["ncoeff"])
+    k = e.scalars_be([reps] * v["ncoeff"], 2)
+    exp = e.gt_pow_batch(buf(v["out"]), k, 2)
+    assert got.tobytes() == exp.tobytes()
+
+
+def test_gt_pow_secret(golden):
+    e, v = engine_for(golden), golden["decrypt_l2"]
+    assert e.gt_pow_secret_batch(buf(v["in"])).tobytes() == unhex(v["csk"])
+
+
+def test_decrypt_l2(golden):
+    e, v = engine_for(golden), golden["decrypt_l2"]
+    vals, st = e.decrypt_batch(buf(v["in"]), True)
+    assert list(st) == v["status"]
+    assert [int(x) for x in vals] == v["out"]
+
+
+def test_decrypt_l1(golden):
+    e, v = engine_for(golden), golden["decrypt_l1"]
+    vals, st = e.decrypt_batch(buf(v["in"]), False)
+    assert list(st) == v["status"]
+    assert [int(x) for x in vals] == v["out"]
+
+
+def test_empty_batches(golden):
+    e = engine_for(golden)
+    z = np.zeros(0, dtype=np.uint8)
+    assert e.g1_add_batch(z, z).size == 0
+    assert e.pair_batch(z, z).size == 0
+    assert e.encrypt_batch(np.zeros(0, dtype=np.int64), None).size == 0
+    vals, st = e.decrypt_batch(z, True)
+    assert vals.size == 0 and st.size == 0
+
+
+def test_decrypt_before_setup():
+    from bgn_b200 import BgnError, Engine
+    g = load_golden(64)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    with pytest.raises(BgnError) as ei:
+        e.decrypt_batch(buf(g["decrypt_l2"]["in"]), True)
+    assert ei.value.status == -3 and "DL tables not computed" in str(ei.value)
+    e.close()
+
+
+def test_bad_params_rejected():
+    from bgn_b200 import BgnError, Engine
+    g = load_golden(64)
+    with pytest.raises(BgnError):  # p + 1 != l * n
+        Engine(int(g["p"], 16), int(g["n"], 16), g["l"] + 4, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    bad = bytearray(bytes.fromhex(g["P"]))
+    bad[-1] ^= 1
+    with pytest.raises(BgnError):  # generator not on the curve
+        Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes(bad), bytes.fromhex(g["Q"]))
+
+
+def test_off_curve_input_becomes_O(golden):
+    """curve_from_bytes: a pair not on the curve is O."""
+    e, v = engine_for(golden), golden["g1_add"]
+    a = bytearray(bytes.fromhex(v["a"][0]))
+    a[-1] ^= 1
+    out = e.g1_add_batch(np.frombuffer(bytes(a), dtype=np.uint8), buf([v["b"][0]]))
+    assert out.tobytes() == bytes.fromhex(v["b"][0])
+
+
+# ---------------------------------------------------------------- seeded random parity vs the oracle
+@pytest.mark.parametrize("kb", [128, 512])
+def test_random_vs_oracle(kb):
+    from oracle import bgn_oracle as O
+    g = load_golden(kb)
+    e = engine_for(g)
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    P = O.g1_from_bytes(bytes.fromhex(g["P"]), par)
+    Q = O.g1_from_bytes(bytes.fromhex(g["Q"]), par)
+    pk = O.PublicKey(par, P, Q, g["msg_space"])
+    rng = random.Random(kb)
+    cnt = 24 if kb == 128 else 6
+    xs = [rng.randrange(-3, 4) for _ in range(cnt)]
+    rs = [rng.randrange(par.n) for _ in range(cnt)]
+    exp = []
+    for x, r in zip(xs, rs):
+        c = O.encrypt_with_randomness(pk, abs(x), r).C
+        exp.append(O.g1_neg(c, par.p) if x < 0 else c)
+    got = e.encrypt_batch(np.array(xs, dtype=np.int64), e.scalars_be(rs))
+    assert got.tobytes() == b"".join(O.g1_to_bytes(c, par) for c in exp)
+    # pairings of consecutive ciphertexts
+    a, b = got[: (cnt - 1) * e.elem_bytes], got[e.elem_bytes:]
+    pe = [O.pairing(exp[i], exp[i + 1], par) for i in range(cnt - 1)]
+    assert e.pair_batch(a.copy(), b.copy()).tobytes() == b"".join(O.gt_to_bytes(v, par) for v in pe)
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+def test_properties_512_scale():
+    """keyBits=512, a few thousand elements: encrypt -> EMult -> decrypt recovers the product
+    polynomial; bilinearity e(aP, bP) = e(P,P)^(ab); commutativity of the batch product."""
+    g = load_golden(512)
+    e = engine_for(g)
+    n = int(g["n"], 16)
+    rng = random.Random(7)
+    count, d = 256, 4
+    c1 = np.array([[rng.randrange(-1, 2) for _ in range(d)] for _ in range(count)], dtype=np.int64)
+    c2 = np.array([[rng.randrange(-1, 2) for _ in range(d)] for _ in range(count)], dtype=np.int64)
+    r1 = e.scalars_be([rng.randrange(n) for _ in range(count * d)])
+    r2 = e.scalars_be([rng.randrange(n) for _ in range(count * d)])
+    E1 = e.encrypt_batch(c1.reshape(-1), r1)
+    E2 = e.encrypt_batch(c2.reshape(-1), r2)
+    prod = e.multpoly_batch(E1, d, E2, d, count)
+    assert prod.tobytes() == e.multpoly_batch(E2, d, E1, d, count).tobytes()
+    vals, st = e.decrypt_batch(prod, True)
+    assert not st.any()
+    vals = vals.reshape(count, 2 * d)
+    for u in range(count):
+        exp = np.convolve(c1[u], c2[u]).tolist() + [0]
+        assert vals[u].tolist() == exp
+    # L1 decrypt of the inputs
+    v1, s1 = e.decrypt_batch(E1, False)
+    assert not s1.any() and v1.tolist() == c1.reshape(-1).tolist()
+    # inner product: sum over units, slot-wise
+    total = e.l2_sum_reduce(prod, count, 2 * d)
+    tv, ts = e.decrypt_batch(total, True)
+    assert not ts.any()
+    assert tv.tolist() == sum(np.convolve(c1[u], c2[u]) for u in range(count)).tolist() + [0]
+
+
+def test_device_pointer_io():
+    """device-resident buffers (CUDA tensors) give the same bytes as host buffers."""
+    import torch
+    g = load_golden(128)
+    e, v = engine_for(g), g["pair"]
+    a = torch.from_numpy(buf(v["a"]).copy()).cuda()
+    b = torch.from_numpy(buf(v["b"]).copy()).cuda()
+    out = e.pair_batch(a, b)
+    assert out.is_cuda and out.cpu().numpy().tobytes() == unhex(v["out"])
+
+
+def test_mirror_api_truth_table():
+    """cmd/main.go:74-107: Add / Mult / Neg over {0, 1, -1} through the Go-named host mirror."""
+    from bgn_b200 import PublicKey, SecretKey
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    cts = {m: pk.Encrypt(m) for m in (0, 1, -1)}
+    for a in (0, 1, -1):
+        assert sk.Decrypt(pk.Neg(cts[a]), pk) == -a
+        for b in (0, 1, -1):
+            assert sk.Decrypt(pk.Add(cts[a], cts[b]), pk) == a + b
+            assert sk.Decrypt(pk.Sub(cts[a], cts[b]), pk) == a - b
+            assert sk.Decrypt(pk.Mult(cts[a], cts[b]), pk) == a * b
+            assert sk.Decrypt(pk.Add(pk.Mult(cts[a], cts[b]), cts[a]), pk) == a * b + a
+    assert sk.Decrypt(pk.MultConst(cts[1], 7), pk) == 7
+    assert sk.Decrypt(pk.MultConst(pk.makeL2(cts[-1]), 9), pk) == -9
+
+
+def test_mirror_api_poly():
+    """poly_test.go:92-189 with the reference's constants (POLYBASE=3, FPSCALEBASE=3, FPPREC=0.0001)."""
+    from bgn_b200 import PublicKey, SecretKey
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    f1 = lambda x: "%.1f" % x  # noqa: E731
+    c = pk.EncryptPoly(pk.NewPolyPlaintext(9.123))
+    assert f1(sk.DecryptPoly(c, pk).PolyEval()) == "9.1"
+    a, b = pk.EncryptPoly(pk.NewPolyPlaintext(0.1)), pk.EncryptPoly(pk.NewPolyPlaintext(4.2))
+    assert f1(sk.DecryptPoly(pk.AddPoly(a, b), pk).PolyEval()) == "4.3"
+    a, b = pk.EncryptPoly(pk.NewPolyPlaintext(50.1)), pk.EncryptPoly(pk.NewPolyPlaintext(41.2))
+    s = pk.AddPoly(pk.MakePolyL2(a), pk.MakePolyL2(b))
+    assert s.L2 and f1(sk.DecryptPoly(s, pk).PolyEval()) == "91.3"
+    a = pk.EncryptPoly(pk.NewPolyPlaintext(9.13))
+    assert f1(sk.DecryptPoly(pk.MultConstPoly(a, 4.12), pk).PolyEval()) == f1(9.13 * 4.12)
+    assert f1(sk.DecryptPoly(pk.MultConstPoly(pk.MakePolyL2(a), 4.12), pk).PolyEval()) == f1(9.13 * 4.12)
+    a, b = pk.EncryptPoly(pk.NewPolyPlaintext(1.1)), pk.EncryptPoly(pk.NewPolyPlaintext(40.2))
+    assert f1(sk.DecryptPoly(pk.MultPoly(a, b), pk).PolyEval()) == f1(1.1 * 40.2)
+    assert f1(sk.DecryptPoly(pk.SubPoly(b, a), pk).PolyEval()) == f1(40.2 - 1.1)
