@@ -107,7 +107,7 @@ BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N,
 // ------------------------------------------------------------ G1 kernels
 // Fixed-base window tables: entry (win, d) = d * 2^(8 win) * Base, affine
 // Montgomery, AoS: tab[(win*255 + d-1) * 2L + {0..L-1: x, L..2L-1: y}].
-// C = x*P + r*Q  (EncryptWithRandomness, bgn.go:340-353), Jacobian out.
+// C = x*P + r*Q  (EncryptWithRandomness, bgn.go:340-353), x < 0: C = -(|x|*P + r*Q); Jacobian out.
 template <int L>
 BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
   if (e >= a.count) return;
@@ -132,9 +132,11 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
     if (d) {
       const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
-      G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), neg);
+      G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false);
     }
   }
+  // negative plaintext: -(|x|*P + r*Q), the Sub(encryptZero(), Encrypt(|c|)) of poly.go:17-21
+  if (neg) F<L>::neg(vY, vY);
   st<L>(mkv(a.X + e, (int)a.N), X);
   st<L>(mkv(a.Y + e, (int)a.N), Y);
   st<L>(mkv(a.Z + e, (int)a.N), Z);

@@ -74,7 +74,8 @@ int bgn_ctx_info(const bgn_ctx* ctx, int* limbs, int* coord_bytes, int* scalar_b
 int bgn_ctx_set_secret(bgn_ctx* ctx, const uint8_t* q1_be, size_t q1_len, uint64_t msg_space, uint32_t baby_steps);
 
 /* EncryptWithRandomness over a batch (bgn.go:340-353; the negative branch of
- * EncryptPoly, poly.go:17-21, is x < 0):  out[i] = x[i]*P + r[i]*Q.
+ * EncryptPoly, poly.go:17-21, is x < 0):  out[i] = x[i]*P + r[i]*Q for x >= 0 and
+ * -(|x[i]|*P + r[i]*Q) for x < 0 (Sub(encryptZero(), Encrypt(|x|)), as EncryptPoly does).
  * r_be: count scalars of scalar_bytes each, or NULL for EncryptDeterministic
  * (bgn.go:325-331).  out: count G1 elements. */
 int bgn_encrypt_batch(bgn_ctx* ctx, const int64_t* x, const uint8_t* r_be, size_t count, uint8_t* out);
