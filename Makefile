@@ -2,7 +2,9 @@
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
-LIMBS     := 3 5 9 17 33
+# limb counts to instantiate; `make LIMBS=17` is a quick single-size developer build
+LIMBS     ?= 3 5 9 17 33
+HAVE      := $(foreach l,$(LIMBS),-DBGN_HAVE_L$(l))
 SRC       := bgn_b200/csrc
 OBJ       := build
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h) include/bgn_b200.h
@@ -21,7 +23,7 @@ $(OBJ)/inst_b_%.o: $(SRC)/inst_b.cu $(HDRS)
 
 $(OBJ)/api.o: $(SRC)/api.cu $(HDRS)
 	@mkdir -p $(OBJ)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/api.log || (tail -30 $(OBJ)/api.log; false)
+	$(NVCC) $(NVFLAGS) $(HAVE) -c $< -o $@ 2> $(OBJ)/api.log || (tail -30 $(OBJ)/api.log; false)
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)

@@ -382,13 +382,11 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   if (!count) return;
   size_t per_thread = (size_t)BGN_MILLER_NSLOT * c->L * 4 + 2;
   int TS = dE;
-  size_t budget2 = 113000, budget1 = 227 * 1024 - 1024;
-  int nt_max = (int)std::min<size_t>(144, budget2 / per_thread);
+  const size_t smem_max = 227 * 1024 - 64;
+  // one block of up to 256 threads; as many whole teams as shared memory holds.  For small fields
+  // several blocks share an SM, for L = 17 one block of 7 warps fills it.
+  int nt_max = (int)std::min<size_t>(256, smem_max / per_thread);
   int teams = nt_max / TS;
-  if (teams == 0) {
-    nt_max = (int)std::min<size_t>(160, budget1 / per_thread);
-    teams = nt_max / TS;
-  }
   if (teams == 0) throw ArgErr{"polynomial has too many coefficients for one thread block"};
   if (TS == 1) teams = std::min(teams, 128);
   int nt = teams * TS;
@@ -512,9 +510,26 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->A = bgn_opsA_##n();   \
     c->Bo = bgn_opsB_##n();  \
     break;
-      BGN_PICK(3) BGN_PICK(5) BGN_PICK(9) BGN_PICK(17) BGN_PICK(33)
+#ifdef BGN_HAVE_L3
+      BGN_PICK(3)
+#endif
+#ifdef BGN_HAVE_L5
+      BGN_PICK(5)
+#endif
+#ifdef BGN_HAVE_L9
+      BGN_PICK(9)
+#endif
+#ifdef BGN_HAVE_L17
+      BGN_PICK(17)
+#endif
+#ifdef BGN_HAVE_L33
+      BGN_PICK(33)
+#endif
 #undef BGN_PICK
+      default:
+        break;
     }
+    if (!c->A || !c->Bo) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
     c->B = (pbits + 7) / 8;
     Big p(p0.begin(), p0.begin() + L);
     Big n = big_from_be(prm->n_be, prm->n_len, BGN_MAXL);

@@ -5,193 +5,168 @@
 // Replaces libpbc curve.c (element_mul / element_double / element_pow_mpz on
 // G1, affine with one inversion per operation) as reached from bgn.go:344-350,
 // 482, 419, 258 -- redesigned inversion-free; affine output is recovered by a
-// batched inversion (kernels.cu: k_normalize).  Line convention (evaluated at
-// the distorted point phi(B) = (-xB, i*yB), F_p factors dropped because the
-// final exponentiation kills them):
+// batched inversion (kernels.cuh: normalize_body).  Everything is three-address
+// code over element handles (field.cuh): the only arithmetic instantiated is
+// F<L>::mul / add / sub.  Line convention (evaluated at the distorted point
+// phi(B) = (-xB, i*yB), F_p factors dropped because the final exponentiation
+// kills them):
 //     l(B) = (cR + aR*xB) + (bI*yB) i
 #pragma once
 #include "field.cuh"
 
 template <int L>
 struct G {
-  typedef Fp<L> P;
   typedef F<L> FF;
 
-  // V <- 2V and tangent line at the old V.  12 products.
-  template <bool LINE>
-  BGN_DEV static void dbl_impl(V X, V Y, V Z, V cR, V aR, V bI) {
-    uint32_t x[L], y[L], z[L], xx[L], yy[L], zz[L], m[L], s[L], t[L], u[L];
-    ld<L>(x, X);
-    ld<L>(y, Y);
-    ld<L>(z, Z);
-    P::sqr(xx, x);
-    P::sqr(yy, y);
-    P::sqr(zz, z);
-    P::sqr(t, zz);
-    P::add(m, xx, xx);
-    P::add(m, m, xx);
-    P::add(m, m, t);  // M = 3XX + ZZ^2   (curve a = 1)
-    P::mul(t, x, yy);
-    P::add(s, t, t);
-    P::add(s, s, s);  // S = 4 X YY
-    P::mul(t, y, z);
-    P::add(u, t, t);  // Z3 = 2YZ
-    st<L>(Z, u);
-    if (LINE) {
-      P::mul(t, u, zz);
-      st<L>(bI, t);  // bI = Z3*ZZ
-      P::mul(t, m, zz);
-      st<L>(aR, t);  // aR = M*ZZ
-      P::mul(t, m, x);
-      P::add(u, yy, yy);
-      P::sub(t, t, u);
-      st<L>(cR, t);  // cR = M*X - 2YY
-    }
-    P::sqr(t, m);
-    P::sub(t, t, s);
-    P::sub(t, t, s);  // X3 = M^2 - 2S
-    st<L>(X, t);
-    P::sub(s, s, t);
-    P::mul(u, m, s);  // M (S - X3)
-    P::sqr(t, yy);
-    P::add(t, t, t);
-    P::add(t, t, t);
-    P::add(t, t, t);  // 8 YYYY
-    P::sub(u, u, t);
-    st<L>(Y, u);
+  // V <- 2V and the tangent line at the old V.  12 products.
+  // cR, aR, bI receive the line and double as scratch; t0..t2 scratch.
+  BGN_DEV static void dbl_line(V X, V Y, V Z, V cR, V aR, V bI, V t0, V t1, V t2) {
+    FF::sqr(t0, X);       // XX
+    FF::sqr(t1, Y);       // YY
+    FF::sqr(t2, Z);       // ZZ
+    FF::sqr(cR, t2);      // ZZ^2
+    FF::add(aR, t0, t0);
+    FF::add(t0, aR, t0);
+    FF::add(t0, t0, cR);  // M = 3XX + ZZ^2   (curve a = 1)
+    FF::mul(Z, Y, Z);
+    FF::add(Z, Z, Z);     // Z3 = 2YZ
+    FF::mul(bI, Z, t2);   // bI = Z3*ZZ
+    FF::mul(aR, t0, t2);  // aR = M*ZZ
+    FF::mul(cR, t0, X);
+    FF::sub(cR, cR, t1);
+    FF::sub(cR, cR, t1);  // cR = M*X - 2YY
+    FF::mul(t2, X, t1);
+    FF::add(t2, t2, t2);
+    FF::add(t2, t2, t2);  // S = 4 X YY
+    FF::sqr(X, t0);
+    FF::sub(X, X, t2);
+    FF::sub(X, X, t2);    // X3 = M^2 - 2S
+    FF::sub(t2, t2, X);
+    FF::mul(Y, t0, t2);   // M (S - X3)
+    FF::sqr(t1, t1);
+    FF::add(t1, t1, t1);
+    FF::add(t1, t1, t1);
+    FF::add(t1, t1, t1);  // 8 YYYY
+    FF::sub(Y, Y, t1);
   }
-  BGN_DEVNI static void dbl_line(V X, V Y, V Z, V cR, V aR, V bI) { dbl_impl<true>(X, Y, Z, cR, aR, bI); }
-  BGN_DEVNI static void dbl(V X, V Y, V Z) { dbl_impl<false>(X, Y, Z, X, X, X); }
 
-  // V <- V + (xA, sgn*yA) (mixed) and the chord through them.  13 products.
+  // V <- 2V (no line).  9 products; t0..t3 scratch.
+  BGN_DEV static void dbl(V X, V Y, V Z, V t0, V t1, V t2, V t3) {
+    FF::sqr(t0, X);
+    FF::sqr(t1, Y);
+    FF::sqr(t2, Z);
+    FF::sqr(t2, t2);
+    FF::add(t3, t0, t0);
+    FF::add(t0, t3, t0);
+    FF::add(t0, t0, t2);  // M
+    FF::mul(Z, Y, Z);
+    FF::add(Z, Z, Z);
+    FF::mul(t2, X, t1);
+    FF::add(t2, t2, t2);
+    FF::add(t2, t2, t2);  // S
+    FF::sqr(X, t0);
+    FF::sub(X, X, t2);
+    FF::sub(X, X, t2);
+    FF::sub(t2, t2, X);
+    FF::mul(Y, t0, t2);
+    FF::sqr(t1, t1);
+    FF::add(t1, t1, t1);
+    FF::add(t1, t1, t1);
+    FF::add(t1, t1, t1);
+    FF::sub(Y, Y, t1);
+  }
+
+  // V <- V + (xA, yA) (mixed) and the chord through them.  13 products.
   // No special cases: the Miller loop never meets them for points of order n
   // except at the very last step, which the schedule drops (vertical line).
-  BGN_DEVNI static void madd_line(V X, V Y, V Z, V xA, V yA, bool negate, V cR, V aR, V bI) {
-    uint32_t x[L], y[L], z[L], ax[L], ay[L], zz[L], h[L], r[L], t[L], u[L], i4[L], j[L], vv[L];
-    ld<L>(x, X);
-    ld<L>(y, Y);
-    ld<L>(z, Z);
-    ld<L>(ax, xA);
-    ld<L>(t, yA);
-    if (negate) {
-      BGN_UNROLL
-      for (int k = 0; k < L; k++) u[k] = 0;
-      P::sub(ay, u, t);
-    } else {
-      BGN_UNROLL
-      for (int k = 0; k < L; k++) ay[k] = t[k];
-    }
-    P::sqr(zz, z);
-    P::mul(t, ax, zz);  // U2
-    P::sub(h, t, x);    // H
-    P::mul(t, z, zz);
-    P::mul(u, ay, t);  // S2
-    P::sub(r, u, y);
-    P::add(r, r, r);  // r = 2(S2 - Y)
-    P::mul(t, z, h);
-    P::add(t, t, t);  // Z3 = 2 Z H
-    st<L>(Z, t);
-    st<L>(bI, t);  // bI = Z3
-    st<L>(aR, r);  // aR = r
-    P::mul(u, ay, t);
-    P::mul(t, r, ax);
-    P::sub(t, t, u);
-    st<L>(cR, t);  // cR = r*xA - yA*Z3
-    P::sqr(t, h);
-    P::add(t, t, t);
-    P::add(i4, t, t);    // I = 4 HH
-    P::mul(j, h, i4);    // J
-    P::mul(vv, x, i4);   // V
-    P::sqr(t, r);
-    P::sub(t, t, j);
-    P::sub(t, t, vv);
-    P::sub(t, t, vv);  // X3
-    st<L>(X, t);
-    P::sub(u, vv, t);
-    P::mul(t, r, u);
-    P::mul(u, y, j);
-    P::add(u, u, u);
-    P::sub(t, t, u);  // Y3 = r(V - X3) - 2 Y J
-    st<L>(Y, t);
+  // The caller passes yA already negated for a subtraction step.
+  BGN_DEV static void madd_line(V X, V Y, V Z, V xA, V yA, V cR, V aR, V bI, V t0, V t1, V t2) {
+    FF::sqr(t0, Z);        // ZZ
+    FF::mul(t1, xA, t0);
+    FF::sub(t1, t1, X);    // H = U2 - X
+    FF::mul(t0, Z, t0);
+    FF::mul(t0, yA, t0);   // S2
+    FF::sub(t0, t0, Y);
+    FF::add(aR, t0, t0);   // aR = r = 2(S2 - Y)
+    FF::mul(Z, Z, t1);
+    FF::add(Z, Z, Z);      // Z3 = 2 Z H
+    FF::copy(bI, Z);       // bI = Z3
+    FF::mul(cR, aR, xA);
+    FF::mul(t0, yA, Z);
+    FF::sub(cR, cR, t0);   // cR = r*xA - yA*Z3
+    FF::sqr(t0, t1);
+    FF::add(t0, t0, t0);
+    FF::add(t0, t0, t0);   // I = 4 HH
+    FF::mul(t2, t1, t0);   // J = H*I
+    FF::mul(t0, X, t0);    // V = X*I
+    FF::sqr(X, aR);
+    FF::sub(X, X, t2);
+    FF::sub(X, X, t0);
+    FF::sub(X, X, t0);     // X3 = r^2 - J - 2V
+    FF::sub(t0, t0, X);
+    FF::mul(t0, aR, t0);   // r (V - X3)
+    FF::mul(t2, Y, t2);
+    FF::add(t2, t2, t2);   // 2 Y J
+    FF::sub(Y, t0, t2);
   }
 
   // Complete mixed addition V <- V + (xA, sgn*yA) for scalar multiplication and
   // EAdd: handles V == O, V == A (doubling) and V == -A (-> O).  11 products on
-  // the common path.
-  BGN_DEVNI static void madd(V X, V Y, V Z, V xA, V yA, bool negate) {
-    uint32_t x[L], y[L], z[L], ax[L], ay[L], zz[L], h[L], r[L], t[L], u[L], i4[L], j[L], vv[L];
-    ld<L>(z, Z);
-    ld<L>(ax, xA);
-    ld<L>(t, yA);
+  // the common path.  t0..t4 scratch.
+  BGN_DEVNI static void madd(V X, V Y, V Z, V xA, V yA, bool negate, V t0, V t1, V t2, V t3, V t4) {
+    V ay = yA;
     if (negate) {
-      BGN_UNROLL
-      for (int k = 0; k < L; k++) u[k] = 0;
-      P::sub(ay, u, t);
-    } else {
-      BGN_UNROLL
-      for (int k = 0; k < L; k++) ay[k] = t[k];
+      FF::neg(t4, yA);
+      ay = t4;
     }
-    P::canon(t, z);
-    if (P::is_zero_raw(t)) {  // O + A
-      st<L>(X, ax);
-      st<L>(Y, ay);
+    if (FF::is_zero(Z)) {  // O + A
+      FF::copy(X, xA);
+      FF::copy(Y, ay);
       FF::set_one(Z);
       return;
     }
-    ld<L>(x, X);
-    ld<L>(y, Y);
-    P::sqr(zz, z);
-    P::mul(t, ax, zz);
-    P::sub(h, t, x);
-    P::mul(t, z, zz);
-    P::mul(u, ay, t);
-    P::sub(r, u, y);
-    P::canon(t, h);
-    if (P::is_zero_raw(t)) {
-      P::canon(t, r);
-      if (P::is_zero_raw(t)) {  // same point: double the affine one
-        st<L>(X, ax);
-        st<L>(Y, ay);
+    FF::sqr(t0, Z);       // ZZ
+    FF::mul(t1, xA, t0);
+    FF::sub(t1, t1, X);   // H
+    FF::mul(t0, Z, t0);
+    FF::mul(t0, ay, t0);
+    FF::sub(t0, t0, Y);   // S2 - Y
+    if (FF::is_zero(t1)) {
+      if (FF::is_zero(t0)) {  // same point: double the affine one
+        FF::copy(X, xA);
+        FF::copy(Y, ay);
         FF::set_one(Z);
-        dbl(X, Y, Z);
+        dbl(X, Y, Z, t0, t1, t2, t3);
       } else {  // inverse points
         FF::set_zero(Z);
       }
       return;
     }
-    P::add(r, r, r);
-    P::mul(t, z, h);
-    P::add(t, t, t);
-    st<L>(Z, t);
-    P::sqr(t, h);
-    P::add(t, t, t);
-    P::add(i4, t, t);
-    P::mul(j, h, i4);
-    P::mul(vv, x, i4);
-    P::sqr(t, r);
-    P::sub(t, t, j);
-    P::sub(t, t, vv);
-    P::sub(t, t, vv);
-    st<L>(X, t);
-    P::sub(u, vv, t);
-    P::mul(t, r, u);
-    P::mul(u, y, j);
-    P::add(u, u, u);
-    P::sub(t, t, u);
-    st<L>(Y, t);
+    FF::add(t3, t0, t0);  // r
+    FF::mul(Z, Z, t1);
+    FF::add(Z, Z, Z);     // Z3
+    FF::sqr(t0, t1);
+    FF::add(t0, t0, t0);
+    FF::add(t0, t0, t0);  // I
+    FF::mul(t2, t1, t0);  // J
+    FF::mul(t0, X, t0);   // V
+    FF::sqr(X, t3);
+    FF::sub(X, X, t2);
+    FF::sub(X, X, t0);
+    FF::sub(X, X, t0);    // X3
+    FF::sub(t0, t0, X);
+    FF::mul(t0, t3, t0);
+    FF::mul(t2, Y, t2);
+    FF::add(t2, t2, t2);
+    FF::sub(Y, t0, t2);
   }
 
   // y^2 == x^3 + x ?  (pbc curve_from_bytes falls back to O otherwise)
-  BGN_DEVNI static bool on_curve(V xA, V yA) {
-    uint32_t x[L], y[L], t[L], u[L];
-    ld<L>(x, xA);
-    ld<L>(y, yA);
-    P::sqr(t, x);
-    P::mul(u, t, x);
-    P::add(u, u, x);
-    P::sqr(t, y);
-    P::sub(t, t, u);
-    P::canon(u, t);
-    return P::is_zero_raw(u);
+  BGN_DEVNI static bool on_curve(V xA, V yA, V t0, V t1) {
+    FF::sqr(t0, xA);
+    FF::mul(t0, t0, xA);
+    FF::add(t0, t0, xA);
+    FF::sqr(t1, yA);
+    return FF::equal(t0, t1);
   }
 };

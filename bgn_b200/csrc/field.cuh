@@ -3,9 +3,16 @@
 // An element handle V = {pointer to limb 0, stride in words}.  The same code
 // addresses (i) the limb-major SoA arrays in HBM ([limb][batch], stride =
 // batch), (ii) per-thread state slots in shared memory ([slot][limb][thread],
-// stride = blockDim) and (iii) thread-local scratch (stride 1).  The heavy ops
-// are __noinline__ so a kernel is a short straight-line program of calls and
-// the register allocator only ever sees one or a few Montgomery products.
+// stride = blockDim) and (iii) thread-local scratch (stride 1).
+//
+// Code-size rule (measured, profiles/r01_miller_v1.md): with the Montgomery
+// product inlined at every use the Miller kernel was 625 KB of SASS and spent
+// most of its issue slots waiting for instruction fetch.  So there is exactly
+// ONE copy of the product per translation unit -- F<L>::mul, __noinline__,
+// operands and result in memory -- and everything above it (F_p^2, curve,
+// pairing) is written as straight-line "three-address code" over handles with
+// caller-provided temporaries.  The whole hot loop is then ~20 KB of SASS and
+// stays in the instruction cache; register pressure is that of one product.
 //
 // Replaces libpbc montfp.c / fieldquadratic.c behaviour (element_mul, _add,
 // _sub, _invert, _square on F_p and F_p[i]); see SURVEY.md 8(a) row a8.
@@ -46,11 +53,19 @@ BGN_DEV V2 mkv2(V re, V im) {
   return v;
 }
 
+// thread-local scratch element (lives in local memory because its address is taken)
+template <int L>
+struct Loc {
+  uint32_t w[L];
+  BGN_DEV V v() { return mkv(w, 1); }
+};
+
 template <int L>
 struct F {
   typedef Fp<L> P;
 
-  // ---------------- F_p ----------------
+  // ---------------- F_p primitives (the only places that touch limbs) ----------------
+  // r = a*b (Montgomery).  r may alias a and/or b.
   BGN_DEVNI static void mul(V r, V a, V b) {
     uint32_t x[L], y[L], z[L];
     ld<L>(x, a);
@@ -58,12 +73,7 @@ struct F {
     P::mul(z, x, y);
     st<L>(r, z);
   }
-  BGN_DEVNI static void sqr(V r, V a) {
-    uint32_t x[L], z[L];
-    ld<L>(x, a);
-    P::sqr(z, x);
-    st<L>(r, z);
-  }
+  BGN_DEV static void sqr(V r, V a) { mul(r, a, a); }
   BGN_DEVNI static void add(V r, V a, V b) {
     uint32_t x[L], y[L], z[L];
     ld<L>(x, a);
@@ -114,6 +124,15 @@ struct F {
     P::canon(w, y);
     return P::eq_raw(u, w);
   }
+  BGN_DEVNI static bool is_one(V a) {
+    uint32_t x[L], y[L], o[L], w[L];
+    ld<L>(x, a);
+    P::canon(y, x);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) o[j] = c_fc.one[j];
+    P::canon(w, o);
+    return P::eq_raw(y, w);
+  }
   // r = canonical [0,p) of a (stays in Montgomery form)
   BGN_DEVNI static void canon(V r, V a) {
     uint32_t x[L], y[L];
@@ -122,97 +141,53 @@ struct F {
     st<L>(r, y);
   }
   // standard integer -> Montgomery form (a < 2^(32L), result lazy)
-  BGN_DEVNI static void to_mont(V r, V a) {
-    uint32_t x[L], y[L], z[L];
-    ld<L>(x, a);
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) y[j] = c_fc.r2[j];
-    P::mul(z, x, y);
-    st<L>(r, z);
-  }
+  BGN_DEV static void to_mont(V r, V a) { mul(r, a, mkvc(c_fc_r2(), 1)); }
   // Montgomery form -> canonical standard integer in [0,p)
   BGN_DEVNI static void from_mont(V r, V a) {
-    uint32_t x[L], y[L], z[L];
-    ld<L>(x, a);
+    uint32_t y[L];
     BGN_UNROLL
     for (int j = 0; j < L; j++) y[j] = 0;
     y[0] = 1;
-    P::mul(z, x, y);
-    P::canon(x, z);
-    st<L>(r, x);
+    mul(r, a, mkv(y, 1));
+    canon(r, r);
+  }
+  BGN_DEV static const uint32_t* c_fc_r2() { return c_fc.r2; }
+
+  // r = a^(p-2) (Fermat inverse); 0 -> 0.  Left-to-right binary, uniform control flow across
+  // threads (the exponent is a key constant).  t must not alias r or a; r may alias a.
+  BGN_DEVNI static void inv(V r, V a, V t) {
+    copy(t, a);
+    int top = 32 * L - 1;
+    while (top > 0 && !((c_fc.p[top >> 5] >> (top & 31)) & 1)) top--;
+    // exponent e = p - 2: p = 3 (mod 4), so subtracting 2 only touches the low limb (no borrow)
+    copy(r, t);  // consumes the top bit of e
+    for (int bit = top - 1; bit >= 0; bit--) {
+      uint32_t limb = c_fc.p[bit >> 5];
+      if ((bit >> 5) == 0) limb -= 2;
+      sqr(r, r);
+      if ((limb >> (bit & 31)) & 1) mul(r, r, t);
+    }
   }
 
-  // r = a^(p-2) (Fermat inverse); 0 -> 0.  4-bit fixed window, uniform control flow.
-  BGN_DEVNI static void inv(V r, V a) {
-    uint32_t tab[15][L];  // a^1 .. a^15
-    uint32_t acc[L], t[L];
-    ld<L>(t, a);
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) tab[0][j] = t[j];
-    for (int i = 1; i < 15; i++) {
-      uint32_t u[L], w[L];
-      for (int j = 0; j < L; j++) u[j] = tab[i - 1][j];
-      P::mul(w, u, t);
-      for (int j = 0; j < L; j++) tab[i][j] = w[j];
-    }
-    // exponent e = p - 2 (p = 3 mod 4, so no borrow out of limb 0)
-    bool started = false;
-    for (int w = 8 * L - 1; w >= 0; w--) {
-      uint32_t limb = c_fc.p[w >> 3];
-      if ((w >> 3) == 0) limb -= 2;
-      uint32_t d = (limb >> ((w & 7) * 4)) & 15u;
-      if (started) {
-        P::sqr(t, acc);
-        P::sqr(acc, t);
-        P::sqr(t, acc);
-        P::sqr(acc, t);
-      }
-      if (d) {
-        uint32_t u[L];
-        for (int j = 0; j < L; j++) u[j] = tab[d - 1][j];
-        if (started) {
-          P::mul(t, acc, u);
-          for (int j = 0; j < L; j++) acc[j] = t[j];
-        } else {
-          for (int j = 0; j < L; j++) acc[j] = u[j];
-          started = true;
-        }
-      }
-    }
-    st<L>(r, acc);
+  // ---------------- F_p^2 = F_p[i]/(i^2+1), three-address code ----------------
+  // r = a*b (Karatsuba, 3 products).  r may alias a or b; t0..t2 are scratch.
+  BGN_DEV static void mul2(V2 r, V2 a, V2 b, V t0, V t1, V t2) {
+    mul(t0, a.re, b.re);
+    mul(t1, a.im, b.im);
+    add(t2, a.re, a.im);
+    add(r.im, b.re, b.im);
+    mul(r.im, t2, r.im);
+    sub(r.re, t0, t1);
+    sub(r.im, r.im, t0);
+    sub(r.im, r.im, t1);
   }
-
-  // ---------------- F_p^2 = F_p[i]/(i^2+1) ----------------
-  // r = a*b, Karatsuba, 3 products; operands are read before r is written.
-  BGN_DEVNI static void mul2(V2 r, V2 a, V2 b) {
-    uint32_t a0[L], a1[L], b0[L], b1[L], t0[L], t1[L], t2[L], s[L], u[L];
-    ld<L>(a0, a.re);
-    ld<L>(a1, a.im);
-    ld<L>(b0, b.re);
-    ld<L>(b1, b.im);
-    P::mul(t0, a0, b0);
-    P::mul(t1, a1, b1);
-    P::add(s, a0, a1);
-    P::add(u, b0, b1);
-    P::mul(t2, s, u);
-    P::sub(s, t0, t1);
-    st<L>(r.re, s);
-    P::sub(u, t2, t0);
-    P::sub(s, u, t1);
-    st<L>(r.im, s);
-  }
-  // r = a^2: (a0+a1)(a0-a1) + 2 a0 a1 i, 2 products
-  BGN_DEVNI static void sqr2(V2 r, V2 a) {
-    uint32_t a0[L], a1[L], s[L], d[L], t[L];
-    ld<L>(a0, a.re);
-    ld<L>(a1, a.im);
-    P::add(s, a0, a1);
-    P::sub(d, a0, a1);
-    P::mul(t, s, d);
-    st<L>(r.re, t);
-    P::mul(t, a0, a1);
-    P::add(s, t, t);
-    st<L>(r.im, s);
+  // r = a^2: (a0+a1)(a0-a1) + 2 a0 a1 i, 2 products.  r may alias a.
+  BGN_DEV static void sqr2(V2 r, V2 a, V t0, V t1) {
+    add(t0, a.re, a.im);
+    sub(t1, a.re, a.im);
+    mul(r.im, a.re, a.im);
+    add(r.im, r.im, r.im);
+    mul(r.re, t0, t1);
   }
   BGN_DEV static void conj2(V2 r, V2 a) {
     copy(r.re, a.re);
@@ -227,29 +202,19 @@ struct F {
     set_zero(r.im);
   }
 
-  // Miller-loop term: f <- f * ((cR + aR*xB) + (bI*yB) i); 5 products, all
-  // intermediates in registers (eval 2 + f*line 3).
-  BGN_DEVNI static void line_mul(V2 f, V cR, V aR, V bI, V xB, V yB) {
-    uint32_t l0[L], l1[L], x[L], y[L], t0[L], t1[L], t2[L];
-    ld<L>(x, aR);
-    ld<L>(y, xB);
-    P::mul(t0, x, y);
-    ld<L>(x, cR);
-    P::add(l0, x, t0);
-    ld<L>(x, bI);
-    ld<L>(y, yB);
-    P::mul(l1, x, y);
-    ld<L>(x, f.re);
-    ld<L>(y, f.im);
-    P::mul(t0, x, l0);
-    P::mul(t1, y, l1);
-    P::add(t2, x, y);
-    P::add(x, l0, l1);
-    P::mul(y, t2, x);
-    P::sub(x, t0, t1);
-    st<L>(f.re, x);
-    P::sub(x, y, t0);
-    P::sub(y, x, t1);
-    st<L>(f.im, y);
+  // Miller-loop term: f <- f * ((cR + aR*xB) + (bI*yB) i); 5 products
+  // (eval 2 + f*line 3).  t0..t3 scratch.
+  BGN_DEV static void line_mul(V2 f, V cR, V aR, V bI, V xB, V yB, V t0, V t1, V t2, V t3) {
+    mul(t0, aR, xB);
+    add(t0, t0, cR);  // l0
+    mul(t1, bI, yB);  // l1
+    mul(t2, f.re, t0);
+    mul(t3, f.im, t1);
+    add(f.re, f.re, f.im);
+    add(t0, t0, t1);
+    mul(f.im, f.re, t0);
+    sub(f.re, t2, t3);
+    sub(f.im, f.im, t2);
+    sub(f.im, f.im, t3);
   }
 };

@@ -62,7 +62,10 @@ BGN_DEV void g1_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_t
   F<L>::to_mont(vx, mkv(a, 1));
   F<L>::to_mont(vy, mkv(b, 1));
   bool isinf = (o == 0);
-  if (!isinf) isinf = !G<L>::on_curve(vx, vy);
+  if (!isinf) {
+    Loc<L> t0, t1;
+    isinf = !G<L>::on_curve(vx, vy, t0.v(), t1.v());
+  }
   inf[e] = isinf ? 1 : 0;
 }
 
@@ -111,17 +114,18 @@ BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N,
 template <int L>
 BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
   if (e >= a.count) return;
-  uint32_t X[L], Y[L], Z[L];
-  V vX = mkv(X, 1), vY = mkv(Y, 1), vZ = mkv(Z, 1);
-  BGN_UNROLL
-  for (int j = 0; j < L; j++) X[j] = Y[j] = Z[j] = 0;
+  Loc<L> X, Y, Z, t0, t1, t2, t3, t4;
+  V vX = X.v(), vY = Y.v(), vZ = Z.v();
+  F<L>::set_zero(vX);
+  F<L>::set_zero(vY);
+  F<L>::set_zero(vZ);
   if (a.r_be) {
     const uint8_t* r = a.r_be + e * a.rbytes;
     for (int win = 0; win < a.rbytes; win++) {
       uint32_t d = r[a.rbytes - 1 - win];
       if (d) {
         const uint32_t* ent = a.tabQ + ((size_t)win * 255 + (d - 1)) * 2 * L;
-        G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false);
+        G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
       }
     }
   }
@@ -132,14 +136,14 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
     if (d) {
       const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
-      G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false);
+      G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
     }
   }
   // negative plaintext: -(|x|*P + r*Q), the Sub(encryptZero(), Encrypt(|c|)) of poly.go:17-21
   if (neg) F<L>::neg(vY, vY);
-  st<L>(mkv(a.X + e, (int)a.N), X);
-  st<L>(mkv(a.Y + e, (int)a.N), Y);
-  st<L>(mkv(a.Z + e, (int)a.N), Z);
+  F<L>::copy(mkv(a.X + e, (int)a.N), vX);
+  F<L>::copy(mkv(a.Y + e, (int)a.N), vY);
+  F<L>::copy(mkv(a.Z + e, (int)a.N), vZ);
 }
 
 // Jacobian -> affine with one inversion per thread (Montgomery's trick over
@@ -147,46 +151,33 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
 // so the same kernel fills SoA arrays and AoS tables.
 template <int L>
 BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
-  typedef Fp<L> P;
+  typedef F<L> FF;
   if (g >= (size_t)a.G || g >= a.count) return;
-  uint32_t acc[L], z[L], t[L];
-  BGN_UNROLL
-  for (int j = 0; j < L; j++) acc[j] = c_fc.one[j];
+  Loc<L> acc, zi, zz, t;
+  FF::set_one(acc.v());
   for (size_t e = g; e < a.count; e += a.G) {
-    ld<L>(z, mkvc(a.Z + e, (int)a.N));
-    P::canon(t, z);
-    if (P::is_zero_raw(t)) continue;
-    st<L>(mkv(a.scratch + e, (int)a.N), acc);
-    P::mul(t, acc, z);
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) acc[j] = t[j];
+    V z = mkvc(a.Z + e, (int)a.N);
+    if (FF::is_zero(z)) continue;
+    FF::copy(mkv(a.scratch + e, (int)a.N), acc.v());
+    FF::mul(acc.v(), acc.v(), z);
   }
-  F<L>::inv(mkv(acc, 1), mkv(acc, 1));
+  FF::inv(acc.v(), acc.v(), t.v());
   size_t last = ((a.count - 1 - g) / a.G) * a.G + g;  // largest e = g (mod G) below count
   for (size_t e = last;; e -= a.G) {
-    ld<L>(z, mkvc(a.Z + e, (int)a.N));
-    P::canon(t, z);
-    bool isinf = P::is_zero_raw(t);
+    V z = mkvc(a.Z + e, (int)a.N);
+    bool isinf = FF::is_zero(z);
     V ox = mkv(a.ox + e * a.o_estride, (int)a.o_lstride), oy = mkv(a.oy + e * a.o_estride, (int)a.o_lstride);
     if (a.inf) a.inf[e] = isinf ? 1 : 0;
     if (isinf) {
-      F<L>::set_zero(ox);
-      F<L>::set_zero(oy);
+      FF::set_zero(ox);
+      FF::set_zero(oy);
     } else {
-      uint32_t zi[L], zz[L], u[L];
-      ld<L>(t, mkvc(a.scratch + e, (int)a.N));
-      P::mul(zi, acc, t);  // 1/Z_e
-      P::mul(t, acc, z);   // drop Z_e from the running inverse
-      BGN_UNROLL
-      for (int j = 0; j < L; j++) acc[j] = t[j];
-      P::sqr(zz, zi);
-      ld<L>(u, mkvc(a.X + e, (int)a.N));
-      P::mul(t, u, zz);
-      st<L>(ox, t);
-      P::mul(u, zz, zi);
-      ld<L>(zz, mkvc(a.Y + e, (int)a.N));
-      P::mul(t, zz, u);
-      st<L>(oy, t);
+      FF::mul(zi.v(), acc.v(), mkvc(a.scratch + e, (int)a.N));  // 1/Z_e
+      FF::mul(acc.v(), acc.v(), z);                              // drop Z_e from the running inverse
+      FF::sqr(zz.v(), zi.v());
+      FF::mul(ox, mkvc(a.X + e, (int)a.N), zz.v());
+      FF::mul(zz.v(), zz.v(), zi.v());
+      FF::mul(oy, mkvc(a.Y + e, (int)a.N), zz.v());
     }
     if (e < (size_t)a.G) break;
   }
@@ -195,47 +186,57 @@ BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
 // EAdd / ESub on L1: affine + affine -> Jacobian (bgn.go:482, 419)
 template <int L>
 BGN_DEV void g1_add_body(const G1AddArgs& a, size_t e) {
+  typedef F<L> FF;
   if (e >= a.count) return;
   size_t e1 = a.bcast1 ? 0 : e;
-  uint32_t X[L], Y[L], Z[L];
-  V vX = mkv(X, 1), vY = mkv(Y, 1), vZ = mkv(Z, 1);
+  Loc<L> X, Y, Z, t0, t1, t2, t3, t4;
+  V vX = X.v(), vY = Y.v(), vZ = Z.v();
   if (a.inf1[e1]) {
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) X[j] = Y[j] = Z[j] = 0;
+    FF::set_zero(vX);
+    FF::set_zero(vY);
+    FF::set_zero(vZ);
   } else {
-    ld<L>(X, mkvc(a.x1 + e1, (int)a.N1));
-    ld<L>(Y, mkvc(a.y1 + e1, (int)a.N1));
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) Z[j] = c_fc.one[j];
+    FF::copy(vX, mkvc(a.x1 + e1, (int)a.N1));
+    FF::copy(vY, mkvc(a.y1 + e1, (int)a.N1));
+    FF::set_one(vZ);
   }
-  if (!a.inf2[e]) G<L>::madd(vX, vY, vZ, mkvc(a.x2 + e, (int)a.N2), mkvc(a.y2 + e, (int)a.N2), a.subtract != 0);
-  st<L>(mkv(a.X + e, (int)a.N), X);
-  st<L>(mkv(a.Y + e, (int)a.N), Y);
-  st<L>(mkv(a.Z + e, (int)a.N), Z);
+  if (!a.inf2[e])
+    G<L>::madd(vX, vY, vZ, mkvc(a.x2 + e, (int)a.N2), mkvc(a.y2 + e, (int)a.N2), a.subtract != 0, t0.v(), t1.v(),
+               t2.v(), t3.v(), t4.v());
+  FF::copy(mkv(a.X + e, (int)a.N), vX);
+  FF::copy(mkv(a.Y + e, (int)a.N), vY);
+  FF::copy(mkv(a.Z + e, (int)a.N), vZ);
 }
 
 // MultConst on L1: k*C, per-element big-endian scalar (bgn.go:258)
 template <int L>
 BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
+  typedef F<L> FF;
   if (e >= a.count) return;
-  uint32_t X[L], Y[L], Z[L];
-  V vX = mkv(X, 1), vY = mkv(Y, 1), vZ = mkv(Z, 1);
-  BGN_UNROLL
-  for (int j = 0; j < L; j++) X[j] = Y[j] = Z[j] = 0;
+  Loc<L> X, Y, Z, ax, ay, t0, t1, t2, t3, t4;
+  V vX = X.v(), vY = Y.v(), vZ = Z.v();
+  FF::set_zero(vX);
+  FF::set_zero(vY);
+  FF::set_zero(vZ);
   if (!a.inf[e]) {
-    V ax = mkvc(a.x + e, (int)a.Nin), ay = mkvc(a.y + e, (int)a.Nin);
+    FF::copy(ax.v(), mkvc(a.x + e, (int)a.Nin));
+    FF::copy(ay.v(), mkvc(a.y + e, (int)a.Nin));
     const uint8_t* k = a.k_be + e * a.kbytes;
+    bool started = false;  // leading zero bits: doubling O is a no-op
     for (int i = 0; i < a.kbytes; i++) {
       uint32_t byte = k[i];
       for (int bit = 7; bit >= 0; bit--) {
-        G<L>::dbl(vX, vY, vZ);
-        if ((byte >> bit) & 1) G<L>::madd(vX, vY, vZ, ax, ay, false);
+        if (started) G<L>::dbl(vX, vY, vZ, t0.v(), t1.v(), t2.v(), t3.v());
+        if ((byte >> bit) & 1) {
+          G<L>::madd(vX, vY, vZ, ax.v(), ay.v(), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
+          started = true;
+        }
       }
     }
   }
-  st<L>(mkv(a.X + e, (int)a.N), X);
-  st<L>(mkv(a.Y + e, (int)a.N), Y);
-  st<L>(mkv(a.Z + e, (int)a.N), Z);
+  FF::copy(mkv(a.X + e, (int)a.N), vX);
+  FF::copy(mkv(a.Y + e, (int)a.N), vY);
+  FF::copy(mkv(a.Z + e, (int)a.N), vZ);
 }
 
 // table construction -----------------------------------------------------
@@ -243,64 +244,74 @@ BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
 template <int L>
 BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
                             size_t N, size_t g) {
+  typedef F<L> FF;
   if (g != 0) return;
-  uint32_t x[L], y[L], z[L];
-  ld<L>(x, mkvc(bx, 1));
-  ld<L>(y, mkvc(by, 1));
-  BGN_UNROLL
-  for (int j = 0; j < L; j++) z[j] = c_fc.one[j];
-  V vX = mkv(x, 1), vY = mkv(y, 1), vZ = mkv(z, 1);
+  Loc<L> x, y, z, t0, t1, t2, t3;
+  FF::copy(x.v(), mkvc(bx, 1));
+  FF::copy(y.v(), mkvc(by, 1));
+  FF::set_one(z.v());
   for (int win = 0; win < nwin; win++) {
-    st<L>(mkv(X + win, (int)N), x);
-    st<L>(mkv(Y + win, (int)N), y);
-    st<L>(mkv(Z + win, (int)N), z);
-    for (int i = 0; i < 8; i++) G<L>::dbl(vX, vY, vZ);
+    FF::copy(mkv(X + win, (int)N), x.v());
+    FF::copy(mkv(Y + win, (int)N), y.v());
+    FF::copy(mkv(Z + win, (int)N), z.v());
+    for (int i = 0; i < 8; i++) G<L>::dbl(x.v(), y.v(), z.v(), t0.v(), t1.v(), t2.v(), t3.v());
   }
 }
 // entries (win, d), d = 1..255, by repeated addition of the affine base of the window
 template <int L>
 BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
                            uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N, size_t g) {
+  typedef F<L> FF;
   int win = (int)g;
   if (g >= (size_t)nwin) return;
-  uint32_t x[L], y[L], z[L];
-  BGN_UNROLL
-  for (int j = 0; j < L; j++) x[j] = y[j] = z[j] = 0;
-  V vX = mkv(x, 1), vY = mkv(y, 1), vZ = mkv(z, 1);
+  Loc<L> x, y, z, t0, t1, t2, t3, t4;
+  FF::set_zero(x.v());
+  FF::set_zero(y.v());
+  FF::set_zero(z.v());
   for (int d = 1; d <= 255; d++) {
-    if (!ainf[win]) G<L>::madd(vX, vY, vZ, mkvc(ax + win, (int)Nb), mkvc(ay + win, (int)Nb), false);
+    if (!ainf[win])
+      G<L>::madd(x.v(), y.v(), z.v(), mkvc(ax + win, (int)Nb), mkvc(ay + win, (int)Nb), false, t0.v(), t1.v(), t2.v(),
+                 t3.v(), t4.v());
     size_t o = (size_t)win * 255 + (d - 1);
-    st<L>(mkv(X + o, (int)N), x);
-    st<L>(mkv(Y + o, (int)N), y);
-    st<L>(mkv(Z + o, (int)N), z);
+    FF::copy(mkv(X + o, (int)N), x.v());
+    FF::copy(mkv(Y + o, (int)N), y.v());
+    FF::copy(mkv(Z + o, (int)N), z.v());
   }
 }
 
 // ------------------------------------------------------------ GT kernels
 template <int L>
 BGN_DEV void gt_mul_body(const GtBinArgs& a, size_t e) {
+  typedef F<L> FF;
   if (e >= a.count) return;
-  uint32_t b0[L], b1[L];
-  ld<L>(b0, mkvc(a.bre + e, (int)a.Nb));
-  ld<L>(b1, mkvc(a.bim + e, (int)a.Nb));
-  if (a.conj_b) F<L>::neg(mkv(b1, 1), mkv(b1, 1));
-  F<L>::mul2(mkv2(mkv(a.ore + e, (int)a.N), mkv(a.oim + e, (int)a.N)),
-             mkv2(mkvc(a.are + e, (int)a.Na), mkvc(a.aim + e, (int)a.Na)), mkv2(mkv(b0, 1), mkv(b1, 1)));
+  Loc<L> b0, b1, t0, t1, t2;
+  FF::copy(b0.v(), mkvc(a.bre + e, (int)a.Nb));
+  if (a.conj_b)
+    FF::neg(b1.v(), mkvc(a.bim + e, (int)a.Nb));
+  else
+    FF::copy(b1.v(), mkvc(a.bim + e, (int)a.Nb));
+  FF::mul2(mkv2(mkv(a.ore + e, (int)a.N), mkv(a.oim + e, (int)a.N)),
+           mkv2(mkvc(a.are + e, (int)a.Na), mkvc(a.aim + e, (int)a.Na)), mkv2(b0.v(), b1.v()), t0.v(), t1.v(), t2.v());
 }
 
 template <int L>
 BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
+  typedef F<L> FF;
   if (e >= a.count) return;
-  V2 in = mkv2(mkvc(a.re + e, (int)a.Nin), mkvc(a.im + e, (int)a.Nin));
-  V2 out = mkv2(mkv(a.ore + e, (int)a.N), mkv(a.oim + e, (int)a.N));
+  Loc<L> a0, a1, r0, r1, t0, t1, t2;
+  V2 in = mkv2(a0.v(), a1.v()), r = mkv2(r0.v(), r1.v());
+  FF::copy(in.re, mkvc(a.re + e, (int)a.Nin));
+  FF::copy(in.im, mkvc(a.im + e, (int)a.Nin));
   if (a.mode == 1) {
-    GT<L>::pow_fixed(out, in);
+    GT<L>::pow_fixed(r, in, t0.v(), t1.v(), t2.v());
   } else if (a.mode == 2) {
-    F<L>::conj2(out, in);
+    FF::conj2(r, in);
   } else {
-    GT<L>::pow_var(out, in, a.e_be + e * a.ebytes, a.ebytes);
-    if (a.mode == 3) F<L>::neg(out.im, out.im);
+    GT<L>::pow_var(r, in, a.e_be + e * a.ebytes, a.ebytes, t0.v(), t1.v(), t2.v());
+    if (a.mode == 3) FF::neg(r.im, r.im);
   }
+  FF::copy(mkv(a.ore + e, (int)a.N), r.re);
+  FF::copy(mkv(a.oim + e, (int)a.N), r.im);
 }
 
 // One pass of the GT product tree of an L2 sum (bgn.go:460 folded over terms):
@@ -308,75 +319,63 @@ BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
 template <int L>
 BGN_DEV void gt_reduce_body(const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms, int ncoeff, int G,
                             uint32_t* ore, uint32_t* oim, size_t N, size_t id) {
+  typedef F<L> FF;
   if (id >= (size_t)G * ncoeff) return;
   size_t g = id / ncoeff;
   int c = (int)(id % ncoeff);
-  uint32_t r0[L], r1[L];
-  V2 acc = mkv2(mkv(r0, 1), mkv(r1, 1));
-  F<L>::set_one2(acc);
+  Loc<L> r0, r1, t0, t1, t2;
+  V2 acc = mkv2(r0.v(), r1.v());
+  FF::set_one2(acc);
   for (size_t t = g; t < nterms; t += G) {
     size_t e = t * ncoeff + c;
-    F<L>::mul2(acc, acc, mkv2(mkvc(re + e, (int)Nin), mkvc(im + e, (int)Nin)));
+    FF::mul2(acc, acc, mkv2(mkvc(re + e, (int)Nin), mkvc(im + e, (int)Nin)), t0.v(), t1.v(), t2.v());
   }
-  st<L>(mkv(ore + id, (int)N), r0);
-  st<L>(mkv(oim + id, (int)N), r1);
+  FF::copy(mkv(ore + id, (int)N), acc.re);
+  FF::copy(mkv(oim + id, (int)N), acc.im);
 }
 
 // ------------------------------------------------------------ BSGS (gsbs.go)
 // Baby steps: elems[j] = gen^(j+1), j < S, canonical Montgomery AoS [S][2L];
 // open-addressing hash table slots[hmask+1] holding j+1 (0 = empty).
-template <int L>
-BGN_DEV uint32_t bsgs_hash(const uint32_t (&re)[L], const uint32_t (&im)[L]) {
+BGN_DEV uint32_t bsgs_hash(const uint32_t* re, const uint32_t* im) {
   uint32_t h = re[0] * 0x9E3779B1u ^ im[0] * 0x85EBCA77u ^ (re[1] >> 7);
   return h ^ (h >> 15);
 }
 
 template <int L>
 BGN_DEV void bsgs_build_body(const BsgsBuildArgs& a, size_t g) {
-  typedef Fp<L> P;
+  typedef F<L> FF;
   uint64_t j0 = (uint64_t)g * a.chunk;
   if (j0 >= a.S) return;
-  uint32_t g0[L], g1[L], r0[L], r1[L];
-  ld<L>(g0, mkvc(a.gen, 1));
-  ld<L>(g1, mkvc(a.gen + L, 1));
-  V2 gg = mkv2(mkv(g0, 1), mkv(g1, 1)), rr = mkv2(mkv(r0, 1), mkv(r1, 1));
+  Loc<L> r0, r1, t0, t1, t2;
+  V2 gg = mkv2(mkvc(a.gen, 1), mkvc(a.gen + L, 1)), rr = mkv2(r0.v(), r1.v());
   // rr = gen^(j0+1)
   uint64_t ex = j0 + 1;
-  F<L>::set_one2(rr);
+  FF::set_one2(rr);
   for (int bit = 40; bit >= 0; bit--) {
-    F<L>::sqr2(rr, rr);
-    if ((ex >> bit) & 1) F<L>::mul2(rr, rr, gg);
+    FF::sqr2(rr, rr, t0.v(), t1.v());
+    if ((ex >> bit) & 1) FF::mul2(rr, rr, gg, t0.v(), t1.v(), t2.v());
   }
   for (int i = 0; i < a.chunk && j0 + i < a.S; i++) {
-    uint32_t c0[L], c1[L];
-    P::canon(c0, r0);
-    P::canon(c1, r1);
     uint32_t j = (uint32_t)(j0 + i);
     uint32_t* dst = a.elems + (size_t)j * 2 * L;
-    BGN_UNROLL
-    for (int k = 0; k < L; k++) {
-      dst[k] = c0[k];
-      dst[L + k] = c1[k];
-    }
-    uint32_t h = bsgs_hash<L>(c0, c1) & a.hmask;
+    FF::canon(mkv(dst, 1), rr.re);
+    FF::canon(mkv(dst + L, 1), rr.im);
+    uint32_t h = bsgs_hash(dst, dst + L) & a.hmask;
     while (atomicCAS(a.slots + h, 0u, j + 1) != 0u) h = (h + 1) & a.hmask;
-    F<L>::mul2(rr, rr, gg);
+    FF::mul2(rr, rr, gg, t0.v(), t1.v(), t2.v());
   }
 }
 
+// index of the canonical element (c0, c1) in the baby-step table, or -1
 template <int L>
-BGN_DEVNI int64_t bsgs_probe(const BsgsLookupArgs& a, const uint32_t (&r0)[L], const uint32_t (&r1)[L]) {
-  typedef Fp<L> P;
-  uint32_t c0[L], c1[L];
-  P::canon(c0, r0);
-  P::canon(c1, r1);
-  uint32_t h = bsgs_hash<L>(c0, c1) & a.hmask;
+BGN_DEVNI int64_t bsgs_probe(const BsgsLookupArgs& a, const uint32_t* c0, const uint32_t* c1) {
+  uint32_t h = bsgs_hash(c0, c1) & a.hmask;
   for (;;) {
     uint32_t s = a.slots[h];
     if (s == 0) return -1;
     const uint32_t* el = a.elems + (size_t)(s - 1) * 2 * L;
     uint32_t diff = 0;
-    BGN_UNROLL
     for (int k = 0; k < L; k++) diff |= (el[k] ^ c0[k]) | (el[L + k] ^ c1[k]);
     if (diff == 0) return (int64_t)(s - 1);
     h = (h + 1) & a.hmask;
@@ -385,36 +384,30 @@ BGN_DEVNI int64_t bsgs_probe(const BsgsLookupArgs& a, const uint32_t (&r0)[L], c
 
 template <int L>
 BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
-  typedef Fp<L> P;
+  typedef F<L> FF;
   if (e >= a.count) return;
-  uint32_t p0[L], p1[L], n0[L], n1[L], gi0[L], gi1[L], t[L];
-  ld<L>(p0, mkvc(a.re + e, (int)a.Nin));
-  ld<L>(p1, mkvc(a.im + e, (int)a.Nin));
+  Loc<L> p0, p1, n1, c0, c1, t0, t1, t2;
+  FF::copy(p0.v(), mkvc(a.re + e, (int)a.Nin));
+  FF::copy(p1.v(), mkvc(a.im + e, (int)a.Nin));
   // identity => 0 (recoverMessage, bgn.go:359-363)
-  {
-    uint32_t c0[L], c1[L], one[L];
-    P::canon(c0, p0);
-    P::canon(c1, p1);
-    BGN_UNROLL
-    for (int k = 0; k < L; k++) one[k] = c_fc.one[k];
-    P::canon(t, one);
-    if (P::eq_raw(c0, t) && P::is_zero_raw(c1)) {
-      a.out[e] = 0;
-      a.status[e] = 0;
-      return;
-    }
+  if (FF::is_one(p0.v()) && FF::is_zero(p1.v())) {
+    a.out[e] = 0;
+    a.status[e] = 0;
+    return;
   }
-  BGN_UNROLL
-  for (int k = 0; k < L; k++) {
-    n0[k] = p0[k];
-    t[k] = 0;
-  }
-  P::sub(n1, t, p1);  // conj(csk) = csk^-1 (GT is unitary): the Neg(ct) retry of bgn.go:235-241
-  ld<L>(gi0, mkvc(a.ginv, 1));
-  ld<L>(gi1, mkvc(a.ginv + L, 1));
-  V2 vp = mkv2(mkv(p0, 1), mkv(p1, 1)), vn = mkv2(mkv(n0, 1), mkv(n1, 1)), vg = mkv2(mkv(gi0, 1), mkv(gi1, 1));
+  // conj(csk) = csk^-1 (GT is unitary) is the Neg(ct) retry of bgn.go:235-241; walking csk * g^(-iS)
+  // and its conjugate csk^-1 * g^(+iS) needs only ONE running product: conj(x * y) = conj(x) * conj(y),
+  // so the negative candidate of step i is the conjugate of (csk * conj(ginv)^i) ... which is a second
+  // walk.  Keep two walks but share the probe code.
+  FF::neg(n1.v(), p1.v());
+  Loc<L> n0;
+  FF::copy(n0.v(), p0.v());
+  V2 vp = mkv2(p0.v(), p1.v()), vn = mkv2(n0.v(), n1.v());
+  V2 vg = mkv2(mkvc(a.ginv, 1), mkvc(a.ginv + L, 1));
   for (uint32_t i = 0; i < a.giant_steps; i++) {
-    int64_t j = bsgs_probe<L>(a, p0, p1);
+    FF::canon(c0.v(), vp.re);
+    FF::canon(c1.v(), vp.im);
+    int64_t j = bsgs_probe<L>(a, c0.w, c1.w);
     if (j >= 0) {
       uint64_t m = (uint64_t)i * a.S + (uint64_t)j + 1;
       if (m <= a.mmax) {
@@ -423,7 +416,9 @@ BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
         return;
       }
     }
-    j = bsgs_probe<L>(a, n0, n1);
+    FF::canon(c0.v(), vn.re);
+    FF::canon(c1.v(), vn.im);
+    j = bsgs_probe<L>(a, c0.w, c1.w);
     if (j >= 0) {
       uint64_t m = (uint64_t)i * a.S + (uint64_t)j + 1;
       if (m <= a.mmax) {
@@ -433,8 +428,8 @@ BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
       }
     }
     if (i + 1 < a.giant_steps) {
-      F<L>::mul2(vp, vp, vg);
-      F<L>::mul2(vn, vn, vg);
+      FF::mul2(vp, vp, vg, t0.v(), t1.v(), t2.v());
+      FF::mul2(vn, vn, vg, t0.v(), t1.v(), t2.v());
     }
   }
   a.out[e] = 0;
@@ -493,9 +488,10 @@ __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uin
   gt_reduce_body<L>(re, im, Nin, nterms, ncoeff, G, ore, oim, N, BGN_GID(size_t));
 }
 
-// the Miller team kernel: <= 144 threads per block, 2 blocks per SM (shared-memory bound)
+// the Miller team kernel: <= 256 threads per block; blocks per SM are bounded by shared memory
+// (16 element slots per thread)
 template <int L>
-__global__ void __launch_bounds__(144, 2) k_miller(const __grid_constant__ MillerArgs a) {
+__global__ void __launch_bounds__(256, 1) k_miller(const __grid_constant__ MillerArgs a) {
   extern __shared__ uint32_t smem_dyn[];
   MillerTeam<L> T(a, smem_dyn, threadIdx.x, blockIdx.x, blockDim.x);
   T.run([] { __syncthreads(); });

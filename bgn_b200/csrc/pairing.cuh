@@ -22,86 +22,57 @@ BGN_CONST PairConsts c_pc;
 
 template <int L>
 struct GT {
-  typedef Fp<L> P;
   typedef F<L> FF;
 
   // f <- f^((p^2-1)/n) = (conj(f)/f)^l, in place.  conj(f)/f = conj(f)^2 / N(f).
-  BGN_DEVNI static void final_exp(V2 f) {
-    uint32_t f0[L], f1[L], a[L], b[L], ni[L], g0[L], g1[L], r0[L], r1[L];
-    ld<L>(f0, f.re);
-    ld<L>(f1, f.im);
-    P::sqr(a, f0);
-    P::sqr(b, f1);
-    P::add(ni, a, b);
-    FF::inv(mkv(ni, 1), mkv(ni, 1));
-    P::sub(g0, a, b);
-    P::mul(g0, g0, ni);
-    P::mul(g1, f0, f1);
-    P::add(g1, g1, g1);
-    BGN_UNROLL
-    for (int k = 0; k < L; k++) a[k] = 0;
-    P::sub(g1, a, g1);
-    P::mul(g1, g1, ni);
-    // (g0 + g1 i)^l, MSB-first
-    BGN_UNROLL
-    for (int k = 0; k < L; k++) {
-      r0[k] = g0[k];
-      r1[k] = g1[k];
-    }
+  // g (2 elements) and t0..t2 are scratch.
+  BGN_DEV static void final_exp(V2 f, V2 g, V t0, V t1, V t2) {
+    FF::sqr(t0, f.re);
+    FF::sqr(t1, f.im);
+    FF::add(t2, t0, t1);        // N(f)
+    FF::sub(g.re, t0, t1);      // re(conj(f)^2)
+    FF::mul(g.im, f.re, f.im);
+    FF::add(g.im, g.im, g.im);
+    FF::neg(g.im, g.im);        // im(conj(f)^2)
+    FF::inv(t0, t2, t1);        // 1/N(f)
+    FF::mul(g.re, g.re, t0);
+    FF::mul(g.im, g.im, t0);
+    // f = g^l, MSB-first
+    FF::copy2(f, g);
     uint64_t l = c_pc.l;
     int top = 63;
     while (top > 0 && !((l >> top) & 1)) top--;
-    V2 r = mkv2(mkv(r0, 1), mkv(r1, 1));
-    V2 g = mkv2(mkv(g0, 1), mkv(g1, 1));
     for (int bit = top - 1; bit >= 0; bit--) {
-      FF::sqr2(r, r);
-      if ((l >> bit) & 1) FF::mul2(r, r, g);
+      FF::sqr2(f, f, t0, t1);
+      if ((l >> bit) & 1) FF::mul2(f, f, g, t0, t1, t2);
     }
-    st<L>(f.re, r0);
-    st<L>(f.im, r1);
   }
 
-  // r <- a^e for the fixed exponent c_pc.exp (Decrypt: C^q1, bgn.go:223).
-  BGN_DEVNI static void pow_fixed(V2 r, V2 a) {
-    uint32_t a0[L], a1[L], r0[L], r1[L];
-    ld<L>(a0, a.re);
-    ld<L>(a1, a.im);
-    BGN_UNROLL
-    for (int k = 0; k < L; k++) {
-      r0[k] = a0[k];
-      r1[k] = a1[k];
-    }
-    V2 rr = mkv2(mkv(r0, 1), mkv(r1, 1));
-    V2 aa = mkv2(mkv(a0, 1), mkv(a1, 1));
+  // r <- a^e for the fixed exponent c_pc.exp (Decrypt: C^q1, bgn.go:223).  r must not alias a.
+  BGN_DEV static void pow_fixed(V2 r, V2 a, V t0, V t1, V t2) {
     int nb = c_pc.exp_bits;
     if (nb == 0) {
-      FF::set_one2(rr);
+      FF::set_one2(r);
+      return;
     }
+    FF::copy2(r, a);
     for (int bit = nb - 2; bit >= 0; bit--) {
-      FF::sqr2(rr, rr);
-      if ((c_pc.exp[bit >> 5] >> (bit & 31)) & 1) FF::mul2(rr, rr, aa);
+      FF::sqr2(r, r, t0, t1);
+      if ((c_pc.exp[bit >> 5] >> (bit & 31)) & 1) FF::mul2(r, r, a, t0, t1, t2);
     }
-    st<L>(r.re, r0);
-    st<L>(r.im, r1);
   }
 
   // r <- a^e, per-element exponent given as big-endian bytes (MultConst on L2, bgn.go:277).
-  BGN_DEVNI static void pow_var(V2 r, V2 a, const uint8_t* e_be, int ebytes) {
-    uint32_t a0[L], a1[L], r0[L], r1[L];
-    ld<L>(a0, a.re);
-    ld<L>(a1, a.im);
-    V2 rr = mkv2(mkv(r0, 1), mkv(r1, 1));
-    V2 aa = mkv2(mkv(a0, 1), mkv(a1, 1));
-    FF::set_one2(rr);
+  // r must not alias a.
+  BGN_DEV static void pow_var(V2 r, V2 a, const uint8_t* e_be, int ebytes, V t0, V t1, V t2) {
+    FF::set_one2(r);
     for (int i = 0; i < ebytes; i++) {
       uint32_t byte = e_be[i];
       for (int bit = 7; bit >= 0; bit--) {
-        FF::sqr2(rr, rr);
-        if ((byte >> bit) & 1) FF::mul2(rr, rr, aa);
+        FF::sqr2(r, r, t0, t1);
+        if ((byte >> bit) & 1) FF::mul2(r, r, a, t0, t1, t2);
       }
     }
-    st<L>(r.re, r0);
-    st<L>(r.im, r1);
   }
 };
 
@@ -115,7 +86,7 @@ template <int L>
 struct MillerTeam {
   typedef F<L> FF;
   typedef G<L> GG;
-  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_BX = 7, S_BY = 8, S_CR = 9, S_AR = 10, S_BI = 11, NSLOT = BGN_MILLER_NSLOT };
+  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_BX = 7, S_BY = 8, S_CR = 9, S_AR = 10, S_BI = 11, S_T0 = 12, S_T1 = 13, S_T2 = 14, S_T3 = 15, NSLOT = BGN_MILLER_NSLOT };
 
   const MillerArgs& a;
   uint32_t* smem;   // NSLOT*L*nt words of state, then nt bytes flagsA, nt bytes flagsB
@@ -167,17 +138,24 @@ struct MillerTeam {
   // phase A: advance own Miller point, publish its line; square own accumulators on doubling steps
   BGN_DEV void phaseA(int op, bool first) {
     if (!active) return;
+    V t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2), t3 = slot(tid, S_T3);
     if (op == MOP_DBL && !first) {
-      FF::sqr2(facc(tid, 0), facc(tid, 0));
-      if (t + a.dE < a.dM + a.dE - 1) FF::sqr2(facc(tid, 1), facc(tid, 1));
+      FF::sqr2(facc(tid, 0), facc(tid, 0), t0, t1);
+      if (t + a.dE < a.dM + a.dE - 1) FF::sqr2(facc(tid, 1), facc(tid, 1), t0, t1);
     }
     if (t < a.dM && flagsA()[tid]) {
       if (op == MOP_DBL) {
-        GG::dbl_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
+        GG::dbl_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI),
+                     t0, t1, t2);
       } else {
         size_t idx = (size_t)unit * a.dM + t;
-        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), mkvc(a.Mx + idx, a.NM), mkvc(a.My + idx, a.NM),
-                      op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
+        V ya = mkvc(a.My + idx, a.NM);
+        if (op == MOP_SUB) {
+          FF::neg(t3, ya);
+          ya = t3;
+        }
+        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), mkvc(a.Mx + idx, a.NM), ya, slot(tid, S_CR),
+                      slot(tid, S_AR), slot(tid, S_BI), t0, t1, t2);
       }
     }
   }
@@ -196,7 +174,7 @@ struct MillerTeam {
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
       FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), slot(base + k, S_BX),
-                   slot(base + k, S_BY));
+                   slot(base + k, S_BY), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2), slot(tid, S_T3));
     }
   }
 
@@ -207,7 +185,8 @@ struct MillerTeam {
       int j = t + s * a.dE;
       if (j >= nslots || j >= a.out_slots) continue;
       V2 f = facc(tid, s);
-      GT<L>::final_exp(f);
+      // the Miller point / line slots of this thread are dead by now: scratch for the exponentiation
+      GT<L>::final_exp(f, mkv2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2));
       size_t o = (size_t)unit * a.out_slots + j;
       FF::copy(mkv(a.out_re + o, a.NOUT), f.re);
       FF::copy(mkv(a.out_im + o, a.NOUT), f.im);

@@ -35,19 +35,9 @@ def naf_digits(n: int) -> List[int]:
 
 
 def fermat_inv_modmuls(p: int, L: int) -> int:
-    """F<L>::inv: 4-bit fixed window over p-2 (field.cuh)."""
+    """F<L>::inv: left-to-right binary exponentiation by p-2 (field.cuh)."""
     e = p - 2
-    cnt = 14  # table a^2..a^15
-    started = False
-    for w in range(8 * L - 1, -1, -1):
-        d = (e >> (4 * w)) & 15
-        if started:
-            cnt += 4
-        if d:
-            if started:
-                cnt += 1
-            started = True
-    return cnt
+    return (e.bit_length() - 1) + (bin(e).count("1") - 1)
 
 
 def final_exp_modmuls(p: int, l: int, L: int) -> int:

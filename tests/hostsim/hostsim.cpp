@@ -11,7 +11,7 @@
 namespace {
 template <int L>
 void sim_miller(const MillerArgs& a, int nblocks, int nt) {
-  std::vector<uint32_t> smem((size_t)BGN_MILLER_NSLOT * L * nt + nt);
+  std::vector<uint32_t> smem((size_t)BGN_MILLER_NSLOT * L * nt + nt + 8);
   for (int b = 0; b < nblocks; b++) {
     std::vector<MillerTeam<L>> T;
     T.reserve(nt);
@@ -89,5 +89,5 @@ uint64_t hs_mul_count(int reset) {
   if (reset) bgnsim::nmul = 0;
   return v;
 }
-int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv(mkv(r, 1), mkvc(a, 1))) }
+int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(mkv(r, 1), mkvc(a, 1), t.v())) }
 }

@@ -302,3 +302,73 @@ def test_mirror_api_poly():
     a, b = pk.EncryptPoly(pk.NewPolyPlaintext(1.1)), pk.EncryptPoly(pk.NewPolyPlaintext(40.2))
     assert f1(sk.DecryptPoly(pk.MultPoly(a, b), pk).PolyEval()) == f1(1.1 * 40.2)
     assert f1(sk.DecryptPoly(pk.SubPoly(b, a), pk).PolyEval()) == f1(40.2 - 1.1)
+
+
+# ---------------------------------------------------------------- mid-size parity vs the C port of the oracle
+@pytest.mark.parametrize("kb,count,d1,d2", [(512, 48, 11, 11), (512, 64, 3, 7), (1024, 6, 8, 8), (256, 200, 5, 4)])
+def test_multpoly_vs_cpu_ref(kb, count, d1, d2):
+    """Encrypt + EMult at BASELINE.json's shapes (d = 11 at 512 bit, d = 8 at 1024 bit) on sizes the
+    multi-threaded C oracle finishes in seconds; includes zero digits with r = 0 (O coefficients)."""
+    import os
+    from oracle.cpu_ref import CpuRef
+    g = load_golden(kb)
+    e = engine_for(g)
+    R = CpuRef(int(g["p"], 16), int(g["n"], 16), g["l"], threads=min(16, os.cpu_count() or 1))
+    rng = np.random.default_rng(kb + count)
+    P, Q = bytes.fromhex(g["P"]), bytes.fromhex(g["Q"])
+
+    def batch(d):
+        x = rng.integers(-1, 2, count * d)
+        r = rng.integers(0, 256, (count * d, e.scalar_bytes), dtype=np.uint8)
+        r[:, 0] &= 0x3F
+        r[::7] = 0  # every 7th coefficient deterministic: zero digits there are the point at infinity
+        got = e.encrypt_batch(x, r.reshape(-1))
+        exp = R.encrypt_batch(P, Q, x, r.reshape(-1))
+        assert got.tobytes() == exp.tobytes()
+        return got
+
+    c1, c2 = batch(d1), batch(d2)
+    assert e.multpoly_batch(c1, d1, c2, d2, count).tobytes() == R.multpoly_batch(c1, d1, c2, d2, count).tobytes()
+
+
+def test_full_size_properties_emult():
+    """BASELINE.json config 3 at FULL size (2^14 pairs, d = 11): the oracle cannot follow, so check
+    size-independent properties: commutativity, decrypt == plaintext convolution on a sample of the
+    batch, and the L2 sum of the whole batch decrypting to the plaintext inner product."""
+    import torch
+    g = load_golden(512)
+    e = engine_for(g)
+    count, d = 1 << 14, 11
+    dev = "cuda:0"
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+
+    def batch():
+        x = torch.randint(-1, 2, (count * d,), generator=gen, device=dev, dtype=torch.int64)
+        r = torch.randint(0, 256, (count * d, e.scalar_bytes), generator=gen, device=dev, dtype=torch.uint8)
+        r[:, 0] &= 0x3F
+        return x, e.encrypt_batch(x, r.reshape(-1))
+
+    x1, c1 = batch()
+    x2, c2 = batch()
+    prod = e.multpoly_batch(c1, d, c2, d, count)
+    assert torch.equal(prod, e.multpoly_batch(c2, d, c1, d, count))
+    EB = e.elem_bytes
+    sample = [0, 1, 4097, count - 1]
+    sel = torch.cat([prod[u * 2 * d * EB:(u + 1) * 2 * d * EB] for u in sample])
+    vals, st = e.decrypt_batch(sel, True)
+    assert not st.any().item()
+    vals = vals.cpu().numpy().reshape(len(sample), 2 * d)
+    a1 = x1.cpu().numpy().reshape(count, d)
+    a2 = x2.cpu().numpy().reshape(count, d)
+    for row, u in zip(vals, sample):
+        assert row.tolist() == np.convolve(a1[u], a2[u]).tolist() + [0]
+    # inner product over the whole batch: per-slot sums are bounded by 11 * 2^14 < T = 2^20
+    total = e.l2_sum_reduce(prod, count, 2 * d)
+    tv, ts = e.decrypt_batch(total, True)
+    assert not ts.any().item()
+    exp = np.zeros(2 * d, dtype=np.int64)
+    for k in range(d):
+        for j in range(d):
+            exp[k + j] += int((a1[:, k] * a2[:, j]).sum())
+    assert tv.cpu().numpy().tolist() == exp.tolist()
