@@ -21,7 +21,13 @@ $(OBJ)/inst_b_%.o: $(SRC)/inst_b.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -DBGN_L=$* -c $< -o $@ 2> $(OBJ)/inst_b_$*.log || (tail -30 $(OBJ)/inst_b_$*.log; false)
 
-$(OBJ)/api.o: $(SRC)/api.cu $(HDRS)
+# api.o depends on WHICH limb counts are linked in: re-made whenever LIMBS changes
+$(OBJ)/limbs.stamp: FORCE
+	@mkdir -p $(OBJ)
+	@echo '$(LIMBS)' | cmp -s - $@ || echo '$(LIMBS)' > $@
+FORCE:
+
+$(OBJ)/api.o: $(SRC)/api.cu $(HDRS) $(OBJ)/limbs.stamp
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(HAVE) -c $< -o $@ 2> $(OBJ)/api.log || (tail -30 $(OBJ)/api.log; false)
 
@@ -31,4 +37,4 @@ $(LIB): $(OBJS)
 clean:
 	rm -rf $(OBJ) $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean FORCE

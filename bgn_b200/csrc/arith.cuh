@@ -194,6 +194,32 @@ struct Fp {
     }
   }
 
+  // Same product with the multiplier streamed from memory: row i reads b[i] = bp[i*bs] when it
+  // needs it, so b never occupies registers and its loads overlap the previous rows.
+  BGN_DEV static void mul_stream(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp, int bs) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    bgnsim::nmul++;
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row<true>(X, Y, a, *bp, pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      bp += bs;
+      row<false>(Y, X, a, *bp, pm, np0);
+      bp += bs;
+      row<false>(X, Y, a, *bp, pm, np0);
+    }
+    if ((L & 1) == 0) {
+      bp += bs;
+      row<false>(Y, X, a, *bp, pm, np0);
+      merge(r, X, Y);
+    } else {
+      merge(r, Y, X);
+    }
+  }
+
   // after the final row with roles (X=aligned, Y=offset): result = Y + (X >> 32)
   BGN_DEV static void merge(uint32_t (&r)[L], const uint32_t (&A)[W], const uint32_t (&B)[W]) {
     add_cc(r[0], A[0], B[1]);

@@ -18,9 +18,9 @@ template <int L>
 struct G {
   typedef F<L> FF;
 
-  // V <- 2V and the tangent line at the old V.  12 products.
+  // P <- 2P and the tangent line at the old P.  12 products.
   // cR, aR, bI receive the line and double as scratch; t0..t2 scratch.
-  BGN_DEV static void dbl_line(V X, V Y, V Z, V cR, V aR, V bI, V t0, V t1, V t2) {
+  BGN_DEV static void dbl_line(E X, E Y, E Z, E cR, E aR, E bI, E t0, E t1, E t2) {
     FF::sqr(t0, X);       // XX
     FF::sqr(t1, Y);       // YY
     FF::sqr(t2, Z);       // ZZ
@@ -50,8 +50,8 @@ struct G {
     FF::sub(Y, Y, t1);
   }
 
-  // V <- 2V (no line).  9 products; t0..t3 scratch.
-  BGN_DEV static void dbl(V X, V Y, V Z, V t0, V t1, V t2, V t3) {
+  // P <- 2P (no line).  9 products; t0..t3 scratch.
+  BGN_DEV static void dbl(E X, E Y, E Z, E t0, E t1, E t2, E t3) {
     FF::sqr(t0, X);
     FF::sqr(t1, Y);
     FF::sqr(t2, Z);
@@ -76,24 +76,29 @@ struct G {
     FF::sub(Y, Y, t1);
   }
 
-  // V <- V + (xA, yA) (mixed) and the chord through them.  13 products.
-  // No special cases: the Miller loop never meets them for points of order n
-  // except at the very last step, which the schedule drops (vertical line).
-  // The caller passes yA already negated for a subtraction step.
-  BGN_DEV static void madd_line(V X, V Y, V Z, V xA, V yA, V cR, V aR, V bI, V t0, V t1, V t2) {
+  // P <- P + (xA, sgn*yA) (mixed) and the chord through them.  13 products.  xA, yA may be
+  // strided (SoA in HBM).  No special cases: the Miller loop never meets them for points of
+  // order n except at the very last step, which the schedule drops (vertical line).
+  BGN_DEV static void madd_line(E X, E Y, E Z, V xA, V yA, bool negate, E cR, E aR, E bI, E t0, E t1, E t2) {
     FF::sqr(t0, Z);        // ZZ
-    FF::mul(t1, xA, t0);
+    FF::mul(t1, t0, xA);
     FF::sub(t1, t1, X);    // H = U2 - X
     FF::mul(t0, Z, t0);
-    FF::mul(t0, yA, t0);   // S2
-    FF::sub(t0, t0, Y);
+    FF::mul(t0, t0, yA);   // |S2|
+    if (negate)
+      FF::add(t0, t0, Y), FF::neg(t0, t0);  // S2 - Y with S2 = -(yA Z^3)
+    else
+      FF::sub(t0, t0, Y);
     FF::add(aR, t0, t0);   // aR = r = 2(S2 - Y)
     FF::mul(Z, Z, t1);
     FF::add(Z, Z, Z);      // Z3 = 2 Z H
     FF::copy(bI, Z);       // bI = Z3
     FF::mul(cR, aR, xA);
-    FF::mul(t0, yA, Z);
-    FF::sub(cR, cR, t0);   // cR = r*xA - yA*Z3
+    FF::mul(t0, Z, yA);
+    if (negate)
+      FF::add(cR, cR, t0);
+    else
+      FF::sub(cR, cR, t0);  // cR = r*xA - (sgn yA)*Z3
     FF::sqr(t0, t1);
     FF::add(t0, t0, t0);
     FF::add(t0, t0, t0);   // I = 4 HH
@@ -110,31 +115,30 @@ struct G {
     FF::sub(Y, t0, t2);
   }
 
-  // Complete mixed addition V <- V + (xA, sgn*yA) for scalar multiplication and
-  // EAdd: handles V == O, V == A (doubling) and V == -A (-> O).  11 products on
-  // the common path.  t0..t4 scratch.
-  BGN_DEVNI static void madd(V X, V Y, V Z, V xA, V yA, bool negate, V t0, V t1, V t2, V t3, V t4) {
-    V ay = yA;
-    if (negate) {
-      FF::neg(t4, yA);
-      ay = t4;
-    }
+  // Complete mixed addition P <- P + (xA, sgn*yA) for scalar multiplication and EAdd: handles
+  // P == O, P == A (doubling) and P == -A (-> O).  11 products on the common path.
+  BGN_DEVNI static void madd(E X, E Y, E Z, V xA, V yA, bool negate, E t0, E t1, E t2, E t3) {
     if (FF::is_zero(Z)) {  // O + A
-      FF::copy(X, xA);
-      FF::copy(Y, ay);
+      FF::load(X, xA);
+      FF::load(Y, yA);
+      if (negate) FF::neg(Y, Y);
       FF::set_one(Z);
       return;
     }
     FF::sqr(t0, Z);       // ZZ
-    FF::mul(t1, xA, t0);
+    FF::mul(t1, t0, xA);
     FF::sub(t1, t1, X);   // H
     FF::mul(t0, Z, t0);
-    FF::mul(t0, ay, t0);
-    FF::sub(t0, t0, Y);   // S2 - Y
+    FF::mul(t0, t0, yA);
+    if (negate)
+      FF::add(t0, t0, Y), FF::neg(t0, t0);
+    else
+      FF::sub(t0, t0, Y);  // S2 - Y
     if (FF::is_zero(t1)) {
       if (FF::is_zero(t0)) {  // same point: double the affine one
-        FF::copy(X, xA);
-        FF::copy(Y, ay);
+        FF::load(X, xA);
+        FF::load(Y, yA);
+        if (negate) FF::neg(Y, Y);
         FF::set_one(Z);
         dbl(X, Y, Z, t0, t1, t2, t3);
       } else {  // inverse points
@@ -162,7 +166,7 @@ struct G {
   }
 
   // y^2 == x^3 + x ?  (pbc curve_from_bytes falls back to O otherwise)
-  BGN_DEVNI static bool on_curve(V xA, V yA, V t0, V t1) {
+  BGN_DEVNI static bool on_curve(const uint32_t* xA, const uint32_t* yA, E t0, E t1) {
     FF::sqr(t0, xA);
     FF::mul(t0, t0, xA);
     FF::add(t0, t0, xA);

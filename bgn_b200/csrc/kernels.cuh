@@ -51,60 +51,68 @@ BGN_DEV void limbs_to_be_bytes(uint8_t* b, int B, const uint32_t (&x)[L]) {
 template <int L>
 BGN_DEV void g1_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf,
                                 size_t N, size_t e) {
+  typedef F<L> FF;
   if (e >= count) return;
-  uint32_t a[L], b[L];
-  be_bytes_to_limbs<L>(a, in + e * 2 * B, B);
-  be_bytes_to_limbs<L>(b, in + e * 2 * B + B, B);
+  Loc<L> a, b, t0, t1;
+  be_bytes_to_limbs<L>(a.w, in + e * 2 * B, B);
+  be_bytes_to_limbs<L>(b.w, in + e * 2 * B + B, B);
   uint32_t o = 0;
   BGN_UNROLL
-  for (int j = 0; j < L; j++) o |= a[j] | b[j];
-  V vx = mkv(x + e, (int)N), vy = mkv(y + e, (int)N);
-  F<L>::to_mont(vx, mkv(a, 1));
-  F<L>::to_mont(vy, mkv(b, 1));
+  for (int j = 0; j < L; j++) o |= a.w[j] | b.w[j];
+  FF::to_mont(a.v(), a.v());
+  FF::to_mont(b.v(), b.v());
   bool isinf = (o == 0);
-  if (!isinf) {
-    Loc<L> t0, t1;
-    isinf = !G<L>::on_curve(vx, vy, t0.v(), t1.v());
-  }
+  if (!isinf) isinf = !G<L>::on_curve(a.v(), b.v(), t0.v(), t1.v());
+  FF::store(x + e, (int)N, a.v());
+  FF::store(y + e, (int)N, b.v());
   inf[e] = isinf ? 1 : 0;
 }
 
 template <int L>
 BGN_DEV void g1_to_bytes_body(const uint32_t* x, const uint32_t* y, const uint8_t* inf, size_t N, size_t count,
                               uint8_t* out, int B, size_t e) {
+  typedef F<L> FF;
   if (e >= count) return;
-  uint32_t a[L], b[L];
+  Loc<L> a, b;
   if (inf[e]) {
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) a[j] = b[j] = 0;
+    FF::set_zero(a.v());
+    FF::set_zero(b.v());
   } else {
-    F<L>::from_mont(mkv(a, 1), mkvc(x + e, (int)N));
-    F<L>::from_mont(mkv(b, 1), mkvc(y + e, (int)N));
+    FF::load(a.v(), mkv(x + e, (int)N));
+    FF::load(b.v(), mkv(y + e, (int)N));
+    FF::from_mont(a.v(), a.v());
+    FF::from_mont(b.v(), b.v());
   }
-  limbs_to_be_bytes<L>(out + e * 2 * B, B, a);
-  limbs_to_be_bytes<L>(out + e * 2 * B + B, B, b);
+  limbs_to_be_bytes<L>(out + e * 2 * B, B, a.w);
+  limbs_to_be_bytes<L>(out + e * 2 * B + B, B, b.w);
 }
 
 template <int L>
 BGN_DEV void fp2_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N,
                                  size_t e) {
+  typedef F<L> FF;
   if (e >= count) return;
-  uint32_t a[L], b[L];
-  be_bytes_to_limbs<L>(a, in + e * 2 * B, B);
-  be_bytes_to_limbs<L>(b, in + e * 2 * B + B, B);
-  F<L>::to_mont(mkv(re + e, (int)N), mkv(a, 1));
-  F<L>::to_mont(mkv(im + e, (int)N), mkv(b, 1));
+  Loc<L> a, b;
+  be_bytes_to_limbs<L>(a.w, in + e * 2 * B, B);
+  be_bytes_to_limbs<L>(b.w, in + e * 2 * B + B, B);
+  FF::to_mont(a.v(), a.v());
+  FF::to_mont(b.v(), b.v());
+  FF::store(re + e, (int)N, a.v());
+  FF::store(im + e, (int)N, b.v());
 }
 
 template <int L>
 BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B,
                                size_t e) {
+  typedef F<L> FF;
   if (e >= count) return;
-  uint32_t a[L], b[L];
-  F<L>::from_mont(mkv(a, 1), mkvc(re + e, (int)N));
-  F<L>::from_mont(mkv(b, 1), mkvc(im + e, (int)N));
-  limbs_to_be_bytes<L>(out + e * 2 * B, B, a);
-  limbs_to_be_bytes<L>(out + e * 2 * B + B, B, b);
+  Loc<L> a, b;
+  FF::load(a.v(), mkv(re + e, (int)N));
+  FF::load(b.v(), mkv(im + e, (int)N));
+  FF::from_mont(a.v(), a.v());
+  FF::from_mont(b.v(), b.v());
+  limbs_to_be_bytes<L>(out + e * 2 * B, B, a.w);
+  limbs_to_be_bytes<L>(out + e * 2 * B + B, B, b.w);
 }
 
 // ------------------------------------------------------------ G1 kernels
@@ -113,19 +121,19 @@ BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N,
 // C = x*P + r*Q  (EncryptWithRandomness, bgn.go:340-353), x < 0: C = -(|x|*P + r*Q); Jacobian out.
 template <int L>
 BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
+  typedef F<L> FF;
   if (e >= a.count) return;
-  Loc<L> X, Y, Z, t0, t1, t2, t3, t4;
-  V vX = X.v(), vY = Y.v(), vZ = Z.v();
-  F<L>::set_zero(vX);
-  F<L>::set_zero(vY);
-  F<L>::set_zero(vZ);
+  Loc<L> X, Y, Z, t0, t1, t2, t3;
+  FF::set_zero(X.v());
+  FF::set_zero(Y.v());
+  FF::set_zero(Z.v());
   if (a.r_be) {
     const uint8_t* r = a.r_be + e * a.rbytes;
     for (int win = 0; win < a.rbytes; win++) {
       uint32_t d = r[a.rbytes - 1 - win];
       if (d) {
         const uint32_t* ent = a.tabQ + ((size_t)win * 255 + (d - 1)) * 2 * L;
-        G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
+        G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ent), mkv(ent + L), false, t0.v(), t1.v(), t2.v(), t3.v());
       }
     }
   }
@@ -136,48 +144,51 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
     if (d) {
       const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
-      G<L>::madd(vX, vY, vZ, mkvc(ent, 1), mkvc(ent + L, 1), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
+      G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ent), mkv(ent + L), false, t0.v(), t1.v(), t2.v(), t3.v());
     }
   }
   // negative plaintext: -(|x|*P + r*Q), the Sub(encryptZero(), Encrypt(|c|)) of poly.go:17-21
-  if (neg) F<L>::neg(vY, vY);
-  F<L>::copy(mkv(a.X + e, (int)a.N), vX);
-  F<L>::copy(mkv(a.Y + e, (int)a.N), vY);
-  F<L>::copy(mkv(a.Z + e, (int)a.N), vZ);
+  if (neg) FF::neg(Y.v(), Y.v());
+  FF::store(a.X + e, (int)a.N, X.v());
+  FF::store(a.Y + e, (int)a.N, Y.v());
+  FF::store(a.Z + e, (int)a.N, Z.v());
 }
 
 // Jacobian -> affine with one inversion per thread (Montgomery's trick over
-// the elements g, g+G, g+2G, ... of thread g).  Output layout is handle-based
+// the elements g, g+G, g+2G, ... of thread g).  Output layout is stride-based
 // so the same kernel fills SoA arrays and AoS tables.
 template <int L>
 BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
   typedef F<L> FF;
   if (g >= (size_t)a.G || g >= a.count) return;
-  Loc<L> acc, zi, zz, t;
+  Loc<L> acc, z, zi, zz, t;
   FF::set_one(acc.v());
   for (size_t e = g; e < a.count; e += a.G) {
-    V z = mkvc(a.Z + e, (int)a.N);
-    if (FF::is_zero(z)) continue;
-    FF::copy(mkv(a.scratch + e, (int)a.N), acc.v());
-    FF::mul(acc.v(), acc.v(), z);
+    FF::load(z.v(), mkv(a.Z + e, (int)a.N));
+    if (FF::is_zero(z.v())) continue;
+    FF::store(a.scratch + e, (int)a.N, acc.v());
+    FF::mul(acc.v(), acc.v(), z.v());
   }
   FF::inv(acc.v(), acc.v(), t.v());
   size_t last = ((a.count - 1 - g) / a.G) * a.G + g;  // largest e = g (mod G) below count
   for (size_t e = last;; e -= a.G) {
-    V z = mkvc(a.Z + e, (int)a.N);
-    bool isinf = FF::is_zero(z);
-    V ox = mkv(a.ox + e * a.o_estride, (int)a.o_lstride), oy = mkv(a.oy + e * a.o_estride, (int)a.o_lstride);
+    FF::load(z.v(), mkv(a.Z + e, (int)a.N));
+    bool isinf = FF::is_zero(z.v());
+    uint32_t* ox = a.ox + e * a.o_estride;
+    uint32_t* oy = a.oy + e * a.o_estride;
     if (a.inf) a.inf[e] = isinf ? 1 : 0;
     if (isinf) {
-      FF::set_zero(ox);
-      FF::set_zero(oy);
+      FF::store_zero(ox, (int)a.o_lstride);
+      FF::store_zero(oy, (int)a.o_lstride);
     } else {
-      FF::mul(zi.v(), acc.v(), mkvc(a.scratch + e, (int)a.N));  // 1/Z_e
-      FF::mul(acc.v(), acc.v(), z);                              // drop Z_e from the running inverse
+      FF::mul(zi.v(), acc.v(), mkv(a.scratch + e, (int)a.N));  // 1/Z_e
+      FF::mul(acc.v(), acc.v(), z.v());                          // drop Z_e from the running inverse
       FF::sqr(zz.v(), zi.v());
-      FF::mul(ox, mkvc(a.X + e, (int)a.N), zz.v());
+      FF::mul(t.v(), zz.v(), mkv(a.X + e, (int)a.N));
+      FF::store(ox, (int)a.o_lstride, t.v());
       FF::mul(zz.v(), zz.v(), zi.v());
-      FF::mul(oy, mkvc(a.Y + e, (int)a.N), zz.v());
+      FF::mul(t.v(), zz.v(), mkv(a.Y + e, (int)a.N));
+      FF::store(oy, (int)a.o_lstride, t.v());
     }
     if (e < (size_t)a.G) break;
   }
@@ -189,23 +200,22 @@ BGN_DEV void g1_add_body(const G1AddArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
   size_t e1 = a.bcast1 ? 0 : e;
-  Loc<L> X, Y, Z, t0, t1, t2, t3, t4;
-  V vX = X.v(), vY = Y.v(), vZ = Z.v();
+  Loc<L> X, Y, Z, t0, t1, t2, t3;
   if (a.inf1[e1]) {
-    FF::set_zero(vX);
-    FF::set_zero(vY);
-    FF::set_zero(vZ);
+    FF::set_zero(X.v());
+    FF::set_zero(Y.v());
+    FF::set_zero(Z.v());
   } else {
-    FF::copy(vX, mkvc(a.x1 + e1, (int)a.N1));
-    FF::copy(vY, mkvc(a.y1 + e1, (int)a.N1));
-    FF::set_one(vZ);
+    FF::load(X.v(), mkv(a.x1 + e1, (int)a.N1));
+    FF::load(Y.v(), mkv(a.y1 + e1, (int)a.N1));
+    FF::set_one(Z.v());
   }
   if (!a.inf2[e])
-    G<L>::madd(vX, vY, vZ, mkvc(a.x2 + e, (int)a.N2), mkvc(a.y2 + e, (int)a.N2), a.subtract != 0, t0.v(), t1.v(),
-               t2.v(), t3.v(), t4.v());
-  FF::copy(mkv(a.X + e, (int)a.N), vX);
-  FF::copy(mkv(a.Y + e, (int)a.N), vY);
-  FF::copy(mkv(a.Z + e, (int)a.N), vZ);
+    G<L>::madd(X.v(), Y.v(), Z.v(), mkv(a.x2 + e, (int)a.N2), mkv(a.y2 + e, (int)a.N2), a.subtract != 0, t0.v(),
+               t1.v(), t2.v(), t3.v());
+  FF::store(a.X + e, (int)a.N, X.v());
+  FF::store(a.Y + e, (int)a.N, Y.v());
+  FF::store(a.Z + e, (int)a.N, Z.v());
 }
 
 // MultConst on L1: k*C, per-element big-endian scalar (bgn.go:258)
@@ -213,30 +223,29 @@ template <int L>
 BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
-  Loc<L> X, Y, Z, ax, ay, t0, t1, t2, t3, t4;
-  V vX = X.v(), vY = Y.v(), vZ = Z.v();
-  FF::set_zero(vX);
-  FF::set_zero(vY);
-  FF::set_zero(vZ);
+  Loc<L> X, Y, Z, ax, ay, t0, t1, t2, t3;
+  FF::set_zero(X.v());
+  FF::set_zero(Y.v());
+  FF::set_zero(Z.v());
   if (!a.inf[e]) {
-    FF::copy(ax.v(), mkvc(a.x + e, (int)a.Nin));
-    FF::copy(ay.v(), mkvc(a.y + e, (int)a.Nin));
+    FF::load(ax.v(), mkv(a.x + e, (int)a.Nin));
+    FF::load(ay.v(), mkv(a.y + e, (int)a.Nin));
     const uint8_t* k = a.k_be + e * a.kbytes;
     bool started = false;  // leading zero bits: doubling O is a no-op
     for (int i = 0; i < a.kbytes; i++) {
       uint32_t byte = k[i];
       for (int bit = 7; bit >= 0; bit--) {
-        if (started) G<L>::dbl(vX, vY, vZ, t0.v(), t1.v(), t2.v(), t3.v());
+        if (started) G<L>::dbl(X.v(), Y.v(), Z.v(), t0.v(), t1.v(), t2.v(), t3.v());
         if ((byte >> bit) & 1) {
-          G<L>::madd(vX, vY, vZ, ax.v(), ay.v(), false, t0.v(), t1.v(), t2.v(), t3.v(), t4.v());
+          G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ax.w), mkv(ay.w), false, t0.v(), t1.v(), t2.v(), t3.v());
           started = true;
         }
       }
     }
   }
-  FF::copy(mkv(a.X + e, (int)a.N), vX);
-  FF::copy(mkv(a.Y + e, (int)a.N), vY);
-  FF::copy(mkv(a.Z + e, (int)a.N), vZ);
+  FF::store(a.X + e, (int)a.N, X.v());
+  FF::store(a.Y + e, (int)a.N, Y.v());
+  FF::store(a.Z + e, (int)a.N, Z.v());
 }
 
 // table construction -----------------------------------------------------
@@ -247,13 +256,13 @@ BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, ui
   typedef F<L> FF;
   if (g != 0) return;
   Loc<L> x, y, z, t0, t1, t2, t3;
-  FF::copy(x.v(), mkvc(bx, 1));
-  FF::copy(y.v(), mkvc(by, 1));
+  FF::copy(x.v(), bx);
+  FF::copy(y.v(), by);
   FF::set_one(z.v());
   for (int win = 0; win < nwin; win++) {
-    FF::copy(mkv(X + win, (int)N), x.v());
-    FF::copy(mkv(Y + win, (int)N), y.v());
-    FF::copy(mkv(Z + win, (int)N), z.v());
+    FF::store(X + win, (int)N, x.v());
+    FF::store(Y + win, (int)N, y.v());
+    FF::store(Z + win, (int)N, z.v());
     for (int i = 0; i < 8; i++) G<L>::dbl(x.v(), y.v(), z.v(), t0.v(), t1.v(), t2.v(), t3.v());
   }
 }
@@ -264,18 +273,18 @@ BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t
   typedef F<L> FF;
   int win = (int)g;
   if (g >= (size_t)nwin) return;
-  Loc<L> x, y, z, t0, t1, t2, t3, t4;
+  Loc<L> x, y, z, t0, t1, t2, t3;
   FF::set_zero(x.v());
   FF::set_zero(y.v());
   FF::set_zero(z.v());
   for (int d = 1; d <= 255; d++) {
     if (!ainf[win])
-      G<L>::madd(x.v(), y.v(), z.v(), mkvc(ax + win, (int)Nb), mkvc(ay + win, (int)Nb), false, t0.v(), t1.v(), t2.v(),
-                 t3.v(), t4.v());
+      G<L>::madd(x.v(), y.v(), z.v(), mkv(ax + win, (int)Nb), mkv(ay + win, (int)Nb), false, t0.v(), t1.v(), t2.v(),
+                 t3.v());
     size_t o = (size_t)win * 255 + (d - 1);
-    FF::copy(mkv(X + o, (int)N), x.v());
-    FF::copy(mkv(Y + o, (int)N), y.v());
-    FF::copy(mkv(Z + o, (int)N), z.v());
+    FF::store(X + o, (int)N, x.v());
+    FF::store(Y + o, (int)N, y.v());
+    FF::store(Z + o, (int)N, z.v());
   }
 }
 
@@ -284,14 +293,16 @@ template <int L>
 BGN_DEV void gt_mul_body(const GtBinArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
-  Loc<L> b0, b1, t0, t1, t2;
-  FF::copy(b0.v(), mkvc(a.bre + e, (int)a.Nb));
-  if (a.conj_b)
-    FF::neg(b1.v(), mkvc(a.bim + e, (int)a.Nb));
-  else
-    FF::copy(b1.v(), mkvc(a.bim + e, (int)a.Nb));
-  FF::mul2(mkv2(mkv(a.ore + e, (int)a.N), mkv(a.oim + e, (int)a.N)),
-           mkv2(mkvc(a.are + e, (int)a.Na), mkvc(a.aim + e, (int)a.Na)), mkv2(b0.v(), b1.v()), t0.v(), t1.v(), t2.v());
+  Loc<L> a0, a1, b0, b1, t0, t1, t2;
+  FF::load(a0.v(), mkv(a.are + e, (int)a.Na));
+  FF::load(a1.v(), mkv(a.aim + e, (int)a.Na));
+  FF::load(b0.v(), mkv(a.bre + e, (int)a.Nb));
+  FF::load(b1.v(), mkv(a.bim + e, (int)a.Nb));
+  if (a.conj_b) FF::neg(b1.v(), b1.v());
+  E2 r = mke2(a0.v(), a1.v());
+  FF::mul2(r, r, mke2(b0.v(), b1.v()), t0.v(), t1.v(), t2.v());
+  FF::store(a.ore + e, (int)a.N, r.re);
+  FF::store(a.oim + e, (int)a.N, r.im);
 }
 
 template <int L>
@@ -299,9 +310,9 @@ BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
   Loc<L> a0, a1, r0, r1, t0, t1, t2;
-  V2 in = mkv2(a0.v(), a1.v()), r = mkv2(r0.v(), r1.v());
-  FF::copy(in.re, mkvc(a.re + e, (int)a.Nin));
-  FF::copy(in.im, mkvc(a.im + e, (int)a.Nin));
+  E2 in = mke2(a0.v(), a1.v()), r = mke2(r0.v(), r1.v());
+  FF::load(in.re, mkv(a.re + e, (int)a.Nin));
+  FF::load(in.im, mkv(a.im + e, (int)a.Nin));
   if (a.mode == 1) {
     GT<L>::pow_fixed(r, in, t0.v(), t1.v(), t2.v());
   } else if (a.mode == 2) {
@@ -310,8 +321,8 @@ BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
     GT<L>::pow_var(r, in, a.e_be + e * a.ebytes, a.ebytes, t0.v(), t1.v(), t2.v());
     if (a.mode == 3) FF::neg(r.im, r.im);
   }
-  FF::copy(mkv(a.ore + e, (int)a.N), r.re);
-  FF::copy(mkv(a.oim + e, (int)a.N), r.im);
+  FF::store(a.ore + e, (int)a.N, r.re);
+  FF::store(a.oim + e, (int)a.N, r.im);
 }
 
 // One pass of the GT product tree of an L2 sum (bgn.go:460 folded over terms):
@@ -323,15 +334,17 @@ BGN_DEV void gt_reduce_body(const uint32_t* re, const uint32_t* im, size_t Nin, 
   if (id >= (size_t)G * ncoeff) return;
   size_t g = id / ncoeff;
   int c = (int)(id % ncoeff);
-  Loc<L> r0, r1, t0, t1, t2;
-  V2 acc = mkv2(r0.v(), r1.v());
+  Loc<L> r0, r1, b0, b1, t0, t1, t2;
+  E2 acc = mke2(r0.v(), r1.v()), b = mke2(b0.v(), b1.v());
   FF::set_one2(acc);
   for (size_t t = g; t < nterms; t += G) {
     size_t e = t * ncoeff + c;
-    FF::mul2(acc, acc, mkv2(mkvc(re + e, (int)Nin), mkvc(im + e, (int)Nin)), t0.v(), t1.v(), t2.v());
+    FF::load(b.re, mkv(re + e, (int)Nin));
+    FF::load(b.im, mkv(im + e, (int)Nin));
+    FF::mul2(acc, acc, b, t0.v(), t1.v(), t2.v());
   }
-  FF::copy(mkv(ore + id, (int)N), acc.re);
-  FF::copy(mkv(oim + id, (int)N), acc.im);
+  FF::store(ore + id, (int)N, acc.re);
+  FF::store(oim + id, (int)N, acc.im);
 }
 
 // ------------------------------------------------------------ BSGS (gsbs.go)
@@ -347,8 +360,10 @@ BGN_DEV void bsgs_build_body(const BsgsBuildArgs& a, size_t g) {
   typedef F<L> FF;
   uint64_t j0 = (uint64_t)g * a.chunk;
   if (j0 >= a.S) return;
-  Loc<L> r0, r1, t0, t1, t2;
-  V2 gg = mkv2(mkvc(a.gen, 1), mkvc(a.gen + L, 1)), rr = mkv2(r0.v(), r1.v());
+  Loc<L> g0, g1, r0, r1, t0, t1, t2;
+  FF::copy(g0.v(), a.gen);
+  FF::copy(g1.v(), a.gen + L);
+  E2 gg = mke2(g0.v(), g1.v()), rr = mke2(r0.v(), r1.v());
   // rr = gen^(j0+1)
   uint64_t ex = j0 + 1;
   FF::set_one2(rr);
@@ -359,8 +374,8 @@ BGN_DEV void bsgs_build_body(const BsgsBuildArgs& a, size_t g) {
   for (int i = 0; i < a.chunk && j0 + i < a.S; i++) {
     uint32_t j = (uint32_t)(j0 + i);
     uint32_t* dst = a.elems + (size_t)j * 2 * L;
-    FF::canon(mkv(dst, 1), rr.re);
-    FF::canon(mkv(dst + L, 1), rr.im);
+    FF::canon(dst, rr.re);
+    FF::canon(dst + L, rr.im);
     uint32_t h = bsgs_hash(dst, dst + L) & a.hmask;
     while (atomicCAS(a.slots + h, 0u, j + 1) != 0u) h = (h + 1) & a.hmask;
     FF::mul2(rr, rr, gg, t0.v(), t1.v(), t2.v());
@@ -386,24 +401,22 @@ template <int L>
 BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
-  Loc<L> p0, p1, n1, c0, c1, t0, t1, t2;
-  FF::copy(p0.v(), mkvc(a.re + e, (int)a.Nin));
-  FF::copy(p1.v(), mkvc(a.im + e, (int)a.Nin));
+  Loc<L> p0, p1, n0, n1, gi0, gi1, c0, c1, t0, t1, t2;
+  FF::load(p0.v(), mkv(a.re + e, (int)a.Nin));
+  FF::load(p1.v(), mkv(a.im + e, (int)a.Nin));
   // identity => 0 (recoverMessage, bgn.go:359-363)
   if (FF::is_one(p0.v()) && FF::is_zero(p1.v())) {
     a.out[e] = 0;
     a.status[e] = 0;
     return;
   }
-  // conj(csk) = csk^-1 (GT is unitary) is the Neg(ct) retry of bgn.go:235-241; walking csk * g^(-iS)
-  // and its conjugate csk^-1 * g^(+iS) needs only ONE running product: conj(x * y) = conj(x) * conj(y),
-  // so the negative candidate of step i is the conjugate of (csk * conj(ginv)^i) ... which is a second
-  // walk.  Keep two walks but share the probe code.
-  FF::neg(n1.v(), p1.v());
-  Loc<L> n0;
+  // conj(csk) = csk^-1 (GT is unitary) is the Neg(ct) retry of bgn.go:235-241: the positive and
+  // the negated candidate walk the giant steps together, so a negative plaintext costs no retry
   FF::copy(n0.v(), p0.v());
-  V2 vp = mkv2(p0.v(), p1.v()), vn = mkv2(n0.v(), n1.v());
-  V2 vg = mkv2(mkvc(a.ginv, 1), mkvc(a.ginv + L, 1));
+  FF::neg(n1.v(), p1.v());
+  FF::copy(gi0.v(), a.ginv);
+  FF::copy(gi1.v(), a.ginv + L);
+  E2 vp = mke2(p0.v(), p1.v()), vn = mke2(n0.v(), n1.v()), vg = mke2(gi0.v(), gi1.v());
   for (uint32_t i = 0; i < a.giant_steps; i++) {
     FF::canon(c0.v(), vp.re);
     FF::canon(c1.v(), vp.im);
@@ -506,8 +519,11 @@ __global__ void __launch_bounds__(128) k_mulmod_bench(uint32_t* io, size_t N, in
   size_t e = BGN_GID(size_t);
   uint32_t a[ILP][L], b[L];
 #pragma unroll
-  for (int c = 0; c < ILP; c++) ld<L>(a[c], mkvc(io + e, (int)N));
-  ld<L>(b, mkvc(io + e, (int)N));
+  for (int c = 0; c < ILP; c++)
+#pragma unroll
+    for (int j = 0; j < L; j++) a[c][j] = io[(size_t)j * N + e];
+#pragma unroll
+  for (int j = 0; j < L; j++) b[j] = io[(size_t)j * N + e];
 #pragma unroll
   for (int c = 0; c < ILP; c++) a[c][0] += c;
   for (int i = 0; i < iters; i++) {
@@ -518,6 +534,7 @@ __global__ void __launch_bounds__(128) k_mulmod_bench(uint32_t* io, size_t N, in
   for (int c = 1; c < ILP; c++)
 #pragma unroll
     for (int j = 0; j < L; j++) a[0][j] ^= a[c][j];
-  st<L>(mkv(io + e, (int)N), a[0]);
+#pragma unroll
+  for (int j = 0; j < L; j++) io[(size_t)j * N + e] = a[0][j];
 }
 #endif  // !BGN_HOSTSIM

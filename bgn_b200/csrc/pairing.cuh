@@ -26,7 +26,7 @@ struct GT {
 
   // f <- f^((p^2-1)/n) = (conj(f)/f)^l, in place.  conj(f)/f = conj(f)^2 / N(f).
   // g (2 elements) and t0..t2 are scratch.
-  BGN_DEV static void final_exp(V2 f, V2 g, V t0, V t1, V t2) {
+  BGN_DEV static void final_exp(E2 f, E2 g, E t0, E t1, E t2) {
     FF::sqr(t0, f.re);
     FF::sqr(t1, f.im);
     FF::add(t2, t0, t1);        // N(f)
@@ -49,7 +49,7 @@ struct GT {
   }
 
   // r <- a^e for the fixed exponent c_pc.exp (Decrypt: C^q1, bgn.go:223).  r must not alias a.
-  BGN_DEV static void pow_fixed(V2 r, V2 a, V t0, V t1, V t2) {
+  BGN_DEV static void pow_fixed(E2 r, E2 a, E t0, E t1, E t2) {
     int nb = c_pc.exp_bits;
     if (nb == 0) {
       FF::set_one2(r);
@@ -64,13 +64,17 @@ struct GT {
 
   // r <- a^e, per-element exponent given as big-endian bytes (MultConst on L2, bgn.go:277).
   // r must not alias a.
-  BGN_DEV static void pow_var(V2 r, V2 a, const uint8_t* e_be, int ebytes, V t0, V t1, V t2) {
+  BGN_DEV static void pow_var(E2 r, E2 a, const uint8_t* e_be, int ebytes, E t0, E t1, E t2) {
     FF::set_one2(r);
+    bool started = false;  // squaring 1 is a no-op
     for (int i = 0; i < ebytes; i++) {
       uint32_t byte = e_be[i];
       for (int bit = 7; bit >= 0; bit--) {
-        FF::sqr2(r, r, t0, t1);
-        if ((byte >> bit) & 1) FF::mul2(r, r, a, t0, t1, t2);
+        if (started) FF::sqr2(r, r, t0, t1);
+        if ((byte >> bit) & 1) {
+          FF::mul2(r, r, a, t0, t1, t2);
+          started = true;
+        }
       }
     }
   }
@@ -86,10 +90,13 @@ template <int L>
 struct MillerTeam {
   typedef F<L> FF;
   typedef G<L> GG;
-  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_BX = 7, S_BY = 8, S_CR = 9, S_AR = 10, S_BI = 11, S_T0 = 12, S_T1 = 13, S_T2 = 14, S_T3 = 15, NSLOT = BGN_MILLER_NSLOT };
+  // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
+  // the line it publishes, three temporaries.  Evaluation points stay in HBM/L2 (SoA).
+  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_T0 = 10, S_T1 = 11, S_T2 = 12,
+         NSLOT = BGN_MILLER_NSLOT };
 
   const MillerArgs& a;
-  uint32_t* smem;   // NSLOT*L*nt words of state, then nt bytes flagsA, nt bytes flagsB
+  uint32_t* smem;   // NSLOT*nt elements of L words ([slot][thread][limb]), then nt bytes flagsA, nt bytes flagsB
   int nt, tid, bid;
   int t, team, unit;
   bool active;
@@ -103,10 +110,13 @@ struct MillerTeam {
     active = team < a.teams_per_block && unit < a.count;
   }
   static BGN_DEV size_t smem_bytes(int nt) { return (size_t)NSLOT * L * nt * 4 + 2 * (size_t)nt; }
-  BGN_DEV V slot(int thread, int k) const { return mkv(smem + (size_t)k * L * nt + thread, nt); }
+  // thread stride L words is odd for every supported L, so a warp touching one limb of one slot
+  // hits 32 different banks
+  BGN_DEV E slot(int thread, int k) const { return smem + ((size_t)k * nt + thread) * L; }
   BGN_DEV uint8_t* flagsA() const { return reinterpret_cast<uint8_t*>(smem + (size_t)NSLOT * L * nt); }
   BGN_DEV uint8_t* flagsB() const { return flagsA() + nt; }
-  BGN_DEV V2 facc(int thread, int s) const { return mkv2(slot(thread, S_F0 + 2 * s), slot(thread, S_F0 + 2 * s + 1)); }
+  BGN_DEV E2 facc(int thread, int s) const { return mke2(slot(thread, S_F0 + 2 * s), slot(thread, S_F0 + 2 * s + 1)); }
+  BGN_DEV size_t eidx(int k) const { return a.e_bcast ? (size_t)k : (size_t)unit * a.dE + k; }
 
   BGN_DEV void init() {
     flagsA()[tid] = 0;
@@ -119,26 +129,18 @@ struct MillerTeam {
       bool inf = a.Minf[idx] != 0;
       flagsA()[tid] = inf ? 0 : 1;
       if (!inf) {
-        FF::copy(slot(tid, S_X), mkvc(a.Mx + idx, a.NM));
-        FF::copy(slot(tid, S_Y), mkvc(a.My + idx, a.NM));
+        FF::load(slot(tid, S_X), mkv(a.Mx + idx, a.NM));
+        FF::load(slot(tid, S_Y), mkv(a.My + idx, a.NM));
         FF::set_one(slot(tid, S_Z));
       }
     }
-    {
-      size_t idx = a.e_bcast ? (size_t)t : (size_t)unit * a.dE + t;
-      bool inf = a.Einf[idx] != 0;
-      flagsB()[tid] = inf ? 0 : 1;
-      if (!inf) {
-        FF::copy(slot(tid, S_BX), mkvc(a.Ex + idx, a.NE));
-        FF::copy(slot(tid, S_BY), mkvc(a.Ey + idx, a.NE));
-      }
-    }
+    flagsB()[tid] = a.Einf[eidx(t)] ? 0 : 1;
   }
 
   // phase A: advance own Miller point, publish its line; square own accumulators on doubling steps
   BGN_DEV void phaseA(int op, bool first) {
     if (!active) return;
-    V t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2), t3 = slot(tid, S_T3);
+    E t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2);
     if (op == MOP_DBL && !first) {
       FF::sqr2(facc(tid, 0), facc(tid, 0), t0, t1);
       if (t + a.dE < a.dM + a.dE - 1) FF::sqr2(facc(tid, 1), facc(tid, 1), t0, t1);
@@ -149,13 +151,8 @@ struct MillerTeam {
                      t0, t1, t2);
       } else {
         size_t idx = (size_t)unit * a.dM + t;
-        V ya = mkvc(a.My + idx, a.NM);
-        if (op == MOP_SUB) {
-          FF::neg(t3, ya);
-          ya = t3;
-        }
-        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), mkvc(a.Mx + idx, a.NM), ya, slot(tid, S_CR),
-                      slot(tid, S_AR), slot(tid, S_BI), t0, t1, t2);
+        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), mkv(a.Mx + idx, a.NM), mkv(a.My + idx, a.NM),
+                      op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), t0, t1, t2);
       }
     }
   }
@@ -165,6 +162,7 @@ struct MillerTeam {
     if (!active) return;
     int TS = a.dE;
     int base = tid - t;  // first thread of the team
+    E t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2);
     for (int i = 0; i < a.dM; i++) {
       int k = t - i;
       int s = 0;
@@ -173,8 +171,9 @@ struct MillerTeam {
         s = 1;
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
-      FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), slot(base + k, S_BX),
-                   slot(base + k, S_BY), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2), slot(tid, S_T3));
+      size_t ei = eidx(k);
+      FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), mkv(a.Ex + ei, a.NE),
+                   mkv(a.Ey + ei, a.NE), t0, t1, t2);
     }
   }
 
@@ -184,18 +183,18 @@ struct MillerTeam {
     for (int s = 0; s < 2; s++) {
       int j = t + s * a.dE;
       if (j >= nslots || j >= a.out_slots) continue;
-      V2 f = facc(tid, s);
-      // the Miller point / line slots of this thread are dead by now: scratch for the exponentiation
-      GT<L>::final_exp(f, mkv2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2));
+      E2 f = facc(tid, s);
+      // the Miller point of this thread is dead by now: scratch for the exponentiation
+      GT<L>::final_exp(f, mke2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2));
       size_t o = (size_t)unit * a.out_slots + j;
-      FF::copy(mkv(a.out_re + o, a.NOUT), f.re);
-      FF::copy(mkv(a.out_im + o, a.NOUT), f.im);
+      FF::store(a.out_re + o, a.NOUT, f.re);
+      FF::store(a.out_im + o, a.NOUT, f.im);
     }
     if (t == 0) {
       for (int j = nslots; j < a.out_slots; j++) {  // padding slot(s): GT identity (poly.go:130-137)
         size_t o = (size_t)unit * a.out_slots + j;
-        FF::set_one(mkv(a.out_re + o, a.NOUT));
-        FF::set_zero(mkv(a.out_im + o, a.NOUT));
+        FF::store_one(a.out_re + o, a.NOUT);
+        FF::store_zero(a.out_im + o, a.NOUT);
       }
     }
   }

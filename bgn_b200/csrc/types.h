@@ -24,7 +24,7 @@ struct PairConsts {
   int8_t naf[BGN_MAX_NAF];
 };
 
-#define BGN_MILLER_NSLOT 16  // shared-memory F_p slots per thread of the Miller team kernel
+#define BGN_MILLER_NSLOT 13  // shared-memory F_p slots per thread of the Miller team kernel
 struct MillerArgs {
   const uint32_t* Mx;  // Miller-side points, Montgomery SoA [L][NM], index unit*dM + i
   const uint32_t* My;

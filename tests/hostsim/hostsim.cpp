@@ -89,5 +89,5 @@ uint64_t hs_mul_count(int reset) {
   if (reset) bgnsim::nmul = 0;
   return v;
 }
-int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(mkv(r, 1), mkvc(a, 1), t.v())) }
+int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(r, a, t.v())) }
 }

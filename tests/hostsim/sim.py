@@ -12,7 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-MAXL, MAX_NAF, MAX_EXPW, NSLOT = 34, 1100, 34, 16
+MAXL, MAX_NAF, MAX_EXPW, NSLOT = 34, 1100, 34, 13
 SUPPORTED_L = (3, 5, 17)  # limb counts instantiated in hostsim.cpp
 PRODUCT_L = (3, 5, 9, 17, 33)  # limb counts the CUDA library instantiates
 
