@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -127,6 +128,7 @@ struct bgn_ctx {
   size_t arena_cap = 0, arena_off = 0;
   // instrumentation
   bool timing = false;
+  int miller_skew = 1500;  // cycles; see MillerArgs::skew_cycles
   std::map<std::string, KTime> ktimes;
   struct Pending {
     std::string name;
@@ -383,13 +385,16 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   size_t per_thread = (size_t)BGN_MILLER_NSLOT * c->L * 4 + 2;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
-  // one block of up to 256 threads; as many whole teams as shared memory holds.  For small fields
-  // several blocks share an SM, for L = 17 one block of 7 warps fills it.
-  int nt_max = (int)std::min<size_t>(256, smem_max / per_thread);
-  int teams = nt_max / TS;
-  if (teams == 0) throw ArgErr{"polynomial has too many coefficients for one thread block"};
-  if (TS == 1) teams = std::min(teams, 128);
-  int nt = teams * TS;
+  // a block is 1 or 2 barrier groups of 128 threads (whole teams per group); two groups when shared
+  // memory holds 256 threads (L <= 17), so that every scheduler hosts one warp of each group
+  const int GT_ = 128;
+  if (TS > GT_) throw ArgErr{"polynomial has too many coefficients for one thread group"};
+  int groups = (2 * GT_ * per_thread + 16 <= smem_max) ? 2 : 1;
+  if (GT_ * per_thread + 16 > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
+  int tpg = GT_ / TS;
+  size_t units_per_block = (size_t)groups * tpg;
+  if (count <= (size_t)tpg) groups = 1, units_per_block = tpg;
+  int nt = groups * GT_;
   size_t smem = per_thread * nt + 16;
   MillerArgs a;
   a.Mx = M.x;
@@ -408,10 +413,12 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.dE = dE;
   a.out_slots = out_slots;
   a.count = (int)count;
-  a.teams_per_block = teams;
+  a.teams_per_group = tpg;
+  a.group_threads = GT_;
+  a.skew_cycles = c->miller_skew;
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
-  c->A->miller(cfg(c, nblk(count, teams), nt, smem), a);
+  c->A->miller(cfg(c, (count + units_per_block - 1) / units_per_block, nt, smem), a);
   t.done();
 }
 
@@ -493,6 +500,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
   try {
     c = new bgn_ctx();
     c->device = device;
+    if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};

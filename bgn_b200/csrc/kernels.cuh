@@ -501,13 +501,19 @@ __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uin
   gt_reduce_body<L>(re, im, Nin, nterms, ncoeff, G, ore, oim, N, BGN_GID(size_t));
 }
 
-// the Miller team kernel: <= 256 threads per block; blocks per SM are bounded by shared memory
-// (16 element slots per thread)
+// the Miller team kernel: 1 or 2 barrier groups of 128 threads per block; blocks per SM are bounded
+// by shared memory (13 element slots per thread)
 template <int L>
 __global__ void __launch_bounds__(256, 1) k_miller(const __grid_constant__ MillerArgs a) {
   extern __shared__ uint32_t smem_dyn[];
   MillerTeam<L> T(a, smem_dyn, threadIdx.x, blockIdx.x, blockDim.x);
-  T.run([] { __syncthreads(); });
+  const int bar_id = 1 + T.group, bar_n = a.group_threads;
+  if ((T.group & 1) && a.skew_cycles > 0) {
+    long long t0 = clock64();
+    while (clock64() - t0 < a.skew_cycles) {
+    }
+  }
+  T.run([=] { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory"); });
 }
 
 // Register-resident Montgomery products: `iters` dependent modmuls per thread on

@@ -98,16 +98,24 @@ struct MillerTeam {
   const MillerArgs& a;
   uint32_t* smem;   // NSLOT*nt elements of L words ([slot][thread][limb]), then nt bytes flagsA, nt bytes flagsB
   int nt, tid, bid;
-  int t, team, unit;
+  int t, team, unit, group;
   bool active;
 
+  // A block is `groups` barrier groups of a.group_threads threads; each group holds whole teams and
+  // synchronises on its own named barrier, so the groups drift independently: while the warps of one
+  // group run the add/sub/load glue between two products, the warps of the other group (which share
+  // the same schedulers) keep the multiply pipe busy (profiles/r01_miller_v3_ncu.txt: in lockstep the
+  // pipe idles during the glue of BOTH warps of a scheduler).
   BGN_DEV MillerTeam(const MillerArgs& a_, uint32_t* smem_, int tid_, int bid_, int nt_)
       : a(a_), smem(smem_), nt(nt_), tid(tid_), bid(bid_) {
     int TS = a.dE;
-    t = tid % TS;
-    team = tid / TS;
-    unit = bid * a.teams_per_block + team;
-    active = team < a.teams_per_block && unit < a.count;
+    int groups = nt / a.group_threads;
+    group = tid / a.group_threads;
+    int ltid = tid - group * a.group_threads;
+    t = ltid % TS;
+    team = ltid / TS;
+    unit = (bid * groups + group) * a.teams_per_group + team;
+    active = team < a.teams_per_group && unit < a.count;
   }
   static BGN_DEV size_t smem_bytes(int nt) { return (size_t)NSLOT * L * nt * 4 + 2 * (size_t)nt; }
   // thread stride L words is odd for every supported L, so a warp touching one limb of one slot

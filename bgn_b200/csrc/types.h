@@ -39,7 +39,9 @@ struct MillerArgs {
   int dM, dE;       // dM <= dE; team size TS = dE
   int out_slots;    // slots written per unit (dM+dE for MultPoly: last one is the identity; 1 for Pair)
   int count;        // units
-  int teams_per_block;
+  int teams_per_group;  // whole teams in one barrier group
+  int group_threads;    // threads per barrier group (128 on the GPU); blockDim = groups * group_threads
+  int skew_cycles;      // start-up delay of odd groups (decorrelates the two warps of a scheduler)
 };
 
 struct EncArgs {
