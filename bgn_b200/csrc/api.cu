@@ -128,7 +128,8 @@ struct bgn_ctx {
   size_t arena_cap = 0, arena_off = 0;
   // instrumentation
   bool timing = false;
-  int miller_skew = 1500;  // cycles; see MillerArgs::skew_cycles
+  int miller_skew = 20000;  // cycles; see MillerArgs::skew_cycles
+  int miller_groups = 0;    // 0 = choose per batch, 1 / 2 = force (tuning knob BGN_MILLER_GROUPS)
   std::map<std::string, KTime> ktimes;
   struct Pending {
     std::string name;
@@ -375,7 +376,7 @@ void normalize(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, uin
   t.done();
 }
 void normalize_soa(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, const G1Arr& o) {
-  normalize(c, j, count, scratch, o.x, o.y, 1, o.N, o.inf);
+  normalize(c, j, count, scratch, o.x, o.y, (size_t)c->L, 1, o.inf);
 }
 
 // the Miller team kernel; dM <= dE
@@ -385,15 +386,33 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   size_t per_thread = (size_t)BGN_MILLER_NSLOT * c->L * 4 + 2;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
-  // a block is 1 or 2 barrier groups of 128 threads (whole teams per group); two groups when shared
-  // memory holds 256 threads (L <= 17), so that every scheduler hosts one warp of each group
-  const int GT_ = 128;
-  if (TS > GT_) throw ArgErr{"polynomial has too many coefficients for one thread group"};
-  int groups = (2 * GT_ * per_thread + 16 <= smem_max) ? 2 : 1;
-  if (GT_ * per_thread + 16 > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
-  int tpg = GT_ / TS;
+  // A block is either ONE barrier group of up to 256 threads or TWO independent groups of 128
+  // (whole teams per group).  Two groups run ~7 % faster per wave (the groups drift apart and
+  // fill each other's pipeline bubbles; measured at L = 17, d = 11) but hold fewer teams when
+  // 128 is not a multiple of the team size; pick whichever needs less time for this batch:
+  // waves x time-per-wave, waves = ceil(units / (SMs x blocks/SM x units/block)).
+  if (TS > 128) throw ArgErr{"polynomial has too many coefficients for one thread group"};
+  if (128 * per_thread + 16 > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int nt1 = (int)std::min<size_t>(256, (smem_max - 16) / per_thread) / 32 * 32;  // one group: whole warps
+  int tpg1 = nt1 / TS;
+  if (tpg1 == 0) throw ArgErr{"polynomial has too many coefficients for the shared-memory state at this key size"};
+  bool can2 = 2 * 128 * per_thread + 16 <= smem_max;
+  int tpg2 = 128 / TS;
+  auto cost = [&](int groups, int tpg, int nt, double twave) {
+    size_t bps = std::max<size_t>(1, std::min<size_t>(8, smem_max / (per_thread * nt + 16)));  // blocks per SM
+    size_t per_wave = (size_t)sms * bps * groups * tpg;
+    return (double)((count + per_wave - 1) / per_wave) * twave;
+  };
+  int groups = 1, tpg = tpg1, GT_ = nt1;
+  if (can2 && c->miller_groups != 1 &&
+      (c->miller_groups == 2 || cost(2, tpg2, 256, 0.932) < cost(1, tpg1, nt1, 1.0))) {
+    groups = 2;
+    tpg = tpg2;
+    GT_ = 128;
+  }
   size_t units_per_block = (size_t)groups * tpg;
-  if (count <= (size_t)tpg) groups = 1, units_per_block = tpg;
   int nt = groups * GT_;
   size_t smem = per_thread * nt + 16;
   MillerArgs a;
@@ -501,6 +520,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c = new bgn_ctx();
     c->device = device;
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
+    if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -1184,7 +1204,8 @@ int bgn_timing_last_call(bgn_ctx* c, double* ms) {
 
 int bgn_bench_mulmod(bgn_ctx* c, int ilp, int iters, int blocks, int threads, float* ms) {
   return guarded(c, [&] {
-    if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 128) throw ArgErr{"bad argument"};
+    if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > (ilp >= 10 ? 256 : 128))
+      throw ArgErr{"bad argument"};
     size_t N = (size_t)blocks * threads;
     arena_reserve(c, pad256(N * c->L * 4) + 4096);
     uint32_t* io = arena_get<uint32_t>(c, N * c->L);
@@ -1194,7 +1215,7 @@ int bgn_bench_mulmod(bgn_ctx* c, int ilp, int iters, int blocks, int threads, fl
     CK(cudaEventCreate(&b));
     auto launch = [&](int it) {
       c->total_launches++;
-      if (ilp != 1 && ilp != 2) throw ArgErr{"ilp must be 1 or 2"};
+      if (ilp != 1 && ilp != 2 && (ilp < 10 || ilp > 29)) throw ArgErr{"ilp must be 1, 2 or a primitive mode 10..13"};
       c->A->mulmod_bench(cfg(c, blocks, threads, 0), ilp, io, N, it);
     };
     launch(4);  // warm-up

@@ -194,29 +194,56 @@ struct Fp {
     }
   }
 
-  // Same product with the multiplier streamed from memory: row i reads b[i] = bp[i*bs] when it
-  // needs it, so b never occupies registers and its loads overlap the previous rows.
-  BGN_DEV static void mul_stream(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp, int bs) {
+  // Same product with the multiplier streamed from memory: row i reads b[i] when it needs it, so b
+  // never occupies registers and its loads overlap the previous rows.
+  BGN_DEV static void mul_stream(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
     uint32_t X[W], Y[W];
 #ifdef BGN_HOSTSIM
     bgnsim::nmul++;
 #endif
     const uint32_t* pm = c_fc.p;
     const uint32_t np0 = c_fc.np0;
-    row<true>(X, Y, a, *bp, pm, np0);
+    row<true>(X, Y, a, bp[0], pm, np0);
     BGN_UNROLL
     for (int i = 1; i + 1 < L; i += 2) {
-      bp += bs;
-      row<false>(Y, X, a, *bp, pm, np0);
-      bp += bs;
-      row<false>(X, Y, a, *bp, pm, np0);
+      row<false>(Y, X, a, bp[i], pm, np0);
+      row<false>(X, Y, a, bp[i + 1], pm, np0);
     }
     if ((L & 1) == 0) {
-      bp += bs;
-      row<false>(Y, X, a, *bp, pm, np0);
+      row<false>(Y, X, a, bp[L - 1], pm, np0);
       merge(r, X, Y);
     } else {
       merge(r, Y, X);
+    }
+  }
+
+  // Two independent products with their rows interleaved in program order (ILP 2): the carry
+  // chains of one product fill the dependency gaps of the other.
+  BGN_DEV static void mul_pair(uint32_t (&r1)[L], const uint32_t (&a1)[L], const uint32_t* b1, uint32_t (&r2)[L],
+                               const uint32_t (&a2)[L], const uint32_t* b2) {
+    uint32_t X1[W], Y1[W], X2[W], Y2[W];
+#ifdef BGN_HOSTSIM
+    bgnsim::nmul += 2;
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row<true>(X1, Y1, a1, b1[0], pm, np0);
+    row<true>(X2, Y2, a2, b2[0], pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      row<false>(Y1, X1, a1, b1[i], pm, np0);
+      row<false>(Y2, X2, a2, b2[i], pm, np0);
+      row<false>(X1, Y1, a1, b1[i + 1], pm, np0);
+      row<false>(X2, Y2, a2, b2[i + 1], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row<false>(Y1, X1, a1, b1[L - 1], pm, np0);
+      row<false>(Y2, X2, a2, b2[L - 1], pm, np0);
+      merge(r1, X1, Y1);
+      merge(r2, X2, Y2);
+    } else {
+      merge(r1, Y1, X1);
+      merge(r2, Y2, X2);
     }
   }
 

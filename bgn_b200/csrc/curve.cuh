@@ -76,10 +76,9 @@ struct G {
     FF::sub(Y, Y, t1);
   }
 
-  // P <- P + (xA, sgn*yA) (mixed) and the chord through them.  13 products.  xA, yA may be
-  // strided (SoA in HBM).  No special cases: the Miller loop never meets them for points of
+  // P <- P + (xA, sgn*yA) (mixed) and the chord through them.  13 products.  No special cases: the Miller loop never meets them for points of
   // order n except at the very last step, which the schedule drops (vertical line).
-  BGN_DEV static void madd_line(E X, E Y, E Z, V xA, V yA, bool negate, E cR, E aR, E bI, E t0, E t1, E t2) {
+  BGN_DEV static void madd_line(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E cR, E aR, E bI, E t0, E t1, E t2) {
     FF::sqr(t0, Z);        // ZZ
     FF::mul(t1, t0, xA);
     FF::sub(t1, t1, X);    // H = U2 - X
@@ -117,10 +116,10 @@ struct G {
 
   // Complete mixed addition P <- P + (xA, sgn*yA) for scalar multiplication and EAdd: handles
   // P == O, P == A (doubling) and P == -A (-> O).  11 products on the common path.
-  BGN_DEVNI static void madd(E X, E Y, E Z, V xA, V yA, bool negate, E t0, E t1, E t2, E t3) {
+  BGN_DEVNI static void madd(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E t0, E t1, E t2, E t3) {
     if (FF::is_zero(Z)) {  // O + A
-      FF::load(X, xA);
-      FF::load(Y, yA);
+      FF::copy(X, xA);
+      FF::copy(Y, yA);
       if (negate) FF::neg(Y, Y);
       FF::set_one(Z);
       return;
@@ -136,8 +135,8 @@ struct G {
       FF::sub(t0, t0, Y);  // S2 - Y
     if (FF::is_zero(t1)) {
       if (FF::is_zero(t0)) {  // same point: double the affine one
-        FF::load(X, xA);
-        FF::load(Y, yA);
+        FF::copy(X, xA);
+        FF::copy(Y, yA);
         if (negate) FF::neg(Y, Y);
         FF::set_one(Z);
         dbl(X, Y, Z, t0, t1, t2, t3);

@@ -1,9 +1,8 @@
 // field.cuh -- memory-level F_p / F_p^2 operations on strided element handles.
 //
-// An element handle V = {pointer to limb 0, stride in words}.  The same code
-// addresses (i) the limb-major SoA arrays in HBM ([limb][batch], stride =
-// batch), (ii) per-thread state slots in shared memory ([slot][limb][thread],
-// stride = blockDim) and (iii) thread-local scratch (stride 1).
+// An element handle is a pointer to L consecutive words; the same code addresses (i) the
+// batch arrays in HBM ([N][L]), (ii) per-thread state slots in shared memory
+// ([slot][thread][L]) and (iii) thread-local scratch.
 //
 // Code-size rule (measured, profiles/r01_miller_v1.md): with the Montgomery
 // product inlined at every use the Miller kernel was 625 KB of SASS and spent
@@ -19,26 +18,13 @@
 #pragma once
 #include "arith.cuh"
 
-// Two kinds of element handle:
-//   E  = pointer to L consecutive words (unit stride): thread-local scratch, shared-memory
-//        slots, AoS tables.  Limb j is at a compile-time offset, so loads/stores need no
-//        address arithmetic (which would otherwise land on the integer-multiply pipe as
-//        IMAD.WIDE and compete with the products; measured, profiles/r01_miller_v2_ncu.txt).
-//   V  = {pointer, stride in words}: limb-major SoA arrays in HBM (stride = batch size).
-// Results and first operands are always E; only the multiplier of mul() and the copy
-// helpers take a strided V.
+// Element handle: E = pointer to L consecutive words.  Every device array is array-of-elements
+// ([N][L] words, element e at e*L): thread-local scratch, shared-memory slots, tables and the
+// batch arrays in HBM alike.  Limb j of any operand is then at a compile-time offset, so loads and
+// stores need no address arithmetic -- with a runtime stride (limb-major SoA) ptxas computes each
+// limb address with an IMAD.WIDE, i.e. on the very pipe the products saturate (measured:
+// tools/primbench.py, 85.0 % -> 89.7 % of the IMAD.WIDE peak for the memory-operand product).
 typedef uint32_t* E;
-struct V {
-  const uint32_t* p;
-  int s;
-};
-BGN_DEV V mkv(const uint32_t* p, int s) {
-  V v;
-  v.p = p;
-  v.s = s;
-  return v;
-}
-BGN_DEV V mkv(const uint32_t* p) { return mkv(p, 1); }
 
 template <int L>
 BGN_DEV void ld(uint32_t (&r)[L], const uint32_t* a) {
@@ -74,16 +60,34 @@ struct F {
   typedef Fp<L> P;
 
   // ---------------- F_p primitives (the only places that touch limbs) ----------------
-  // r = a*b (Montgomery).  r may alias a and/or b.  The multiplier b is streamed one limb
-  // per row from memory (any stride); a sits in registers.
-  BGN_DEVNI static void mul(E r, const uint32_t* a, V b) {
-    uint32_t x[L], z[L];
+  // r = a*b (Montgomery).  r may alias a and/or b.  Both operands are loaded up front (measured
+  // 88.5 % of the IMAD.WIDE peak at 2 warps/scheduler vs 85 % when the multiplier is read row by
+  // row, tools/primbench.py modes 20 / 10).
+  BGN_DEVNI static void mul(E r, const uint32_t* a, const uint32_t* b) {
+    uint32_t x[L], y[L], z[L];
     ld<L>(x, a);
-    P::mul_stream(z, x, b.p, b.s);
+    ld<L>(y, b);
+    P::mul(z, x, y);
     st<L>(r, z);
   }
-  BGN_DEV static void mul(E r, const uint32_t* a, const uint32_t* b) { mul(r, a, mkv(b, 1)); }
-  BGN_DEV static void sqr(E r, const uint32_t* a) { mul(r, a, mkv(a, 1)); }
+  BGN_DEV static void sqr(E r, const uint32_t* a) { mul(r, a, a); }
+  // measured alternatives (tools/primbench.py modes 10, 22): multiplier streamed from memory / two
+  // interleaved products per call
+  BGN_DEVNI static void mul_stream(E r, const uint32_t* a, const uint32_t* b) {
+    uint32_t x[L], z[L];
+    ld<L>(x, a);
+    P::mul_stream(z, x, b);
+    st<L>(r, z);
+  }
+  BGN_DEVNI static void mul_pair(E r1, const uint32_t* a1, const uint32_t* b1, E r2, const uint32_t* a2,
+                                 const uint32_t* b2) {
+    uint32_t x1[L], x2[L], z1[L], z2[L];
+    ld<L>(x1, a1);
+    ld<L>(x2, a2);
+    P::mul_pair(z1, x1, b1, z2, x2, b2);
+    st<L>(r1, z1);
+    st<L>(r2, z2);
+  }
   BGN_DEVNI static void add(E r, const uint32_t* a, const uint32_t* b) {
     uint32_t x[L], y[L], z[L];
     ld<L>(x, a);
@@ -107,16 +111,10 @@ struct F {
     P::sub(z, x, y);
     st<L>(r, z);
   }
-  // strided copies: the only way data moves between SoA arrays and unit-stride elements
-  BGN_DEVNI static void load(E r, V a) {
+  BGN_DEVNI static void copy(E r, const uint32_t* a) {
     BGN_UNROLL
-    for (int j = 0; j < L; j++) r[j] = a.p[(size_t)j * a.s];
+    for (int j = 0; j < L; j++) r[j] = a[j];
   }
-  BGN_DEVNI static void store(uint32_t* dst, int stride, const uint32_t* a) {
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) dst[(size_t)j * stride] = a[j];
-  }
-  BGN_DEV static void copy(E r, const uint32_t* a) { load(r, mkv(a, 1)); }
   BGN_DEVNI static void set_one(E r) {
     BGN_UNROLL
     for (int j = 0; j < L; j++) r[j] = c_fc.one[j];
@@ -124,14 +122,6 @@ struct F {
   BGN_DEVNI static void set_zero(E r) {
     BGN_UNROLL
     for (int j = 0; j < L; j++) r[j] = 0;
-  }
-  BGN_DEVNI static void store_one(uint32_t* dst, int stride) {
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) dst[(size_t)j * stride] = c_fc.one[j];
-  }
-  BGN_DEVNI static void store_zero(uint32_t* dst, int stride) {
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) dst[(size_t)j * stride] = 0;
   }
   // value == 0 (mod p) for a lazy-form element
   BGN_DEVNI static bool is_zero(const uint32_t* a) {
@@ -165,14 +155,14 @@ struct F {
     st<L>(r, y);
   }
   // standard integer -> Montgomery form (a < 2^(32L), result lazy)
-  BGN_DEV static void to_mont(E r, const uint32_t* a) { mul(r, a, mkv(c_fc.r2, 1)); }
+  BGN_DEV static void to_mont(E r, const uint32_t* a) { mul(r, a, c_fc.r2); }
   // Montgomery form -> canonical standard integer in [0,p)
   BGN_DEVNI static void from_mont(E r, const uint32_t* a) {
     uint32_t y[L];
     BGN_UNROLL
     for (int j = 0; j < L; j++) y[j] = 0;
     y[0] = 1;
-    mul(r, a, mkv(y, 1));
+    mul(r, a, y);
     canon(r, r);
   }
 
@@ -226,8 +216,8 @@ struct F {
   }
 
   // Miller-loop term: f <- f * ((cR + aR*xB) + (bI*yB) i); 5 products
-  // (eval 2 + f*line 3).  xB, yB may be strided (SoA in HBM).  t0..t2 scratch.
-  BGN_DEV static void line_mul(E2 f, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI, V xB, V yB, E t0, E t1,
+  // (eval 2 + f*line 3).  t0..t2 scratch.
+  BGN_DEV static void line_mul(E2 f, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI, const uint32_t* xB, const uint32_t* yB, E t0, E t1,
                                E t2) {
     mul(t0, aR, xB);
     add(t0, t0, cR);  // l0

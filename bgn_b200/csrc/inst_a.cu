@@ -32,7 +32,11 @@ void fp2_to_bytes(LaunchCfg cfg, const uint32_t* re, const uint32_t* im, size_t 
 void bsgs_build(LaunchCfg cfg, const BsgsBuildArgs& a) { k_bsgs_build<LL><<<CFG>>>(a); }
 void bsgs_lookup(LaunchCfg cfg, const BsgsLookupArgs& a) { k_bsgs_lookup<LL><<<CFG>>>(a); }
 void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
-  if (ilp == 2)
+  if (ilp >= 10) {
+    size_t smem = (size_t)13 * LL * 4 * cfg.block;
+    cudaFuncSetAttribute(k_prim_bench<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_prim_bench<LL><<<cfg.grid, cfg.block, smem, cfg.stream>>>(io, N, iters, ilp);
+  } else if (ilp == 2)
     k_mulmod_bench<LL, 2><<<CFG>>>(io, N, iters);
   else
     k_mulmod_bench<LL, 1><<<CFG>>>(io, N, iters);

@@ -1,5 +1,5 @@
 // kernels.cuh -- the sm_100a kernels of the batched BGN engine (templated on
-// the limb count L).  Device data layout: limb-major SoA, array[limb][N] of
+// the limb count L).  Device data layout: arrays of elements, array[N][L] of
 // u32 in Montgomery form ("lazy" range [0,2p)); G1 arrays carry an extra
 // byte-per-element infinity flag.  See DESIGN.md for the per-kernel roofline.
 //
@@ -63,8 +63,8 @@ BGN_DEV void g1_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_t
   FF::to_mont(b.v(), b.v());
   bool isinf = (o == 0);
   if (!isinf) isinf = !G<L>::on_curve(a.v(), b.v(), t0.v(), t1.v());
-  FF::store(x + e, (int)N, a.v());
-  FF::store(y + e, (int)N, b.v());
+  FF::copy(x + (size_t)(e) * L, a.v());
+  FF::copy(y + (size_t)(e) * L, b.v());
   inf[e] = isinf ? 1 : 0;
 }
 
@@ -78,8 +78,8 @@ BGN_DEV void g1_to_bytes_body(const uint32_t* x, const uint32_t* y, const uint8_
     FF::set_zero(a.v());
     FF::set_zero(b.v());
   } else {
-    FF::load(a.v(), mkv(x + e, (int)N));
-    FF::load(b.v(), mkv(y + e, (int)N));
+    FF::copy(a.v(), (x + (size_t)(e) * L));
+    FF::copy(b.v(), (y + (size_t)(e) * L));
     FF::from_mont(a.v(), a.v());
     FF::from_mont(b.v(), b.v());
   }
@@ -97,8 +97,8 @@ BGN_DEV void fp2_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_
   be_bytes_to_limbs<L>(b.w, in + e * 2 * B + B, B);
   FF::to_mont(a.v(), a.v());
   FF::to_mont(b.v(), b.v());
-  FF::store(re + e, (int)N, a.v());
-  FF::store(im + e, (int)N, b.v());
+  FF::copy(re + (size_t)(e) * L, a.v());
+  FF::copy(im + (size_t)(e) * L, b.v());
 }
 
 template <int L>
@@ -107,8 +107,8 @@ BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N,
   typedef F<L> FF;
   if (e >= count) return;
   Loc<L> a, b;
-  FF::load(a.v(), mkv(re + e, (int)N));
-  FF::load(b.v(), mkv(im + e, (int)N));
+  FF::copy(a.v(), (re + (size_t)(e) * L));
+  FF::copy(b.v(), (im + (size_t)(e) * L));
   FF::from_mont(a.v(), a.v());
   FF::from_mont(b.v(), b.v());
   limbs_to_be_bytes<L>(out + e * 2 * B, B, a.w);
@@ -133,7 +133,7 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
       uint32_t d = r[a.rbytes - 1 - win];
       if (d) {
         const uint32_t* ent = a.tabQ + ((size_t)win * 255 + (d - 1)) * 2 * L;
-        G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ent), mkv(ent + L), false, t0.v(), t1.v(), t2.v(), t3.v());
+        G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
       }
     }
   }
@@ -144,19 +144,19 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
     if (d) {
       const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
-      G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ent), mkv(ent + L), false, t0.v(), t1.v(), t2.v(), t3.v());
+      G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
     }
   }
   // negative plaintext: -(|x|*P + r*Q), the Sub(encryptZero(), Encrypt(|c|)) of poly.go:17-21
   if (neg) FF::neg(Y.v(), Y.v());
-  FF::store(a.X + e, (int)a.N, X.v());
-  FF::store(a.Y + e, (int)a.N, Y.v());
-  FF::store(a.Z + e, (int)a.N, Z.v());
+  FF::copy(a.X + (size_t)(e) * L, X.v());
+  FF::copy(a.Y + (size_t)(e) * L, Y.v());
+  FF::copy(a.Z + (size_t)(e) * L, Z.v());
 }
 
 // Jacobian -> affine with one inversion per thread (Montgomery's trick over
-// the elements g, g+G, g+2G, ... of thread g).  Output layout is stride-based
-// so the same kernel fills SoA arrays and AoS tables.
+// the elements g, g+G, g+2G, ... of thread g).  Output element e goes to
+// ox/oy + e*o_estride, so the same kernel fills x[]/y[] arrays and x||y tables.
 template <int L>
 BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
   typedef F<L> FF;
@@ -164,31 +164,31 @@ BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
   Loc<L> acc, z, zi, zz, t;
   FF::set_one(acc.v());
   for (size_t e = g; e < a.count; e += a.G) {
-    FF::load(z.v(), mkv(a.Z + e, (int)a.N));
+    FF::copy(z.v(), (a.Z + (size_t)(e) * L));
     if (FF::is_zero(z.v())) continue;
-    FF::store(a.scratch + e, (int)a.N, acc.v());
+    FF::copy(a.scratch + (size_t)(e) * L, acc.v());
     FF::mul(acc.v(), acc.v(), z.v());
   }
   FF::inv(acc.v(), acc.v(), t.v());
   size_t last = ((a.count - 1 - g) / a.G) * a.G + g;  // largest e = g (mod G) below count
   for (size_t e = last;; e -= a.G) {
-    FF::load(z.v(), mkv(a.Z + e, (int)a.N));
+    FF::copy(z.v(), (a.Z + (size_t)(e) * L));
     bool isinf = FF::is_zero(z.v());
     uint32_t* ox = a.ox + e * a.o_estride;
     uint32_t* oy = a.oy + e * a.o_estride;
     if (a.inf) a.inf[e] = isinf ? 1 : 0;
     if (isinf) {
-      FF::store_zero(ox, (int)a.o_lstride);
-      FF::store_zero(oy, (int)a.o_lstride);
+      FF::set_zero(ox);
+      FF::set_zero(oy);
     } else {
-      FF::mul(zi.v(), acc.v(), mkv(a.scratch + e, (int)a.N));  // 1/Z_e
+      FF::mul(zi.v(), acc.v(), (a.scratch + (size_t)(e) * L));  // 1/Z_e
       FF::mul(acc.v(), acc.v(), z.v());                          // drop Z_e from the running inverse
       FF::sqr(zz.v(), zi.v());
-      FF::mul(t.v(), zz.v(), mkv(a.X + e, (int)a.N));
-      FF::store(ox, (int)a.o_lstride, t.v());
+      FF::mul(t.v(), zz.v(), (a.X + (size_t)(e) * L));
+      FF::copy(ox, t.v());
       FF::mul(zz.v(), zz.v(), zi.v());
-      FF::mul(t.v(), zz.v(), mkv(a.Y + e, (int)a.N));
-      FF::store(oy, (int)a.o_lstride, t.v());
+      FF::mul(t.v(), zz.v(), (a.Y + (size_t)(e) * L));
+      FF::copy(oy, t.v());
     }
     if (e < (size_t)a.G) break;
   }
@@ -206,16 +206,16 @@ BGN_DEV void g1_add_body(const G1AddArgs& a, size_t e) {
     FF::set_zero(Y.v());
     FF::set_zero(Z.v());
   } else {
-    FF::load(X.v(), mkv(a.x1 + e1, (int)a.N1));
-    FF::load(Y.v(), mkv(a.y1 + e1, (int)a.N1));
+    FF::copy(X.v(), (a.x1 + (size_t)(e1) * L));
+    FF::copy(Y.v(), (a.y1 + (size_t)(e1) * L));
     FF::set_one(Z.v());
   }
   if (!a.inf2[e])
-    G<L>::madd(X.v(), Y.v(), Z.v(), mkv(a.x2 + e, (int)a.N2), mkv(a.y2 + e, (int)a.N2), a.subtract != 0, t0.v(),
+    G<L>::madd(X.v(), Y.v(), Z.v(), (a.x2 + (size_t)(e) * L), (a.y2 + (size_t)(e) * L), a.subtract != 0, t0.v(),
                t1.v(), t2.v(), t3.v());
-  FF::store(a.X + e, (int)a.N, X.v());
-  FF::store(a.Y + e, (int)a.N, Y.v());
-  FF::store(a.Z + e, (int)a.N, Z.v());
+  FF::copy(a.X + (size_t)(e) * L, X.v());
+  FF::copy(a.Y + (size_t)(e) * L, Y.v());
+  FF::copy(a.Z + (size_t)(e) * L, Z.v());
 }
 
 // MultConst on L1: k*C, per-element big-endian scalar (bgn.go:258)
@@ -228,8 +228,8 @@ BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
   FF::set_zero(Y.v());
   FF::set_zero(Z.v());
   if (!a.inf[e]) {
-    FF::load(ax.v(), mkv(a.x + e, (int)a.Nin));
-    FF::load(ay.v(), mkv(a.y + e, (int)a.Nin));
+    FF::copy(ax.v(), (a.x + (size_t)(e) * L));
+    FF::copy(ay.v(), (a.y + (size_t)(e) * L));
     const uint8_t* k = a.k_be + e * a.kbytes;
     bool started = false;  // leading zero bits: doubling O is a no-op
     for (int i = 0; i < a.kbytes; i++) {
@@ -237,15 +237,15 @@ BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
       for (int bit = 7; bit >= 0; bit--) {
         if (started) G<L>::dbl(X.v(), Y.v(), Z.v(), t0.v(), t1.v(), t2.v(), t3.v());
         if ((byte >> bit) & 1) {
-          G<L>::madd(X.v(), Y.v(), Z.v(), mkv(ax.w), mkv(ay.w), false, t0.v(), t1.v(), t2.v(), t3.v());
+          G<L>::madd(X.v(), Y.v(), Z.v(), ax.w, ay.w, false, t0.v(), t1.v(), t2.v(), t3.v());
           started = true;
         }
       }
     }
   }
-  FF::store(a.X + e, (int)a.N, X.v());
-  FF::store(a.Y + e, (int)a.N, Y.v());
-  FF::store(a.Z + e, (int)a.N, Z.v());
+  FF::copy(a.X + (size_t)(e) * L, X.v());
+  FF::copy(a.Y + (size_t)(e) * L, Y.v());
+  FF::copy(a.Z + (size_t)(e) * L, Z.v());
 }
 
 // table construction -----------------------------------------------------
@@ -260,9 +260,9 @@ BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, ui
   FF::copy(y.v(), by);
   FF::set_one(z.v());
   for (int win = 0; win < nwin; win++) {
-    FF::store(X + win, (int)N, x.v());
-    FF::store(Y + win, (int)N, y.v());
-    FF::store(Z + win, (int)N, z.v());
+    FF::copy(X + (size_t)(win) * L, x.v());
+    FF::copy(Y + (size_t)(win) * L, y.v());
+    FF::copy(Z + (size_t)(win) * L, z.v());
     for (int i = 0; i < 8; i++) G<L>::dbl(x.v(), y.v(), z.v(), t0.v(), t1.v(), t2.v(), t3.v());
   }
 }
@@ -279,12 +279,12 @@ BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t
   FF::set_zero(z.v());
   for (int d = 1; d <= 255; d++) {
     if (!ainf[win])
-      G<L>::madd(x.v(), y.v(), z.v(), mkv(ax + win, (int)Nb), mkv(ay + win, (int)Nb), false, t0.v(), t1.v(), t2.v(),
+      G<L>::madd(x.v(), y.v(), z.v(), (ax + (size_t)(win) * L), (ay + (size_t)(win) * L), false, t0.v(), t1.v(), t2.v(),
                  t3.v());
     size_t o = (size_t)win * 255 + (d - 1);
-    FF::store(X + o, (int)N, x.v());
-    FF::store(Y + o, (int)N, y.v());
-    FF::store(Z + o, (int)N, z.v());
+    FF::copy(X + (size_t)(o) * L, x.v());
+    FF::copy(Y + (size_t)(o) * L, y.v());
+    FF::copy(Z + (size_t)(o) * L, z.v());
   }
 }
 
@@ -294,15 +294,15 @@ BGN_DEV void gt_mul_body(const GtBinArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
   Loc<L> a0, a1, b0, b1, t0, t1, t2;
-  FF::load(a0.v(), mkv(a.are + e, (int)a.Na));
-  FF::load(a1.v(), mkv(a.aim + e, (int)a.Na));
-  FF::load(b0.v(), mkv(a.bre + e, (int)a.Nb));
-  FF::load(b1.v(), mkv(a.bim + e, (int)a.Nb));
+  FF::copy(a0.v(), (a.are + (size_t)(e) * L));
+  FF::copy(a1.v(), (a.aim + (size_t)(e) * L));
+  FF::copy(b0.v(), (a.bre + (size_t)(e) * L));
+  FF::copy(b1.v(), (a.bim + (size_t)(e) * L));
   if (a.conj_b) FF::neg(b1.v(), b1.v());
   E2 r = mke2(a0.v(), a1.v());
   FF::mul2(r, r, mke2(b0.v(), b1.v()), t0.v(), t1.v(), t2.v());
-  FF::store(a.ore + e, (int)a.N, r.re);
-  FF::store(a.oim + e, (int)a.N, r.im);
+  FF::copy(a.ore + (size_t)(e) * L, r.re);
+  FF::copy(a.oim + (size_t)(e) * L, r.im);
 }
 
 template <int L>
@@ -311,8 +311,8 @@ BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
   if (e >= a.count) return;
   Loc<L> a0, a1, r0, r1, t0, t1, t2;
   E2 in = mke2(a0.v(), a1.v()), r = mke2(r0.v(), r1.v());
-  FF::load(in.re, mkv(a.re + e, (int)a.Nin));
-  FF::load(in.im, mkv(a.im + e, (int)a.Nin));
+  FF::copy(in.re, (a.re + (size_t)(e) * L));
+  FF::copy(in.im, (a.im + (size_t)(e) * L));
   if (a.mode == 1) {
     GT<L>::pow_fixed(r, in, t0.v(), t1.v(), t2.v());
   } else if (a.mode == 2) {
@@ -321,8 +321,8 @@ BGN_DEV void gt_pow_body(const GtPowArgs& a, size_t e) {
     GT<L>::pow_var(r, in, a.e_be + e * a.ebytes, a.ebytes, t0.v(), t1.v(), t2.v());
     if (a.mode == 3) FF::neg(r.im, r.im);
   }
-  FF::store(a.ore + e, (int)a.N, r.re);
-  FF::store(a.oim + e, (int)a.N, r.im);
+  FF::copy(a.ore + (size_t)(e) * L, r.re);
+  FF::copy(a.oim + (size_t)(e) * L, r.im);
 }
 
 // One pass of the GT product tree of an L2 sum (bgn.go:460 folded over terms):
@@ -339,12 +339,12 @@ BGN_DEV void gt_reduce_body(const uint32_t* re, const uint32_t* im, size_t Nin, 
   FF::set_one2(acc);
   for (size_t t = g; t < nterms; t += G) {
     size_t e = t * ncoeff + c;
-    FF::load(b.re, mkv(re + e, (int)Nin));
-    FF::load(b.im, mkv(im + e, (int)Nin));
+    FF::copy(b.re, (re + (size_t)(e) * L));
+    FF::copy(b.im, (im + (size_t)(e) * L));
     FF::mul2(acc, acc, b, t0.v(), t1.v(), t2.v());
   }
-  FF::store(ore + id, (int)N, acc.re);
-  FF::store(oim + id, (int)N, acc.im);
+  FF::copy(ore + (size_t)(id) * L, acc.re);
+  FF::copy(oim + (size_t)(id) * L, acc.im);
 }
 
 // ------------------------------------------------------------ BSGS (gsbs.go)
@@ -402,8 +402,8 @@ BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
   Loc<L> p0, p1, n0, n1, gi0, gi1, c0, c1, t0, t1, t2;
-  FF::load(p0.v(), mkv(a.re + e, (int)a.Nin));
-  FF::load(p1.v(), mkv(a.im + e, (int)a.Nin));
+  FF::copy(p0.v(), (a.re + (size_t)(e) * L));
+  FF::copy(p1.v(), (a.im + (size_t)(e) * L));
   // identity => 0 (recoverMessage, bgn.go:359-363)
   if (FF::is_one(p0.v()) && FF::is_zero(p1.v())) {
     a.out[e] = 0;
@@ -542,5 +542,40 @@ __global__ void __launch_bounds__(128) k_mulmod_bench(uint32_t* io, size_t N, in
     for (int j = 0; j < L; j++) a[0][j] ^= a[c][j];
 #pragma unroll
   for (int j = 0; j < L; j++) io[(size_t)j * N + e] = a[0][j];
+}
+// The same products through the memory-operand primitives (F<L>::mul etc. on shared-memory slots,
+// laid out as in k_miller): mode 10 = mul only, 11 = the line_mul sequence (5 mul + 6 add/sub),
+// 12 = sqr2, 13 = dbl_line.  Counts `iters` sequences per thread; used by tools/microbench.py to
+// separate call / load-store / add-sub overhead from the register-resident product.
+template <int L>
+__global__ void __launch_bounds__(256, 1) k_prim_bench(uint32_t* io, size_t N, int iters, int mode) {
+  extern __shared__ uint32_t smem_dyn[];
+  typedef F<L> FF;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  auto slot = [&](int k) -> E { return smem_dyn + ((size_t)k * nt + tid) * L; };
+  size_t e = BGN_GID(size_t);
+  for (int k = 0; k < 13; k++) {
+    for (int j = 0; j < L; j++) slot(k)[j] = io[(size_t)j * N + e];
+    slot(k)[0] += k;
+  }
+  for (int i = 0; i < iters; i++) {
+    if (mode == 10) {
+      FF::mul_stream(slot(0), slot(0), slot(1));
+    } else if (mode == 20) {
+      FF::mul(slot(0), slot(0), slot(1));
+    } else if (mode == 22) {
+      FF::mul_pair(slot(0), slot(0), slot(1), slot(2), slot(2), slot(3));
+    } else if (mode == 11) {
+      FF::line_mul(mke2(slot(0), slot(1)), slot(7), slot(8), slot(9), slot(4), slot(5), slot(10), slot(11),
+                   slot(12));
+    } else if (mode == 12) {
+      FF::sqr2(mke2(slot(0), slot(1)), mke2(slot(0), slot(1)), slot(10), slot(11));
+    } else {
+      G<L>::dbl_line(slot(4), slot(5), slot(6), slot(7), slot(8), slot(9), slot(10), slot(11), slot(12));
+    }
+  }
+  FF::add(slot(0), slot(0), slot(4));
+  FF::add(slot(0), slot(0), slot(1));
+  for (int j = 0; j < L; j++) io[(size_t)j * N + e] = slot(0)[j];
 }
 #endif  // !BGN_HOSTSIM

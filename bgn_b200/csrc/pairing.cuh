@@ -137,8 +137,8 @@ struct MillerTeam {
       bool inf = a.Minf[idx] != 0;
       flagsA()[tid] = inf ? 0 : 1;
       if (!inf) {
-        FF::load(slot(tid, S_X), mkv(a.Mx + idx, a.NM));
-        FF::load(slot(tid, S_Y), mkv(a.My + idx, a.NM));
+        FF::copy(slot(tid, S_X), (a.Mx + (size_t)(idx) * L));
+        FF::copy(slot(tid, S_Y), (a.My + (size_t)(idx) * L));
         FF::set_one(slot(tid, S_Z));
       }
     }
@@ -159,7 +159,7 @@ struct MillerTeam {
                      t0, t1, t2);
       } else {
         size_t idx = (size_t)unit * a.dM + t;
-        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), mkv(a.Mx + idx, a.NM), mkv(a.My + idx, a.NM),
+        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), (a.Mx + (size_t)(idx) * L), (a.My + (size_t)(idx) * L),
                       op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), t0, t1, t2);
       }
     }
@@ -180,8 +180,8 @@ struct MillerTeam {
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
       size_t ei = eidx(k);
-      FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), mkv(a.Ex + ei, a.NE),
-                   mkv(a.Ey + ei, a.NE), t0, t1, t2);
+      FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), (a.Ex + (size_t)(ei) * L),
+                   (a.Ey + (size_t)(ei) * L), t0, t1, t2);
     }
   }
 
@@ -195,14 +195,14 @@ struct MillerTeam {
       // the Miller point of this thread is dead by now: scratch for the exponentiation
       GT<L>::final_exp(f, mke2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2));
       size_t o = (size_t)unit * a.out_slots + j;
-      FF::store(a.out_re + o, a.NOUT, f.re);
-      FF::store(a.out_im + o, a.NOUT, f.im);
+      FF::copy(a.out_re + o * L, f.re);
+      FF::copy(a.out_im + o * L, f.im);
     }
     if (t == 0) {
       for (int j = nslots; j < a.out_slots; j++) {  // padding slot(s): GT identity (poly.go:130-137)
         size_t o = (size_t)unit * a.out_slots + j;
-        FF::store_one(a.out_re + o, a.NOUT);
-        FF::store_zero(a.out_im + o, a.NOUT);
+        FF::set_one(a.out_re + (size_t)(o) * L);
+        FF::set_zero(a.out_im + (size_t)(o) * L);
       }
     }
   }

@@ -26,13 +26,13 @@ struct PairConsts {
 
 #define BGN_MILLER_NSLOT 13  // shared-memory F_p slots per thread of the Miller team kernel
 struct MillerArgs {
-  const uint32_t* Mx;  // Miller-side points, Montgomery SoA [L][NM], index unit*dM + i
+  const uint32_t* Mx;  // Miller-side points, Montgomery [L][NM], index unit*dM + i
   const uint32_t* My;
   const uint8_t* Minf;  // 1 = point at infinity
   const uint32_t* Ex;   // evaluation-side points, SoA [L][NE], index unit*dE + k
   const uint32_t* Ey;
   const uint8_t* Einf;
-  uint32_t* out_re;  // GT out, Montgomery SoA [L][NOUT], index unit*out_slots + j
+  uint32_t* out_re;  // GT out, Montgomery [L][NOUT], index unit*out_slots + j
   uint32_t* out_im;
   int NM, NE, NOUT;
   int e_bcast;      // evaluation side is ONE polynomial shared by all units (makeL2: B = P)
@@ -50,13 +50,13 @@ struct EncArgs {
   int rbytes;
   const uint32_t* tabP;   // 8 windows
   const uint32_t* tabQ;   // rbytes windows
-  uint32_t *X, *Y, *Z;    // Jacobian out, SoA [L][N]
+  uint32_t *X, *Y, *Z;    // Jacobian out, [N][L]
   size_t count, N;
 };
 
 struct NormArgs {
-  const uint32_t *X, *Y, *Z;  // SoA [L][N]
-  uint32_t* scratch;          // SoA [L][N] prefix products
+  const uint32_t *X, *Y, *Z;  // [N][L]
+  uint32_t* scratch;          // [N][L] prefix products
   size_t count, N;
   int G;                      // number of worker threads
   uint32_t* ox;               // out x: element e, limb j at ox[e*o_estride + j*o_lstride]

@@ -166,12 +166,12 @@ class Sim:
     # ---- conversions between Python integers and Montgomery SoA
     def soa(self, vals: Sequence[int], mont: bool = True) -> np.ndarray:
         n = max(1, len(vals))
-        a = np.zeros((self.L, n), dtype=np.uint32)
+        a = np.zeros((n, self.L), dtype=np.uint32)  # array of elements: [N][L]
         for e, v in enumerate(vals):
             if mont:
                 v = v * self.R % self.p
             for j in range(self.L):
-                a[j, e] = (v >> (32 * j)) & 0xFFFFFFFF
+                a[e, j] = (v >> (32 * j)) & 0xFFFFFFFF
         return a
 
     def unsoa(self, a: np.ndarray, count: int, mont: bool = True) -> List[int]:
@@ -179,7 +179,7 @@ class Sim:
         for e in range(count):
             v = 0
             for j in range(self.L):
-                v |= int(a[j, e]) << (32 * j)
+                v |= int(a[e, j]) << (32 * j)
             out.append(v * self.Rinv % self.p if mont else v)
         return out
 
@@ -194,10 +194,10 @@ class Sim:
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
         nout = count * out_slots
-        ore = np.zeros((self.L, nout), dtype=np.uint32)
-        oim = np.zeros((self.L, nout), dtype=np.uint32)
-        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), Mx.shape[1],
-                       Ex.shape[1], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
+        ore = np.zeros((nout, self.L), dtype=np.uint32)
+        oim = np.zeros((nout, self.L), dtype=np.uint32)
+        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), Mx.shape[0],
+                       Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
                        teams_per_block * dE + 1, 0)  # one idle thread per group: exercises the inactive path
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
@@ -214,13 +214,13 @@ class Sim:
         return self.miller(A, 1, Bp, 1, len(A), 1, teams_per_block=3)
 
     def normalize(self, X, Y, Z, count, G=None):
-        N = X.shape[1]
+        N = X.shape[0]
         scratch = np.zeros_like(X)
         ox = np.zeros_like(X)
         oy = np.zeros_like(X)
         inf = np.zeros(max(1, count), dtype=np.uint8)
         G = G or max(1, min(count, 3))
-        a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), count, N, G, P32(ox), P32(oy), 1, N, P8(inf))
+        a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), count, N, G, P32(ox), P32(oy), self.L, 1, P8(inf))
         assert lib().hs_normalize(self.L, C.byref(a)) == 0
         xs, ys = self.unsoa(ox, count), self.unsoa(oy, count)
         return [None if inf[e] else (xs[e], ys[e]) for e in range(count)]
@@ -228,14 +228,14 @@ class Sim:
     def build_table(self, base, nwin):
         L = self.L
         bx, by = self.soa([base[0]]), self.soa([base[1]])
-        X = np.zeros((L, nwin), dtype=np.uint32)
+        X = np.zeros((nwin, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
         assert lib().hs_tab_bases(L, P32(bx), P32(by), nwin, P32(X), P32(Y), P32(Z), nwin) == 0
         bases = self.normalize(X, Y, Z, nwin)
         ax, ay, ainf = self.g1_arrays(bases)
         nent = nwin * 255
-        X = np.zeros((L, nent), dtype=np.uint32)
+        X = np.zeros((nent, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
         assert lib().hs_tab_fill(L, P32(ax), P32(ay), P8(ainf), nwin, nwin, P32(X), P32(Y), P32(Z), nent) == 0
@@ -248,7 +248,7 @@ class Sim:
     def encrypt(self, xs, rs, tabP, tabQ):
         count = len(xs)
         x = np.array(xs, dtype=np.int64)
-        X = np.zeros((self.L, count), dtype=np.uint32)
+        X = np.zeros((max(1, count), self.L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
         if rs is None:
@@ -265,10 +265,10 @@ class Sim:
         count = len(Bp)
         x1, y1, i1 = self.g1_arrays(A)
         x2, y2, i2 = self.g1_arrays(Bp)
-        X = np.zeros((self.L, count), dtype=np.uint32)
+        X = np.zeros((max(1, count), self.L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
-        a = G1AddArgs(P32(x1), P32(y1), P8(i1), P32(x2), P32(y2), P8(i2), x1.shape[1], x2.shape[1],
+        a = G1AddArgs(P32(x1), P32(y1), P8(i1), P32(x2), P32(y2), P8(i2), x1.shape[0], x2.shape[0],
                       1 if bcast1 else 0, 1 if subtract else 0, P32(X), P32(Y), P32(Z), count, count)
         assert lib().hs_g1_add(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
@@ -277,10 +277,10 @@ class Sim:
         count = len(A)
         x, y, inf = self.g1_arrays(A)
         kb = np.frombuffer(b"".join(int(k).to_bytes(kbytes, "big") for k in ks), dtype=np.uint8).copy()
-        X = np.zeros((self.L, count), dtype=np.uint32)
+        X = np.zeros((max(1, count), self.L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
-        a = G1MulArgs(P32(x), P32(y), P8(inf), x.shape[1], P8(kb), kbytes, P32(X), P32(Y), P32(Z), count, count)
+        a = G1MulArgs(P32(x), P32(y), P8(inf), x.shape[0], P8(kb), kbytes, P32(X), P32(Y), P32(Z), count, count)
         assert lib().hs_g1_mulvar(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
 
@@ -311,9 +311,9 @@ class Sim:
 
     def gt_reduce(self, vals, nterms, ncoeff, G):
         re, im = self.gt_arrays(vals)
-        ore = np.zeros((self.L, G * ncoeff), dtype=np.uint32)
+        ore = np.zeros((G * ncoeff, self.L), dtype=np.uint32)
         oim = np.zeros_like(ore)
-        assert lib().hs_gt_reduce(self.L, P32(re), P32(im), re.shape[1], nterms, ncoeff, G, P32(ore), P32(oim),
+        assert lib().hs_gt_reduce(self.L, P32(re), P32(im), re.shape[0], nterms, ncoeff, G, P32(ore), P32(oim),
                                   G * ncoeff) == 0
         return list(zip(self.unsoa(ore, G * ncoeff), self.unsoa(oim, G * ncoeff)))
 
@@ -326,14 +326,14 @@ class Sim:
         hs = 1
         while hs < 2 * S:
             hs <<= 1
-        gen = np.concatenate([self.soa([gsk[0]])[:, 0], self.soa([gsk[1]])[:, 0]]).astype(np.uint32)
+        gen = np.concatenate([self.soa([gsk[0]])[0], self.soa([gsk[1]])[0]]).astype(np.uint32)
         self.bs_elems = np.zeros(S * 2 * L, dtype=np.uint32)
         self.bs_slots = np.zeros(hs, dtype=np.uint32)
         a = BsgsBuildArgs(P32(gen), P32(self.bs_elems), P32(self.bs_slots), hs - 1, S, 7)
         assert lib().hs_bsgs_build(L, C.byref(a)) == 0
         from oracle import bgn_oracle as O
         gi = O.fp2_conj(O.fp2_pow(gsk, S, p), p)
-        self.bs_ginv = np.concatenate([self.soa([gi[0]])[:, 0], self.soa([gi[1]])[:, 0]]).astype(np.uint32)
+        self.bs_ginv = np.concatenate([self.soa([gi[0]])[0], self.soa([gi[1]])[0]]).astype(np.uint32)
         self.bs_S, self.bs_hmask = S, hs - 1
         self.bs_giant = (self.mmax + S - 1) // S
 
@@ -351,7 +351,7 @@ class Sim:
     # ---- byte formats
     def g1_from_bytes(self, data: bytes, count: int):
         buf = np.frombuffer(data, dtype=np.uint8).copy()
-        x = np.zeros((self.L, count), dtype=np.uint32)
+        x = np.zeros((count, self.L), dtype=np.uint32)
         y = np.zeros_like(x)
         inf = np.zeros(count, dtype=np.uint8)
         assert lib().hs_g1_from_bytes(self.L, P8(buf), self.B, count, P32(x), P32(y), P8(inf), count) == 0
@@ -362,7 +362,7 @@ class Sim:
         count = len(pts)
         x, y, inf = self.g1_arrays(pts)
         out = np.zeros(count * 2 * self.B, dtype=np.uint8)
-        assert lib().hs_g1_to_bytes(self.L, P32(x), P32(y), P8(inf), x.shape[1], count, P8(out), self.B) == 0
+        assert lib().hs_g1_to_bytes(self.L, P32(x), P32(y), P8(inf), x.shape[0], count, P8(out), self.B) == 0
         return out.tobytes()
 
     def gt_roundtrip_bytes(self, vals) -> bytes:

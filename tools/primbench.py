@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Memory-operand primitive microbenchmarks (k_prim_bench) at L = 17: fraction of the IMAD.WIDE
+peak reached by mul-only, line_mul, sqr2 and dbl_line sequences at several occupancies."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bgn_b200 import Engine, bench_imad_peak, workmodel
+
+g = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kb512.json")))
+e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+ms, ipt = bench_imad_peak(0, 4096, 148 * 8, 256)
+peak = 148 * 8 * 256 * ipt / (ms * 1e-3)
+MM = {1: 1, 10: 1, 11: 5, 12: 2, 13: 12, 20: 1, 22: 2}
+MODES = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 10, 11, 12, 13]
+for mode in MODES:
+    for threads in (128, 256):
+        if mode == 1 and threads > 128:
+            continue
+        iters = 400
+        ms = e.bench_mulmod(mode, iters, 148, threads)
+        mm = 148 * threads * iters * MM[mode] / (ms * 1e-3)
+        print("mode %2d threads %3d  %.2f Gmodmul/s  frac %.3f" % (mode, threads, mm / 1e9, mm * 595 / peak))
