@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbgn_b200.so")
+LIB_PATH = os.environ.get("BGN_B200_LIB") or os.path.join(HERE, "libbgn_b200.so")  # env: developer A/B builds
 
 BGN_OK, BGN_E_BADARG, BGN_E_CUDA, BGN_E_NOTSETUP, BGN_E_NOMEM, BGN_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

@@ -526,7 +526,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
     int L = 0;
     for (int cand : kSupportedL)
-      if (32 * cand >= pbits + 7) {
+      if (32 * cand >= pbits + 8) {
         L = cand;
         break;
       }
@@ -594,6 +594,13 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     Big p2(L);
     big_add(p2, p, p);
     for (int i = 0; i < L; i++) c->fc.p2[i] = p2[i];
+    {
+      Big p4(L), p8(L), p16(L);
+      big_add(p4, p2, p2);
+      big_add(p8, p4, p4);
+      big_add(p16, p8, p8);
+      for (int i = 0; i < L; i++) c->fc.p4[i] = p4[i], c->fc.p8[i] = p8[i], c->fc.p16[i] = p16[i];
+    }
     Big x(L, 0);
     x[0] = 1;
     for (int i = 0; i < 32 * L; i++) big_dbl_mod(x, p);
@@ -1215,7 +1222,7 @@ int bgn_bench_mulmod(bgn_ctx* c, int ilp, int iters, int blocks, int threads, fl
     CK(cudaEventCreate(&b));
     auto launch = [&](int it) {
       c->total_launches++;
-      if (ilp != 1 && ilp != 2 && (ilp < 10 || ilp > 29)) throw ArgErr{"ilp must be 1, 2 or a primitive mode 10..13"};
+      if (ilp != 1 && ilp != 2 && (ilp < 10 || ilp > 79)) throw ArgErr{"ilp must be 1, 2 or a primitive mode 10..79"};
       c->A->mulmod_bench(cfg(c, blocks, threads, 0), ilp, io, N, it);
     };
     launch(4);  // warm-up

@@ -25,10 +25,44 @@
 #define BGN_DEVNI
 #define BGN_CONST static
 #define BGN_UNROLL
+#define BGN_UNROLL1
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <unordered_map>
 namespace bgnsim {
 static thread_local uint32_t cc = 0;
 static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
+// Range tracker (tests only): every element written by the arithmetic below carries an upper
+// bound in multiples of p, keyed by its address, so the CPU run of the device programs PROVES
+// (by worst-case interval propagation, not by the sampled values) that the relaxed-range code
+// never overflows a product and never lets a difference go negative.
+static std::unordered_map<const void*, double> bnd;
+static double headroom = 128.0;  // floor(2^(32L) / p), set with the constants
+static double max_bound = 0.0;   // largest bound ever attached (reported to the tests)
+static uint64_t unknown = 0;     // reads of untracked addresses (treated as < 2p)
+static uint64_t violations = 0;
+inline double getb(const void* a) {
+  auto it = bnd.find(a);
+  if (it == bnd.end()) {
+    unknown++;
+    return 2.0;
+  }
+  return it->second;
 }
+inline void setb(const void* a, double b) {
+  bnd[a] = b;
+  if (b > max_bound) max_bound = b;
+}
+inline void check(bool ok, const char* what) {
+  if (!ok) {
+    if (violations++ < 10) fprintf(stderr, "bgnsim: range violation: %s\n", what);
+  }
+}
+}
+#define BGN_SETB(a, b) bgnsim::setb((const void*)(a), (b))
+#define BGN_GETB(a) bgnsim::getb((const void*)(a))
+#define BGN_CHECK(c, w) bgnsim::check((c), (w))
 BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t t = (uint64_t)a * b;
   lo = (uint32_t)t;
@@ -79,10 +113,14 @@ BGN_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) {
   r = a - b - bgnsim::cc;
 }
 #else
+#define BGN_SETB(a, b)
+#define BGN_GETB(a) 0.0
+#define BGN_CHECK(c, w)
 #define BGN_DEV __device__ __forceinline__
 #define BGN_DEVNI __device__ __noinline__
 #define BGN_CONST __constant__
 #define BGN_UNROLL _Pragma("unroll")
+#define BGN_UNROLL1 _Pragma("unroll 1")
 BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
@@ -133,6 +171,17 @@ struct Fp {
   static constexpr int KE = (L + 1) / 2;       // even-index limbs of an operand
   static constexpr int KO = L / 2;             // odd-index limbs
 
+#ifdef BGN_HOSTSIM
+  static void trk_mul(const void* r, const void* a, const void* b) {
+    double A = BGN_GETB(a), B = BGN_GETB(b);
+    BGN_CHECK(A + 1.0 <= bgnsim::headroom && B <= bgnsim::headroom, "product operand too large");
+    BGN_SETB(r, A * B / bgnsim::headroom + 1.0);
+    bgnsim::nmul++;
+  }
+#else
+  BGN_DEV static void trk_mul(const void*, const void*, const void*) {}
+#endif
+
   // one CIOS row: acc += a*s (then caller reduces).  X is the array aligned at
   // limb 0, Y sits one limb higher; on entry (not FIRST) Y is the previous
   // row's X whose limb 0 is zero and whose limb 1 is the pending carry limb.
@@ -175,9 +224,7 @@ struct Fp {
   // r = a*b/R mod p, r in [0,2p) for a,b in [0,2p).  2L^2+L products.
   BGN_DEV static void mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
     uint32_t X[W], Y[W];
-#ifdef BGN_HOSTSIM
-    bgnsim::nmul++;
-#endif
+    trk_mul(r, a, b);
     const uint32_t* pm = c_fc.p;
     const uint32_t np0 = c_fc.np0;
     row<true>(X, Y, a, b[0], pm, np0);
@@ -198,9 +245,7 @@ struct Fp {
   // never occupies registers and its loads overlap the previous rows.
   BGN_DEV static void mul_stream(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
     uint32_t X[W], Y[W];
-#ifdef BGN_HOSTSIM
-    bgnsim::nmul++;
-#endif
+    trk_mul(r, a, bp);
     const uint32_t* pm = c_fc.p;
     const uint32_t np0 = c_fc.np0;
     row<true>(X, Y, a, bp[0], pm, np0);
@@ -222,9 +267,8 @@ struct Fp {
   BGN_DEV static void mul_pair(uint32_t (&r1)[L], const uint32_t (&a1)[L], const uint32_t* b1, uint32_t (&r2)[L],
                                const uint32_t (&a2)[L], const uint32_t* b2) {
     uint32_t X1[W], Y1[W], X2[W], Y2[W];
-#ifdef BGN_HOSTSIM
-    bgnsim::nmul += 2;
-#endif
+    trk_mul(r1, a1, b1);
+    trk_mul(r2, a2, b2);
     const uint32_t* pm = c_fc.p;
     const uint32_t np0 = c_fc.np0;
     row<true>(X1, Y1, a1, b1[0], pm, np0);
@@ -247,6 +291,96 @@ struct Fp {
     }
   }
 
+  // Same product as mul_stream with the rows in a NON-unrolled loop of 2U rows per iteration (the
+  // accumulators swap roles every row and move down one register pair every two rows, which a
+  // loop pays for with ~2L register moves per iteration; unrolled code renames for free): 1 + 2U
+  // rows of code instead of L, so many products can be fused into one routine without leaving the
+  // instruction cache.  The multiplicand a stays in registers, the multiplier is read from memory
+  // row by row (dynamic index).
+  template <int U>
+  BGN_DEV static void mul_loop(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
+    uint32_t X[W], Y[W];
+    trk_mul(r, a, bp);
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    constexpr int NI = (L - 1) / (2 * U);  // whole iterations
+    constexpr int T0 = 1 + NI * 2 * U;     // first row of the unrolled tail
+    row<true>(X, Y, a, bp[0], pm, np0);
+    if (NI > 0) {
+      const uint32_t* q = bp + 1;
+      BGN_UNROLL1
+      for (int it = 0; it < NI; it++) {
+        BGN_UNROLL
+        for (int k = 0; k < U; k++) {
+          row<false>(Y, X, a, q[2 * k], pm, np0);
+          row<false>(X, Y, a, q[2 * k + 1], pm, np0);
+        }
+        q += 2 * U;
+      }
+    }
+    BGN_UNROLL
+    for (int i = T0; i + 1 < L; i += 2) {
+      row<false>(Y, X, a, bp[i], pm, np0);
+      row<false>(X, Y, a, bp[i + 1], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row<false>(Y, X, a, bp[L - 1], pm, np0);
+      merge(r, X, Y);
+    } else {
+      merge(r, Y, X);
+    }
+  }
+
+  // ---- relaxed-range helpers (fused.cuh): values are bounded multiples of p far below
+  // R = 2^(32L) >= 256 p, so sums need no reduction and differences only a fixed offset K*p
+  // that keeps them non-negative; the product absorbs the slack: a < A p, b < B p gives
+  // a*b/R mod p < (A*B/256 + 1) p.  tests/hostsim tracks the bounds of every value.
+  BGN_DEV static void addn(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+#ifdef BGN_HOSTSIM
+    {
+      double s = BGN_GETB(a) + BGN_GETB(b);
+      BGN_CHECK(s <= bgnsim::headroom, "sum too large");
+      BGN_SETB(r, s);
+    }
+#endif
+    add_cc(r[0], a[0], b[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(r[j], a[j], b[j]);
+    addc(r[L - 1], a[L - 1], b[L - 1]);
+  }
+  // r = a - b + K p, kp = the limbs of K p (K in {2, 4, 8, 16}); requires b <= K p
+  BGN_DEV static void subk(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t* kp, int K) {
+#ifdef BGN_HOSTSIM
+    {
+      double A = BGN_GETB(a), B = BGN_GETB(b);
+      BGN_CHECK(B <= (double)K, "difference may go negative");
+      BGN_CHECK(A + K <= bgnsim::headroom, "difference too large");
+      BGN_SETB(r, A + K);
+    }
+#endif
+    uint32_t t[L];
+    add_cc(t[0], a[0], kp[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(t[j], a[j], kp[j]);
+    addc(t[L - 1], a[L - 1], kp[L - 1]);
+    sub_cc(r[0], t[0], b[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) subc_cc(r[j], t[j], b[j]);
+    subc(r[L - 1], t[L - 1], b[L - 1]);
+  }
+
+  // r = K p - a; requires a <= K p
+  BGN_DEV static void negk(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* kp, int K) {
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) <= (double)K, "negation may go negative");
+    BGN_SETB(r, (double)K);
+#endif
+    sub_cc(r[0], kp[0], a[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) subc_cc(r[j], kp[j], a[j]);
+    subc(r[L - 1], kp[L - 1], a[L - 1]);
+  }
+
   // after the final row with roles (X=aligned, Y=offset): result = Y + (X >> 32)
   BGN_DEV static void merge(uint32_t (&r)[L], const uint32_t (&A)[W], const uint32_t (&B)[W]) {
     add_cc(r[0], A[0], B[1]);
@@ -260,6 +394,10 @@ struct Fp {
   // r = a + b, kept in [0,2p)
   BGN_DEV static void add(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
     uint32_t t[L], u[L];
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) + BGN_GETB(b) <= 4.0, "reduced add expects operands below 2p");
+    BGN_SETB(r, 2.0);
+#endif
     add_cc(t[0], a[0], b[0]);
     BGN_UNROLL
     for (int j = 1; j < L - 1; j++) addc_cc(t[j], a[j], b[j]);
@@ -282,6 +420,10 @@ struct Fp {
   // r = a - b, kept in [0,2p)
   BGN_DEV static void sub(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
     uint32_t t[L], mask;
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) <= 2.0 && BGN_GETB(b) <= 2.0, "reduced sub expects operands below 2p");
+    BGN_SETB(r, 2.0);
+#endif
     sub_cc(t[0], a[0], b[0]);
     BGN_UNROLL
     for (int j = 1; j < L; j++) subc_cc(t[j], a[j], b[j]);
@@ -295,6 +437,10 @@ struct Fp {
   // canonical representative in [0,p) of a value in [0,2p]
   BGN_DEV static void canon(uint32_t (&r)[L], const uint32_t (&a)[L]) {
     uint32_t t[L], u[L], bw;
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) <= 2.0, "canon expects an operand of at most 2p");
+    BGN_SETB(r, 1.0);
+#endif
     sub_cc(t[0], a[0], c_fc.p[0]);
     BGN_UNROLL
     for (int j = 1; j < L; j++) subc_cc(t[j], a[j], c_fc.p[j]);

@@ -28,11 +28,13 @@ typedef uint32_t* E;
 
 template <int L>
 BGN_DEV void ld(uint32_t (&r)[L], const uint32_t* a) {
+  BGN_SETB(r, BGN_GETB(a));
   BGN_UNROLL
   for (int j = 0; j < L; j++) r[j] = a[j];
 }
 template <int L>
 BGN_DEV void st(E a, const uint32_t (&r)[L]) {
+  BGN_SETB(a, BGN_GETB(r));
   BGN_UNROLL
   for (int j = 0; j < L; j++) a[j] = r[j];
 }
@@ -105,6 +107,7 @@ struct F {
   BGN_DEV static void dbl(E r, const uint32_t* a) { add(r, a, a); }
   BGN_DEVNI static void neg(E r, const uint32_t* a) {
     uint32_t x[L], y[L], z[L];
+    BGN_SETB(x, 0.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) x[j] = 0;
     ld<L>(y, a);
@@ -112,14 +115,17 @@ struct F {
     st<L>(r, z);
   }
   BGN_DEVNI static void copy(E r, const uint32_t* a) {
+    BGN_SETB(r, BGN_GETB(a));
     BGN_UNROLL
     for (int j = 0; j < L; j++) r[j] = a[j];
   }
   BGN_DEVNI static void set_one(E r) {
+    BGN_SETB(r, 1.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) r[j] = c_fc.one[j];
   }
   BGN_DEVNI static void set_zero(E r) {
+    BGN_SETB(r, 0.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) r[j] = 0;
   }
@@ -142,6 +148,7 @@ struct F {
     uint32_t x[L], y[L], o[L], w[L];
     ld<L>(x, a);
     P::canon(y, x);
+    BGN_SETB(o, 1.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) o[j] = c_fc.one[j];
     P::canon(w, o);
@@ -159,6 +166,7 @@ struct F {
   // Montgomery form -> canonical standard integer in [0,p)
   BGN_DEVNI static void from_mont(E r, const uint32_t* a) {
     uint32_t y[L];
+    BGN_SETB(y, 1.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) y[j] = 0;
     y[0] = 1;

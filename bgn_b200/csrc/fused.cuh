@@ -1,0 +1,180 @@
+// fused.cuh -- the Miller loop's four inner routines as FUSED register-level programs.
+//
+// Why (measured, profiles/r01_miller_v4_ncu.txt + r01_primbench_v4.txt): a warp can issue one
+// IMAD.WIDE per ~6 cycles while the pipe accepts one per 4 cycles per scheduler, so the pipe only
+// saturates when BOTH warps of a scheduler are inside a product at the same time.  With the
+// three-address code of field.cuh every F_p operation is a call that loads its operands from
+// shared memory, runs, and stores its result; the loads, the carry chains of the add/sub glue and
+// the stores of one operation never overlap the products of the same warp, and the sequences ran
+// at 72-76 % of the pipe where the bare product reaches 98 %.  Here each routine is ONE function:
+// intermediates stay in registers, the glue sits in the issue slots the multiplier leaves free,
+// and additions are "relaxed" (no conditional subtraction):
+//
+//   values are bounded multiples of p, far below R = 2^(32L) >= 256 p.  A sum is a plain
+//   multi-limb add; a difference adds a fixed K p (K in {2,4,8,16}) that keeps it non-negative;
+//   the Montgomery product absorbs the slack -- a < A p, b < B p gives a b / R mod p below
+//   (A B / 256 + 1) p.  The CPU run of this very code (tests/hostsim) propagates the worst-case
+//   bound of every value and fails on any product operand >= R - p or any difference whose
+//   subtrahend may exceed its offset, so the ranges are proven, not sampled.
+//
+// Every product is (register operand) x (memory operand): the multiplier is read from its
+// shared-memory slot row by row, so it never occupies registers.  U selects the non-unrolled
+// row loop (Fp::mul_loop<U>, 2U rows per iteration, 1 + 2U rows of code per product) or, U = 0,
+// the fully unrolled product (Fp::mul_stream); which one ships is decided by measurement
+// (tools/primbench.py).
+//
+// Replaces the same libpbc behaviour as curve.cuh / pairing.cuh (a1_param.c Miller loop steps).
+#pragma once
+#include "field.cuh"
+
+template <int L, int U>
+struct MF {
+  typedef Fp<L> P;
+  typedef uint32_t R[L];
+
+  BGN_DEV static void mulm(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
+    if (U > 0)
+      P::template mul_loop<(U > 0 ? U : 1)>(r, a, bp);
+    else
+      P::mul_stream(r, a, bp);
+  }
+  BGN_DEV static void dbl(uint32_t (&r)[L], const uint32_t (&a)[L]) { P::addn(r, a, a); }
+
+  // f <- f * ((cR + aR*xB) + (bI*yB) i): the Miller-loop term, 5 products.
+  // in: f.re, f.im < 8p; cR < 8p; aR < 64p; bI, xB, yB < 8p.   out: f.re < 4p, f.im < 7p.
+  BGN_DEVNI static void line_mul(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
+                                 const uint32_t* xB, const uint32_t* yB) {
+    R a, l0, l1, t, u, v;
+    ld<L>(a, xB);
+    mulm(l0, a, aR);
+    ld<L>(a, cR);
+    P::addn(l0, l0, a);  // l0 = cR + aR xB
+    ld<L>(a, yB);
+    mulm(l1, a, bI);     // l1 = bI yB
+    mulm(t, l0, fre);    // f0 l0
+    mulm(u, l1, fim);    // f1 l1
+    ld<L>(a, fre);
+    ld<L>(v, fim);
+    P::addn(a, a, v);
+    st<L>(fre, a);       // f0 + f1 (f0 itself is dead)
+    P::addn(l0, l0, l1);
+    mulm(v, l0, fre);    // (f0 + f1)(l0 + l1)
+    P::subk(a, t, u, c_fc.p2, 2);
+    st<L>(fre, a);       // f0 l0 - f1 l1
+    P::addn(t, t, u);
+    P::subk(v, v, t, c_fc.p4, 4);
+    st<L>(fim, v);       // f0 l1 + f1 l0
+  }
+
+  // f <- f^2 = (f0 + f1)(f0 - f1) + 2 f0 f1 i, 2 products.  in: < 8p.  out: < 4p.
+  BGN_DEVNI static void sqr2(E fre, E fim) {
+    R a, b, s, d, m;
+    ld<L>(a, fre);
+    ld<L>(b, fim);
+    P::addn(s, a, b);
+    P::subk(d, a, b, c_fc.p8, 8);
+    mulm(m, a, fim);     // f0 f1
+    st<L>(fre, d);
+    mulm(a, s, fre);     // (f0 + f1)(f0 - f1)
+    st<L>(fre, a);
+    dbl(m, m);
+    st<L>(fim, m);
+  }
+
+  // (X, Y, Z) <- 2 (X, Y, Z) on y^2 = x^3 + x (Jacobian) and the tangent at the old point:
+  // cR = M X - 2 YY, aR = M ZZ, bI = Z3 ZZ with M = 3 XX + ZZ^2.  12 products.
+  // in: X, Y, Z < 9p.   out: X, Y < 6p, Z < 3p, cR < 6p, aR, bI < 2p.
+  // The six slots double as scratch for the multipliers, in an order that never overwrites a
+  // value still to be read.
+  BGN_DEVNI static void dbl_line(E X, E Y, E Z, E cR, E aR, E bI) {
+    R x, w, xx, yy, zz, m, s;
+    ld<L>(x, X);
+    mulm(xx, x, X);            // XX
+    ld<L>(w, Y);
+    mulm(yy, w, Y);            // YY
+    dbl(w, w);                 // 2Y
+    ld<L>(s, Z);
+    mulm(zz, s, Z);            // ZZ
+    st<L>(bI, zz);
+    mulm(m, zz, bI);           // ZZ^2
+    P::addn(m, m, xx);
+    dbl(xx, xx);
+    P::addn(m, m, xx);         // M = 3 XX + ZZ^2
+    mulm(s, w, Z);             // Z3 = 2Y * Z
+    st<L>(Z, s);
+    mulm(w, m, bI);            // aR = M ZZ   (bI still holds ZZ)
+    st<L>(aR, w);
+    mulm(w, s, bI);            // bI = Z3 ZZ
+    st<L>(bI, w);
+    dbl(yy, yy);               // 2 YY
+    st<L>(cR, yy);
+    mulm(w, m, X);             // M X
+    P::subk(w, w, yy, c_fc.p4, 4);  // cR = M X - 2 YY   (kept in registers until the slot is free)
+    dbl(x, x);
+    mulm(s, x, cR);            // S = 2X * 2YY = 4 X YY
+    mulm(zz, yy, cR);          // 4 YY^2
+    st<L>(cR, w);
+    st<L>(Y, m);
+    mulm(xx, m, Y);            // M^2
+    dbl(w, s);
+    P::subk(xx, xx, w, c_fc.p4, 4);  // X3 = M^2 - 2S
+    st<L>(X, xx);
+    P::subk(s, s, xx, c_fc.p8, 8);   // S - X3
+    mulm(w, s, Y);             // M (S - X3)
+    dbl(zz, zz);               // 8 YY^2
+    P::subk(w, w, zz, c_fc.p4, 4);
+    st<L>(Y, w);               // Y3
+  }
+
+  // (X, Y, Z) <- (X, Y, Z) + (xA, +-yA) (mixed) and the chord through them: aR = r = 2 (S2 - Y),
+  // bI = Z3, cR = r xA - (+-yA) Z3.  13 products.  No special cases: the Miller loop never meets
+  // them for points of order n except at the very last step, which the schedule drops.
+  // in: X, Y, Z < 9p; xA, yA < 2p.   out: X, Y < 9p, Z, bI, cR < 4p, aR < 24p.
+  BGN_DEVNI static void madd_line(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E cR, E aR,
+                                  E bI) {
+    R xa, ya, z, h, r, w, v, c;
+    ld<L>(xa, xA);
+    ld<L>(ya, yA);
+    if (negate) P::negk(ya, ya, c_fc.p2, 2);  // 2p - yA = -yA
+    ld<L>(z, Z);
+    mulm(w, z, Z);             // ZZ
+    st<L>(bI, w);
+    mulm(h, xa, bI);           // U2 = xA ZZ
+    ld<L>(w, X);
+    P::subk(h, h, w, c_fc.p16, 16);  // H = U2 - X
+    mulm(w, z, bI);            // Z ZZ
+    st<L>(aR, w);
+    mulm(r, ya, aR);           // S2 = yA Z^3
+    ld<L>(w, Y);
+    P::subk(r, r, w, c_fc.p16, 16);
+    dbl(r, r);                 // r = 2 (S2 - Y)
+    st<L>(aR, r);              // aR = r
+    dbl(w, h);
+    st<L>(cR, w);              // 2H
+    mulm(v, z, cR);            // Z3 = Z * 2H
+    st<L>(Z, v);
+    st<L>(bI, v);              // bI = Z3
+    mulm(c, xa, aR);           // r xA
+    mulm(w, ya, Z);            // yA Z3
+    P::subk(c, c, w, c_fc.p2, 2);   // cR, kept in registers until the slot is free
+    ld<L>(w, cR);
+    mulm(v, w, cR);            // I = (2H)^2
+    ld<L>(z, X);               // z now holds X
+    st<L>(X, v);
+    mulm(w, h, X);             // J = H I
+    mulm(v, z, X);             // V = X I
+    st<L>(cR, c);
+    mulm(c, r, aR);            // r^2
+    dbl(z, v);
+    P::addn(z, z, w);          // J + 2V
+    P::subk(c, c, z, c_fc.p4, 4);   // X3 = r^2 - J - 2V
+    st<L>(X, c);
+    mulm(h, w, Y);             // Y J
+    P::subk(v, v, c, c_fc.p16, 16); // V - X3
+    st<L>(Y, v);
+    mulm(w, r, Y);             // r (V - X3)
+    dbl(h, h);
+    P::subk(w, w, h, c_fc.p4, 4);
+    st<L>(Y, w);               // Y3 = r (V - X3) - 2 Y J
+  }
+};

@@ -1,5 +1,8 @@
 // inst_a.cu -- pairing / GT kernels for one limb count (compile with -DBGN_L=<L>).
 #define BGN_GROUP_A 1
+#if BGN_L == 17
+#define BGN_PRIM_UNROLLED 1  // primitive microbenchmarks of the fully unrolled fused routines (tools/primbench.py)
+#endif
 #include "kernels.cuh"
 #include "ops.h"
 #ifndef BGN_L

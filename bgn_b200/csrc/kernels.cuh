@@ -22,6 +22,15 @@ static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
 // ------------------------------------------------------------------ helpers
 template <int L>
 BGN_DEV void be_bytes_to_limbs(uint32_t (&x)[L], const uint8_t* b, int B) {
+#ifdef BGN_HOSTSIM
+  {  // raw integer below 2^(8B): bound in multiples of p
+    long double pd = 0;
+    for (int j = L - 1; j >= 0; j--) pd = pd * 4294967296.0L + c_fc.p[j];
+    long double v = 1;
+    for (int i = 0; i < B; i++) v *= 256.0L;
+    BGN_SETB(x, (double)(v / pd));
+  }
+#endif
   BGN_UNROLL
   for (int j = 0; j < L; j++) {
     uint32_t w = 0;
@@ -570,6 +579,23 @@ __global__ void __launch_bounds__(256, 1) k_prim_bench(uint32_t* io, size_t N, i
                    slot(12));
     } else if (mode == 12) {
       FF::sqr2(mke2(slot(0), slot(1)), mke2(slot(0), slot(1)), slot(10), slot(11));
+#define BGN_PRIM_FUSED(BASE, UU)                                                                             \
+    } else if (mode == BASE) {                                                                                 \
+      MF<L, UU>::line_mul(slot(0), slot(1), slot(7), slot(8), slot(9), slot(4), slot(5));                       \
+    } else if (mode == BASE + 2) {                                                                             \
+      MF<L, UU>::sqr2(slot(0), slot(1));                                                                        \
+    } else if (mode == BASE + 3) {                                                                             \
+      MF<L, UU>::dbl_line(slot(4), slot(5), slot(6), slot(7), slot(8), slot(9));                                \
+    } else if (mode == BASE + 4) {                                                                             \
+      MF<L, UU>::madd_line(slot(4), slot(5), slot(6), slot(10), slot(11), (i & 1) != 0, slot(7), slot(8), slot(9));
+    // fused routines (fused.cuh): the variant the Miller kernel ships, and, for L = 17, the others
+    BGN_PRIM_FUSED(30, BGN_MILLER_LOOP)
+#ifdef BGN_PRIM_UNROLLED
+    BGN_PRIM_FUSED(40, 0)
+    BGN_PRIM_FUSED(50, 2)
+    BGN_PRIM_FUSED(60, 4)
+    BGN_PRIM_FUSED(70, 1)
+#endif
     } else {
       G<L>::dbl_line(slot(4), slot(5), slot(6), slot(7), slot(8), slot(9), slot(10), slot(11), slot(12));
     }

@@ -17,6 +17,19 @@
 //  * a plain pairing batch is the same program with TS = 1.
 #pragma once
 #include "curve.cuh"
+#include "fused.cuh"
+
+// U of fused.cuh for the phase-B routine (line_mul) and for the phase-A routines (sqr2, dbl_line,
+// madd_line): 0 = fully unrolled products, U > 0 = 2U rows per loop iteration.  Measured at L = 17
+// (profiles/r01_primbench_v5.txt, 2 warps per scheduler): unrolled 94 % of the IMAD.WIDE peak,
+// U = 4 87 %, U = 1 80 %; an unrolled product is L(2L+1) x 16 B of code (9.5 KB at L = 17,
+// 35 KB at L = 33), so the big field keeps the loop.
+#ifndef BGN_MILLER_LOOP
+#define BGN_MILLER_LOOP (BGN_L <= 17 ? 0 : 4)
+#endif
+#ifndef BGN_MILLER_LOOP_A
+#define BGN_MILLER_LOOP_A (BGN_L <= 17 ? 0 : 4)
+#endif
 
 BGN_CONST PairConsts c_pc;
 
@@ -90,9 +103,12 @@ template <int L>
 struct MillerTeam {
   typedef F<L> FF;
   typedef G<L> GG;
+  typedef MF<L, BGN_MILLER_LOOP> M;      // phase B
+  typedef MF<L, BGN_MILLER_LOOP_A> MA;   // phase A
   // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
-  // the line it publishes, three temporaries.  Evaluation points stay in HBM/L2 (SoA).
-  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_T0 = 10, S_T1 = 11, S_T2 = 12,
+  // the line it publishes, its evaluation point.  The loop's routines are fused (fused.cuh) and
+  // keep their temporaries in registers.
+  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_EX = 10, S_EY = 11,
          NSLOT = BGN_MILLER_NSLOT };
 
   const MillerArgs& a;
@@ -142,25 +158,28 @@ struct MillerTeam {
         FF::set_one(slot(tid, S_Z));
       }
     }
-    flagsB()[tid] = a.Einf[eidx(t)] ? 0 : 1;
+    bool einf = a.Einf[eidx(t)] != 0;
+    flagsB()[tid] = einf ? 0 : 1;
+    if (!einf) {
+      FF::copy(slot(tid, S_EX), a.Ex + eidx(t) * L);
+      FF::copy(slot(tid, S_EY), a.Ey + eidx(t) * L);
+    }
   }
 
   // phase A: advance own Miller point, publish its line; square own accumulators on doubling steps
   BGN_DEV void phaseA(int op, bool first) {
     if (!active) return;
-    E t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2);
     if (op == MOP_DBL && !first) {
-      FF::sqr2(facc(tid, 0), facc(tid, 0), t0, t1);
-      if (t + a.dE < a.dM + a.dE - 1) FF::sqr2(facc(tid, 1), facc(tid, 1), t0, t1);
+      MA::sqr2(slot(tid, S_F0), slot(tid, S_F0 + 1));
+      if (t + a.dE < a.dM + a.dE - 1) MA::sqr2(slot(tid, S_F1), slot(tid, S_F1 + 1));
     }
     if (t < a.dM && flagsA()[tid]) {
       if (op == MOP_DBL) {
-        GG::dbl_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI),
-                     t0, t1, t2);
+        MA::dbl_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
       } else {
         size_t idx = (size_t)unit * a.dM + t;
-        GG::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), (a.Mx + (size_t)(idx) * L), (a.My + (size_t)(idx) * L),
-                      op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), t0, t1, t2);
+        MA::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), (a.Mx + (size_t)(idx) * L), (a.My + (size_t)(idx) * L),
+                     op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
       }
     }
   }
@@ -170,7 +189,6 @@ struct MillerTeam {
     if (!active) return;
     int TS = a.dE;
     int base = tid - t;  // first thread of the team
-    E t0 = slot(tid, S_T0), t1 = slot(tid, S_T1), t2 = slot(tid, S_T2);
     for (int i = 0; i < a.dM; i++) {
       int k = t - i;
       int s = 0;
@@ -179,9 +197,8 @@ struct MillerTeam {
         s = 1;
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
-      size_t ei = eidx(k);
-      FF::line_mul(facc(tid, s), slot(base + i, S_CR), slot(base + i, S_AR), slot(base + i, S_BI), (a.Ex + (size_t)(ei) * L),
-                   (a.Ey + (size_t)(ei) * L), t0, t1, t2);
+      M::line_mul(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
+                  slot(base + i, S_BI), slot(base + k, S_EX), slot(base + k, S_EY));
     }
   }
 
@@ -193,7 +210,7 @@ struct MillerTeam {
       if (j >= nslots || j >= a.out_slots) continue;
       E2 f = facc(tid, s);
       // the Miller point of this thread is dead by now: scratch for the exponentiation
-      GT<L>::final_exp(f, mke2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_T0), slot(tid, S_T1), slot(tid, S_T2));
+      GT<L>::final_exp(f, mke2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR));
       size_t o = (size_t)unit * a.out_slots + j;
       FF::copy(a.out_re + o * L, f.re);
       FF::copy(a.out_im + o * L, f.im);

@@ -10,6 +10,9 @@ struct FieldConsts {
   uint32_t p2[BGN_MAXL];   // 2p
   uint32_t one[BGN_MAXL];  // R mod p   (Montgomery 1)
   uint32_t r2[BGN_MAXL];   // R^2 mod p (to-Montgomery factor)
+  uint32_t p4[BGN_MAXL];   // 4p, 8p, 16p: offsets that keep relaxed-range differences non-negative
+  uint32_t p8[BGN_MAXL];
+  uint32_t p16[BGN_MAXL];
   uint32_t np0;            // -p^{-1} mod 2^32
   uint32_t pad[3];
 };
@@ -24,7 +27,7 @@ struct PairConsts {
   int8_t naf[BGN_MAX_NAF];
 };
 
-#define BGN_MILLER_NSLOT 13  // shared-memory F_p slots per thread of the Miller team kernel
+#define BGN_MILLER_NSLOT 12  // shared-memory F_p slots per thread of the Miller team kernel
 struct MillerArgs {
   const uint32_t* Mx;  // Miller-side points, Montgomery [L][NM], index unit*dM + i
   const uint32_t* My;

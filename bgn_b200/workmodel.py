@@ -17,7 +17,7 @@ def products_per_modmul(L: int) -> int:
 
 def pick_limbs(p: int) -> int:
     for L in (3, 5, 9, 17, 33):
-        if 32 * L >= p.bit_length() + 7:
+        if 32 * L >= p.bit_length() + 8:
             return L
     raise ValueError("field too large")
 

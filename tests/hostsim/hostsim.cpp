@@ -4,6 +4,9 @@
 // kernels' per-thread logic against the oracle without a GPU.  It is never
 // linked into libbgn_b200.so and nothing in bgn_b200/ can reach it.
 #define BGN_HOSTSIM 1
+#ifndef BGN_L
+#define BGN_L 17  // only selects the default loop shape of the fused routines (pairing.cuh)
+#endif
 #include <vector>
 
 #include "../../bgn_b200/csrc/kernels.cuh"
@@ -42,9 +45,41 @@ void sim_miller(const MillerArgs& a, int nblocks, int nt) {
   return 0;
 
 extern "C" {
-void hs_set_consts(const FieldConsts* fc, const PairConsts* pc) {
+void hs_set_consts(const FieldConsts* fc, const PairConsts* pc, int L) {
   c_fc = *fc;
   c_pc = *pc;
+  long double pd = 0, R = 1;
+  for (int j = L - 1; j >= 0; j--) pd = pd * 4294967296.0L + c_fc.p[j];
+  for (int j = 0; j < L; j++) R *= 4294967296.0L;
+  bgnsim::bnd.clear();
+  // the limb-count rule (32L >= bits(p) + 8) guarantees R/p >= 256; the tracker proves the ranges
+  // for that worst case, not just for this key's (usually much larger) headroom
+  bgnsim::headroom = (double)(R / pd) < 256.0 ? (double)(R / pd) : 256.0;
+  bgnsim::setb(c_fc.p, 1.0);
+  bgnsim::setb(c_fc.p2, 2.0);
+  bgnsim::setb(c_fc.p4, 4.0);
+  bgnsim::setb(c_fc.p8, 8.0);
+  bgnsim::setb(c_fc.p16, 16.0);
+  bgnsim::setb(c_fc.one, 1.0);
+  bgnsim::setb(c_fc.r2, 1.0);
+  bgnsim::max_bound = 0;
+  bgnsim::unknown = bgnsim::violations = 0;
+}
+// range tracker report: out[0] = largest bound attached (multiples of p), out[1] = headroom R/p,
+// out[2] = reads of untracked addresses, out[3] = violations
+void hs_range_report(double* out, int reset) {
+  out[0] = bgnsim::max_bound;
+  out[1] = bgnsim::headroom;
+  out[2] = (double)bgnsim::unknown;
+  out[3] = (double)bgnsim::violations;
+  if (reset) {
+    bgnsim::max_bound = 0;
+    bgnsim::unknown = bgnsim::violations = 0;
+  }
+}
+// inputs built by the test driver (Montgomery arrays of canonical values): bound 1 per element
+void hs_track_array(const uint32_t* a, size_t count, int L, double bound) {
+  for (size_t e = 0; e < count; e++) bgnsim::setb(a + e * L, bound);
 }
 int hs_miller(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller<LL>(*a, nblocks, nt)) }
 int hs_encrypt(int L, const EncArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) encrypt_body<LL>(*a, e)) }

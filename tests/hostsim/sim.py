@@ -12,7 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-MAXL, MAX_NAF, MAX_EXPW, NSLOT = 34, 1100, 34, 13
+MAXL, MAX_NAF, MAX_EXPW, NSLOT = 34, 1100, 34, 12
 SUPPORTED_L = (3, 5, 17)  # limb counts instantiated in hostsim.cpp
 PRODUCT_L = (3, 5, 9, 17, 33)  # limb counts the CUDA library instantiates
 
@@ -22,7 +22,8 @@ u8p = C.POINTER(C.c_uint8)
 
 class FieldConsts(C.Structure):
     _fields_ = [("p", C.c_uint32 * MAXL), ("p2", C.c_uint32 * MAXL), ("one", C.c_uint32 * MAXL),
-                ("r2", C.c_uint32 * MAXL), ("np0", C.c_uint32), ("pad", C.c_uint32 * 3)]
+                ("r2", C.c_uint32 * MAXL), ("p4", C.c_uint32 * MAXL), ("p8", C.c_uint32 * MAXL),
+                ("p16", C.c_uint32 * MAXL), ("np0", C.c_uint32), ("pad", C.c_uint32 * 3)]
 
 
 class PairConsts(C.Structure):
@@ -123,7 +124,7 @@ def naf_digits(n: int) -> List[int]:
 
 def pick_L(p: int) -> int:
     for L in PRODUCT_L:
-        if 32 * L >= p.bit_length() + 7:
+        if 32 * L >= p.bit_length() + 8:
             return L
     raise ValueError("p too large")
 
@@ -141,7 +142,8 @@ class Sim:
         self.B = par.coord_bytes
         self.nbytes = (par.n.bit_length() + 7) // 8
         fc = FieldConsts()
-        for name, v in (("p", self.p), ("p2", 2 * self.p), ("one", self.R % self.p), ("r2", self.R * self.R % self.p)):
+        for name, v in (("p", self.p), ("p2", 2 * self.p), ("one", self.R % self.p), ("r2", self.R * self.R % self.p),
+                        ("p4", 4 * self.p), ("p8", 8 * self.p), ("p16", 16 * self.p)):
             arr = getattr(fc, name)
             for i in range(MAXL):
                 arr[i] = (v >> (32 * i)) & 0xFFFFFFFF
@@ -161,7 +163,7 @@ class Sim:
         self.activate()
 
     def activate(self):
-        lib().hs_set_consts(C.byref(self.fc), C.byref(self.pc))
+        lib().hs_set_consts(C.byref(self.fc), C.byref(self.pc), self.L)
 
     # ---- conversions between Python integers and Montgomery SoA
     def soa(self, vals: Sequence[int], mont: bool = True) -> np.ndarray:
@@ -172,7 +174,15 @@ class Sim:
                 v = v * self.R % self.p
             for j in range(self.L):
                 a[e, j] = (v >> (32 * j)) & 0xFFFFFFFF
+        # range tracker: arrays built here hold canonical values (< p)
+        lib().hs_track_array(P32(a), C.c_size_t(n), self.L, C.c_double(1.0))
         return a
+
+    def range_report(self, reset: bool = True):
+        """(largest bound attached in multiples of p, headroom R/p assumed, untracked reads, violations)"""
+        out = (C.c_double * 4)()
+        lib().hs_range_report(out, 1 if reset else 0)
+        return out[0], out[1], int(out[2]), int(out[3])
 
     def unsoa(self, a: np.ndarray, count: int, mont: bool = True) -> List[int]:
         out = []
