@@ -76,7 +76,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    count = max(40, cores)  # EMults per step: ~0.5 s of one core each at 512 bit
+    count = 4 * cores  # EMults per step (~0.3 s of one core each at 512 bit): every thread gets 4
     t0 = time.perf_counter()
     for _ in range(min(args.warmup, 1)):
         cpu_emults(max(1, cores // 4), cores)
@@ -310,7 +310,7 @@ def run_ours(args):
     }
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = host_cores()
-        cnt = max(40, cores)
+        cnt = 4 * cores  # ~20 core-seconds
         v, el = cpu_emults(cnt, cores)
         line["cpu_baseline"] = {
             "value": v, "unit": "pairings/s", "cores": cores, "kind": "port",

@@ -61,3 +61,19 @@ def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
 def canonical_pairing_modmuls(n: int, l: int) -> int:
     """PBC-like unshared schedule, one full pairing."""
     return 23 * n.bit_length() + 18 * bin(n).count("1") - 70 + 4 + 3 + 2 * l.bit_length() + 3 * bin(l).count("1") + 1
+
+
+def gt_pow_modmuls(e: int) -> int:
+    """GT<L>::pow_fixed: left-to-right binary, sqr2 = 2 products, mul2 = 3 (pairing.cuh)."""
+    if e == 0:
+        return 0
+    return 2 * (e.bit_length() - 1) + 3 * (bin(e).count("1") - 1)
+
+
+def encrypt_modmuls(n: int, rbytes: int, window_bits: int = 8, p_x_nonzero: float = 2.0 / 3.0) -> float:
+    """k_encrypt, EXPECTED products per coefficient for uniform r: one complete mixed addition (11
+    products; the first one into O is a copy) per non-zero window digit of r, plus one for a non-zero
+    plaintext digit.  Jacobian -> affine (k_normalize) is accounted separately."""
+    windows = (8 * rbytes + window_bits - 1) // window_bits
+    adds = windows * (1.0 - 2.0 ** -window_bits) + p_x_nonzero
+    return max(0.0, adds - 1.0) * 11
