@@ -118,6 +118,8 @@ struct bgn_ctx {
   uint32_t *dPx = nullptr, *dPy = nullptr, *dQx = nullptr, *dQy = nullptr;
   uint8_t *dPinf = nullptr, *dQinf = nullptr;
   uint32_t *tabP = nullptr, *tabQ = nullptr;
+  uint32_t* tabQ16 = nullptr;  // 16-bit windows of Q, built on the first randomised encryption
+  int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
   // decryption
   bool has_secret = false;
   uint32_t *bs_elems = nullptr, *bs_slots = nullptr, *bs_ginv = nullptr;
@@ -469,6 +471,44 @@ void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, u
   finish(c);
 }
 
+// 16-bit window table of Q for Encrypt (half the additions of the 8-bit one): ceil(nbytes/2) x
+// 65535 affine points, 285 MB at 512-bit keys, 1.1 GB at 1024 -- sized for HBM, not for shared
+// memory.  Built once from the 8-bit table with one addition per entry; its temporaries are
+// released again.
+void ensure_tabQ16(bgn_ctx* c) {
+  if (c->tabQ16 || c->enc_window != 16) return;
+  int nw = (c->nbytes + 1) / 2;
+  size_t nent = (size_t)nw * 65535, ew = (size_t)c->L * 4;
+  uint32_t *tab = nullptr, *tmp = nullptr;
+  CK(cudaMalloc(&tab, nent * 2 * ew));
+  cudaError_t e = cudaMalloc(&tmp, nent * 4 * ew);
+  if (e != cudaSuccess) {
+    cudaFree(tab);
+    CK(e);
+  }
+  JacArr j;
+  j.X = tmp;
+  j.Y = tmp + nent * c->L;
+  j.Z = tmp + 2 * nent * c->L;
+  j.N = nent;
+  uint32_t* scratch = tmp + 3 * nent * c->L;
+  try {
+    {
+      Timer t(c, "k_tab16_fill");
+      c->Bo->tab16_fill(cfg(c, nblk(nent, 128), 128, 0), c->tabQ, c->nbytes, j.X, j.Y, j.Z, nent);
+      t.done();
+    }
+    normalize(c, j, nent, scratch, tab, tab + c->L, 2 * (size_t)c->L, 1, nullptr);
+    CK(cudaStreamSynchronize(c->stream));
+  } catch (...) {
+    cudaFree(tab);
+    cudaFree(tmp);
+    throw;
+  }
+  CK(cudaFree(tmp));
+  c->tabQ16 = tab;
+}
+
 template <typename Fn>
 int guarded(bgn_ctx* c, Fn fn) {
   if (!c) return BGN_E_BADARG;
@@ -521,6 +561,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->device = device;
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
+    if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : 16;
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -676,6 +717,7 @@ void bgn_ctx_destroy(bgn_ctx* c) {
   cudaFree(c->dPinf);
   cudaFree(c->tabP);
   cudaFree(c->tabQ);
+  cudaFree(c->tabQ16);
   cudaFree(c->bs_elems);
   cudaFree(c->bs_slots);
   cudaFree(c->bs_ginv);
@@ -714,8 +756,10 @@ int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t 
     ea.x = dx;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
+    if (dr) ensure_tabQ16(c);
     ea.tabP = c->tabP;
-    ea.tabQ = c->tabQ;
+    ea.tabQ = c->tabQ16 ? c->tabQ16 : c->tabQ;
+    ea.wbitsQ = c->tabQ16 ? 16 : 8;
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;

@@ -136,7 +136,21 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
   FF::set_zero(X.v());
   FF::set_zero(Y.v());
   FF::set_zero(Z.v());
-  if (a.r_be) {
+  if (a.r_be && a.wbitsQ == 16) {
+    // 16-bit windows: half the additions; the table (2^16 - 1 points per window, 285 MB at
+    // 512 bit) lives in HBM and each lookup is one 8L-byte read at a random address
+    const uint8_t* r = a.r_be + e * a.rbytes;
+    int nw = (a.rbytes + 1) / 2;
+    for (int win = 0; win < nw; win++) {
+      int lo = a.rbytes - 1 - 2 * win;
+      uint32_t d = r[lo];
+      if (lo > 0) d |= (uint32_t)r[lo - 1] << 8;
+      if (d) {
+        const uint32_t* ent = a.tabQ + ((size_t)win * 65535 + (d - 1)) * 2 * L;
+        G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+      }
+    }
+  } else if (a.r_be) {
     const uint8_t* r = a.r_be + e * a.rbytes;
     for (int win = 0; win < a.rbytes; win++) {
       uint32_t d = r[a.rbytes - 1 - win];
@@ -295,6 +309,36 @@ BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t
     FF::copy(Y + (size_t)(o) * L, y.v());
     FF::copy(Z + (size_t)(o) * L, z.v());
   }
+}
+
+// 16-bit window table from the 8-bit one: entry (w, hi*256 + lo) = T8[2w][lo] + T8[2w+1][hi]
+// (one complete mixed addition per entry, all entries in parallel; Jacobian out).  An odd byte
+// count leaves the top window with its low byte only: those hi != 0 entries stay O and are never
+// addressed.
+template <int L>
+BGN_DEV void tab16_fill_body(const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent,
+                             size_t id) {
+  typedef F<L> FF;
+  if (id >= nent) return;
+  int w = (int)(id / 65535);
+  uint32_t d = (uint32_t)(id % 65535) + 1, lo = d & 255u, hi = d >> 8;
+  Loc<L> x, y, z, t0, t1, t2, t3;
+  FF::set_zero(x.v());
+  FF::set_zero(y.v());
+  FF::set_zero(z.v());
+  if (hi == 0 || 2 * w + 1 < nwin8) {
+    if (lo) {
+      const uint32_t* ent = tab8 + ((size_t)(2 * w) * 255 + (lo - 1)) * 2 * L;
+      G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+    }
+    if (hi) {
+      const uint32_t* ent = tab8 + ((size_t)(2 * w + 1) * 255 + (hi - 1)) * 2 * L;
+      G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+    }
+  }
+  FF::copy(X + id * L, x.v());
+  FF::copy(Y + id * L, y.v());
+  FF::copy(Z + id * L, z.v());
 }
 
 // ------------------------------------------------------------ GT kernels
@@ -503,6 +547,11 @@ template <int L>
 __global__ void k_tab_fill(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
                            uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
   tab_fill_body<L>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, BGN_GID(size_t));
+}
+template <int L>
+__global__ void __launch_bounds__(128) k_tab16_fill(const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                                                    size_t nent) {
+  tab16_fill_body<L>(tab8, nwin8, X, Y, Z, nent, BGN_GID(size_t));
 }
 template <int L>
 __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms,

@@ -44,6 +44,7 @@ struct LOpsB {
                     size_t N);
   void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
                    uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
+  void (*tab16_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent);
 };
 
 #define BGN_DECL_OPS(L)               \

@@ -106,6 +106,9 @@ int hs_tab_fill(int L, const uint32_t* ax, const uint32_t* ay, const uint8_t* ai
                 uint32_t* Y, uint32_t* Z, size_t N) {
   FOR_L(L, for (int w = 0; w < nwin; w++) tab_fill_body<LL>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, w))
 }
+int hs_tab16_fill(int L, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent) {
+  FOR_L(L, for (size_t id = 0; id < nent; id++) tab16_fill_body<LL>(tab8, nwin8, X, Y, Z, nent, id))
+}
 int hs_g1_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf, size_t N) {
   FOR_L(L, for (size_t e = 0; e < count; e++) g1_from_bytes_body<LL>(in, B, count, x, y, inf, N, e))
 }
@@ -118,6 +121,17 @@ int hs_fp2_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* r
 }
 int hs_fp2_to_bytes(int L, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B) {
   FOR_L(L, for (size_t e = 0; e < count; e++) fp2_to_bytes_body<LL>(re, im, N, count, out, B, e))
+}
+// tracker self-test: a difference whose subtrahend may exceed its offset must be flagged
+int hs_selftest_violation() {
+  uint64_t before = bgnsim::violations;
+  uint32_t a[3] = {5, 0, 0}, b[3] = {1, 0, 0}, r[3];
+  bgnsim::setb(a, 1.0);
+  bgnsim::setb(b, 3.0);  // b may be as large as 3p, offset is only 2p
+  Fp<3>::subk(r, a, b, c_fc.p2, 2);
+  int fired = bgnsim::violations > before;
+  bgnsim::violations = before;
+  return fired;
 }
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;

@@ -39,7 +39,7 @@ class MillerArgs(C.Structure):
 
 
 class EncArgs(C.Structure):
-    _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p),
+    _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p), ("wbitsQ", C.c_int),
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
 
 
@@ -84,14 +84,16 @@ class BsgsLookupArgs(C.Structure):
 _lib = None
 
 
-def build() -> str:
-    """(Re)build libhostsim.so when a device header is newer than it."""
-    so = os.path.join(HERE, "libhostsim.so")
+def build(loop: Optional[int] = None) -> str:
+    """(Re)build libhostsim.so when a device header is newer than it.  `loop` builds a variant whose
+    fused Miller routines use Fp::mul_loop<loop> (0 = unrolled products) instead of the default."""
+    so = os.path.join(HERE, "libhostsim.so" if loop is None else "libhostsim_u%d.so" % loop)
     src = os.path.join(HERE, "hostsim.cpp")
     csrc = os.path.join(ROOT, "bgn_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+        flags = [] if loop is None else ["-DBGN_MILLER_LOOP=%d" % loop, "-DBGN_MILLER_LOOP_A=%d" % loop]
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC"] + flags + ["-o", so, src])
     return so
 
 
@@ -99,6 +101,14 @@ def lib():
     global _lib
     if _lib is None:
         _lib = C.CDLL(build())
+    return _lib
+
+
+def use_variant(loop: Optional[int]):
+    """Switch the simulator to a loop-shape variant (None = default build); callers re-activate
+    their Sim afterwards (constants live in the library)."""
+    global _lib
+    _lib = C.CDLL(build(loop))
     return _lib
 
 
@@ -255,7 +265,21 @@ class Sim:
         assert lib().hs_normalize(L, C.byref(a)) == 0
         return tab
 
-    def encrypt(self, xs, rs, tabP, tabQ):
+    def build_table16(self, tab8, nwin8):
+        """k_tab16_fill + k_normalize: 16-bit windows from the 8-bit table (api.cu: ensure_tabQ16)"""
+        L = self.L
+        nent = ((nwin8 + 1) // 2) * 65535
+        X = np.zeros((nent, L), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        assert lib().hs_tab16_fill(L, P32(tab8), nwin8, P32(X), P32(Y), P32(Z), C.c_size_t(nent)) == 0
+        tab = np.zeros(nent * 2 * L, dtype=np.uint32)
+        scratch = np.zeros_like(X)
+        a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), nent, nent, 64, P32(tab), P32(tab[L:]), 2 * L, 1, None)
+        assert lib().hs_normalize(L, C.byref(a)) == 0
+        return tab
+
+    def encrypt(self, xs, rs, tabP, tabQ, wbitsQ=8):
         count = len(xs)
         x = np.array(xs, dtype=np.int64)
         X = np.zeros((max(1, count), self.L), dtype=np.uint32)
@@ -266,8 +290,8 @@ class Sim:
         else:
             rbuf = np.frombuffer(b"".join(int(r).to_bytes(self.nbytes, "big") for r in rs), dtype=np.uint8).copy()
             rp = P8(rbuf)
-        a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)), rp, self.nbytes, P32(tabP), P32(tabQ), P32(X), P32(Y),
-                    P32(Z), count, count)
+        a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)), rp, self.nbytes, P32(tabP), P32(tabQ), wbitsQ, P32(X),
+                    P32(Y), P32(Z), count, count)
         assert lib().hs_encrypt(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
 

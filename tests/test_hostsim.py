@@ -27,6 +27,17 @@ def setup(kb):
     return g, par, S, tabs
 
 
+@pytest.fixture(autouse=True)
+def no_range_violations():
+    """Every simulated kernel run is also a worst-case range proof (arith.cuh, bgnsim): no product
+    operand may reach R - p and no relaxed difference may go negative, for ANY input values."""
+    yield
+    import ctypes
+    out = (ctypes.c_double * 4)()
+    sim.lib().hs_range_report(out, 0)
+    assert int(out[3]) == 0, "range violations reported by the simulated device code"
+
+
 def g1s(par, hexes):
     return [O.g1_from_bytes(bytes.fromhex(h), par) for h in hexes]
 
@@ -45,6 +56,17 @@ def test_sim_encrypt(kb):
     k = len(v["x"]) if kb < 512 else 5
     got = S.encrypt(v["x"][:k], [int(r, 16) for r in v["r"][:k]], tabs["P"], tabs["Q"])
     assert got == g1s(par, v["out"][:k])
+    if kb == 64:  # the 16-bit window table the GPU path uses (2^16 - 1 points per window)
+        if "Q16" not in tabs:
+            tabs["Q16"] = S.build_table16(tabs["Q"], S.nbytes)
+        assert S.encrypt(v["x"], [int(r, 16) for r in v["r"]], tabs["P"], tabs["Q16"], wbitsQ=16) == g1s(par, v["out"])
+        small = [int(r, 16) >> 8 for r in v["r"]]  # zero top byte: a window with an empty high half
+
+        def enc(x, r):
+            c = O.g1_add(O.g1_mul(abs(x), S.P, par.p), O.g1_mul(r, S.Q, par.p), par.p)
+            return O.g1_neg(c, par.p) if x < 0 else c
+
+        assert S.encrypt(v["x"], small, tabs["P"], tabs["Q16"], wbitsQ=16) == [enc(x, r) for x, r in zip(v["x"], small)]
     got = S.encrypt(v["x"][:k], None, tabs["P"], tabs["Q"])  # EncryptDeterministic
     exp = [O.g1_mul(x, S.P, par.p) for x in v["x"][:k]]
     assert got == exp
@@ -149,3 +171,38 @@ def test_work_model_matches_executed_products(kb):
     executed = lib.hs_mul_count(1)
     assert executed == workmodel.miller_unit_modmuls(par.p, par.n, par.l, v["d1"], v["d2"])
     assert workmodel.pick_limbs(par.p) == S.L
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
+def test_range_tracker_proves_miller_ranges(kb):
+    """The fused Miller routines (fused.cuh) skip the per-operation reduction; the simulation
+    propagates the worst-case bound of every value (with the smallest headroom the limb-count rule
+    allows, R/p = 256): no untracked operand, no violation, all bounds far below the headroom."""
+    g, par, S, _ = setup(kb)
+    S.range_report()
+    v = g["multpoly"]
+    c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+    assert S.multpoly(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+    worst, headroom, unknown, violations = S.range_report()
+    assert headroom == 256.0
+    assert unknown == 0 and violations == 0
+    assert 16.0 < worst < 64.0  # the chord slope 2 (S2 - Y + 16p) is the largest value
+    assert sim.lib().hs_selftest_violation() == 1  # and the checker does fire
+
+
+@pytest.mark.parametrize("loop", (1, 2, 4))
+def test_sim_miller_loop_variants(loop):
+    """Fp::mul_loop<U> (the row loop the 1024-bit field ships with) gives the same bytes."""
+    try:
+        sim.use_variant(loop)
+        for kb in (64, 128):
+            g, par, S, _ = setup(kb)
+            v = g["multpoly"]
+            c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+            assert S.multpoly(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+            v = g["pair"]
+            assert S.pair(g1s(par, v["a"]), g1s(par, v["b"])) == gts(par, v["out"])
+            _, _, unknown, violations = S.range_report()
+            assert unknown == 0 and violations == 0
+    finally:
+        sim.use_variant(None)

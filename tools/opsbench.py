@@ -24,8 +24,11 @@ def main():
     ap.add_argument("--plaintexts", type=int, default=1 << 16)
     ap.add_argument("--decrypts", type=int, default=1 << 14)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--key-bits", type=int, default=512)
+    ap.add_argument("--emults", type=int, default=0, help="also time MultPoly of this many pairs")
+    ap.add_argument("--d", type=int, default=D, help="coefficient slots per polynomial for --emults")
     args = ap.parse_args()
-    with open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kb512.json")) as f:
+    with open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kb%d.json" % args.key_bits)) as f:
         g = json.load(f)
     p, n, l, q1 = int(g["p"], 16), int(g["n"], 16), g["l"], int(g["q1"], 16)
     eng = Engine(p, n, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=0)
@@ -37,7 +40,7 @@ def main():
     peak = 148 * 8 * 256 * ipt / (ms * 1e-3)
     ppm = workmodel.products_per_modmul(L)
     eng.timing_enable(True)
-    res = {"key_bits": 512, "limbs": L, "imad_wide_peak_T": peak / 1e12, "ops": {}}
+    res = {"key_bits": args.key_bits, "limbs": L, "imad_wide_peak_T": peak / 1e12, "ops": {}}
 
     def timed(fn, reps=args.reps):
         fn()  # warm-up
@@ -69,8 +72,18 @@ def main():
     r = r.reshape(-1)
     out = torch.empty(cnt * EB, dtype=torch.uint8, device=dev)
     t, k = timed(lambda: eng.encrypt_batch(digits, r, out=out))
-    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_modmuls(n, SB), "k_encrypt")
+    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_modmuls(n, SB, 16), "k_encrypt")
+    res["ops"]["encrypt"]["window_bits"] = 16
     res["ops"]["encrypt"]["plaintexts_per_s"] = args.plaintexts / (t * 1e-3)
+
+    if args.emults:
+        d, m = args.d, args.emults
+        c1, c2 = out[: m * d * EB], out[m * d * EB: 2 * m * d * EB]
+        o_em = torch.empty(m * 2 * d * EB, dtype=torch.uint8, device=dev)
+        t, k = timed(lambda: eng.multpoly_batch(c1, d, c2, d, m, out=o_em))
+        entry("emult_d%d" % d, m, "MultPoly products (%d pairings each)" % (d * d), t, k,
+              workmodel.miller_unit_modmuls(p, n, l, d, d), "k_miller")
+        res["ops"]["emult_d%d" % d]["pairings_per_s"] = m * d * d / (t * 1e-3)
 
     # ---- config 2: EAdd = pairwise AddPoly of the two halves
     half = cnt // 2
