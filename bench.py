@@ -294,6 +294,42 @@ def run_ours(args):
     e2e_value = sum_over_ranks(float(pairs)) * e2e_steps * D1 * D2 / (e2e_ms * 1e-3)
     same = bool((ho.to(dev) == out).all().item())  # host path and device path give identical bytes
 
+    # ---- the other operations north_star names, measured briefly on the same key (device-resident
+    # inputs, best of 2 calls after one warm-up; tools/opsbench.py has the per-kernel breakdown)
+    def best_ms(fn, reps=2):
+        fn()
+        best = None
+        for _ in range(reps):
+            fn()
+            t = eng.timing_last_call()
+            best = t if best is None else min(best, t)
+        return best
+
+    n_enc = 1 << 18
+    digits = torch.randint(-1, 2, (n_enc,), generator=gen, device=dev, dtype=torch.int64)
+    rr = torch.randint(0, 256, (n_enc, SB), generator=gen, device=dev, dtype=torch.uint8)
+    rr[:, 0] &= 0x3F
+    rr = rr.reshape(-1)
+    enc_out = torch.empty(n_enc * EB, dtype=torch.uint8, device=dev)
+    enc_ms = best_ms(lambda: eng.encrypt_batch(digits, rr, out=enc_out))
+    add_out = torch.empty((n_enc // 2) * EB, dtype=torch.uint8, device=dev)
+    add_ms = best_ms(lambda: eng.g1_add_batch(enc_out[: (n_enc // 2) * EB], enc_out[(n_enc // 2) * EB:], out=add_out))
+    eng.set_secret(int(g["q1"], 16), 1 << 20)
+    n_dec = 1 << 14
+    l2 = out[: n_dec * EB]  # level-2 coefficient ciphertexts produced by the timed EMult batch
+    dec = {}
+
+    def do_dec():
+        dec["v"], dec["s"] = eng.decrypt_batch(l2, True)
+
+    dec_ms = best_ms(do_dec)
+    ops = {"encrypt_coeff_per_s": sum_over_ranks(n_enc / (enc_ms * 1e-3)),
+           "eadd_coeff_per_s": sum_over_ranks((n_enc // 2) / (add_ms * 1e-3)),
+           "decrypt_l2_per_s": sum_over_ranks(n_dec / (dec_ms * 1e-3)),
+           "decrypt_all_found": not bool(dec["s"].any().item()),
+           "note": "keyBits=512, per-call device time incl. (de)serialisation kernels; Encrypt: x in {-1,0,1}, "
+                   "512-bit r; Decrypt: GT^q1 + table lookup over T=2^20; summed over ranks"}
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -306,7 +342,7 @@ def run_ours(args):
         "emult_per_s": value / (D1 * D2),
         "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": int(h1.numel() + h2.numel()),
                 "d2h_bytes_per_step": int(ho.numel()), "steps": e2e_steps, "bytes_match_device_path": same},
-        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "wall_s": t_wall,
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "wall_s": t_wall, "ops": ops,
     }
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = host_cores()

@@ -369,6 +369,25 @@ struct Fp {
     subc(r[L - 1], t[L - 1], b[L - 1]);
   }
 
+  // r = a - {0, 2, 4, 6} p, whichever lies in [0, 2p); requires a < 8p.  Brings a relaxed-range
+  // value back to the range every other kernel expects.
+  BGN_DEV static void norm2p(uint32_t (&r)[L], const uint32_t (&a)[L]) {
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) <= 8.0, "norm2p expects an operand below 8p");
+    BGN_SETB(r, 2.0);
+#endif
+    uint32_t u[L], v[L], bw;
+    sub_cc(u[0], a[0], c_fc.p4[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L; j++) subc_cc(u[j], a[j], c_fc.p4[j]);
+    subc(bw, 0, 0);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) v[j] = bw ? a[j] : u[j];  // < 4p
+    bw = sub_p2(u, v);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) r[j] = bw ? v[j] : u[j];
+  }
+
   // r = K p - a; requires a <= K p
   BGN_DEV static void negk(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* kp, int K) {
 #ifdef BGN_HOSTSIM

@@ -177,4 +177,87 @@ struct MF {
     P::subk(w, w, h, c_fc.p4, 4);
     st<L>(Y, w);               // Y3 = r (V - X3) - 2 Y J
   }
+
+  // ---- final exponentiation f^((p^2-1)/n) = (conj(f)/f)^l = (conj(f)^2 / N(f))^l, fused.
+  // Step 1: f <- conj(f)^2 = (f0^2 - f1^2) - 2 f0 f1 i and nrm <- N(f) = f0^2 + f1^2.  3 products.
+  // in: f < 8p.  out: f.re < 4p, f.im < 4p, nrm < 4p.
+  BGN_DEVNI static void fe_prepare(E fre, E fim, E nrm) {
+    R a, b, t, u, v;
+    ld<L>(a, fre);
+    ld<L>(b, fim);
+    mulm(t, a, fre);   // f0^2
+    mulm(u, b, fim);   // f1^2
+    mulm(v, a, fim);   // f0 f1
+    P::addn(a, t, u);
+    st<L>(nrm, a);
+    P::subk(t, t, u, c_fc.p2, 2);
+    st<L>(fre, t);
+    dbl(v, v);
+    P::negk(v, v, c_fc.p4, 4);
+    st<L>(fim, v);
+  }
+  // r <- a^(p-2) (Fermat inverse; 0 -> 0) with the running power kept in registers: bits(p) - 1
+  // squarings and wt(p-2) - 1 products, no loads or stores in between.  The exponent is a key
+  // constant, so control flow is uniform.  r may alias a.  in: a < 16p.  out: r < 2p.
+  BGN_DEVNI static void fp_inv(E r, const uint32_t* a) {
+    R x, y;
+    ld<L>(x, a);
+    ld<L>(y, a);
+    int top = 32 * L - 1;
+    while (top > 0 && !((c_fc.p[top >> 5] >> (top & 31)) & 1)) top--;
+    // exponent e = p - 2: p = 3 (mod 4), so subtracting 2 only clears bit 1 (no borrow)
+    BGN_UNROLL1
+    for (int bit = top - 1; bit >= 0; bit--) {
+      uint32_t limb = c_fc.p[bit >> 5];
+      if ((bit >> 5) == 0) limb -= 2;
+      P::mul(y, y, y);
+      if ((limb >> (bit & 31)) & 1) P::mul(y, y, x);
+    }
+    st<L>(r, y);
+  }
+  // r <- a * b in F_p (register operand a, memory operand b); r may alias either
+  BGN_DEVNI static void fp_mul(E r, const uint32_t* a, const uint32_t* b) {
+    R x, y;
+    ld<L>(x, a);
+    mulm(y, x, b);
+    st<L>(r, y);
+  }
+  // f <- f * s for s in F_p.  2 products.
+  BGN_DEVNI static void scale2(E fre, E fim, const uint32_t* s) {
+    R x, y;
+    ld<L>(x, s);
+    mulm(y, x, fre);
+    st<L>(fre, y);
+    mulm(y, x, fim);
+    st<L>(fim, y);
+  }
+  // f <- f * g in F_p^2 (Karatsuba, 3 products).  in: f, g < 8p.  out: f.re < 4p, f.im < 6p.
+  BGN_DEVNI static void mul2(E fre, E fim, const uint32_t* gre, const uint32_t* gim) {
+    R a, b, t, u, v;
+    ld<L>(a, fre);
+    ld<L>(b, fim);
+    mulm(t, a, gre);   // f0 g0
+    mulm(u, b, gim);   // f1 g1
+    P::addn(a, a, b);
+    ld<L>(b, gre);
+    ld<L>(v, gim);
+    P::addn(b, b, v);
+    st<L>(fre, b);     // g0 + g1 (f0 is dead)
+    mulm(v, a, fre);   // (f0 + f1)(g0 + g1)
+    P::subk(a, t, u, c_fc.p2, 2);
+    st<L>(fre, a);
+    P::addn(t, t, u);
+    P::subk(v, v, t, c_fc.p4, 4);
+    st<L>(fim, v);
+  }
+  // bring both coordinates back to [0, 2p) (what the GT kernels downstream expect).  in: < 8p.
+  BGN_DEVNI static void norm2(E fre, E fim) {
+    R a;
+    ld<L>(a, fre);
+    P::norm2p(a, a);
+    st<L>(fre, a);
+    ld<L>(a, fim);
+    P::norm2p(a, a);
+    st<L>(fim, a);
+  }
 };

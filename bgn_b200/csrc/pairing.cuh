@@ -37,30 +37,6 @@ template <int L>
 struct GT {
   typedef F<L> FF;
 
-  // f <- f^((p^2-1)/n) = (conj(f)/f)^l, in place.  conj(f)/f = conj(f)^2 / N(f).
-  // g (2 elements) and t0..t2 are scratch.
-  BGN_DEV static void final_exp(E2 f, E2 g, E t0, E t1, E t2) {
-    FF::sqr(t0, f.re);
-    FF::sqr(t1, f.im);
-    FF::add(t2, t0, t1);        // N(f)
-    FF::sub(g.re, t0, t1);      // re(conj(f)^2)
-    FF::mul(g.im, f.re, f.im);
-    FF::add(g.im, g.im, g.im);
-    FF::neg(g.im, g.im);        // im(conj(f)^2)
-    FF::inv(t0, t2, t1);        // 1/N(f)
-    FF::mul(g.re, g.re, t0);
-    FF::mul(g.im, g.im, t0);
-    // f = g^l, MSB-first
-    FF::copy2(f, g);
-    uint64_t l = c_pc.l;
-    int top = 63;
-    while (top > 0 && !((l >> top) & 1)) top--;
-    for (int bit = top - 1; bit >= 0; bit--) {
-      FF::sqr2(f, f, t0, t1);
-      if ((l >> bit) & 1) FF::mul2(f, f, g, t0, t1, t2);
-    }
-  }
-
   // r <- a^e for the fixed exponent c_pc.exp (Decrypt: C^q1, bgn.go:223).  r must not alias a.
   BGN_DEV static void pow_fixed(E2 r, E2 a, E t0, E t1, E t2) {
     int nb = c_pc.exp_bits;
@@ -202,18 +178,44 @@ struct MillerTeam {
     }
   }
 
+  // Final exponentiation of the <= 2 slots this thread owns, (conj(f)^2 / N(f))^l, with fused
+  // routines (fused.cuh) and ONE Fermat inversion per thread: a thread that owns two slots inverts
+  // N0 N1 and recovers both inverses with three products (Montgomery's trick).  The thread's
+  // Miller point and line slots are dead by now and serve as scratch.
   BGN_DEV void finalize() {
     if (!active) return;
     int nslots = a.dM + a.dE - 1;
+    bool own0 = t < nslots && t < a.out_slots;
+    bool own1 = t + a.dE < nslots && t + a.dE < a.out_slots;
+    E f0r = slot(tid, S_F0), f0i = slot(tid, S_F0 + 1), f1r = slot(tid, S_F1), f1i = slot(tid, S_F1 + 1);
+    E n0 = slot(tid, S_X), n1 = slot(tid, S_Y), w = slot(tid, S_Z), i0 = slot(tid, S_CR), i1 = slot(tid, S_AR);
+    if (own0) MA::fe_prepare(f0r, f0i, n0);
+    if (own1) MA::fe_prepare(f1r, f1i, n1);
+    if (own1) {
+      MA::fp_mul(w, n0, n1);
+      MA::fp_inv(w, w);
+      MA::fp_mul(i0, w, n1);
+      MA::fp_mul(i1, w, n0);
+    } else if (own0) {
+      MA::fp_inv(i0, n0);
+    }
     for (int s = 0; s < 2; s++) {
-      int j = t + s * a.dE;
-      if (j >= nslots || j >= a.out_slots) continue;
-      E2 f = facc(tid, s);
-      // the Miller point of this thread is dead by now: scratch for the exponentiation
-      GT<L>::final_exp(f, mke2(slot(tid, S_X), slot(tid, S_Y)), slot(tid, S_Z), slot(tid, S_CR), slot(tid, S_AR));
-      size_t o = (size_t)unit * a.out_slots + j;
-      FF::copy(a.out_re + o * L, f.re);
-      FF::copy(a.out_im + o * L, f.im);
+      if (!(s ? own1 : own0)) continue;
+      E fr = s ? f1r : f0r, fi = s ? f1i : f0i;
+      MA::scale2(fr, fi, s ? i1 : i0);  // g = conj(f)^2 / N(f) = f^(p-1)
+      FF::copy(n0, fr);
+      FF::copy(n1, fi);
+      uint64_t l = c_pc.l;
+      int top = 63;
+      while (top > 0 && !((l >> top) & 1)) top--;
+      for (int bit = top - 1; bit >= 0; bit--) {  // f = g^l, MSB first
+        MA::sqr2(fr, fi);
+        if ((l >> bit) & 1) MA::mul2(fr, fi, n0, n1);
+      }
+      MA::norm2(fr, fi);
+      size_t o = (size_t)unit * a.out_slots + t + s * a.dE;
+      FF::copy(a.out_re + o * L, fr);
+      FF::copy(a.out_im + o * L, fi);
     }
     if (t == 0) {
       for (int j = nslots; j < a.out_slots; j++) {  // padding slot(s): GT identity (poly.go:130-137)

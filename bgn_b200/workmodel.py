@@ -40,9 +40,13 @@ def fermat_inv_modmuls(p: int, L: int) -> int:
     return (e.bit_length() - 1) + (bin(e).count("1") - 1)
 
 
-def final_exp_modmuls(p: int, l: int, L: int) -> int:
-    """GT<L>::final_exp: conj(f)^2/N(f) then ^l (pairing.cuh)."""
-    return 5 + fermat_inv_modmuls(p, L) + 2 * (l.bit_length() - 1) + 3 * (bin(l).count("1") - 1)
+def final_exp_modmuls(p: int, l: int, L: int, nslots: int = 1, team: int = 1) -> int:
+    """MillerTeam::finalize for one unit: per slot conj(f)^2 and N(f) (3), g = conj(f)^2 / N (2) and
+    g^l; one Fermat inversion per THREAD that owns a slot (thread t owns slots t and t + team), a
+    thread with two slots adds 3 products (Montgomery's trick)."""
+    pow_l = 2 * (l.bit_length() - 1) + 3 * (bin(l).count("1") - 1)
+    owners = min(team, nslots)
+    return nslots * (5 + pow_l) + owners * fermat_inv_modmuls(p, L) + (nslots - owners) * 3
 
 
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
@@ -55,7 +59,7 @@ def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
     nslots = dM + dE - 1
     per_dbl = dM * 12 + dM * dE * 5
     per_add = dM * 13 + dM * dE * 5
-    return D * per_dbl + (D - 1) * nslots * 2 + A * per_add + nslots * final_exp_modmuls(p, l, L)
+    return D * per_dbl + (D - 1) * nslots * 2 + A * per_add + final_exp_modmuls(p, l, L, nslots, dE)
 
 
 def canonical_pairing_modmuls(n: int, l: int) -> int:
