@@ -1266,7 +1266,7 @@ int bgn_bench_mulmod(bgn_ctx* c, int ilp, int iters, int blocks, int threads, fl
     CK(cudaEventCreate(&b));
     auto launch = [&](int it) {
       c->total_launches++;
-      if (ilp != 1 && ilp != 2 && (ilp < 10 || ilp > 79)) throw ArgErr{"ilp must be 1, 2 or a primitive mode 10..79"};
+      if (ilp != 1 && ilp != 2 && (ilp < 10 || ilp > 89)) throw ArgErr{"ilp must be 1, 2 or a primitive mode 10..89"};
       c->A->mulmod_bench(cfg(c, blocks, threads, 0), ilp, io, N, it);
     };
     launch(4);  // warm-up

@@ -33,12 +33,18 @@
 namespace bgnsim {
 static thread_local uint32_t cc = 0;
 static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
+static uint64_t nmulw = 0, nredc = 0;  // double-width products / separate reductions executed
 // Range tracker (tests only): every element written by the arithmetic below carries an upper
 // bound in multiples of p, keyed by its address, so the CPU run of the device programs PROVES
 // (by worst-case interval propagation, not by the sampled values) that the relaxed-range code
 // never overflows a product and never lets a difference go negative.
 static std::unordered_map<const void*, double> bnd;
 static double headroom = 128.0;  // floor(2^(32L) / p), set with the constants
+// double-width values (lazy reduction): value < bw * p^2 + kk * p * R
+struct WB {
+  double bw, kk;
+};
+static std::unordered_map<const void*, WB> bndw;
 static double max_bound = 0.0;   // largest bound ever attached (reported to the tests)
 static uint64_t unknown = 0;     // reads of untracked addresses (treated as < 2p)
 static uint64_t violations = 0;
@@ -63,6 +69,21 @@ inline void check(bool ok, const char* what) {
 #define BGN_SETB(a, b) bgnsim::setb((const void*)(a), (b))
 #define BGN_GETB(a) bgnsim::getb((const void*)(a))
 #define BGN_CHECK(c, w) bgnsim::check((c), (w))
+namespace bgnsim {
+inline WB getw(const void* a) {
+  auto it = bndw.find(a);
+  if (it == bndw.end()) {
+    unknown++;
+    return WB{4.0, 0.0};
+  }
+  return it->second;
+}
+inline void setw(const void* a, double bw, double kk) {
+  bndw[a] = WB{bw, kk};
+  // must fit 2L limbs: bw p^2 + kk p R < R^2  <=>  bw / H^2 + kk / H < 1
+  check(bw / (headroom * headroom) + kk / headroom < 1.0, "double-width value too large");
+}
+}
 BGN_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t t = (uint64_t)a * b;
   lo = (uint32_t)t;
@@ -329,6 +350,174 @@ struct Fp {
     } else {
       merge(r, Y, X);
     }
+  }
+
+  // ---- double-width arithmetic for lazy reduction (fused.cuh: line_mul).  A product and its
+  // Montgomery reduction are separated so that sums of products share ONE reduction:
+  //   mulw : T[2L] = a * b           (L^2 products: the CIOS rows without their reduction half; the
+  //                                   sliding window retires one finished limb of T per row)
+  //   redc : r = T / R mod p         (L^2 + L products: the rows' reduction half on T's low L limbs,
+  //                                   then + T's high L limbs); r < T/R + p
+  // One multiplication row without reduction; returns the finished lowest limb.
+  template <bool FIRST>
+  BGN_DEV static uint32_t mrow(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t (&a)[L], uint32_t s) {
+    if (FIRST) {
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) mul_wide(Y[2 * k], Y[2 * k + 1], a[2 * k + 1], s);
+      Y[W - 2] = 0;
+      Y[W - 1] = 0;
+      BGN_UNROLL
+      for (int k = 0; k < KE; k++) mul_wide(X[2 * k], X[2 * k + 1], a[2 * k], s);
+      if (2 * KE < W) {
+        X[W - 2] = 0;
+        X[W - 1] = 0;
+      }
+    } else {
+      add_cc(X[0], X[0], Y[1]);
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) madc_wide_cc3(Y[2 * k], Y[2 * k + 1], a[2 * k + 1], s, Y[2 * k + 2], Y[2 * k + 3]);
+      addc(Y[W - 2], 0, 0);
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], a[0], s);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a[2 * k], s);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+    return X[0];
+  }
+  // T = a * b, multiplier streamed from memory
+  BGN_DEV static void mulw(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t* bp) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    {
+      double A = BGN_GETB(a), B = BGN_GETB(bp);
+      BGN_CHECK(A <= bgnsim::headroom && B <= bgnsim::headroom, "wide product operand too large");
+      bgnsim::setw(T, A * B, 0.0);
+      bgnsim::nmulw++;
+    }
+#endif
+    T[0] = mrow<true>(X, Y, a, bp[0]);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      T[i] = mrow<false>(Y, X, a, bp[i]);
+      T[i + 1] = mrow<false>(X, Y, a, bp[i + 1]);
+    }
+    uint32_t hi[L];
+    if ((L & 1) == 0) {
+      T[L - 1] = mrow<false>(Y, X, a, bp[L - 1]);
+      merge(hi, X, Y);
+    } else {
+      merge(hi, Y, X);
+    }
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) T[L + j] = hi[j];
+  }
+  // one reduction row on the sliding window (no multiplication half)
+  template <bool FIRST>
+  BGN_DEV static void rrow(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t* __restrict__ pm, uint32_t np0) {
+    if (FIRST) {
+      uint32_t m = X[0] * np0;
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) mul_wide(Y[2 * k], Y[2 * k + 1], pm[2 * k + 1], m);
+      Y[W - 2] = 0;
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], pm[0], m);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], pm[2 * k], m);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    } else {
+      add_cc(X[0], X[0], Y[1]);
+      uint32_t m = X[0] * np0;
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) madc_wide_cc3(Y[2 * k], Y[2 * k + 1], pm[2 * k + 1], m, Y[2 * k + 2], Y[2 * k + 3]);
+      addc(Y[W - 2], 0, 0);
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], pm[0], m);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], pm[2 * k], m);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+  }
+  // r = T / R mod p (Montgomery reduction of a double-width value), r < T/R + p
+  BGN_DEV static void redc(uint32_t (&r)[L], const uint32_t (&T)[2 * L]) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    {
+      bgnsim::WB w = bgnsim::getw(T);
+      BGN_SETB(r, w.bw / bgnsim::headroom + w.kk + 1.0);
+      bgnsim::nredc++;
+    }
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) X[j] = T[j];
+    BGN_UNROLL
+    for (int j = L; j < W; j++) X[j] = 0;
+    rrow<true>(X, Y, pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      rrow<false>(Y, X, pm, np0);
+      rrow<false>(X, Y, pm, np0);
+    }
+    uint32_t u[L];
+    if ((L & 1) == 0) {
+      rrow<false>(Y, X, pm, np0);
+      merge(u, X, Y);
+    } else {
+      merge(u, Y, X);
+    }
+    // + high half of T
+    add_cc(r[0], u[0], T[L]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(r[j], u[j], T[L + j]);
+    addc(r[L - 1], u[L - 1], T[2 * L - 1]);
+  }
+  // S = A + B (double width)
+  BGN_DEV static void addw(uint32_t (&S)[2 * L], const uint32_t (&A)[2 * L], const uint32_t (&B)[2 * L]) {
+#ifdef BGN_HOSTSIM
+    {
+      bgnsim::WB a = bgnsim::getw(A), b = bgnsim::getw(B);
+      bgnsim::setw(S, a.bw + b.bw, a.kk + b.kk);
+    }
+#endif
+    add_cc(S[0], A[0], B[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * L - 1; j++) addc_cc(S[j], A[j], B[j]);
+    addc(S[2 * L - 1], A[2 * L - 1], B[2 * L - 1]);
+  }
+  // D = A - B + K p R (double width; K p is added to the high half); requires B <= K p R
+  BGN_DEV static void subw_k(uint32_t (&D)[2 * L], const uint32_t (&A)[2 * L], const uint32_t (&B)[2 * L],
+                             const uint32_t* kp, int K) {
+#ifdef BGN_HOSTSIM
+    {
+      bgnsim::WB a = bgnsim::getw(A), b = bgnsim::getw(B);
+      // B < bw p^2 + kk p R <= (bw / H + kk) p R with H >= 256
+      BGN_CHECK(b.bw / bgnsim::headroom + b.kk <= (double)K, "double-width difference may go negative");
+      bgnsim::setw(D, a.bw, a.kk + K);
+    }
+#endif
+    sub_cc(D[0], A[0], B[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * L - 1; j++) subc_cc(D[j], A[j], B[j]);
+    subc(D[2 * L - 1], A[2 * L - 1], B[2 * L - 1]);
+    add_cc(D[L], D[L], kp[0]);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(D[L + j], D[L + j], kp[j]);
+    addc(D[2 * L - 1], D[2 * L - 1], kp[L - 1]);
+  }
+  // D = A - B (double width) for B <= A by construction (caller's algebra)
+  BGN_DEV static void subw(uint32_t (&D)[2 * L], const uint32_t (&A)[2 * L], const uint32_t (&B)[2 * L]) {
+#ifdef BGN_HOSTSIM
+    {
+      bgnsim::WB a = bgnsim::getw(A);
+      bgnsim::setw(D, a.bw, a.kk);
+    }
+#endif
+    sub_cc(D[0], A[0], B[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * L - 1; j++) subc_cc(D[j], A[j], B[j]);
+    subc(D[2 * L - 1], A[2 * L - 1], B[2 * L - 1]);
   }
 
   // ---- relaxed-range helpers (fused.cuh): values are bounded multiples of p far below

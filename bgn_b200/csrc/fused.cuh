@@ -66,6 +66,38 @@ struct MF {
     st<L>(fim, v);       // f0 l1 + f1 l0
   }
 
+  // The same term with LAZY REDUCTION: the three products of the F_p^2 multiplication stay
+  // double-width and share two Montgomery reductions (re = redc(f0 l0 - f1 l1 + p R),
+  // im = redc((f0 + f1)(l0 + l1) - f0 l0 - f1 l1)): 5 multiplications + 4 reductions =
+  // 5 L^2 + 4 (L^2 + L) products instead of 5 (2 L^2 + L), i.e. 2669 instead of 2975 at L = 17.
+  // in: as line_mul.   out: f.re < 3p, f.im < 2p.
+  BGN_DEVNI static void line_mul_lazy(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
+                                      const uint32_t* xB, const uint32_t* yB) {
+    R a, b, c, l0, l1;
+    uint32_t T0[2 * L], T1[2 * L], S[2 * L];
+    ld<L>(a, xB);
+    mulm(l0, a, aR);
+    ld<L>(a, cR);
+    P::addn(l0, l0, a);       // l0 = cR + aR xB
+    ld<L>(a, yB);
+    mulm(l1, a, bI);          // l1 = bI yB
+    P::mulw(T0, l0, fre);     // f0 l0
+    P::mulw(T1, l1, fim);     // f1 l1
+    P::addw(S, T0, T1);
+    P::subw_k(T0, T0, T1, c_fc.p, 1);
+    P::redc(a, T0);           // re; stays in registers while the f.re slot feeds the last product
+    ld<L>(b, fre);
+    ld<L>(c, fim);
+    P::addn(b, b, c);
+    st<L>(fre, b);            // f0 + f1
+    P::addn(l0, l0, l1);
+    P::mulw(T1, l0, fre);     // (f0 + f1)(l0 + l1)
+    P::subw(T1, T1, S);       // = f0 l1 + f1 l0 >= 0
+    st<L>(fre, a);
+    P::redc(b, T1);
+    st<L>(fim, b);
+  }
+
   // f <- f^2 = (f0 + f1)(f0 - f1) + 2 f0 f1 i, 2 products.  in: < 8p.  out: < 4p.
   BGN_DEVNI static void sqr2(E fre, E fim) {
     R a, b, s, d, m;

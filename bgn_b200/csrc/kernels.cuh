@@ -644,6 +644,8 @@ __global__ void __launch_bounds__(256, 1) k_prim_bench(uint32_t* io, size_t N, i
     BGN_PRIM_FUSED(50, 2)
     BGN_PRIM_FUSED(60, 4)
     BGN_PRIM_FUSED(70, 1)
+    } else if (mode == 80) {  // lazy reduction: 5 products + 4 reductions
+      MF<L, 0>::line_mul_lazy(slot(0), slot(1), slot(7), slot(8), slot(9), slot(4), slot(5));
 #endif
     } else {
       G<L>::dbl_line(slot(4), slot(5), slot(6), slot(7), slot(8), slot(9), slot(10), slot(11), slot(12));

@@ -49,6 +49,28 @@ def final_exp_modmuls(p: int, l: int, L: int, nslots: int = 1, team: int = 1) ->
     return nslots * (5 + pow_l) + owners * fermat_inv_modmuls(p, L) + (nslots - owners) * 3
 
 
+def line_lazy(L: int) -> bool:
+    """pairing.cuh BGN_LINE_LAZY: phase B uses the lazy-reduction line_mul up to 17 limbs."""
+    return L <= 17
+
+
+def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int) -> int:
+    """32x32->64 products one unit of k_miller executes.  Every F_p product is a fused
+    multiply-and-reduce of 2L^2 + L, except that the lazy-reduction line_mul (fused.cuh) spends
+    2 (2L^2 + L) + 3 L^2 + 2 (L^2 + L) on its 5 multiplications and 4 reductions."""
+    L = pick_limbs(p)
+    mm = miller_unit_modmuls(p, n, l, dM, dE)
+    if not line_lazy(L):
+        return mm * products_per_modmul(L)
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    lines = (D + A) * dM * dE
+    full = products_per_modmul(L)
+    lazy = 2 * full + 3 * L * L + 2 * (L * L + L)
+    return (mm - 5 * lines) * full + lines * lazy
+
+
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
     """One unit of k_miller (dM Miller points x dE evaluation points, dM <= dE; all points finite):
     dbl_line 12, madd_line 13, line_mul 5, sqr2 2 per output slot."""

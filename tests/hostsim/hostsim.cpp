@@ -133,6 +133,12 @@ int hs_selftest_violation() {
   bgnsim::violations = before;
   return fired;
 }
+// double-width products / separate reductions executed (lazy reduction, fused.cuh)
+void hs_wide_count(uint64_t* out, int reset) {
+  out[0] = bgnsim::nmulw;
+  out[1] = bgnsim::nredc;
+  if (reset) bgnsim::nmulw = bgnsim::nredc = 0;
+}
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;
   if (reset) bgnsim::nmul = 0;

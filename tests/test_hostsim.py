@@ -165,11 +165,18 @@ def test_work_model_matches_executed_products(kb):
     c1 = [O.g1_mul(3 + i, S.P, par.p) for i in range(v["d1"])]
     c2 = [O.g1_mul(5 + i, S.Q, par.p) for i in range(v["d2"])]
     lib = sim.lib()
-    lib.hs_mul_count.restype = __import__("ctypes").c_uint64
+    ctypes = __import__("ctypes")
+    lib.hs_mul_count.restype = ctypes.c_uint64
     lib.hs_mul_count(1)
+    wide = (ctypes.c_uint64 * 2)()
+    lib.hs_wide_count(wide, 1)
     S.miller(c1, v["d1"], c2, v["d2"], 1, v["d1"] + v["d2"], teams_per_block=1)
-    executed = lib.hs_mul_count(1)
-    assert executed == workmodel.miller_unit_modmuls(par.p, par.n, par.l, v["d1"], v["d2"])
+    fused = lib.hs_mul_count(1)  # multiply-and-reduce products (2L^2 + L each)
+    lib.hs_wide_count(wide, 1)   # double-width multiplications (L^2) and separate reductions (L^2 + L)
+    L = S.L
+    executed = fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L)
+    assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
+    assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
 
 

@@ -10,7 +10,7 @@ the GPUs of one box (one process per GPU, torchrun), checked against the plainte
              convolution sum computed independently with torch integer arithmetic
 
 usage (N GPUs):  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
-                     tools/inner_product.py [--key-bits 1024] [--length 65536] [--d 8]
+                     tools/inner_product.py [--key-bits 1024] [--length 65536] [--slots 8]
 Prints one JSON object on rank 0."""
 import argparse
 import json
@@ -31,7 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--key-bits", type=int, default=1024)
     ap.add_argument("--length", type=int, default=1 << 16)
-    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--slots", dest="d", type=int, default=8)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
