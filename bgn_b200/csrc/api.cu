@@ -381,42 +381,76 @@ void normalize_soa(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch,
   normalize(c, j, count, scratch, o.x, o.y, (size_t)c->L, 1, o.inf);
 }
 
+// global scratch the Miller kernel needs for `count` units with teams of dE threads (0 unless
+// the key's limb count uses the interleaved layout); callers add it to their arena reservation
+size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
+  size_t pb = c->A->miller_priv_bytes();
+  int fixed = c->A->miller_fixed_threads();
+  if (!pb || !fixed || !count || dE <= 0 || dE > fixed) return 0;
+  size_t upb = (size_t)(fixed / dE);
+  return pad256(((count + upb - 1) / upb + 160) * pb) + 256;  // + one block per SM: small batches are spread out
+}
+
 // the Miller team kernel; dM <= dE
 void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
                 const GtArr& out) {
   if (!count) return;
-  size_t per_thread = (size_t)BGN_MILLER_NSLOT * c->L * 4 + 2;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
-  // A block is either ONE barrier group of up to 256 threads or TWO independent groups of 128
-  // (whole teams per group).  Two groups run ~7 % faster per wave (the groups drift apart and
-  // fill each other's pipeline bubbles; measured at L = 17, d = 11) but hold fewer teams when
-  // 128 is not a multiple of the team size; pick whichever needs less time for this batch:
-  // waves x time-per-wave, waves = ceil(units / (SMs x blocks/SM x units/block)).
-  if (TS > 128) throw ArgErr{"polynomial has too many coefficients for one thread group"};
-  if (128 * per_thread + 16 > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  int nt1 = (int)std::min<size_t>(256, (smem_max - 16) / per_thread) / 32 * 32;  // one group: whole warps
-  int tpg1 = nt1 / TS;
-  if (tpg1 == 0) throw ArgErr{"polynomial has too many coefficients for the shared-memory state at this key size"};
-  bool can2 = 2 * 128 * per_thread + 16 <= smem_max;
-  int tpg2 = 128 / TS;
-  auto cost = [&](int groups, int tpg, int nt, double twave) {
-    size_t bps = std::max<size_t>(1, std::min<size_t>(8, smem_max / (per_thread * nt + 16)));  // blocks per SM
-    size_t per_wave = (size_t)sms * bps * groups * tpg;
-    return (double)((count + per_wave - 1) / per_wave) * twave;
-  };
-  int groups = 1, tpg = tpg1, GT_ = nt1;
-  if (can2 && c->miller_groups != 1 &&
-      (c->miller_groups == 2 || cost(2, tpg2, 256, 0.932) < cost(1, tpg1, nt1, 1.0))) {
-    groups = 2;
-    tpg = tpg2;
-    GT_ = 128;
+  int groups = 1, tpg = 0, GT_ = 0;
+  size_t smem = 0;
+  if (int fixed = c->A->miller_fixed_threads()) {
+    // interleaved layout (1024-bit field): blockDim is the layout's thread stride; the private
+    // slots of every block live in a global scratch array (L2-resident)
+    if (TS > fixed) throw ArgErr{"polynomial has too many coefficients for one thread group"};
+    GT_ = fixed;
+    tpg = fixed / TS;
+    smem = c->A->miller_smem_bytes(fixed) + 16;
+    if (smem > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
+  } else {
+    size_t per_thread = c->A->miller_smem_bytes(256) / 256;  // bytes per thread (slots + 2 flag bytes)
+    // A block is either ONE barrier group of up to 256 threads or TWO independent groups of 128
+    // (whole teams per group).  Pick whichever needs less time for this batch:
+    // waves x time-per-wave, waves = ceil(units / (SMs x blocks/SM x units/block)).
+    if (TS > 128) throw ArgErr{"polynomial has too many coefficients for one thread group"};
+    if (128 * per_thread + 16 > smem_max) throw ArgErr{"field too large for the Miller kernel's shared-memory state"};
+    int nt1 = (int)std::min<size_t>(256, (smem_max - 16) / per_thread) / 32 * 32;  // one group: whole warps
+    int tpg1 = nt1 / TS;
+    if (tpg1 == 0) throw ArgErr{"polynomial has too many coefficients for the shared-memory state at this key size"};
+    bool can2 = 2 * 128 * per_thread + 16 <= smem_max;
+    int tpg2 = 128 / TS;
+    auto cost = [&](int ngroups, int tpgx, int nt, double twave) {
+      size_t bps = std::max<size_t>(1, std::min<size_t>(8, smem_max / (per_thread * nt + 16)));  // blocks per SM
+      size_t per_wave = (size_t)sms * bps * ngroups * tpgx;
+      return (double)((count + per_wave - 1) / per_wave) * twave;
+    };
+    tpg = tpg1;
+    GT_ = nt1;
+    if (can2 && c->miller_groups == 2 && cost(2, tpg2, 256, 1.0) <= cost(1, tpg1, nt1, 1.0)) {
+      groups = 2;  // tuning knob only: with the fused routines two groups no longer beat one
+      tpg = tpg2;
+      GT_ = 128;
+    }
+    smem = c->A->miller_smem_bytes(groups * GT_) + 16;
+  }
+  // A batch smaller than one full wave: use the fewest warps per scheduler that still fit the batch
+  // in one wave, in blocks of whole scheduler rounds (128 threads = one warp on each of the four
+  // schedulers).  Measured: 1 warp per scheduler finishes ~25 % sooner than 2, while an unbalanced
+  // 7-warp block is SLOWER than an 8-warp one (profiles/r01_ops1024_v13.json vs v12).
+  if (groups == 1 && count < (size_t)sms * tpg) {
+    size_t thr_per_sm = (count * TS + sms - 1) / sms;
+    int ntM = (int)std::min<size_t>(GT_, std::max<size_t>((thr_per_sm + 127) / 128 * 128, (size_t)(TS + 31) / 32 * 32));
+    tpg = std::max(1, ntM / TS);
+    GT_ = ntM;
+    if (!c->A->miller_fixed_threads()) smem = c->A->miller_smem_bytes(GT_) + 16;
   }
   size_t units_per_block = (size_t)groups * tpg;
   int nt = groups * GT_;
-  size_t smem = per_thread * nt + 16;
+  size_t nblocks = (count + units_per_block - 1) / units_per_block;
+  uint32_t* priv = nullptr;
+  if (size_t pb = c->A->miller_priv_bytes()) priv = reinterpret_cast<uint32_t*>(arena_get<uint8_t>(c, nblocks * pb));  // see miller_scratch()
   MillerArgs a;
   a.Mx = M.x;
   a.My = M.y;
@@ -427,6 +461,7 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.Einf = E.inf;
   a.NE = (int)E.N;
   a.e_bcast = e_bcast;
+  a.priv = priv;
   a.out_re = out.re;
   a.out_im = out.im;
   a.NOUT = (int)out.N;
@@ -439,7 +474,7 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.skew_cycles = c->miller_skew;
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
-  c->A->miller(cfg(c, (count + units_per_block - 1) / units_per_block, nt, smem), a);
+  c->A->miller(cfg(c, nblocks, nt, smem), a);
   t.done();
 }
 
@@ -959,7 +994,7 @@ int bgn_gt_inv_batch(bgn_ctx* c, const uint8_t* a, size_t count, uint8_t* out) {
 }
 
 static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
-  arena_reserve(c, 3 * io_bytes(c, count) + 2 * g1_bytes(c, count) + gt_bytes(c, count) + 8192);
+  arena_reserve(c, 3 * io_bytes(c, count) + 2 * g1_bytes(c, count) + gt_bytes(c, count) + miller_scratch(c, count, 1) + 8192);
   OutBuf ob = stage_out(c, out, count * 2 * c->B);
   const uint8_t* da = stage_in(c, a, count * 2 * c->B);
   G1Arr A = g1_alloc(c, count);
@@ -1002,7 +1037,7 @@ int bgn_multpoly_batch(bgn_ctx* c, const uint8_t* c1, size_t d1, const uint8_t* 
     check_count(count * (d1 + d2));
     size_t n1 = count * d1, n2 = count * d2, no = count * (d1 + d2);
     arena_reserve(c, io_bytes(c, n1) + io_bytes(c, n2) + io_bytes(c, no) + g1_bytes(c, n1) + g1_bytes(c, n2) +
-                         gt_bytes(c, no) + 8192);
+                         gt_bytes(c, no) + miller_scratch(c, count, (int)std::max(d1, d2)) + 8192);
     OutBuf ob = stage_out(c, out, no * 2 * c->B);
     const uint8_t* da = stage_in(c, c1, n1 * 2 * c->B);
     const uint8_t* db = stage_in(c, c2, n2 * 2 * c->B);
@@ -1088,7 +1123,7 @@ int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t
     CK(cudaMalloc(&c->bs_ginv, 4 * (size_t)c->L * 4));
     CK(cudaMemsetAsync(c->bs_slots, 0, hs * 4, c->stream));
     // gsk = e(P,P)^q1   (bgn.go:198-199)
-    arena_reserve(c, 4 * gt_bytes(c, 1) + 8192);
+    arena_reserve(c, 4 * gt_bytes(c, 1) + miller_scratch(c, 1, 1) + 8192);
     G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
     GtArr e = gt_alloc(c, 1), gsk = gt_alloc(c, 1), gs = gt_alloc(c, 1);
     run_miller(c, Pv, 1, Pv, 1, 0, 1, 1, e);
@@ -1161,7 +1196,7 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
     if (!in || !out || !status) throw ArgErr{"null buffer"};
     check_count(count);
     arena_reserve(c, io_bytes(c, count) + g1_bytes(c, count) + 3 * gt_bytes(c, count) + pad256(count * 8) +
-                         pad256(count) + 8192);
+                         pad256(count) + miller_scratch(c, count, 1) + 8192);
     const uint8_t* di = stage_in(c, in, count * 2 * c->B);
     OutBuf oo = stage_out(c, out, count * 8);
     OutBuf os = stage_out(c, status, count);

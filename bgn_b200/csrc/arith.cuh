@@ -22,6 +22,7 @@
 
 #ifdef BGN_HOSTSIM
 #define BGN_DEV inline
+#define BGN_HD inline
 #define BGN_DEVNI
 #define BGN_CONST static
 #define BGN_UNROLL
@@ -34,6 +35,7 @@ namespace bgnsim {
 static thread_local uint32_t cc = 0;
 static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
 static uint64_t nmulw = 0, nredc = 0;  // double-width products / separate reductions executed
+static uint64_t nmulk = 0;             // of which Karatsuba products (counted apart from nmulw)
 // Range tracker (tests only): every element written by the arithmetic below carries an upper
 // bound in multiples of p, keyed by its address, so the CPU run of the device programs PROVES
 // (by worst-case interval propagation, not by the sampled values) that the relaxed-range code
@@ -138,6 +140,7 @@ BGN_DEV void subc(uint32_t& r, uint32_t a, uint32_t b) {
 #define BGN_GETB(a) 0.0
 #define BGN_CHECK(c, w)
 #define BGN_DEV __device__ __forceinline__
+#define BGN_HD __host__ __device__ __forceinline__
 #define BGN_DEVNI __device__ __noinline__
 #define BGN_CONST __constant__
 #define BGN_UNROLL _Pragma("unroll")
@@ -264,6 +267,8 @@ struct Fp {
 
   // Same product with the multiplier streamed from memory: row i reads b[i] when it needs it, so b
   // never occupies registers and its loads overlap the previous rows.
+  // (ES = element stride of the memory operand: limb i at bp[i * ES])
+  template <int ES = 1>
   BGN_DEV static void mul_stream(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
     uint32_t X[W], Y[W];
     trk_mul(r, a, bp);
@@ -272,11 +277,11 @@ struct Fp {
     row<true>(X, Y, a, bp[0], pm, np0);
     BGN_UNROLL
     for (int i = 1; i + 1 < L; i += 2) {
-      row<false>(Y, X, a, bp[i], pm, np0);
-      row<false>(X, Y, a, bp[i + 1], pm, np0);
+      row<false>(Y, X, a, bp[i * ES], pm, np0);
+      row<false>(X, Y, a, bp[(i + 1) * ES], pm, np0);
     }
     if ((L & 1) == 0) {
-      row<false>(Y, X, a, bp[L - 1], pm, np0);
+      row<false>(Y, X, a, bp[(L - 1) * ES], pm, np0);
       merge(r, X, Y);
     } else {
       merge(r, Y, X);
@@ -318,7 +323,7 @@ struct Fp {
   // rows of code instead of L, so many products can be fused into one routine without leaving the
   // instruction cache.  The multiplicand a stays in registers, the multiplier is read from memory
   // row by row (dynamic index).
-  template <int U>
+  template <int U, int ES = 1>
   BGN_DEV static void mul_loop(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
     uint32_t X[W], Y[W];
     trk_mul(r, a, bp);
@@ -328,24 +333,24 @@ struct Fp {
     constexpr int T0 = 1 + NI * 2 * U;     // first row of the unrolled tail
     row<true>(X, Y, a, bp[0], pm, np0);
     if (NI > 0) {
-      const uint32_t* q = bp + 1;
+      const uint32_t* q = bp + ES;
       BGN_UNROLL1
       for (int it = 0; it < NI; it++) {
         BGN_UNROLL
         for (int k = 0; k < U; k++) {
-          row<false>(Y, X, a, q[2 * k], pm, np0);
-          row<false>(X, Y, a, q[2 * k + 1], pm, np0);
+          row<false>(Y, X, a, q[(2 * k) * ES], pm, np0);
+          row<false>(X, Y, a, q[(2 * k + 1) * ES], pm, np0);
         }
-        q += 2 * U;
+        q += 2 * U * ES;
       }
     }
     BGN_UNROLL
     for (int i = T0; i + 1 < L; i += 2) {
-      row<false>(Y, X, a, bp[i], pm, np0);
-      row<false>(X, Y, a, bp[i + 1], pm, np0);
+      row<false>(Y, X, a, bp[i * ES], pm, np0);
+      row<false>(X, Y, a, bp[(i + 1) * ES], pm, np0);
     }
     if ((L & 1) == 0) {
-      row<false>(Y, X, a, bp[L - 1], pm, np0);
+      row<false>(Y, X, a, bp[(L - 1) * ES], pm, np0);
       merge(r, X, Y);
     } else {
       merge(r, Y, X);
@@ -386,6 +391,7 @@ struct Fp {
     return X[0];
   }
   // T = a * b, multiplier streamed from memory
+  template <int ES = 1>
   BGN_DEV static void mulw(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t* bp) {
     uint32_t X[W], Y[W];
 #ifdef BGN_HOSTSIM
@@ -399,12 +405,12 @@ struct Fp {
     T[0] = mrow<true>(X, Y, a, bp[0]);
     BGN_UNROLL
     for (int i = 1; i + 1 < L; i += 2) {
-      T[i] = mrow<false>(Y, X, a, bp[i]);
-      T[i + 1] = mrow<false>(X, Y, a, bp[i + 1]);
+      T[i] = mrow<false>(Y, X, a, bp[i * ES]);
+      T[i + 1] = mrow<false>(X, Y, a, bp[(i + 1) * ES]);
     }
     uint32_t hi[L];
     if ((L & 1) == 0) {
-      T[L - 1] = mrow<false>(Y, X, a, bp[L - 1]);
+      T[L - 1] = mrow<false>(Y, X, a, bp[(L - 1) * ES]);
       merge(hi, X, Y);
     } else {
       merge(hi, Y, X);
@@ -412,6 +418,27 @@ struct Fp {
     BGN_UNROLL
     for (int j = 0; j < L; j++) T[L + j] = hi[j];
   }
+  // plain integer product T[2L] = a * b of two L-limb numbers held in registers (no field
+  // semantics, no range bookkeeping): the building block of the Karatsuba product below
+  BGN_DEV static void mulw_raw(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t X[W], Y[W];
+    T[0] = mrow<true>(X, Y, a, b[0]);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      T[i] = mrow<false>(Y, X, a, b[i]);
+      T[i + 1] = mrow<false>(X, Y, a, b[i + 1]);
+    }
+    uint32_t hi[L];
+    if ((L & 1) == 0) {
+      T[L - 1] = mrow<false>(Y, X, a, b[L - 1]);
+      merge(hi, X, Y);
+    } else {
+      merge(hi, Y, X);
+    }
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) T[L + j] = hi[j];
+  }
+
   // one reduction row on the sliding window (no multiplication half)
   template <bool FIRST>
   BGN_DEV static void rrow(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t* __restrict__ pm, uint32_t np0) {
@@ -675,5 +702,88 @@ struct Fp {
     BGN_UNROLL
     for (int j = 0; j < L; j++) o |= a[j] ^ b[j];
     return o == 0;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// One level of Karatsuba on the double-width product: T = a * b with the operands split into a
+// low part of N0 = L/2 limbs and a high part of N1 = L - N0 limbs,
+//   a b = z0 + (zm - z0 - z2) B^N0 + z2 B^(2 N0),  z0 = a0 b0, z2 = a1 b1, zm = (a0 + a1)(b0 + b1):
+// N0^2 + 2 N1^2 products instead of L^2 (226 instead of 289 at L = 17) for ~5L additions that sit
+// in the issue slots the multiplier leaves free.  The sums a0 + a1 and b0 + b1 need no carry
+// limb: operands are below R / 4, so their top limb is far from full (checked by the tracker).
+// ---------------------------------------------------------------------------
+template <int L>
+struct Kara {
+  static constexpr int N0 = L / 2, N1 = L - N0;
+  typedef Fp<L> P;
+
+  template <int ES = 1>
+  BGN_DEV static void mulw(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t* bp) {
+#ifdef BGN_HOSTSIM
+    {
+      double A = BGN_GETB(a), B = BGN_GETB(bp);
+      // a < R/4 keeps the top limb of a below 2^30: a0 + a1 fits N1 limbs
+      BGN_CHECK(4.0 * A <= bgnsim::headroom && 4.0 * B <= bgnsim::headroom, "Karatsuba operand too large");
+      bgnsim::setw(T, A * B, 0.0);
+      bgnsim::nmulk++;
+    }
+#endif
+    uint32_t a0[N0], a1[N1], b0[N0], b1[N1], sa[N1], sb[N1];
+    BGN_UNROLL
+    for (int j = 0; j < N0; j++) a0[j] = a[j], b0[j] = bp[j * ES];
+    BGN_UNROLL
+    for (int j = 0; j < N1; j++) a1[j] = a[N0 + j], b1[j] = bp[(N0 + j) * ES];
+    // sa = a1 + a0, sb = b1 + b0 (N1 limbs)
+    add_cc(sa[0], a1[0], a0[0]);
+    BGN_UNROLL
+    for (int j = 1; j < N1; j++) {
+      if (j < N1 - 1)
+        addc_cc(sa[j], a1[j], j < N0 ? a0[j] : 0u);
+      else
+        addc(sa[j], a1[j], j < N0 ? a0[j] : 0u);
+    }
+    add_cc(sb[0], b1[0], b0[0]);
+    BGN_UNROLL
+    for (int j = 1; j < N1; j++) {
+      if (j < N1 - 1)
+        addc_cc(sb[j], b1[j], j < N0 ? b0[j] : 0u);
+      else
+        addc(sb[j], b1[j], j < N0 ? b0[j] : 0u);
+    }
+    uint32_t z0[2 * N0], z2[2 * N1], zm[2 * N1];
+    Fp<N0>::mulw_raw(z0, a0, b0);
+    Fp<N1>::mulw_raw(z2, a1, b1);
+    Fp<N1>::mulw_raw(zm, sa, sb);
+    // zm <- zm - z0 - z2  (= a0 b1 + a1 b0 >= 0)
+    sub_cc(zm[0], zm[0], z0[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * N1; j++) {
+      if (j < 2 * N1 - 1)
+        subc_cc(zm[j], zm[j], j < 2 * N0 ? z0[j] : 0u);
+      else
+        subc(zm[j], zm[j], j < 2 * N0 ? z0[j] : 0u);
+    }
+    sub_cc(zm[0], zm[0], z2[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * N1; j++) {
+      if (j < 2 * N1 - 1)
+        subc_cc(zm[j], zm[j], z2[j]);
+      else
+        subc(zm[j], zm[j], z2[j]);
+    }
+    // T = z0 | z2 (concatenation), then += zm at limb N0
+    BGN_UNROLL
+    for (int j = 0; j < 2 * N0; j++) T[j] = z0[j];
+    BGN_UNROLL
+    for (int j = 0; j < 2 * N1; j++) T[2 * N0 + j] = z2[j];
+    add_cc(T[N0], T[N0], zm[0]);
+    BGN_UNROLL
+    for (int j = 1; j < 2 * L - N0; j++) {
+      if (j < 2 * L - N0 - 1)
+        addc_cc(T[N0 + j], T[N0 + j], j < 2 * N1 ? zm[j] : 0u);
+      else
+        addc(T[N0 + j], T[N0 + j], j < 2 * N1 ? zm[j] : 0u);
+    }
   }
 };

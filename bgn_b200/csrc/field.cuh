@@ -26,17 +26,19 @@
 // tools/primbench.py, 85.0 % -> 89.7 % of the IMAD.WIDE peak for the memory-operand product).
 typedef uint32_t* E;
 
-template <int L>
+// (ES = element stride: limb j at a[j * ES]; 1 everywhere except the Miller kernel's
+// thread-interleaved layout for the 1024-bit field, pairing.cuh)
+template <int L, int ES = 1>
 BGN_DEV void ld(uint32_t (&r)[L], const uint32_t* a) {
   BGN_SETB(r, BGN_GETB(a));
   BGN_UNROLL
-  for (int j = 0; j < L; j++) r[j] = a[j];
+  for (int j = 0; j < L; j++) r[j] = a[j * ES];
 }
-template <int L>
+template <int L, int ES = 1>
 BGN_DEV void st(E a, const uint32_t (&r)[L]) {
   BGN_SETB(a, BGN_GETB(r));
   BGN_UNROLL
-  for (int j = 0; j < L; j++) a[j] = r[j];
+  for (int j = 0; j < L; j++) a[j * ES] = r[j];
 }
 
 // F_p^2 handle: re and im

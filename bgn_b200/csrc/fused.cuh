@@ -27,16 +27,16 @@
 #pragma once
 #include "field.cuh"
 
-template <int L, int U>
+template <int L, int U, int ES = 1>
 struct MF {
   typedef Fp<L> P;
   typedef uint32_t R[L];
 
   BGN_DEV static void mulm(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* bp) {
     if (U > 0)
-      P::template mul_loop<(U > 0 ? U : 1)>(r, a, bp);
+      P::template mul_loop<(U > 0 ? U : 1), ES>(r, a, bp);
     else
-      P::mul_stream(r, a, bp);
+      P::template mul_stream<ES>(r, a, bp);
   }
   BGN_DEV static void dbl(uint32_t (&r)[L], const uint32_t (&a)[L]) { P::addn(r, a, a); }
 
@@ -45,25 +45,25 @@ struct MF {
   BGN_DEVNI static void line_mul(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
                                  const uint32_t* xB, const uint32_t* yB) {
     R a, l0, l1, t, u, v;
-    ld<L>(a, xB);
+    ld<L, ES>(a, xB);
     mulm(l0, a, aR);
-    ld<L>(a, cR);
+    ld<L, ES>(a, cR);
     P::addn(l0, l0, a);  // l0 = cR + aR xB
-    ld<L>(a, yB);
+    ld<L, ES>(a, yB);
     mulm(l1, a, bI);     // l1 = bI yB
     mulm(t, l0, fre);    // f0 l0
     mulm(u, l1, fim);    // f1 l1
-    ld<L>(a, fre);
-    ld<L>(v, fim);
+    ld<L, ES>(a, fre);
+    ld<L, ES>(v, fim);
     P::addn(a, a, v);
-    st<L>(fre, a);       // f0 + f1 (f0 itself is dead)
+    st<L, ES>(fre, a);       // f0 + f1 (f0 itself is dead)
     P::addn(l0, l0, l1);
     mulm(v, l0, fre);    // (f0 + f1)(l0 + l1)
     P::subk(a, t, u, c_fc.p2, 2);
-    st<L>(fre, a);       // f0 l0 - f1 l1
+    st<L, ES>(fre, a);       // f0 l0 - f1 l1
     P::addn(t, t, u);
     P::subk(v, v, t, c_fc.p4, 4);
-    st<L>(fim, v);       // f0 l1 + f1 l0
+    st<L, ES>(fim, v);       // f0 l1 + f1 l0
   }
 
   // The same term with LAZY REDUCTION: the three products of the F_p^2 multiplication stay
@@ -71,46 +71,66 @@ struct MF {
   // im = redc((f0 + f1)(l0 + l1) - f0 l0 - f1 l1)): 5 multiplications + 4 reductions =
   // 5 L^2 + 4 (L^2 + L) products instead of 5 (2 L^2 + L), i.e. 2669 instead of 2975 at L = 17.
   // in: as line_mul.   out: f.re < 3p, f.im < 2p.
+  // KM selects the multiplier: 0 = schoolbook rows, 1 = one level of Karatsuba (arith.cuh: Kara)
+  // for the three double-width products, 2 = also for aR xB and bI yB (then reduced separately).
+  template <int KM>
+  BGN_DEV static void mulwk(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t* bp) {
+    if (KM > 0 && L >= 9)
+      Kara<L>::template mulw<ES>(T, a, bp);
+    else
+      P::template mulw<ES>(T, a, bp);
+  }
+  template <int KM>
   BGN_DEVNI static void line_mul_lazy(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
                                       const uint32_t* xB, const uint32_t* yB) {
     R a, b, c, l0, l1;
     uint32_t T0[2 * L], T1[2 * L], S[2 * L];
-    ld<L>(a, xB);
-    mulm(l0, a, aR);
-    ld<L>(a, cR);
+    ld<L, ES>(a, xB);
+    if (KM > 1 && L >= 9) {
+      Kara<L>::template mulw<ES>(T0, a, aR);
+      P::redc(l0, T0);
+    } else {
+      mulm(l0, a, aR);
+    }
+    ld<L, ES>(a, cR);
     P::addn(l0, l0, a);       // l0 = cR + aR xB
-    ld<L>(a, yB);
-    mulm(l1, a, bI);          // l1 = bI yB
-    P::mulw(T0, l0, fre);     // f0 l0
-    P::mulw(T1, l1, fim);     // f1 l1
+    ld<L, ES>(a, yB);
+    if (KM > 1 && L >= 9) {
+      Kara<L>::template mulw<ES>(T0, a, bI);
+      P::redc(l1, T0);
+    } else {
+      mulm(l1, a, bI);        // l1 = bI yB
+    }
+    mulwk<KM>(T0, l0, fre);   // f0 l0
+    mulwk<KM>(T1, l1, fim);   // f1 l1
     P::addw(S, T0, T1);
     P::subw_k(T0, T0, T1, c_fc.p, 1);
     P::redc(a, T0);           // re; stays in registers while the f.re slot feeds the last product
-    ld<L>(b, fre);
-    ld<L>(c, fim);
+    ld<L, ES>(b, fre);
+    ld<L, ES>(c, fim);
     P::addn(b, b, c);
-    st<L>(fre, b);            // f0 + f1
+    st<L, ES>(fre, b);            // f0 + f1
     P::addn(l0, l0, l1);
-    P::mulw(T1, l0, fre);     // (f0 + f1)(l0 + l1)
+    mulwk<KM>(T1, l0, fre);   // (f0 + f1)(l0 + l1)
     P::subw(T1, T1, S);       // = f0 l1 + f1 l0 >= 0
-    st<L>(fre, a);
+    st<L, ES>(fre, a);
     P::redc(b, T1);
-    st<L>(fim, b);
+    st<L, ES>(fim, b);
   }
 
   // f <- f^2 = (f0 + f1)(f0 - f1) + 2 f0 f1 i, 2 products.  in: < 8p.  out: < 4p.
   BGN_DEVNI static void sqr2(E fre, E fim) {
     R a, b, s, d, m;
-    ld<L>(a, fre);
-    ld<L>(b, fim);
+    ld<L, ES>(a, fre);
+    ld<L, ES>(b, fim);
     P::addn(s, a, b);
     P::subk(d, a, b, c_fc.p8, 8);
     mulm(m, a, fim);     // f0 f1
-    st<L>(fre, d);
+    st<L, ES>(fre, d);
     mulm(a, s, fre);     // (f0 + f1)(f0 - f1)
-    st<L>(fre, a);
+    st<L, ES>(fre, a);
     dbl(m, m);
-    st<L>(fim, m);
+    st<L, ES>(fim, m);
   }
 
   // (X, Y, Z) <- 2 (X, Y, Z) on y^2 = x^3 + x (Jacobian) and the tangent at the old point:
@@ -120,42 +140,42 @@ struct MF {
   // value still to be read.
   BGN_DEVNI static void dbl_line(E X, E Y, E Z, E cR, E aR, E bI) {
     R x, w, xx, yy, zz, m, s;
-    ld<L>(x, X);
+    ld<L, ES>(x, X);
     mulm(xx, x, X);            // XX
-    ld<L>(w, Y);
+    ld<L, ES>(w, Y);
     mulm(yy, w, Y);            // YY
     dbl(w, w);                 // 2Y
-    ld<L>(s, Z);
+    ld<L, ES>(s, Z);
     mulm(zz, s, Z);            // ZZ
-    st<L>(bI, zz);
+    st<L, ES>(bI, zz);
     mulm(m, zz, bI);           // ZZ^2
     P::addn(m, m, xx);
     dbl(xx, xx);
     P::addn(m, m, xx);         // M = 3 XX + ZZ^2
     mulm(s, w, Z);             // Z3 = 2Y * Z
-    st<L>(Z, s);
+    st<L, ES>(Z, s);
     mulm(w, m, bI);            // aR = M ZZ   (bI still holds ZZ)
-    st<L>(aR, w);
+    st<L, ES>(aR, w);
     mulm(w, s, bI);            // bI = Z3 ZZ
-    st<L>(bI, w);
+    st<L, ES>(bI, w);
     dbl(yy, yy);               // 2 YY
-    st<L>(cR, yy);
+    st<L, ES>(cR, yy);
     mulm(w, m, X);             // M X
     P::subk(w, w, yy, c_fc.p4, 4);  // cR = M X - 2 YY   (kept in registers until the slot is free)
     dbl(x, x);
     mulm(s, x, cR);            // S = 2X * 2YY = 4 X YY
     mulm(zz, yy, cR);          // 4 YY^2
-    st<L>(cR, w);
-    st<L>(Y, m);
+    st<L, ES>(cR, w);
+    st<L, ES>(Y, m);
     mulm(xx, m, Y);            // M^2
     dbl(w, s);
     P::subk(xx, xx, w, c_fc.p4, 4);  // X3 = M^2 - 2S
-    st<L>(X, xx);
+    st<L, ES>(X, xx);
     P::subk(s, s, xx, c_fc.p8, 8);   // S - X3
     mulm(w, s, Y);             // M (S - X3)
     dbl(zz, zz);               // 8 YY^2
     P::subk(w, w, zz, c_fc.p4, 4);
-    st<L>(Y, w);               // Y3
+    st<L, ES>(Y, w);               // Y3
   }
 
   // (X, Y, Z) <- (X, Y, Z) + (xA, +-yA) (mixed) and the chord through them: aR = r = 2 (S2 - Y),
@@ -165,49 +185,49 @@ struct MF {
   BGN_DEVNI static void madd_line(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E cR, E aR,
                                   E bI) {
     R xa, ya, z, h, r, w, v, c;
-    ld<L>(xa, xA);
-    ld<L>(ya, yA);
+    ld<L, 1>(xa, xA);  // the affine point lives in the batch arrays (unit stride)
+    ld<L, 1>(ya, yA);
     if (negate) P::negk(ya, ya, c_fc.p2, 2);  // 2p - yA = -yA
-    ld<L>(z, Z);
+    ld<L, ES>(z, Z);
     mulm(w, z, Z);             // ZZ
-    st<L>(bI, w);
+    st<L, ES>(bI, w);
     mulm(h, xa, bI);           // U2 = xA ZZ
-    ld<L>(w, X);
+    ld<L, ES>(w, X);
     P::subk(h, h, w, c_fc.p16, 16);  // H = U2 - X
     mulm(w, z, bI);            // Z ZZ
-    st<L>(aR, w);
+    st<L, ES>(aR, w);
     mulm(r, ya, aR);           // S2 = yA Z^3
-    ld<L>(w, Y);
+    ld<L, ES>(w, Y);
     P::subk(r, r, w, c_fc.p16, 16);
     dbl(r, r);                 // r = 2 (S2 - Y)
-    st<L>(aR, r);              // aR = r
+    st<L, ES>(aR, r);              // aR = r
     dbl(w, h);
-    st<L>(cR, w);              // 2H
+    st<L, ES>(cR, w);              // 2H
     mulm(v, z, cR);            // Z3 = Z * 2H
-    st<L>(Z, v);
-    st<L>(bI, v);              // bI = Z3
+    st<L, ES>(Z, v);
+    st<L, ES>(bI, v);              // bI = Z3
     mulm(c, xa, aR);           // r xA
     mulm(w, ya, Z);            // yA Z3
     P::subk(c, c, w, c_fc.p2, 2);   // cR, kept in registers until the slot is free
-    ld<L>(w, cR);
+    ld<L, ES>(w, cR);
     mulm(v, w, cR);            // I = (2H)^2
-    ld<L>(z, X);               // z now holds X
-    st<L>(X, v);
+    ld<L, ES>(z, X);               // z now holds X
+    st<L, ES>(X, v);
     mulm(w, h, X);             // J = H I
     mulm(v, z, X);             // V = X I
-    st<L>(cR, c);
+    st<L, ES>(cR, c);
     mulm(c, r, aR);            // r^2
     dbl(z, v);
     P::addn(z, z, w);          // J + 2V
     P::subk(c, c, z, c_fc.p4, 4);   // X3 = r^2 - J - 2V
-    st<L>(X, c);
+    st<L, ES>(X, c);
     mulm(h, w, Y);             // Y J
     P::subk(v, v, c, c_fc.p16, 16); // V - X3
-    st<L>(Y, v);
+    st<L, ES>(Y, v);
     mulm(w, r, Y);             // r (V - X3)
     dbl(h, h);
     P::subk(w, w, h, c_fc.p4, 4);
-    st<L>(Y, w);               // Y3 = r (V - X3) - 2 Y J
+    st<L, ES>(Y, w);               // Y3 = r (V - X3) - 2 Y J
   }
 
   // ---- final exponentiation f^((p^2-1)/n) = (conj(f)/f)^l = (conj(f)^2 / N(f))^l, fused.
@@ -215,26 +235,26 @@ struct MF {
   // in: f < 8p.  out: f.re < 4p, f.im < 4p, nrm < 4p.
   BGN_DEVNI static void fe_prepare(E fre, E fim, E nrm) {
     R a, b, t, u, v;
-    ld<L>(a, fre);
-    ld<L>(b, fim);
+    ld<L, ES>(a, fre);
+    ld<L, ES>(b, fim);
     mulm(t, a, fre);   // f0^2
     mulm(u, b, fim);   // f1^2
     mulm(v, a, fim);   // f0 f1
     P::addn(a, t, u);
-    st<L>(nrm, a);
+    st<L, ES>(nrm, a);
     P::subk(t, t, u, c_fc.p2, 2);
-    st<L>(fre, t);
+    st<L, ES>(fre, t);
     dbl(v, v);
     P::negk(v, v, c_fc.p4, 4);
-    st<L>(fim, v);
+    st<L, ES>(fim, v);
   }
   // r <- a^(p-2) (Fermat inverse; 0 -> 0) with the running power kept in registers: bits(p) - 1
   // squarings and wt(p-2) - 1 products, no loads or stores in between.  The exponent is a key
   // constant, so control flow is uniform.  r may alias a.  in: a < 16p.  out: r < 2p.
   BGN_DEVNI static void fp_inv(E r, const uint32_t* a) {
     R x, y;
-    ld<L>(x, a);
-    ld<L>(y, a);
+    ld<L, ES>(x, a);
+    ld<L, ES>(y, a);
     int top = 32 * L - 1;
     while (top > 0 && !((c_fc.p[top >> 5] >> (top & 31)) & 1)) top--;
     // exponent e = p - 2: p = 3 (mod 4), so subtracting 2 only clears bit 1 (no borrow)
@@ -245,51 +265,51 @@ struct MF {
       P::mul(y, y, y);
       if ((limb >> (bit & 31)) & 1) P::mul(y, y, x);
     }
-    st<L>(r, y);
+    st<L, ES>(r, y);
   }
   // r <- a * b in F_p (register operand a, memory operand b); r may alias either
   BGN_DEVNI static void fp_mul(E r, const uint32_t* a, const uint32_t* b) {
     R x, y;
-    ld<L>(x, a);
+    ld<L, ES>(x, a);
     mulm(y, x, b);
-    st<L>(r, y);
+    st<L, ES>(r, y);
   }
   // f <- f * s for s in F_p.  2 products.
   BGN_DEVNI static void scale2(E fre, E fim, const uint32_t* s) {
     R x, y;
-    ld<L>(x, s);
+    ld<L, ES>(x, s);
     mulm(y, x, fre);
-    st<L>(fre, y);
+    st<L, ES>(fre, y);
     mulm(y, x, fim);
-    st<L>(fim, y);
+    st<L, ES>(fim, y);
   }
   // f <- f * g in F_p^2 (Karatsuba, 3 products).  in: f, g < 8p.  out: f.re < 4p, f.im < 6p.
   BGN_DEVNI static void mul2(E fre, E fim, const uint32_t* gre, const uint32_t* gim) {
     R a, b, t, u, v;
-    ld<L>(a, fre);
-    ld<L>(b, fim);
+    ld<L, ES>(a, fre);
+    ld<L, ES>(b, fim);
     mulm(t, a, gre);   // f0 g0
     mulm(u, b, gim);   // f1 g1
     P::addn(a, a, b);
-    ld<L>(b, gre);
-    ld<L>(v, gim);
+    ld<L, ES>(b, gre);
+    ld<L, ES>(v, gim);
     P::addn(b, b, v);
-    st<L>(fre, b);     // g0 + g1 (f0 is dead)
+    st<L, ES>(fre, b);     // g0 + g1 (f0 is dead)
     mulm(v, a, fre);   // (f0 + f1)(g0 + g1)
     P::subk(a, t, u, c_fc.p2, 2);
-    st<L>(fre, a);
+    st<L, ES>(fre, a);
     P::addn(t, t, u);
     P::subk(v, v, t, c_fc.p4, 4);
-    st<L>(fim, v);
+    st<L, ES>(fim, v);
   }
   // bring both coordinates back to [0, 2p) (what the GT kernels downstream expect).  in: < 8p.
   BGN_DEVNI static void norm2(E fre, E fim) {
     R a;
-    ld<L>(a, fre);
+    ld<L, ES>(a, fre);
     P::norm2p(a, a);
-    st<L>(fre, a);
-    ld<L>(a, fim);
+    st<L, ES>(fre, a);
+    ld<L, ES>(a, fim);
     P::norm2p(a, a);
-    st<L>(fim, a);
+    st<L, ES>(fim, a);
   }
 };

@@ -19,6 +19,9 @@ cudaError_t upload(const FieldConsts* fc, const PairConsts* pc, cudaStream_t s) 
 cudaError_t miller_set_smem(size_t smem) {
   return cudaFuncSetAttribute(k_miller<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
+size_t miller_smem_bytes(int nt) { return MillerTeam<LL>::smem_words(nt) * 4; }
+size_t miller_priv_bytes() { return MillerTeam<LL>::priv_words() * 4; }
+int miller_fixed_threads() { return MillerTeam<LL>::fixed_threads(); }
 void miller(LaunchCfg cfg, const MillerArgs& a) { k_miller<LL><<<CFG>>>(a); }
 void gt_mul(LaunchCfg cfg, const GtBinArgs& a) { k_gt_mul<LL><<<CFG>>>(a); }
 void gt_pow(LaunchCfg cfg, const GtPowArgs& a) { k_gt_pow<LL><<<CFG>>>(a); }
@@ -44,7 +47,8 @@ void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
   else
     k_mulmod_bench<LL, 1><<<CFG>>>(io, N, iters);
 }
-const LOpsA ops = {LL,        upload,         miller_set_smem, miller,     gt_mul,      gt_pow,
+const LOpsA ops = {LL,        upload,         miller_set_smem, miller_smem_bytes, miller_priv_bytes, miller_fixed_threads,
+                   miller,     gt_mul,      gt_pow,
                    gt_reduce, fp2_from_bytes, fp2_to_bytes,    bsgs_build, bsgs_lookup, mulmod_bench};
 }  // namespace
 #define BGN_CAT2(a, b) a##b

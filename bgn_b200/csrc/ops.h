@@ -17,6 +17,9 @@ struct LOpsA {
   int L;
   cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
   cudaError_t (*miller_set_smem)(size_t smem);
+  size_t (*miller_smem_bytes)(int nt);   // shared memory a block of nt threads needs
+  size_t (*miller_priv_bytes)();         // global scratch per block (0: all state in shared memory)
+  int (*miller_fixed_threads)();         // != 0: the layout fixes blockDim to this value
   void (*miller)(LaunchCfg, const MillerArgs&);
   void (*gt_mul)(LaunchCfg, const GtBinArgs&);
   void (*gt_pow)(LaunchCfg, const GtPowArgs&);

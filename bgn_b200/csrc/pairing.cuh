@@ -34,6 +34,22 @@
 #ifndef BGN_LINE_LAZY
 #define BGN_LINE_LAZY (BGN_L <= 17 ? 1 : 0)
 #endif
+// Thread-interleaved layout with the thread-private state in global memory (the 1024-bit field):
+// 12 slots of 33 limbs are 1.5 KB per thread, so shared memory holds only 4 warps per SM -- one per
+// scheduler, where a single warp cannot issue more than ~2/3 of the multiplier's rate.  With
+// BGN_MILLER_GP the 7 private slots (accumulators, Miller point) live in an L2-resident scratch
+// array and only the 5 slots other threads read (line, evaluation point) stay in shared memory;
+// every slot is laid out [slot][limb][thread] with a compile-time thread stride BGN_MILLER_NT, so
+// limb addresses are immediates and a warp's access to one limb is one 128-byte line.
+#ifndef BGN_MILLER_GP
+#define BGN_MILLER_GP (BGN_L > 17 ? 1 : 0)
+#endif
+#ifndef BGN_MILLER_NT
+#define BGN_MILLER_NT 256
+#endif
+#ifndef BGN_LINE_KARATSUBA
+#define BGN_LINE_KARATSUBA 0  // KM of fused.cuh line_mul_lazy
+#endif
 #ifndef BGN_MILLER_LOOP_A
 #define BGN_MILLER_LOOP_A (BGN_L <= 17 ? 0 : 4)
 #endif
@@ -86,16 +102,19 @@ template <int L>
 struct MillerTeam {
   typedef F<L> FF;
   typedef G<L> GG;
-  typedef MF<L, BGN_MILLER_LOOP> M;      // phase B
-  typedef MF<L, BGN_MILLER_LOOP_A> MA;   // phase A
+  static constexpr bool GP = BGN_MILLER_GP != 0;
+  static constexpr int NT = BGN_MILLER_NT;
+  static constexpr int ES = GP ? NT : 1;          // element stride of every slot
+  typedef MF<L, BGN_MILLER_LOOP, ES> M;      // phase B
+  typedef MF<L, BGN_MILLER_LOOP_A, ES> MA;   // phase A
   // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
   // the line it publishes, its evaluation point.  The loop's routines are fused (fused.cuh) and
   // keep their temporaries in registers.
   enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_EX = 10, S_EY = 11,
-         NSLOT = BGN_MILLER_NSLOT };
+         NSLOT = BGN_MILLER_NSLOT, NPRIV = BGN_MILLER_NPRIV };  // slots < NPRIV are thread-private
 
   const MillerArgs& a;
-  uint32_t* smem;   // NSLOT*nt elements of L words ([slot][thread][limb]), then nt bytes flagsA, nt bytes flagsB
+  uint32_t* smem;   // the block's slots (layout: slot()), then one flagsA and one flagsB byte per thread
   int nt, tid, bid;
   int t, team, unit, group;
   bool active;
@@ -116,36 +135,68 @@ struct MillerTeam {
     unit = (bid * groups + group) * a.teams_per_group + team;
     active = team < a.teams_per_group && unit < a.count;
   }
-  static BGN_DEV size_t smem_bytes(int nt) { return (size_t)NSLOT * L * nt * 4 + 2 * (size_t)nt; }
-  // thread stride L words is odd for every supported L, so a warp touching one limb of one slot
-  // hits 32 different banks
-  BGN_DEV E slot(int thread, int k) const { return smem + ((size_t)k * nt + thread) * L; }
-  BGN_DEV uint8_t* flagsA() const { return reinterpret_cast<uint8_t*>(smem + (size_t)NSLOT * L * nt); }
-  BGN_DEV uint8_t* flagsB() const { return flagsA() + nt; }
-  BGN_DEV E2 facc(int thread, int s) const { return mke2(slot(thread, S_F0 + 2 * s), slot(thread, S_F0 + 2 * s + 1)); }
+  // shared-memory words a block of nt threads needs (host side: api.cu, hostsim.cpp)
+  static BGN_HD size_t smem_words(int nt) {
+    return GP ? (size_t)(NSLOT - NPRIV) * L * NT + (2 * (size_t)NT + 3) / 4 : (size_t)NSLOT * L * nt + (2 * (size_t)nt + 3) / 4;
+  }
+  // global scratch words per block (GP only)
+  static BGN_HD size_t priv_words() { return GP ? (size_t)NPRIV * L * NT : 0; }
+  static BGN_HD int fixed_threads() { return GP ? NT : 0; }  // interleaved layout: blockDim is fixed
+  // unit-stride layout: thread stride L words is odd for every supported L, so a warp touching one
+  // limb of one slot hits 32 different banks; interleaved layout: consecutive threads, consecutive words
+  BGN_DEV E slot(int thread, int k) const {
+    if (GP) {
+      if (k < NPRIV) return a.priv + ((size_t)bid * NPRIV + k) * L * NT + thread;
+      return smem + (size_t)(k - NPRIV) * L * NT + thread;
+    }
+    return smem + ((size_t)k * nt + thread) * L;
+  }
+  BGN_DEV uint8_t* flagsA() const {
+    return reinterpret_cast<uint8_t*>(smem + (GP ? (size_t)(NSLOT - NPRIV) * L * NT : (size_t)NSLOT * L * nt));
+  }
+  BGN_DEV uint8_t* flagsB() const { return flagsA() + (GP ? NT : nt); }
   BGN_DEV size_t eidx(int k) const { return a.e_bcast ? (size_t)k : (size_t)unit * a.dE + k; }
+  // element moves between slots (stride ES) and the batch arrays (unit stride)
+  BGN_DEV static void s_in(E dst, const uint32_t* src) {
+    BGN_SETB(dst, BGN_GETB(src));
+    for (int j = 0; j < L; j++) dst[j * ES] = src[j];
+  }
+  BGN_DEV static void s_out(uint32_t* dst, const uint32_t* src) {
+    BGN_SETB(dst, BGN_GETB(src));
+    for (int j = 0; j < L; j++) dst[j] = src[j * ES];
+  }
+  BGN_DEV static void s_copy(E dst, const uint32_t* src) {
+    BGN_SETB(dst, BGN_GETB(src));
+    for (int j = 0; j < L; j++) dst[j * ES] = src[j * ES];
+  }
+  BGN_DEV static void s_zero(E dst) {
+    BGN_SETB(dst, 0.0);
+    for (int j = 0; j < L; j++) dst[j * ES] = 0;
+  }
 
   BGN_DEV void init() {
     flagsA()[tid] = 0;
     flagsB()[tid] = 0;
     if (!active) return;
-    FF::set_one2(facc(tid, 0));
-    FF::set_one2(facc(tid, 1));
+    for (int s = 0; s < 2; s++) {
+      s_in(slot(tid, S_F0 + 2 * s), c_fc.one);
+      s_zero(slot(tid, S_F0 + 2 * s + 1));
+    }
     if (t < a.dM) {
       size_t idx = (size_t)unit * a.dM + t;
       bool inf = a.Minf[idx] != 0;
       flagsA()[tid] = inf ? 0 : 1;
       if (!inf) {
-        FF::copy(slot(tid, S_X), (a.Mx + (size_t)(idx) * L));
-        FF::copy(slot(tid, S_Y), (a.My + (size_t)(idx) * L));
-        FF::set_one(slot(tid, S_Z));
+        s_in(slot(tid, S_X), a.Mx + idx * L);
+        s_in(slot(tid, S_Y), a.My + idx * L);
+        s_in(slot(tid, S_Z), c_fc.one);
       }
     }
     bool einf = a.Einf[eidx(t)] != 0;
     flagsB()[tid] = einf ? 0 : 1;
     if (!einf) {
-      FF::copy(slot(tid, S_EX), a.Ex + eidx(t) * L);
-      FF::copy(slot(tid, S_EY), a.Ey + eidx(t) * L);
+      s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);
+      s_in(slot(tid, S_EY), a.Ey + eidx(t) * L);
     }
   }
 
@@ -181,7 +232,7 @@ struct MillerTeam {
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
 #if BGN_LINE_LAZY
-      M::line_mul_lazy(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
+      M::template line_mul_lazy<BGN_LINE_KARATSUBA>(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
                        slot(base + i, S_BI), slot(base + k, S_EX), slot(base + k, S_EY));
 #else
       M::line_mul(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
@@ -215,8 +266,8 @@ struct MillerTeam {
       if (!(s ? own1 : own0)) continue;
       E fr = s ? f1r : f0r, fi = s ? f1i : f0i;
       MA::scale2(fr, fi, s ? i1 : i0);  // g = conj(f)^2 / N(f) = f^(p-1)
-      FF::copy(n0, fr);
-      FF::copy(n1, fi);
+      s_copy(n0, fr);
+      s_copy(n1, fi);
       uint64_t l = c_pc.l;
       int top = 63;
       while (top > 0 && !((l >> top) & 1)) top--;
@@ -226,8 +277,8 @@ struct MillerTeam {
       }
       MA::norm2(fr, fi);
       size_t o = (size_t)unit * a.out_slots + t + s * a.dE;
-      FF::copy(a.out_re + o * L, fr);
-      FF::copy(a.out_im + o * L, fi);
+      s_out(a.out_re + o * L, fr);
+      s_out(a.out_im + o * L, fi);
     }
     if (t == 0) {
       for (int j = nslots; j < a.out_slots; j++) {  // padding slot(s): GT identity (poly.go:130-137)

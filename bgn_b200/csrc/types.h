@@ -27,7 +27,8 @@ struct PairConsts {
   int8_t naf[BGN_MAX_NAF];
 };
 
-#define BGN_MILLER_NSLOT 12  // shared-memory F_p slots per thread of the Miller team kernel
+#define BGN_MILLER_NSLOT 12  // F_p slots per thread of the Miller team kernel
+#define BGN_MILLER_NPRIV 7   // of which thread-private (accumulators, Miller point): slots 0..6
 struct MillerArgs {
   const uint32_t* Mx;  // Miller-side points, Montgomery [L][NM], index unit*dM + i
   const uint32_t* My;
@@ -35,6 +36,7 @@ struct MillerArgs {
   const uint32_t* Ex;   // evaluation-side points, SoA [L][NE], index unit*dE + k
   const uint32_t* Ey;
   const uint8_t* Einf;
+  uint32_t* priv;    // global scratch for the thread-private slots (interleaved layout only, else null)
   uint32_t* out_re;  // GT out, Montgomery [L][NOUT], index unit*out_slots + j
   uint32_t* out_im;
   int NM, NE, NOUT;

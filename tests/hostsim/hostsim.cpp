@@ -13,8 +13,11 @@
 
 namespace {
 template <int L>
-void sim_miller(const MillerArgs& a, int nblocks, int nt) {
-  std::vector<uint32_t> smem((size_t)BGN_MILLER_NSLOT * L * nt + nt + 8);
+void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
+  std::vector<uint32_t> smem(MillerTeam<L>::smem_words(nt) + 8);
+  std::vector<uint32_t> priv((size_t)nblocks * MillerTeam<L>::priv_words() + 8);
+  MillerArgs a = a0;
+  a.priv = priv.data();
   for (int b = 0; b < nblocks; b++) {
     std::vector<MillerTeam<L>> T;
     T.reserve(nt);
@@ -137,7 +140,8 @@ int hs_selftest_violation() {
 void hs_wide_count(uint64_t* out, int reset) {
   out[0] = bgnsim::nmulw;
   out[1] = bgnsim::nredc;
-  if (reset) bgnsim::nmulw = bgnsim::nredc = 0;
+  out[2] = bgnsim::nmulk;
+  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = 0;
 }
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;

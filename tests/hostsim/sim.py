@@ -33,7 +33,7 @@ class PairConsts(C.Structure):
 
 class MillerArgs(C.Structure):
     _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
-                ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
+                ("priv", u32p), ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
                 ("e_bcast", C.c_int), ("dM", C.c_int), ("dE", C.c_int), ("out_slots", C.c_int), ("count", C.c_int),
                 ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int)]
 
@@ -84,16 +84,16 @@ class BsgsLookupArgs(C.Structure):
 _lib = None
 
 
-def build(loop: Optional[int] = None) -> str:
+def build(loop: Optional[int] = None, extra: Sequence[str] = (), tag: str = "") -> str:
     """(Re)build libhostsim.so when a device header is newer than it.  `loop` builds a variant whose
     fused Miller routines use Fp::mul_loop<loop> (0 = unrolled products) instead of the default."""
-    so = os.path.join(HERE, "libhostsim.so" if loop is None else "libhostsim_u%d.so" % loop)
+    so = os.path.join(HERE, "libhostsim%s%s.so" % ("" if loop is None else "_u%d" % loop, tag))
     src = os.path.join(HERE, "hostsim.cpp")
     csrc = os.path.join(ROOT, "bgn_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         flags = [] if loop is None else ["-DBGN_MILLER_LOOP=%d" % loop, "-DBGN_MILLER_LOOP_A=%d" % loop]
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC"] + flags + ["-o", so, src])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC"] + flags + list(extra) + ["-o", so, src])
     return so
 
 
@@ -104,11 +104,11 @@ def lib():
     return _lib
 
 
-def use_variant(loop: Optional[int]):
-    """Switch the simulator to a loop-shape variant (None = default build); callers re-activate
-    their Sim afterwards (constants live in the library)."""
+def use_variant(loop: Optional[int], extra: Sequence[str] = (), tag: str = ""):
+    """Switch the simulator to a build variant (loop shape and/or extra -D flags; None = default
+    build); callers re-activate their Sim afterwards (constants live in the library)."""
     global _lib
-    _lib = C.CDLL(build(loop))
+    _lib = C.CDLL(build(loop, extra, tag))
     return _lib
 
 
@@ -216,7 +216,7 @@ class Sim:
         nout = count * out_slots
         ore = np.zeros((nout, self.L), dtype=np.uint32)
         oim = np.zeros((nout, self.L), dtype=np.uint32)
-        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), Mx.shape[0],
+        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
                        teams_per_block * dE + 1, 0)  # one idle thread per group: exercises the inactive path
         groups = 2 if count > teams_per_block else 1

@@ -168,7 +168,7 @@ def test_work_model_matches_executed_products(kb):
     ctypes = __import__("ctypes")
     lib.hs_mul_count.restype = ctypes.c_uint64
     lib.hs_mul_count(1)
-    wide = (ctypes.c_uint64 * 2)()
+    wide = (ctypes.c_uint64 * 3)()
     lib.hs_wide_count(wide, 1)
     S.miller(c1, v["d1"], c2, v["d2"], 1, v["d1"] + v["d2"], teams_per_block=1)
     fused = lib.hs_mul_count(1)  # multiply-and-reduce products (2L^2 + L each)
@@ -207,6 +207,30 @@ def test_sim_miller_loop_variants(loop):
             v = g["multpoly"]
             c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
             assert S.multpoly(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+            v = g["pair"]
+            assert S.pair(g1s(par, v["a"]), g1s(par, v["b"])) == gts(par, v["out"])
+            _, _, unknown, violations = S.range_report()
+            assert unknown == 0 and violations == 0
+    finally:
+        sim.use_variant(None)
+
+
+@pytest.mark.parametrize("flags,tag", [(("-DBGN_MILLER_GP=1", "-DBGN_MILLER_NT=32", "-DBGN_LINE_LAZY=0"), "_gp"),
+                                       (("-DBGN_MILLER_GP=1", "-DBGN_MILLER_NT=32"), "_gplazy"),
+                                       (("-DBGN_LINE_KARATSUBA=2",), "_kara")])
+def test_sim_miller_layout_and_multiplier_variants(flags, tag):
+    """Build variants of the Miller kernel: the thread-interleaved layout with the private slots in
+    global memory (what the 1024-bit field ships with) and the Karatsuba multiplier (measured, not
+    shipped) produce the same bytes and stay within the proven ranges."""
+    try:
+        sim.use_variant(None, flags, tag)
+        for kb in (64, 512):
+            g, par, S, _ = setup(kb)
+            v = g["multpoly"]
+            c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+            assert S.multpoly(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+            if kb == 64:
+                assert S.multpoly(c1 * 3, v["d1"], c2 * 3, v["d2"], 3) == gts(par, v["out"]) * 3
             v = g["pair"]
             assert S.pair(g1s(par, v["a"]), g1s(par, v["b"])) == gts(par, v["out"])
             _, _, unknown, violations = S.range_report()
