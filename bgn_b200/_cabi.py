@@ -44,6 +44,12 @@ SIGNATURES = {
     "bgn_l2_sum_reduce": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_size_t, u8p]),
     "bgn_gt_pow_secret_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, u8p]),
     "bgn_decrypt_batch": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_size_t, u8p, u8p]),
+    "bgn_g1_blind_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),
+    "bgn_gt_blind_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),
+    "bgn_multconstpoly_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.c_int,
+                                           C.c_size_t, u8p]),
+    "bgn_evalpoly_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_int, C.c_uint32, C.c_size_t, u8p]),
+    "bgn_make_poly_l2_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_size_t, u8p]),
     "bgn_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "bgn_timing_reset": (C.c_int, [C.c_void_p]),
     "bgn_timing_get": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -115,7 +115,6 @@ class PublicKey:
         self._table = EncodingTable(polyBase)  # computeEncodingTable, bgn.go:135
         self.engine = Engine(p, n, l, P, Q, device)
         self._secret_set = False
-        self._qq: Optional[bytes] = None
 
     @classmethod
     def FromPBCParams(cls, params: str, P: bytes, Q: bytes, MsgSpace: int, **kw) -> "PublicKey":
@@ -148,18 +147,22 @@ class PublicKey:
         return secrets.randbelow(self.N) if r is None else r
 
     def _blind_g1(self, elem: np.ndarray, r: Optional[int]) -> np.ndarray:
-        """+ r*Q (bgn.go:264-268, 491-495)."""
-        h = self.engine.encrypt_batch(np.zeros(1, dtype=np.int64), self.engine.scalars_be([self._rand(r)]))
-        return self.engine.g1_add_batch(elem, h)
+        """+ r*Q (bgn.go:264-268, 491-495): bgn_g1_blind_batch, fixed-base windows of Q."""
+        return self.engine.g1_blind_batch(elem, self.engine.scalars_be([self._rand(r) % self.N]))
 
     def _blind_gt(self, elem: np.ndarray, r: Optional[int]) -> np.ndarray:
-        """* e(Q,Q)^r (bgn.go:283-287, 306-310, 469-474); e(Q,Q) is computed once per key."""
-        if self._qq is None:
-            q = np.frombuffer(self.Q, dtype=np.uint8)
-            self._qq = self.engine.pair_batch(q, q).tobytes()
-        e = self.engine.gt_pow_batch(np.frombuffer(self._qq, dtype=np.uint8), self.engine.scalars_be([self._rand(r)]),
-                                     self.engine.scalar_bytes)
-        return self.engine.gt_mul_batch(elem, e)
+        """* e(Q,Q)^r (bgn.go:283-287, 306-310, 469-474): bgn_gt_blind_batch; e(Q,Q) is a fixed-base
+        table built once per key (the reference recomputes the pairing per call)."""
+        return self.engine.gt_blind_batch(elem, self.engine.scalars_be([self._rand(r) % self.N]))
+
+    def _rand_be(self, count: int, rs=None):
+        """count scalars below N as the C-ABI's big-endian buffer (newCryptoRandom, bgn.go:567-574)"""
+        if rs is None:
+            rs = [secrets.randbelow(self.N) for _ in range(count)]
+        if hasattr(rs, "dtype") or type(rs).__module__.startswith("torch"):
+            return rs  # already a packed buffer
+        assert len(rs) == count
+        return self.engine.scalars_be([int(r) % self.N for r in rs])
 
     # ---------------------------------------------------------------- plaintexts
     def NewPolyPlaintext(self, m: float) -> PolyPlaintext:
@@ -362,11 +365,43 @@ class PublicKey:
         res = self.engine.gt_mul_batch(a.data, b.data) if a.L2 else self.engine.g1_add_batch(a.data, b.data)
         return PolyCiphertextBatch(res, a.count, a.Degree, a.ScaleFactor, a.L2)
 
-    def MultPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch) -> PolyCiphertextBatch:
+    def MultPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, rs=None) -> PolyCiphertextBatch:
+        """MultPoly over a batch.  Non-deterministic keys re-randomise every output slot: the
+        reference multiplies e(Q,Q)^r into each of the d1*d2 coefficient pairings (bgn.go:302-311 via
+        poly.go:140-152), which per slot is e(Q,Q)^(sum of its r's); `rs` injects one scalar per
+        output slot (count * (d1+d2-1) ... the padding slot included: count * (d1+d2))."""
         if a.L2 or b.L2 or a.count != b.count:
             raise ValueError("MultPolyBatch needs two level-1 batches of equal count")
         out = self.engine.multpoly_batch(a.data, a.Degree, b.data, b.Degree, a.count)
+        if not self.Deterministic:
+            out = self.engine.gt_blind_batch(out, self._rand_be(a.count * (a.Degree + b.Degree), rs))
         return PolyCiphertextBatch(out, a.count, a.Degree + b.Degree, a.ScaleFactor + b.ScaleFactor, True)
+
+    def MakePolyL2Batch(self, a: PolyCiphertextBatch) -> PolyCiphertextBatch:
+        """MakePolyL2 (poly.go:159-163) over a batch: e(c_i, P) per slot plus the identity top slot."""
+        if a.L2:
+            raise ValueError("MakePolyL2Batch needs a level-1 batch")
+        out = self.engine.make_poly_l2_batch(a.data, a.Degree, a.count)
+        return PolyCiphertextBatch(out, a.count, a.Degree + 1, a.ScaleFactor, True)
+
+    def MultConstPolyBatch(self, a: PolyCiphertextBatch, constant: float) -> PolyCiphertextBatch:
+        """MultConstPoly (poly.go:71-120) over a batch: one kernel launch, one thread per output slot."""
+        poly = self.NewUnbalancedPlaintext(abs(constant))
+        out = self.engine.multconstpoly_batch(a.data, a.Degree, a.L2, poly.Coefficients[: poly.Degree], constant < 0,
+                                              a.count)
+        return PolyCiphertextBatch(out, a.count, a.Degree + poly.Degree, a.ScaleFactor + poly.ScaleFactor, a.L2)
+
+    def EvalPolyBatch(self, a: PolyCiphertextBatch):
+        """EvalPoly (poly.go:58-68) over a batch -> count elements (level of the batch)."""
+        return self.engine.evalpoly_batch(a.data, a.Degree, a.L2, self.PolyEncodingParams.PolyBase, a.count)
+
+    def AddPolyBatchRand(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, rs=None) -> PolyCiphertextBatch:
+        """AddPolyBatch followed by the per-coefficient re-randomisation of a non-deterministic key."""
+        res = self.AddPolyBatch(a, b)
+        if not self.Deterministic:
+            blind = self.engine.gt_blind_batch if res.L2 else self.engine.g1_blind_batch
+            res.data = blind(res.data, self._rand_be(res.count * res.Degree, rs))
+        return res
 
     def SumPolyBatch(self, a: PolyCiphertextBatch) -> PolyCiphertext:
         """AddPoly folded over a whole L2 batch (one GPU's share of an inner product)."""

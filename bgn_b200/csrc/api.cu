@@ -119,6 +119,7 @@ struct bgn_ctx {
   uint8_t *dPinf = nullptr, *dQinf = nullptr;
   uint32_t *tabP = nullptr, *tabQ = nullptr;
   uint32_t* tabQ16 = nullptr;  // 16-bit windows of Q, built on the first randomised encryption
+  uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
   // decryption
   bool has_secret = false;
@@ -347,10 +348,11 @@ void gt_from_bytes(bgn_ctx* c, const uint8_t* d_in, size_t count, const GtArr& a
   c->A->fp2_from_bytes(cfg(c, nblk(count, 128), 128, 0), d_in, c->B, count, a.re, a.im, a.N);
   t.done();
 }
-void gt_to_bytes(bgn_ctx* c, const GtArr& a, size_t count, uint8_t* d_out) {
+// grp > 0: the output is polynomials of grp + pad slots, the pad slots written as the GT identity
+void gt_to_bytes(bgn_ctx* c, const GtArr& a, size_t count, uint8_t* d_out, int grp = 0, int pad = 0) {
   if (!count) return;
   Timer t(c, "k_fp2_to_bytes");
-  c->A->fp2_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.re, a.im, a.N, count, d_out, c->B);
+  c->A->fp2_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.re, a.im, a.N, count, d_out, c->B, grp, pad);
   t.done();
 }
 
@@ -542,6 +544,45 @@ void ensure_tabQ16(bgn_ctx* c) {
   }
   CK(cudaFree(tmp));
   c->tabQ16 = tab;
+}
+
+// Fixed-base table of E = e(Q,Q) for the level-2 re-randomisation `* e(Q,Q)^r` (bgn.go:283-287,
+// 306-310, 469-474): nbytes windows of 8 bits, 255 canonical GT elements each (2.2 MB at 512-bit
+// keys: L2-resident).  The reference computes the pairing e(Q,Q) anew in every such call.  Uses and
+// releases the arena: call before carving a call's buffers.
+void ensure_tabE(bgn_ctx* c) {
+  if (c->tabE) return;
+  int nwin = c->nbytes;
+  size_t ew = (size_t)c->L * 4;
+  arena_reset(c);
+  arena_reserve(c, gt_bytes(c, 1) + miller_scratch(c, 1, 1) + pad256(2 * ew) + pad256((size_t)nwin * 2 * ew) + 8192);
+  G1Arr Qv{c->dQx, c->dQy, c->dQinf, 1};
+  GtArr e = gt_alloc(c, 1);
+  run_miller(c, Qv, 1, Qv, 1, 0, 1, 1, e);
+  uint32_t* gen = arena_get<uint32_t>(c, 2 * c->L);
+  uint32_t* bases = arena_get<uint32_t>(c, (size_t)nwin * 2 * c->L);
+  CK(cudaMemcpyAsync(gen, e.re, ew, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(gen + c->L, e.im, ew, cudaMemcpyDeviceToDevice, c->stream));
+  uint32_t* tab = nullptr;
+  CK(cudaMalloc(&tab, (size_t)nwin * 255 * 2 * ew));
+  try {
+    {
+      Timer t(c, "k_gt_tab_bases");
+      c->A->gt_tab_bases(cfg(c, 1, 32, 0), gen, nwin, bases);
+      t.done();
+    }
+    {
+      Timer t(c, "k_gt_tab_fill");
+      c->A->gt_tab_fill(cfg(c, nblk(nwin, 32), 32, 0), bases, nwin, tab);
+      t.done();
+    }
+    finish(c);
+  } catch (...) {
+    cudaFree(tab);
+    throw;
+  }
+  c->tabE = tab;
+  arena_reset(c);
 }
 
 template <typename Fn>
@@ -753,6 +794,7 @@ void bgn_ctx_destroy(bgn_ctx* c) {
   cudaFree(c->tabP);
   cudaFree(c->tabQ);
   cudaFree(c->tabQ16);
+  cudaFree(c->tabE);
   cudaFree(c->bs_elems);
   cudaFree(c->bs_slots);
   cudaFree(c->bs_ginv);
@@ -800,6 +842,8 @@ int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t 
     ea.Z = j.Z;
     ea.count = count;
     ea.N = count;
+    ea.bx = ea.by = nullptr;
+    ea.binf = nullptr;
     {
       Timer t(c, "k_encrypt");
       c->Bo->encrypt(cfg(c, nblk(count, 128), 128, 0), ea);
@@ -1091,6 +1135,186 @@ int bgn_l2_sum_reduce(bgn_ctx* c, const uint8_t* in, size_t nterms, size_t ncoef
       R = reduce_tree(c, A, nterms, ncoeff);
     }
     gt_to_bytes(c, R, ncoeff, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+// ---- non-deterministic mode ------------------------------------------------
+int bgn_g1_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !r_be || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    arena_reserve(c, 2 * io_bytes(c, count) + pad256(count * c->nbytes) + jac_bytes(c, count) + 2 * g1_bytes(c, count) +
+                         pad256(count * c->L * 4) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+    const uint8_t* dr = stage_in(c, r_be, count * c->nbytes);
+    G1Arr A = g1_alloc(c, count), R = g1_alloc(c, count);
+    g1_from_bytes(c, da, count, A);
+    JacArr j = jac_alloc(c, count);
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    ensure_tabQ16(c);
+    EncArgs ea;
+    ea.x = nullptr;
+    ea.r_be = dr;
+    ea.rbytes = c->nbytes;
+    ea.tabP = c->tabP;
+    ea.tabQ = c->tabQ16 ? c->tabQ16 : c->tabQ;
+    ea.wbitsQ = c->tabQ16 ? 16 : 8;
+    ea.X = j.X;
+    ea.Y = j.Y;
+    ea.Z = j.Z;
+    ea.count = count;
+    ea.N = count;
+    ea.bx = A.x;
+    ea.by = A.y;
+    ea.binf = A.inf;
+    {
+      Timer t(c, "k_encrypt");
+      c->Bo->encrypt(cfg(c, nblk(count, 128), 128, 0), ea);
+      t.done();
+    }
+    normalize_soa(c, j, count, scratch, R);
+    g1_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+int bgn_gt_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!a || !r_be || !out) throw ArgErr{"null buffer"};
+    check_count(count);
+    ensure_tabE(c);
+    arena_reserve(c, 2 * io_bytes(c, count) + pad256(count * c->nbytes) + 2 * gt_bytes(c, count) + 8192);
+    OutBuf ob = stage_out(c, out, count * 2 * c->B);
+    const uint8_t* da = stage_in(c, a, count * 2 * c->B);
+    const uint8_t* dr = stage_in(c, r_be, count * c->nbytes);
+    GtArr A = gt_alloc(c, count), R = gt_alloc(c, count);
+    gt_from_bytes(c, da, count, A);
+    GtBlindArgs ba;
+    ba.re = A.re;
+    ba.im = A.im;
+    ba.r_be = dr;
+    ba.rbytes = c->nbytes;
+    ba.tabE = c->tabE;
+    ba.ore = R.re;
+    ba.oim = R.im;
+    ba.count = count;
+    {
+      Timer t(c, "k_gt_blind");
+      c->A->gt_blind(cfg(c, nblk(count, 128), 128, 0), ba);
+      t.done();
+    }
+    gt_to_bytes(c, R, count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+
+// ---- polynomial-ciphertext helpers ------------------------------------------
+// out[u][jj] = sum_k w[k] * in[u][j_begin + jj - k]   (types.h: PolyConvArgs)
+static void polyconv(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const uint64_t* w, size_t nw, int j_begin,
+                     int j_count, int negate, size_t count, uint8_t* out) {
+  size_t nin = count * d, nout = count * (size_t)j_count;
+  check_count(nin);
+  check_count(nout);
+  arena_reserve(c, io_bytes(c, nin) + io_bytes(c, nout) + g1_bytes(c, nin) + g1_bytes(c, nout) + jac_bytes(c, nout) +
+                       pad256(nout * c->L * 4) + 8192);
+  OutBuf ob = stage_out(c, out, nout * 2 * c->B);
+  const uint8_t* di = stage_in(c, in, nin * 2 * c->B);
+  PolyConvArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.d = (int)d;
+  pa.nw = (int)nw;
+  pa.j_begin = j_begin;
+  pa.j_count = j_count;
+  pa.negate = negate;
+  pa.count = count;
+  uint64_t any = 0;
+  for (size_t k = 0; k < nw; k++) {
+    pa.w[k] = w[k];
+    any |= w[k];
+  }
+  pa.top_bit = any ? 63 - __builtin_clzll(any) : -1;
+  if (is_l2) {
+    GtArr A = gt_alloc(c, nin), R = gt_alloc(c, nout);
+    gt_from_bytes(c, di, nin, A);
+    pa.x = A.re;
+    pa.y = A.im;
+    pa.X = R.re;
+    pa.Y = R.im;
+    {
+      Timer t(c, "k_gt_polyconv");
+      c->A->gt_polyconv(cfg(c, nblk(nout, 128), 128, 0), pa);
+      t.done();
+    }
+    gt_to_bytes(c, R, nout, ob.dev);
+  } else {
+    G1Arr A = g1_alloc(c, nin), R = g1_alloc(c, nout);
+    g1_from_bytes(c, di, nin, A);
+    JacArr j = jac_alloc(c, nout);
+    uint32_t* scratch = arena_get<uint32_t>(c, nout * c->L);
+    pa.x = A.x;
+    pa.y = A.y;
+    pa.inf = A.inf;
+    pa.X = j.X;
+    pa.Y = j.Y;
+    pa.Z = j.Z;
+    {
+      Timer t(c, "k_g1_polyconv");
+      c->Bo->g1_polyconv(cfg(c, nblk(nout, 128), 128, 0), pa);
+      t.done();
+    }
+    normalize_soa(c, j, nout, scratch, R);
+    g1_to_bytes(c, R, nout, ob.dev);
+  }
+  commit_out(c, ob);
+}
+
+int bgn_multconstpoly_batch(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const uint8_t* digits, size_t nd,
+                            int negate, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!in || !out || !digits || !d || !nd || nd > BGN_CONV_MAXW || d > 4096) throw ArgErr{"bad argument"};
+    uint64_t w[BGN_CONV_MAXW];
+    for (size_t k = 0; k < nd; k++) w[k] = digits[k];
+    polyconv(c, in, d, is_l2, w, nd, 0, (int)(d + nd), negate, count, out);
+  });
+}
+
+int bgn_evalpoly_batch(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, uint32_t base, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!in || !out || !d || d > BGN_CONV_MAXW || base < 2) throw ArgErr{"bad argument"};
+    // sum_i base^i c_i as a correlation: w[k] = base^(d-1-k), output slot j = d-1 only
+    uint64_t w[BGN_CONV_MAXW];
+    unsigned __int128 pw = 1;
+    for (size_t i = 0; i < d; i++) {
+      if (pw >> 64) throw ArgErr{"base^(d-1) does not fit 64 bits"};
+      w[d - 1 - i] = (uint64_t)pw;
+      pw *= base;
+    }
+    polyconv(c, in, d, is_l2, w, d, (int)d - 1, 1, 0, count, out);
+  });
+}
+
+int bgn_make_poly_l2_batch(bgn_ctx* c, const uint8_t* in, size_t d, size_t count, uint8_t* out) {
+  return guarded(c, [&] {
+    if (!count) return;
+    if (!in || !out || !d) throw ArgErr{"bad argument"};
+    size_t nin = count * d, nout = count * (d + 1);
+    check_count(nout);
+    arena_reserve(c, io_bytes(c, nin) + io_bytes(c, nout) + g1_bytes(c, nin) + gt_bytes(c, nin) +
+                         miller_scratch(c, nin, 1) + 8192);
+    OutBuf ob = stage_out(c, out, nout * 2 * c->B);
+    const uint8_t* da = stage_in(c, in, nin * 2 * c->B);
+    G1Arr A = g1_alloc(c, nin);
+    g1_from_bytes(c, da, nin, A);
+    GtArr R = gt_alloc(c, nin);
+    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+    run_miller(c, A, 1, Pv, 1, 1, nin, 1, R);
+    gt_to_bytes(c, R, nout, ob.dev, (int)d, 1);
     commit_out(c, ob);
   });
 }

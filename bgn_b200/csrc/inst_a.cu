@@ -32,9 +32,18 @@ void gt_reduce(LaunchCfg cfg, const uint32_t* re, const uint32_t* im, size_t Nin
 void fp2_from_bytes(LaunchCfg cfg, const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N) {
   k_fp2_from_bytes<LL><<<CFG>>>(in, B, count, re, im, N);
 }
-void fp2_to_bytes(LaunchCfg cfg, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B) {
-  k_fp2_to_bytes<LL><<<CFG>>>(re, im, N, count, out, B);
+void fp2_to_bytes(LaunchCfg cfg, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B,
+                  int grp, int pad) {
+  k_fp2_to_bytes<LL><<<CFG>>>(re, im, N, count, out, B, grp, pad);
 }
+void gt_blind(LaunchCfg cfg, const GtBlindArgs& a) { k_gt_blind<LL><<<CFG>>>(a); }
+void gt_tab_bases(LaunchCfg cfg, const uint32_t* gen, int nwin, uint32_t* bases) {
+  k_gt_tab_bases<LL><<<CFG>>>(gen, nwin, bases);
+}
+void gt_tab_fill(LaunchCfg cfg, const uint32_t* bases, int nwin, uint32_t* tab) {
+  k_gt_tab_fill<LL><<<CFG>>>(bases, nwin, tab);
+}
+void gt_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_gt_polyconv<LL><<<CFG>>>(a); }
 void bsgs_build(LaunchCfg cfg, const BsgsBuildArgs& a) { k_bsgs_build<LL><<<CFG>>>(a); }
 void bsgs_lookup(LaunchCfg cfg, const BsgsLookupArgs& a) { k_bsgs_lookup<LL><<<CFG>>>(a); }
 void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
@@ -49,7 +58,8 @@ void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
 }
 const LOpsA ops = {LL,        upload,         miller_set_smem, miller_smem_bytes, miller_priv_bytes, miller_fixed_threads,
                    miller,     gt_mul,      gt_pow,
-                   gt_reduce, fp2_from_bytes, fp2_to_bytes,    bsgs_build, bsgs_lookup, mulmod_bench};
+                   gt_reduce, fp2_from_bytes, fp2_to_bytes,    bsgs_build, bsgs_lookup, mulmod_bench,
+                   gt_blind,  gt_tab_bases,   gt_tab_fill,     gt_polyconv};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

@@ -110,14 +110,27 @@ BGN_DEV void fp2_from_bytes_body(const uint8_t* in, int B, size_t count, uint32_
   FF::copy(im + (size_t)(e) * L, b.v());
 }
 
+// `count` output elements.  grp == 0: element e of the array.  grp > 0: the output is grouped as
+// polynomials of grp + pad slots, the first grp taken from consecutive array elements and the pad
+// slots written as the GT identity (MakePolyL2's unused top slot, poly.go:130-137, 159-163).
 template <int L>
 BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B,
-                               size_t e) {
+                               int grp, int pad, size_t e) {
   typedef F<L> FF;
   if (e >= count) return;
   Loc<L> a, b;
-  FF::copy(a.v(), (re + (size_t)(e) * L));
-  FF::copy(b.v(), (im + (size_t)(e) * L));
+  size_t src = e;
+  if (grp > 0) {
+    size_t u = e / (size_t)(grp + pad), s = e % (size_t)(grp + pad);
+    if (s >= (size_t)grp) {
+      uint8_t* o = out + e * 2 * B;
+      for (int i = 0; i < 2 * B; i++) o[i] = (i == B - 1) ? 1 : 0;
+      return;
+    }
+    src = u * grp + s;
+  }
+  FF::copy(a.v(), (re + (size_t)(src) * L));
+  FF::copy(b.v(), (im + (size_t)(src) * L));
   FF::from_mont(a.v(), a.v());
   FF::from_mont(b.v(), b.v());
   limbs_to_be_bytes<L>(out + e * 2 * B, B, a.w);
@@ -136,6 +149,11 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
   FF::set_zero(X.v());
   FF::set_zero(Y.v());
   FF::set_zero(Z.v());
+  if (a.bx && !a.binf[e]) {  // re-randomisation: start from the ciphertext instead of O
+    FF::copy(X.v(), a.bx + e * L);
+    FF::copy(Y.v(), a.by + e * L);
+    FF::set_one(Z.v());
+  }
   if (a.r_be && a.wbitsQ == 16) {
     // 16-bit windows: half the additions; the table (2^16 - 1 points per window, 285 MB at
     // 512 bit) lives in HBM and each lookup is one 8L-byte read at a random address
@@ -160,7 +178,7 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
       }
     }
   }
-  int64_t xs = a.x[e];
+  int64_t xs = a.x ? a.x[e] : 0;
   bool neg = xs < 0;
   uint64_t xm = neg ? (uint64_t)(-(xs + 1)) + 1u : (uint64_t)xs;
   for (int win = 0; win < 8; win++) {
@@ -400,6 +418,117 @@ BGN_DEV void gt_reduce_body(const uint32_t* re, const uint32_t* im, size_t Nin, 
   FF::copy(oim + (size_t)(id) * L, acc.im);
 }
 
+// Level-2 re-randomisation: out = a * E^r, E = e(Q,Q), through the fixed-base table of E
+// (bgn.go:283-287, 306-310, 469-474; the reference computes the pairing e(Q,Q) anew per call).
+template <int L>
+BGN_DEV void gt_blind_body(const GtBlindArgs& a, size_t e) {
+  typedef F<L> FF;
+  if (e >= a.count) return;
+  Loc<L> r0, r1, t0, t1, t2;
+  E2 acc = mke2(r0.v(), r1.v());
+  FF::copy(acc.re, a.re + e * L);
+  FF::copy(acc.im, a.im + e * L);
+  const uint8_t* r = a.r_be + e * a.rbytes;
+  for (int win = 0; win < a.rbytes; win++) {
+    uint32_t d = r[a.rbytes - 1 - win];
+    if (d) {
+      uint32_t* ent = const_cast<uint32_t*>(a.tabE) + ((size_t)win * 255 + (d - 1)) * 2 * L;
+      FF::mul2(acc, acc, mke2(ent, ent + L), t0.v(), t1.v(), t2.v());
+    }
+  }
+  FF::copy(a.ore + e * L, acc.re);
+  FF::copy(a.oim + e * L, acc.im);
+}
+
+// Fixed-base table of a GT element: bases[w] = gen^(256^w) (single thread), then entry
+// (w, d) = bases[w]^d for d = 1..255 (one thread per window), AoS [w][d-1][re||im], canonical.
+template <int L>
+BGN_DEV void gt_tab_bases_body(const uint32_t* gen, int nwin, uint32_t* bases, size_t g) {
+  typedef F<L> FF;
+  if (g != 0) return;
+  Loc<L> r0, r1, t0, t1;
+  E2 acc = mke2(r0.v(), r1.v());
+  FF::copy(acc.re, gen);
+  FF::copy(acc.im, gen + L);
+  for (int w = 0; w < nwin; w++) {
+    FF::canon(bases + (size_t)w * 2 * L, acc.re);
+    FF::canon(bases + (size_t)w * 2 * L + L, acc.im);
+    for (int i = 0; i < 8; i++) FF::sqr2(acc, acc, t0.v(), t1.v());
+  }
+}
+template <int L>
+BGN_DEV void gt_tab_fill_body(const uint32_t* bases, int nwin, uint32_t* tab, size_t g) {
+  typedef F<L> FF;
+  if (g >= (size_t)nwin) return;
+  Loc<L> r0, r1, b0, b1, t0, t1, t2;
+  E2 acc = mke2(r0.v(), r1.v()), b = mke2(b0.v(), b1.v());
+  FF::copy(b.re, bases + g * 2 * L);
+  FF::copy(b.im, bases + g * 2 * L + L);
+  FF::copy2(acc, b);
+  for (int d = 1; d <= 255; d++) {
+    uint32_t* dst = tab + (g * 255 + (d - 1)) * 2 * L;
+    FF::canon(dst, acc.re);
+    FF::canon(dst + L, acc.im);
+    FF::mul2(acc, acc, b, t0.v(), t1.v(), t2.v());
+  }
+}
+
+// Integer-weighted correlation (types.h: PolyConvArgs), one thread per output slot; bit-plane
+// Horner over the weights: acc <- 2 acc + sum_{k: bit b of w[k]} in[j-k].  Every addition is a
+// complete mixed addition with an affine input, so no general Jacobian addition is needed.
+template <int L>
+BGN_DEV void g1_polyconv_body(const PolyConvArgs& a, size_t id) {
+  typedef F<L> FF;
+  if (id >= a.count * (size_t)a.j_count) return;
+  size_t u = id / (size_t)a.j_count;
+  int j = a.j_begin + (int)(id % (size_t)a.j_count);
+  Loc<L> X, Y, Z, t0, t1, t2, t3;
+  FF::set_zero(X.v());
+  FF::set_zero(Y.v());
+  FF::set_zero(Z.v());
+  bool started = false;  // doubling O is a no-op
+  for (int b = a.top_bit; b >= 0; b--) {
+    if (started) G<L>::dbl(X.v(), Y.v(), Z.v(), t0.v(), t1.v(), t2.v(), t3.v());
+    for (int k = 0; k < a.nw; k++) {
+      int i = j - k;
+      if (i < 0 || i >= a.d || !((a.w[k] >> b) & 1)) continue;
+      size_t e = u * a.d + i;
+      if (a.inf[e]) continue;
+      G<L>::madd(X.v(), Y.v(), Z.v(), a.x + e * L, a.y + e * L, false, t0.v(), t1.v(), t2.v(), t3.v());
+      started = true;
+    }
+  }
+  if (a.negate) FF::neg(Y.v(), Y.v());
+  FF::copy(a.X + id * L, X.v());
+  FF::copy(a.Y + id * L, Y.v());
+  FF::copy(a.Z + id * L, Z.v());
+}
+template <int L>
+BGN_DEV void gt_polyconv_body(const PolyConvArgs& a, size_t id) {
+  typedef F<L> FF;
+  if (id >= a.count * (size_t)a.j_count) return;
+  size_t u = id / (size_t)a.j_count;
+  int j = a.j_begin + (int)(id % (size_t)a.j_count);
+  Loc<L> r0, r1, t0, t1, t2;
+  E2 acc = mke2(r0.v(), r1.v());
+  FF::set_one2(acc);
+  bool started = false;
+  for (int b = a.top_bit; b >= 0; b--) {
+    if (started) FF::sqr2(acc, acc, t0.v(), t1.v());
+    for (int k = 0; k < a.nw; k++) {
+      int i = j - k;
+      if (i < 0 || i >= a.d || !((a.w[k] >> b) & 1)) continue;
+      size_t e = u * a.d + i;
+      FF::mul2(acc, acc, mke2(const_cast<uint32_t*>(a.x) + e * L, const_cast<uint32_t*>(a.y) + e * L), t0.v(), t1.v(),
+               t2.v());
+      started = true;
+    }
+  }
+  if (a.negate) FF::neg(acc.im, acc.im);  // unitary: conj = inverse
+  FF::copy(a.X + id * L, acc.re);
+  FF::copy(a.Y + id * L, acc.im);
+}
+
 // ------------------------------------------------------------ BSGS (gsbs.go)
 // Baby steps: elems[j] = gen^(j+1), j < S, canonical Montgomery AoS [S][2L];
 // open-addressing hash table slots[hmask+1] holding j+1 (0 = empty).
@@ -517,6 +646,17 @@ BGN_KERNEL_1D(gt_mul, GtBinArgs)
 BGN_KERNEL_1D(gt_pow, GtPowArgs)
 BGN_KERNEL_1D(bsgs_build, BsgsBuildArgs)
 BGN_KERNEL_1D(bsgs_lookup, BsgsLookupArgs)
+BGN_KERNEL_1D(gt_blind, GtBlindArgs)
+BGN_KERNEL_1D(g1_polyconv, PolyConvArgs)
+BGN_KERNEL_1D(gt_polyconv, PolyConvArgs)
+template <int L>
+__global__ void k_gt_tab_bases(const uint32_t* gen, int nwin, uint32_t* bases) {
+  gt_tab_bases_body<L>(gen, nwin, bases, BGN_GID(size_t));
+}
+template <int L>
+__global__ void k_gt_tab_fill(const uint32_t* bases, int nwin, uint32_t* tab) {
+  gt_tab_fill_body<L>(bases, nwin, tab, BGN_GID(size_t));
+}
 
 template <int L>
 __global__ void k_g1_from_bytes(const uint8_t* __restrict__ in, int B, size_t count, uint32_t* x, uint32_t* y,
@@ -535,8 +675,8 @@ __global__ void k_fp2_from_bytes(const uint8_t* __restrict__ in, int B, size_t c
 }
 template <int L>
 __global__ void k_fp2_to_bytes(const uint32_t* re, const uint32_t* im, size_t N, size_t count,
-                               uint8_t* __restrict__ out, int B) {
-  fp2_to_bytes_body<L>(re, im, N, count, out, B, BGN_GID(size_t));
+                               uint8_t* __restrict__ out, int B, int grp, int pad) {
+  fp2_to_bytes_body<L>(re, im, N, count, out, B, grp, pad, BGN_GID(size_t));
 }
 template <int L>
 __global__ void k_tab_bases(const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,

@@ -26,10 +26,15 @@ struct LOpsA {
   void (*gt_reduce)(LaunchCfg, const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms, int ncoeff, int G,
                     uint32_t* ore, uint32_t* oim, size_t N);
   void (*fp2_from_bytes)(LaunchCfg, const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N);
-  void (*fp2_to_bytes)(LaunchCfg, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B);
+  void (*fp2_to_bytes)(LaunchCfg, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B,
+                       int grp, int pad);
   void (*bsgs_build)(LaunchCfg, const BsgsBuildArgs&);
   void (*bsgs_lookup)(LaunchCfg, const BsgsLookupArgs&);
   void (*mulmod_bench)(LaunchCfg, int ilp, uint32_t* io, size_t N, int iters);
+  void (*gt_blind)(LaunchCfg, const GtBlindArgs&);
+  void (*gt_tab_bases)(LaunchCfg, const uint32_t* gen, int nwin, uint32_t* bases);
+  void (*gt_tab_fill)(LaunchCfg, const uint32_t* bases, int nwin, uint32_t* tab);
+  void (*gt_polyconv)(LaunchCfg, const PolyConvArgs&);
 };
 
 struct LOpsB {
@@ -48,6 +53,7 @@ struct LOpsB {
   void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
                    uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
   void (*tab16_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent);
+  void (*g1_polyconv)(LaunchCfg, const PolyConvArgs&);
 };
 
 #define BGN_DECL_OPS(L)               \

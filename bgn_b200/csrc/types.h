@@ -58,6 +58,10 @@ struct EncArgs {
   int wbitsQ;             // 8 or 16: window width of tabQ (entries per window = 2^wbitsQ - 1)
   uint32_t *X, *Y, *Z;    // Jacobian out, [N][L]
   size_t count, N;
+  // optional starting point per element (affine, [count][L] + infinity flags): out = base + r*Q,
+  // the re-randomisation of the non-deterministic mode (bgn.go:264-268, 491-495).  x may then be null.
+  const uint32_t *bx, *by;
+  const uint8_t* binf;
 };
 
 struct NormArgs {
@@ -109,6 +113,34 @@ struct GtPowArgs {
   int mode;             // 0: a^e[i]; 1: a^q1 (c_pc.exp); 2: conj(a) = a^-1 (unitary); 3: conj(a^e[i])
   uint32_t *ore, *oim;
   size_t count, N;
+};
+
+// out[i] = a[i] * E^r[i] with E = e(Q,Q): the level-2 re-randomisation (bgn.go:283-287, 306-310,
+// 469-474) through a fixed-base table of E (8-bit windows, AoS [win][d-1][re||im], canonical)
+struct GtBlindArgs {
+  const uint32_t *re, *im;
+  const uint8_t* r_be;
+  int rbytes;
+  const uint32_t* tabE;
+  uint32_t *ore, *oim;
+  size_t count;
+};
+
+// Integer-weighted correlation of coefficient vectors: out[u][jj] = sum_k w[k] * in[u][j_begin + jj - k]
+// over the k with 0 <= j_begin + jj - k < d.  MultConstPoly (poly.go:71-120) is w = the unbalanced
+// digits of the constant, j_begin = 0, j_count = d + nw; EvalPoly (poly.go:58-68) is w[k] =
+// base^(d-1-k), j_begin = d - 1, j_count = 1.  G1 inputs are affine (x, y, inf) and the result is
+// Jacobian (X, Y, Z); GT inputs/outputs use (x, y) / (X, Y) as (re, im).
+#define BGN_CONV_MAXW 64
+struct PolyConvArgs {
+  const uint32_t *x, *y;
+  const uint8_t* inf;  // G1 only
+  int d, nw, j_begin, j_count;
+  int top_bit;         // highest set bit over all weights
+  int negate;          // NegPoly of the result (negative constant)
+  uint64_t w[BGN_CONV_MAXW];
+  uint32_t *X, *Y, *Z;
+  size_t count;        // polynomials
 };
 
 struct BsgsBuildArgs {

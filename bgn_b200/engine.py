@@ -184,6 +184,49 @@ class Engine:
         self._check(self._lib.bgn_l2_sum_reduce(self._ctx, pt, nterms, ncoeff, _as_buf(o)[0]))
         return o
 
+    def _blind(self, fn, a, r_be, out=None):
+        pa, na, ka, ca = _as_buf(a)
+        pr, nr, kr, cr = _as_buf(r_be)
+        count = self._count(na)
+        assert nr == count * self.scalar_bytes
+        o = self._out(na, ca or cr, out)
+        self._check(fn(self._ctx, pa, pr, count, _as_buf(o)[0]))
+        return o
+
+    def g1_blind_batch(self, a, r_be, out=None):
+        """a[i] + r[i]*Q (level-1 re-randomisation of the non-deterministic mode)."""
+        return self._blind(self._lib.bgn_g1_blind_batch, a, r_be, out)
+
+    def gt_blind_batch(self, a, r_be, out=None):
+        """a[i] * e(Q,Q)^r[i] (level-2 re-randomisation)."""
+        return self._blind(self._lib.bgn_gt_blind_batch, a, r_be, out)
+
+    def multconstpoly_batch(self, cts, d: int, is_l2: bool, digits: Sequence[int], negate: bool, count: int, out=None):
+        """MultConstPoly over `count` polynomials of d slots -> count*(d+len(digits)) elements."""
+        pc, nc, kc, cc = _as_buf(cts)
+        assert nc == count * d * self.elem_bytes
+        dg = bytes(bytearray(int(x) for x in digits))
+        o = self._out(count * (d + len(dg)) * self.elem_bytes, cc, out)
+        self._check(self._lib.bgn_multconstpoly_batch(self._ctx, pc, d, 1 if is_l2 else 0, dg, len(dg),
+                                                      1 if negate else 0, count, _as_buf(o)[0]))
+        return o
+
+    def evalpoly_batch(self, cts, d: int, is_l2: bool, base: int, count: int, out=None):
+        """EvalPoly: one element per polynomial, sum_i base^i * c_i."""
+        pc, nc, kc, cc = _as_buf(cts)
+        assert nc == count * d * self.elem_bytes
+        o = self._out(count * self.elem_bytes, cc, out)
+        self._check(self._lib.bgn_evalpoly_batch(self._ctx, pc, d, 1 if is_l2 else 0, base, count, _as_buf(o)[0]))
+        return o
+
+    def make_poly_l2_batch(self, cts, d: int, count: int, out=None):
+        """MakePolyL2 (deterministic): count*(d+1) GT elements."""
+        pc, nc, kc, cc = _as_buf(cts)
+        assert nc == count * d * self.elem_bytes
+        o = self._out(count * (d + 1) * self.elem_bytes, cc, out)
+        self._check(self._lib.bgn_make_poly_l2_batch(self._ctx, pc, d, count, _as_buf(o)[0]))
+        return o
+
     def gt_pow_secret_batch(self, a, out=None):
         return self._unop(self._lib.bgn_gt_pow_secret_batch, a, out)
 

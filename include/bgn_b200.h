@@ -18,8 +18,9 @@
  *     synchronous (they return after the device work has finished).
  *
  * Homomorphic operations implement the reference's Deterministic=true behaviour
- * (bgn_test.go:13); re-randomisation is done by the caller with bgn_encrypt_batch
- * of zero plus an add (DESIGN.md "non-deterministic mode").
+ * (bgn_test.go:13).  The non-deterministic mode is the same operation followed by
+ * bgn_g1_blind_batch / bgn_gt_blind_batch with caller-supplied randomness (the
+ * reference draws it from crypto/rand inside the call, bgn.go:567-574).
  */
 #ifndef BGN_B200_H
 #define BGN_B200_H
@@ -117,6 +118,31 @@ int bgn_gt_pow_secret_batch(bgn_ctx* ctx, const uint8_t* in, size_t count, uint8
  * including the negate-and-retry path.  status[i]: 0 ok, 1 "cannot find discrete
  * log; out of bounds" (gsbs.go:105), in which case out[i] = 0 (DecryptFailSafe). */
 int bgn_decrypt_batch(bgn_ctx* ctx, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status);
+
+/* ---- non-deterministic mode: the re-randomisation every homomorphic operation appends when
+ * !pk.Deterministic.  r_be: count scalars of scalar_bytes each (the reference's newCryptoRandom(N)).
+ * Level 1:  out[i] = a[i] + r[i]*Q              (bgn.go:260-269, 421-432, 488-495)
+ * Level 2:  out[i] = a[i] * e(Q,Q)^r[i]         (bgn.go:279-288, 302-311, 404-411, 466-474)
+ * e(Q,Q) -- a full pairing per call in the reference (bgn.go:283, 306, 406, 469) -- is computed once
+ * per context and kept as a fixed-base table.  MultPoly in this mode (one r per coefficient pairing,
+ * poly.go:140-152) is bgn_multpoly_batch followed by one blind per slot j with
+ * r_j = sum_{i+k=j} r_ik mod n. */
+int bgn_g1_blind_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* r_be, size_t count, uint8_t* out);
+int bgn_gt_blind_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* r_be, size_t count, uint8_t* out);
+
+/* ---- polynomial-ciphertext helpers beside MultPoly.
+ * MultConstPoly (poly.go:71-120) over `count` polynomials of d slots (level 1 or 2): digits = the nd
+ * coefficients of NewUnbalancedPlaintext(|constant|) (values 0..base-1, poly.go:78-80);
+ * out: count*(d+nd) elements, out[u][j] = sum_{i+k=j} digits[k]*in[u][i] (top slot = identity);
+ * negate != 0 applies NegPoly (negative constant, poly.go:116-118). */
+int bgn_multconstpoly_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, int is_l2, const uint8_t* digits, size_t nd,
+                            int negate, size_t count, uint8_t* out);
+/* EvalPoly (poly.go:58-68): out[u] = sum_i base^i * in[u][i]  (Horner with MultConst/Add in the
+ * reference); base = PolyEncodingParams.PolyBase; base^(d-1) must fit 64 bits. */
+int bgn_evalpoly_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, int is_l2, uint32_t base, size_t count, uint8_t* out);
+/* MakePolyL2 (poly.go:159-163) in deterministic mode: MultPoly(E(1.0), ct) with E(1.0) = [P]:
+ * out: count*(d+1) GT elements, out[u][i] = e(in[u][i], P), out[u][d] = identity. */
+int bgn_make_poly_l2_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, size_t count, uint8_t* out);
 
 /* ---- instrumentation (bench.py) ---- */
 /* When enabled, every kernel launch is bracketed by CUDA events on the context's

@@ -141,6 +141,46 @@ def make(kb: int, small: bool) -> dict:
         l1.append(O.g1_neg(c, p) if m < 0 else c)
     vals = [O.decrypt(pk, sk, O.Ciphertext(c, False)) for c in l1]
     out["decrypt_l1"] = {"in": [g1b(c) for c in l1], "m": l1m, "out": vals, "status": [0] * len(vals)}
+    # ---- sections added later draw from their own generator so the ones above never change
+    rng2 = random.Random(SEEDS[kb] ^ 0xF1F2)
+    # non-deterministic mode, injected r (bgn.go:264-268, 488-495 / 283-287, 306-310, 469-474):
+    # + r*Q on level 1 (incl. O as the value and r = 0), * e(Q,Q)^r on level 2
+    nk = 3 if small else 5
+    ba = ([enc[1], None, enc[3], enc[2], enc[4]])[:nk]
+    br = ([rng2.randrange(n), rng2.randrange(n), 0, n - 1, rng2.randrange(n)])[:nk]
+    out["g1_blind"] = {"a": [g1b(a) for a in ba], "r": [hex(r) for r in br],
+                       "out": [g1b(O.g1_add(a, O.g1_mul(r, pk.Q, p), p)) for a, r in zip(ba, br)]}
+    eQQ = O.pairing(pk.Q, pk.Q, par)
+    bg = ([pr[0], O.GT_ONE, pr[1], pr[2], pr[1]])[:nk]
+    out["gt_blind"] = {"a": [gtb(a) for a in bg], "r": [hex(r) for r in br],
+                       "out": [gtb(O.fp2_mul(a, O.fp2_pow(eQQ, r, p), p)) for a, r in zip(bg, br)]}
+    # MultConstPoly / EvalPoly / MakePolyL2 (poly.go:58-120, 159-163) on two polynomials of 3 slots
+    pcount, pd = 2, 3
+    polys = []
+    for u in range(pcount):
+        coeffs = [[1, -1, 0], [0, 1, 1]][u]
+        cs = []
+        for i, x in enumerate(coeffs):
+            r = 0 if (u == 1 and i == 0) else rng2.randrange(n)  # one O coefficient
+            c = O.encrypt_with_randomness(pk, abs(x), r).C
+            cs.append(O.Ciphertext(O.g1_neg(c, p) if x < 0 else c, False))
+        polys.append(O.PolyCiphertext(cs, pd, 0, False))
+    polys2 = [O.make_poly_l2(pk, ct) for ct in polys]  # pd + 1 slots
+    out["make_poly_l2"] = {"d": pd, "count": pcount, "in": [g1b(c.C) for ct in polys for c in ct.coefficients],
+                           "out": [gtb(c.C) for ct in polys2 for c in ct.coefficients]}
+    for name, cts, dd in (("l1", polys, pd), ("l2", polys2, pd + 1)):
+        enc_el = (lambda c: gtb(c.C)) if name == "l2" else (lambda c: g1b(c.C))
+        cases = []
+        for constant in ((4.12, -2.0) if not small else (5.0,)):
+            digits = pk.new_unbalanced_plaintext(abs(constant)).coefficients
+            res = [O.mult_const_poly(pk, ct, constant) for ct in cts]
+            cases.append({"constant": constant, "digits": digits, "negate": constant < 0,
+                          "out": [enc_el(c) for ct in res for c in ct.coefficients]})
+        out["multconstpoly_" + name] = {"d": dd, "count": pcount, "in": [enc_el(c) for ct in cts for c in ct.coefficients],
+                                        "cases": cases}
+        out["evalpoly_" + name] = {"d": dd, "count": pcount, "base": pk.poly_base,
+                                   "in": [enc_el(c) for ct in cts for c in ct.coefficients],
+                                   "out": [enc_el(O.eval_poly(pk, ct)) for ct in cts]}
     return out
 
 

@@ -122,8 +122,22 @@ int hs_g1_to_bytes(int L, const uint32_t* x, const uint32_t* y, const uint8_t* i
 int hs_fp2_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* re, uint32_t* im, size_t N) {
   FOR_L(L, for (size_t e = 0; e < count; e++) fp2_from_bytes_body<LL>(in, B, count, re, im, N, e))
 }
-int hs_fp2_to_bytes(int L, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B) {
-  FOR_L(L, for (size_t e = 0; e < count; e++) fp2_to_bytes_body<LL>(re, im, N, count, out, B, e))
+int hs_fp2_to_bytes(int L, const uint32_t* re, const uint32_t* im, size_t N, size_t count, uint8_t* out, int B, int grp,
+                    int pad) {
+  FOR_L(L, for (size_t e = 0; e < count; e++) fp2_to_bytes_body<LL>(re, im, N, count, out, B, grp, pad, e))
+}
+int hs_gt_blind(int L, const GtBlindArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_blind_body<LL>(*a, e)) }
+int hs_gt_tab_bases(int L, const uint32_t* gen, int nwin, uint32_t* bases) {
+  FOR_L(L, gt_tab_bases_body<LL>(gen, nwin, bases, 0))
+}
+int hs_gt_tab_fill(int L, const uint32_t* bases, int nwin, uint32_t* tab) {
+  FOR_L(L, for (int w = 0; w < nwin; w++) gt_tab_fill_body<LL>(bases, nwin, tab, w))
+}
+int hs_g1_polyconv(int L, const PolyConvArgs* a) {
+  FOR_L(L, for (size_t id = 0; id < a->count * (size_t)a->j_count; id++) g1_polyconv_body<LL>(*a, id))
+}
+int hs_gt_polyconv(int L, const PolyConvArgs* a) {
+  FOR_L(L, for (size_t id = 0; id < a->count * (size_t)a->j_count; id++) gt_polyconv_body<LL>(*a, id))
 }
 // tracker self-test: a difference whose subtrahend may exceed its offset must be flagged
 int hs_selftest_violation() {

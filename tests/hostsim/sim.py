@@ -40,7 +40,22 @@ class MillerArgs(C.Structure):
 
 class EncArgs(C.Structure):
     _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p), ("wbitsQ", C.c_int),
-                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
+                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t),
+                ("bx", u32p), ("by", u32p), ("binf", u8p)]
+
+
+class GtBlindArgs(C.Structure):
+    _fields_ = [("re", u32p), ("im", u32p), ("r_be", u8p), ("rbytes", C.c_int), ("tabE", u32p), ("ore", u32p),
+                ("oim", u32p), ("count", C.c_size_t)]
+
+
+CONV_MAXW = 64
+
+
+class PolyConvArgs(C.Structure):
+    _fields_ = [("x", u32p), ("y", u32p), ("inf", u8p), ("d", C.c_int), ("nw", C.c_int), ("j_begin", C.c_int),
+                ("j_count", C.c_int), ("top_bit", C.c_int), ("negate", C.c_int), ("w", C.c_uint64 * CONV_MAXW),
+                ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t)]
 
 
 class NormArgs(C.Structure):
@@ -279,9 +294,14 @@ class Sim:
         assert lib().hs_normalize(L, C.byref(a)) == 0
         return tab
 
-    def encrypt(self, xs, rs, tabP, tabQ, wbitsQ=8):
-        count = len(xs)
-        x = np.array(xs, dtype=np.int64)
+    def encrypt(self, xs, rs, tabP, tabQ, wbitsQ=8, base=None):
+        """base: optional list of starting points (bgn_g1_blind_batch: base + r*Q; xs then None)"""
+        count = len(rs) if xs is None else len(xs)
+        x = np.array(xs if xs is not None else [0], dtype=np.int64)
+        bx = by = binf = None
+        if base is not None:
+            bxa, bya, binfa = self.g1_arrays(base)
+            bx, by, binf = P32(bxa), P32(bya), P8(binfa)
         X = np.zeros((max(1, count), self.L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
@@ -290,8 +310,8 @@ class Sim:
         else:
             rbuf = np.frombuffer(b"".join(int(r).to_bytes(self.nbytes, "big") for r in rs), dtype=np.uint8).copy()
             rp = P8(rbuf)
-        a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)), rp, self.nbytes, P32(tabP), P32(tabQ), wbitsQ, P32(X),
-                    P32(Y), P32(Z), count, count)
+        a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)) if xs is not None else None, rp, self.nbytes, P32(tabP),
+                    P32(tabQ), wbitsQ, P32(X), P32(Y), P32(Z), count, count, bx, by, binf)
         assert lib().hs_encrypt(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
 
@@ -351,6 +371,57 @@ class Sim:
                                   G * ncoeff) == 0
         return list(zip(self.unsoa(ore, G * ncoeff), self.unsoa(oim, G * ncoeff)))
 
+    def gt_table(self, gen: Tuple[int, int], nwin: int) -> np.ndarray:
+        """k_gt_tab_bases + k_gt_tab_fill (api.cu: ensure_tabE)"""
+        L = self.L
+        g = np.concatenate([self.soa([gen[0]])[0], self.soa([gen[1]])[0]]).astype(np.uint32)
+        lib().hs_track_array(P32(g), C.c_size_t(2), L, C.c_double(1.0))
+        bases = np.zeros(nwin * 2 * L, dtype=np.uint32)
+        tab = np.zeros(nwin * 255 * 2 * L, dtype=np.uint32)
+        assert lib().hs_gt_tab_bases(L, P32(g), nwin, P32(bases)) == 0
+        assert lib().hs_gt_tab_fill(L, P32(bases), nwin, P32(tab)) == 0
+        return tab
+
+    def gt_blind(self, A, rs, tabE):
+        count = len(A)
+        are, aim = self.gt_arrays(A)
+        ore, oim = np.zeros_like(are), np.zeros_like(are)
+        rbuf = np.frombuffer(b"".join(int(r).to_bytes(self.nbytes, "big") for r in rs), dtype=np.uint8).copy()
+        a = GtBlindArgs(P32(are), P32(aim), P8(rbuf), self.nbytes, P32(tabE), P32(ore), P32(oim), count)
+        assert lib().hs_gt_blind(self.L, C.byref(a)) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
+
+    def polyconv(self, elems, d, is_l2, w, j_begin, j_count, negate, count):
+        """k_g1_polyconv (+ k_normalize) / k_gt_polyconv as api.cu: polyconv() drives them"""
+        nout = count * j_count
+        a = PolyConvArgs()
+        a.d, a.nw, a.j_begin, a.j_count, a.negate, a.count = d, len(w), j_begin, j_count, 1 if negate else 0, count
+        anyw = 0
+        for k, v in enumerate(w):
+            a.w[k] = v
+            anyw |= v
+        a.top_bit = anyw.bit_length() - 1
+        X = np.zeros((max(1, nout), self.L), dtype=np.uint32)
+        Y = np.zeros_like(X)
+        Z = np.zeros_like(X)
+        a.X, a.Y, a.Z = P32(X), P32(Y), P32(Z)
+        if is_l2:
+            re, im = self.gt_arrays(elems)
+            a.x, a.y = P32(re), P32(im)
+            assert lib().hs_gt_polyconv(self.L, C.byref(a)) == 0
+            return list(zip(self.unsoa(X, nout), self.unsoa(Y, nout)))
+        x, y, inf = self.g1_arrays(elems)
+        a.x, a.y, a.inf = P32(x), P32(y), P8(inf)
+        assert lib().hs_g1_polyconv(self.L, C.byref(a)) == 0
+        return self.normalize(X, Y, Z, nout)
+
+    def gt_to_bytes_padded(self, vals, grp: int, pad: int) -> bytes:
+        re, im = self.gt_arrays(vals)
+        count = (len(vals) // grp) * (grp + pad)
+        out = np.zeros(count * 2 * self.B, dtype=np.uint8)
+        assert lib().hs_fp2_to_bytes(self.L, P32(re), P32(im), re.shape[0], count, P8(out), self.B, grp, pad) == 0
+        return out.tobytes()
+
     def bsgs_setup(self, gsk: Tuple[int, int], msg_space: int, S: Optional[int] = None):
         import math
         L, p = self.L, self.p
@@ -403,7 +474,7 @@ class Sim:
         count = len(vals)
         re, im = self.gt_arrays(vals)
         out = np.zeros(count * 2 * self.B, dtype=np.uint8)
-        assert lib().hs_fp2_to_bytes(self.L, P32(re), P32(im), count, count, P8(out), self.B) == 0
+        assert lib().hs_fp2_to_bytes(self.L, P32(re), P32(im), count, count, P8(out), self.B, 0, 0) == 0
         re2, im2 = np.zeros_like(re), np.zeros_like(im)
         assert lib().hs_fp2_from_bytes(self.L, P8(out), self.B, count, P32(re2), P32(im2), count) == 0
         back = list(zip(self.unsoa(re2, count), self.unsoa(im2, count)))

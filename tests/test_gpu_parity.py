@@ -152,6 +152,38 @@ def test_decrypt_l1(golden):
     assert [int(x) for x in vals] == v["out"]
 
 
+# ---------------------------------------------------------------- non-deterministic mode
+def test_g1_blind(golden):
+    e, v = engine_for(golden), golden["g1_blind"]
+    assert e.g1_blind_batch(buf(v["a"]), scal(e, v["r"], e.scalar_bytes)).tobytes() == unhex(v["out"])
+
+
+def test_gt_blind(golden):
+    e, v = engine_for(golden), golden["gt_blind"]
+    assert e.gt_blind_batch(buf(v["a"]), scal(e, v["r"], e.scalar_bytes)).tobytes() == unhex(v["out"])
+
+
+# ---------------------------------------------------------------- polynomial helpers
+@pytest.mark.parametrize("lvl", ["l1", "l2"])
+def test_multconstpoly(golden, lvl):
+    e, v = engine_for(golden), golden["multconstpoly_" + lvl]
+    for case in v["cases"]:
+        out = e.multconstpoly_batch(buf(v["in"]), v["d"], lvl == "l2", case["digits"], case["negate"], v["count"])
+        assert out.tobytes() == unhex(case["out"]), case["constant"]
+
+
+@pytest.mark.parametrize("lvl", ["l1", "l2"])
+def test_evalpoly(golden, lvl):
+    e, v = engine_for(golden), golden["evalpoly_" + lvl]
+    out = e.evalpoly_batch(buf(v["in"]), v["d"], lvl == "l2", v["base"], v["count"])
+    assert out.tobytes() == unhex(v["out"])
+
+
+def test_make_poly_l2(golden):
+    e, v = engine_for(golden), golden["make_poly_l2"]
+    assert e.make_poly_l2_batch(buf(v["in"]), v["d"], v["count"]).tobytes() == unhex(v["out"])
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)
@@ -302,6 +334,79 @@ def test_mirror_api_poly():
     a, b = pk.EncryptPoly(pk.NewPolyPlaintext(1.1)), pk.EncryptPoly(pk.NewPolyPlaintext(40.2))
     assert f1(sk.DecryptPoly(pk.MultPoly(a, b), pk).PolyEval()) == f1(1.1 * 40.2)
     assert f1(sk.DecryptPoly(pk.SubPoly(b, a), pk).PolyEval()) == f1(40.2 - 1.1)
+
+
+def test_mirror_api_nondeterministic():
+    """Deterministic=false: every homomorphic op re-randomises (bgn.go:260-269, 279-288, 302-311,
+    466-474, 488-495).  With the randomness injected the bytes must equal the oracle's; with fresh
+    randomness the plaintext algebra must still hold and ciphertexts must differ between calls."""
+    from bgn_b200 import PublicKey, SecretKey
+    from oracle import bgn_oracle as O
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"],
+                                 Deterministic=False)
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    opk = O.PublicKey(par, O.g1_from_bytes(bytes.fromhex(g["P"]), par), O.g1_from_bytes(bytes.fromhex(g["Q"]), par),
+                      g["msg_space"], deterministic=False)
+    rng = random.Random(3)
+    r = lambda: rng.randrange(par.n)  # noqa: E731
+    r1, r2, r3, r4, r5, r6 = (r() for _ in range(6))
+    a, b = pk.EncryptWithRandomness(3, r1), pk.EncryptWithRandomness(2, r2)
+    oa, ob = O.encrypt_with_randomness(opk, 3, r1), O.encrypt_with_randomness(opk, 2, r2)
+    assert a.C == O.ct_bytes(opk, oa) and b.C == O.ct_bytes(opk, ob)
+    assert pk.Add(a, b, r=r3).C == O.ct_bytes(opk, O.add(opk, oa, ob, r3))
+    assert pk.Sub(a, b, r=r4).C == O.ct_bytes(opk, O.sub(opk, oa, ob, r4))
+    m, om = pk.Mult(a, b, r=r5), O.mult(opk, oa, ob, r5)
+    assert m.L2 and m.C == O.ct_bytes(opk, om)
+    assert pk.Add(m, m, r=r6).C == O.ct_bytes(opk, O.add(opk, om, om, r6))
+    assert pk.MultConst(a, 5, r=r3).C == O.ct_bytes(opk, O.mult_const(opk, oa, 5, r3))
+    assert pk.MultConst(m, 5, r=r4).C == O.ct_bytes(opk, O.mult_const(opk, om, 5, r4))
+    # fresh randomness: same plaintexts, different ciphertexts
+    s1, s2 = pk.Add(a, b), pk.Add(a, b)
+    assert s1.C != s2.C and sk.Decrypt(s1, pk) == sk.Decrypt(s2, pk) == 5
+    p1, p2 = pk.Mult(a, b), pk.Mult(a, b)
+    assert p1.C != p2.C and sk.Decrypt(p1, pk) == sk.Decrypt(p2, pk) == 6
+    assert sk.Decrypt(pk.Sub(p1, pk.makeL2(a)), pk) == 3
+
+
+def test_batch_poly_helpers_match_mirror():
+    """MultConstPolyBatch / EvalPolyBatch / MakePolyL2Batch (one kernel launch per batch) give the
+    same bytes as the per-polynomial mirror methods composed from the scalar C-ABI primitives."""
+    from bgn_b200 import PublicKey, SecretKey
+    from bgn_b200.bgn import PolyCiphertextBatch
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    rng = random.Random(11)
+    vals = [9.13, 4.0, 17.5, 0.0]
+    pts = [pk.NewPolyPlaintext(v) for v in vals]
+    d = max(p.Degree for p in pts)
+    coeffs = np.array([p.Coefficients[: p.Degree] + [0] * (d - p.Degree) for p in pts], dtype=np.int64)
+    rs = [[rng.randrange(pk.N) for _ in range(d)] for _ in pts]
+    batch = pk.EncryptPolyBatch(coeffs, pk.engine.scalars_be([r for row in rs for r in row]), ScaleFactor=0)
+    singles = []
+    for p, row in zip(pts, rs):
+        pp = type(p)(p.Coefficients[: p.Degree] + [0] * (d - p.Degree), d, p.ScaleFactor, p.params)
+        singles.append(pk.EncryptPoly(pp, rs=row))
+    assert batch.data.tobytes() == b"".join(s.Bytes() for s in singles)
+    for lvl2 in (False, True):
+        bb = pk.MakePolyL2Batch(batch) if lvl2 else batch
+        ss = [pk.MakePolyL2(s) for s in singles] if lvl2 else singles
+        assert bb.data.tobytes() == b"".join(s.Bytes() for s in ss)
+        for constant in (4.12, -3.0):
+            got = pk.MultConstPolyBatch(bb, constant)
+            exp = [pk.MultConstPoly(s, constant) for s in ss]
+            assert got.Degree == exp[0].Degree and got.data.tobytes() == b"".join(x.Bytes() for x in exp)
+        ev = pk.EvalPolyBatch(bb)
+        assert ev.tobytes() == b"".join(pk.EvalPoly(s).C for s in ss)
+    # decrypt the evaluated polynomials: EvalPoly recovers the encoded integer
+    evals, st = pk.engine.decrypt_batch(pk.EvalPolyBatch(batch), False)
+    for v, ok, val in zip(evals, st, vals):
+        if val == int(val):  # integer plaintexts are below MsgSpace
+            assert not ok and int(v) == int(val)
 
 
 # ---------------------------------------------------------------- mid-size parity vs the C port of the oracle

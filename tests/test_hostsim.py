@@ -237,3 +237,96 @@ def test_sim_miller_layout_and_multiplier_variants(flags, tag):
             assert unknown == 0 and violations == 0
     finally:
         sim.use_variant(None)
+
+
+# ---------------------------------------------------------------- non-deterministic mode + poly helpers (8(f1), 8(f2))
+@pytest.mark.parametrize("kb", (64, 128))
+def test_sim_blind(kb):
+    """bgn_g1_blind_batch / bgn_gt_blind_batch device programs against the oracle's
+    non-deterministic Add / Mult with injected r (bgn.go:466-474, 488-495)."""
+    import random
+    g, par, S, tabs = setup(kb)
+    if "P" not in tabs:
+        tabs["P"] = S.build_table(S.P, 8)
+        tabs["Q"] = S.build_table(S.Q, S.nbytes)
+    rng = random.Random(kb)
+    pk = O.PublicKey(par, S.P, S.Q, g["msg_space"], deterministic=False)
+    a = [O.encrypt_with_randomness(pk, x, rng.randrange(par.n)) for x in (0, 1, 5)]
+    b = [O.encrypt_with_randomness(pk, x, rng.randrange(par.n)) for x in (2, 3, 4)]
+    rs = [rng.randrange(par.n) for _ in a] + [0]
+    pdet = O.PublicKey(par, S.P, S.Q, g["msg_space"])
+    sums = [O.add(pdet, x, y).C for x, y in zip(a, b)] + [None]  # O as a base point
+    exp = [O.add(pk, x, y, r).C for x, y, r in zip(a, b, rs)] + [None]
+    assert S.encrypt(None, rs, tabs["P"], tabs["Q"], base=sums) == exp
+    # level 2
+    if "E" not in tabs:
+        tabs["E"] = S.gt_table(O.pairing(S.Q, S.Q, par), S.nbytes)
+    prods = [O.mult(pdet, x, y).C for x, y in zip(a, b)]
+    expm = [O.mult(pk, x, y, r).C for x, y, r in zip(a, b, rs)]
+    assert S.gt_blind(prods, rs[:3], tabs["E"]) == expm
+    assert S.gt_blind(prods[:1], [0], tabs["E"]) == prods[:1]
+
+
+@pytest.mark.parametrize("kb", (64, 128))
+@pytest.mark.parametrize("l2", (False, True))
+def test_sim_polyconv(kb, l2):
+    """MultConstPoly / EvalPoly device programs against the oracle (poly.go:58-120)."""
+    import random
+    g, par, S, _ = setup(kb)
+    rng = random.Random(kb + 5)
+    pk = O.PublicKey(par, S.P, S.Q, g["msg_space"])
+    count = 3
+    polys = []
+    for u in range(count):
+        pt = pk.new_poly_plaintext([9.13, 4.0, 0.0][u])
+        ct = O.encrypt_poly(pk, pt, [rng.randrange(par.n) if u else 0 for _ in range(pt.degree)])
+        polys.append(O.make_poly_l2(pk, ct) if l2 else ct)
+    d = max(p_.degree for p_ in polys)
+    ident = O.make_l2(pk, O.encrypt_zero(pk)) if l2 else O.encrypt_zero(pk)
+    for p_ in polys:  # pad to a common slot count with the identity, as a batch caller does
+        while p_.degree < d:
+            p_.coefficients.append(ident)
+            p_.degree += 1
+    flat = [c.C for p_ in polys for c in p_.coefficients]
+    for constant in (4.12, -2.0):
+        digits = pk.new_unbalanced_plaintext(abs(constant)).coefficients
+        nd = len(digits)
+        got = S.polyconv(flat, d, l2, digits, 0, d + nd, constant < 0, count)
+        exp = [c.C for p_ in polys for c in O.mult_const_poly(pk, p_, constant).coefficients]
+        assert got == exp
+    w = [pk.poly_base ** (d - 1 - k) for k in range(d)]
+    got = S.polyconv(flat, d, l2, w, d - 1, 1, False, count)
+    assert got == [O.eval_poly(pk, p_).C for p_ in polys]
+
+
+def test_sim_padded_gt_bytes():
+    g, par, S, _ = setup(64)
+    vals = gts(par, g["gt_mul"]["a"])[:4]
+    out = S.gt_to_bytes_padded(vals, 2, 1)
+    one = O.gt_to_bytes((1, 0), par)
+    exp = b"".join(O.gt_to_bytes(v, par) for v in vals[:2]) + one + b"".join(O.gt_to_bytes(v, par) for v in vals[2:]) + one
+    assert out == exp
+
+
+@pytest.mark.parametrize("kb", (64, 128))
+def test_sim_new_sections_golden(kb):
+    """the committed golden vectors of the 8(f) sections through the simulated device programs"""
+    g, par, S, tabs = setup(kb)
+    if "P" not in tabs:
+        tabs["P"] = S.build_table(S.P, 8)
+        tabs["Q"] = S.build_table(S.Q, S.nbytes)
+    v = g["g1_blind"]
+    assert S.encrypt(None, [int(r, 16) for r in v["r"]], tabs["P"], tabs["Q"], base=g1s(par, v["a"])) == g1s(par, v["out"])
+    if "E" not in tabs:
+        tabs["E"] = S.gt_table(O.pairing(S.Q, S.Q, par), S.nbytes)
+    v = g["gt_blind"]
+    assert S.gt_blind(gts(par, v["a"]), [int(r, 16) for r in v["r"]], tabs["E"]) == gts(par, v["out"])
+    for lvl, conv in (("l1", g1s), ("l2", gts)):
+        v = g["multconstpoly_" + lvl]
+        for case in v["cases"]:
+            got = S.polyconv(conv(par, v["in"]), v["d"], lvl == "l2", case["digits"], 0, v["d"] + len(case["digits"]),
+                             case["negate"], v["count"])
+            assert got == conv(par, case["out"])
+        v = g["evalpoly_" + lvl]
+        w = [v["base"] ** (v["d"] - 1 - k) for k in range(v["d"])]
+        assert S.polyconv(conv(par, v["in"]), v["d"], lvl == "l2", w, v["d"] - 1, 1, False, v["count"]) == conv(par, v["out"])
