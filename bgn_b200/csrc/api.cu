@@ -121,6 +121,7 @@ struct bgn_ctx {
   uint32_t* tabQ16 = nullptr;  // 16-bit windows of Q, built on the first randomised encryption
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
+  bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
   bool has_secret = false;
   uint32_t *bs_elems = nullptr, *bs_slots = nullptr, *bs_ginv = nullptr;
@@ -638,6 +639,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
     if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : 16;
+    if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -1433,6 +1435,27 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
       g1_from_bytes(c, di, count, C1);
       G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
       run_miller(c, C1, 1, Pv, 1, 1, count, 1, A);
+    }
+    if (c->bs_giant == 1 && c->dec_lucas) {
+      // the whole message space is in the baby-step table: Lucas ladder on the trace, a pair of
+      // lanes per ciphertext, search by real part (lucas.cuh)
+      DecLucasArgs da;
+      da.re = A.re;
+      da.im = A.im;
+      da.count = count;
+      da.elems = c->bs_elems;
+      da.slots = c->bs_slots;
+      da.hmask = c->bs_hmask;
+      da.S = c->bs_S;
+      da.mmax = c->bs_mmax;
+      da.out = reinterpret_cast<int64_t*>(oo.dev);
+      da.status = os.dev;
+      Timer t(c, "k_dec_lucas");
+      c->A->dec_lucas(cfg(c, nblk(2 * count, 64), 64, 0), da);
+      t.done();
+      commit_out(c, oo);
+      commit_out(c, os);
+      return;
     }
     GtPowArgs pa;
     pa.re = A.re;

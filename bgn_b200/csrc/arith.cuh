@@ -691,6 +691,22 @@ struct Fp {
     for (int j = 0; j < L; j++) r[j] = bw ? u[j] : t[j];
   }
 
+  // r = a / 2 mod p for a < 2p: an odd a first gains p (3p < R), then one right shift.  r < 1.5p.
+  BGN_DEV static void halve(uint32_t (&r)[L], const uint32_t (&a)[L]) {
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(a) <= 2.0, "halve expects an operand below 2p");
+    BGN_SETB(r, 1.5);
+#endif
+    uint32_t t[L], mask = 0u - (a[0] & 1u);
+    add_cc(t[0], a[0], c_fc.p[0] & mask);
+    BGN_UNROLL
+    for (int j = 1; j < L - 1; j++) addc_cc(t[j], a[j], c_fc.p[j] & mask);
+    addc(t[L - 1], a[L - 1], c_fc.p[L - 1] & mask);
+    BGN_UNROLL
+    for (int j = 0; j < L - 1; j++) r[j] = (t[j] >> 1) | (t[j + 1] << 31);
+    r[L - 1] = t[L - 1] >> 1;
+  }
+
   BGN_DEV static bool is_zero_raw(const uint32_t (&a)[L]) {
     uint32_t o = 0;
     BGN_UNROLL

@@ -8,6 +8,7 @@
 // very same per-thread program; the wrappers only exist in the CUDA build.
 #pragma once
 #include "pairing.cuh"
+#include "lucas.cuh"
 
 #ifdef BGN_HOSTSIM
 static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -532,9 +533,11 @@ BGN_DEV void gt_polyconv_body(const PolyConvArgs& a, size_t id) {
 // ------------------------------------------------------------ BSGS (gsbs.go)
 // Baby steps: elems[j] = gen^(j+1), j < S, canonical Montgomery AoS [S][2L];
 // open-addressing hash table slots[hmask+1] holding j+1 (0 = empty).
+// hashed on the real part only: gsk^m and gsk^-m share it and only positive m are stored, so the
+// same table serves the full-element search below and the trace search of lucas.cuh
 BGN_DEV uint32_t bsgs_hash(const uint32_t* re, const uint32_t* im) {
-  uint32_t h = re[0] * 0x9E3779B1u ^ im[0] * 0x85EBCA77u ^ (re[1] >> 7);
-  return h ^ (h >> 15);
+  (void)im;
+  return bsgs_hash_re(re);
 }
 
 template <int L>
@@ -631,6 +634,26 @@ BGN_DEV void bsgs_lookup_body(const BsgsLookupArgs& a, size_t e) {
   a.status[e] = 1;
 }
 
+// Decrypt = Lucas ladder for C^q1 + table search, a pair of lanes per ciphertext (lucas.cuh).
+// CPU simulation: both roles of one pair in lockstep.
+#ifdef BGN_HOSTSIM
+template <int L>
+void dec_lucas_pair_sim(const DecLucasArgs& a, size_t e) {
+  typedef Lucas<L> LU;
+  typename LU::State s0, s1;
+  LU::init(s0, a, e, true);
+  LU::init(s1, a, e, true);
+  for (int i = LU::nbits() - 2; i >= 0; i--) {
+    uint32_t r0[L], r1[L];
+    LU::step(r0, s0, LU::bit(i), 0);
+    LU::step(r1, s1, LU::bit(i), 1);
+    LU::update(s0, r0, r1, LU::bit(i), 0);
+    LU::update(s1, r1, r0, LU::bit(i), 1);
+  }
+  LU::finish(s0, a, e);
+}
+#endif
+
 // =========================================================== CUDA wrappers
 #ifndef BGN_HOSTSIM
 #define BGN_KERNEL_1D(NAME, ARGT)                                                   \
@@ -656,6 +679,27 @@ __global__ void k_gt_tab_bases(const uint32_t* gen, int nwin, uint32_t* bases) {
 template <int L>
 __global__ void k_gt_tab_fill(const uint32_t* bases, int nwin, uint32_t* tab) {
   gt_tab_fill_body<L>(bases, nwin, tab, BGN_GID(size_t));
+}
+
+template <int L>
+__global__ void __launch_bounds__(64) k_dec_lucas(const __grid_constant__ DecLucasArgs a) {
+  typedef Lucas<L> LU;
+  const size_t gid = BGN_GID(size_t);
+  const size_t e = gid >> 1;
+  const int s = (int)(gid & 1);
+  const bool active = e < a.count;
+  typename LU::State st;
+  LU::init(st, a, e, active);
+  BGN_UNROLL1
+  for (int i = LU::nbits() - 2; i >= 0; i--) {
+    const int b = LU::bit(i);
+    uint32_t mine[L], other[L];
+    LU::step(mine, st, b, s);
+#pragma unroll
+    for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
+    LU::update(st, mine, other, b, s);
+  }
+  if (active && s == 0) LU::finish(st, a, e);
 }
 
 template <int L>

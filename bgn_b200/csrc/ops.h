@@ -35,6 +35,7 @@ struct LOpsA {
   void (*gt_tab_bases)(LaunchCfg, const uint32_t* gen, int nwin, uint32_t* bases);
   void (*gt_tab_fill)(LaunchCfg, const uint32_t* bases, int nwin, uint32_t* tab);
   void (*gt_polyconv)(LaunchCfg, const PolyConvArgs&);
+  void (*dec_lucas)(LaunchCfg, const DecLucasArgs&);
 };
 
 struct LOpsB {

@@ -165,3 +165,17 @@ struct BsgsLookupArgs {
   int64_t* out;
   uint8_t* status;          // 0 ok, 1 out of bounds (gsbs.go:105)
 };
+
+// Decrypt with the whole message space in the baby-step table (lucas.cuh)
+struct DecLucasArgs {
+  const uint32_t *re, *im;  // C, Montgomery [count][L], values below 2p
+  size_t count;
+  const uint32_t* elems;    // baby steps gsk^(j+1), canonical Montgomery AoS [S][2L]
+  const uint32_t* slots;    // open addressing on the real part, value j+1 (0 = empty)
+  uint32_t hmask;
+  uint32_t S;
+  uint64_t mmax;
+  int64_t* out;
+  uint8_t* status;
+};
+

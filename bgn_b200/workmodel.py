@@ -96,6 +96,15 @@ def gt_pow_modmuls(e: int) -> int:
     return 2 * (e.bit_length() - 1) + 3 * (bin(e).count("1") - 1)
 
 
+def dec_lucas_modmuls(e: int) -> int:
+    """k_dec_lucas (lucas.cuh), per ciphertext: one squaring and one product per exponent bit below
+    the top one (one each per lane of the pair), the set-up both lanes run (norm check 2, V_2 1) and
+    the two products of the sign test."""
+    if e == 0:
+        return 0
+    return 2 * (e.bit_length() - 1) + 2 * 3 + 2
+
+
 def encrypt_modmuls(n: int, rbytes: int, window_bits: int = 8, p_x_nonzero: float = 2.0 / 3.0) -> float:
     """k_encrypt, EXPECTED products per coefficient for uniform r: one complete mixed addition (11
     products; the first one into O is a copy) per non-zero window digit of r, plus one for a non-zero

@@ -139,6 +139,9 @@ int hs_g1_polyconv(int L, const PolyConvArgs* a) {
 int hs_gt_polyconv(int L, const PolyConvArgs* a) {
   FOR_L(L, for (size_t id = 0; id < a->count * (size_t)a->j_count; id++) gt_polyconv_body<LL>(*a, id))
 }
+int hs_dec_lucas(int L, const DecLucasArgs* a) {
+  FOR_L(L, for (size_t e = 0; e < a->count; e++) dec_lucas_pair_sim<LL>(*a, e))
+}
 // tracker self-test: a difference whose subtrahend may exceed its offset must be flagged
 int hs_selftest_violation() {
   uint64_t before = bgnsim::violations;

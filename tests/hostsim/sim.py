@@ -58,6 +58,12 @@ class PolyConvArgs(C.Structure):
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t)]
 
 
+class DecLucasArgs(C.Structure):
+    _fields_ = [("re", u32p), ("im", u32p), ("count", C.c_size_t), ("elems", u32p), ("slots", u32p),
+                ("hmask", C.c_uint32), ("S", C.c_uint32), ("mmax", C.c_uint64), ("out", C.POINTER(C.c_int64)),
+                ("status", u8p)]
+
+
 class NormArgs(C.Structure):
     _fields_ = [("X", u32p), ("Y", u32p), ("Z", u32p), ("scratch", u32p), ("count", C.c_size_t), ("N", C.c_size_t),
                 ("G", C.c_int), ("ox", u32p), ("oy", u32p), ("o_estride", C.c_size_t), ("o_lstride", C.c_size_t),
@@ -451,6 +457,20 @@ class Sim:
                            self.bs_S, P32(self.bs_ginv), self.bs_giant, self.mmax,
                            out.ctypes.data_as(C.POINTER(C.c_int64)), P8(status))
         assert lib().hs_bsgs_lookup(self.L, C.byref(a)) == 0
+        return list(out), list(status)
+
+    def dec_lucas(self, cts):
+        """k_dec_lucas: Lucas ladder for C^q1 + search by real part (needs bsgs_setup with S = mmax)"""
+        assert self.bs_giant == 1
+        count = len(cts)
+        re, im = self.gt_arrays(cts)
+        lib().hs_track_array(P32(re), C.c_size_t(count), self.L, C.c_double(2.0))
+        lib().hs_track_array(P32(im), C.c_size_t(count), self.L, C.c_double(2.0))
+        out = np.zeros(count, dtype=np.int64)
+        status = np.zeros(count, dtype=np.uint8)
+        a = DecLucasArgs(P32(re), P32(im), count, P32(self.bs_elems), P32(self.bs_slots), self.bs_hmask, self.bs_S,
+                         self.mmax, out.ctypes.data_as(C.POINTER(C.c_int64)), P8(status))
+        assert lib().hs_dec_lucas(self.L, C.byref(a)) == 0
         return list(out), list(status)
 
     # ---- byte formats

@@ -140,6 +140,32 @@ def test_sim_decrypt(kb):
         assert [int(x) for x in out] == v["out"]
 
 
+@pytest.mark.parametrize("kb", (64, 128))
+def test_sim_decrypt_lucas(kb):
+    """k_dec_lucas (Lucas ladder on the trace, a lane pair per ciphertext, search by real part)
+    gives the plaintexts and statuses of the reference's decrypt, incl. negatives, zero, the
+    out-of-bounds values, and status 1 for a non-unitary input."""
+    g, par, S, _ = setup(kb)
+    v = g["decrypt_l2"]
+    gsk = O.fp2_pow(O.pairing(S.P, S.P, par), int(g["q1"], 16), par.p)
+    S.bsgs_setup(gsk, g["msg_space"], None)
+    cts = gts(par, v["in"])
+    out, status = S.dec_lucas(cts)
+    assert [int(s) for s in status] == v["status"]
+    assert [int(x) for x in out] == v["out"]
+    # every |m| up to a few dozen, both signs, blinded by a random e(Q,Q) power
+    import random
+    rng = random.Random(kb)
+    ePP, eQQ = O.pairing(S.P, S.P, par), O.pairing(S.Q, S.Q, par)
+    ms = list(range(-20, 21)) + [S.mmax, -S.mmax, S.mmax + 1]
+    cts = [O.fp2_mul(O.fp2_pow(ePP, m % par.n, par.p), O.fp2_pow(eQQ, rng.randrange(par.n), par.p), par.p) for m in ms]
+    out, status = S.dec_lucas(cts)
+    assert [int(x) for x in out] == ms[:-1] + [0]
+    assert [int(s) for s in status] == [0] * (len(ms) - 1) + [1]
+    bad = (cts[3][0], (cts[3][1] + 1) % par.p)  # not of norm 1
+    assert S.dec_lucas([bad]) == ([0], [1])
+
+
 @pytest.mark.parametrize("kb", SIM_KB)
 def test_sim_bytes(kb):
     g, par, S, _ = setup(kb)

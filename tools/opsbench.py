@@ -53,6 +53,7 @@ def main():
                 best = t
                 kern = {k: eng.timing_get(k)[0] for k in
                         ("k_encrypt", "k_normalize", "k_g1_add", "k_g1_mulvar", "k_gt_pow", "k_bsgs_lookup", "k_miller",
+                         "k_dec_lucas", "k_gt_blind", "k_g1_polyconv", "k_gt_polyconv", "k_gt_mul",
                          "k_g1_from_bytes", "k_g1_to_bytes", "k_fp2_from_bytes", "k_fp2_to_bytes")}
         return best, {k: v for k, v in kern.items() if v > 0}
 
@@ -119,7 +120,10 @@ def main():
         vals["v"], vals["s"] = eng.decrypt_batch(l2, True)
 
     t, k = timed(dec)
-    entry("decrypt_l2", nd, "decryptions (T = 2^20)", t, k, workmodel.gt_pow_modmuls(q1), "k_gt_pow")
+    if "k_dec_lucas" in k:
+        entry("decrypt_l2", nd, "decryptions (T = 2^20)", t, k, workmodel.dec_lucas_modmuls(q1), "k_dec_lucas")
+    else:
+        entry("decrypt_l2", nd, "decryptions (T = 2^20)", t, k, workmodel.gt_pow_modmuls(q1), "k_gt_pow")
     ok = bool((vals["v"] == av * bv).all().item()) and not bool(vals["s"].any().item())
     res["ops"]["decrypt_l2"]["plaintexts_match"] = ok
     t, k = timed(lambda: eng.gt_pow_secret_batch(l2))
@@ -128,6 +132,39 @@ def main():
                             rr.reshape(-1))
     t, k = timed(lambda: eng.decrypt_batch(dl1, False))
     entry("decrypt_l1", nd, "decryptions of level-1 ciphertexts", t, k)
+    # ---- larger decrypt batch (the kernel's rate once every scheduler holds two warps)
+    big = 1 << 18
+    l2big = l2.repeat(big // nd) if big > nd else l2
+    t, k = timed(lambda: eng.decrypt_batch(l2big, True))
+    dom = "k_dec_lucas" if "k_dec_lucas" in k else "k_gt_pow"
+    entry("decrypt_l2_2e18", l2big.numel() // EB, "decryptions (T = 2^20)", t, k,
+          workmodel.dec_lucas_modmuls(q1) if dom == "k_dec_lucas" else workmodel.gt_pow_modmuls(q1), dom)
+
+    # ---- non-deterministic mode: re-randomisation of level-1 / level-2 coefficients
+    nb = 1 << 18
+    rb = torch.randint(0, 256, (nb, SB), generator=gen, device=dev, dtype=torch.uint8)
+    rb[:, 0] &= 0x3F
+    rb = rb.reshape(-1)
+    ob = torch.empty(nb * EB, dtype=torch.uint8, device=dev)
+    t, k = timed(lambda: eng.g1_blind_batch(out[: nb * EB], rb, out=ob))
+    entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k, workmodel.encrypt_modmuls(n, SB, 16, 0.0) + 11,
+          "k_encrypt")
+    l2b = l2.repeat(nb // nd)
+    t, k = timed(lambda: eng.gt_blind_batch(l2b, rb, out=ob))
+    entry("blind_l2", nb, "level-2 re-randomisations (* e(Q,Q)^r)", t, k, 3 * SB * 255.0 / 256.0, "k_gt_blind")
+
+    # ---- polynomial helpers on 2^16 polynomials of 11 slots
+    npoly = min(args.plaintexts, 1 << 16)
+    polys = out[: npoly * D * EB]
+    digits3 = [2, 1, 0, 2, 1]
+    t, k = timed(lambda: eng.multconstpoly_batch(polys, D, False, digits3, False, npoly))
+    entry("multconstpoly_l1", npoly, "MultConstPoly (11 slots x 5 digits)", t, k)
+    t, k = timed(lambda: eng.evalpoly_batch(polys, D, False, 3, npoly))
+    entry("evalpoly_l1", npoly, "EvalPoly (11 slots)", t, k)
+    nl2 = 1 << 12
+    t, k = timed(lambda: eng.make_poly_l2_batch(polys[: nl2 * D * EB], D, nl2))
+    entry("make_poly_l2", nl2, "MakePolyL2 (11 pairings with P each)", t, k,
+          D * workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
     print(json.dumps(res, indent=1))
     eng.close()
 
