@@ -120,6 +120,8 @@ struct bgn_ctx {
   uint32_t *tabP = nullptr, *tabQ = nullptr;
   uint32_t* tabQ16 = nullptr;  // 16-bit windows of Q, built on the first randomised encryption
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
+  uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
+  bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
   int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
@@ -396,7 +398,7 @@ size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
 
 // the Miller team kernel; dM <= dE
 void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
-                const GtArr& out) {
+                const GtArr& out, uint32_t* lines_out = nullptr) {
   if (!count) return;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
@@ -475,9 +477,65 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.teams_per_group = tpg;
   a.group_threads = GT_;
   a.skew_cycles = c->miller_skew;
+  a.lines_out = lines_out;
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
   c->A->miller(cfg(c, nblocks, nt, smem), a);
+  t.done();
+}
+
+// lines of the Miller loop of P, recorded once per key by a one-unit run of the general kernel
+int miller_nsteps(const bgn_ctx* c) {
+  int n = 0;
+  for (int idx = 1; idx < c->pc.naf_len; idx++) {
+    n++;
+    if (c->pc.naf[idx] != 0 && idx != c->pc.naf_len - 1) n++;
+  }
+  return n;
+}
+// uses and releases the arena: call before carving a call's buffers
+void ensure_linesP(bgn_ctx* c) {
+  if (c->linesP || !c->fixed_lines) return;
+  uint32_t* tab = nullptr;
+  CK(cudaMalloc(&tab, (size_t)miller_nsteps(c) * 3 * c->L * 4));
+  try {
+    arena_reset(c);
+    arena_reserve(c, gt_bytes(c, 1) + miller_scratch(c, 1, 1) + 8192);
+    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+    GtArr e = gt_alloc(c, 1);
+    run_miller(c, Pv, 1, Pv, 1, 0, 1, 1, e, tab);
+    finish(c);
+  } catch (...) {
+    cudaFree(tab);
+    throw;
+  }
+  c->linesP = tab;
+  arena_reset(c);
+}
+// out[i] = e(E[i], P) through the line table
+void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out) {
+  if (!count) return;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  // one block per SM up to 256 threads; smaller batches use whole scheduler rounds (128 threads)
+  size_t per_sm = (count + sms - 1) / sms;
+  int nt = (int)std::min<size_t>(256, std::max<size_t>(128, (per_sm + 127) / 128 * 128));
+  size_t smem = c->A->miller_fixed_smem_bytes(nt);
+  while (smem > 227 * 1024 - 64 && nt > 32) {
+    nt -= 32;
+    smem = c->A->miller_fixed_smem_bytes(nt);
+  }
+  MillerFixedArgs a;
+  a.lines = c->linesP;
+  a.Ex = E.x;
+  a.Ey = E.y;
+  a.Einf = E.inf;
+  a.out_re = out.re;
+  a.out_im = out.im;
+  a.count = (int)count;
+  Timer t(c, "k_miller_fixed");
+  CK(c->A->miller_fixed_set_smem(smem));
+  c->A->miller_fixed(cfg(c, nblk(count, nt), nt, smem), a);
   t.done();
 }
 
@@ -640,6 +698,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
     if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : 16;
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
+    if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -797,6 +856,7 @@ void bgn_ctx_destroy(bgn_ctx* c) {
   cudaFree(c->tabQ);
   cudaFree(c->tabQ16);
   cudaFree(c->tabE);
+  cudaFree(c->linesP);
   cudaFree(c->bs_elems);
   cudaFree(c->bs_slots);
   cudaFree(c->bs_ginv);
@@ -1040,6 +1100,7 @@ int bgn_gt_inv_batch(bgn_ctx* c, const uint8_t* a, size_t count, uint8_t* out) {
 }
 
 static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  if (!b) ensure_linesP(c);
   arena_reserve(c, 3 * io_bytes(c, count) + 2 * g1_bytes(c, count) + gt_bytes(c, count) + miller_scratch(c, count, 1) + 8192);
   OutBuf ob = stage_out(c, out, count * 2 * c->B);
   const uint8_t* da = stage_in(c, a, count * 2 * c->B);
@@ -1051,6 +1112,8 @@ static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t c
     G1Arr Bv = g1_alloc(c, count);
     g1_from_bytes(c, db, count, Bv);
     run_miller(c, A, 1, Bv, 1, 0, count, 1, R);
+  } else if (c->linesP) {
+    run_miller_fixed(c, A, count, R);
   } else {
     G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
     run_miller(c, A, 1, Pv, 1, 1, count, 1, R);
@@ -1307,6 +1370,7 @@ int bgn_make_poly_l2_batch(bgn_ctx* c, const uint8_t* in, size_t d, size_t count
     if (!in || !out || !d) throw ArgErr{"bad argument"};
     size_t nin = count * d, nout = count * (d + 1);
     check_count(nout);
+    ensure_linesP(c);
     arena_reserve(c, io_bytes(c, nin) + io_bytes(c, nout) + g1_bytes(c, nin) + gt_bytes(c, nin) +
                          miller_scratch(c, nin, 1) + 8192);
     OutBuf ob = stage_out(c, out, nout * 2 * c->B);
@@ -1314,8 +1378,12 @@ int bgn_make_poly_l2_batch(bgn_ctx* c, const uint8_t* in, size_t d, size_t count
     G1Arr A = g1_alloc(c, nin);
     g1_from_bytes(c, da, nin, A);
     GtArr R = gt_alloc(c, nin);
-    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
-    run_miller(c, A, 1, Pv, 1, 1, nin, 1, R);
+    if (c->linesP) {
+      run_miller_fixed(c, A, nin, R);
+    } else {
+      G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+      run_miller(c, A, 1, Pv, 1, 1, nin, 1, R);
+    }
     gt_to_bytes(c, R, nout, ob.dev, (int)d, 1);
     commit_out(c, ob);
   });
@@ -1421,6 +1489,7 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
     if (!count) return;
     if (!in || !out || !status) throw ArgErr{"null buffer"};
     check_count(count);
+    if (!is_l2) ensure_linesP(c);
     arena_reserve(c, io_bytes(c, count) + g1_bytes(c, count) + 3 * gt_bytes(c, count) + pad256(count * 8) +
                          pad256(count) + miller_scratch(c, count, 1) + 8192);
     const uint8_t* di = stage_in(c, in, count * 2 * c->B);
@@ -1433,8 +1502,12 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
       // level 1: e(C, P)^q1 = e(P,P)^(q1 m); same m as the reference's G1 table search (bgn.go:222-223)
       G1Arr C1 = g1_alloc(c, count);
       g1_from_bytes(c, di, count, C1);
-      G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
-      run_miller(c, C1, 1, Pv, 1, 1, count, 1, A);
+      if (c->linesP) {
+        run_miller_fixed(c, C1, count, A);
+      } else {
+        G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+        run_miller(c, C1, 1, Pv, 1, 1, count, 1, A);
+      }
     }
     if (c->bs_giant == 1 && c->dec_lucas) {
       // the whole message space is in the baby-step table: Lucas ladder on the trace, a pair of

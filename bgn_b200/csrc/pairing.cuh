@@ -118,6 +118,7 @@ struct MillerTeam {
   int nt, tid, bid;
   int t, team, unit, group;
   bool active;
+  int step = 0;  // index of the current line (one per phase A / phase B round)
 
   // A block is `groups` barrier groups of a.group_threads threads; each group holds whole teams and
   // synchronises on its own named barrier, so the groups drift independently: while the warps of one
@@ -215,11 +216,18 @@ struct MillerTeam {
         MA::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), (a.Mx + (size_t)(idx) * L), (a.My + (size_t)(idx) * L),
                      op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
       }
+      if (a.lines_out && unit == 0 && t == 0) {  // record mode: the fixed point's line table
+        uint32_t* dst = a.lines_out + (size_t)step * 3 * L;
+        s_out(dst, slot(tid, S_CR));
+        s_out(dst + L, slot(tid, S_AR));
+        s_out(dst + 2 * L, slot(tid, S_BI));
+      }
     }
   }
 
   // phase B: fold line_i(B_k) into the slot i+k for every Miller point i; this thread owns slots t and t+TS
   BGN_DEV void phaseB() {
+    step++;
     if (!active) return;
     int TS = a.dE;
     int base = tid - t;  // first thread of the team
@@ -309,5 +317,77 @@ struct MillerTeam {
       }
     }
     finalize();
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Fixed-first-argument pairing: replay of a recorded line table (types.h: MillerFixedArgs)
+// ---------------------------------------------------------------------------
+template <int L>
+struct MillerFixed {
+  typedef MF<L, BGN_MILLER_LOOP, 1> M;
+  typedef MF<L, BGN_MILLER_LOOP_A, 1> MA;
+  // unit-stride shared-memory slots [slot][thread][L]: the accumulator, the evaluation point, and
+  // two more for the final exponentiation (the evaluation point's slots are dead by then)
+  enum { S_FR = 0, S_FI = 1, S_EX = 2, S_EY = 3, S_G0 = 4, S_G1 = 5, NSLOT = 6 };
+  static BGN_HD size_t smem_words(int nt) { return (size_t)NSLOT * L * nt; }
+  // number of lines a key's table holds: one per doubling and one per non-zero digit below the top
+  // one, the last digit's chord dropped (vertical line)
+  static BGN_HD int nsteps(const PairConsts& pc) {
+    int n = 0;
+    for (int idx = 1; idx < pc.naf_len; idx++) {
+      n++;
+      if (pc.naf[idx] != 0 && idx != pc.naf_len - 1) n++;
+    }
+    return n;
+  }
+
+  BGN_DEV static void run(const MillerFixedArgs& a, uint32_t* smem, int tid, int nt, size_t e) {
+    typedef F<L> FF;
+    if (e >= (size_t)a.count) return;
+    auto slot = [&](int k) -> E { return smem + ((size_t)k * nt + tid) * L; };
+    E fr = slot(S_FR), fi = slot(S_FI), ex = slot(S_EX), ey = slot(S_EY);
+    if (a.Einf[e]) {  // e(., O) = 1
+      FF::set_one(a.out_re + e * L);
+      FF::set_zero(a.out_im + e * L);
+      return;
+    }
+    FF::copy(fr, c_fc.one);
+    FF::set_zero(fi);
+    FF::copy(ex, a.Ex + e * L);
+    FF::copy(ey, a.Ey + e * L);
+    const uint32_t* ln = a.lines;
+    const int n = c_pc.naf_len;
+    auto fold = [&]() {
+#if BGN_LINE_LAZY
+      M::template line_mul_lazy<BGN_LINE_KARATSUBA>(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+#else
+      M::line_mul(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+#endif
+      ln += 3 * L;
+    };
+    BGN_UNROLL1
+    for (int idx = 1; idx < n; idx++) {
+      if (idx != 1) MA::sqr2(fr, fi);
+      fold();
+      if (c_pc.naf[idx] != 0 && idx != n - 1) fold();
+    }
+    // final exponentiation (conj(f)^2 / N(f))^l, as MillerTeam::finalize for one slot
+    E n0 = ex, i0 = ey, g0 = slot(S_G0), g1 = slot(S_G1);
+    MA::fe_prepare(fr, fi, n0);
+    MA::fp_inv(i0, n0);
+    MA::scale2(fr, fi, i0);
+    FF::copy(g0, fr);
+    FF::copy(g1, fi);
+    uint64_t l = c_pc.l;
+    int top = 63;
+    while (top > 0 && !((l >> top) & 1)) top--;
+    for (int bit = top - 1; bit >= 0; bit--) {
+      MA::sqr2(fr, fi);
+      if ((l >> bit) & 1) MA::mul2(fr, fi, g0, g1);
+    }
+    MA::norm2(fr, fi);
+    FF::copy(a.out_re + e * L, fr);
+    FF::copy(a.out_im + e * L, fi);
   }
 };

@@ -84,6 +84,19 @@ def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
     return D * per_dbl + (D - 1) * nslots * 2 + A * per_add + final_exp_modmuls(p, l, L, nslots, dE)
 
 
+def miller_fixed_products(p: int, n: int, l: int) -> int:
+    """32x32->64 products of one k_miller_fixed thread (pairing with the recorded line table of a
+    fixed first argument): per step one line_mul (lazy up to 17 limbs) and, on doubling steps after
+    the first, one sqr2; then the final exponentiation of one slot."""
+    L = pick_limbs(p)
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    full = products_per_modmul(L)
+    line = (2 * full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 5 * full
+    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1)) * full
+
+
 def canonical_pairing_modmuls(n: int, l: int) -> int:
     """PBC-like unshared schedule, one full pairing."""
     return 23 * n.bit_length() + 18 * bin(n).count("1") - 70 + 4 + 3 + 2 * l.bit_length() + 3 * bin(l).count("1") + 1

@@ -139,6 +139,13 @@ int hs_g1_polyconv(int L, const PolyConvArgs* a) {
 int hs_gt_polyconv(int L, const PolyConvArgs* a) {
   FOR_L(L, for (size_t id = 0; id < a->count * (size_t)a->j_count; id++) gt_polyconv_body<LL>(*a, id))
 }
+int hs_miller_fixed(int L, const MillerFixedArgs* a, int nt) {
+  FOR_L(L, {
+    std::vector<uint32_t> smem(MillerFixed<LL>::smem_words(nt) + 8);
+    for (int e = 0; e < a->count; e++) MillerFixed<LL>::run(*a, smem.data(), e % nt, nt, (size_t)e);
+  })
+}
+int hs_miller_nsteps(int L) { FOR_L(L, return MillerFixed<LL>::nsteps(c_pc)) }
 int hs_dec_lucas(int L, const DecLucasArgs* a) {
   FOR_L(L, for (size_t e = 0; e < a->count; e++) dec_lucas_pair_sim<LL>(*a, e))
 }

@@ -35,7 +35,13 @@ class MillerArgs(C.Structure):
     _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
                 ("priv", u32p), ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
                 ("e_bcast", C.c_int), ("dM", C.c_int), ("dE", C.c_int), ("out_slots", C.c_int), ("count", C.c_int),
-                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int)]
+                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int),
+                ("lines_out", u32p)]
+
+
+class MillerFixedArgs(C.Structure):
+    _fields_ = [("lines", u32p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p), ("out_re", u32p), ("out_im", u32p),
+                ("count", C.c_int)]
 
 
 class EncArgs(C.Structure):
@@ -231,7 +237,7 @@ class Sim:
         return x, y, inf
 
     # ---- kernels
-    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2):
+    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2, lines_out=None):
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
         nout = count * out_slots
@@ -239,12 +245,31 @@ class Sim:
         oim = np.zeros((nout, self.L), dtype=np.uint32)
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
-                       teams_per_block * dE + 1, 0)  # one idle thread per group: exercises the inactive path
+                       teams_per_block * dE + 1, 0,  # one idle thread per group: exercises the inactive path
+                       None if lines_out is None else P32(lines_out))
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
         nblocks = (count + groups * teams_per_block - 1) // (groups * teams_per_block)
         assert lib().hs_miller(self.L, C.byref(a), nblocks, nt) == 0
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
+
+    def record_lines(self, base):
+        """api.cu: ensure_linesP -- one-unit run of the general kernel in record mode"""
+        ns = naf_digits(self.par.n)
+        nsteps = sum(1 + (1 if (ns[i] != 0 and i != len(ns) - 1) else 0) for i in range(1, len(ns)))
+        lines = np.zeros(nsteps * 3 * self.L, dtype=np.uint32)
+        self.miller([base], 1, [base], 1, 1, 1, teams_per_block=1, lines_out=lines)
+        return lines
+
+    def pair_fixed(self, lines, Epts, nt=4):
+        """k_miller_fixed: e(E[i], base) through the recorded line table"""
+        count = len(Epts)
+        Ex, Ey, Ei = self.g1_arrays(Epts)
+        ore = np.zeros((count, self.L), dtype=np.uint32)
+        oim = np.zeros_like(ore)
+        a = MillerFixedArgs(P32(lines), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), count)
+        assert lib().hs_miller_fixed(self.L, C.byref(a), nt) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
     def multpoly(self, c1, d1, c2, d2, count):
         if d1 <= d2:

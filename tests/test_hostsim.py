@@ -356,3 +356,17 @@ def test_sim_new_sections_golden(kb):
         v = g["evalpoly_" + lvl]
         w = [v["base"] ** (v["d"] - 1 - k) for k in range(v["d"])]
         assert S.polyconv(conv(par, v["in"]), v["d"], lvl == "l2", w, v["d"] - 1, 1, False, v["count"]) == conv(par, v["out"])
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_pair_fixed(kb):
+    """k_miller_fixed (replay of the recorded line table of P) against the golden makeL2 vectors
+    and the oracle's pairing for arbitrary evaluation points, incl. O."""
+    g, par, S, tabs = setup(kb)
+    if "linesP" not in tabs:
+        tabs["linesP"] = S.record_lines(S.P)
+    v = g["make_l2"]
+    assert S.pair_fixed(tabs["linesP"], g1s(par, v["a"])) == gts(par, v["out"])
+    if kb < 512:
+        pts = g1s(par, g["g1_add"]["out"])
+        assert S.pair_fixed(tabs["linesP"], pts, nt=3) == [O.pairing(pt, S.P, par) for pt in pts]

@@ -52,10 +52,11 @@ def main():
             if best is None or t < best:
                 best = t
                 kern = {k: eng.timing_get(k)[0] for k in
-                        ("k_encrypt", "k_normalize", "k_g1_add", "k_g1_mulvar", "k_gt_pow", "k_bsgs_lookup", "k_miller",
+                        ("k_encrypt", "k_normalize", "k_g1_add", "k_g1_mulvar", "k_gt_pow", "k_bsgs_lookup", "k_miller", "k_miller_fixed",
                          "k_dec_lucas", "k_gt_blind", "k_g1_polyconv", "k_gt_polyconv", "k_gt_mul",
                          "k_g1_from_bytes", "k_g1_to_bytes", "k_fp2_from_bytes", "k_fp2_to_bytes")}
-        return best, {k: v for k, v in kern.items() if v > 0}
+        kern["k_miller"] -= kern["k_miller_fixed"]  # timing_get matches by prefix
+        return best, {k: v for k, v in kern.items() if v > 1e-9}
 
     def entry(name, units, unit_name, ms_call, kern, modmuls_per_unit=None, dominant=None):
         e = {"units": units, "unit": unit_name, "ms": ms_call, "per_s": units / (ms_call * 1e-3), "kernel_ms": kern}
@@ -131,7 +132,8 @@ def main():
     dl1 = eng.encrypt_batch(torch.randint(-1000, 1000, (nd,), generator=gen, device=dev, dtype=torch.int64),
                             rr.reshape(-1))
     t, k = timed(lambda: eng.decrypt_batch(dl1, False))
-    entry("decrypt_l1", nd, "decryptions of level-1 ciphertexts", t, k)
+    entry("decrypt_l1", nd, "decryptions of level-1 ciphertexts", t, k, workmodel.miller_fixed_products(p, n, l) / ppm,
+          "k_miller_fixed")
     # ---- larger decrypt batch (the kernel's rate once every scheduler holds two warps)
     big = 1 << 18
     l2big = l2.repeat(big // nd) if big > nd else l2
@@ -164,7 +166,7 @@ def main():
     nl2 = 1 << 12
     t, k = timed(lambda: eng.make_poly_l2_batch(polys[: nl2 * D * EB], D, nl2))
     entry("make_poly_l2", nl2, "MakePolyL2 (11 pairings with P each)", t, k,
-          D * workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
+          D * workmodel.miller_fixed_products(p, n, l) / ppm, "k_miller_fixed")
     print(json.dumps(res, indent=1))
     eng.close()
 
