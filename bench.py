@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 D1 = D2 = 11
 KEY_BITS = 512
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_miller<17> launch over 3404 units (one full
+# wave), from the `ncu --set full` capture summarised in profiles/r01_miller_v17_ncu.txt
+NCU_DRAM_BYTES_PER_UNIT = 10820864 / 3404.0
 METRIC = "pairings/s"
 WORKLOAD = "keyBits=512 batched EMult (MultPoly) of 2^14 L1 poly-ciphertext pairs, d1=d2=11 (121 pairings/EMult)"
 
@@ -76,7 +79,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    count = 4 * cores  # EMults per step (~0.3 s of one core each at 512 bit): every thread gets 4
+    count = 16 * cores  # EMults per step (~0.25 s of one core each at 512 bit): every thread gets 16
     t0 = time.perf_counter()
     for _ in range(min(args.warmup, 1)):
         cpu_emults(max(1, cores // 4), cores)
@@ -259,7 +262,10 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {
         "bound": "imad", "kernel": "k_miller<17>", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
-        "unit": "T(32x32->64 products)/s", "frac": achieved / imad_peak, "traffic": None,
+        "unit": "T(32x32->64 products)/s", "frac": achieved / imad_peak,
+        "traffic": NCU_DRAM_BYTES_PER_UNIT * pairs,
+        "traffic_note": "DRAM bytes per launch scaled from the ncu capture of one full wave (profiles/); algorithmic "
+                        "bytes per launch = %d" % algo_bytes,
         "peak_source": "IMAD.WIDE.U32 microkernel measured in this run (nominal 148 SM x 64/clk x %.3f GHz = %.2f)" % (
             (clocks.get("sm_max_mhz") or 1965.0) / 1e3, 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12),
         "fp_products_per_emult": modmuls_unit, "products_per_emult": workmodel.miller_unit_products(p, n, l, D1, D2),
@@ -324,9 +330,23 @@ def run_ours(args):
         dec["v"], dec["s"] = eng.decrypt_batch(l2, True)
 
     dec_ms = best_ms(do_dec)
+    dec1 = {}
+
+    def do_dec1():
+        dec1["v"], dec1["s"] = eng.decrypt_batch(enc_out[: n_dec * EB], False)
+
+    dec1_ms = best_ms(do_dec1)
+    bl_out = torch.empty(n_dec * EB, dtype=torch.uint8, device=dev)
+    bl1_ms = best_ms(lambda: eng.g1_blind_batch(enc_out, rr, out=enc_out.new_empty(n_enc * EB)))
+    bl2_ms = best_ms(lambda: eng.gt_blind_batch(l2, rr[: n_dec * SB], out=bl_out))
     ops = {"encrypt_coeff_per_s": sum_over_ranks(n_enc / (enc_ms * 1e-3)),
            "eadd_coeff_per_s": sum_over_ranks((n_enc // 2) / (add_ms * 1e-3)),
            "decrypt_l2_per_s": sum_over_ranks(n_dec / (dec_ms * 1e-3)),
+           "decrypt_l1_per_s": sum_over_ranks(n_dec / (dec1_ms * 1e-3)),
+           "decrypt_l1_matches_plaintext": bool((dec1["v"] == digits[:n_dec]).all().item())
+           and not bool(dec1["s"].any().item()),
+           "rerandomize_l1_per_s": sum_over_ranks(n_enc / (bl1_ms * 1e-3)),
+           "rerandomize_l2_per_s": sum_over_ranks(n_dec / (bl2_ms * 1e-3)),
            "decrypt_all_found": not bool(dec["s"].any().item()),
            "note": "keyBits=512, per-call device time incl. (de)serialisation kernels; Encrypt: x in {-1,0,1}, "
                    "512-bit r; Decrypt: GT^q1 + table lookup over T=2^20; summed over ranks"}
@@ -347,7 +367,7 @@ def run_ours(args):
     }
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = host_cores()
-        cnt = 4 * cores  # ~20 core-seconds
+        cnt = 48 * cores  # ~12 s on every core (~0.25 core-seconds per EMult at 512 bit)
         v, el = cpu_emults(cnt, cores)
         line["cpu_baseline"] = {
             "value": v, "unit": "pairings/s", "cores": cores, "kind": "port",

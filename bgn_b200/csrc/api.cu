@@ -111,6 +111,7 @@ struct bgn_ctx {
   int L = 0, B = 0, nbytes = 0;
   const LOpsA* A = nullptr;
   const LOpsB* Bo = nullptr;
+  const LOpsC* Co = nullptr;
   FieldConsts fc;
   PairConsts pc;
   cudaStream_t stream = nullptr;
@@ -170,6 +171,7 @@ void activate(bgn_ctx* c) {
   if (it == g_active.end() || it->second != c) {
     CK(c->A->upload(&c->fc, &c->pc, c->stream));
     CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
+    CK(c->Co->upload(&c->fc, &c->pc, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     g_active[c->device] = c;
   }
@@ -177,6 +179,7 @@ void activate(bgn_ctx* c) {
 void reupload_pc(bgn_ctx* c) {
   CK(c->A->upload(&c->fc, &c->pc, c->stream));
   CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
+  CK(c->Co->upload(&c->fc, &c->pc, c->stream));
   CK(cudaStreamSynchronize(c->stream));
 }
 
@@ -398,7 +401,7 @@ size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
 
 // the Miller team kernel; dM <= dE
 void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
-                const GtArr& out, uint32_t* lines_out = nullptr) {
+                const GtArr& out) {
   if (!count) return;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
@@ -477,14 +480,13 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.teams_per_group = tpg;
   a.group_threads = GT_;
   a.skew_cycles = c->miller_skew;
-  a.lines_out = lines_out;
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
   c->A->miller(cfg(c, nblocks, nt, smem), a);
   t.done();
 }
 
-// lines of the Miller loop of P, recorded once per key by a one-unit run of the general kernel
+// lines of the Miller loop of P, recorded once per key (k_miller_record: point arithmetic only)
 int miller_nsteps(const bgn_ctx* c) {
   int n = 0;
   for (int idx = 1; idx < c->pc.naf_len; idx++) {
@@ -493,24 +495,20 @@ int miller_nsteps(const bgn_ctx* c) {
   }
   return n;
 }
-// uses and releases the arena: call before carving a call's buffers
 void ensure_linesP(bgn_ctx* c) {
   if (c->linesP || !c->fixed_lines) return;
   uint32_t* tab = nullptr;
   CK(cudaMalloc(&tab, (size_t)miller_nsteps(c) * 3 * c->L * 4));
   try {
-    arena_reset(c);
-    arena_reserve(c, gt_bytes(c, 1) + miller_scratch(c, 1, 1) + 8192);
-    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
-    GtArr e = gt_alloc(c, 1);
-    run_miller(c, Pv, 1, Pv, 1, 0, 1, 1, e, tab);
+    Timer t(c, "k_miller_record");
+    c->Co->miller_record(cfg(c, 1, 32, 0), c->dPx, c->dPy, tab);
+    t.done();
     finish(c);
   } catch (...) {
     cudaFree(tab);
     throw;
   }
   c->linesP = tab;
-  arena_reset(c);
 }
 // out[i] = e(E[i], P) through the line table
 void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out) {
@@ -520,10 +518,10 @@ void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out
   // one block per SM up to 256 threads; smaller batches use whole scheduler rounds (128 threads)
   size_t per_sm = (count + sms - 1) / sms;
   int nt = (int)std::min<size_t>(256, std::max<size_t>(128, (per_sm + 127) / 128 * 128));
-  size_t smem = c->A->miller_fixed_smem_bytes(nt);
+  size_t smem = c->Co->miller_fixed_smem_bytes(nt);
   while (smem > 227 * 1024 - 64 && nt > 32) {
     nt -= 32;
-    smem = c->A->miller_fixed_smem_bytes(nt);
+    smem = c->Co->miller_fixed_smem_bytes(nt);
   }
   MillerFixedArgs a;
   a.lines = c->linesP;
@@ -534,8 +532,8 @@ void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out
   a.out_im = out.im;
   a.count = (int)count;
   Timer t(c, "k_miller_fixed");
-  CK(c->A->miller_fixed_set_smem(smem));
-  c->A->miller_fixed(cfg(c, nblk(count, nt), nt, smem), a);
+  CK(c->Co->miller_fixed_set_smem(smem));
+  c->Co->miller_fixed(cfg(c, nblk(count, nt), nt, smem), a);
   t.done();
 }
 
@@ -627,12 +625,12 @@ void ensure_tabE(bgn_ctx* c) {
   try {
     {
       Timer t(c, "k_gt_tab_bases");
-      c->A->gt_tab_bases(cfg(c, 1, 32, 0), gen, nwin, bases);
+      c->Co->gt_tab_bases(cfg(c, 1, 32, 0), gen, nwin, bases);
       t.done();
     }
     {
       Timer t(c, "k_gt_tab_fill");
-      c->A->gt_tab_fill(cfg(c, nblk(nwin, 32), 32, 0), bases, nwin, tab);
+      c->Co->gt_tab_fill(cfg(c, nblk(nwin, 32), 32, 0), bases, nwin, tab);
       t.done();
     }
     finish(c);
@@ -715,6 +713,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
   case n:                    \
     c->A = bgn_opsA_##n();   \
     c->Bo = bgn_opsB_##n();  \
+    c->Co = bgn_opsC_##n();  \
     break;
 #ifdef BGN_HAVE_L3
       BGN_PICK(3)
@@ -735,7 +734,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
       default:
         break;
     }
-    if (!c->A || !c->Bo) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
+    if (!c->A || !c->Bo || !c->Co) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
     c->B = (pbits + 7) / 8;
     Big p(p0.begin(), p0.begin() + L);
     Big n = big_from_be(prm->n_be, prm->n_len, BGN_MAXL);
@@ -1269,7 +1268,7 @@ int bgn_gt_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t
     ba.count = count;
     {
       Timer t(c, "k_gt_blind");
-      c->A->gt_blind(cfg(c, nblk(count, 128), 128, 0), ba);
+      c->Co->gt_blind(cfg(c, nblk(count, 128), 128, 0), ba);
       t.done();
     }
     gt_to_bytes(c, R, count, ob.dev);
@@ -1311,7 +1310,7 @@ static void polyconv(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const u
     pa.Y = R.im;
     {
       Timer t(c, "k_gt_polyconv");
-      c->A->gt_polyconv(cfg(c, nblk(nout, 128), 128, 0), pa);
+      c->Co->gt_polyconv(cfg(c, nblk(nout, 128), 128, 0), pa);
       t.done();
     }
     gt_to_bytes(c, R, nout, ob.dev);
@@ -1524,7 +1523,7 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
       da.out = reinterpret_cast<int64_t*>(oo.dev);
       da.status = os.dev;
       Timer t(c, "k_dec_lucas");
-      c->A->dec_lucas(cfg(c, nblk(2 * count, 64), 64, 0), da);
+      c->Co->dec_lucas(cfg(c, nblk(2 * count, 64), 64, 0), da);
       t.done();
       commit_out(c, oo);
       commit_out(c, os);

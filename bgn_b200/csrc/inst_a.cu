@@ -36,20 +36,6 @@ void fp2_to_bytes(LaunchCfg cfg, const uint32_t* re, const uint32_t* im, size_t 
                   int grp, int pad) {
   k_fp2_to_bytes<LL><<<CFG>>>(re, im, N, count, out, B, grp, pad);
 }
-void gt_blind(LaunchCfg cfg, const GtBlindArgs& a) { k_gt_blind<LL><<<CFG>>>(a); }
-void gt_tab_bases(LaunchCfg cfg, const uint32_t* gen, int nwin, uint32_t* bases) {
-  k_gt_tab_bases<LL><<<CFG>>>(gen, nwin, bases);
-}
-void gt_tab_fill(LaunchCfg cfg, const uint32_t* bases, int nwin, uint32_t* tab) {
-  k_gt_tab_fill<LL><<<CFG>>>(bases, nwin, tab);
-}
-void gt_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_gt_polyconv<LL><<<CFG>>>(a); }
-void dec_lucas(LaunchCfg cfg, const DecLucasArgs& a) { k_dec_lucas<LL><<<CFG>>>(a); }
-cudaError_t miller_fixed_set_smem(size_t smem) {
-  return cudaFuncSetAttribute(k_miller_fixed<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-size_t miller_fixed_smem_bytes(int nt) { return MillerFixed<LL>::smem_words(nt) * 4; }
-void miller_fixed(LaunchCfg cfg, const MillerFixedArgs& a) { k_miller_fixed<LL><<<CFG>>>(a); }
 void bsgs_build(LaunchCfg cfg, const BsgsBuildArgs& a) { k_bsgs_build<LL><<<CFG>>>(a); }
 void bsgs_lookup(LaunchCfg cfg, const BsgsLookupArgs& a) { k_bsgs_lookup<LL><<<CFG>>>(a); }
 void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
@@ -64,9 +50,7 @@ void mulmod_bench(LaunchCfg cfg, int ilp, uint32_t* io, size_t N, int iters) {
 }
 const LOpsA ops = {LL,        upload,         miller_set_smem, miller_smem_bytes, miller_priv_bytes, miller_fixed_threads,
                    miller,     gt_mul,      gt_pow,
-                   gt_reduce, fp2_from_bytes, fp2_to_bytes,    bsgs_build, bsgs_lookup, mulmod_bench,
-                   gt_blind,  gt_tab_bases,   gt_tab_fill,     gt_polyconv, dec_lucas,
-                   miller_fixed_set_smem, miller_fixed_smem_bytes, miller_fixed};
+                   gt_reduce, fp2_from_bytes, fp2_to_bytes,    bsgs_build, bsgs_lookup, mulmod_bench};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

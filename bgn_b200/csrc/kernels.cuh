@@ -755,12 +755,7 @@ __global__ void __launch_bounds__(256, 1) k_miller(const __grid_constant__ Mille
     while (clock64() - t0 < a.skew_cycles) {
     }
   }
-  // teams of one thread (plain pairings) exchange nothing between threads: no barrier, so the warps
-  // of a scheduler drift apart and overlap each other's glue
-  const bool need_sync = a.dE > 1;
-  T.run([=] {
-    if (need_sync) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
-  });
+  T.run([=] { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory"); });
 }
 
 // fixed-first-argument pairing: one thread per evaluation point, no barriers
@@ -768,6 +763,11 @@ template <int L>
 __global__ void __launch_bounds__(256, 1) k_miller_fixed(const __grid_constant__ MillerFixedArgs a) {
   extern __shared__ uint32_t smem_dyn[];
   MillerFixed<L>::run(a, smem_dyn, threadIdx.x, blockDim.x, BGN_GID(size_t));
+}
+
+template <int L>
+__global__ void __launch_bounds__(32) k_miller_record(const uint32_t* px, const uint32_t* py, uint32_t* lines) {
+  if (BGN_GID(size_t) == 0) MillerFixed<L>::record(px, py, lines);
 }
 
 // Register-resident Montgomery products: `iters` dependent modmuls per thread on

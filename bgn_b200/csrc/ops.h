@@ -31,6 +31,14 @@ struct LOpsA {
   void (*bsgs_build)(LaunchCfg, const BsgsBuildArgs&);
   void (*bsgs_lookup)(LaunchCfg, const BsgsLookupArgs&);
   void (*mulmod_bench)(LaunchCfg, int ilp, uint32_t* io, size_t N, int iters);
+};
+
+// inst_c.cu: the kernels added after the headline path (re-randomisation, polynomial helpers,
+// Lucas decrypt, fixed-argument pairing).  Their own translation unit keeps the register allocation
+// of k_miller in inst_a.cu independent of them (measured: sharing a unit cost k_miller 1.5 %).
+struct LOpsC {
+  int L;
+  cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
   void (*gt_blind)(LaunchCfg, const GtBlindArgs&);
   void (*gt_tab_bases)(LaunchCfg, const uint32_t* gen, int nwin, uint32_t* bases);
   void (*gt_tab_fill)(LaunchCfg, const uint32_t* bases, int nwin, uint32_t* tab);
@@ -39,6 +47,7 @@ struct LOpsA {
   cudaError_t (*miller_fixed_set_smem)(size_t smem);
   size_t (*miller_fixed_smem_bytes)(int nt);
   void (*miller_fixed)(LaunchCfg, const MillerFixedArgs&);
+  void (*miller_record)(LaunchCfg, const uint32_t* px, const uint32_t* py, uint32_t* lines);
 };
 
 struct LOpsB {
@@ -62,7 +71,8 @@ struct LOpsB {
 
 #define BGN_DECL_OPS(L)               \
   extern "C" const LOpsA* bgn_opsA_##L(); \
-  extern "C" const LOpsB* bgn_opsB_##L();
+  extern "C" const LOpsB* bgn_opsB_##L(); \
+  extern "C" const LOpsC* bgn_opsC_##L();
 BGN_DECL_OPS(3)
 BGN_DECL_OPS(5)
 BGN_DECL_OPS(9)

@@ -118,7 +118,6 @@ struct MillerTeam {
   int nt, tid, bid;
   int t, team, unit, group;
   bool active;
-  int step = 0;  // index of the current line (one per phase A / phase B round)
 
   // A block is `groups` barrier groups of a.group_threads threads; each group holds whole teams and
   // synchronises on its own named barrier, so the groups drift independently: while the warps of one
@@ -216,18 +215,11 @@ struct MillerTeam {
         MA::madd_line(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), (a.Mx + (size_t)(idx) * L), (a.My + (size_t)(idx) * L),
                      op == MOP_SUB, slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI));
       }
-      if (a.lines_out && unit == 0 && t == 0) {  // record mode: the fixed point's line table
-        uint32_t* dst = a.lines_out + (size_t)step * 3 * L;
-        s_out(dst, slot(tid, S_CR));
-        s_out(dst + L, slot(tid, S_AR));
-        s_out(dst + 2 * L, slot(tid, S_BI));
-      }
     }
   }
 
   // phase B: fold line_i(B_k) into the slot i+k for every Miller point i; this thread owns slots t and t+TS
   BGN_DEV void phaseB() {
-    step++;
     if (!active) return;
     int TS = a.dE;
     int base = tid - t;  // first thread of the team
@@ -340,6 +332,32 @@ struct MillerFixed {
       if (pc.naf[idx] != 0 && idx != pc.naf_len - 1) n++;
     }
     return n;
+  }
+
+  // The line table of the affine point (px, py): the Miller loop's point arithmetic alone, one
+  // thread, [step][cR, aR, bI][L] (same step order as MillerTeam::run).
+  BGN_DEV static void record(const uint32_t* px, const uint32_t* py, uint32_t* lines) {
+    typedef F<L> FF;
+    Loc<L> X, Y, Z, cR, aR, bI;
+    FF::copy(X.v(), px);
+    FF::copy(Y.v(), py);
+    FF::copy(Z.v(), c_fc.one);
+    const int n = c_pc.naf_len;
+    auto emit = [&]() {
+      FF::copy(lines, cR.v());
+      FF::copy(lines + L, aR.v());
+      FF::copy(lines + 2 * L, bI.v());
+      lines += 3 * L;
+    };
+    for (int idx = 1; idx < n; idx++) {
+      MA::dbl_line(X.v(), Y.v(), Z.v(), cR.v(), aR.v(), bI.v());
+      emit();
+      int d = c_pc.naf[idx];
+      if (d != 0 && idx != n - 1) {
+        MA::madd_line(X.v(), Y.v(), Z.v(), px, py, d < 0, cR.v(), aR.v(), bI.v());
+        emit();
+      }
+    }
   }
 
   BGN_DEV static void run(const MillerFixedArgs& a, uint32_t* smem, int tid, int nt, size_t e) {

@@ -47,13 +47,11 @@ struct MillerArgs {
   int teams_per_group;  // whole teams in one barrier group
   int group_threads;    // threads per barrier group (128 on the GPU); blockDim = groups * group_threads
   int skew_cycles;      // start-up delay of odd groups (decorrelates the two warps of a scheduler)
-  uint32_t* lines_out;  // record mode (else null): unit 0 / Miller point 0 stores the line of every step,
-                        // [step][cR, aR, bI][L] -- the table MillerFixedArgs::lines replays
 };
 
 // Pairing with a FIXED first argument (makeL2: e(C, P) = e(P, C), bgn.go:316-321; level-1 decrypt;
 // MakePolyL2): the Miller point's multiples and therefore the line coefficients of every step do
-// not depend on the batch, so they are computed once per key (record mode above) and a thread only
+// not depend on the batch, so they are computed once per key (MillerFixed::record) and a thread only
 // squares its accumulator and folds in the line evaluated at its own point: 2 + 5 products per
 // step instead of 12..13 + 2 + 5, no inter-thread traffic, no barriers.
 struct MillerFixedArgs {

@@ -145,6 +145,9 @@ int hs_miller_fixed(int L, const MillerFixedArgs* a, int nt) {
     for (int e = 0; e < a->count; e++) MillerFixed<LL>::run(*a, smem.data(), e % nt, nt, (size_t)e);
   })
 }
+int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* lines) {
+  FOR_L(L, MillerFixed<LL>::record(px, py, lines))
+}
 int hs_miller_nsteps(int L) { FOR_L(L, return MillerFixed<LL>::nsteps(c_pc)) }
 int hs_dec_lucas(int L, const DecLucasArgs* a) {
   FOR_L(L, for (size_t e = 0; e < a->count; e++) dec_lucas_pair_sim<LL>(*a, e))

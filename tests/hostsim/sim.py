@@ -35,8 +35,7 @@ class MillerArgs(C.Structure):
     _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
                 ("priv", u32p), ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
                 ("e_bcast", C.c_int), ("dM", C.c_int), ("dE", C.c_int), ("out_slots", C.c_int), ("count", C.c_int),
-                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int),
-                ("lines_out", u32p)]
+                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int)]
 
 
 class MillerFixedArgs(C.Structure):
@@ -237,7 +236,7 @@ class Sim:
         return x, y, inf
 
     # ---- kernels
-    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2, lines_out=None):
+    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2):
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
         nout = count * out_slots
@@ -245,8 +244,7 @@ class Sim:
         oim = np.zeros((nout, self.L), dtype=np.uint32)
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
-                       teams_per_block * dE + 1, 0,  # one idle thread per group: exercises the inactive path
-                       None if lines_out is None else P32(lines_out))
+                       teams_per_block * dE + 1, 0)  # one idle thread per group: exercises the inactive path
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
         nblocks = (count + groups * teams_per_block - 1) // (groups * teams_per_block)
@@ -254,11 +252,13 @@ class Sim:
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
 
     def record_lines(self, base):
-        """api.cu: ensure_linesP -- one-unit run of the general kernel in record mode"""
+        """api.cu: ensure_linesP -- k_miller_record"""
+        nsteps = lib().hs_miller_nsteps(self.L)
         ns = naf_digits(self.par.n)
-        nsteps = sum(1 + (1 if (ns[i] != 0 and i != len(ns) - 1) else 0) for i in range(1, len(ns)))
+        assert nsteps == sum(1 + (1 if (ns[i] != 0 and i != len(ns) - 1) else 0) for i in range(1, len(ns)))
         lines = np.zeros(nsteps * 3 * self.L, dtype=np.uint32)
-        self.miller([base], 1, [base], 1, 1, 1, teams_per_block=1, lines_out=lines)
+        bx, by = self.soa([base[0]]), self.soa([base[1]])
+        assert lib().hs_miller_record(self.L, P32(bx), P32(by), P32(lines)) == 0
         return lines
 
     def pair_fixed(self, lines, Epts, nt=4):
