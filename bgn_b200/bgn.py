@@ -23,6 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import gobwire
 from .engine import Engine
 from .plaintext import (EncodingTable, NewPolyPlaintext, NewUnbalancedPlaintext, PolyEncodingParams, PolyPlaintext)
 
@@ -40,7 +41,8 @@ class Ciphertext:  # ciphertext.go:12-15
         return Ciphertext(self.C, self.L2)
 
     def Bytes(self) -> bytes:
-        return bytes(self.C)
+        """ciphertext.go:76-91: the gob envelope of ciphertextWrapper{CBytes, L2}."""
+        return gobwire.encode_ciphertext(self.C, self.L2)
 
 
 @dataclass
@@ -53,8 +55,13 @@ class PolyCiphertext:  # ciphertext.go:26-31
     def Copy(self) -> "PolyCiphertext":
         return PolyCiphertext(self.Coefficients, self.Degree, self.ScaleFactor, self.L2)
 
-    def Bytes(self) -> bytes:
+    def CoeffBytes(self) -> bytes:
+        """the coefficients' element bytes back to back: the layout of a PolyCiphertextBatch row"""
         return b"".join(c.C for c in self.Coefficients)
+
+    def Bytes(self) -> bytes:
+        """ciphertext.go:93-116: the gob envelope of polyCiphertextWrapper."""
+        return gobwire.encode_poly_ciphertext([c.C for c in self.Coefficients], self.Degree, self.ScaleFactor, self.L2)
 
 
 @dataclass
@@ -163,6 +170,35 @@ class PublicKey:
             return rs  # already a packed buffer
         assert len(rs) == count
         return self.engine.scalars_be([int(r) % self.N for r in rs])
+
+    # ---------------------------------------------------------------- wire formats
+    def _canonical(self, raw: bytes, L2: bool) -> bytes:
+        """Element.SetBytes semantics (coordinates reduced mod p; a G1 pair off the curve becomes O)
+        obtained from the device's own parser: x -> O + x  /  1 * x."""
+        eb = self.elem_bytes
+        if len(raw) % eb:
+            raise ValueError("element bytes have the wrong length for this key")
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        if L2:
+            one = (b"\x00" * (eb // 2 - 1) + b"\x01" + b"\x00" * (eb // 2)) * (len(raw) // eb)
+            return self.engine.gt_mul_batch(np.frombuffer(one, dtype=np.uint8), buf).tobytes()
+        return self.engine.g1_add_batch(np.zeros(len(raw), dtype=np.uint8), buf).tobytes()
+
+    def NewCiphertextFromBytes(self, data: bytes) -> Ciphertext:
+        """bgn.go:505-528 -- without the pairing e(Q,Q) the reference evaluates per call (bgn.go:517)."""
+        if len(data) == 0:
+            raise ValueError("no data provided")
+        C, L2 = gobwire.decode_ciphertext(data)
+        return Ciphertext(self._canonical(C, L2), L2)
+
+    def NewPolyCiphertextFromBytes(self, data: bytes) -> PolyCiphertext:
+        """bgn.go:530-555; one device call for all coefficients."""
+        if len(data) == 0:
+            raise ValueError("no data provided")
+        coeffs, degree, sf, L2 = gobwire.decode_poly_ciphertext(data)
+        raw = self._canonical(b"".join(coeffs), L2) if coeffs else b""
+        eb = self.elem_bytes
+        return PolyCiphertext([Ciphertext(raw[i * eb:(i + 1) * eb], L2) for i in range(len(coeffs))], degree, sf, L2)
 
     # ---------------------------------------------------------------- plaintexts
     def NewPolyPlaintext(self, m: float) -> PolyPlaintext:

@@ -156,3 +156,52 @@ func (pk *PublicKey) PolyCiphertextFromBatch(buf []byte, elem int, degree, scale
 	}
 	return &PolyCiphertext{coeffs, degree, scaleFactor, l2}
 }
+
+// ---- non-deterministic mode (Deterministic == false) --------------------------------------------
+// Blind re-randomises a batch of coefficients the way every homomorphic operation of the reference
+// does when !pk.Deterministic: `+ r*Q` on level 1 (bgn.go:264-268, 491-495), `* e(Q,Q)^r` on level 2
+// (bgn.go:283-287, 306-310, 469-474).  r: count big-endian scalars of ScalarSize bytes drawn by the
+// caller with newCryptoRandom(pk.N) (bgn.go:567-574).  e(Q,Q) is a per-context table, not a pairing
+// per call.
+func (e *Engine) Blind(cts []byte, r []byte, l2 bool) ([]byte, error) {
+	out := make([]byte, len(cts))
+	n := C.size_t(len(cts) / e.ElemBytes)
+	var st C.int
+	if l2 {
+		st = C.bgn_gt_blind_batch(e.ctx, ptr(cts), ptr(r), n, ptr(out))
+	} else {
+		st = C.bgn_g1_blind_batch(e.ctx, ptr(cts), ptr(r), n, ptr(out))
+	}
+	return out, statusErr(e, st)
+}
+
+// MultConstPolyBatch replaces MultConstPoly (poly.go:71-120) for `count` polynomials of `degree` slots:
+// digits are the coefficients of pk.NewUnbalancedPlaintext(|constant|) (poly.go:78-80), negate is
+// constant < 0 (poly.go:116-118).  The result has degree+len(digits) slots per polynomial.
+func (e *Engine) MultConstPolyBatch(cts []byte, degree int, l2 bool, digits []byte, negate bool, count int) ([]byte, error) {
+	out := make([]byte, count*(degree+len(digits))*e.ElemBytes)
+	st := C.bgn_multconstpoly_batch(e.ctx, ptr(cts), C.size_t(degree), cbool(l2), ptr(digits), C.size_t(len(digits)),
+		cbool(negate), C.size_t(count), ptr(out))
+	return out, statusErr(e, st)
+}
+
+// EvalPolyBatch replaces EvalPoly (poly.go:58-68): one element per polynomial.
+func (e *Engine) EvalPolyBatch(cts []byte, degree int, l2 bool, polyBase int, count int) ([]byte, error) {
+	out := make([]byte, count*e.ElemBytes)
+	st := C.bgn_evalpoly_batch(e.ctx, ptr(cts), C.size_t(degree), cbool(l2), C.uint32_t(polyBase), C.size_t(count), ptr(out))
+	return out, statusErr(e, st)
+}
+
+// MakePolyL2Batch replaces MakePolyL2 (poly.go:159-163) in deterministic mode: degree+1 slots per polynomial.
+func (e *Engine) MakePolyL2Batch(cts []byte, degree int, count int) ([]byte, error) {
+	out := make([]byte, count*(degree+1)*e.ElemBytes)
+	st := C.bgn_make_poly_l2_batch(e.ctx, ptr(cts), C.size_t(degree), C.size_t(count), ptr(out))
+	return out, statusErr(e, st)
+}
+
+func cbool(b bool) C.int {
+	if b {
+		return 1
+	}
+	return 0
+}

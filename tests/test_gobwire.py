@@ -1,0 +1,67 @@
+"""encoding/gob envelopes (bgn_b200/gobwire.py) -- pinned by the worked example of the gob
+documentation; the bgn wrappers round-trip and survive foreign type ids and field orders."""
+import pytest
+
+from bgn_b200 import gobwire as G
+
+# "struct { A, B int }" named Point, value {22, 33}: the byte stream of the encoding/gob package documentation
+DOC_EXAMPLE = bytes.fromhex(
+    "1fff810301010550 6f696e7401ff8200 0102010158010400 0101590104000000 07ff82012c014200".replace(" ", ""))
+
+
+def test_doc_example_encodes_byte_exact():
+    assert G.encode_struct("Point", [("X", "int", 22), ("Y", "int", 33)]) == DOC_EXAMPLE
+
+
+def test_doc_example_decodes():
+    assert G.decode_stream(DOC_EXAMPLE) == [("Point", {"X": 22, "Y": 33})]
+
+
+def test_uint_and_int_forms():
+    assert G.enc_uint(0) == b"\x00" and G.enc_uint(127) == b"\x7f"
+    assert G.enc_uint(256) == b"\xfe\x01\x00"  # documented example
+    assert G.enc_int(-65) == b"\xff\x81" and G.enc_int(65) == b"\xff\x82"
+    for v in (0, 1, -1, 63, 64, -64, -65, 1 << 40, -(1 << 40), (1 << 62), -(1 << 62)):
+        assert G.Reader(G.enc_int(v)).int() == v
+    for v in (0, 127, 128, 255, 256, 1 << 32, (1 << 64) - 1):
+        assert G.Reader(G.enc_uint(v)).uint() == v
+
+
+def test_ciphertext_roundtrip_and_zero_fields():
+    c = bytes(range(1, 35))
+    for l2 in (False, True):
+        env = G.encode_ciphertext(c, l2)
+        assert G.decode_ciphertext(env) == (c, l2)
+    # the false flag is a zero value and is not transmitted: the value message is id, field 0, end
+    env = G.encode_ciphertext(c, False)
+    assert env.endswith(G.enc_uint(2 + 1 + 1 + len(c) + 1) + b"\xff\x82" + b"\x01" + G.enc_uint(len(c)) + c + b"\x00")
+    assert G.decode_ciphertext(G.encode_ciphertext(b"", False)) == (b"", False)
+
+
+def test_poly_ciphertext_roundtrip():
+    coeffs = [bytes([i]) * 130 for i in range(1, 12)]
+    for deg, sf, l2 in ((11, 0, False), (11, 3, True), (0, 0, False)):
+        cs = coeffs[:deg] if deg else []
+        assert G.decode_poly_ciphertext(G.encode_poly_ciphertext(cs, deg, sf, l2)) == (cs, deg, sf, l2)
+    env = G.encode_poly_ciphertext(coeffs, 11, 2, True)
+    names = [n for n, _ in G.decode_stream(env)]
+    assert names == ["polyCiphertextWrapper"]
+
+
+def test_decoder_accepts_foreign_ids_and_field_order():
+    """Go assigns type ids per process and matches fields by name: a stream whose struct is id 70,
+    whose slice is id 71 and whose fields come in another order must decode the same."""
+    types = {70: G.StructT("polyCiphertextWrapper", [("L2", G.T_BOOL), ("ScaleFactor", G.T_INT),
+                                                      ("CoeffBytes", 71), ("Degree", G.T_INT)]),
+             71: G.SliceT("[][]uint8", G.T_BYTES)}
+    val = {"L2": True, "ScaleFactor": 4, "CoeffBytes": [b"ab", b"cd"], "Degree": 2}
+    stream = b"".join(G._message(G.enc_int(-t) + G._enc_wiretype(t, types[t])) for t in (70, 71))
+    stream += G._message(G.enc_int(70) + G._enc_value(70, val, types))
+    assert G.decode_poly_ciphertext(stream) == ([b"ab", b"cd"], 2, 4, True)
+
+
+def test_malformed_streams_raise():
+    env = G.encode_ciphertext(b"abc", True)
+    for bad in (env[:-3], env[:5], b"\x03\xff\x82\x00"):
+        with pytest.raises((G.GobError, KeyError)):
+            G.decode_ciphertext(bad)

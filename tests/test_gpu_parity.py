@@ -371,6 +371,35 @@ def test_mirror_api_nondeterministic():
     assert sk.Decrypt(pk.Sub(p1, pk.makeL2(a)), pk) == 3
 
 
+def test_mirror_wire_roundtrip():
+    """bgn_test.go:37-85 (TestMarshalUnmarshal*): ciphertext -> gob envelope -> ciphertext keeps the
+    element, level, Degree and ScaleFactor, on both levels; malformed element bytes follow
+    Element.SetBytes (off-curve -> O)."""
+    from bgn_b200 import PublicKey, SecretKey
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    c = pk.Encrypt(9)
+    c2 = pk.NewCiphertextFromBytes(c.Bytes())
+    assert (c2.C, c2.L2) == (c.C, False) and sk.Decrypt(c2, pk) == 9
+    m = pk.Mult(c, c)
+    m2 = pk.NewCiphertextFromBytes(m.Bytes())
+    assert (m2.C, m2.L2) == (m.C, True) and sk.Decrypt(m2, pk) == 81
+    pc = pk.EncryptPoly(pk.NewPolyPlaintext(9.123))
+    for poly in (pc, pk.MakePolyL2(pc)):
+        back = pk.NewPolyCiphertextFromBytes(poly.Bytes())
+        assert back.CoeffBytes() == poly.CoeffBytes()
+        assert (back.Degree, back.ScaleFactor, back.L2) == (poly.Degree, poly.ScaleFactor, poly.L2)
+    bad = bytearray(c.C)
+    bad[-1] ^= 1
+    from bgn_b200 import gobwire
+    o = pk.NewCiphertextFromBytes(gobwire.encode_ciphertext(bytes(bad), False))
+    assert o.C == bytes(pk.elem_bytes)
+    with pytest.raises(ValueError):
+        pk.NewCiphertextFromBytes(b"")
+
+
 def test_batch_poly_helpers_match_mirror():
     """MultConstPolyBatch / EvalPolyBatch / MakePolyL2Batch (one kernel launch per batch) give the
     same bytes as the per-polynomial mirror methods composed from the scalar C-ABI primitives."""
@@ -391,15 +420,15 @@ def test_batch_poly_helpers_match_mirror():
     for p, row in zip(pts, rs):
         pp = type(p)(p.Coefficients[: p.Degree] + [0] * (d - p.Degree), d, p.ScaleFactor, p.params)
         singles.append(pk.EncryptPoly(pp, rs=row))
-    assert batch.data.tobytes() == b"".join(s.Bytes() for s in singles)
+    assert batch.data.tobytes() == b"".join(s.CoeffBytes() for s in singles)
     for lvl2 in (False, True):
         bb = pk.MakePolyL2Batch(batch) if lvl2 else batch
         ss = [pk.MakePolyL2(s) for s in singles] if lvl2 else singles
-        assert bb.data.tobytes() == b"".join(s.Bytes() for s in ss)
+        assert bb.data.tobytes() == b"".join(s.CoeffBytes() for s in ss)
         for constant in (4.12, -3.0):
             got = pk.MultConstPolyBatch(bb, constant)
             exp = [pk.MultConstPoly(s, constant) for s in ss]
-            assert got.Degree == exp[0].Degree and got.data.tobytes() == b"".join(x.Bytes() for x in exp)
+            assert got.Degree == exp[0].Degree and got.data.tobytes() == b"".join(x.CoeffBytes() for x in exp)
         ev = pk.EvalPolyBatch(bb)
         assert ev.tobytes() == b"".join(pk.EvalPoly(s).C for s in ss)
     # decrypt the evaluated polynomials: EvalPoly recovers the encoded integer
