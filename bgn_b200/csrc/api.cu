@@ -124,6 +124,8 @@ struct bgn_ctx {
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
   int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
+  int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
+  int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
   bool has_secret = false;
@@ -373,7 +375,12 @@ void normalize(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, uin
   a.scratch = scratch;
   a.count = count;
   a.N = j.N;
-  size_t G = (count + 63) / 64;
+  // elements per thread (= per inversion): the binary-GCD inversion costs about as much as 85
+  // products and each element 6, so ~10 elements per thread already amortise it; fewer elements
+  // per thread mean more threads, which is what a latency-bound chain needs.  Aim at two warps per
+  // scheduler (148 x 256 threads), between 8 and 64 elements per thread.
+  size_t per = std::min<size_t>(64, std::max<size_t>(c->norm_per_thread, (count + c->norm_threads - 1) / c->norm_threads));
+  size_t G = (count + per - 1) / per;
   if (G < 4096) G = std::min<size_t>(count, 4096);  // small batches: favour parallelism over shared inversions
   a.G = (int)G;
   a.ox = ox;
@@ -696,6 +703,8 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
     if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : 16;
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
+    if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
+    if (const char* nt = getenv("BGN_NORM_THREADS")) c->norm_threads = std::max(128, atoi(nt));
     if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);

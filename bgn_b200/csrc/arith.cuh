@@ -707,6 +707,84 @@ struct Fp {
     r[L - 1] = t[L - 1] >> 1;
   }
 
+  // r = x^-1 mod p as plain integers, x canonical in [0, p); 0 -> 0.  Constant-time binary extended
+  // GCD on the ALU pipe (adds, selects, shifts -- no multiplications): with a = u x, b = v x (mod p),
+  // b odd, every iteration halves a (after a <- |a - b| when a is odd), so the product a b at least
+  // halves and 2 bits(p) iterations reach a = 0, b = 1, v = x^-1.  About 12 L plain-ALU
+  // instructions per iteration against the ~1.2 bits(p) Montgomery products of the Fermat inversion
+  // (F<L>::inv): a quarter of the issue slots, none of them on the multiply pipe, and a sixth of the
+  // dependent-chain latency, which is what bounds the batched inversion of k_normalize.
+  BGN_DEV static void inv_bgcd(uint32_t (&r)[L], const uint32_t (&x)[L]) {
+#ifdef BGN_HOSTSIM
+    BGN_CHECK(BGN_GETB(x) <= 1.0, "inv_bgcd expects a canonical operand");
+    BGN_SETB(r, 1.0);
+#endif
+    uint32_t a[L], b[L], u[L], v[L];
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) {
+      a[j] = x[j];
+      b[j] = c_fc.p[j];
+      u[j] = 0;
+      v[j] = 0;
+    }
+    u[0] = 1;
+    int top = 32 * L - 1;
+    while (top > 0 && !((c_fc.p[top >> 5] >> (top & 31)) & 1)) top--;
+    const int iters = 2 * (top + 1);
+    BGN_UNROLL1
+    for (int it = 0; it < iters; it++) {
+      const uint32_t odd = 0u - (a[0] & 1u);
+      uint32_t d[L], nd[L], lt;
+      sub_cc(d[0], a[0], b[0]);
+      BGN_UNROLL
+      for (int j = 1; j < L; j++) subc_cc(d[j], a[j], b[j]);
+      subc(lt, 0, 0);  // all-ones when a < b
+      sub_cc(nd[0], 0, d[0]);
+      BGN_UNROLL
+      for (int j = 1; j < L - 1; j++) subc_cc(nd[j], 0, d[j]);
+      subc(nd[L - 1], 0, d[L - 1]);  // b - a
+      const uint32_t sw = odd & lt;
+      BGN_UNROLL
+      for (int j = 0; j < L; j++) {
+        const uint32_t diff = lt ? nd[j] : d[j];
+        const uint32_t aj = a[j];
+        a[j] = odd ? diff : aj;
+        b[j] = sw ? aj : b[j];
+      }
+      BGN_UNROLL
+      for (int j = 0; j < L - 1; j++) a[j] = (a[j] >> 1) | (a[j + 1] << 31);
+      a[L - 1] >>= 1;
+      // the same steps on the cofactors, mod p
+      BGN_UNROLL
+      for (int j = 0; j < L; j++) {
+        const uint32_t uj = u[j];
+        u[j] = sw ? v[j] : uj;
+        v[j] = sw ? uj : v[j];
+      }
+      uint32_t w[L], m;
+      sub_cc(w[0], u[0], v[0]);
+      BGN_UNROLL
+      for (int j = 1; j < L; j++) subc_cc(w[j], u[j], v[j]);
+      subc(m, 0, 0);  // borrow: add p back
+      add_cc(w[0], w[0], c_fc.p[0] & m);
+      BGN_UNROLL
+      for (int j = 1; j < L - 1; j++) addc_cc(w[j], w[j], c_fc.p[j] & m);
+      addc(w[L - 1], w[L - 1], c_fc.p[L - 1] & m);
+      BGN_UNROLL
+      for (int j = 0; j < L; j++) u[j] = odd ? w[j] : u[j];
+      const uint32_t h = 0u - (u[0] & 1u);  // u / 2 mod p: an odd u first gains p (u + p < 2p < R)
+      add_cc(u[0], u[0], c_fc.p[0] & h);
+      BGN_UNROLL
+      for (int j = 1; j < L - 1; j++) addc_cc(u[j], u[j], c_fc.p[j] & h);
+      addc(u[L - 1], u[L - 1], c_fc.p[L - 1] & h);
+      BGN_UNROLL
+      for (int j = 0; j < L - 1; j++) u[j] = (u[j] >> 1) | (u[j + 1] << 31);
+      u[L - 1] >>= 1;
+    }
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) r[j] = v[j];
+  }
+
   BGN_DEV static bool is_zero_raw(const uint32_t (&a)[L]) {
     uint32_t o = 0;
     BGN_UNROLL

@@ -192,6 +192,20 @@ struct F {
     }
   }
 
+  // r = a^-1 (Montgomery in, Montgomery out; 0 -> 0) through the binary GCD of arith.cuh:
+  // inv(a R) = a^-1 R^-1 as an integer, times R^3 (= r2 * r2 / R) in a Montgomery product = a^-1 R.
+  // r may alias a.  in: a < 2p.  out: r < 2p.
+  BGN_DEVNI static void inv_gcd(E r, const uint32_t* a) {
+    uint32_t x[L], y[L], r2[L], r3[L];
+    ld<L>(x, a);
+    P::canon(x, x);
+    P::inv_bgcd(y, x);
+    ld<L>(r2, c_fc.r2);
+    P::mul(r3, r2, r2);
+    P::mul(x, y, r3);
+    st<L>(r, x);
+  }
+
   // ---------------- F_p^2 = F_p[i]/(i^2+1), three-address code ----------------
   // r = a*b (Karatsuba, 3 products).  r may alias a or b; t0..t2 are scratch.
   BGN_DEV static void mul2(E2 r, E2 a, E2 b, E t0, E t1, E t2) {

@@ -211,7 +211,11 @@ BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
     FF::copy(a.scratch + (size_t)(e) * L, acc.v());
     FF::mul(acc.v(), acc.v(), z.v());
   }
+#ifdef BGN_NORMALIZE_FERMAT
   FF::inv(acc.v(), acc.v(), t.v());
+#else
+  FF::inv_gcd(acc.v(), acc.v());
+#endif
   size_t last = ((a.count - 1 - g) / a.G) * a.G + g;  // largest e = g (mod G) below count
   for (size_t e = last;; e -= a.G) {
     FF::copy(z.v(), (a.Z + (size_t)(e) * L));

@@ -176,4 +176,5 @@ uint64_t hs_mul_count(int reset) {
   return v;
 }
 int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(r, a, t.v())) }
+int hs_fp_inv_gcd(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv_gcd(r, a)) }
 }

@@ -370,3 +370,32 @@ def test_sim_pair_fixed(kb):
     if kb < 512:
         pts = g1s(par, g["g1_add"]["out"])
         assert S.pair_fixed(tabs["linesP"], pts, nt=3) == [O.pairing(pt, S.P, par) for pt in pts]
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_inv_gcd(kb):
+    """F<L>::inv_gcd (constant-time binary GCD on plain ALU instructions) equals the Fermat inverse
+    and the integer inverse, incl. 0 -> 0, 1, p - 1 and a value in [p, 2p)."""
+    import ctypes as C
+    import random
+    import numpy as np
+    g, par, S, _ = setup(kb)
+    rng = random.Random(kb + 77)
+    p = par.p
+    vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2] + [rng.randrange(p) for _ in range(12 if kb < 512 else 4)]
+    for v in vals:
+        a = S.soa([v])
+        r1, r2 = np.zeros_like(a), np.zeros_like(a)
+        assert sim.lib().hs_fp_inv_gcd(S.L, sim.P32(r1), sim.P32(a)) == 0
+        assert sim.lib().hs_fp_inv(S.L, sim.P32(r2), sim.P32(a)) == 0
+        exp = pow(v, -1, p) if v else 0
+        assert S.unsoa(r1, 1) == [exp] and S.unsoa(r2, 1) == [exp]
+    # lazy-form input: v + p represents v
+    a = S.soa([5])
+    raw = sum(int(a[0, j]) << (32 * j) for j in range(S.L)) + p
+    for j in range(S.L):
+        a[0, j] = (raw >> (32 * j)) & 0xFFFFFFFF
+    sim.lib().hs_track_array(sim.P32(a), C.c_size_t(1), S.L, C.c_double(2.0))
+    r1 = np.zeros_like(a)
+    assert sim.lib().hs_fp_inv_gcd(S.L, sim.P32(r1), sim.P32(a)) == 0
+    assert S.unsoa(r1, 1) == [pow(5, -1, p)]
