@@ -506,3 +506,93 @@ def test_full_size_properties_emult():
         for j in range(d):
             exp[k + j] += int((a1[:, k] * a2[:, j]).sum())
     assert tv.cpu().numpy().tolist() == exp.tolist()
+
+
+def test_full_size_properties_encrypt_eadd():
+    """BASELINE.json config 2 at FULL size: 2^16 plaintexts x 11 balanced base-3 digits = 720 896
+    coefficient encryptions with r < n, then 2^15 pairwise AddPoly.  Size-independent properties, all
+    bit-exact: (i) E(x1, r1) + E(x2, r2) == E(x1 + x2, r1 + r2 mod n) computed by a second Encrypt;
+    (ii) Sub undoes Add; (iii) re-randomising with r and then with n - r is the identity;
+    (iv) a sample of the sums decrypts to the digit sums."""
+    import torch
+    g = load_golden(512)
+    e = engine_for(g)
+    n = int(g["n"], 16)
+    count, d = 1 << 16, 11
+    dev = "cuda:0"
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2)
+    SB, EB = e.scalar_bytes, e.elem_bytes
+    half = count * d // 2
+    x = torch.randint(-1, 2, (count * d,), generator=gen, device=dev, dtype=torch.int64)
+    # randomness below 2^(8 SB - 2) <= n / 2: r1 + r2 needs no reduction mod n, so it can be formed bytewise
+    r = torch.randint(0, 256, (count * d, SB), generator=gen, device=dev, dtype=torch.uint8)
+    r[:, 0] &= 0x1F
+    c = e.encrypt_batch(x, r.reshape(-1))
+    a, b = c[: half * EB], c[half * EB:]
+    s = e.g1_add_batch(a, b)
+    # (i) homomorphism against a direct encryption of the sums (non-negative digits only: the sign
+    # convention -(|x| P + r Q) makes E(x1) + E(x2) = E(x1 + x2, r1 + r2) hold for x1, x2 >= 0)
+    xa, xb = x[:half].abs(), x[half:].abs()
+    ra = r[:half].to(torch.int32)
+    rb = r[half:].to(torch.int32)
+    acc = ra + rb
+    for col in range(SB - 1, 0, -1):  # propagate byte carries, most significant byte is column 0
+        carry = acc[:, col] >> 8
+        acc[:, col] &= 0xFF
+        acc[:, col - 1] += carry
+    assert int(acc[:, 0].max().item()) < 256
+    pos = e.encrypt_batch(xa, r[:half].reshape(-1))
+    pos2 = e.encrypt_batch(xb, r[half:].reshape(-1))
+    direct = e.encrypt_batch(xa + xb, acc.to(torch.uint8).reshape(-1))
+    assert torch.equal(e.g1_add_batch(pos, pos2), direct)
+    # (ii) Sub undoes Add
+    assert torch.equal(e.g1_sub_batch(s, b), a)
+    # (iii) blind by r, then by n - r
+    m = 1 << 15
+    rr = r[:m]
+    nr = e.scalars_be([n - int.from_bytes(bytes(row), "big") for row in rr.cpu().numpy()])
+    bl = e.g1_blind_batch(s[: m * EB], rr.reshape(-1))
+    assert not torch.equal(bl, s[: m * EB])
+    assert torch.equal(e.g1_blind_batch(bl, torch.from_numpy(nr).to(dev)), s[: m * EB])
+    # (iv) a sample decrypts to the plaintext sums
+    idx = [0, 1, 2, 12345, half - 1]
+    sel = torch.cat([s[i * EB:(i + 1) * EB] for i in idx])
+    vals, st = e.decrypt_batch(sel, False)
+    assert not st.any().item()
+    assert vals.cpu().tolist() == [int(x[i].item() + x[half + i].item()) for i in idx]
+
+
+def test_full_size_decrypt_l2():
+    """BASELINE.json config 4 at FULL size: 2^14 level-2 ciphertexts e(E(a), E(b)) with a b uniform in
+    (-T, T), T = 2^20, half of them negative and 1 % exact zeros; every plaintext is recovered, through
+    the Lucas path and (same inputs) through the generic exponentiation + table search."""
+    import os
+    import torch
+    from bgn_b200 import Engine
+    g = load_golden(512)
+    e = engine_for(g)
+    count = 1 << 14
+    dev = "cuda:0"
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4)
+    av = torch.randint(1, 1 << 10, (count,), generator=gen, device=dev, dtype=torch.int64)
+    bv = torch.randint(-(1 << 10) + 1, 1 << 10, (count,), generator=gen, device=dev, dtype=torch.int64)
+    bv[::100] = 0
+    r = torch.randint(0, 256, (2 * count, e.scalar_bytes), generator=gen, device=dev, dtype=torch.uint8)
+    r[:, 0] &= 0x3F
+    ca = e.encrypt_batch(av, r[:count].reshape(-1))
+    cb = e.encrypt_batch(bv, r[count:].reshape(-1))
+    l2 = e.pair_batch(ca, cb)
+    vals, st = e.decrypt_batch(l2, True)
+    assert not st.any().item() and torch.equal(vals, av * bv)
+    assert int((av * bv < 0).sum().item()) > count // 3
+    os.environ["BGN_DEC_LUCAS"] = "0"
+    try:
+        e2 = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    finally:
+        del os.environ["BGN_DEC_LUCAS"]
+    e2.set_secret(int(g["q1"], 16), g["msg_space"])
+    v2, s2 = e2.decrypt_batch(l2, True)
+    assert torch.equal(v2, vals) and not s2.any().item()
+    e2.close()
