@@ -28,6 +28,7 @@ SIGNATURES = {
     "bgn_ctx_destroy": (None, [C.c_void_p]),
     "bgn_last_error": (C.c_char_p, [C.c_void_p]),
     "bgn_ctx_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgn_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     "bgn_ctx_set_secret": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32]),
     "bgn_encrypt_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),
     "bgn_g1_add_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),

@@ -119,11 +119,12 @@ struct bgn_ctx {
   uint32_t *dPx = nullptr, *dPy = nullptr, *dQx = nullptr, *dQy = nullptr;
   uint8_t *dPinf = nullptr, *dQinf = nullptr;
   uint32_t *tabP = nullptr, *tabQ = nullptr;
-  uint32_t* tabQ16 = nullptr;  // 16-bit windows of Q, built on the first randomised encryption
+  uint32_t* tabQw = nullptr;   // 16- or 24-bit windows of Q, built on the first randomised encryption
+  int tabQw_bits = 0;
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
-  int enc_window = 16;         // 16, or 8 to stay with the small table (BGN_ENC_WINDOW)
+  int enc_window = 16;         // 16; 8 stays with the small table, 24 builds the 50 GB one (BGN_ENC_WINDOW)
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
@@ -572,42 +573,62 @@ void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, u
   finish(c);
 }
 
-// 16-bit window table of Q for Encrypt (half the additions of the 8-bit one): ceil(nbytes/2) x
-// 65535 affine points, 285 MB at 512-bit keys, 1.1 GB at 1024 -- sized for HBM, not for shared
-// memory.  Built once from the 8-bit table with one addition per entry; its temporaries are
-// released again.
-void ensure_tabQ16(bgn_ctx* c) {
-  if (c->tabQ16 || c->enc_window != 16) return;
-  int nw = (c->nbytes + 1) / 2;
-  size_t nent = (size_t)nw * 65535, ew = (size_t)c->L * 4;
+// Wide-window table of Q for Encrypt, sized for HBM rather than shared memory: windows of 16 bits
+// (ceil(nbytes/2) x 65535 affine points: 285 MB at 512-bit keys, 1.1 GB at 1024; half the additions
+// of the 8-bit table) or, on request, of 24 bits (ceil(nbytes/3) x (2^24 - 1) points: 50 GB at 512
+// bit, a third of the additions).  Built once from the 8-bit table, in chunks whose temporaries are
+// released again.  A 24-bit table that does not fit the free memory falls back to 16 bits.
+void ensure_tabQw(bgn_ctx* c) {
+  if (c->tabQw || c->enc_window == 8) return;
+  int wbits = c->enc_window;
+  size_t ew = (size_t)c->L * 4;
+  auto table_bytes = [&](int bits) {
+    int wb = bits / 8;
+    return (size_t)((c->nbytes + wb - 1) / wb) * (((size_t)1 << bits) - 1) * 2 * ew;
+  };
+  const size_t chunk_max = (size_t)1 << 22;
+  if (wbits == 24) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (table_bytes(24) + chunk_max * 4 * ew + ((size_t)16 << 30) > free_b) wbits = 16;
+  }
+  const int wb = wbits / 8;
+  const size_t ents = ((size_t)1 << wbits) - 1;
+  const size_t nent = (size_t)((c->nbytes + wb - 1) / wb) * ents;
+  const size_t chunk = std::min(nent, chunk_max);
   uint32_t *tab = nullptr, *tmp = nullptr;
   CK(cudaMalloc(&tab, nent * 2 * ew));
-  cudaError_t e = cudaMalloc(&tmp, nent * 4 * ew);
+  cudaError_t e = cudaMalloc(&tmp, chunk * 4 * ew);
   if (e != cudaSuccess) {
     cudaFree(tab);
     CK(e);
   }
   JacArr j;
   j.X = tmp;
-  j.Y = tmp + nent * c->L;
-  j.Z = tmp + 2 * nent * c->L;
-  j.N = nent;
-  uint32_t* scratch = tmp + 3 * nent * c->L;
+  j.Y = tmp + chunk * c->L;
+  j.Z = tmp + 2 * chunk * c->L;
+  j.N = chunk;
+  uint32_t* scratch = tmp + 3 * chunk * c->L;
   try {
-    {
-      Timer t(c, "k_tab16_fill");
-      c->Bo->tab16_fill(cfg(c, nblk(nent, 128), 128, 0), c->tabQ, c->nbytes, j.X, j.Y, j.Z, nent);
-      t.done();
+    for (size_t first = 0; first < nent; first += chunk) {
+      size_t cnt = std::min(chunk, nent - first);
+      {
+        Timer t(c, "k_tabw_fill");
+        c->Bo->tabw_fill(cfg(c, nblk(cnt, 128), 128, 0), c->tabQ, c->nbytes, wb, j.X, j.Y, j.Z, first, cnt);
+        t.done();
+      }
+      uint32_t* dst = tab + first * 2 * c->L;
+      normalize(c, j, cnt, scratch, dst, dst + c->L, 2 * (size_t)c->L, 1, nullptr);
     }
-    normalize(c, j, nent, scratch, tab, tab + c->L, 2 * (size_t)c->L, 1, nullptr);
-    CK(cudaStreamSynchronize(c->stream));
+    finish(c);
   } catch (...) {
     cudaFree(tab);
     cudaFree(tmp);
     throw;
   }
   CK(cudaFree(tmp));
-  c->tabQ16 = tab;
+  c->tabQw = tab;
+  c->tabQw_bits = wbits;
 }
 
 // Fixed-base table of E = e(Q,Q) for the level-2 re-randomisation `* e(Q,Q)^r` (bgn.go:283-287,
@@ -701,7 +722,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->device = device;
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
-    if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : 16;
+    if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : (atoi(ew) == 24 ? 24 : 16);
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
     if (const char* nt = getenv("BGN_NORM_THREADS")) c->norm_threads = std::max(128, atoi(nt));
@@ -862,7 +883,7 @@ void bgn_ctx_destroy(bgn_ctx* c) {
   cudaFree(c->dPinf);
   cudaFree(c->tabP);
   cudaFree(c->tabQ);
-  cudaFree(c->tabQ16);
+  cudaFree(c->tabQw);
   cudaFree(c->tabE);
   cudaFree(c->linesP);
   cudaFree(c->bs_elems);
@@ -877,6 +898,34 @@ void bgn_ctx_destroy(bgn_ctx* c) {
 }
 
 const char* bgn_last_error(const bgn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
+  if (!c || !name) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string k(name);
+  if (k == "enc_window") {
+    if (value != 8 && value != 16 && value != 24) {
+      c->err = "enc_window must be 8, 16 or 24";
+      return BGN_E_BADARG;
+    }
+    if (c->enc_window != (int)value || (c->tabQw && c->tabQw_bits != (int)value)) {
+      cudaSetDevice(c->device);
+      if (c->stream) cudaStreamSynchronize(c->stream);
+      cudaFree(c->tabQw);
+      c->tabQw = nullptr;
+      c->tabQw_bits = 0;
+    }
+    c->enc_window = (int)value;
+  } else if (k == "dec_lucas") {
+    c->dec_lucas = value != 0;
+  } else if (k == "fixed_lines") {
+    c->fixed_lines = value != 0;
+  } else {
+    c->err = "unknown option " + k;
+    return BGN_E_BADARG;
+  }
+  return BGN_OK;
+}
 
 int bgn_ctx_info(const bgn_ctx* c, int* limbs, int* coord_bytes, int* scalar_bytes) {
   if (!c) return BGN_E_BADARG;
@@ -903,10 +952,10 @@ int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t 
     ea.x = dx;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
-    if (dr) ensure_tabQ16(c);
+    if (dr) ensure_tabQw(c);
     ea.tabP = c->tabP;
-    ea.tabQ = c->tabQ16 ? c->tabQ16 : c->tabQ;
-    ea.wbitsQ = c->tabQ16 ? 16 : 8;
+    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
+    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;
@@ -1120,7 +1169,7 @@ static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t c
     G1Arr Bv = g1_alloc(c, count);
     g1_from_bytes(c, db, count, Bv);
     run_miller(c, A, 1, Bv, 1, 0, count, 1, R);
-  } else if (c->linesP) {
+  } else if (c->linesP && c->fixed_lines) {
     run_miller_fixed(c, A, count, R);
   } else {
     G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
@@ -1227,14 +1276,14 @@ int bgn_g1_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t
     g1_from_bytes(c, da, count, A);
     JacArr j = jac_alloc(c, count);
     uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
-    ensure_tabQ16(c);
+    ensure_tabQw(c);
     EncArgs ea;
     ea.x = nullptr;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
     ea.tabP = c->tabP;
-    ea.tabQ = c->tabQ16 ? c->tabQ16 : c->tabQ;
-    ea.wbitsQ = c->tabQ16 ? 16 : 8;
+    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
+    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;
@@ -1386,7 +1435,7 @@ int bgn_make_poly_l2_batch(bgn_ctx* c, const uint8_t* in, size_t d, size_t count
     G1Arr A = g1_alloc(c, nin);
     g1_from_bytes(c, da, nin, A);
     GtArr R = gt_alloc(c, nin);
-    if (c->linesP) {
+    if (c->linesP && c->fixed_lines) {
       run_miller_fixed(c, A, nin, R);
     } else {
       G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
@@ -1510,7 +1559,7 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
       // level 1: e(C, P)^q1 = e(P,P)^(q1 m); same m as the reference's G1 table search (bgn.go:222-223)
       G1Arr C1 = g1_alloc(c, count);
       g1_from_bytes(c, di, count, C1);
-      if (c->linesP) {
+      if (c->linesP && c->fixed_lines) {
         run_miller_fixed(c, C1, count, A);
       } else {
         G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};

@@ -33,12 +33,13 @@ void tab_fill(LaunchCfg cfg, const uint32_t* ax, const uint32_t* ay, const uint8
               uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
   k_tab_fill<LL><<<CFG>>>(ax, ay, ainf, Nb, nwin, X, Y, Z, N);
 }
-void tab16_fill(LaunchCfg cfg, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent) {
-  k_tab16_fill<LL><<<CFG>>>(tab8, nwin8, X, Y, Z, nent);
+void tabw_fill(LaunchCfg cfg, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
+               size_t nent) {
+  k_tabw_fill<LL><<<CFG>>>(tab8, nwin8, wb, X, Y, Z, first, nent);
 }
 void g1_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_g1_polyconv<LL><<<CFG>>>(a); }
 const LOpsB ops = {LL,     upload,    g1_from_bytes, g1_to_bytes, encrypt,    normalize,
-                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tab16_fill, g1_polyconv};
+                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tabw_fill,  g1_polyconv};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

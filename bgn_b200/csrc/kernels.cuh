@@ -155,26 +155,21 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     FF::copy(Y.v(), a.by + e * L);
     FF::set_one(Z.v());
   }
-  if (a.r_be && a.wbitsQ == 16) {
-    // 16-bit windows: half the additions; the table (2^16 - 1 points per window, 285 MB at
-    // 512 bit) lives in HBM and each lookup is one 8L-byte read at a random address
+  if (a.r_be) {
+    // fixed-base windows of wbitsQ = 8, 16 or 24 bits: one complete mixed addition per non-zero
+    // window digit.  The wide tables (2^16 - 1 or 2^24 - 1 points per window: 285 MB / 50 GB at 512
+    // bit) live in HBM and each lookup is one 8L-byte read at a random address.
     const uint8_t* r = a.r_be + e * a.rbytes;
-    int nw = (a.rbytes + 1) / 2;
+    const int wb = a.wbitsQ >> 3;
+    const size_t ents = ((size_t)1 << a.wbitsQ) - 1;
+    const int nw = (a.rbytes + wb - 1) / wb;
     for (int win = 0; win < nw; win++) {
-      int lo = a.rbytes - 1 - 2 * win;
+      int lo = a.rbytes - 1 - wb * win;
       uint32_t d = r[lo];
-      if (lo > 0) d |= (uint32_t)r[lo - 1] << 8;
+      for (int k = 1; k < wb; k++)
+        if (lo - k >= 0) d |= (uint32_t)r[lo - k] << (8 * k);
       if (d) {
-        const uint32_t* ent = a.tabQ + ((size_t)win * 65535 + (d - 1)) * 2 * L;
-        G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
-      }
-    }
-  } else if (a.r_be) {
-    const uint8_t* r = a.r_be + e * a.rbytes;
-    for (int win = 0; win < a.rbytes; win++) {
-      uint32_t d = r[a.rbytes - 1 - win];
-      if (d) {
-        const uint32_t* ent = a.tabQ + ((size_t)win * 255 + (d - 1)) * 2 * L;
+        const uint32_t* ent = a.tabQ + ((size_t)win * ents + (d - 1)) * 2 * L;
         G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
       }
     }
@@ -334,29 +329,34 @@ BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t
   }
 }
 
-// 16-bit window table from the 8-bit one: entry (w, hi*256 + lo) = T8[2w][lo] + T8[2w+1][hi]
-// (one complete mixed addition per entry, all entries in parallel; Jacobian out).  An odd byte
-// count leaves the top window with its low byte only: those hi != 0 entries stay O and are never
-// addressed.
+// Wide-window table from the 8-bit one: entry (w, d) of a table with windows of wb bytes is the sum
+// of the 8-bit entries of d's bytes, T8[wb w + k][byte k of d] (wb - 1 complete mixed additions per
+// entry, all entries in parallel; Jacobian out).  `first` is the global index of this launch's first
+// entry (the 24-bit table is built in chunks).  A window that reaches past the scalar's top byte
+// leaves the entries with a non-zero byte there as O; they are never addressed.
 template <int L>
-BGN_DEV void tab16_fill_body(const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent,
-                             size_t id) {
+BGN_DEV void tabw_fill_body(const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                            size_t first, size_t nent, size_t id) {
   typedef F<L> FF;
   if (id >= nent) return;
-  int w = (int)(id / 65535);
-  uint32_t d = (uint32_t)(id % 65535) + 1, lo = d & 255u, hi = d >> 8;
+  const size_t ents = ((size_t)1 << (8 * wb)) - 1;
+  const size_t gidx = first + id;
+  const int w = (int)(gidx / ents);
+  const uint32_t d = (uint32_t)(gidx % ents) + 1;
   Loc<L> x, y, z, t0, t1, t2, t3;
   FF::set_zero(x.v());
   FF::set_zero(y.v());
   FF::set_zero(z.v());
-  if (hi == 0 || 2 * w + 1 < nwin8) {
-    if (lo) {
-      const uint32_t* ent = tab8 + ((size_t)(2 * w) * 255 + (lo - 1)) * 2 * L;
-      G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
-    }
-    if (hi) {
-      const uint32_t* ent = tab8 + ((size_t)(2 * w + 1) * 255 + (hi - 1)) * 2 * L;
-      G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+  bool valid = true;
+  for (int k = 0; k < wb; k++)
+    if (((d >> (8 * k)) & 255u) && w * wb + k >= nwin8) valid = false;
+  if (valid) {
+    for (int k = 0; k < wb; k++) {
+      uint32_t byte = (d >> (8 * k)) & 255u;
+      if (byte) {
+        const uint32_t* ent = tab8 + ((size_t)(w * wb + k) * 255 + (byte - 1)) * 2 * L;
+        G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+      }
     }
   }
   FF::copy(X + id * L, x.v());
@@ -737,9 +737,9 @@ __global__ void k_tab_fill(const uint32_t* ax, const uint32_t* ay, const uint8_t
   tab_fill_body<L>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, BGN_GID(size_t));
 }
 template <int L>
-__global__ void __launch_bounds__(128) k_tab16_fill(const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z,
-                                                    size_t nent) {
-  tab16_fill_body<L>(tab8, nwin8, X, Y, Z, nent, BGN_GID(size_t));
+__global__ void __launch_bounds__(128) k_tabw_fill(const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y,
+                                                   uint32_t* Z, size_t first, size_t nent) {
+  tabw_fill_body<L>(tab8, nwin8, wb, X, Y, Z, first, nent, BGN_GID(size_t));
 }
 template <int L>
 __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms,

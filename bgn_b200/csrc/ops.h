@@ -65,7 +65,8 @@ struct LOpsB {
                     size_t N);
   void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
                    uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
-  void (*tab16_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent);
+  void (*tabw_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
+                    size_t nent);
   void (*g1_polyconv)(LaunchCfg, const PolyConvArgs&);
 };
 

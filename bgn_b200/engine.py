@@ -110,6 +110,10 @@ class Engine:
         return np.frombuffer(b"".join(int(k).to_bytes(width, "big") for k in ks), dtype=np.uint8).copy()
 
     # ------------------------------------------------------------------ C-ABI calls
+    def set_option(self, name: str, value: int):
+        """tuning knobs (include/bgn_b200.h: bgn_ctx_set_option); none changes any result"""
+        self._check(self._lib.bgn_ctx_set_option(self._ctx, name.encode(), int(value)))
+
     def set_secret(self, q1: int, msg_space: int, baby_steps: int = 0):
         qb = q1.to_bytes((q1.bit_length() + 7) // 8, "big")
         self._check(self._lib.bgn_ctx_set_secret(self._ctx, qb, len(qb), msg_space, baby_steps))

@@ -64,6 +64,16 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out);
 void bgn_ctx_destroy(bgn_ctx* ctx);
 const char* bgn_last_error(const bgn_ctx* ctx);
 
+/* Tuning knobs of a context (none changes any result):
+ *   "enc_window"   8 | 16 | 24   fixed-base window of Q for Encrypt / level-1 re-randomisation.  16 (default):
+ *                                285 MB table at 512-bit keys; 24: 50 GB table, a third fewer additions (+39 %
+ *                                Encrypt throughput), ~2 s to build -- for long-lived contexts; falls back to 16
+ *                                when the table does not fit the free device memory.  The table is (re)built on
+ *                                the next randomised encryption.
+ *   "dec_lucas"    0 | 1         Decrypt through the Lucas ladder when one giant step suffices (default 1)
+ *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)                            */
+int bgn_ctx_set_option(bgn_ctx* ctx, const char* name, long value);
+
 /* limbs: 32-bit limbs of the field; coord_bytes: B; scalar_bytes: ceil(bits(n)/8). */
 int bgn_ctx_info(const bgn_ctx* ctx, int* limbs, int* coord_bytes, int* scalar_bytes);
 

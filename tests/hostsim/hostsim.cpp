@@ -109,8 +109,9 @@ int hs_tab_fill(int L, const uint32_t* ax, const uint32_t* ay, const uint8_t* ai
                 uint32_t* Y, uint32_t* Z, size_t N) {
   FOR_L(L, for (int w = 0; w < nwin; w++) tab_fill_body<LL>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, w))
 }
-int hs_tab16_fill(int L, const uint32_t* tab8, int nwin8, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t nent) {
-  FOR_L(L, for (size_t id = 0; id < nent; id++) tab16_fill_body<LL>(tab8, nwin8, X, Y, Z, nent, id))
+int hs_tabw_fill(int L, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
+                 size_t nent) {
+  FOR_L(L, for (size_t id = 0; id < nent; id++) tabw_fill_body<LL>(tab8, nwin8, wb, X, Y, Z, first, nent, id))
 }
 int hs_g1_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf, size_t N) {
   FOR_L(L, for (size_t e = 0; e < count; e++) g1_from_bytes_body<LL>(in, B, count, x, y, inf, N, e))

@@ -312,13 +312,17 @@ class Sim:
         return tab
 
     def build_table16(self, tab8, nwin8):
-        """k_tab16_fill + k_normalize: 16-bit windows from the 8-bit table (api.cu: ensure_tabQ16)"""
+        """k_tabw_fill + k_normalize: 16-bit windows from the 8-bit table (api.cu: ensure_tabQw), built in
+        two chunks the way the 24-bit table is"""
         L = self.L
         nent = ((nwin8 + 1) // 2) * 65535
         X = np.zeros((nent, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
-        assert lib().hs_tab16_fill(L, P32(tab8), nwin8, P32(X), P32(Y), P32(Z), C.c_size_t(nent)) == 0
+        half = nent // 2 + 3
+        assert lib().hs_tabw_fill(L, P32(tab8), nwin8, 2, P32(X), P32(Y), P32(Z), C.c_size_t(0), C.c_size_t(half)) == 0
+        assert lib().hs_tabw_fill(L, P32(tab8), nwin8, 2, P32(X[half:]), P32(Y[half:]), P32(Z[half:]), C.c_size_t(half),
+                                  C.c_size_t(nent - half)) == 0
         tab = np.zeros(nent * 2 * L, dtype=np.uint32)
         scratch = np.zeros_like(X)
         a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), nent, nent, 64, P32(tab), P32(tab[L:]), 2 * L, 1, None)

@@ -596,3 +596,35 @@ def test_full_size_decrypt_l2():
     v2, s2 = e2.decrypt_batch(l2, True)
     assert torch.equal(v2, vals) and not s2.any().item()
     e2.close()
+
+
+def test_encrypt_window_24():
+    """The HBM-scale 24-bit fixed-base windows of Q (enc_window = 24; 4 GB at keyBits=128) give the
+    golden bytes, and on a random batch the same bytes as the default 16-bit table, incl. scalars with
+    zero top bytes (windows that reach past the scalar's top byte)."""
+    from bgn_b200 import BgnError, Engine
+    g = load_golden(128)
+    e24 = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    e24.set_option("enc_window", 24)
+    with pytest.raises(BgnError):
+        e24.set_option("enc_window", 12)
+    with pytest.raises(BgnError):
+        e24.set_option("no_such_knob", 1)
+    v = g["encrypt"]
+    out = e24.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(e24, v["r"], e24.scalar_bytes))
+    assert out.tobytes() == unhex(v["out"])
+    v = g["g1_blind"]
+    assert e24.g1_blind_batch(buf(v["a"]), scal(e24, v["r"], e24.scalar_bytes)).tobytes() == unhex(v["out"])
+    rng = np.random.default_rng(24)
+    cnt = 4096
+    x = rng.integers(-1, 2, cnt)
+    r = rng.integers(0, 256, (cnt, e24.scalar_bytes), dtype=np.uint8)
+    r[:, 0] &= 0x3F
+    r[::5, :4] = 0
+    r[::7] = 0
+    e16 = engine_for(g)
+    exp = e16.encrypt_batch(x, r.reshape(-1)).tobytes()
+    assert e24.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
+    e24.set_option("enc_window", 8)  # drops the wide table: the 8-bit windows built with the context
+    assert e24.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
+    e24.close()

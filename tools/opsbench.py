@@ -27,11 +27,13 @@ def main():
     ap.add_argument("--key-bits", type=int, default=512)
     ap.add_argument("--emults", type=int, default=0, help="also time MultPoly of this many pairs")
     ap.add_argument("--d", type=int, default=D, help="coefficient slots per polynomial for --emults")
+    ap.add_argument("--enc-window", type=int, default=16, help="fixed-base window of Q: 8, 16 or 24 bits")
     args = ap.parse_args()
     with open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kb%d.json" % args.key_bits)) as f:
         g = json.load(f)
     p, n, l, q1 = int(g["p"], 16), int(g["n"], 16), g["l"], int(g["q1"], 16)
     eng = Engine(p, n, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=0)
+    eng.set_option("enc_window", args.enc_window)
     L, EB, SB = eng.limbs, eng.elem_bytes, eng.scalar_bytes
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev)
@@ -74,8 +76,8 @@ def main():
     r = r.reshape(-1)
     out = torch.empty(cnt * EB, dtype=torch.uint8, device=dev)
     t, k = timed(lambda: eng.encrypt_batch(digits, r, out=out))
-    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_modmuls(n, SB, 16), "k_encrypt")
-    res["ops"]["encrypt"]["window_bits"] = 16
+    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_modmuls(n, SB, args.enc_window), "k_encrypt")
+    res["ops"]["encrypt"]["window_bits"] = args.enc_window
     res["ops"]["encrypt"]["plaintexts_per_s"] = args.plaintexts / (t * 1e-3)
 
     if args.emults:
@@ -149,7 +151,7 @@ def main():
     rb = rb.reshape(-1)
     ob = torch.empty(nb * EB, dtype=torch.uint8, device=dev)
     t, k = timed(lambda: eng.g1_blind_batch(out[: nb * EB], rb, out=ob))
-    entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k, workmodel.encrypt_modmuls(n, SB, 16, 0.0) + 11,
+    entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k, workmodel.encrypt_modmuls(n, SB, args.enc_window, 0.0) + 11,
           "k_encrypt")
     l2b = l2.repeat(nb // nd)
     t, k = timed(lambda: eng.gt_blind_batch(l2b, rb, out=ob))
