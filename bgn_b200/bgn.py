@@ -131,6 +131,21 @@ class PublicKey:
             raise ValueError("only PBC type a1 parameters are supported")
         return cls(int(vals["p"]), int(vals["n"]), int(vals["l"]), P, Q, MsgSpace, **kw)
 
+    def MarshalBinary(self) -> bytes:
+        """bgn.go:597-624: the gob envelope of publicKeyWrapper.  G1 (an element used only as a factory,
+        bgn.go:29) is written as the generator P."""
+        pe = self.PolyEncodingParams
+        return gobwire.encode_public_key(self.P, self.P, self.Q, self.N, self.MsgSpace, self.PairingParams,
+                                         self.Deterministic, pe.PolyBase, pe.FPScaleBase, pe.FPPrecision)
+
+    @classmethod
+    def UnmarshalBinary(cls, data: bytes, device: int = 0) -> "PublicKey":
+        """bgn.go:628-666: a public key marshalled by the reference (or by MarshalBinary) onto a GPU."""
+        w = gobwire.decode_public_key(data)
+        return cls.FromPBCParams(w["PairingParams"], w["P"], w["Q"], w["MsgSpace"], Deterministic=w["Deterministic"],
+                                 polyBase=w["PolyBase"], fpScaleBase=w["FPScaleBase"], fpPrecision=w["FPPrecision"],
+                                 device=device)
+
     # ---------------------------------------------------------------- setup
     def SetupDecryption(self, sk: SecretKey):
         """bgn.go:195-201 + PrecomputeTables (gsbs.go:41-51): tables live on the device."""

@@ -25,6 +25,7 @@ here the element bytes go to the device as they are.
 """
 from __future__ import annotations
 
+import struct
 from typing import Any, Dict, List, Optional, Tuple
 
 # builtin type ids (encoding/gob type.go)
@@ -100,8 +101,43 @@ class StructT:
         self.name, self.fields = name, fields
 
 
+class GobEncT:
+    """a type that implements GobEncoder (math/big.Int here): its values travel as opaque bytes"""
+
+    def __init__(self, name: str):
+        self.name = name
+
+
+T_GOBENCTYPE = 1000  # gobEncoderType{CommonType}: no fixed id in Go, only its shape matters here
+
+
+def enc_float(f: float) -> bytes:
+    """float64 bits, byte-reversed (small exponents and mantissas with trailing zeros become short uints)"""
+    return enc_uint(int.from_bytes(struct.pack("<d", float(f)), "big"))
+
+
+def dec_float(r: "Reader") -> float:
+    return struct.unpack("<d", r.uint().to_bytes(8, "big"))[0]
+
+
+def bigint_gob(x: int) -> bytes:
+    """math/big.(*Int).GobEncode: version 1 in the upper 7 bits, sign in bit 0, then the magnitude"""
+    mag = abs(x)
+    return bytes([(1 << 1) | (1 if x < 0 else 0)]) + mag.to_bytes((mag.bit_length() + 7) // 8, "big")
+
+
+def bigint_ungob(b: bytes) -> int:
+    if len(b) == 0:
+        return 0
+    if b[0] >> 1 != 1:
+        raise GobError("unsupported big.Int gob version %d" % (b[0] >> 1))
+    v = int.from_bytes(b[1:], "big")
+    return -v if b[0] & 1 else v
+
+
 def _go_name(tid: int, types: Dict[int, Any]) -> str:
-    return {T_BOOL: "bool", T_INT: "int", T_UINT: "uint", T_BYTES: "[]uint8", T_STRING: "string"}.get(tid) or types[tid].name
+    return {T_BOOL: "bool", T_INT: "int", T_UINT: "uint", T_FLOAT: "float64", T_BYTES: "[]uint8",
+            T_STRING: "string"}.get(tid) or types[tid].name
 
 
 def _enc_common(name: str, tid: int) -> bytes:
@@ -114,6 +150,8 @@ def _enc_wiretype(tid: int, t: Any) -> bytes:
     if isinstance(t, SliceT):
         body = b"\x01" + _enc_common(t.name, tid) + b"\x01" + enc_int(t.elem) + b"\x00"  # sliceType
         return b"\x02" + body + b"\x00"  # field 1 of wireType
+    if isinstance(t, GobEncT):
+        return b"\x05" + b"\x01" + _enc_common(t.name, tid) + b"\x00" + b"\x00"  # field 4 of wireType
     body = b"\x01" + _enc_common(t.name, tid)
     if t.fields:
         body += b"\x01" + enc_uint(len(t.fields))
@@ -135,10 +173,12 @@ def _is_zero(tid: int, v: Any, types) -> bool:
         return v == 0
     if tid in (T_BYTES, T_STRING):
         return len(v) == 0
+    if tid == T_FLOAT:
+        return v == 0.0
     t = types[tid]
     if isinstance(t, SliceT):
         return len(v) == 0
-    return False
+    return v is None  # nil pointers (structs, GobEncoders) are not transmitted
 
 
 def _enc_value(tid: int, v: Any, types) -> bytes:
@@ -152,9 +192,13 @@ def _enc_value(tid: int, v: Any, types) -> bytes:
         return enc_bytes(bytes(v))
     if tid == T_STRING:
         return enc_bytes(v.encode() if isinstance(v, str) else bytes(v))
+    if tid == T_FLOAT:
+        return enc_float(v)
     t = types[tid]
     if isinstance(t, SliceT):
         return enc_uint(len(v)) + b"".join(_enc_value(t.elem, x, types) for x in v)
+    if isinstance(t, GobEncT):
+        return enc_bytes(v)
     out, last = b"", -1
     for idx, (fname, ftid) in enumerate(t.fields):
         fv = v[fname]
@@ -176,9 +220,13 @@ def _dec_value(r: Reader, tid: int, types) -> Any:
         return r.bytes_()
     if tid == T_STRING:
         return r.bytes_().decode()
+    if tid == T_FLOAT:
+        return dec_float(r)
     if tid not in types:
         raise GobError("value of undefined type id %d" % tid)
     t = types[tid]
+    if isinstance(t, GobEncT):
+        return r.bytes_()
     if isinstance(t, SliceT):
         n = r.uint()
         if n > r.end - r.pos:
@@ -206,8 +254,10 @@ _BOOT: Dict[int, Any] = {
     T_FIELDSLICE: SliceT("[]*gob.fieldType", T_FIELDTYPE),
     T_STRUCTTYPE: StructT("structType", [("CommonType", T_COMMONTYPE), ("Field", T_FIELDSLICE)]),
     T_MAPTYPE: StructT("mapType", [("CommonType", T_COMMONTYPE), ("Key", T_INT), ("Elem", T_INT)]),
+    T_GOBENCTYPE: StructT("gobEncoderType", [("CommonType", T_COMMONTYPE)]),
     T_WIRETYPE: StructT("wireType", [("ArrayT", T_ARRAYTYPE), ("SliceT", T_SLICETYPE), ("StructT", T_STRUCTTYPE),
-                                     ("MapT", T_MAPTYPE)]),
+                                     ("MapT", T_MAPTYPE), ("GobEncoderT", T_GOBENCTYPE),
+                                     ("BinaryMarshalerT", T_GOBENCTYPE), ("TextMarshalerT", T_GOBENCTYPE)]),
 }
 
 
@@ -230,6 +280,9 @@ def decode_stream(data: bytes) -> List[Tuple[str, Any]]:
             elif "SliceT" in w:
                 sl = w["SliceT"]
                 types[-tid] = SliceT(sl.get("CommonType", {}).get("Name", ""), sl.get("Elem", 0))
+            elif "GobEncoderT" in w or "BinaryMarshalerT" in w:
+                ge = w.get("GobEncoderT") or w.get("BinaryMarshalerT")
+                types[-tid] = GobEncT(ge.get("CommonType", {}).get("Name", ""))
             else:
                 raise GobError("unsupported wire type (only structs and slices occur in the bgn envelopes)")
             continue
@@ -301,3 +354,36 @@ def decode_poly_ciphertext(data: bytes) -> Tuple[List[bytes], int, int, bool]:
     v = vals[0][1]
     return ([bytes(c) for c in v.get("CoeffBytes", [])], int(v.get("Degree", 0)), int(v.get("ScaleFactor", 0)),
             bool(v.get("L2", False)))
+
+
+def encode_public_key(G1: bytes, P: bytes, Q: bytes, N: int, MsgSpace: int, PairingParams: str, Deterministic: bool,
+                      PolyBase: int, FPScaleBase: int, FPPrecision: float) -> bytes:
+    """PublicKey.MarshalBinary (bgn.go:597-624): gob of publicKeyWrapper{G1, P, Q []byte; N, MsgSpace *big.Int;
+    PairingParams string; Deterministic bool; PolyEncodingParams *PolyEncodingParams} (bgn.go:45-55)."""
+    sid, bid, pid = FIRST_USER_ID, FIRST_USER_ID + 1, FIRST_USER_ID + 2
+    types = {
+        sid: StructT("publicKeyWrapper", [("G1", T_BYTES), ("P", T_BYTES), ("Q", T_BYTES), ("N", bid), ("MsgSpace", bid),
+                                          ("PairingParams", T_STRING), ("Deterministic", T_BOOL),
+                                          ("PolyEncodingParams", pid)]),
+        bid: GobEncT("Int"),
+        pid: StructT("PolyEncodingParams", [("PolyBase", T_INT), ("FPScaleBase", T_INT), ("FPPrecision", T_FLOAT)]),
+    }
+    value = {"G1": G1, "P": P, "Q": Q, "N": bigint_gob(N), "MsgSpace": bigint_gob(MsgSpace),
+             "PairingParams": PairingParams, "Deterministic": Deterministic,
+             "PolyEncodingParams": {"PolyBase": PolyBase, "FPScaleBase": FPScaleBase, "FPPrecision": FPPrecision}}
+    out = b"".join(_message(enc_int(-t) + _enc_wiretype(t, types[t])) for t in (sid, bid, pid))
+    return out + _message(enc_int(sid) + _enc_value(sid, value, types))
+
+
+def decode_public_key(data: bytes) -> Dict[str, Any]:
+    """PublicKey.UnmarshalBinary (bgn.go:628-666) up to, not including, the PBC objects: plain values."""
+    vals = decode_stream(data)
+    if len(vals) != 1:
+        raise GobError("expected one value")
+    v = vals[0][1]
+    pe = v.get("PolyEncodingParams") or {}
+    return {"G1": bytes(v.get("G1", b"")), "P": bytes(v.get("P", b"")), "Q": bytes(v.get("Q", b"")),
+            "N": bigint_ungob(v.get("N", b"")), "MsgSpace": bigint_ungob(v.get("MsgSpace", b"")),
+            "PairingParams": v.get("PairingParams", ""), "Deterministic": bool(v.get("Deterministic", False)),
+            "PolyBase": int(pe.get("PolyBase", 0)), "FPScaleBase": int(pe.get("FPScaleBase", 0)),
+            "FPPrecision": float(pe.get("FPPrecision", 0.0))}

@@ -65,3 +65,26 @@ def test_malformed_streams_raise():
     for bad in (env[:-3], env[:5], b"\x03\xff\x82\x00"):
         with pytest.raises((G.GobError, KeyError)):
             G.decode_ciphertext(bad)
+
+
+def test_float_and_bigint_forms():
+    # documented: 17.0 is fe 31 40 (exponent and high mantissa only)
+    assert G.enc_float(17.0) == bytes.fromhex("fe3140")
+    for f in (0.0001, 1.5, -2.25, 1e300):
+        assert G.dec_float(G.Reader(G.enc_float(f))) == f
+    assert G.bigint_gob(0) == b"\x02" and G.bigint_gob(255) == b"\x02\xff" and G.bigint_gob(-256) == b"\x03\x01\x00"
+    for v in (0, 1, -1, 1 << 512, -(1 << 100) + 7):
+        assert G.bigint_ungob(G.bigint_gob(v)) == v
+
+
+def test_public_key_roundtrip():
+    n = (1 << 511) + 12345
+    env = G.encode_public_key(b"g" * 130, b"p" * 130, b"q" * 130, n, 1 << 20, "type a1\np 7\nn 3\nl 4\n", True, 3, 3, 0.0001)
+    w = G.decode_public_key(env)
+    assert w == {"G1": b"g" * 130, "P": b"p" * 130, "Q": b"q" * 130, "N": n, "MsgSpace": 1 << 20,
+                 "PairingParams": "type a1\np 7\nn 3\nl 4\n", "Deterministic": True, "PolyBase": 3, "FPScaleBase": 3,
+                 "FPPrecision": 0.0001}
+    names = [nm for nm, _ in G.decode_stream(env)]
+    assert names == ["publicKeyWrapper"]
+    # Deterministic=false is a zero value: omitted on the wire, false after decoding
+    assert G.decode_public_key(G.encode_public_key(b"a", b"b", b"c", 5, 7, "x", False, 3, 3, 0.5))["Deterministic"] is False

@@ -398,6 +398,11 @@ def test_mirror_wire_roundtrip():
     assert o.C == bytes(pk.elem_bytes)
     with pytest.raises(ValueError):
         pk.NewCiphertextFromBytes(b"")
+    # the public key itself (bgn.go:597-666): marshal, load onto the GPU again, same ciphertext bytes
+    pk2 = PublicKey.UnmarshalBinary(pk.MarshalBinary())
+    assert (pk2.N, pk2.MsgSpace, pk2.Deterministic, pk2.PairingParams) == (pk.N, pk.MsgSpace, True, pk.PairingParams)
+    assert pk2.EncryptWithRandomness(5, 12345).C == pk.EncryptWithRandomness(5, 12345).C
+    pk2.engine.close()
 
 
 def test_batch_poly_helpers_match_mirror():
