@@ -96,8 +96,14 @@ std::vector<int8_t> big_naf(Big n) {
 
 const int kSupportedL[] = {3, 5, 9, 17, 33};
 
-std::mutex g_mu;                         // serialises device work of this library in the process
-std::map<int, const bgn_ctx*> g_active;  // device -> context whose constants are resident
+// One lock per device: the kernels read their key material from __constant__ memory, of which there
+// is one copy per device, so calls on contexts of the SAME device are serialised (thread-compatible,
+// like the reference's pk.mu, bgn.go:40) while contexts on different devices run concurrently -- a
+// single process may drive all GPUs of a box from one thread each.
+constexpr int kMaxDevices = 64;
+std::mutex g_dev_mu[kMaxDevices];
+const bgn_ctx* g_active[kMaxDevices] = {};  // device -> context whose constants are resident (under its lock)
+std::mutex& dev_mu(int device) { return g_dev_mu[(unsigned)device % kMaxDevices]; }
 }  // namespace
 
 // ---------------------------------------------------------------- context
@@ -170,8 +176,7 @@ struct ArgErr {
 
 void activate(bgn_ctx* c) {
   CK(cudaSetDevice(c->device));
-  auto it = g_active.find(c->device);
-  if (it == g_active.end() || it->second != c) {
+  if (g_active[c->device] != c) {
     CK(c->A->upload(&c->fc, &c->pc, c->stream));
     CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
     CK(c->Co->upload(&c->fc, &c->pc, c->stream));
@@ -673,7 +678,7 @@ void ensure_tabE(bgn_ctx* c) {
 template <typename Fn>
 int guarded(bgn_ctx* c, Fn fn) {
   if (!c) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   try {
     activate(c);
     arena_reset(c);
@@ -715,7 +720,8 @@ extern "C" {
 int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
   if (!prm || !out || !prm->p_be || !prm->n_be || !prm->P_bytes || !prm->Q_bytes || prm->l == 0) return BGN_E_BADARG;
   *out = nullptr;
-  std::lock_guard<std::mutex> lk(g_mu);
+  if (device < 0 || device >= kMaxDevices) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(dev_mu(device));
   bgn_ctx* c = nullptr;
   try {
     c = new bgn_ctx();
@@ -825,7 +831,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
 
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    g_active.erase(device);
+    g_active[device] = nullptr;
     activate(c);
     // generators
     size_t lw = (size_t)L * 4;
@@ -874,11 +880,10 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
 
 void bgn_ctx_destroy(bgn_ctx* c) {
   if (!c) return;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  auto it = g_active.find(c->device);
-  if (it != g_active.end() && it->second == c) g_active.erase(it);
+  if (g_active[c->device] == c) g_active[c->device] = nullptr;
   cudaFree(c->dPx);
   cudaFree(c->dPinf);
   cudaFree(c->tabP);
@@ -901,7 +906,7 @@ const char* bgn_last_error(const bgn_ctx* c) { return c ? c->err.c_str() : "null
 
 int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
   if (!c || !name) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   std::string k(name);
   if (k == "enc_window") {
     if (value != 8 && value != 16 && value != 24) {
@@ -1630,20 +1635,20 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
 // ---------------------------------------------------------------- instrumentation
 int bgn_timing_enable(bgn_ctx* c, int on) {
   if (!c) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   c->timing = on != 0;
   return BGN_OK;
 }
 int bgn_timing_reset(bgn_ctx* c) {
   if (!c) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   c->ktimes.clear();
   c->total_launches = 0;
   return BGN_OK;
 }
 int bgn_timing_get(bgn_ctx* c, const char* prefix, double* ms_total, uint64_t* launches) {
   if (!c || !prefix) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   double ms = 0;
   uint64_t n = 0;
   size_t pl = strlen(prefix);
@@ -1660,7 +1665,7 @@ int bgn_timing_get(bgn_ctx* c, const char* prefix, double* ms_total, uint64_t* l
 
 int bgn_timing_last_call(bgn_ctx* c, double* ms) {
   if (!c || !ms) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   *ms = c->last_call_ms;
   return BGN_OK;
 }
@@ -1717,8 +1722,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, int iters, uin
 }
 
 int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread) {
-  if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256) return BGN_E_BADARG;
-  std::lock_guard<std::mutex> lk(g_mu);
+  if (!ms || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256 || device < 0) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(dev_mu(device));
   if (cudaSetDevice(device) != cudaSuccess) return BGN_E_CUDA;
   uint32_t* d = nullptr;
   if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return BGN_E_CUDA;

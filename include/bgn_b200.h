@@ -14,8 +14,9 @@
  *     copied in/out inside the call.
  *   - the caller owns all buffers; the library keeps no caller pointer after return.
  *   - all functions return 0 on success or a negative bgn_status; none throws or aborts.
- *   - a context is thread-compatible: calls are serialised internally and are
- *     synchronous (they return after the device work has finished).
+ *   - a context is thread-compatible: calls are synchronous (they return after the
+ *     device work has finished) and serialised per DEVICE -- contexts on different
+ *     GPUs may be driven concurrently from one process, one thread each.
  *
  * Homomorphic operations implement the reference's Deterministic=true behaviour
  * (bgn_test.go:13).  The non-deterministic mode is the same operation followed by

@@ -633,3 +633,31 @@ def test_encrypt_window_24():
     e24.set_option("enc_window", 8)  # drops the wide table: the 8-bit windows built with the context
     assert e24.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
     e24.close()
+
+
+def test_two_contexts_two_threads_same_device():
+    """Contexts of different keys share one device's __constant__ key material: calls are serialised
+    per device and the constants follow the active context.  Two threads hammer two keys at once and
+    every result must still equal the golden bytes."""
+    import threading
+    errs = []
+
+    def work(kb):
+        try:
+            g = load_golden(kb)
+            e, v, w = engine_for(g), g["pair"], g["encrypt"]
+            for _ in range(12):
+                assert e.pair_batch(buf(v["a"]), buf(v["b"])).tobytes() == unhex(v["out"])
+                out = e.encrypt_batch(np.array(w["x"], dtype=np.int64), scal(e, w["r"], e.scalar_bytes))
+                assert out.tobytes() == unhex(w["out"])
+        except Exception as ex:  # noqa: BLE001
+            errs.append((kb, repr(ex)))
+
+    for kb in (64, 128):
+        engine_for(load_golden(kb))  # create outside the threads (the engine cache is not thread-safe)
+    ts = [threading.Thread(target=work, args=(kb,)) for kb in (64, 128)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
