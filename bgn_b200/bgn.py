@@ -28,6 +28,16 @@ from .engine import Engine
 from .plaintext import (EncodingTable, NewPolyPlaintext, NewUnbalancedPlaintext, PolyEncodingParams, PolyPlaintext)
 
 
+def _element_string(raw: bytes, L2: bool) -> str:
+    """pbc Element.String() in base 10: "[x, y]" for G1 (or "O"), "[re, im]" for GT
+    (ciphertext.go:60-72 prints these)."""
+    h = len(raw) // 2
+    a, b = int.from_bytes(raw[:h], "big"), int.from_bytes(raw[h:], "big")
+    if not L2 and a == 0 and b == 0:
+        return "O"
+    return "[%d, %d]" % (a, b)
+
+
 class DLError(Exception):
     """errors.New("cannot find discrete log; out of bounds") (gsbs.go:105)."""
 
@@ -44,6 +54,9 @@ class Ciphertext:  # ciphertext.go:12-15
         """ciphertext.go:76-91: the gob envelope of ciphertextWrapper{CBytes, L2}."""
         return gobwire.encode_ciphertext(self.C, self.L2)
 
+    def String(self) -> str:
+        return _element_string(self.C, self.L2) + "\n"  # ciphertext.go:60-62
+
 
 @dataclass
 class PolyCiphertext:  # ciphertext.go:26-31
@@ -54,6 +67,9 @@ class PolyCiphertext:  # ciphertext.go:26-31
 
     def Copy(self) -> "PolyCiphertext":
         return PolyCiphertext(self.Coefficients, self.Degree, self.ScaleFactor, self.L2)
+
+    def String(self) -> str:
+        return "".join(_element_string(c.C, c.L2) + "\n" for c in self.Coefficients)  # ciphertext.go:64-72
 
     def CoeffBytes(self) -> bytes:
         """the coefficients' element bytes back to back: the layout of a PolyCiphertextBatch row"""

@@ -7,7 +7,7 @@ import re
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, load_golden
 from oracle import bgn_oracle as O
 
 
@@ -93,3 +93,19 @@ def test_work_model_numbers():
     assert unit < canon / 3  # sharing (lines, squarings, final exp) removes > 2/3 of the canonical work
     assert W.canonical_pairing_modmuls(n, l) == O.canonical_modmuls_per_pairing(O.A1Params(p, n, l))
     assert sum(d * 2 ** i for i, d in enumerate(reversed(W.naf_digits(n)))) == n
+
+
+def test_element_string_format():
+    """pbc's base-10 element format as printed by Ciphertext.String (ciphertext.go:60-72)."""
+    from bgn_b200.bgn import Ciphertext, PolyCiphertext
+    from oracle import bgn_oracle as O
+    g = load_golden(64)
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    raw = bytes.fromhex(g["encrypt"]["out"][2])
+    pt = O.g1_from_bytes(raw, par)
+    assert Ciphertext(raw, False).String() == O.g1_string(pt) + "\n"
+    assert Ciphertext(bytes(len(raw)), False).String() == "O\n"
+    gt = bytes.fromhex(g["pair"]["out"][0])
+    assert Ciphertext(gt, True).String() == O.gt_string(O.gt_from_bytes(gt, par)) + "\n"
+    pc = PolyCiphertext([Ciphertext(raw, False), Ciphertext(bytes(len(raw)), False)], 2, 0, False)
+    assert pc.String() == O.g1_string(pt) + "\nO\n"

@@ -116,6 +116,17 @@ def main():
     entry("pair_single", nd, "pairings (unshared, one team of 1)", t, k,
           workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
     l2 = eng.pair_batch(ca, cb)
+    # the same kernels on a batch that gives every scheduler two warps (2^17 pairings)
+    rep = (1 << 17) // nd
+    if rep > 1:
+        ca_big, cb_big = ca.repeat(rep), cb.repeat(rep)
+        t, k = timed(lambda: eng.pair_batch(ca_big, cb_big), reps=1)
+        entry("pair_single_2e17", nd * rep, "pairings (unshared)", t, k,
+              workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
+        t, k = timed(lambda: eng.make_l2_batch(ca_big), reps=1)
+        entry("make_l2_2e17", nd * rep, "pairings with P (line table)", t, k,
+              workmodel.miller_fixed_products(p, n, l) / ppm, "k_miller_fixed")
+        del ca_big, cb_big
     eng.set_secret(q1, T)
     vals = {}
 
