@@ -425,12 +425,54 @@ class PublicKey:
         out = self.engine.encrypt_batch(flat, r_be)
         return PolyCiphertextBatch(out, count, degree, ScaleFactor, False)
 
+    @staticmethod
+    def _rows(data, count: int, degree: int, eb: int):
+        """a batch buffer as [count, degree * eb] (numpy array or torch tensor alike)"""
+        return data.reshape(count, degree * eb)
+
+    @staticmethod
+    def _flat(x):
+        x = x.contiguous() if hasattr(x, "contiguous") else np.ascontiguousarray(x)
+        return x.reshape(-1)
+
     def AddPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch) -> PolyCiphertextBatch:
-        """AddPoly over equal-shape batches (same level, Degree and ScaleFactor)."""
-        if (a.count, a.Degree, a.L2, a.ScaleFactor) != (b.count, b.Degree, b.L2, b.ScaleFactor):
-            raise ValueError("AddPolyBatch needs aligned batches; use AddPoly for mixed shapes")
-        res = self.engine.gt_mul_batch(a.data, b.data) if a.L2 else self.engine.g1_add_batch(a.data, b.data)
-        return PolyCiphertextBatch(res, a.count, a.Degree, a.ScaleFactor, a.L2)
+        """AddPoly (poly.go:171-207) over two batches of equal count, with everything the scalar
+        version does: a level-1 operand is promoted with MakePolyL2 when the other is level 2
+        (poly.go:173-182), the operand with the smaller ScaleFactor is multiplied by
+        FPScaleBase^diff (alignPolyCiphertexts, poly.go:209-226), the common slots are added and the
+        longer operand's tail is passed through (poly.go:191-204)."""
+        if a.count != b.count:
+            raise ValueError("AddPolyBatch needs batches of equal count")
+        if a.L2 != b.L2:
+            if not a.L2:
+                a = self.MakePolyL2Batch(a)
+            else:
+                b = self.MakePolyL2Batch(b)
+        if a.ScaleFactor != b.ScaleFactor:
+            lo, hi = (a, b) if a.ScaleFactor < b.ScaleFactor else (b, a)
+            diff = hi.ScaleFactor - lo.ScaleFactor
+            up = self.MultConstPolyBatch(lo, math.pow(float(self.PolyEncodingParams.FPScaleBase), float(diff)))
+            up.ScaleFactor = hi.ScaleFactor
+            a, b = hi, up
+        eb = self.elem_bytes
+        if a.Degree == b.Degree:
+            res = self.engine.gt_mul_batch(a.data, b.data) if a.L2 else self.engine.g1_add_batch(a.data, b.data)
+            return PolyCiphertextBatch(res, a.count, a.Degree, a.ScaleFactor, a.L2)
+        if a.Degree < b.Degree:
+            a, b = b, a  # a is the longer one; addition is commutative
+        common = b.Degree
+        ra = self._rows(a.data, a.count, a.Degree, eb)
+        head = self._flat(ra[:, : common * eb])
+        summed = self.engine.gt_mul_batch(head, b.data) if a.L2 else self.engine.g1_add_batch(head, b.data)
+        out = ra.clone() if hasattr(ra, "clone") else ra.copy()
+        sm = self._rows(summed, a.count, common, eb)
+        if hasattr(out, "is_cuda") and not hasattr(sm, "is_cuda"):
+            import torch
+            sm = torch.from_numpy(sm).to(out.device)
+        elif not hasattr(out, "is_cuda") and hasattr(sm, "is_cuda"):
+            sm = sm.cpu().numpy()
+        out[:, : common * eb] = sm
+        return PolyCiphertextBatch(out.reshape(-1), a.count, a.Degree, a.ScaleFactor, a.L2)
 
     def MultPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, rs=None) -> PolyCiphertextBatch:
         """MultPoly over a batch.  Non-deterministic keys re-randomise every output slot: the

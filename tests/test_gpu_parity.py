@@ -661,3 +661,42 @@ def test_two_contexts_two_threads_same_device():
     for t in ts:
         t.join()
     assert not errs, errs
+
+
+def test_addpoly_batch_mixed_shapes():
+    """AddPolyBatch with mixed levels, slot counts and scale factors equals AddPoly per polynomial
+    (poly.go:171-226: MakePolyL2 promotion, alignPolyCiphertexts, tail pass-through)."""
+    from bgn_b200 import PublicKey, SecretKey
+    from bgn_b200.bgn import PolyCiphertextBatch
+    g = load_golden(128)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    rng = random.Random(5)
+
+    def make(values, pad_to):
+        polys = []
+        for v in values:
+            pt = pk.NewPolyPlaintext(v)
+            co = pt.Coefficients[: pt.Degree] + [0] * (pad_to - pt.Degree)
+            pp = type(pt)(co, pad_to, pt.ScaleFactor, pt.params)
+            polys.append(pk.EncryptPoly(pp, rs=[rng.randrange(pk.N) for _ in range(pad_to)]))
+        sf = polys[0].ScaleFactor
+        assert all(p.ScaleFactor == sf for p in polys)
+        data = np.frombuffer(b"".join(p.CoeffBytes() for p in polys), dtype=np.uint8).copy()
+        return polys, PolyCiphertextBatch(data, len(polys), pad_to, sf, False)
+
+    ints, bi = make([5.0, 12.0, 40.0], 5)          # ScaleFactor 0, 5 slots
+    thirds, bt = make([1 / 3, 2 / 3, 4 / 3], 3)    # ScaleFactor 1, 3 slots
+    assert bt.ScaleFactor == 1
+    cases = [(ints, bi, thirds, bt), (thirds, bt, ints, bi)]
+    l2i = [pk.MakePolyL2(p) for p in ints]
+    bl2 = pk.MakePolyL2Batch(bi)
+    cases.append((l2i, bl2, thirds, bt))  # level 2 + level 1, different scale factors and slot counts
+    for pa, ba, pb, bb in cases:
+        got = pk.AddPolyBatch(ba, bb)
+        exp = [pk.AddPoly(x, y) for x, y in zip(pa, pb)]
+        assert (got.Degree, got.ScaleFactor, got.L2) == (exp[0].Degree, exp[0].ScaleFactor, exp[0].L2)
+        assert bytes(got.data.tobytes()) == b"".join(e.CoeffBytes() for e in exp)
+    vals = [sk.DecryptPoly(pk.AddPoly(x, y), pk).PolyEval() for x, y in zip(ints, thirds)]
+    assert ["%.2f" % v for v in vals] == ["5.33", "12.67", "41.33"]
