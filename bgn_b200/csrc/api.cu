@@ -146,6 +146,7 @@ struct bgn_ctx {
   bool timing = false;
   int miller_skew = 20000;  // cycles; see MillerArgs::skew_cycles
   int miller_groups = 0;    // 0 = choose per batch, 1 / 2 = force (tuning knob BGN_MILLER_GROUPS)
+  int miller_tail = 0;      // block-size granularity of a separate launch for a partial last wave (0 = off)
   std::map<std::string, KTime> ktimes;
   struct Pending {
     std::string name;
@@ -414,7 +415,7 @@ size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
 
 // the Miller team kernel; dM <= dE
 void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
-                const GtArr& out) {
+                const GtArr& out, bool is_tail = false) {
   if (!count) return;
   int TS = dE;
   const size_t smem_max = 227 * 1024 - 64;
@@ -460,9 +461,20 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   // in one wave, in blocks of whole scheduler rounds (128 threads = one warp on each of the four
   // schedulers).  Measured: 1 warp per scheduler finishes ~25 % sooner than 2, while an unbalanced
   // 7-warp block is SLOWER than an 8-warp one (profiles/r01_ops1024_v13.json vs v12).
+  // Several waves with a partial last one: run the full waves, then the remainder as its own launch
+  // spread over all SMs (BGN_MILLER_TAIL: granularity of that launch's block size in threads, 0 = off).
+  if (groups == 1 && c->miller_tail > 0 && !is_tail && count > (size_t)sms * tpg && count % ((size_t)sms * tpg) != 0) {
+    size_t full = count / ((size_t)sms * tpg) * ((size_t)sms * tpg), rem = count - full;
+    auto g1_off = [&](const G1Arr& a, size_t n) { return G1Arr{a.x + n * c->L, a.y + n * c->L, a.inf + n, a.N - n}; };
+    GtArr o2{out.re + full * out_slots * c->L, out.im + full * out_slots * c->L, out.N - full * out_slots};
+    run_miller(c, M, dM, E, dE, e_bcast, full, out_slots, out, false);
+    run_miller(c, g1_off(M, full * dM), dM, e_bcast ? E : g1_off(E, full * dE), dE, e_bcast, rem, out_slots, o2, true);
+    return;
+  }
   if (groups == 1 && count < (size_t)sms * tpg) {
     size_t thr_per_sm = (count * TS + sms - 1) / sms;
-    int ntM = (int)std::min<size_t>(GT_, std::max<size_t>((thr_per_sm + 127) / 128 * 128, (size_t)(TS + 31) / 32 * 32));
+    size_t gran = is_tail ? (size_t)c->miller_tail : 128;
+    int ntM = (int)std::min<size_t>(GT_, std::max<size_t>((thr_per_sm + gran - 1) / gran * gran, (size_t)(TS + 31) / 32 * 32));
     tpg = std::max(1, ntM / TS);
     GT_ = ntM;
     if (!c->A->miller_fixed_threads()) smem = c->A->miller_smem_bytes(GT_) + 16;
@@ -728,6 +740,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->device = device;
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
+    if (const char* tl = getenv("BGN_MILLER_TAIL")) c->miller_tail = atoi(tl);
     if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : (atoi(ew) == 24 ? 24 : 16);
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
