@@ -128,7 +128,10 @@ class PublicKey:
     one-off host computation and out of the accelerated path)."""
 
     def __init__(self, p: int, n: int, l: int, P: bytes, Q: bytes, MsgSpace: int, Deterministic: bool = True,
-                 polyBase: int = 3, fpScaleBase: int = 3, fpPrecision: float = 0.0001, device: int = 0):
+                 polyBase: int = 3, fpScaleBase: int = 3, fpPrecision: float = 0.0001, device: int = 0,
+                 engine=None):
+        """`engine`: an already constructed engine for this key (anything with Engine's methods; the CPU
+        test-suite passes a stand-in so the host logic of this file can be exercised without a GPU)."""
         self.N = n
         self.P, self.Q = bytes(P), bytes(Q)
         self.MsgSpace = MsgSpace
@@ -136,7 +139,7 @@ class PublicKey:
         self.Deterministic = Deterministic
         self.PolyEncodingParams = PolyEncodingParams(polyBase, fpScaleBase, fpPrecision)
         self._table = EncodingTable(polyBase)  # computeEncodingTable, bgn.go:135
-        self.engine = Engine(p, n, l, P, Q, device)
+        self.engine = engine if engine is not None else Engine(p, n, l, P, Q, device)
         self._secret_set = False
 
     @classmethod

@@ -1,0 +1,154 @@
+"""The host mirror of the Go API (bgn_b200/bgn.py) on the CPU: its engine is replaced by a stand-in that
+answers every C-ABI call from the oracle (tests/fake_engine.py), so what is tested here is the HOST logic --
+level promotion, scale alignment, tail pass-through, slot counts, wire formats, error behaviour -- against
+the oracle's own implementation of the same reference functions (poly.go, bgn.go)."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from fake_engine import FakeEngine
+from oracle import bgn_oracle as O
+
+from bgn_b200.bgn import DLError, PolyCiphertextBatch, PublicKey, SecretKey
+
+
+@pytest.fixture(scope="module")
+def keys():
+    g = load_golden(64)
+    p, n, l = int(g["p"], 16), int(g["n"], 16), g["l"]
+    P, Q = bytes.fromhex(g["P"]), bytes.fromhex(g["Q"])
+    pk = PublicKey(p, n, l, P, Q, g["msg_space"], engine=FakeEngine(p, n, l, P, Q))
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    par = O.A1Params(p, n, l)
+    opk = O.PublicKey(par, O.g1_from_bytes(P, par), O.g1_from_bytes(Q, par), g["msg_space"])
+    osk = O.SecretKey(sk.Key, 0)
+    O.setup_decryption(opk, osk)
+    return pk, sk, opk, osk
+
+
+def test_truth_table(keys):
+    """cmd/main.go:74-107."""
+    pk, sk, _, _ = keys
+    cts = {m: pk.Encrypt(m) for m in (0, 1, -1)}
+    for a in (0, 1, -1):
+        assert sk.Decrypt(pk.Neg(cts[a]), pk) == -a
+        for b in (0, 1, -1):
+            assert sk.Decrypt(pk.Add(cts[a], cts[b]), pk) == a + b
+            assert sk.Decrypt(pk.Sub(cts[a], cts[b]), pk) == a - b
+            assert sk.Decrypt(pk.Mult(cts[a], cts[b]), pk) == a * b
+            assert sk.Decrypt(pk.Add(pk.Mult(cts[a], cts[b]), cts[a]), pk) == a * b + a
+
+
+def test_decrypt_errors(keys):
+    pk, sk, _, _ = keys
+    big = pk.EncryptDeterministic(10 ** 6)  # beyond bound^2 + bound + 2 for MsgSpace = 1021
+    with pytest.raises(DLError):
+        sk.Decrypt(big, pk)
+    assert sk.DecryptFailSafe(big, pk) == 0
+    g = load_golden(64)
+    p, n, l = int(g["p"], 16), int(g["n"], 16), g["l"]
+    P, Q = bytes.fromhex(g["P"]), bytes.fromhex(g["Q"])
+    fresh = PublicKey(p, n, l, P, Q, g["msg_space"], engine=FakeEngine(p, n, l, P, Q))
+    with pytest.raises(RuntimeError, match="DL tables not computed"):  # gsbs.go:56-58
+        sk.Decrypt(fresh.Encrypt(1), fresh)
+
+
+def test_poly_ops_match_oracle_bytes(keys):
+    """EncryptPoly / AddPoly / SubPoly / MultPoly / MultConstPoly / MakePolyL2 / EvalPoly give the
+    oracle's bytes and metadata for the same injected randomness."""
+    pk, sk, opk, osk = keys
+    rng = random.Random(1)
+
+    def both(v):
+        pt, opt = pk.NewPolyPlaintext(v), opk.new_poly_plaintext(v)
+        assert pt.Coefficients[: pt.Degree] == opt.coefficients and pt.ScaleFactor == opt.scale_factor
+        rs = [rng.randrange(pk.N) for _ in range(pt.Degree)]
+        return pk.EncryptPoly(pt, rs=rs), O.encrypt_poly(opk, opt, rs)
+
+    def same(ct, oct):
+        assert (ct.Degree, ct.ScaleFactor, ct.L2) == (oct.degree, oct.scale_factor, oct.L2)
+        assert ct.CoeffBytes() == O.poly_ct_bytes(opk, oct)
+
+    a, oa = both(9.13)
+    b, ob = both(4.0)
+    c, oc = both(1 / 3)
+    same(a, oa)
+    same(pk.AddPoly(a, b), O.add_poly(opk, oa, ob))          # different scale factors: alignment
+    same(pk.AddPoly(b, c), O.add_poly(opk, ob, oc))
+    same(pk.SubPoly(b, c), O.sub_poly(opk, ob, oc))
+    same(pk.MultPoly(b, c), O.mult_poly(opk, ob, oc))
+    same(pk.MakePolyL2(b), O.make_poly_l2(opk, ob))
+    same(pk.AddPoly(pk.MakePolyL2(b), c), O.add_poly(opk, O.make_poly_l2(opk, ob), oc))  # level promotion
+    for const in (4.12, -2.0, 0.5):
+        same(pk.MultConstPoly(b, const), O.mult_const_poly(opk, ob, const))
+        same(pk.MultConstPoly(pk.MakePolyL2(b), const), O.mult_const_poly(opk, O.make_poly_l2(opk, ob), const))
+    assert pk.EvalPoly(b).C == O.ct_bytes(opk, O.eval_poly(opk, ob))
+    assert "%.1f" % sk.DecryptPoly(pk.MultPoly(b, c), pk).PolyEval() == "1.3"
+
+
+def test_batch_entry_points_equal_per_polynomial_calls(keys):
+    pk, sk, _, _ = keys
+    rng = random.Random(2)
+
+    def make(values, pad_to):
+        polys = []
+        for v in values:
+            pt = pk.NewPolyPlaintext(v)
+            pp = type(pt)(pt.Coefficients[: pt.Degree] + [0] * (pad_to - pt.Degree), pad_to, pt.ScaleFactor, pt.params)
+            polys.append(pk.EncryptPoly(pp, rs=[rng.randrange(pk.N) for _ in range(pad_to)]))
+        data = np.frombuffer(b"".join(x.CoeffBytes() for x in polys), dtype=np.uint8).copy()
+        return polys, PolyCiphertextBatch(data, len(polys), pad_to, polys[0].ScaleFactor, False)
+
+    ints, bi = make([5.0, 7.0], 4)
+    thirds, bt = make([1 / 3, 2 / 3], 3)
+    for pa, ba, pb, bb in ((ints, bi, thirds, bt), (thirds, bt, ints, bi),
+                           ([pk.MakePolyL2(x) for x in ints], pk.MakePolyL2Batch(bi), thirds, bt)):
+        got = pk.AddPolyBatch(ba, bb)
+        exp = [pk.AddPoly(x, y) for x, y in zip(pa, pb)]
+        assert (got.Degree, got.ScaleFactor, got.L2) == (exp[0].Degree, exp[0].ScaleFactor, exp[0].L2)
+        assert bytes(np.asarray(got.data).tobytes()) == b"".join(e.CoeffBytes() for e in exp)
+    prod = pk.MultPolyBatch(bi, bt)
+    assert bytes(prod.data.tobytes()) == b"".join(pk.MultPoly(x, y).CoeffBytes() for x, y in zip(ints, thirds))
+    total = pk.InnerProduct(bi, bt)
+    assert "%.2f" % sk.DecryptPoly(total, pk).PolyEval() == "%.2f" % (5 / 3 + 14 / 3)
+    mc = pk.MultConstPolyBatch(bi, -2.0)
+    assert bytes(mc.data.tobytes()) == b"".join(pk.MultConstPoly(x, -2.0).CoeffBytes() for x in ints)
+    assert pk.EvalPolyBatch(bi).tobytes() == b"".join(pk.EvalPoly(x).C for x in ints)
+    vals, st = sk.DecryptPolyBatch(bi, pk)
+    assert not st.any() and [int(sum(c * 3 ** i for i, c in enumerate(row))) for row in vals] == [5, 7]
+
+
+def test_nondeterministic_mode_matches_oracle(keys):
+    pk0, sk, opk, _ = keys
+    pk = PublicKey(pk0.engine.p, pk0.N, pk0.engine.l, pk0.P, pk0.Q, pk0.MsgSpace, Deterministic=False,
+                   engine=pk0.engine)
+    pk._secret_set = True
+    ond = O.PublicKey(opk.params, opk.P, opk.Q, opk.msg_space, deterministic=False)
+    rng = random.Random(3)
+    r = [rng.randrange(pk.N) for _ in range(8)]
+    a, b = pk.EncryptWithRandomness(3, r[0]), pk.EncryptWithRandomness(2, r[1])
+    oa, ob = O.encrypt_with_randomness(ond, 3, r[0]), O.encrypt_with_randomness(ond, 2, r[1])
+    assert pk.Add(a, b, r=r[2]).C == O.ct_bytes(ond, O.add(ond, oa, ob, r[2]))
+    assert pk.Sub(a, b, r=r[3]).C == O.ct_bytes(ond, O.sub(ond, oa, ob, r[3]))
+    m, om = pk.Mult(a, b, r=r[4]), O.mult(ond, oa, ob, r[4])
+    assert m.C == O.ct_bytes(ond, om)
+    assert pk.MultConst(m, 5, r=r[5]).C == O.ct_bytes(ond, O.mult_const(ond, om, 5, r[5]))
+    assert pk.Add(m, a, r=r[6]).C == O.ct_bytes(ond, O.add(ond, om, oa, r[6]))  # mixed levels
+    s1, s2 = pk.Add(a, b), pk.Add(a, b)
+    assert s1.C != s2.C and sk.Decrypt(s1, pk) == sk.Decrypt(s2, pk) == 5
+
+
+def test_wire_roundtrip(keys):
+    pk, sk, _, _ = keys
+    c = pk.Encrypt(9)
+    back = pk.NewCiphertextFromBytes(c.Bytes())
+    assert (back.C, back.L2) == (c.C, False)
+    pc = pk.MakePolyL2(pk.EncryptPoly(pk.NewPolyPlaintext(9.123)))
+    pb = pk.NewPolyCiphertextFromBytes(pc.Bytes())
+    assert pb.CoeffBytes() == pc.CoeffBytes() and (pb.Degree, pb.ScaleFactor, pb.L2) == (pc.Degree, pc.ScaleFactor, True)
+    assert c.String().startswith("[") and pk.encryptZero().String() == "O\n"
+    with pytest.raises(ValueError):
+        pk.NewPolyCiphertextFromBytes(b"")
