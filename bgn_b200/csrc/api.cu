@@ -1354,8 +1354,8 @@ int bgn_gt_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t
 
 // ---- polynomial-ciphertext helpers ------------------------------------------
 // out[u][jj] = sum_k w[k] * in[u][j_begin + jj - k]   (types.h: PolyConvArgs)
-static void polyconv(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const uint64_t* w, size_t nw, int j_begin,
-                     int j_count, int negate, size_t count, uint8_t* out) {
+static void polyconv(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const unsigned __int128* w, size_t nw,
+                     int j_begin, int j_count, int negate, size_t count, uint8_t* out) {
   size_t nin = count * d, nout = count * (size_t)j_count;
   check_count(nin);
   check_count(nout);
@@ -1371,12 +1371,17 @@ static void polyconv(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, const u
   pa.j_count = j_count;
   pa.negate = negate;
   pa.count = count;
-  uint64_t any = 0;
+  unsigned __int128 any = 0;
   for (size_t k = 0; k < nw; k++) {
-    pa.w[k] = w[k];
+    pa.w[k] = (uint64_t)w[k];
+    pa.whi[k] = (uint64_t)(w[k] >> 64);
     any |= w[k];
   }
-  pa.top_bit = any ? 63 - __builtin_clzll(any) : -1;
+  pa.top_bit = -1;
+  if (any >> 64)
+    pa.top_bit = 127 - __builtin_clzll((uint64_t)(any >> 64));
+  else if (any)
+    pa.top_bit = 63 - __builtin_clzll((uint64_t)any);
   if (is_l2) {
     GtArr A = gt_alloc(c, nin), R = gt_alloc(c, nout);
     gt_from_bytes(c, di, nin, A);
@@ -1417,7 +1422,7 @@ int bgn_multconstpoly_batch(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, 
   return guarded(c, [&] {
     if (!count) return;
     if (!in || !out || !digits || !d || !nd || nd > BGN_CONV_MAXW || d > 4096) throw ArgErr{"bad argument"};
-    uint64_t w[BGN_CONV_MAXW];
+    unsigned __int128 w[BGN_CONV_MAXW];
     for (size_t k = 0; k < nd; k++) w[k] = digits[k];
     polyconv(c, in, d, is_l2, w, nd, 0, (int)(d + nd), negate, count, out);
   });
@@ -1428,12 +1433,15 @@ int bgn_evalpoly_batch(bgn_ctx* c, const uint8_t* in, size_t d, int is_l2, uint3
     if (!count) return;
     if (!in || !out || !d || d > BGN_CONV_MAXW || base < 2) throw ArgErr{"bad argument"};
     // sum_i base^i c_i as a correlation: w[k] = base^(d-1-k), output slot j = d-1 only
-    uint64_t w[BGN_CONV_MAXW];
+    unsigned __int128 w[BGN_CONV_MAXW];
     unsigned __int128 pw = 1;
+    const unsigned __int128 lim = ~(unsigned __int128)0 / base;
     for (size_t i = 0; i < d; i++) {
-      if (pw >> 64) throw ArgErr{"base^(d-1) does not fit 64 bits"};
-      w[d - 1 - i] = (uint64_t)pw;
-      pw *= base;
+      w[d - 1 - i] = pw;
+      if (i + 1 < d) {
+        if (pw > lim) throw ArgErr{"base^(d-1) does not fit 128 bits"};
+        pw *= base;
+      }
     }
     polyconv(c, in, d, is_l2, w, d, (int)d - 1, 1, 0, count, out);
   });

@@ -478,6 +478,9 @@ BGN_DEV void gt_tab_fill_body(const uint32_t* bases, int nwin, uint32_t* tab, si
   }
 }
 
+BGN_DEV bool conv_bit(const PolyConvArgs& a, int k, int b) {
+  return ((b < 64 ? a.w[k] >> b : a.whi[k] >> (b - 64)) & 1) != 0;
+}
 // Integer-weighted correlation (types.h: PolyConvArgs), one thread per output slot; bit-plane
 // Horner over the weights: acc <- 2 acc + sum_{k: bit b of w[k]} in[j-k].  Every addition is a
 // complete mixed addition with an affine input, so no general Jacobian addition is needed.
@@ -496,7 +499,7 @@ BGN_DEV void g1_polyconv_body(const PolyConvArgs& a, size_t id) {
     if (started) G<L>::dbl(X.v(), Y.v(), Z.v(), t0.v(), t1.v(), t2.v(), t3.v());
     for (int k = 0; k < a.nw; k++) {
       int i = j - k;
-      if (i < 0 || i >= a.d || !((a.w[k] >> b) & 1)) continue;
+      if (i < 0 || i >= a.d || !conv_bit(a, k, b)) continue;
       size_t e = u * a.d + i;
       if (a.inf[e]) continue;
       G<L>::madd(X.v(), Y.v(), Z.v(), a.x + e * L, a.y + e * L, false, t0.v(), t1.v(), t2.v(), t3.v());
@@ -522,7 +525,7 @@ BGN_DEV void gt_polyconv_body(const PolyConvArgs& a, size_t id) {
     if (started) FF::sqr2(acc, acc, t0.v(), t1.v());
     for (int k = 0; k < a.nw; k++) {
       int i = j - k;
-      if (i < 0 || i >= a.d || !((a.w[k] >> b) & 1)) continue;
+      if (i < 0 || i >= a.d || !conv_bit(a, k, b)) continue;
       size_t e = u * a.d + i;
       FF::mul2(acc, acc, mke2(const_cast<uint32_t*>(a.x) + e * L, const_cast<uint32_t*>(a.y) + e * L), t0.v(), t1.v(),
                t2.v());

@@ -151,7 +151,8 @@ struct PolyConvArgs {
   int d, nw, j_begin, j_count;
   int top_bit;         // highest set bit over all weights
   int negate;          // NegPoly of the result (negative constant)
-  uint64_t w[BGN_CONV_MAXW];
+  uint64_t w[BGN_CONV_MAXW];    // weights, low 64 bits
+  uint64_t whi[BGN_CONV_MAXW];  // bits 64..127 (EvalPoly of long polynomials: base^(d-1) up to 2^128)
   uint32_t *X, *Y, *Z;
   size_t count;        // polynomials
 };

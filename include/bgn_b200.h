@@ -149,7 +149,8 @@ int bgn_gt_blind_batch(bgn_ctx* ctx, const uint8_t* a, const uint8_t* r_be, size
 int bgn_multconstpoly_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, int is_l2, const uint8_t* digits, size_t nd,
                             int negate, size_t count, uint8_t* out);
 /* EvalPoly (poly.go:58-68): out[u] = sum_i base^i * in[u][i]  (Horner with MultConst/Add in the
- * reference); base = PolyEncodingParams.PolyBase; base^(d-1) must fit 64 bits. */
+ * reference); base = PolyEncodingParams.PolyBase; d <= 64 and base^(d-1) < 2^128
+ * (base 3: any d <= 64). */
 int bgn_evalpoly_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, int is_l2, uint32_t base, size_t count, uint8_t* out);
 /* MakePolyL2 (poly.go:159-163) in deterministic mode: MultPoly(E(1.0), ct) with E(1.0) = [P]:
  * out: count*(d+1) GT elements, out[u][i] = e(in[u][i], P), out[u][d] = identity. */

@@ -59,7 +59,7 @@ CONV_MAXW = 64
 
 class PolyConvArgs(C.Structure):
     _fields_ = [("x", u32p), ("y", u32p), ("inf", u8p), ("d", C.c_int), ("nw", C.c_int), ("j_begin", C.c_int),
-                ("j_count", C.c_int), ("top_bit", C.c_int), ("negate", C.c_int), ("w", C.c_uint64 * CONV_MAXW),
+                ("j_count", C.c_int), ("top_bit", C.c_int), ("negate", C.c_int), ("w", C.c_uint64 * CONV_MAXW), ("whi", C.c_uint64 * CONV_MAXW),
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t)]
 
 
@@ -433,7 +433,8 @@ class Sim:
         a.d, a.nw, a.j_begin, a.j_count, a.negate, a.count = d, len(w), j_begin, j_count, 1 if negate else 0, count
         anyw = 0
         for k, v in enumerate(w):
-            a.w[k] = v
+            a.w[k] = v & 0xFFFFFFFFFFFFFFFF
+            a.whi[k] = v >> 64
             anyw |= v
         a.top_bit = anyw.bit_length() - 1
         X = np.zeros((max(1, nout), self.L), dtype=np.uint32)

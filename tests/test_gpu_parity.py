@@ -702,3 +702,20 @@ def test_addpoly_batch_mixed_shapes():
         assert bytes(got.data.tobytes()) == b"".join(e.CoeffBytes() for e in exp)
     vals = [sk.DecryptPoly(pk.AddPoly(x, y), pk).PolyEval() for x, y in zip(ints, thirds)]
     assert ["%.2f" % v for v in vals] == ["5.33", "12.67", "41.33"]
+
+
+@pytest.mark.parametrize("steps", [7, 33, 1026])
+def test_decrypt_with_giant_steps(steps):
+    """A baby-step table smaller than the message space (the reference's own sizing is
+    ceil(sqrt(T)) + 2 = 1026 entries at T = 2^20, gsbs.go:41-51): the search walks giant steps with
+    the full element (k_gt_pow + k_bsgs_lookup) and must return what the one-probe Lucas path does."""
+    from bgn_b200 import Engine
+    for kb in (128, 512):
+        g = load_golden(kb)
+        e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+        e.set_secret(int(g["q1"], 16), g["msg_space"], baby_steps=steps)
+        for lvl, key in ((True, "decrypt_l2"), (False, "decrypt_l1")):
+            v = g[key]
+            vals, st = e.decrypt_batch(buf(v["in"]), lvl)
+            assert list(st) == v["status"] and [int(x) for x in vals] == v["out"]
+        e.close()

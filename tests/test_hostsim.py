@@ -399,3 +399,17 @@ def test_sim_inv_gcd(kb):
     r1 = np.zeros_like(a)
     assert sim.lib().hs_fp_inv_gcd(S.L, sim.P32(r1), sim.P32(a)) == 0
     assert S.unsoa(r1, 1) == [pow(5, -1, p)]
+
+
+def test_sim_evalpoly_wide_weights():
+    """EvalPoly of a 50-slot polynomial: base^(d-1) = 3^49 needs the weights' upper 64 bits."""
+    import random
+    g, par, S, _ = setup(64)
+    rng = random.Random(50)
+    pk = O.PublicKey(par, S.P, S.Q, g["msg_space"])
+    d = 50
+    cs = [O.encrypt_with_randomness(pk, rng.randrange(3), rng.randrange(par.n)) for _ in range(d)]
+    ct = O.PolyCiphertext(cs, d, 0, False)
+    w = [3 ** (d - 1 - k) for k in range(d)]
+    assert w[0] >> 64
+    assert S.polyconv([c.C for c in cs], d, False, w, d - 1, 1, False, 1) == [O.eval_poly(pk, ct).C]
