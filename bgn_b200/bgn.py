@@ -525,3 +525,8 @@ class PublicKey:
     def InnerProduct(self, u: PolyCiphertextBatch, v: PolyCiphertextBatch) -> PolyCiphertext:
         """sum_i u[i]*v[i] as one L2 polynomial ciphertext (BASELINE.json config 5)."""
         return self.SumPolyBatch(self.MultPolyBatch(u, v))
+
+
+def ComputeDecryptionPreprocessing(pk: PublicKey, sk: SecretKey) -> None:
+    """bgn.go:140-149: the package-level spelling of pk.SetupDecryption(sk)."""
+    pk.SetupDecryption(sk)

@@ -719,3 +719,23 @@ def test_decrypt_with_giant_steps(steps):
             vals, st = e.decrypt_batch(buf(v["in"]), lvl)
             assert list(st) == v["status"] and [int(x) for x in vals] == v["out"]
         e.close()
+
+
+@pytest.mark.parametrize("key_bits", [64, 128])
+def test_keygen_on_gpu(key_bits):
+    """NewKeyGen (bgn.go:65-138): fresh keys whose generators have the right orders (checked with the
+    oracle) and which encrypt / multiply / decrypt correctly -- bgn_test.go's flow on a key made here."""
+    from bgn_b200 import NewKeyGen
+    from oracle import bgn_oracle as O
+    rng = random.Random(key_bits)
+    pk, sk = NewKeyGen(key_bits, 1021, 3, 3, 0.0001, True, rng=rng)
+    par = O.a1_from_string(pk.PairingParams)
+    P, Q = O.g1_from_bytes(pk.P, par), O.g1_from_bytes(pk.Q, par)
+    assert pk.N.bit_length() == key_bits and O.g1_mul(pk.N, P, par.p) is None and O.g1_mul(sk.Key, P, par.p) is not None
+    assert O.g1_mul(sk.Key, Q, par.p) is None
+    pk.SetupDecryption(sk)
+    a, b = pk.Encrypt(12), pk.Encrypt(-5)
+    assert sk.Decrypt(pk.Add(a, b), pk) == 7 and sk.Decrypt(pk.Mult(a, b), pk) == -60
+    c = pk.EncryptPoly(pk.NewPolyPlaintext(9.123))
+    assert "%.1f" % sk.DecryptPoly(c, pk).PolyEval() == "9.1"
+    pk.engine.close()

@@ -152,3 +152,31 @@ def test_wire_roundtrip(keys):
     assert c.String().startswith("[") and pk.encryptZero().String() == "O\n"
     with pytest.raises(ValueError):
         pk.NewPolyCiphertextFromBytes(b"")
+
+
+def test_keygen_host_logic():
+    """NewKeyGen (bgn.go:65-138) with the group operations answered by the oracle-backed stand-in:
+    type-A1 parameters, generator orders, key sizes, the reference's panics, and a round trip."""
+    from bgn_b200 import NewKeyGen
+    from bgn_b200.keygen import a1_params, is_probable_prime, rand_prime
+    rng = random.Random(11)
+    assert [m for m in range(2, 60) if is_probable_prime(m, rng)] == [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43,
+                                                                     47, 53, 59]
+    q = rand_prime(rng, 24)
+    assert q.bit_length() == 24 and q >> 22 == 3 and is_probable_prime(q, rng)
+    pk, sk = NewKeyGen(48, 1021, 3, 3, 0.0001, True, rng=rng, engine_factory=FakeEngine)
+    par = O.a1_from_string(pk.PairingParams)
+    assert pk.N.bit_length() == 48 and pk.N % sk.Key == 0 and par.n == pk.N
+    assert (par.p, par.l) == a1_params(pk.N, rng) == (O.a1_gen(pk.N).p, O.a1_gen(pk.N).l)
+    P, Q = O.g1_from_bytes(pk.P, par), O.g1_from_bytes(pk.Q, par)
+    q1, q2 = sk.Key, pk.N // sk.Key
+    assert O.g1_mul(pk.N, P, par.p) is None and O.g1_mul(q1, P, par.p) is not None and O.g1_mul(q2, P, par.p) is not None
+    assert O.g1_mul(q1, Q, par.p) is None and Q is not None  # Q generates the subgroup of order q1
+    pk.SetupDecryption(sk)
+    assert sk.Decrypt(pk.Mult(pk.Encrypt(-7), pk.Encrypt(6)), pk) == -42
+    with pytest.raises(ValueError, match="divisible by 2"):
+        NewKeyGen(33, 10, rng=rng, engine_factory=FakeEngine)
+    with pytest.raises(ValueError, match=">= 16"):
+        NewKeyGen(8, 10, rng=rng, engine_factory=FakeEngine)
+    with pytest.raises(ValueError, match="Message space"):
+        NewKeyGen(32, 1 << 20, rng=rng, engine_factory=FakeEngine)
