@@ -7,5 +7,6 @@ compute entry point without the built CUDA library raises.
 """
 from .engine import BgnError, Engine, bench_imad_peak  # noqa: F401
 from .bgn import (Ciphertext, DLError, PolyCiphertext, PolyCiphertextBatch, PublicKey, SecretKey)  # noqa: F401
+from .gadgets import DecryptionProof, NewDecryptionProof, ProofOfPlaintextKnowledge  # noqa: F401
 from .keygen import NewKeyGen  # noqa: F401
 from .plaintext import PolyEncodingParams, PolyPlaintext  # noqa: F401

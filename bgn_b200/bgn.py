@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import gobwire
+from . import gadgets, gobwire
 from .engine import Engine
 from .plaintext import (EncodingTable, NewPolyPlaintext, NewUnbalancedPlaintext, PolyEncodingParams, PolyPlaintext)
 
@@ -242,12 +242,34 @@ class PublicKey:
         return NewUnbalancedPlaintext(m, self.PolyEncodingParams, self._table)
 
     # ---------------------------------------------------------------- scalar scheme
+    def _encrypt_big(self, xs: Sequence[int], rs: Sequence[int]) -> bytes:
+        """P^x * Q^r for arbitrary-size x (the reference takes a *big.Int, gadgets_test.go encrypts
+        values below N): x*P as a variable-scalar multiplication of P, then + r*Q through the
+        fixed-base windows of Q.  x and r are reduced mod N, the order of P (Q's order divides it)."""
+        eng, nb = self.engine, self.engine.scalar_bytes
+        P = np.frombuffer(self.P * len(xs), dtype=np.uint8)
+        xp = eng.g1_mulconst_batch(P, eng.scalars_be([x % self.N for x in xs], nb), nb)
+        out = eng.g1_blind_batch(xp, eng.scalars_be([r % self.N for r in rs], nb))
+        return bytes(np.asarray(out).tobytes())
+
     def EncryptWithRandomness(self, x: int, r: int) -> Ciphertext:
         """bgn.go:340-353: C = P^x * Q^r."""
         if abs(x) >= 1 << 63:
-            raise ValueError("plaintext does not fit int64")
+            return Ciphertext(self._encrypt_big([x], [r]), False)
         out = self.engine.encrypt_batch(np.array([x], dtype=np.int64), self.engine.scalars_be([r % self.N]))
         return Ciphertext(out.tobytes(), False)
+
+    # ---------------------------------------------------------------- zero-knowledge gadgets (gadgets.go)
+    def NewProofOfPlaintextKnowledge(self, sk: SecretKey, v: int, z: int, nonce1: Optional[int] = None):
+        return gadgets.new_proof_of_plaintext_knowledge(self, sk, v, z, nonce1)
+
+    def CheckDecryptionProof(self, ct: Ciphertext, proof) -> bool:
+        return gadgets.check_decryption_proofs(self, [ct], [proof])[0]
+
+    def CheckProofOfPlaintextKnoewledge(self, ct: Ciphertext, proof) -> bool:  # the reference's spelling
+        return gadgets.check_proofs_of_plaintext_knowledge(self, [ct], [proof])[0]
+
+    CheckProofOfPlaintextKnowledge = CheckProofOfPlaintextKnoewledge
 
     def Encrypt(self, x: int, r: Optional[int] = None) -> Ciphertext:
         """bgn.go:334-337."""

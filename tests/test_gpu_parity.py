@@ -739,3 +739,27 @@ def test_keygen_on_gpu(key_bits):
     c = pk.EncryptPoly(pk.NewPolyPlaintext(9.123))
     assert "%.1f" % sk.DecryptPoly(c, pk).PolyEval() == "9.1"
     pk.engine.close()
+
+
+def test_gadgets_on_gpu():
+    """gadgets_test.go:8-108 on a key generated here (keyBits=128), values and randomness below N."""
+    from bgn_b200 import NewDecryptionProof, NewKeyGen, gadgets
+    rng = random.Random(31)
+    pk, sk = NewKeyGen(128, 1021, rng=rng)
+    N = pk.N
+    r, v, r2, v2 = (rng.randrange(N) for _ in range(4))
+    ct, ct2 = pk.EncryptWithRandomness(v, r), pk.EncryptWithRandomness(v2, r2)
+    assert pk.CheckDecryptionProof(ct, NewDecryptionProof(v, r))
+    assert not pk.CheckDecryptionProof(ct, NewDecryptionProof(v, r2))
+    assert not pk.CheckDecryptionProof(ct, NewDecryptionProof(r2, r))
+    assert pk.CheckDecryptionProof(pk.Add(ct, ct2), NewDecryptionProof(v + v2, r + r2))
+    good = pk.NewProofOfPlaintextKnowledge(sk, v, r)
+    assert pk.CheckProofOfPlaintextKnoewledge(ct, good)
+    assert not pk.CheckProofOfPlaintextKnoewledge(ct, pk.NewProofOfPlaintextKnowledge(sk, v, r2))
+    assert not pk.CheckProofOfPlaintextKnoewledge(ct, pk.NewProofOfPlaintextKnowledge(sk, r2, r))
+    many = [pk.NewProofOfPlaintextKnowledge(sk, v + i, r + i) for i in range(16)]
+    cts = [p.Ct for p in many]
+    assert gadgets.check_proofs_of_plaintext_knowledge(pk, cts, many) == [True] * 16
+    cts[3], cts[4] = cts[4], cts[3]
+    assert gadgets.check_proofs_of_plaintext_knowledge(pk, cts, many) == [True] * 3 + [False] * 2 + [True] * 11
+    pk.engine.close()

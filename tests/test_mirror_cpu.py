@@ -180,3 +180,37 @@ def test_keygen_host_logic():
         NewKeyGen(8, 10, rng=rng, engine_factory=FakeEngine)
     with pytest.raises(ValueError, match="Message space"):
         NewKeyGen(32, 1 << 20, rng=rng, engine_factory=FakeEngine)
+
+
+def test_gadgets(keys):
+    """gadgets_test.go:8-108: decryption proofs (valid, aggregate, bad) and proofs of plaintext
+    knowledge (valid, bad) with values and randomness below N."""
+    from bgn_b200 import NewDecryptionProof
+    from bgn_b200 import gadgets
+    pk, _, _, _ = keys
+    g = load_golden(64)
+    sk = SecretKey(int(g["q1"], 16), R=0)
+    rng = random.Random(8)
+    N = pk.N
+    r, v, r2, v2 = (rng.randrange(N) for _ in range(4))
+    ct = pk.EncryptWithRandomness(v, r)
+    assert pk.CheckDecryptionProof(ct, NewDecryptionProof(v, r))
+    assert not pk.CheckDecryptionProof(ct, NewDecryptionProof(v, r2))
+    assert not pk.CheckDecryptionProof(ct, NewDecryptionProof(r2, r))
+    ct2 = pk.EncryptWithRandomness(v2, r2)
+    assert pk.CheckDecryptionProof(pk.Add(ct, ct2), NewDecryptionProof(v + v2, r + r2))  # aggregate
+    assert gadgets.check_decryption_proofs(pk, [ct, ct2, ct], [NewDecryptionProof(v, r), NewDecryptionProof(v2, r2),
+                                                                 NewDecryptionProof(v2, r)]) == [True, True, False]
+
+
+def test_proof_of_plaintext_knowledge_on_generated_key():
+    """needs SecretKey.R (Q = P^(R q2)), so the key comes from NewKeyGen"""
+    from bgn_b200 import NewKeyGen
+    rng = random.Random(21)
+    pk, sk = NewKeyGen(48, 1021, rng=rng, engine_factory=FakeEngine)
+    N = pk.N
+    r, v, r2 = (rng.randrange(N) for _ in range(3))
+    ct = pk.EncryptWithRandomness(v, r)
+    assert pk.CheckProofOfPlaintextKnoewledge(ct, pk.NewProofOfPlaintextKnowledge(sk, v, r))
+    assert not pk.CheckProofOfPlaintextKnoewledge(ct, pk.NewProofOfPlaintextKnowledge(sk, v, r2))
+    assert not pk.CheckProofOfPlaintextKnoewledge(ct, pk.NewProofOfPlaintextKnowledge(sk, r2, r))
