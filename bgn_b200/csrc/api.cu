@@ -1155,7 +1155,11 @@ static int gt_pow_impl(bgn_ctx* c, const uint8_t* a, const uint8_t* k_be, size_t
     pa.oim = R.im;
     pa.count = count;
     pa.N = R.N;
-    {
+    if (mode == 1 && c->dec_lucas) {  // fixed exponent q1: a lane pair per element (lucas.cuh: GtPowPair)
+      Timer t(c, "k_gt_pow_pair");
+      c->Co->gt_pow_pair(cfg(c, nblk(2 * count, 64), 64, 0), pa);
+      t.done();
+    } else {
       Timer t(c, "k_gt_pow");
       c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
       t.done();

@@ -23,6 +23,7 @@ void gt_tab_fill(LaunchCfg cfg, const uint32_t* bases, int nwin, uint32_t* tab) 
 }
 void gt_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_gt_polyconv<LL><<<CFG>>>(a); }
 void dec_lucas(LaunchCfg cfg, const DecLucasArgs& a) { k_dec_lucas<LL><<<CFG>>>(a); }
+void gt_pow_pair(LaunchCfg cfg, const GtPowArgs& a) { k_gt_pow_pair<LL><<<CFG>>>(a); }
 cudaError_t miller_fixed_set_smem(size_t smem) {
   return cudaFuncSetAttribute(k_miller_fixed<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
@@ -33,7 +34,7 @@ void miller_record(LaunchCfg cfg, const uint32_t* px, const uint32_t* py, uint32
 }
 const LOpsC ops = {LL,          upload,    gt_blind,
                    gt_tab_bases, gt_tab_fill, gt_polyconv,
-                   dec_lucas,   miller_fixed_set_smem, miller_fixed_smem_bytes,
+                   dec_lucas,   gt_pow_pair, miller_fixed_set_smem, miller_fixed_smem_bytes,
                    miller_fixed, miller_record};
 }  // namespace
 #define BGN_CAT2(a, b) a##b

@@ -661,6 +661,32 @@ void dec_lucas_pair_sim(const DecLucasArgs& a, size_t e) {
 }
 #endif
 
+#ifdef BGN_HOSTSIM
+// CPU simulation of k_gt_pow_pair: both lanes of one pair in lockstep
+template <int L>
+void gt_pow_pair_sim(const GtPowArgs& a, size_t e) {
+  typedef GtPowPair<L> GP;
+  typename GP::State s0, s1;
+  GP::init(s0, a.re + e * L, a.im + e * L, true);
+  GP::init(s1, a.re + e * L, a.im + e * L, true);
+  for (int i = c_pc.exp_bits - 2; i >= 0; i--) {
+    uint32_t t0[L], t1[L];
+    GP::sqr_half(t0, s0, 0);
+    GP::sqr_half(t1, s1, 1);
+    GP::update(s0, t0, t1, 0);
+    GP::update(s1, t1, t0, 1);
+    if ((c_pc.exp[i >> 5] >> (i & 31)) & 1) {
+      GP::mul_half(t0, s0, 0);
+      GP::mul_half(t1, s1, 1);
+      GP::update(s0, t0, t1, 0);
+      GP::update(s1, t1, t0, 1);
+    }
+  }
+  GP::finish(s0, a.ore + e * L, a.oim + e * L, 0);
+  GP::finish(s1, a.ore + e * L, a.oim + e * L, 1);
+}
+#endif
+
 // =========================================================== CUDA wrappers
 #ifndef BGN_HOSTSIM
 #define BGN_KERNEL_1D(NAME, ARGT)                                                   \
@@ -707,6 +733,34 @@ __global__ void __launch_bounds__(64) k_dec_lucas(const __grid_constant__ DecLuc
     LU::update(st, mine, other, b, s);
   }
   if (active && s == 0) LU::finish(st, a, e);
+}
+
+// a^q1 for the fixed exponent c_pc.exp, a lane pair per element (GtPowArgs mode 1 only)
+template <int L>
+__global__ void __launch_bounds__(64) k_gt_pow_pair(const __grid_constant__ GtPowArgs a) {
+  typedef GtPowPair<L> GP;
+  const size_t gid = BGN_GID(size_t);
+  const size_t e = gid >> 1;
+  const int s = (int)(gid & 1);
+  const bool active = e < a.count;
+  const size_t ee = active ? e : 0;
+  typename GP::State st;
+  GP::init(st, a.re + ee * L, a.im + ee * L, active);
+  BGN_UNROLL1
+  for (int i = c_pc.exp_bits - 2; i >= 0; i--) {
+    uint32_t mine[L], other[L];
+    GP::sqr_half(mine, st, s);
+#pragma unroll
+    for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
+    GP::update(st, mine, other, s);
+    if ((c_pc.exp[i >> 5] >> (i & 31)) & 1) {
+      GP::mul_half(mine, st, s);
+#pragma unroll
+      for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
+      GP::update(st, mine, other, s);
+    }
+  }
+  if (active) GP::finish(st, a.ore + e * L, a.oim + e * L, s);
 }
 
 template <int L>

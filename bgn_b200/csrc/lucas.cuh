@@ -152,3 +152,69 @@ struct Lucas {
   BGN_DEV static int nbits() { return c_pc.exp_bits; }
   BGN_DEV static int bit(int i) { return (c_pc.exp[i >> 5] >> (i & 31)) & 1; }
 };
+
+// ---------------------------------------------------------------------------
+// C^q1 as a full F_p^2 element (bgn_gt_pow_secret_batch; the giant-step decrypt), again with a
+// pair of lanes per element: square-and-multiply in F_p^2 whose products split evenly --
+//   squaring   (r0 + r1)(r0 - r1)  |  2 r0 r1                     one product per lane
+//   times a    r0 a0 - r1 a1       |  r0 a1 + r1 a0               two products per lane
+// -- so a lane runs 1 + 2 wt/bits sequential products per exponent bit instead of the 2 + 3 wt/bits
+// of one thread, and both lanes execute the same instruction stream (operands picked by selects,
+// results swapped with one shuffle per limb).  The exponent is a key constant: uniform control flow.
+// ---------------------------------------------------------------------------
+template <int L>
+struct GtPowPair {
+  typedef Fp<L> P;
+  typedef Lucas<L> LU;
+  struct State {
+    uint32_t r0[L], r1[L];  // running power, both coordinates in both lanes (relaxed range)
+    uint32_t a0[L], a1[L];  // the base
+  };
+
+  BGN_DEV static void init(State& st, const uint32_t* re, const uint32_t* im, bool active) {
+    if (active) {
+      ld<L>(st.a0, re);
+      ld<L>(st.a1, im);
+    } else {
+      BGN_SETB(st.a0, 0.0);
+      BGN_SETB(st.a1, 0.0);
+      BGN_UNROLL
+      for (int j = 0; j < L; j++) st.a0[j] = st.a1[j] = 0;
+    }
+    LU::sel(st.r0, true, st.a0, st.a0);
+    LU::sel(st.r1, true, st.a1, st.a1);
+  }
+  // this lane's half of r^2
+  BGN_DEV static void sqr_half(uint32_t (&t)[L], const State& st, int s) {
+    uint32_t sum[L], dif[L], x[L], y[L], d[L];
+    P::addn(sum, st.r0, st.r1);
+    P::subk(dif, st.r0, st.r1, c_fc.p8, 8);
+    LU::sel(x, s == 0, sum, st.r0);
+    LU::sel(y, s == 0, dif, st.r1);
+    P::mul(t, x, y);
+    P::addn(d, t, t);
+    LU::sel(t, s == 0, t, d);  // lane 1 holds 2 r0 r1
+  }
+  // this lane's half of r * a
+  BGN_DEV static void mul_half(uint32_t (&t)[L], const State& st, int s) {
+    uint32_t x[L], y[L], u[L], v[L], dif[L], sum[L];
+    LU::sel(x, s == 0, st.a0, st.a1);
+    LU::sel(y, s == 0, st.a1, st.a0);
+    P::mul(u, st.r0, x);
+    P::mul(v, st.r1, y);
+    P::subk(dif, u, v, c_fc.p4, 4);
+    P::addn(sum, u, v);
+    LU::sel(t, s == 0, dif, sum);
+  }
+  BGN_DEV static void update(State& st, const uint32_t (&mine)[L], const uint32_t (&other)[L], int s) {
+    LU::sel(st.r0, s == 0, mine, other);
+    LU::sel(st.r1, s == 0, other, mine);
+  }
+  // lane s stores its coordinate (re for lane 0, im for lane 1), back in [0, 2p)
+  BGN_DEV static void finish(const State& S, uint32_t* ore, uint32_t* oim, int s) {
+    uint32_t t[L];
+    LU::sel(t, s == 0, S.r0, S.r1);
+    P::norm2p(t, t);
+    st<L>(s == 0 ? ore : oim, t);
+  }
+};

@@ -44,6 +44,7 @@ struct LOpsC {
   void (*gt_tab_fill)(LaunchCfg, const uint32_t* bases, int nwin, uint32_t* tab);
   void (*gt_polyconv)(LaunchCfg, const PolyConvArgs&);
   void (*dec_lucas)(LaunchCfg, const DecLucasArgs&);
+  void (*gt_pow_pair)(LaunchCfg, const GtPowArgs&);
   cudaError_t (*miller_fixed_set_smem)(size_t smem);
   size_t (*miller_fixed_smem_bytes)(int nt);
   void (*miller_fixed)(LaunchCfg, const MillerFixedArgs&);

@@ -150,6 +150,7 @@ int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* li
   FOR_L(L, MillerFixed<LL>::record(px, py, lines))
 }
 int hs_miller_nsteps(int L) { FOR_L(L, return MillerFixed<LL>::nsteps(c_pc)) }
+int hs_gt_pow_pair(int L, const GtPowArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_pow_pair_sim<LL>(*a, e)) }
 int hs_dec_lucas(int L, const DecLucasArgs* a) {
   FOR_L(L, for (size_t e = 0; e < a->count; e++) dec_lucas_pair_sim<LL>(*a, e))
 }

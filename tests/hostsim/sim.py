@@ -386,7 +386,8 @@ class Sim:
         assert lib().hs_gt_mul(self.L, C.byref(a)) == 0
         return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
-    def gt_pow(self, A, mode, exps=None, ebytes=0):
+    def gt_pow(self, A, mode, exps=None, ebytes=0, pair=False):
+        """pair=True: k_gt_pow_pair (fixed exponent, a lane pair per element)"""
         count = len(A)
         are, aim = self.gt_arrays(A)
         ore, oim = np.zeros_like(are), np.zeros_like(are)
@@ -395,7 +396,12 @@ class Sim:
             eb = np.frombuffer(b"".join(int(k).to_bytes(ebytes, "big") for k in exps), dtype=np.uint8).copy()
             ep = P8(eb)
         a = GtPowArgs(P32(are), P32(aim), count, ep, ebytes, mode, P32(ore), P32(oim), count, count)
-        assert lib().hs_gt_pow(self.L, C.byref(a)) == 0
+        if pair:
+            lib().hs_track_array(P32(are), C.c_size_t(count), self.L, C.c_double(2.0))
+            lib().hs_track_array(P32(aim), C.c_size_t(count), self.L, C.c_double(2.0))
+            assert mode == 1 and lib().hs_gt_pow_pair(self.L, C.byref(a)) == 0
+        else:
+            assert lib().hs_gt_pow(self.L, C.byref(a)) == 0
         return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
     def gt_reduce(self, vals, nterms, ncoeff, G):

@@ -132,6 +132,7 @@ def test_sim_decrypt(kb):
     v = g["decrypt_l2"]
     csk = S.gt_pow(gts(par, v["in"]), 1)  # C^q1
     assert csk == gts(par, v["csk"])
+    assert S.gt_pow(gts(par, v["in"]), 1, pair=True) == csk  # the lane-pair kernel
     gsk = O.fp2_pow(O.pairing(S.P, S.P, par), int(g["q1"], 16), par.p)
     for S_steps in (None, 7):  # the reference-sized table and a deliberately tiny one
         S.bsgs_setup(gsk, g["msg_space"], S_steps)
