@@ -88,3 +88,32 @@ def test_public_key_roundtrip():
     assert names == ["publicKeyWrapper"]
     # Deterministic=false is a zero value: omitted on the wire, false after decoding
     assert G.decode_public_key(G.encode_public_key(b"a", b"b", b"c", 5, 7, "x", False, 3, 3, 0.5))["Deterministic"] is False
+
+
+def test_fuzz_roundtrips():
+    """random envelopes (lengths around the 1-byte/multi-byte uint boundary, empty slices, large ints)"""
+    from hypothesis import given, settings, strategies as st
+
+    blob = st.binary(min_size=0, max_size=300)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(blob, max_size=12), st.integers(0, 1 << 40), st.integers(-(1 << 40), 1 << 40), st.booleans())
+    def poly(coeffs, deg, sf, l2):
+        assert G.decode_poly_ciphertext(G.encode_poly_ciphertext(coeffs, deg, sf, l2)) == (coeffs, deg, sf, l2)
+
+    @settings(max_examples=150, deadline=None)
+    @given(blob, st.booleans())
+    def single(c, l2):
+        assert G.decode_ciphertext(G.encode_ciphertext(c, l2)) == (c, l2)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 1 << 1030), st.integers(0, 1 << 64), st.text(max_size=40), st.booleans(),
+           st.integers(0, 100), st.floats(allow_nan=False, allow_infinity=False))
+    def key(n, t, params, det, base, prec):
+        w = G.decode_public_key(G.encode_public_key(b"g", b"p", b"q", n, t, params, det, base, base + 1, prec))
+        assert (w["N"], w["MsgSpace"], w["PairingParams"], w["Deterministic"], w["PolyBase"], w["FPScaleBase"],
+                w["FPPrecision"]) == (n, t, params, det, base, base + 1, prec)
+
+    poly()
+    single()
+    key()
