@@ -16,6 +16,8 @@
 package main
 
 import (
+	"bytes"
+	"encoding/gob"
 	"encoding/hex"
 	"encoding/json"
 	"fmt"
@@ -27,6 +29,26 @@ import (
 )
 
 type obj = map[string]interface{}
+
+// the reference's wire structs (ciphertext.go:17-20, 33-38), restated so that this tool can emit the
+// gob envelopes bgn_b200/gobwire.py reads and writes
+type ciphertextWrapper struct {
+	CBytes []byte
+	L2     bool
+}
+
+type polyCiphertextWrapper struct {
+	CoeffBytes  [][]byte
+	Degree      int
+	ScaleFactor int
+	L2          bool
+}
+
+func gobHex(v interface{}) string {
+	var buf bytes.Buffer
+	die(gob.NewEncoder(&buf).Encode(v))
+	return hex.EncodeToString(buf.Bytes())
+}
 
 var pairing *pbc.Pairing
 var elemBytes int
@@ -225,6 +247,19 @@ func main() {
 			res[i] = gthex(pairing.NewGT().Mul(gt(a[i]), h))
 		}
 		out["gt_blind"] = obj{"out": res}
+	}
+	{ // gob envelopes made by Go itself (ciphertext.go:76-116): pins bgn_b200/gobwire.py
+		v := sec("multpoly")
+		c1 := strs(v["c1"])
+		coeffs := make([][]byte, len(c1))
+		for i := range c1 {
+			coeffs[i] = unhex(c1[i])
+		}
+		out["gob"] = obj{
+			"ciphertext_l1":   gobHex(ciphertextWrapper{CBytes: coeffs[0], L2: false}),
+			"ciphertext_l2":   gobHex(ciphertextWrapper{CBytes: unhex(strs(sec("pair")["out"])[0]), L2: true}),
+			"poly_ciphertext": gobHex(polyCiphertextWrapper{CoeffBytes: coeffs, Degree: len(coeffs), ScaleFactor: 2, L2: false}),
+		}
 	}
 	enc, err := json.MarshalIndent(out, "", " ")
 	die(err)
