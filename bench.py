@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 D1 = D2 = 11
 KEY_BITS = 512
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_miller<17> launch over 3404 units (one full
-# wave), from the `ncu --set full` capture summarised in profiles/r01_miller_v18_ncu.txt
-NCU_DRAM_BYTES_PER_UNIT = (10848256 + 256) / 3404.0
+# wave), from the `ncu --set full` capture summarised in profiles/r01_miller_v20_ncu.txt
+NCU_DRAM_BYTES_PER_UNIT = (11356928 + 256) / 3404.0
 METRIC = "pairings/s"
 WORKLOAD = "keyBits=512 batched EMult (MultPoly) of 2^14 L1 poly-ciphertext pairs, d1=d2=11 (121 pairings/EMult)"
 
@@ -366,7 +366,7 @@ def run_ours(args):
            "rerandomize_l2_per_s": sum_over_ranks(n_dec / (bl2_ms * 1e-3)),
            "decrypt_all_found": not bool(dec["s"].any().item()),
            "note": "keyBits=512, per-call device time incl. (de)serialisation kernels; Encrypt: x in {-1,0,1}, "
-                   "512-bit r; Decrypt: GT^q1 + table lookup over T=2^20; summed over ranks"}
+                   "512-bit r (16-bit windows of Q unless stated); Decrypt: trace of C^q1 by a Lucas ladder + one table probe over T=2^20 (level 1: pairing with P first); summed over ranks"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
