@@ -94,7 +94,9 @@ def miller_fixed_products(p: int, n: int, l: int) -> int:
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     full = products_per_modmul(L)
     line = (2 * full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 5 * full
-    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1)) * full
+    # final exponentiation of one slot; its inversion is the binary GCD (no products) + 2 to fix the form
+    fexp = final_exp_modmuls(p, l, L, 1, 1) - fermat_inv_modmuls(p, L) + 2
+    return (D + A) * line + ((D - 1) * 2 + fexp) * full
 
 
 def canonical_pairing_modmuls(n: int, l: int) -> int:
