@@ -196,17 +196,17 @@ struct F {
   // inv(a R) = a^-1 R^-1 as an integer, times R^3 (= r2 * r2 / R) in a Montgomery product = a^-1 R.
   // r may alias a.  in: a < 2p.  out: r < 2p.
   // RELAXED: the operand may be anything below 8p (the fused routines' range)
-  template <bool RELAXED = false>
+  template <bool RELAXED = false, int ES = 1>
   BGN_DEVNI static void inv_gcd(E r, const uint32_t* a) {
     uint32_t x[L], y[L], r2[L], r3[L];
-    ld<L>(x, a);
+    ld<L, ES>(x, a);
     if (RELAXED) P::norm2p(x, x);
     P::canon(x, x);
     P::inv_bgcd(y, x);
     ld<L>(r2, c_fc.r2);
     P::mul(r3, r2, r2);
     P::mul(x, y, r3);
-    st<L>(r, x);
+    st<L, ES>(r, x);
   }
 
   // ---------------- F_p^2 = F_p[i]/(i^2+1), three-address code ----------------

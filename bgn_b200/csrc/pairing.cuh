@@ -242,7 +242,7 @@ struct MillerTeam {
   }
 
   // Final exponentiation of the <= 2 slots this thread owns, (conj(f)^2 / N(f))^l, with fused
-  // routines (fused.cuh) and ONE Fermat inversion per thread: a thread that owns two slots inverts
+  // routines (fused.cuh) and ONE inversion per thread: a thread that owns two slots inverts
   // N0 N1 and recovers both inverses with three products (Montgomery's trick).  The thread's
   // Miller point and line slots are dead by now and serve as scratch.
   BGN_DEV void finalize() {
@@ -254,13 +254,20 @@ struct MillerTeam {
     E n0 = slot(tid, S_X), n1 = slot(tid, S_Y), w = slot(tid, S_Z), i0 = slot(tid, S_CR), i1 = slot(tid, S_AR);
     if (own0) MA::fe_prepare(f0r, f0i, n0);
     if (own1) MA::fe_prepare(f1r, f1i, n1);
+    // the inversion is the binary GCD of arith.cuh (ALU pipe), not a Fermat power: measured 610.0 ->
+    // 597.2 ms for the 2^14-pair batch (BGN_MILLER_FERMAT_INV restores the power)
+#ifdef BGN_MILLER_FERMAT_INV
+#define BGN_TEAM_INV(r, a) MA::fp_inv(r, a)
+#else
+#define BGN_TEAM_INV(r, a) FF::template inv_gcd<true, ES>(r, a)
+#endif
     if (own1) {
       MA::fp_mul(w, n0, n1);
-      MA::fp_inv(w, w);
+      BGN_TEAM_INV(w, w);
       MA::fp_mul(i0, w, n1);
       MA::fp_mul(i1, w, n0);
     } else if (own0) {
-      MA::fp_inv(i0, n0);
+      BGN_TEAM_INV(i0, n0);
     }
     for (int s = 0; s < 2; s++) {
       if (!(s ? own1 : own0)) continue;
@@ -393,8 +400,7 @@ struct MillerFixed {
     // final exponentiation (conj(f)^2 / N(f))^l, as MillerTeam::finalize for one slot
     E n0 = ex, i0 = ey, g0 = slot(S_G0), g1 = slot(S_G1);
     MA::fe_prepare(fr, fi, n0);
-    // 1 / N(f) by the binary GCD (ALU pipe, ~1/7 of the Fermat power's dependent latency); the
-    // Miller team kernel keeps MA::fp_inv, where one inversion serves ~48 000 products
+    // 1 / N(f) by the binary GCD (ALU pipe, ~1/7 of the Fermat power's dependent latency)
     FF::template inv_gcd<true>(i0, n0);
     MA::scale2(fr, fi, i0);
     FF::copy(g0, fr);

@@ -40,13 +40,16 @@ def fermat_inv_modmuls(p: int, L: int) -> int:
     return (e.bit_length() - 1) + (bin(e).count("1") - 1)
 
 
+GCD_INV_MODMULS = 2  # F<L>::inv_gcd: the binary GCD itself multiplies nothing; R^3 and the form fix are 2 products
+
+
 def final_exp_modmuls(p: int, l: int, L: int, nslots: int = 1, team: int = 1) -> int:
     """MillerTeam::finalize for one unit: per slot conj(f)^2 and N(f) (3), g = conj(f)^2 / N (2) and
-    g^l; one Fermat inversion per THREAD that owns a slot (thread t owns slots t and t + team), a
-    thread with two slots adds 3 products (Montgomery's trick)."""
+    g^l; one inversion (binary GCD) per THREAD that owns a slot (thread t owns slots t and t + team),
+    a thread with two slots adds 3 products (Montgomery's trick)."""
     pow_l = 2 * (l.bit_length() - 1) + 3 * (bin(l).count("1") - 1)
     owners = min(team, nslots)
-    return nslots * (5 + pow_l) + owners * fermat_inv_modmuls(p, L) + (nslots - owners) * 3
+    return nslots * (5 + pow_l) + owners * GCD_INV_MODMULS + (nslots - owners) * 3
 
 
 def line_lazy(L: int) -> bool:
@@ -94,9 +97,7 @@ def miller_fixed_products(p: int, n: int, l: int) -> int:
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     full = products_per_modmul(L)
     line = (2 * full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 5 * full
-    # final exponentiation of one slot; its inversion is the binary GCD (no products) + 2 to fix the form
-    fexp = final_exp_modmuls(p, l, L, 1, 1) - fermat_inv_modmuls(p, L) + 2
-    return (D + A) * line + ((D - 1) * 2 + fexp) * full
+    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1)) * full
 
 
 def canonical_pairing_modmuls(n: int, l: int) -> int:
