@@ -156,12 +156,13 @@ def main():
           workmodel.dec_lucas_modmuls(q1) if dom == "k_dec_lucas" else workmodel.gt_pow_modmuls(q1), dom)
 
     # ---- non-deterministic mode: re-randomisation of level-1 / level-2 coefficients
-    nb = 1 << 18
+    nb = max(nd, min(1 << 18, cnt) // nd * nd)
     rb = torch.randint(0, 256, (nb, SB), generator=gen, device=dev, dtype=torch.uint8)
     rb[:, 0] &= 0x3F
     rb = rb.reshape(-1)
     ob = torch.empty(nb * EB, dtype=torch.uint8, device=dev)
-    t, k = timed(lambda: eng.g1_blind_batch(out[: nb * EB], rb, out=ob))
+    src1 = out[: nb * EB] if nb <= cnt else out.repeat((nb + cnt - 1) // cnt)[: nb * EB]
+    t, k = timed(lambda: eng.g1_blind_batch(src1, rb, out=ob))
     entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k, workmodel.encrypt_modmuls(n, SB, args.enc_window, 0.0) + 11,
           "k_encrypt")
     l2b = l2.repeat(nb // nd)
