@@ -133,6 +133,7 @@ struct bgn_ctx {
   int enc_window = 16;         // 16; 8 stays with the small table, 24 builds the 50 GB one (BGN_ENC_WINDOW)
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
+  bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
   bool has_secret = false;
@@ -345,30 +346,44 @@ void commit_out(bgn_ctx* c, const OutBuf& o) {
 }
 
 // ---- kernel wrappers
+// shared memory of the (de)serialisation kernels: the block's elements in byte format, word-padded
+size_t io_smem(bgn_ctx* c, int nt) { return ((size_t)nt * 2 * c->B + 15) & ~(size_t)15; }
 void g1_from_bytes(bgn_ctx* c, const uint8_t* d_in, size_t count, const G1Arr& a) {
   if (!count) return;
   Timer t(c, "k_g1_from_bytes");
-  c->Bo->g1_from_bytes(cfg(c, nblk(count, 128), 128, 0), d_in, c->B, count, a.x, a.y, a.inf, a.N);
+  c->Bo->g1_from_bytes(cfg(c, nblk(count, 128), 128, io_smem(c, 128)), d_in, c->B, count, a.x, a.y, a.inf, a.N);
   t.done();
 }
 void g1_to_bytes(bgn_ctx* c, const G1Arr& a, size_t count, uint8_t* d_out) {
   if (!count) return;
   Timer t(c, "k_g1_to_bytes");
-  c->Bo->g1_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.x, a.y, a.inf, a.N, count, d_out, c->B);
+  c->Bo->g1_to_bytes(cfg(c, nblk(count, 128), 128, io_smem(c, 128)), a.x, a.y, a.inf, a.N, count, d_out, c->B);
   t.done();
 }
 void gt_from_bytes(bgn_ctx* c, const uint8_t* d_in, size_t count, const GtArr& a) {
   if (!count) return;
   Timer t(c, "k_fp2_from_bytes");
-  c->A->fp2_from_bytes(cfg(c, nblk(count, 128), 128, 0), d_in, c->B, count, a.re, a.im, a.N);
+  c->A->fp2_from_bytes(cfg(c, nblk(count, 128), 128, io_smem(c, 128)), d_in, c->B, count, a.re, a.im, a.N);
   t.done();
 }
 // grp > 0: the output is polynomials of grp + pad slots, the pad slots written as the GT identity
 void gt_to_bytes(bgn_ctx* c, const GtArr& a, size_t count, uint8_t* d_out, int grp = 0, int pad = 0) {
   if (!count) return;
   Timer t(c, "k_fp2_to_bytes");
-  c->A->fp2_to_bytes(cfg(c, nblk(count, 128), 128, 0), a.re, a.im, a.N, count, d_out, c->B, grp, pad);
+  c->A->fp2_to_bytes(cfg(c, nblk(count, 128), 128, io_smem(c, 128)), a.re, a.im, a.N, count, d_out, c->B, grp, pad);
   t.done();
+}
+
+// Threads for a kernel whose threads share one inversion among their elements (k_normalize,
+// k_g1_affadd).  The binary-GCD inversion costs about as much as 85 products and each element ~6, so
+// ~10 elements per thread already amortise it; fewer elements per thread mean more threads, which is
+// what a latency-bound chain needs.  Aim at two warps per scheduler (148 x 256 threads), between 8 and
+// 64 elements per thread; small batches favour parallelism over shared inversions.
+size_t shared_inversion_threads(bgn_ctx* c, size_t count) {
+  size_t per = std::min<size_t>(64, std::max<size_t>(c->norm_per_thread, (count + c->norm_threads - 1) / c->norm_threads));
+  size_t G = (count + per - 1) / per;
+  if (G < 4096) G = std::min<size_t>(count, 4096);
+  return G;
 }
 
 // Jacobian -> affine; output either SoA (G1Arr) or AoS table
@@ -382,13 +397,7 @@ void normalize(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch, uin
   a.scratch = scratch;
   a.count = count;
   a.N = j.N;
-  // elements per thread (= per inversion): the binary-GCD inversion costs about as much as 85
-  // products and each element 6, so ~10 elements per thread already amortise it; fewer elements
-  // per thread mean more threads, which is what a latency-bound chain needs.  Aim at two warps per
-  // scheduler (148 x 256 threads), between 8 and 64 elements per thread.
-  size_t per = std::min<size_t>(64, std::max<size_t>(c->norm_per_thread, (count + c->norm_threads - 1) / c->norm_threads));
-  size_t G = (count + per - 1) / per;
-  if (G < 4096) G = std::min<size_t>(count, 4096);  // small batches: favour parallelism over shared inversions
+  size_t G = shared_inversion_threads(c, count);
   a.G = (int)G;
   a.ox = ox;
   a.oy = oy;
@@ -743,6 +752,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* tl = getenv("BGN_MILLER_TAIL")) c->miller_tail = atoi(tl);
     if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : (atoi(ew) == 24 ? 24 : 16);
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
+    if (const char* af = getenv("BGN_AFFINE_ADD")) c->affine_add = atoi(af) != 0;
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
     if (const char* nt = getenv("BGN_NORM_THREADS")) c->norm_threads = std::max(128, atoi(nt));
     if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
@@ -1011,6 +1021,31 @@ static int g1_binop(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count
     }
     const uint8_t* db = stage_in(c, b, count * 2 * c->B);
     g1_from_bytes(c, db, count, Bv);
+    if (c->affine_add) {
+      // affine + affine -> affine with one binary-GCD inversion per thread (types.h: G1AffAddArgs)
+      uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+      G1AffAddArgs aa;
+      aa.x1 = A.x;
+      aa.y1 = A.y;
+      aa.inf1 = A.inf;
+      aa.x2 = Bv.x;
+      aa.y2 = Bv.y;
+      aa.inf2 = Bv.inf;
+      aa.bcast1 = neg_only;
+      aa.subtract = subtract;
+      aa.ox = R.x;
+      aa.oy = R.y;
+      aa.oinf = R.inf;
+      aa.scratch = scratch;
+      aa.count = count;
+      aa.G = (int)shared_inversion_threads(c, count);
+      Timer t(c, "k_g1_affadd");
+      c->Bo->g1_affadd(cfg(c, nblk(aa.G, 128), 128, 0), aa);
+      t.done();
+      g1_to_bytes(c, R, count, ob.dev);
+      commit_out(c, ob);
+      return;
+    }
     JacArr j = jac_alloc(c, count);
     uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
     G1AddArgs ga;

@@ -38,8 +38,9 @@ void tabw_fill(LaunchCfg cfg, const uint32_t* tab8, int nwin8, int wb, uint32_t*
   k_tabw_fill<LL><<<CFG>>>(tab8, nwin8, wb, X, Y, Z, first, nent);
 }
 void g1_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_g1_polyconv<LL><<<CFG>>>(a); }
+void g1_affadd(LaunchCfg cfg, const G1AffAddArgs& a) { k_g1_affadd<LL><<<CFG>>>(a); }
 const LOpsB ops = {LL,     upload,    g1_from_bytes, g1_to_bytes, encrypt,    normalize,
-                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tabw_fill,  g1_polyconv};
+                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tabw_fill,  g1_polyconv, g1_affadd};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

@@ -259,6 +259,89 @@ BGN_DEV void g1_add_body(const G1AddArgs& a, size_t e) {
   FF::copy(a.Z + (size_t)(e) * L, Z.v());
 }
 
+// EAdd / ESub in affine coordinates with a shared inversion (types.h: G1AffAddArgs).
+// den(e): the denominator of the chord / tangent slope of element e, or 1 where no slope is needed
+// (an operand is O, the operands are inverse to each other, or a 2-torsion point is doubled).
+// kind: 0 = result O, 1 = copy operand 2 (signed), 2 = copy operand 1, 3 = chord, 4 = tangent.
+template <int L>
+BGN_DEV int g1_affadd_den(const G1AffAddArgs& a, size_t e, E den, E b2y, E t) {
+  typedef F<L> FF;
+  const size_t e1 = a.bcast1 ? 0 : e;
+  const bool i1 = a.inf1[e1] != 0, i2 = a.inf2[e] != 0;
+  FF::set_one(den);
+  if (!i2) {
+    FF::copy(b2y, a.y2 + e * L);
+    if (a.subtract) FF::neg(b2y, b2y);
+  }
+  if (i1) return i2 ? 0 : 1;
+  if (i2) return 2;
+  FF::sub(t, a.x2 + e * L, a.x1 + e1 * L);
+  if (!FF::is_zero(t)) {
+    FF::copy(den, t);
+    return 3;
+  }
+  if (FF::equal(a.y1 + e1 * L, b2y) && !FF::is_zero(b2y)) {
+    FF::add(den, b2y, b2y);
+    return 4;
+  }
+  return 0;
+}
+template <int L>
+BGN_DEV void g1_affadd_body(const G1AffAddArgs& a, size_t g) {
+  typedef F<L> FF;
+  if (g >= (size_t)a.G || g >= a.count) return;
+  Loc<L> acc, den, b2y, t, lam, x3, y3;
+  FF::set_one(acc.v());
+  for (size_t e = g; e < a.count; e += a.G) {
+    g1_affadd_den<L>(a, e, den.v(), b2y.v(), t.v());
+    FF::copy(a.scratch + e * L, acc.v());
+    FF::mul(acc.v(), acc.v(), den.v());
+  }
+  FF::inv_gcd(acc.v(), acc.v());
+  const size_t last = ((a.count - 1 - g) / a.G) * a.G + g;
+  for (size_t e = last;; e -= a.G) {
+    const size_t e1 = a.bcast1 ? 0 : e;
+    const int kind = g1_affadd_den<L>(a, e, den.v(), b2y.v(), t.v());
+    FF::mul(lam.v(), acc.v(), a.scratch + e * L);  // 1 / den(e)
+    FF::mul(acc.v(), acc.v(), den.v());            // drop den(e) from the running inverse
+    uint32_t* ox = a.ox + e * L;
+    uint32_t* oy = a.oy + e * L;
+    a.oinf[e] = kind == 0 ? 1 : 0;
+    if (kind == 0) {
+      FF::set_zero(ox);
+      FF::set_zero(oy);
+    } else if (kind == 1) {
+      FF::copy(ox, a.x2 + e * L);
+      FF::copy(oy, b2y.v());
+    } else if (kind == 2) {
+      FF::copy(ox, a.x1 + e1 * L);
+      FF::copy(oy, a.y1 + e1 * L);
+    } else {
+      const uint32_t* x1 = a.x1 + e1 * L;
+      const uint32_t* y1 = a.y1 + e1 * L;
+      if (kind == 3) {
+        FF::sub(t.v(), b2y.v(), y1);  // y2 - y1
+      } else {
+        FF::sqr(t.v(), x1);           // 3 x1^2 + 1  (curve y^2 = x^3 + x)
+        FF::add(x3.v(), t.v(), t.v());
+        FF::add(t.v(), x3.v(), t.v());
+        FF::set_one(x3.v());
+        FF::add(t.v(), t.v(), x3.v());
+      }
+      FF::mul(lam.v(), lam.v(), t.v());  // slope
+      FF::sqr(x3.v(), lam.v());
+      FF::sub(x3.v(), x3.v(), x1);
+      FF::sub(x3.v(), x3.v(), kind == 3 ? a.x2 + e * L : x1);
+      FF::sub(t.v(), x1, x3.v());
+      FF::mul(y3.v(), lam.v(), t.v());
+      FF::sub(y3.v(), y3.v(), y1);
+      FF::copy(ox, x3.v());
+      FF::copy(oy, y3.v());
+    }
+    if (e < (size_t)a.G) break;
+  }
+}
+
 // MultConst on L1: k*C, per-element big-endian scalar (bgn.go:258)
 template <int L>
 BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
@@ -698,6 +781,7 @@ BGN_KERNEL_1D(encrypt, EncArgs)
 BGN_KERNEL_1D(normalize, NormArgs)
 BGN_KERNEL_1D(g1_add, G1AddArgs)
 BGN_KERNEL_1D(g1_mulvar, G1MulArgs)
+BGN_KERNEL_1D(g1_affadd, G1AffAddArgs)
 BGN_KERNEL_1D(gt_mul, GtBinArgs)
 BGN_KERNEL_1D(gt_pow, GtPowArgs)
 BGN_KERNEL_1D(bsgs_build, BsgsBuildArgs)
@@ -763,25 +847,79 @@ __global__ void __launch_bounds__(64) k_gt_pow_pair(const __grid_constant__ GtPo
   if (active) GP::finish(st, a.ore + e * L, a.oim + e * L, s);
 }
 
+// (De)serialisation kernels: a block stages its elements' bytes in shared memory so that global
+// memory sees whole 32-bit words at consecutive addresses (the byte format has an odd element size,
+// 2B = 130 at 512 bit: one thread per element touching its bytes directly is a stride-130 byte
+// access, 32 sectors per warp instruction).  Block b owns elements [b*nt, (b+1)*nt); its byte range
+// starts at b*nt*2B, a multiple of 4 for every block size that is a multiple of 2.
+BGN_DEV void stage_bytes_in(uint8_t* sm, const uint8_t* g, size_t nbytes) {
+  // g is 4-byte aligned when the caller's buffer is (cudaMalloc / arena / torch); fall back to bytes otherwise
+  if ((reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(sm);
+    for (size_t i = threadIdx.x; i < nbytes / 4; i += blockDim.x) sw[i] = gw[i];
+    for (size_t i = (nbytes & ~(size_t)3) + threadIdx.x; i < nbytes; i += blockDim.x) sm[i] = g[i];
+  } else {
+    for (size_t i = threadIdx.x; i < nbytes; i += blockDim.x) sm[i] = g[i];
+  }
+}
+BGN_DEV void stage_bytes_out(uint8_t* g, const uint8_t* sm, size_t nbytes) {
+  if ((reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+    uint32_t* gw = reinterpret_cast<uint32_t*>(g);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm);
+    for (size_t i = threadIdx.x; i < nbytes / 4; i += blockDim.x) gw[i] = sw[i];
+    for (size_t i = (nbytes & ~(size_t)3) + threadIdx.x; i < nbytes; i += blockDim.x) g[i] = sm[i];
+  } else {
+    for (size_t i = threadIdx.x; i < nbytes; i += blockDim.x) g[i] = sm[i];
+  }
+}
+// elements of this block and their first index
+BGN_DEV size_t block_first() { return (size_t)blockIdx.x * blockDim.x; }
+BGN_DEV size_t block_count(size_t count) {
+  size_t first = block_first();
+  return first >= count ? 0 : (count - first < blockDim.x ? count - first : blockDim.x);
+}
+
 template <int L>
 __global__ void k_g1_from_bytes(const uint8_t* __restrict__ in, int B, size_t count, uint32_t* x, uint32_t* y,
                                 uint8_t* inf, size_t N) {
-  g1_from_bytes_body<L>(in, B, count, x, y, inf, N, BGN_GID(size_t));
+  extern __shared__ __align__(16) uint8_t smem_io[];
+  const size_t first = block_first(), n = block_count(count);
+  stage_bytes_in(smem_io, in + first * 2 * B, n * 2 * B);
+  __syncthreads();
+  g1_from_bytes_body<L>(smem_io, B, n, x + first * L, y + first * L, inf + first, N, threadIdx.x);
 }
 template <int L>
 __global__ void k_g1_to_bytes(const uint32_t* x, const uint32_t* y, const uint8_t* inf, size_t N, size_t count,
                               uint8_t* __restrict__ out, int B) {
-  g1_to_bytes_body<L>(x, y, inf, N, count, out, B, BGN_GID(size_t));
+  extern __shared__ __align__(16) uint8_t smem_io[];
+  const size_t first = block_first(), n = block_count(count);
+  g1_to_bytes_body<L>(x + first * L, y + first * L, inf + first, N, n, smem_io, B, threadIdx.x);
+  __syncthreads();
+  stage_bytes_out(out + first * 2 * B, smem_io, n * 2 * B);
 }
 template <int L>
 __global__ void k_fp2_from_bytes(const uint8_t* __restrict__ in, int B, size_t count, uint32_t* re, uint32_t* im,
                                  size_t N) {
-  fp2_from_bytes_body<L>(in, B, count, re, im, N, BGN_GID(size_t));
+  extern __shared__ __align__(16) uint8_t smem_io[];
+  const size_t first = block_first(), n = block_count(count);
+  stage_bytes_in(smem_io, in + first * 2 * B, n * 2 * B);
+  __syncthreads();
+  fp2_from_bytes_body<L>(smem_io, B, n, re + first * L, im + first * L, N, threadIdx.x);
 }
+// the grouped form (grp > 0: identity padding slots) indexes source elements irregularly: unstaged
 template <int L>
 __global__ void k_fp2_to_bytes(const uint32_t* re, const uint32_t* im, size_t N, size_t count,
                                uint8_t* __restrict__ out, int B, int grp, int pad) {
-  fp2_to_bytes_body<L>(re, im, N, count, out, B, grp, pad, BGN_GID(size_t));
+  extern __shared__ __align__(16) uint8_t smem_io[];
+  if (grp > 0) {
+    fp2_to_bytes_body<L>(re, im, N, count, out, B, grp, pad, BGN_GID(size_t));
+    return;
+  }
+  const size_t first = block_first(), n = block_count(count);
+  fp2_to_bytes_body<L>(re + first * L, im + first * L, N, n, smem_io, B, 0, 0, threadIdx.x);
+  __syncthreads();
+  stage_bytes_out(out + first * 2 * B, smem_io, n * 2 * B);
 }
 template <int L>
 __global__ void k_tab_bases(const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,

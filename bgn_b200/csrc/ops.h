@@ -69,6 +69,7 @@ struct LOpsB {
   void (*tabw_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
                     size_t nent);
   void (*g1_polyconv)(LaunchCfg, const PolyConvArgs&);
+  void (*g1_affadd)(LaunchCfg, const G1AffAddArgs&);
 };
 
 #define BGN_DECL_OPS(L)               \

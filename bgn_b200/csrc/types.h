@@ -100,6 +100,24 @@ struct G1AddArgs {
   size_t count, N;
 };
 
+// EAdd / ESub entirely in affine coordinates: one inversion (binary GCD) per thread shared by the
+// elements g, g+G, g+2G, ... of thread g (Montgomery's trick on the denominators x2 - x1, or 2 y1
+// where the operands coincide), 6 products per element instead of the 11 + 6 of a mixed Jacobian
+// addition followed by the batched normalisation.
+struct G1AffAddArgs {
+  const uint32_t *x1, *y1;
+  const uint8_t* inf1;
+  const uint32_t *x2, *y2;
+  const uint8_t* inf2;
+  int bcast1;    // operand 1 is a single element (Neg: O - c)
+  int subtract;
+  uint32_t *ox, *oy;
+  uint8_t* oinf;
+  uint32_t* scratch;  // [count][L] prefix products
+  size_t count;
+  int G;              // worker threads
+};
+
 struct G1MulArgs {
   const uint32_t *x, *y;
   const uint8_t* inf;

@@ -88,6 +88,7 @@ int hs_miller(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_mi
 int hs_encrypt(int L, const EncArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) encrypt_body<LL>(*a, e)) }
 int hs_normalize(int L, const NormArgs* a) { FOR_L(L, for (size_t g = 0; g < (size_t)a->G; g++) normalize_body<LL>(*a, g)) }
 int hs_g1_add(int L, const G1AddArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) g1_add_body<LL>(*a, e)) }
+int hs_g1_affadd(int L, const G1AffAddArgs* a) { FOR_L(L, for (size_t g = 0; g < (size_t)a->G; g++) g1_affadd_body<LL>(*a, g)) }
 int hs_g1_mulvar(int L, const G1MulArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) g1_mulvar_body<LL>(*a, e)) }
 int hs_gt_mul(int L, const GtBinArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_mul_body<LL>(*a, e)) }
 int hs_gt_pow(int L, const GtPowArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_pow_body<LL>(*a, e)) }

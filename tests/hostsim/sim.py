@@ -81,6 +81,12 @@ class G1AddArgs(C.Structure):
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
 
 
+class G1AffAddArgs(C.Structure):
+    _fields_ = [("x1", u32p), ("y1", u32p), ("inf1", u8p), ("x2", u32p), ("y2", u32p), ("inf2", u8p),
+                ("bcast1", C.c_int), ("subtract", C.c_int), ("ox", u32p), ("oy", u32p), ("oinf", u8p),
+                ("scratch", u32p), ("count", C.c_size_t), ("G", C.c_int)]
+
+
 class G1MulArgs(C.Structure):
     _fields_ = [("x", u32p), ("y", u32p), ("inf", u8p), ("Nin", C.c_size_t), ("k_be", u8p), ("kbytes", C.c_int),
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t)]
@@ -361,6 +367,21 @@ class Sim:
                       1 if bcast1 else 0, 1 if subtract else 0, P32(X), P32(Y), P32(Z), count, count)
         assert lib().hs_g1_add(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
+
+    def g1_affadd(self, A, Bp, subtract=False, bcast1=False, G=3):
+        """k_g1_affadd: EAdd / ESub in affine coordinates with one shared inversion per thread"""
+        count = len(Bp)
+        x1, y1, i1 = self.g1_arrays(A)
+        x2, y2, i2 = self.g1_arrays(Bp)
+        ox = np.zeros((max(1, count), self.L), dtype=np.uint32)
+        oy = np.zeros_like(ox)
+        oinf = np.zeros(max(1, count), dtype=np.uint8)
+        scratch = np.zeros_like(ox)
+        a = G1AffAddArgs(P32(x1), P32(y1), P8(i1), P32(x2), P32(y2), P8(i2), 1 if bcast1 else 0, 1 if subtract else 0,
+                         P32(ox), P32(oy), P8(oinf), P32(scratch), count, max(1, min(G, count)))
+        assert lib().hs_g1_affadd(self.L, C.byref(a)) == 0
+        xs, ys = self.unsoa(ox, count), self.unsoa(oy, count)
+        return [None if oinf[e] else (xs[e], ys[e]) for e in range(count)]
 
     def g1_mulvar(self, A, ks, kbytes):
         count = len(A)

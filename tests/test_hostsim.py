@@ -414,3 +414,20 @@ def test_sim_evalpoly_wide_weights():
     w = [3 ** (d - 1 - k) for k in range(d)]
     assert w[0] >> 64
     assert S.polyconv([c.C for c in cs], d, False, w, d - 1, 1, False, 1) == [O.eval_poly(pk, ct).C]
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_g1_affadd(kb):
+    """k_g1_affadd against the golden Add / Sub / Neg vectors (O operands, doubling, inverse pairs) for
+    several thread counts (elements per shared inversion), and a 2-torsion corner: (0,0) + (0,0) = O."""
+    g, par, S, _ = setup(kb)
+    for G in (1, 3, 50):
+        v = g["g1_add"]
+        assert S.g1_affadd(g1s(par, v["a"]), g1s(par, v["b"]), G=G) == g1s(par, v["out"])
+        v = g["g1_sub"]
+        assert S.g1_affadd(g1s(par, v["a"]), g1s(par, v["b"]), subtract=True, G=G) == g1s(par, v["out"])
+    v = g["g1_neg"]
+    assert S.g1_affadd([None], g1s(par, v["a"]), subtract=True, bcast1=True) == g1s(par, v["out"])
+    if kb == 64:
+        pt = g1s(par, g["g1_add"]["a"])[0]
+        assert S.g1_affadd([(0, 0), pt], [(0, 0), (0, 0)]) == [None, O.g1_add(pt, (0, 0), par.p)]
