@@ -763,3 +763,26 @@ def test_gadgets_on_gpu():
     cts[3], cts[4] = cts[4], cts[3]
     assert gadgets.check_proofs_of_plaintext_knowledge(pk, cts, many) == [True] * 3 + [False] * 2 + [True] * 11
     pk.engine.close()
+
+
+def test_context_lifecycle_releases_device_memory():
+    """create -> use every lazily built table (16-bit windows of Q, e(Q,Q) table, line table, baby steps)
+    -> destroy, 12 times: the free device memory must come back (no leak in bgn_ctx_destroy)."""
+    import torch
+    from bgn_b200 import Engine
+    g = load_golden(128)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    v = g["encrypt"]
+    for i in range(12):
+        e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+        e.set_secret(int(g["q1"], 16), g["msg_space"])
+        c = e.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(e, v["r"], e.scalar_bytes))
+        assert c.tobytes() == unhex(v["out"])
+        l2 = e.make_l2_batch(c)
+        e.gt_blind_batch(l2, scal(e, v["r"], e.scalar_bytes))
+        e.decrypt_batch(c, False)
+        e.close()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, "device memory not released: %d MiB" % ((free0 - free1) >> 20)
