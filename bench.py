@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 D1 = D2 = 11
 KEY_BITS = 512
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_miller<17> launch over 3404 units (one full
-# wave), from the `ncu --set full` capture summarised in profiles/r01_miller_v21_ncu.txt
-NCU_DRAM_BYTES_PER_UNIT = 10928640 / 3404.0
+# wave), from the `ncu --set full` capture summarised in profiles/r01_miller_v24_ncu.txt
+NCU_DRAM_BYTES_PER_UNIT = 10858752 / 3404.0
 METRIC = "pairings/s"
 WORKLOAD = "keyBits=512 batched EMult (MultPoly) of 2^14 L1 poly-ciphertext pairs, d1=d2=11 (121 pairings/EMult)"
 
