@@ -209,7 +209,7 @@ BGN_DEV void normalize_body(const NormArgs& a, size_t g) {
 #ifdef BGN_NORMALIZE_FERMAT
   FF::inv(acc.v(), acc.v(), t.v());
 #else
-  FF::inv_gcd(acc.v(), acc.v());
+  FF::inv_gcd_fast(acc.v(), acc.v());
 #endif
   size_t last = ((a.count - 1 - g) / a.G) * a.G + g;  // largest e = g (mod G) below count
   for (size_t e = last;; e -= a.G) {
@@ -297,7 +297,7 @@ BGN_DEV void g1_affadd_body(const G1AffAddArgs& a, size_t g) {
     FF::copy(a.scratch + e * L, acc.v());
     FF::mul(acc.v(), acc.v(), den.v());
   }
-  FF::inv_gcd(acc.v(), acc.v());
+  FF::inv_gcd_fast(acc.v(), acc.v());
   const size_t last = ((a.count - 1 - g) / a.G) * a.G + g;
   for (size_t e = last;; e -= a.G) {
     const size_t e1 = a.bcast1 ? 0 : e;

@@ -180,4 +180,17 @@ uint64_t hs_mul_count(int reset) {
 }
 int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(r, a, t.v())) }
 int hs_fp_inv_gcd(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv_gcd(r, a)) }
+// the verified fast inversion; *fallbacks receives how often it had to fall back since the last call
+int hs_fp_inv_safe(int L, uint32_t* r, const uint32_t* a, size_t count, uint64_t* fallbacks) {
+  bgnsim::safegcd_fallbacks = 0;
+  int rc = 0;
+  switch (L) {
+    case 3: for (size_t i = 0; i < count; i++) F<3>::inv_gcd_fast(r + i * 3, a + i * 3); break;
+    case 5: for (size_t i = 0; i < count; i++) F<5>::inv_gcd_fast(r + i * 5, a + i * 5); break;
+    case 17: for (size_t i = 0; i < count; i++) F<17>::inv_gcd_fast(r + i * 17, a + i * 17); break;
+    default: rc = -1;
+  }
+  *fallbacks = bgnsim::safegcd_fallbacks;
+  return rc;
+}
 }
