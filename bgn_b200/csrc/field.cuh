@@ -213,9 +213,11 @@ struct F {
   // fails -- a flaw in the fast routine can cost time, never correctness.  Used by k_normalize and
   // k_g1_affadd, where the inversion is the bottleneck; the Miller kernels keep inv_gcd (their
   // inversion is ~0.1 % of the work and their register allocation is left alone).
+  template <bool RELAXED = false>
   BGN_DEVNI static void inv_gcd_fast(E r, const uint32_t* a) {
     uint32_t x[L], y[L], z[L], chk[L], one[L], r3[L];
     ld<L>(x, a);
+    if (RELAXED) P::norm2p(x, x);
     P::canon(x, x);
     ld<L>(one, c_fc.r2);
     P::mul(r3, one, one);

@@ -400,8 +400,8 @@ struct MillerFixed {
     // final exponentiation (conj(f)^2 / N(f))^l, as MillerTeam::finalize for one slot
     E n0 = ex, i0 = ey, g0 = slot(S_G0), g1 = slot(S_G1);
     MA::fe_prepare(fr, fi, n0);
-    // 1 / N(f) by the binary GCD (ALU pipe, ~1/7 of the Fermat power's dependent latency)
-    FF::template inv_gcd<true>(i0, n0);
+    // 1 / N(f) by the verified division-step GCD (ALU pipe; field.cuh: inv_gcd_fast)
+    FF::template inv_gcd_fast<true>(i0, n0);
     MA::scale2(fr, fi, i0);
     FF::copy(g0, fr);
     FF::copy(g1, fi);
