@@ -67,7 +67,7 @@ const char* bgn_last_error(const bgn_ctx* ctx);
 
 /* Tuning knobs of a context (none changes any result):
  *   "enc_window"   8 | 16 | 24   fixed-base window of Q for Encrypt / level-1 re-randomisation.  16 (default):
- *                                285 MB table at 512-bit keys; 24: 50 GB table, a third fewer additions (+39 %
+ *                                285 MB table at 512-bit keys; 24: 50 GB table, a third fewer additions (+42 %
  *                                Encrypt throughput), ~2 s to build -- for long-lived contexts; falls back to 16
  *                                when the table does not fit the free device memory.  The table is (re)built on
  *                                the next randomised encryption.
