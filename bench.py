@@ -273,7 +273,10 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {
-        "bound": "imad", "kernel": "k_miller<17>", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
+        "bound": "imad",
+        "bound_note": "neither hbm nor tensor: north_star names the 32-bit integer multiply pipe (IMAD) as this path's "
+                      "roofline; 50 000 products per byte moved -- the hbm object below shows memory at 0.002 % of its peak",
+        "kernel": "k_miller<17>", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
         "unit": "T(32x32->64 products)/s", "frac": achieved / imad_peak,
         "traffic": NCU_DRAM_BYTES_PER_UNIT * pairs,
         "traffic_note": "DRAM bytes per launch scaled from the ncu capture of one full wave (profiles/); algorithmic "
