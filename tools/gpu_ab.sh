@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B bench of the default library and every variants/lib*.so (developer tool).  Usage: tools/gpu_ab.sh <tag> [bench args]
+# A/B bench of the default library and every tools/_ab/lib*.so (developer tool).  Usage: tools/gpu_ab.sh <tag> [bench args]
 TAG=${1:-ab}; shift
 O=gpurun_out; mkdir -p $O
 cat > /tmp/ab_fmt.py <<'PY'
@@ -13,4 +13,4 @@ run() { local name=$1 lib=$2; shift 2
   BGN_B200_LIB=$lib timeout 600 python bench.py --no-cpu "$@" 2>>$O/${TAG}_err.txt | AB_NAME=$name python /tmp/ab_fmt.py | tee -a $O/${TAG}_ab.txt
 }
 run default "" "$@"
-for f in variants/lib*.so; do [ -f "$f" ] && run $(basename $f .so) $PWD/$f "$@"; done
+for f in tools/_ab/lib*.so; do  # (variants/ and build/ are gpurun-ignored: copy the variant libraries to tools/_ab/) [ -f "$f" ] && run $(basename $f .so) $PWD/$f "$@"; done
