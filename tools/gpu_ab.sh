@@ -13,4 +13,5 @@ run() { local name=$1 lib=$2; shift 2
   BGN_B200_LIB=$lib timeout 600 python bench.py --no-cpu "$@" 2>>$O/${TAG}_err.txt | AB_NAME=$name python /tmp/ab_fmt.py | tee -a $O/${TAG}_ab.txt
 }
 run default "" "$@"
-for f in tools/_ab/lib*.so; do  # (variants/ and build/ are gpurun-ignored: copy the variant libraries to tools/_ab/) [ -f "$f" ] && run $(basename $f .so) $PWD/$f "$@"; done
+# variants/ and build/ are gpurun-ignored: copy the variant libraries to tools/_ab/
+for f in tools/_ab/lib*.so; do [ -f "$f" ] && run $(basename $f .so) $PWD/$f "$@"; done

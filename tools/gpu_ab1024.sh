@@ -7,4 +7,5 @@ import json,sys
 d=json.load(sys.stdin); e=d['ops']['emult_d8']
 print('$1', 'emult/s=%.0f'%e['per_s'], 'frac=%.3f'%e['imad_frac'], 'k_miller_ms=%.1f'%e['kernel_ms']['k_miller'])"; }
 run default ""
-for f in tools/_ab/lib*.so; do  # (variants/ and build/ are gpurun-ignored: copy the variant libraries to tools/_ab/) [ -f "$f" ] && run $(basename $f .so) $PWD/$f; done
+# variants/ and build/ are gpurun-ignored: copy the variant libraries to tools/_ab/
+for f in tools/_ab/lib*.so; do [ -f "$f" ] && run $(basename $f .so) $PWD/$f; done
