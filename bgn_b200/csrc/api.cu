@@ -1520,6 +1520,12 @@ int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t
     if (qb == 0) throw ArgErr{"q1 is zero"};
     for (int i = 0; i < BGN_MAX_EXPW; i++) c->pc.exp[i] = q[i];
     c->pc.exp_bits = qb;
+    {
+      std::vector<int8_t> qn = big_naf(Big(q.begin(), q.begin() + (qb + 31) / 32));
+      if (qn.size() > BGN_MAX_NAF) throw ArgErr{"secret exponent too large"};
+      c->pc.exp_naf_len = (int)qn.size();
+      for (size_t i = 0; i < qn.size(); i++) c->pc.exp_naf[i] = qn[i];
+    }
     reupload_pc(c);
     c->has_secret = false;
     // bound = ceil(sqrt(T)) exactly as gsbs.go:60 (float64 sqrt of an int64)

@@ -752,15 +752,16 @@ void gt_pow_pair_sim(const GtPowArgs& a, size_t e) {
   typename GP::State s0, s1;
   GP::init(s0, a.re + e * L, a.im + e * L, true);
   GP::init(s1, a.re + e * L, a.im + e * L, true);
-  for (int i = c_pc.exp_bits - 2; i >= 0; i--) {
+  for (int i = 1; i < c_pc.exp_naf_len; i++) {
     uint32_t t0[L], t1[L];
     GP::sqr_half(t0, s0, 0);
     GP::sqr_half(t1, s1, 1);
     GP::update(s0, t0, t1, 0);
     GP::update(s1, t1, t0, 1);
-    if ((c_pc.exp[i >> 5] >> (i & 31)) & 1) {
-      GP::mul_half(t0, s0, 0);
-      GP::mul_half(t1, s1, 1);
+    const int dg = c_pc.exp_naf[i];
+    if (dg != 0) {
+      GP::mul_half(t0, s0, 0, dg < 0);
+      GP::mul_half(t1, s1, 1, dg < 0);
       GP::update(s0, t0, t1, 0);
       GP::update(s1, t1, t0, 1);
     }
@@ -831,14 +832,15 @@ __global__ void __launch_bounds__(64) k_gt_pow_pair(const __grid_constant__ GtPo
   typename GP::State st;
   GP::init(st, a.re + ee * L, a.im + ee * L, active);
   BGN_UNROLL1
-  for (int i = c_pc.exp_bits - 2; i >= 0; i--) {
+  for (int i = 1; i < c_pc.exp_naf_len; i++) {  // signed digits, MSB first (digit 0 is the leading 1)
     uint32_t mine[L], other[L];
     GP::sqr_half(mine, st, s);
 #pragma unroll
     for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
     GP::update(st, mine, other, s);
-    if ((c_pc.exp[i >> 5] >> (i & 31)) & 1) {
-      GP::mul_half(mine, st, s);
+    const int dg = c_pc.exp_naf[i];
+    if (dg != 0) {
+      GP::mul_half(mine, st, s, dg < 0);
 #pragma unroll
       for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
       GP::update(st, mine, other, s);

@@ -169,6 +169,7 @@ struct GtPowPair {
   struct State {
     uint32_t r0[L], r1[L];  // running power, both coordinates in both lanes (relaxed range)
     uint32_t a0[L], a1[L];  // the base
+    uint32_t na1[L];        // -Im(a): conj(a) = a^-1 serves the exponent's negative digits
   };
 
   BGN_DEV static void init(State& st, const uint32_t* re, const uint32_t* im, bool active) {
@@ -181,6 +182,7 @@ struct GtPowPair {
       BGN_UNROLL
       for (int j = 0; j < L; j++) st.a0[j] = st.a1[j] = 0;
     }
+    P::negk(st.na1, st.a1, c_fc.p2, 2);
     LU::sel(st.r0, true, st.a0, st.a0);
     LU::sel(st.r1, true, st.a1, st.a1);
   }
@@ -195,11 +197,12 @@ struct GtPowPair {
     P::addn(d, t, t);
     LU::sel(t, s == 0, t, d);  // lane 1 holds 2 r0 r1
   }
-  // this lane's half of r * a
-  BGN_DEV static void mul_half(uint32_t (&t)[L], const State& st, int s) {
-    uint32_t x[L], y[L], u[L], v[L], dif[L], sum[L];
-    LU::sel(x, s == 0, st.a0, st.a1);
-    LU::sel(y, s == 0, st.a1, st.a0);
+  // this lane's half of r * a (neg: r * conj(a))
+  BGN_DEV static void mul_half(uint32_t (&t)[L], const State& st, int s, bool neg) {
+    uint32_t x[L], y[L], u[L], v[L], dif[L], sum[L], b1[L];
+    LU::sel(b1, neg, st.na1, st.a1);
+    LU::sel(x, s == 0, st.a0, b1);
+    LU::sel(y, s == 0, b1, st.a0);
     P::mul(u, st.r0, x);
     P::mul(v, st.r1, y);
     P::subk(dif, u, v, c_fc.p4, 4);

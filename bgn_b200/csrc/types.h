@@ -25,6 +25,10 @@ struct PairConsts {
   int32_t exp_bits;              // bit length of the fixed GT exponent (secret q1)
   uint32_t exp[BGN_MAX_EXPW];    // fixed exponent, little-endian words
   int8_t naf[BGN_MAX_NAF];
+  // appended (keeps every earlier offset): signed digits of the fixed exponent, MSB first, for
+  // k_gt_pow_pair -- inverses in GT are conjugates, so a digit -1 costs what a digit +1 does
+  int32_t exp_naf_len;
+  int8_t exp_naf[BGN_MAX_NAF];
 };
 
 #define BGN_MILLER_NSLOT 12  // F_p slots per thread of the Miller team kernel

@@ -28,7 +28,8 @@ class FieldConsts(C.Structure):
 
 class PairConsts(C.Structure):
     _fields_ = [("l", C.c_uint64), ("naf_len", C.c_int32), ("exp_bits", C.c_int32),
-                ("exp", C.c_uint32 * MAX_EXPW), ("naf", C.c_int8 * MAX_NAF)]
+                ("exp", C.c_uint32 * MAX_EXPW), ("naf", C.c_int8 * MAX_NAF),
+                ("exp_naf_len", C.c_int32), ("exp_naf", C.c_int8 * MAX_NAF)]
 
 
 class MillerArgs(C.Structure):
@@ -200,6 +201,10 @@ class Sim:
             pc.exp_bits = q1.bit_length()
             for i in range(MAX_EXPW):
                 pc.exp[i] = (q1 >> (32 * i)) & 0xFFFFFFFF
+            qn = naf_digits(q1)
+            pc.exp_naf_len = len(qn)
+            for i, z in enumerate(qn):
+                pc.exp_naf[i] = z
         self.fc, self.pc = fc, pc
         self.P, self.Q = P, Q
         self.activate()
