@@ -9,8 +9,9 @@ production caller uses.
 
 What differs from the reference, on purpose:
   * elements are held as PBC `element_to_bytes` byte strings, not *pbc.Element;
-  * randomness is injected (`r=`) or drawn from `secrets`; the reference draws
-    from crypto/rand inside the call (bgn.go:567-574);
+  * randomness is injected (`r=`, `rs=`, or a `PublicKey.rand_source` callable that stands for
+    newCryptoRandom, consumed in the reference's sequential program order) or drawn from
+    `secrets`; the reference draws from crypto/rand inside the call (bgn.go:567-574);
   * O (point at infinity) is all-zero bytes (SURVEY.md 8(a) note);
   * decryption tables are per key, not process globals (gsbs.go:12-15).
 """
@@ -141,6 +142,12 @@ class PublicKey:
         self._table = EncodingTable(polyBase)  # computeEncodingTable, bgn.go:135
         self.engine = engine if engine is not None else Engine(p, n, l, P, Q, device)
         self._secret_set = False
+        self._secret_key = None
+        # newCryptoRandom(pk.N) (bgn.go:567-574).  None: the OS CSPRNG.  A callable: every draw the
+        # reference would make that is not given explicitly (`r=`, `rs=`) is one call of it, in the
+        # reference's sequential program order (goroutine bodies in the textual order of their loops,
+        # poly.go:101-112, 144-151) -- what the parity tests use to reproduce the oracle byte for byte.
+        self.rand_source = None
 
     @classmethod
     def FromPBCParams(cls, params: str, P: bytes, Q: bytes, MsgSpace: int, **kw) -> "PublicKey":
@@ -170,10 +177,13 @@ class PublicKey:
         """bgn.go:195-201 + PrecomputeTables (gsbs.go:41-51): tables live on the device."""
         self.engine.set_secret(sk.Key, self.MsgSpace)
         self._secret_set = True
+        self._secret_key = sk.Key
 
     def _need_secret(self, sk: SecretKey) -> Engine:
         if not self._secret_set:
             raise RuntimeError("DL tables not computed!")  # gsbs.go:56-58
+        if sk is not None and sk.Key != self._secret_key:
+            raise ValueError("this SecretKey is not the one installed by SetupDecryption")
         return self.engine
 
     # ---------------------------------------------------------------- helpers
@@ -184,8 +194,22 @@ class PublicKey:
     def _np(self, *cts: Ciphertext) -> np.ndarray:
         return np.frombuffer(b"".join(c.C for c in cts), dtype=np.uint8)
 
-    def _rand(self, r: Optional[int]) -> int:
-        return secrets.randbelow(self.N) if r is None else r
+    def _rand(self, r: Optional[int] = None) -> int:
+        if r is not None:
+            return r
+        if self.rand_source is not None:
+            return int(self.rand_source()) % self.N
+        return secrets.randbelow(self.N)
+
+    def _blind(self, buf, scalars: Sequence[int], L2: bool):
+        """the re-randomisation of a non-deterministic key over a whole buffer: slot i gains
+        scalars[i]*Q (level 1, bgn.go:264-268, 491-495) or is multiplied by e(Q,Q)^scalars[i] (level 2,
+        bgn.go:283-287, 306-310, 469-474); a scalar 0 leaves its slot untouched."""
+        r_be = self.engine.scalars_be([int(x) % self.N for x in scalars])
+        if type(buf).__module__.startswith("torch") and buf.is_cuda:
+            import torch
+            r_be = torch.from_numpy(r_be).to(buf.device)
+        return self.engine.gt_blind_batch(buf, r_be) if L2 else self.engine.g1_blind_batch(buf, r_be)
 
     def _blind_g1(self, elem: np.ndarray, r: Optional[int]) -> np.ndarray:
         """+ r*Q (bgn.go:264-268, 491-495): bgn_g1_blind_batch, fixed-base windows of Q."""
@@ -277,6 +301,8 @@ class PublicKey:
 
     def EncryptDeterministic(self, x: int) -> Ciphertext:
         """bgn.go:325-331."""
+        if abs(x) >= 1 << 63:  # the reference takes any *big.Int
+            return Ciphertext(self._encrypt_big([x], [0]), False)
         out = self.engine.encrypt_batch(np.array([x], dtype=np.int64), None)
         return Ciphertext(out.tobytes(), False)
 
@@ -336,16 +362,20 @@ class PublicKey:
 
     def MultConst(self, c: Ciphertext, constant: int, r: Optional[int] = None) -> Ciphertext:
         """bgn.go:253-291."""
-        if constant < 0:
-            raise ValueError("negative constants: use Neg(MultConst(c, -k))")
+        negative = constant < 0  # k*C = |k|*(-C): the group-theoretic meaning of PowBig by a negative k
+        constant = abs(constant)
         kb = max(1, (constant.bit_length() + 7) // 8)
         k = self.engine.scalars_be([constant], kb)
         if c.L2:
             res = self.engine.gt_pow_batch(self._np(c), k, kb)
+            if negative:
+                res = self.engine.gt_inv_batch(res)
             if not self.Deterministic:
                 res = self._blind_gt(res, r)
             return Ciphertext(res.tobytes(), True)
         res = self.engine.g1_mulconst_batch(self._np(c), k, kb)
+        if negative:
+            res = self.engine.g1_neg_batch(res)
         if not self.Deterministic:
             res = self._blind_g1(res, r)
         return Ciphertext(res.tobytes(), False)
@@ -357,51 +387,94 @@ class PublicKey:
         return [Ciphertext(raw[i * eb:(i + 1) * eb], L2) for i in range(count)]
 
     def EncryptPoly(self, pt: PolyPlaintext, rs: Optional[Sequence[int]] = None) -> PolyCiphertext:
-        """poly.go:11-29; negative coefficients become -(|c| P + r Q) as there."""
-        x = np.array(pt.Coefficients[: pt.Degree], dtype=np.int64)
-        if rs is None:
-            rs = [secrets.randbelow(self.N) for _ in range(pt.Degree)]
-        out = self.engine.encrypt_batch(x, self.engine.scalars_be([r % self.N for r in rs]))
+        """poly.go:11-29; rs[i] is the randomness of coefficient i's Encrypt.  Negative coefficients are
+        Sub(encryptZero(), Encrypt(|c|)) = -(|c| P + r Q) as there; with a non-deterministic key that Sub
+        adds its own r' Q (bgn.go:421-432), drawn here when a rand_source is installed or `rs` is absent:
+        -(|c| P + (r - r') Q), one engine call either way."""
+        coeffs = [int(c) for c in pt.Coefficients[: pt.Degree]]
+        x = np.array(coeffs, dtype=np.int64)
+        draw_sub = (not self.Deterministic) and (rs is None or self.rand_source is not None)
+        eff = []
+        for i, c in enumerate(coeffs):  # the reference's loop order (ascending), Encrypt's draw first
+            r = self._rand(None if rs is None else rs[i])
+            if c < 0 and draw_sub:
+                r -= self._rand()
+            eff.append(r % self.N)
+        out = self.engine.encrypt_batch(x, self.engine.scalars_be(eff))
         return PolyCiphertext(self._split(out, pt.Degree, False), pt.Degree, pt.ScaleFactor, False)
 
     def NegPoly(self, ct: PolyCiphertext) -> PolyCiphertext:
-        """poly.go:45-55."""
-        buf = self._np(*ct.Coefficients[: ct.Degree])
+        """poly.go:45-55: Sub(encryptZero(), c_i), i = Degree-1 .. 0 -- one draw per slot for a
+        non-deterministic key."""
+        d = ct.Degree
+        buf = self._np(*ct.Coefficients[:d])
         res = self.engine.gt_inv_batch(buf) if ct.L2 else self.engine.g1_neg_batch(buf)
-        return PolyCiphertext(self._split(res, ct.Degree, ct.L2), ct.Degree, ct.ScaleFactor, ct.L2)
+        if not self.Deterministic:
+            res = self._blind(res, [self._rand() for _ in range(d)][::-1], ct.L2)
+        return PolyCiphertext(self._split(res, d, ct.L2), d, ct.ScaleFactor, ct.L2)
+
+    def _multpoly_scalars(self, d1: int, d2: int) -> List[int]:
+        """Per output slot, the sum of the draws the reference makes for it in MultPoly: one in Mult
+        (bgn.go:302-311) and one in the Add that folds the pairing into its slot (bgn.go:466-474), for
+        i = d1-1 .. 0, k = d2-1 .. 0 (poly.go:140-152).  The unused top slot draws nothing and stays 1."""
+        R = [0] * (d1 + d2)
+        for i in range(d1 - 1, -1, -1):
+            for k in range(d2 - 1, -1, -1):
+                R[i + k] += self._rand() + self._rand()
+        return R
 
     def MultPoly(self, ct1: PolyCiphertext, ct2: PolyCiphertext) -> PolyCiphertext:
-        """poly.go:123-156: result[j] = prod_{i+k=j} e(c1[i], c2[k]); Degree = d1 + d2 slots."""
+        """poly.go:123-156: result[j] = prod_{i+k=j} e(c1[i], c2[k]); Degree = d1 + d2 slots.  A
+        non-deterministic key multiplies e(Q,Q)^(its draws) into every slot but the unused top one."""
         if ct1.L2 or ct2.L2:
             raise ValueError("MultPoly needs two level-1 ciphertexts")
         d1, d2 = ct1.Degree, ct2.Degree
         out = self.engine.multpoly_batch(self._np(*ct1.Coefficients[:d1]), d1, self._np(*ct2.Coefficients[:d2]), d2, 1)
+        if not self.Deterministic:
+            out = self._blind(out, self._multpoly_scalars(d1, d2), True)
         return PolyCiphertext(self._split(out, d1 + d2, True), d1 + d2, ct1.ScaleFactor + ct2.ScaleFactor, True)
 
-    def MakePolyL2(self, ct: PolyCiphertext) -> PolyCiphertext:
-        """poly.go:159-163: MultPoly(E(1.0), ct); E(1.0) is one slot, so Degree grows by one."""
-        one = self.EncryptPoly(self.NewPolyPlaintext(1.0), rs=[0])
+    def _one_randomness(self, r_one: Optional[int]) -> int:
+        """The randomness of E(1.0) in MakePolyL2 (poly.go:161: EncryptPoly draws it, also for
+        Deterministic keys).  Explicit, else drawn from the rand_source / the CSPRNG; a Deterministic key
+        without a rand_source uses 0 -- a valid member of the reference's output distribution, the
+        reproducible one, and the one served by the recorded line table of P."""
+        if r_one is not None:
+            return r_one % self.N
+        if self.Deterministic and self.rand_source is None:
+            return 0
+        return self._rand()
+
+    def MakePolyL2(self, ct: PolyCiphertext, r_one: Optional[int] = None) -> PolyCiphertext:
+        """poly.go:159-163: MultPoly(EncryptPoly(1.0), ct); E(1.0) is one slot, so Degree grows by one."""
+        one = self.EncryptPoly(self.NewPolyPlaintext(1.0), rs=[self._one_randomness(r_one)])
         return self.MultPoly(one, ct)
 
+    def _multconst_scalars(self, d: int, nd: int, negative: bool) -> List[int]:
+        """Per output slot of MultConstPoly, the net re-randomisation scalar of a non-deterministic key:
+        every (coefficient i, digit k) pair -- zero digits too -- draws once in MultConst (bgn.go:260-269,
+        279-288) and once in Add, for i = d-1 .. 0, k = nd-1 .. 0 (poly.go:97-112); a negative constant
+        negates all of that and adds NegPoly's draw per slot (poly.go:116-118)."""
+        R = [0] * (d + nd)
+        for i in range(d - 1, -1, -1):
+            for k in range(nd - 1, -1, -1):
+                R[i + k] += self._rand() + self._rand()
+        if negative:
+            neg = [self._rand() for _ in range(d + nd)][::-1]
+            R = [n_ - r_ for n_, r_ in zip(neg, R)]
+        return R
+
     def MultConstPoly(self, ct: PolyCiphertext, constant: float) -> PolyCiphertext:
-        """poly.go:71-120: schoolbook product with the unbalanced digits (0,1,2) of |constant|."""
+        """poly.go:71-120: schoolbook product with the unbalanced digits (0,1,2) of |constant|, one
+        engine call (bgn_multconstpoly_batch)."""
         negative = constant < 0
         poly = self.NewUnbalancedPlaintext(abs(constant))
-        degree = ct.Degree + poly.Degree
-        eb = self.elem_bytes
-        ident = self.makeL2(self.encryptZero()) if ct.L2 else self.encryptZero()
-        acc = np.frombuffer(ident.C * degree, dtype=np.uint8).copy()
-        src = self._np(*ct.Coefficients[: ct.Degree])
-        for k, digit in enumerate(poly.Coefficients[: poly.Degree]):
-            if digit == 0:
-                continue
-            kbuf = self.engine.scalars_be([digit] * ct.Degree, 1)
-            term = (self.engine.gt_pow_batch(src, kbuf, 1) if ct.L2 else self.engine.g1_mulconst_batch(src, kbuf, 1))
-            window = acc[k * eb:(k + ct.Degree) * eb]
-            summed = self.engine.gt_mul_batch(window, term) if ct.L2 else self.engine.g1_add_batch(window, term)
-            acc[k * eb:(k + ct.Degree) * eb] = summed
-        prod = PolyCiphertext(self._split(acc, degree, ct.L2), degree, ct.ScaleFactor + poly.ScaleFactor, ct.L2)
-        return self.NegPoly(prod) if negative else prod
+        d, nd = ct.Degree, poly.Degree
+        out = self.engine.multconstpoly_batch(self._np(*ct.Coefficients[:d]), d, ct.L2, poly.Coefficients[:nd],
+                                              negative, 1)
+        if not self.Deterministic:
+            out = self._blind(out, self._multconst_scalars(d, nd, negative), ct.L2)
+        return PolyCiphertext(self._split(out, d + nd, ct.L2), d + nd, ct.ScaleFactor + poly.ScaleFactor, ct.L2)
 
     def alignPolyCiphertexts(self, ct1: PolyCiphertext, ct2: PolyCiphertext):
         """poly.go:209-226."""
@@ -414,7 +487,8 @@ class PublicKey:
         return ct1, ct2
 
     def AddPoly(self, pct1: PolyCiphertext, pct2: PolyCiphertext) -> PolyCiphertext:
-        """poly.go:171-207."""
+        """poly.go:171-207: the common slots go through Add (re-randomised for a non-deterministic key,
+        i = degree-1 .. 0), the longer operand's tail is passed through untouched."""
         if pct1.L2 or pct2.L2:
             if not pct1.L2:
                 return self.AddPoly(self.MakePolyL2(pct1), pct2)
@@ -425,6 +499,8 @@ class PublicKey:
         common = min(ct1.Degree, ct2.Degree)
         a, b = self._np(*ct1.Coefficients[:common]), self._np(*ct2.Coefficients[:common])
         res = self.engine.gt_mul_batch(a, b) if ct1.L2 else self.engine.g1_add_batch(a, b)
+        if not self.Deterministic:
+            res = self._blind(res, [self._rand() for _ in range(common)][::-1], ct1.L2)
         coeffs = self._split(res, common, ct1.L2)
         longer = ct1 if ct1.Degree > ct2.Degree else ct2
         coeffs += longer.Coefficients[common:degree]
@@ -460,35 +536,27 @@ class PublicKey:
         x = x.contiguous() if hasattr(x, "contiguous") else np.ascontiguousarray(x)
         return x.reshape(-1)
 
-    def AddPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch) -> PolyCiphertextBatch:
-        """AddPoly (poly.go:171-207) over two batches of equal count, with everything the scalar
-        version does: a level-1 operand is promoted with MakePolyL2 when the other is level 2
-        (poly.go:173-182), the operand with the smaller ScaleFactor is multiplied by
-        FPScaleBase^diff (alignPolyCiphertexts, poly.go:209-226), the common slots are added and the
-        longer operand's tail is passed through (poly.go:191-204)."""
-        if a.count != b.count:
-            raise ValueError("AddPolyBatch needs batches of equal count")
-        if a.L2 != b.L2:
-            if not a.L2:
-                a = self.MakePolyL2Batch(a)
-            else:
-                b = self.MakePolyL2Batch(b)
-        if a.ScaleFactor != b.ScaleFactor:
-            lo, hi = (a, b) if a.ScaleFactor < b.ScaleFactor else (b, a)
-            diff = hi.ScaleFactor - lo.ScaleFactor
-            up = self.MultConstPolyBatch(lo, math.pow(float(self.PolyEncodingParams.FPScaleBase), float(diff)))
-            up.ScaleFactor = hi.ScaleFactor
-            a, b = hi, up
+    # The batch forms draw exactly what `count` sequential calls of the scalar form would, unit by unit
+    # (so a replayed rand_source reproduces them), and re-randomise with ONE blind call per stage.
+    def _flatten(self, per_unit: List[List[int]]) -> List[int]:
+        return [x for row in per_unit for x in row]
+
+    def _addpoly_exec(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, Rs) -> PolyCiphertextBatch:
+        """common slots added (and blinded with Rs[u][0..common) when given), longer tail passed through"""
         eb = self.elem_bytes
-        if a.Degree == b.Degree:
-            res = self.engine.gt_mul_batch(a.data, b.data) if a.L2 else self.engine.g1_add_batch(a.data, b.data)
-            return PolyCiphertextBatch(res, a.count, a.Degree, a.ScaleFactor, a.L2)
         if a.Degree < b.Degree:
             a, b = b, a  # a is the longer one; addition is commutative
         common = b.Degree
-        ra = self._rows(a.data, a.count, a.Degree, eb)
-        head = self._flat(ra[:, : common * eb])
+        if a.Degree == common:
+            head = a.data
+        else:
+            ra = self._rows(a.data, a.count, a.Degree, eb)
+            head = self._flat(ra[:, : common * eb])
         summed = self.engine.gt_mul_batch(head, b.data) if a.L2 else self.engine.g1_add_batch(head, b.data)
+        if Rs is not None:
+            summed = self._blind(summed, self._flatten(Rs), a.L2)
+        if a.Degree == common:
+            return PolyCiphertextBatch(summed, a.count, a.Degree, a.ScaleFactor, a.L2)
         out = ra.clone() if hasattr(ra, "clone") else ra.copy()
         sm = self._rows(summed, a.count, common, eb)
         if hasattr(out, "is_cuda") and not hasattr(sm, "is_cuda"):
@@ -499,43 +567,144 @@ class PublicKey:
         out[:, : common * eb] = sm
         return PolyCiphertextBatch(out.reshape(-1), a.count, a.Degree, a.ScaleFactor, a.L2)
 
+    def AddPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch) -> PolyCiphertextBatch:
+        """AddPoly (poly.go:171-207) over two batches of equal count, with everything the scalar
+        version does: a level-1 operand is promoted with MakePolyL2 when the other is level 2
+        (poly.go:173-182), the operand with the smaller ScaleFactor is multiplied by
+        FPScaleBase^diff (alignPolyCiphertexts, poly.go:209-226), the common slots are added --
+        re-randomised for a non-deterministic key -- and the longer operand's tail is passed
+        through (poly.go:191-204)."""
+        if a.count != b.count:
+            raise ValueError("AddPolyBatch needs batches of equal count")
+        count, nondet = a.count, not self.Deterministic
+        promote = None if a.L2 == b.L2 else ("a" if not a.L2 else "b")
+        d_prom = 0 if promote is None else (a.Degree if promote == "a" else b.Degree)
+        da = a.Degree + (1 if promote == "a" else 0)
+        db = b.Degree + (1 if promote == "b" else 0)
+        align, const, nd = None, 0.0, 0
+        if a.ScaleFactor != b.ScaleFactor:
+            align = "a" if a.ScaleFactor < b.ScaleFactor else "b"
+            const = math.pow(float(self.PolyEncodingParams.FPScaleBase), float(abs(a.ScaleFactor - b.ScaleFactor)))
+            nd = self.NewUnbalancedPlaintext(const).Degree
+            if align == "a":
+                da += nd
+            else:
+                db += nd
+        common = min(da, db)
+        # the draws of unit 0's AddPoly, then unit 1's, ... in the scalar form's order
+        r_ones, R_l2, R_mc, R_add = [], [], [], []
+        for _ in range(count):
+            if promote is not None:
+                r_ones.append(self._one_randomness(None))
+                R_l2.append(self._multpoly_scalars(1, d_prom) if nondet else None)
+            if align is not None and nondet:
+                d_al = (a.Degree if align == "a" else b.Degree) + (1 if promote == align else 0)
+                R_mc.append(self._multconst_scalars(d_al, nd, False))
+            if nondet:
+                R_add.append([self._rand() for _ in range(common)][::-1])
+        if promote == "a":
+            a = self._makepolyl2_exec(a, r_ones, R_l2 if nondet else None)
+        elif promote == "b":
+            b = self._makepolyl2_exec(b, r_ones, R_l2 if nondet else None)
+        if align is not None:
+            lo, hi = (a, b) if align == "a" else (b, a)
+            up = self._multconstpoly_exec(lo, const, R_mc if nondet else None)
+            up.ScaleFactor = hi.ScaleFactor
+            a, b = hi, up
+        return self._addpoly_exec(a, b, R_add if nondet else None)
+
+    AddPolyBatchRand = AddPolyBatch  # round-1 name: AddPolyBatch itself honours Deterministic=False now
+
+    def NegPolyBatch(self, a: PolyCiphertextBatch) -> PolyCiphertextBatch:
+        """NegPoly (poly.go:45-55) over a batch."""
+        res = self.engine.gt_inv_batch(a.data) if a.L2 else self.engine.g1_neg_batch(a.data)
+        if not self.Deterministic:
+            Rs = [[self._rand() for _ in range(a.Degree)][::-1] for _ in range(a.count)]
+            res = self._blind(res, self._flatten(Rs), a.L2)
+        return PolyCiphertextBatch(res, a.count, a.Degree, a.ScaleFactor, a.L2)
+
+    def SubPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch) -> PolyCiphertextBatch:
+        return self.AddPolyBatch(a, self.NegPolyBatch(b))  # poly.go:166-168
+
     def MultPolyBatch(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, rs=None) -> PolyCiphertextBatch:
-        """MultPoly over a batch.  Non-deterministic keys re-randomise every output slot: the
-        reference multiplies e(Q,Q)^r into each of the d1*d2 coefficient pairings (bgn.go:302-311 via
-        poly.go:140-152), which per slot is e(Q,Q)^(sum of its r's); `rs` injects one scalar per
-        output slot (count * (d1+d2-1) ... the padding slot included: count * (d1+d2))."""
+        """MultPoly over a batch.  Non-deterministic keys re-randomise every output slot but the
+        unused top one: the reference multiplies e(Q,Q)^r into each of the d1*d2 coefficient pairings
+        and again in the Add that folds each into its slot (bgn.go:302-311, 466-474 via
+        poly.go:140-152), which per slot is e(Q,Q)^(sum of its draws).  `rs` injects the per-slot
+        sums directly: count * (d1+d2) scalars, the top slot's entry ignored (it stays 1,
+        poly.go:130-137)."""
         if a.L2 or b.L2 or a.count != b.count:
             raise ValueError("MultPolyBatch needs two level-1 batches of equal count")
+        d = a.Degree + b.Degree
         out = self.engine.multpoly_batch(a.data, a.Degree, b.data, b.Degree, a.count)
         if not self.Deterministic:
-            out = self.engine.gt_blind_batch(out, self._rand_be(a.count * (a.Degree + b.Degree), rs))
-        return PolyCiphertextBatch(out, a.count, a.Degree + b.Degree, a.ScaleFactor + b.ScaleFactor, True)
+            if rs is None:
+                R = self._flatten([self._multpoly_scalars(a.Degree, b.Degree) for _ in range(a.count)])
+            else:
+                R = [0 if (i + 1) % d == 0 else int(r) for i, r in enumerate(rs)]
+                if len(R) != a.count * d:
+                    raise ValueError("rs must hold count * (d1 + d2) scalars")
+            out = self._blind(out, R, True)
+        return PolyCiphertextBatch(out, a.count, d, a.ScaleFactor + b.ScaleFactor, True)
 
-    def MakePolyL2Batch(self, a: PolyCiphertextBatch) -> PolyCiphertextBatch:
-        """MakePolyL2 (poly.go:159-163) over a batch: e(c_i, P) per slot plus the identity top slot."""
-        if a.L2:
-            raise ValueError("MakePolyL2Batch needs a level-1 batch")
-        out = self.engine.make_poly_l2_batch(a.data, a.Degree, a.count)
+    def _makepolyl2_exec(self, a: PolyCiphertextBatch, r_ones, Rs) -> PolyCiphertextBatch:
+        if all(r == 0 for r in r_ones):
+            out = self.engine.make_poly_l2_batch(a.data, a.Degree, a.count)  # e(., P): the recorded line table of P
+        else:
+            ones = self.engine.encrypt_batch(np.ones(a.count, dtype=np.int64), self.engine.scalars_be(r_ones))
+            if type(a.data).__module__.startswith("torch") and a.data.is_cuda:
+                import torch
+                ones = torch.from_numpy(np.ascontiguousarray(ones)).to(a.data.device)
+            out = self.engine.multpoly_batch(ones, 1, a.data, a.Degree, a.count)
+        if Rs is not None:
+            out = self._blind(out, self._flatten(Rs), True)
         return PolyCiphertextBatch(out, a.count, a.Degree + 1, a.ScaleFactor, True)
 
-    def MultConstPolyBatch(self, a: PolyCiphertextBatch, constant: float) -> PolyCiphertextBatch:
-        """MultConstPoly (poly.go:71-120) over a batch: one kernel launch, one thread per output slot."""
+    def MakePolyL2Batch(self, a: PolyCiphertextBatch, r_one=None) -> PolyCiphertextBatch:
+        """MakePolyL2 (poly.go:159-163) over a batch: e(E(1.0), c_i) per slot plus the identity top slot.
+        r_one: the randomness of every polynomial's E(1.0) (a sequence of count scalars, or one int for
+        all); see _one_randomness for the default."""
+        if a.L2:
+            raise ValueError("MakePolyL2Batch needs a level-1 batch")
+        nondet = not self.Deterministic
+        r_ones, Rs = [], []
+        for u in range(a.count):
+            ru = None if r_one is None else (r_one if isinstance(r_one, int) else r_one[u])
+            r_ones.append(self._one_randomness(ru))
+            if nondet:
+                Rs.append(self._multpoly_scalars(1, a.Degree))
+        return self._makepolyl2_exec(a, r_ones, Rs if nondet else None)
+
+    def _multconstpoly_exec(self, a: PolyCiphertextBatch, constant: float, Rs) -> PolyCiphertextBatch:
         poly = self.NewUnbalancedPlaintext(abs(constant))
         out = self.engine.multconstpoly_batch(a.data, a.Degree, a.L2, poly.Coefficients[: poly.Degree], constant < 0,
                                               a.count)
+        if Rs is not None:
+            out = self._blind(out, self._flatten(Rs), a.L2)
         return PolyCiphertextBatch(out, a.count, a.Degree + poly.Degree, a.ScaleFactor + poly.ScaleFactor, a.L2)
 
-    def EvalPolyBatch(self, a: PolyCiphertextBatch):
-        """EvalPoly (poly.go:58-68) over a batch -> count elements (level of the batch)."""
-        return self.engine.evalpoly_batch(a.data, a.Degree, a.L2, self.PolyEncodingParams.PolyBase, a.count)
-
-    def AddPolyBatchRand(self, a: PolyCiphertextBatch, b: PolyCiphertextBatch, rs=None) -> PolyCiphertextBatch:
-        """AddPolyBatch followed by the per-coefficient re-randomisation of a non-deterministic key."""
-        res = self.AddPolyBatch(a, b)
+    def MultConstPolyBatch(self, a: PolyCiphertextBatch, constant: float) -> PolyCiphertextBatch:
+        """MultConstPoly (poly.go:71-120) over a batch: one kernel launch, one thread per output slot."""
+        Rs = None
         if not self.Deterministic:
-            blind = self.engine.gt_blind_batch if res.L2 else self.engine.g1_blind_batch
-            res.data = blind(res.data, self._rand_be(res.count * res.Degree, rs))
-        return res
+            nd = self.NewUnbalancedPlaintext(abs(constant)).Degree
+            Rs = [self._multconst_scalars(a.Degree, nd, constant < 0) for _ in range(a.count)]
+        return self._multconstpoly_exec(a, constant, Rs)
+
+    def EvalPolyBatch(self, a: PolyCiphertextBatch):
+        """EvalPoly (poly.go:58-68) over a batch -> count elements (level of the batch).  Horner draws
+        once in MultConst and once in Add per coefficient (i = Degree-1 .. 0); the draws of step i are
+        multiplied by base i more times, so the net scalar is sum_i (r_i + r'_i) base^i."""
+        out = self.engine.evalpoly_batch(a.data, a.Degree, a.L2, self.PolyEncodingParams.PolyBase, a.count)
+        if not self.Deterministic:
+            base, R = self.PolyEncodingParams.PolyBase, []
+            for _ in range(a.count):
+                acc = 0
+                for i in range(a.Degree - 1, -1, -1):
+                    acc += (self._rand() + self._rand()) * pow(base, i, self.N)
+                R.append(acc)
+            out = self._blind(out, R, a.L2)
+        return out
 
     def SumPolyBatch(self, a: PolyCiphertextBatch) -> PolyCiphertext:
         """AddPoly folded over a whole L2 batch (one GPU's share of an inner product)."""

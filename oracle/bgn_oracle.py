@@ -24,7 +24,7 @@ from __future__ import annotations
 import math
 import random
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 G1Point = Optional[Tuple[int, int]]  # None == point at infinity O
 Fp2 = Tuple[int, int]  # (re, im), i^2 = -1
@@ -441,6 +441,10 @@ class PublicKey:
     table_g1: dict = field(default_factory=dict, repr=False)
     table_gt: dict = field(default_factory=dict, repr=False)
     tables_computed: bool = False
+    # Injected randomness: every newCryptoRandom(pk.N) call of the reference (bgn.go:567-574) that is
+    # not given an explicit `r` below is one call of rand_source(), in the reference's sequential
+    # program order (goroutine bodies in the textual order of their loops).  None: explicit r only.
+    rand_source: Optional[Callable[[], int]] = field(default=None, repr=False)
 
     @property
     def n(self) -> int:
@@ -559,6 +563,15 @@ def _qq(pk: PublicKey) -> Fp2:
     return pairing(pk.Q, pk.Q, pk.params)
 
 
+def _draw(pk: PublicKey, r: Optional[int] = None) -> int:
+    """newCryptoRandom(pk.N) (bgn.go:567-574): the explicit r, else the next value of pk.rand_source."""
+    if r is not None:
+        return r
+    if pk.rand_source is None:
+        raise ValueError("non-deterministic operation without injected randomness (r= or pk.rand_source)")
+    return pk.rand_source() % pk.params.n
+
+
 def add(pk: PublicKey, a: Ciphertext, b: Ciphertext, r: Optional[int] = None) -> Ciphertext:
     """bgn.go:442-497.  r is the injected randomness used when !Deterministic."""
     p = pk.params.p
@@ -570,11 +583,11 @@ def add(pk: PublicKey, a: Ciphertext, b: Ciphertext, r: Optional[int] = None) ->
     if ct1.L2 and ct2.L2:
         res = fp2_mul(ct1.C, ct2.C, p)
         if not pk.deterministic:
-            res = fp2_mul(res, fp2_pow(_qq(pk), r, p), p)
+            res = fp2_mul(res, fp2_pow(_qq(pk), _draw(pk, r), p), p)
         return Ciphertext(res, True)
     res = g1_add(ct1.C, ct2.C, p)
     if not pk.deterministic:
-        res = g1_add(res, g1_mul(r, pk.Q, p), p)
+        res = g1_add(res, g1_mul(_draw(pk, r), pk.Q, p), p)
     return Ciphertext(res, ct1.L2)
 
 
@@ -590,11 +603,11 @@ def sub(pk: PublicKey, a: Ciphertext, b: Ciphertext, r: Optional[int] = None) ->
         res = _gt_div(ct1.C, ct2.C, p)
         if pk.deterministic:
             return Ciphertext(res, True)
-        res = fp2_mul(res, fp2_pow(_qq(pk), r, p), p)
+        res = fp2_mul(res, fp2_pow(_qq(pk), _draw(pk, r), p), p)
         return Ciphertext(res, False)
     res = g1_add(ct1.C, g1_neg(ct2.C, p), p)
     if not pk.deterministic:
-        res = g1_add(res, g1_mul(r, pk.Q, p), p)
+        res = g1_add(res, g1_mul(_draw(pk, r), pk.Q, p), p)
     return Ciphertext(res, ct1.L2)
 
 
@@ -608,7 +621,7 @@ def mult(pk: PublicKey, a: Ciphertext, b: Ciphertext, r: Optional[int] = None) -
     p = pk.params.p
     res = pairing(a.C, b.C, pk.params)
     if not pk.deterministic:
-        res = fp2_mul(res, fp2_pow(_qq(pk), r, p), p)
+        res = fp2_mul(res, fp2_pow(_qq(pk), _draw(pk, r), p), p)
     return Ciphertext(res, True)
 
 
@@ -618,11 +631,11 @@ def mult_const(pk: PublicKey, c: Ciphertext, k: int, r: Optional[int] = None) ->
     if not c.L2:
         res = g1_mul(k, c.C, p)
         if not pk.deterministic:
-            res = g1_add(res, g1_mul(r, pk.Q, p), p)
+            res = g1_add(res, g1_mul(_draw(pk, r), pk.Q, p), p)
         return Ciphertext(res, False)
     res = fp2_pow(c.C, k, p)
     if not pk.deterministic:
-        res = fp2_mul(res, fp2_pow(_qq(pk), r, p), p)
+        res = fp2_mul(res, fp2_pow(_qq(pk), _draw(pk, r), p), p)
     return Ciphertext(res, True)
 
 
@@ -707,17 +720,27 @@ def decrypt_fail_safe(pk: PublicKey, sk: SecretKey, ct: Ciphertext) -> int:
 
 
 # --------------------------------------------------------------------------
-# polynomial ciphertexts (poly.go).  Randomness is injected: `rs` lists.
+# polynomial ciphertexts (poly.go).  Randomness is injected: the per-coefficient encryption
+# randomness as `rs` lists, every other newCryptoRandom draw through pk.rand_source (see _draw), taken
+# in the reference's sequential program order: the goroutine bodies of poly.go:101-112 and
+# poly.go:144-151 in the textual order of their loops (i and k DEscending).  With
+# pk.deterministic = True and no rand_source the functions are the deterministic mode every reference
+# test uses (bgn_test.go:13).
 # --------------------------------------------------------------------------
-def encrypt_poly(pk: PublicKey, pt: PolyPlaintext, rs: Sequence[int]) -> PolyCiphertext:
-    """poly.go:11-29; rs[i] is the randomness of coefficient i."""
+def encrypt_poly(pk: PublicKey, pt: PolyPlaintext, rs: Optional[Sequence[int]] = None) -> PolyCiphertext:
+    """poly.go:11-29; rs[i] is the randomness of coefficient i's Encrypt (drawn when rs is None).  A
+    negative coefficient is Sub(encryptZero(), Encrypt(|c|)), whose own re-randomisation (non-deterministic
+    keys, bgn.go:421-432) is drawn from pk.rand_source, or is 0 when no source is installed."""
     out = []
     for i, c in enumerate(pt.coefficients):
+        r = rs[i] if rs is not None else _draw(pk)
         if c < 0:
-            out.append(sub(pk, encrypt_zero(pk), encrypt_with_randomness(pk, -c, rs[i]),
-                           None if pk.deterministic else 0))
+            r2 = None
+            if not pk.deterministic:
+                r2 = _draw(pk) if pk.rand_source is not None else 0
+            out.append(sub(pk, encrypt_zero(pk), encrypt_with_randomness(pk, -c, r), r2))
         else:
-            out.append(encrypt_with_randomness(pk, c, rs[i]))
+            out.append(encrypt_with_randomness(pk, c, r))
     return PolyCiphertext(out, pt.degree, pt.scale_factor, False)
 
 
@@ -728,30 +751,42 @@ def decrypt_poly(pk: PublicKey, sk: SecretKey, ct: PolyCiphertext) -> PolyPlaint
 
 
 def neg_poly(pk: PublicKey, ct: PolyCiphertext) -> PolyCiphertext:
-    """poly.go:45-55."""
-    return PolyCiphertext([sub(pk, encrypt_zero(pk) if not c.L2 else make_l2(pk, encrypt_zero(pk)), c)
-                           for c in ct.coefficients], ct.degree, ct.scale_factor, ct.L2)
+    """poly.go:45-55: Sub(encryptZero(), c_i) for i = degree-1 .. 0 (one draw each when !Deterministic).
+    The coefficient flags are reported correctly (the reference's non-deterministic L2 Sub says L2=false,
+    bgn.go:411)."""
+    res: List[Optional[Ciphertext]] = [None] * ct.degree
+    for i in range(ct.degree - 1, -1, -1):
+        c = sub(pk, encrypt_zero(pk), ct.coefficients[i])
+        res[i] = Ciphertext(c.C, ct.coefficients[i].L2)
+    return PolyCiphertext(res, ct.degree, ct.scale_factor, ct.L2)
 
 
 def mult_poly(pk: PublicKey, ct1: PolyCiphertext, ct2: PolyCiphertext) -> PolyCiphertext:
-    """poly.go:123-156 (deterministic mode)."""
+    """poly.go:123-156.  Non-deterministic keys: every coefficient pairing draws once in Mult
+    (bgn.go:302-311) and once in the Add that folds it into its slot (bgn.go:466-474); the unused top
+    slot stays makeL2(encryptZero()) = 1."""
     degree = ct1.degree + ct2.degree
     result = [make_l2(pk, encrypt_zero(pk)) for _ in range(degree)]
-    for i in range(ct1.degree):
-        for k in range(ct2.degree):
-            result[i + k] = add(pk, result[i + k], mult(pk, ct1.coefficients[i], ct2.coefficients[k]))
+    for i in range(ct1.degree - 1, -1, -1):
+        for k in range(ct2.degree - 1, -1, -1):
+            coeff = mult(pk, ct1.coefficients[i], ct2.coefficients[k])
+            result[i + k] = add(pk, result[i + k], coeff)
     return PolyCiphertext(result, degree, ct1.scale_factor + ct2.scale_factor, True)
 
 
 def make_poly_l2(pk: PublicKey, ct: PolyCiphertext) -> PolyCiphertext:
-    """poly.go:159-163 (E(1.0) encrypted deterministically: r = 0)."""
+    """poly.go:159-163: MultPoly(EncryptPoly(1.0), ct).  E(1.0)'s randomness is drawn from pk.rand_source;
+    without a source it is 0 (the reference always draws one, so its MakePolyL2 is randomised even for
+    Deterministic keys; r = 0 is the reproducible member of that family)."""
     one_pt = pk.new_poly_plaintext(1.0)
-    one = encrypt_poly(pk, one_pt, [0] * one_pt.degree)
+    one = encrypt_poly(pk, one_pt, None if pk.rand_source is not None else [0] * one_pt.degree)
     return mult_poly(pk, one, ct)
 
 
 def mult_const_poly(pk: PublicKey, ct: PolyCiphertext, constant: float) -> PolyCiphertext:
-    """poly.go:71-120 (deterministic mode)."""
+    """poly.go:71-120.  Non-deterministic keys: every (coefficient, digit) pair -- zero digits included --
+    draws once in MultConst (bgn.go:260-269, 279-288) and once in Add; a negative constant adds NegPoly's
+    draws."""
     is_neg = constant < 0
     if is_neg:
         constant = -constant
@@ -761,9 +796,10 @@ def mult_const_poly(pk: PublicKey, ct: PolyCiphertext, constant: float) -> PolyC
     if ct.L2:
         zero = make_l2(pk, zero)
     result = [zero] * degree
-    for i in range(ct.degree):
-        for k in range(poly.degree):
-            result[i + k] = add(pk, result[i + k], mult_const(pk, ct.coefficients[i], poly.coefficients[k]))
+    for i in range(ct.degree - 1, -1, -1):
+        for k in range(poly.degree - 1, -1, -1):
+            coeff = mult_const(pk, ct.coefficients[i], poly.coefficients[k])
+            result[i + k] = add(pk, result[i + k], coeff)
     prod = PolyCiphertext(result, degree, ct.scale_factor + poly.scale_factor, ct.L2)
     return neg_poly(pk, prod) if is_neg else prod
 
@@ -780,7 +816,8 @@ def _align(pk: PublicKey, ct1: PolyCiphertext, ct2: PolyCiphertext):
 
 
 def add_poly(pk: PublicKey, a: PolyCiphertext, b: PolyCiphertext) -> PolyCiphertext:
-    """poly.go:171-207 (deterministic mode)."""
+    """poly.go:171-207: common slots go through Add (i = degree-1 .. 0, one draw each when
+    !Deterministic), the longer operand's tail is passed through untouched."""
     if a.L2 or b.L2:
         if not a.L2:
             return add_poly(pk, make_poly_l2(pk, a), b)
@@ -788,14 +825,14 @@ def add_poly(pk: PublicKey, a: PolyCiphertext, b: PolyCiphertext) -> PolyCiphert
             return add_poly(pk, a, make_poly_l2(pk, b))
     ct1, ct2 = _align(pk, a, b)
     degree = max(ct1.degree, ct2.degree)
-    out: List[Ciphertext] = []
-    for i in range(degree):
+    out: List[Optional[Ciphertext]] = [None] * degree
+    for i in range(degree - 1, -1, -1):
         if i >= ct2.degree:
-            out.append(ct1.coefficients[i])
+            out[i] = ct1.coefficients[i]
         elif i >= ct1.degree:
-            out.append(ct2.coefficients[i])
+            out[i] = ct2.coefficients[i]
         else:
-            out.append(add(pk, ct1.coefficients[i], ct2.coefficients[i]))
+            out[i] = add(pk, ct1.coefficients[i], ct2.coefficients[i])
     return PolyCiphertext(out, degree, ct1.scale_factor, ct1.L2)
 
 
@@ -804,7 +841,8 @@ def sub_poly(pk: PublicKey, a: PolyCiphertext, b: PolyCiphertext) -> PolyCiphert
 
 
 def eval_poly(pk: PublicKey, ct: PolyCiphertext) -> Ciphertext:
-    """poly.go:58-68 (Horner in the exponent)."""
+    """poly.go:58-68 (Horner in the exponent; MultConst then Add per coefficient, each drawing once when
+    !Deterministic)."""
     acc = encrypt_deterministic(pk, 0)
     for c in reversed(ct.coefficients[: ct.degree]):
         acc = mult_const(pk, acc, pk.poly_base)

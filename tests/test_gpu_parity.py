@@ -371,6 +371,26 @@ def test_mirror_api_nondeterministic():
     assert sk.Decrypt(pk.Sub(p1, pk.makeL2(a)), pk) == 3
 
 
+@pytest.mark.parametrize("kb", [64, 128])
+def test_mirror_api_nondeterministic_poly_ops(kb):
+    """Deterministic=false at the polynomial level: MultPoly / AddPoly / SubPoly / NegPoly / MultConstPoly /
+    MakePolyL2 / EvalPoly / EncryptPoly and their *Batch forms on the CUDA engine, driven by a replayed
+    randomness stream, byte for byte against the oracle's literal poly.go control flow on the same stream
+    (tests/nondet_cases.py); two un-injected calls must differ and decrypt alike."""
+    from bgn_b200 import PublicKey, SecretKey
+    from nondet_cases import run_poly_cases
+    from oracle import bgn_oracle as O
+    g = load_golden(kb)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    sk = SecretKey(int(g["q1"], 16))
+    pk.SetupDecryption(sk)
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    opk = O.PublicKey(par, O.g1_from_bytes(bytes.fromhex(g["P"]), par), O.g1_from_bytes(bytes.fromhex(g["Q"]), par),
+                      g["msg_space"])
+    run_poly_cases(pk, opk, sk)
+    pk.engine.close()
+
+
 def test_mirror_wire_roundtrip():
     """bgn_test.go:37-85 (TestMarshalUnmarshal*): ciphertext -> gob envelope -> ciphertext keeps the
     element, level, Degree and ScaleFactor, on both levels; malformed element bytes follow

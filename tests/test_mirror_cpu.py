@@ -125,7 +125,7 @@ def test_nondeterministic_mode_matches_oracle(keys):
     pk0, sk, opk, _ = keys
     pk = PublicKey(pk0.engine.p, pk0.N, pk0.engine.l, pk0.P, pk0.Q, pk0.MsgSpace, Deterministic=False,
                    engine=pk0.engine)
-    pk._secret_set = True
+    pk._secret_set, pk._secret_key = True, sk.Key
     ond = O.PublicKey(opk.params, opk.P, opk.Q, opk.msg_space, deterministic=False)
     rng = random.Random(3)
     r = [rng.randrange(pk.N) for _ in range(8)]
@@ -139,6 +139,31 @@ def test_nondeterministic_mode_matches_oracle(keys):
     assert pk.Add(m, a, r=r[6]).C == O.ct_bytes(ond, O.add(ond, om, oa, r[6]))  # mixed levels
     s1, s2 = pk.Add(a, b), pk.Add(a, b)
     assert s1.C != s2.C and sk.Decrypt(s1, pk) == sk.Decrypt(s2, pk) == 5
+
+
+def test_nondeterministic_poly_ops_match_oracle(keys):
+    """every polynomial operation on a Deterministic=False key, fed by a replayed randomness stream,
+    against the oracle's literal poly.go control flow on the same stream (tests/nondet_cases.py)"""
+    from nondet_cases import run_poly_cases
+    pk, sk, opk, osk = keys
+    run_poly_cases(pk, opk, sk, osk)
+
+
+def test_secret_key_mismatch_is_an_error(keys):
+    pk, sk, _, _ = keys
+    with pytest.raises(ValueError, match="not the one installed"):
+        SecretKey(sk.Key + 2).Decrypt(pk.Encrypt(1), pk)
+
+
+def test_big_and_negative_scalars(keys):
+    """EncryptDeterministic takes any *big.Int (bgn.go:325-331); MultConst by a negative constant is
+    |k| * (-C)."""
+    pk, sk, opk, _ = keys
+    x = (1 << 70) + 12345
+    assert pk.EncryptDeterministic(x).C == O.ct_bytes(opk, O.encrypt_deterministic(opk, x % pk.N))
+    c = pk.EncryptDeterministic(7)
+    assert sk.Decrypt(pk.MultConst(c, -3), pk) == -21
+    assert sk.Decrypt(pk.MultConst(pk.makeL2(c), -3), pk) == -21
 
 
 def test_wire_roundtrip(keys):
