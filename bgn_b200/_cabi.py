@@ -27,6 +27,7 @@ SIGNATURES = {
     "bgn_ctx_create": (C.c_int, [C.POINTER(bgn_params), C.c_int, C.POINTER(C.c_void_p)]),
     "bgn_ctx_destroy": (None, [C.c_void_p]),
     "bgn_last_error": (C.c_char_p, [C.c_void_p]),
+    "bgn_global_last_error": (C.c_char_p, []),
     "bgn_ctx_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgn_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     "bgn_ctx_set_secret": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32]),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "bgn_timing_get": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bgn_timing_last_call": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "bgn_bench_mulmod": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "bgn_bench_issue_mix": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_double)]),
     "bgn_bench_imad_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_double)]),
 }

@@ -94,6 +94,22 @@ std::vector<int8_t> big_naf(Big n) {
   return d;
 }
 
+// floor(a / b) for b != 0 (bitwise long division; key set-up only)
+Big big_div(const Big& a, const Big& b) {
+  size_t nl = a.size();
+  Big q(nl, 0), r(nl + 1, 0), bb(nl + 1, 0);
+  for (size_t i = 0; i < nl && i < b.size(); i++) bb[i] = b[i];
+  for (int bit = big_bits(a) - 1; bit >= 0; bit--) {
+    for (size_t i = nl; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+    r[0] = (r[0] << 1) | ((a[bit >> 5] >> (bit & 31)) & 1u);
+    if (big_cmp(r, bb) >= 0) {
+      big_sub(r, r, bb);
+      q[bit >> 5] |= 1u << (bit & 31);
+    }
+  }
+  return q;
+}
+
 const int kSupportedL[] = {3, 5, 9, 17, 33};
 
 // One lock per device: the kernels read their key material from __constant__ memory, of which there
@@ -115,9 +131,11 @@ struct KTime {
 struct bgn_ctx {
   int device = 0;
   int L = 0, B = 0, nbytes = 0;
+  std::vector<uint32_t> n_limbs;  // group order n, little-endian, BGN_MAXL limbs
   const LOpsA* A = nullptr;
   const LOpsB* Bo = nullptr;
   const LOpsC* Co = nullptr;
+  const LOpsD* Do = nullptr;
   FieldConsts fc;
   PairConsts pc;
   cudaStream_t stream = nullptr;
@@ -134,6 +152,7 @@ struct bgn_ctx {
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
+  int fixed_pair = -1;         // e(., P) on a lane pair per point (pairlane.cuh): -1 = by batch size, 0 = never, 1 = always (BGN_FIXED_PAIR)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
   bool has_secret = false;
@@ -182,6 +201,7 @@ void activate(bgn_ctx* c) {
     CK(c->A->upload(&c->fc, &c->pc, c->stream));
     CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
     CK(c->Co->upload(&c->fc, &c->pc, c->stream));
+    CK(c->Do->upload(&c->fc, &c->pc, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     g_active[c->device] = c;
   }
@@ -190,6 +210,7 @@ void reupload_pc(bgn_ctx* c) {
   CK(c->A->upload(&c->fc, &c->pc, c->stream));
   CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
   CK(c->Co->upload(&c->fc, &c->pc, c->stream));
+  CK(c->Do->upload(&c->fc, &c->pc, c->stream));
   CK(cudaStreamSynchronize(c->stream));
 }
 
@@ -549,14 +570,6 @@ void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out
   if (!count) return;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  // one block per SM up to 256 threads; smaller batches use whole scheduler rounds (128 threads)
-  size_t per_sm = (count + sms - 1) / sms;
-  int nt = (int)std::min<size_t>(256, std::max<size_t>(128, (per_sm + 127) / 128 * 128));
-  size_t smem = c->Co->miller_fixed_smem_bytes(nt);
-  while (smem > 227 * 1024 - 64 && nt > 32) {
-    nt -= 32;
-    smem = c->Co->miller_fixed_smem_bytes(nt);
-  }
   MillerFixedArgs a;
   a.lines = c->linesP;
   a.Ex = E.x;
@@ -565,6 +578,24 @@ void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out
   a.out_re = out.re;
   a.out_im = out.im;
   a.count = (int)count;
+  // Below kFixedPairMax points one thread per pairing cannot give every scheduler two warps (148 SMs x
+  // 4 schedulers x 64 lanes): split each pairing over a lane pair (pairlane.cuh).  The crossover is
+  // measured (profiles/r02_fixed_pair_ab.json).
+  const size_t kFixedPairMax = (size_t)sms * 256;
+  if (c->fixed_pair > 0 || (c->fixed_pair < 0 && count < kFixedPairMax)) {
+    Timer t(c, "k_miller_fixed_pair");
+    c->Do->miller_fixed_pair(cfg(c, nblk(2 * count, 64), 64, 0), a);
+    t.done();
+    return;
+  }
+  // one block per SM up to 256 threads; smaller batches use whole scheduler rounds (128 threads)
+  size_t per_sm = (count + sms - 1) / sms;
+  int nt = (int)std::min<size_t>(256, std::max<size_t>(128, (per_sm + 127) / 128 * 128));
+  size_t smem = c->Co->miller_fixed_smem_bytes(nt);
+  while (smem > 227 * 1024 - 64 && nt > 32) {
+    nt -= 32;
+    smem = c->Co->miller_fixed_smem_bytes(nt);
+  }
   Timer t(c, "k_miller_fixed");
   CK(c->Co->miller_fixed_set_smem(smem));
   c->Co->miller_fixed(cfg(c, nblk(count, nt), nt, smem), a);
@@ -696,9 +727,58 @@ void ensure_tabE(bgn_ctx* c) {
   arena_reset(c);
 }
 
+// failures with no context to hold their message (bgn_ctx_create, NULL contexts): per calling thread
+thread_local std::string g_last_error;
+
+// releases everything a context owns (bgn_ctx_destroy and the failure paths of bgn_ctx_create); the
+// device lock is held by the caller
+void ctx_free(bgn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  const bool resident = g_active[c->device] == c;
+  if (resident) g_active[c->device] = nullptr;
+  // the secret exponent must not outlive its context: scrub the host copy and, if this context's
+  // constants are the resident ones, the device copy
+  memset(c->pc.exp, 0, sizeof(c->pc.exp));
+  memset(c->pc.exp_naf, 0, sizeof(c->pc.exp_naf));
+  c->pc.exp_bits = c->pc.exp_naf_len = 0;
+  if (resident && c->has_secret && c->stream && c->A && c->Bo && c->Co) {
+    c->A->upload(&c->fc, &c->pc, c->stream);
+    c->Bo->upload(&c->fc, &c->pc, c->stream);
+    c->Co->upload(&c->fc, &c->pc, c->stream);
+    if (c->Do) c->Do->upload(&c->fc, &c->pc, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(c->dPx);
+  cudaFree(c->dPinf);
+  cudaFree(c->tabP);
+  cudaFree(c->tabQ);
+  cudaFree(c->tabQw);
+  cudaFree(c->tabE);
+  cudaFree(c->linesP);
+  cudaFree(c->bs_elems);
+  cudaFree(c->bs_slots);
+  cudaFree(c->bs_ginv);
+  cudaFree(c->arena);
+  for (auto& pnd : c->pending) {
+    cudaEventDestroy(pnd.a);
+    cudaEventDestroy(pnd.b);
+  }
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->call_a) cudaEventDestroy(c->call_a);
+  if (c->call_b) cudaEventDestroy(c->call_b);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
+  delete c;
+}
+
 template <typename Fn>
 int guarded(bgn_ctx* c, Fn fn) {
-  if (!c) return BGN_E_BADARG;
+  if (!c) {
+    g_last_error = "null context";
+    return BGN_E_BADARG;
+  }
   std::lock_guard<std::mutex> lk(dev_mu(c->device));
   try {
     activate(c);
@@ -729,19 +809,78 @@ int guarded(bgn_ctx* c, Fn fn) {
     return BGN_E_BADARG;
   } catch (const std::bad_alloc&) {
     c->err = "host allocation failed";
+    c->pending.clear();
     return BGN_E_NOMEM;
+  } catch (const std::exception& e) {  // nothing may cross extern "C" as an exception
+    c->err = std::string("internal error: ") + e.what();
+    c->pending.clear();
+    return BGN_E_BADARG;
+  } catch (...) {
+    c->err = "internal error: unknown exception";
+    c->pending.clear();
+    return BGN_E_BADARG;
   }
 }
 
 }  // namespace
 
+// Issue-mix microbenchmark ("is the IMAD.WIDE pipe the whole roofline?"): per inner
+// iteration NW IMAD.WIDE.U32, NLH (IMAD.LO, IMAD.HI) pairs on different operands (so ptxas cannot fuse
+// them into one IMAD.WIDE), NF FFMA and ND DFMA, each class on its own independent accumulators,
+// interleaved in program order.  Comparing a mix's time with the times of its parts shows which
+// classes share an issue pipe: pipes that co-issue give max(parts), a shared pipe gives sum(parts).
+template <int NW, int NLH, int NF, int ND>
+__global__ void __launch_bounds__(256) k_issue_mix(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x, a2 = a ^ 0x5555u, b2 = b + 77u;
+  uint32_t w[16], lo[8], hi[8];
+  float f[8], fx = (float)(threadIdx.x & 7) * 1.0e-3f + 1.0f, fy = 0.999f;
+  double d[8], dx = (double)(threadIdx.x & 7) * 1.0e-3 + 1.0, dy = 0.999;
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = a + i;
+#pragma unroll
+  for (int i = 0; i < 8; i++) lo[i] = b + i, hi[i] = a - i, f[i] = (float)i, d[i] = (double)i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+      constexpr int M = NW > NLH ? (NW > NF ? (NW > ND ? NW : ND) : (NF > ND ? NF : ND))
+                                 : (NLH > NF ? (NLH > ND ? NLH : ND) : (NF > ND ? NF : ND));
+#pragma unroll
+      for (int k = 0; k < M; k++) {
+        if (k < NW)
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                       : "+r"(w[2 * (k & 7)]), "+r"(w[2 * (k & 7) + 1])
+                       : "r"(a), "r"(b));
+        if (k < NLH) {
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k & 7]) : "r"(a2), "r"(b));
+          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k & 7]) : "r"(a), "r"(b2));
+        }
+        if (k < NF) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f[k & 7]) : "f"(fx), "f"(fy));
+        if (k < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[k & 7]) : "d"(dx), "d"(dy));
+      }
+    }
+  }
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) o ^= w[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) o ^= lo[i] ^ hi[i] ^ __float_as_uint(f[i]) ^ (uint32_t)__double_as_longlong(d[i]);
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = o;
+}
+
 // ================================================================== C-ABI
 extern "C" {
 
 int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
-  if (!prm || !out || !prm->p_be || !prm->n_be || !prm->P_bytes || !prm->Q_bytes || prm->l == 0) return BGN_E_BADARG;
+  g_last_error.clear();
+  if (!prm || !out || !prm->p_be || !prm->n_be || !prm->P_bytes || !prm->Q_bytes || prm->l == 0) {
+    g_last_error = "bgn_ctx_create: null argument or l == 0";
+    return BGN_E_BADARG;
+  }
   *out = nullptr;
-  if (device < 0 || device >= kMaxDevices) return BGN_E_BADARG;
+  if (device < 0 || device >= kMaxDevices) {
+    g_last_error = "bgn_ctx_create: bad device ordinal";
+    return BGN_E_BADARG;
+  }
   std::lock_guard<std::mutex> lk(dev_mu(device));
   bgn_ctx* c = nullptr;
   try {
@@ -756,6 +895,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
     if (const char* nt = getenv("BGN_NORM_THREADS")) c->norm_threads = std::max(128, atoi(nt));
     if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
+    if (const char* fp = getenv("BGN_FIXED_PAIR")) c->fixed_pair = atoi(fp);
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -773,6 +913,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->A = bgn_opsA_##n();   \
     c->Bo = bgn_opsB_##n();  \
     c->Co = bgn_opsC_##n();  \
+    c->Do = bgn_opsD_##n();  \
     break;
 #ifdef BGN_HAVE_L3
       BGN_PICK(3)
@@ -793,13 +934,14 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
       default:
         break;
     }
-    if (!c->A || !c->Bo || !c->Co) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
+    if (!c->A || !c->Bo || !c->Co || !c->Do) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
     c->B = (pbits + 7) / 8;
     Big p(p0.begin(), p0.begin() + L);
     Big n = big_from_be(prm->n_be, prm->n_len, BGN_MAXL);
     int nbits = big_bits(n);
     if (nbits < 16 || !(n[0] & 1) || nbits > pbits) throw ArgErr{"bad group order n"};
     c->nbytes = (nbits + 7) / 8;
+    c->n_limbs = n;
     // p + 1 == l * n  (type a1)
     {
       Big acc(BGN_MAXL + 2, 0);
@@ -853,7 +995,11 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     for (size_t i = 0; i < naf.size(); i++) c->pc.naf[i] = naf[i];
 
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // A BLOCKING stream: it orders itself after work already queued on the legacy default stream
+    // (where a caller that hands over device pointers -- e.g. PyTorch -- normally produced them), and
+    // every call ends with a stream synchronise, so results are complete when the call returns.
+    // Producers on other streams must be synchronised by the caller (include/bgn_b200.h).
+    CK(cudaStreamCreate(&c->stream));
     g_active[device] = nullptr;
     activate(c);
     // generators
@@ -887,45 +1033,38 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     *out = c;
     return BGN_OK;
   } catch (const CudaErr& e) {
-    fprintf(stderr, "bgn_ctx_create: %s\n", e.msg.c_str());
+    g_last_error = "bgn_ctx_create: " + e.msg;
     cudaGetLastError();
-    delete c;
+    ctx_free(c);
     return BGN_E_CUDA;
   } catch (const ArgErr& e) {
-    fprintf(stderr, "bgn_ctx_create: %s\n", e.msg.c_str());
-    delete c;
+    g_last_error = "bgn_ctx_create: " + e.msg;
+    ctx_free(c);
     return BGN_E_BADARG;
   } catch (const std::bad_alloc&) {
-    delete c;
+    g_last_error = "bgn_ctx_create: host allocation failed";
+    ctx_free(c);
     return BGN_E_NOMEM;
+  } catch (const std::exception& e) {
+    g_last_error = std::string("bgn_ctx_create: internal error: ") + e.what();
+    ctx_free(c);
+    return BGN_E_BADARG;
+  } catch (...) {
+    g_last_error = "bgn_ctx_create: internal error: unknown exception";
+    ctx_free(c);
+    return BGN_E_BADARG;
   }
 }
+
+const char* bgn_global_last_error(void) { return g_last_error.c_str(); }
 
 void bgn_ctx_destroy(bgn_ctx* c) {
   if (!c) return;
   std::lock_guard<std::mutex> lk(dev_mu(c->device));
-  cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  if (g_active[c->device] == c) g_active[c->device] = nullptr;
-  cudaFree(c->dPx);
-  cudaFree(c->dPinf);
-  cudaFree(c->tabP);
-  cudaFree(c->tabQ);
-  cudaFree(c->tabQw);
-  cudaFree(c->tabE);
-  cudaFree(c->linesP);
-  cudaFree(c->bs_elems);
-  cudaFree(c->bs_slots);
-  cudaFree(c->bs_ginv);
-  cudaFree(c->arena);
-  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-  if (c->call_a) cudaEventDestroy(c->call_a);
-  if (c->call_b) cudaEventDestroy(c->call_b);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
+  ctx_free(c);
 }
 
-const char* bgn_last_error(const bgn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+const char* bgn_last_error(const bgn_ctx* c) { return c ? c->err.c_str() : g_last_error.c_str(); }
 
 int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
   if (!c || !name) return BGN_E_BADARG;
@@ -948,6 +1087,8 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->dec_lucas = value != 0;
   } else if (k == "fixed_lines") {
     c->fixed_lines = value != 0;
+  } else if (k == "fixed_pair") {
+    c->fixed_pair = value < 0 ? -1 : (value != 0);
   } else {
     c->err = "unknown option " + k;
     return BGN_E_BADARG;
@@ -1532,6 +1673,21 @@ int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t
     uint64_t bound = (uint64_t)ceil(sqrt((double)(int64_t)msg_space));
     uint64_t mmax = bound * bound + bound + 2;  // i <= bound, table value j+1 <= bound+2 (gsbs.go:44, 77-98)
     uint64_t S = baby_steps ? baby_steps : std::min<uint64_t>(mmax, (uint64_t)1 << 21);
+    // gsk = e(P,P)^q1 has order q2 = n / q1, and gsk^j, gsk^(q2-j) share their real part -- the key the
+    // table is hashed on and the only thing the Lucas path sees.  Keep the table to j <= (q2-1)/2 so that
+    // no two entries share a real part (and none repeats); the giant steps cover the rest.  Only toy keys
+    // or message spaces near q2 are affected: for q2 >= 2^26 the table (at most 2^24 entries) never gets there.
+    {
+      Big nn = c->n_limbs;
+      Big qq(BGN_MAXL, 0);
+      for (int i = 0; i < BGN_MAX_EXPW && i < BGN_MAXL; i++) qq[i] = q[i];
+      Big q2 = big_div(nn, qq);
+      if (big_bits(q2) <= 26) {
+        uint64_t q2v = q2[0];
+        uint64_t lim = q2v > 2 ? (q2v - 1) / 2 : 1;
+        if (S > lim) S = lim;
+      }
+    }
     if (S < 1) S = 1;
     if (S > ((uint64_t)1 << 24)) throw ArgErr{"baby_steps too large"};
     uint64_t hs = 1;
@@ -1785,6 +1941,58 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, int iters, uin
 #pragma unroll
   for (int i = 0; i < 16; i++) o ^= r[i];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = o;
+}
+
+// mix: 0 WIDE x8 | 1 (LO,HI) x8 | 2 WIDE x8 + (LO,HI) x8 | 3 FFMA x8 | 4 WIDE x8 + FFMA x8 | 5 DFMA x8 |
+//      6 WIDE x8 + DFMA x8 | 7 WIDE x8 + (LO,HI) x4 | 8 WIDE x8 + DFMA x4 | 9 WIDE x4 + DFMA x8
+// per_thread[4] = instructions of each class a thread issues: {IMAD.WIDE, (LO,HI) pairs, FFMA, DFMA}
+int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads, float* ms, double* per_thread) {
+  if (!ms || !per_thread || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256 || device < 0) return BGN_E_BADARG;
+  std::lock_guard<std::mutex> lk(dev_mu(device));
+  if (cudaSetDevice(device) != cudaSuccess) return BGN_E_CUDA;
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return BGN_E_CUDA;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  int nw = 0, nlh = 0, nf = 0, nd = 0;
+  auto go = [&](int it) {
+    switch (mix) {
+#define BGN_MIX(id, W_, LH_, F_, D_)                                  \
+  case id:                                                            \
+    nw = W_, nlh = LH_, nf = F_, nd = D_;                             \
+    k_issue_mix<W_, LH_, F_, D_><<<blocks, threads>>>(d, it, 12345u); \
+    break;
+      BGN_MIX(0, 8, 0, 0, 0)
+      BGN_MIX(1, 0, 8, 0, 0)
+      BGN_MIX(2, 8, 8, 0, 0)
+      BGN_MIX(3, 0, 0, 8, 0)
+      BGN_MIX(4, 8, 0, 8, 0)
+      BGN_MIX(5, 0, 0, 0, 8)
+      BGN_MIX(6, 8, 0, 0, 8)
+      BGN_MIX(7, 8, 4, 0, 0)
+      BGN_MIX(8, 8, 0, 0, 4)
+      BGN_MIX(9, 4, 0, 0, 8)
+#undef BGN_MIX
+      default:
+        break;
+    }
+  };
+  go(8);
+  cudaEventRecord(a);
+  go(iters);
+  cudaEventRecord(b);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaEventElapsedTime(ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  per_thread[0] = (double)iters * 8 * nw;
+  per_thread[1] = (double)iters * 8 * nlh;
+  per_thread[2] = (double)iters * 8 * nf;
+  per_thread[3] = (double)iters * 8 * nd;
+  if (mix < 0 || mix > 9) return BGN_E_BADARG;
+  return e == cudaSuccess ? BGN_OK : BGN_E_CUDA;
 }
 
 int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread) {

@@ -36,6 +36,7 @@ static thread_local uint32_t cc = 0;
 static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
 static uint64_t nmulw = 0, nredc = 0;  // double-width products / separate reductions executed
 static uint64_t nmulk = 0;             // of which Karatsuba products (counted apart from nmulw)
+static uint64_t ndot2 = 0;             // one-pass dot products a0 b0 + a1 b1 (3L^2 + L products each)
 static uint64_t safegcd_fallbacks = 0;  // F<L>::inv_gcd<SAFE>: times the verified fast inversion fell back
 // Range tracker (tests only): every element written by the arithmetic below carries an upper
 // bound in multiples of p, keyed by its address, so the CPU run of the device programs PROVES
@@ -315,6 +316,85 @@ struct Fp {
     } else {
       merge(r1, Y1, X1);
       merge(r2, Y2, X2);
+    }
+  }
+
+  // ---- dot product r = (a0*b0 + a1*b1) / R mod p in ONE pass: every CIOS row accumulates both
+  // multiplicands before its reduction half, so the sum of two products costs 3L^2 + L products (what
+  // two double-width products sharing one reduction cost) without a double-width temporary: the
+  // accumulator window is the same W + W registers as one product's.  Used where an F_p^2 product is
+  // split over a lane pair (pairlane.cuh): re = f0 l0 + (-f1) l1 on one lane, im = f0 l1 + f1 l0 on the
+  // other.  Requires a0 + a1 + p < R / 2 (window head-room); r < (a0 b0 + a1 b1) / R + p.
+  template <bool FIRST>
+  BGN_DEV static void row2(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t (&a0)[L], uint32_t s0,
+                           const uint32_t (&a1)[L], uint32_t s1, const uint32_t* __restrict__ pm, uint32_t np0) {
+    if (FIRST) {
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) mul_wide(Y[2 * k], Y[2 * k + 1], a0[2 * k + 1], s0);
+      Y[W - 2] = 0;
+      Y[W - 1] = 0;
+      BGN_UNROLL
+      for (int k = 0; k < KE; k++) mul_wide(X[2 * k], X[2 * k + 1], a0[2 * k], s0);
+      if (2 * KE < W) {
+        X[W - 2] = 0;
+        X[W - 1] = 0;
+      }
+    } else {
+      add_cc(X[0], X[0], Y[1]);
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) madc_wide_cc3(Y[2 * k], Y[2 * k + 1], a0[2 * k + 1], s0, Y[2 * k + 2], Y[2 * k + 3]);
+      addc(Y[W - 2], 0, 0);
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], a0[0], s0);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a0[2 * k], s0);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+    if (KO > 0) {
+      mad_wide_cc(Y[0], Y[1], a1[1], s1);
+      BGN_UNROLL
+      for (int k = 1; k < KO; k++) madc_wide_cc(Y[2 * k], Y[2 * k + 1], a1[2 * k + 1], s1);
+      addc(Y[W - 2], Y[W - 2], 0);
+    }
+    mad_wide_cc(X[0], X[1], a1[0], s1);
+    BGN_UNROLL
+    for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a1[2 * k], s1);
+    if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    uint32_t m = X[0] * np0;
+    mad_wide_cc(Y[0], Y[1], pm[1], m);
+    BGN_UNROLL
+    for (int k = 1; k < KO; k++) madc_wide_cc(Y[2 * k], Y[2 * k + 1], pm[2 * k + 1], m);
+    addc(Y[W - 2], Y[W - 2], 0);
+    mad_wide_cc(X[0], X[1], pm[0], m);
+    BGN_UNROLL
+    for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], pm[2 * k], m);
+    if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+  }
+  BGN_DEV static void dot2(uint32_t (&r)[L], const uint32_t (&a0)[L], const uint32_t (&b0)[L], const uint32_t (&a1)[L],
+                           const uint32_t (&b1)[L]) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    {
+      double A0 = BGN_GETB(a0), B0 = BGN_GETB(b0), A1 = BGN_GETB(a1), B1 = BGN_GETB(b1);
+      BGN_CHECK(2.0 * (A0 + A1 + 1.0) <= bgnsim::headroom, "dot product multiplicands too large");
+      BGN_CHECK(B0 <= bgnsim::headroom && B1 <= bgnsim::headroom, "dot product multiplier too large");
+      BGN_SETB(r, (A0 * B0 + A1 * B1) / bgnsim::headroom + 1.0);
+      bgnsim::ndot2++;
+    }
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row2<true>(X, Y, a0, b0[0], a1, b1[0], pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      row2<false>(Y, X, a0, b0[i], a1, b1[i], pm, np0);
+      row2<false>(X, Y, a0, b0[i + 1], a1, b1[i + 1], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row2<false>(Y, X, a0, b0[L - 1], a1, b1[L - 1], pm, np0);
+      merge(r, X, Y);
+    } else {
+      merge(r, Y, X);
     }
   }
 

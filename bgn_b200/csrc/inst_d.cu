@@ -1,0 +1,22 @@
+// inst_d.cu -- lane-pair kernels (pairlane.cuh) for one limb count (compile with -DBGN_L=<L>).
+// See ops.h: LOpsD.
+#define BGN_GROUP_D 1
+#include "kernels.cuh"
+#include "ops.h"
+#ifndef BGN_L
+#error "compile with -DBGN_L=<limbs>"
+#endif
+namespace {
+constexpr int LL = BGN_L;
+#define CFG cfg.grid, cfg.block, cfg.smem, cfg.stream
+cudaError_t upload(const FieldConsts* fc, const PairConsts* pc, cudaStream_t s) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_fc, fc, sizeof(FieldConsts), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbolAsync(c_pc, pc, sizeof(PairConsts), 0, cudaMemcpyHostToDevice, s);
+}
+void miller_fixed_pair(LaunchCfg cfg, const MillerFixedArgs& a) { k_miller_fixed_pair<LL><<<CFG>>>(a); }
+const LOpsD ops = {LL, upload, miller_fixed_pair};
+}  // namespace
+#define BGN_CAT2(a, b) a##b
+#define BGN_CAT(a, b) BGN_CAT2(a, b)
+extern "C" const LOpsD* BGN_CAT(bgn_opsD_, BGN_L)() { return &ops; }

@@ -9,6 +9,7 @@
 #pragma once
 #include "pairing.cuh"
 #include "lucas.cuh"
+#include "pairlane.cuh"
 
 #ifdef BGN_HOSTSIM
 static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -964,6 +965,19 @@ template <int L>
 __global__ void __launch_bounds__(256, 1) k_miller_fixed(const __grid_constant__ MillerFixedArgs a) {
   extern __shared__ uint32_t smem_dyn[];
   MillerFixed<L>::run(a, smem_dyn, threadIdx.x, blockDim.x, BGN_GID(size_t));
+}
+
+// the same pairing on a lane pair per evaluation point (pairlane.cuh): registers only, three shuffle
+// exchanges per Miller step
+template <int L>
+__global__ void __launch_bounds__(64) k_miller_fixed_pair(const __grid_constant__ MillerFixedArgs a) {
+  const size_t gid = BGN_GID(size_t);
+  const size_t e = gid >> 1;
+  const int s = (int)(gid & 1);
+  MillerFixedPair<L>::run(a, e, s, e < (size_t)a.count, [](uint32_t (&other)[L], const uint32_t (&mine)[L]) {
+#pragma unroll
+    for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
+  });
 }
 
 template <int L>

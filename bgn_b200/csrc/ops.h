@@ -51,6 +51,14 @@ struct LOpsC {
   void (*miller_record)(LaunchCfg, const uint32_t* px, const uint32_t* py, uint32_t* lines);
 };
 
+// inst_d.cu: kernels that split one item over a pair of lanes (pairlane.cuh), added in round 2 for
+// batches below one wave; their own translation unit for the same reason as inst_c.cu.
+struct LOpsD {
+  int L;
+  cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
+  void (*miller_fixed_pair)(LaunchCfg, const MillerFixedArgs&);
+};
+
 struct LOpsB {
   int L;
   cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
@@ -75,7 +83,8 @@ struct LOpsB {
 #define BGN_DECL_OPS(L)               \
   extern "C" const LOpsA* bgn_opsA_##L(); \
   extern "C" const LOpsB* bgn_opsB_##L(); \
-  extern "C" const LOpsC* bgn_opsC_##L();
+  extern "C" const LOpsC* bgn_opsC_##L(); \
+  extern "C" const LOpsD* bgn_opsD_##L();
 BGN_DECL_OPS(3)
 BGN_DECL_OPS(5)
 BGN_DECL_OPS(9)

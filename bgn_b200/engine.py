@@ -32,6 +32,14 @@ def _as_buf(x):
         return None, 0, None, False
     if _is_torch(x):
         assert x.is_contiguous(), "tensor must be contiguous"
+        if x.is_cuda:
+            # The library works on its own (blocking) stream, which is ordered after the legacy default
+            # stream only (include/bgn_b200.h).  A tensor produced on any other torch stream -- a side
+            # stream, or per-thread default streams -- must be complete before its pointer is handed over.
+            import torch
+            cur = torch.cuda.current_stream(x.device)
+            if cur.cuda_stream != 0:
+                cur.synchronize()
         return x.data_ptr(), x.numel() * x.element_size(), x, x.is_cuda
     if isinstance(x, (bytes, bytearray, memoryview)):
         a = np.frombuffer(x, dtype=np.uint8)
@@ -52,7 +60,7 @@ class Engine:
         st = self._lib.bgn_ctx_create(C.byref(prm), device, C.byref(self._ctx))
         if st != 0:
             self._ctx = C.c_void_p()
-            raise BgnError(st, "bgn_ctx_create failed (see stderr)")
+            raise BgnError(st, self._lib.bgn_global_last_error().decode() or "bgn_ctx_create failed")
         L, B, nbytes = C.c_int(), C.c_int(), C.c_int()
         self._lib.bgn_ctx_info(self._ctx, C.byref(L), C.byref(B), C.byref(nbytes))
         self.limbs, self.coord_bytes, self.scalar_bytes = L.value, B.value, nbytes.value
@@ -282,3 +290,13 @@ def bench_imad_peak(device: int, iters: int, blocks: int, threads: int):
     if st != 0:
         raise BgnError(st, "bgn_bench_imad_peak failed")
     return ms.value, ipt.value
+
+
+def bench_issue_mix(device: int, mix: int, iters: int, blocks: int, threads: int):
+    """-> (ms, [IMAD.WIDE, (IMAD.LO, IMAD.HI) pairs, FFMA, DFMA] instructions per thread)"""
+    lib = _cabi.load()
+    ms, per = C.c_float(), (C.c_double * 4)()
+    st = lib.bgn_bench_issue_mix(device, mix, iters, blocks, threads, C.byref(ms), per)
+    if st != 0:
+        raise BgnError(st, "bgn_bench_issue_mix failed")
+    return ms.value, list(per)

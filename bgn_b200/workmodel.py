@@ -100,6 +100,29 @@ def miller_fixed_products(p: int, n: int, l: int) -> int:
     return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1)) * full
 
 
+def miller_fixed_pair_counts(p: int, n: int, l: int):
+    """k_miller_fixed_pair (pairlane.cuh), BOTH lanes of one pairing together:
+    -> (dot products, plain Montgomery products incl. the inversion's glue).
+    Per step a line evaluation half and a dot-product half per lane, a squaring half per lane on
+    doubling steps after the first; final exponentiation: f0^2 | f1^2, f0 f1 and the scaling in both
+    lanes, the verified inversion (3 products) in both lanes, then g^l."""
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    lb, lw = l.bit_length() - 1, bin(l).count("1") - 1
+    dots = 2 * (D + A) + 2 * lw
+    muls = 2 * (D + A) + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
+    return dots, muls
+
+
+def miller_fixed_pair_products(p: int, n: int, l: int) -> int:
+    """32x32->64 products both lanes of one k_miller_fixed_pair pairing execute: a dot product is
+    3L^2 + L (arith.cuh: Fp::dot2), a Montgomery product 2L^2 + L."""
+    L = pick_limbs(p)
+    dots, muls = miller_fixed_pair_counts(p, n, l)
+    return dots * (3 * L * L + L) + muls * products_per_modmul(L)
+
+
 def canonical_pairing_modmuls(n: int, l: int) -> int:
     """PBC-like unshared schedule, one full pairing."""
     return 23 * n.bit_length() + 18 * bin(n).count("1") - 70 + 4 + 3 + 2 * l.bit_length() + 3 * bin(l).count("1") + 1

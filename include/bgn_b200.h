@@ -11,7 +11,11 @@
  *   - scalars are big-endian byte strings of a caller-stated fixed width.
  *   - every data pointer may be a HOST pointer or a CUDA DEVICE pointer on the
  *     context's device (detected with cudaPointerGetAttributes); host buffers are
- *     copied in/out inside the call.
+ *     copied in/out inside the call.  Device buffers are read and written on the
+ *     context's own stream, a blocking stream: it is ordered after work already queued
+ *     on the legacy default stream (stream 0) and every call returns only after its
+ *     device work has finished.  Inputs still being produced on ANY OTHER stream must
+ *     be synchronised by the caller before the call.
  *   - the caller owns all buffers; the library keeps no caller pointer after return.
  *   - all functions return 0 on success or a negative bgn_status; none throws or aborts.
  *   - a context is thread-compatible: calls are synchronous (they return after the
@@ -64,6 +68,9 @@ typedef struct {
 int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out);
 void bgn_ctx_destroy(bgn_ctx* ctx);
 const char* bgn_last_error(const bgn_ctx* ctx);
+/* Message of the last failure that had no context to report through -- bgn_ctx_create, or a call on a
+ * NULL context -- on the calling thread ("" if none).  bgn_last_error(NULL) returns the same string. */
+const char* bgn_global_last_error(void);
 
 /* Tuning knobs of a context (none changes any result):
  *   "enc_window"   8 | 16 | 24   fixed-base window of Q for Encrypt / level-1 re-randomisation.  16 (default):
@@ -72,7 +79,9 @@ const char* bgn_last_error(const bgn_ctx* ctx);
  *                                when the table does not fit the free device memory.  The table is (re)built on
  *                                the next randomised encryption.
  *   "dec_lucas"    0 | 1         Decrypt through the Lucas ladder when one giant step suffices (default 1)
- *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)                            */
+ *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)
+ *   "fixed_pair"   -1 | 0 | 1    e(., P) with one pairing split over a pair of lanes: -1 (default) below the
+ *                                measured batch-size crossover, 0 never, 1 always                              */
 int bgn_ctx_set_option(bgn_ctx* ctx, const char* name, long value);
 
 /* limbs: 32-bit limbs of the field; coord_bytes: B; scalar_bytes: ceil(bits(n)/8). */
@@ -172,6 +181,12 @@ int bgn_bench_mulmod(bgn_ctx* ctx, int ilp, int iters, int blocks, int threads, 
 /* Peak rate of the 32x32+64 multiply-add instruction (IMAD.WIDE.U32) on `device`:
  * blocks*threads threads issue iters*64 independent-chain instructions each. */
 int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread);
+
+/* Issue-mix microbenchmark on `device`: which instruction classes share the integer-multiply pipe.
+ * mix: 0 IMAD.WIDE | 1 IMAD.LO+IMAD.HI pairs | 2 both | 3 FFMA | 4 IMAD.WIDE+FFMA | 5 DFMA |
+ *      6 IMAD.WIDE+DFMA | 7..9 other ratios (api.cu).  per_thread[4] receives the instructions of each
+ * class one thread issued: {IMAD.WIDE, (LO,HI) pairs, FFMA, DFMA}; *ms the device time. */
+int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads, float* ms, double* per_thread);
 
 #ifdef __cplusplus
 }

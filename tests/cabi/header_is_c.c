@@ -18,7 +18,8 @@ int main(void) {
       (fn)bgn_g1_blind_batch,      (fn)bgn_gt_blind_batch,     (fn)bgn_multconstpoly_batch,
       (fn)bgn_evalpoly_batch,      (fn)bgn_make_poly_l2_batch, (fn)bgn_timing_enable,
       (fn)bgn_timing_reset,        (fn)bgn_timing_get,         (fn)bgn_timing_last_call,
-      (fn)bgn_bench_mulmod,        (fn)bgn_bench_imad_peak};
+      (fn)bgn_bench_mulmod,        (fn)bgn_bench_imad_peak,    (fn)bgn_global_last_error,
+      (fn)bgn_bench_issue_mix};
   unsigned n = (unsigned)(sizeof(syms) / sizeof(syms[0])), ok = 0, i;
   for (i = 0; i < n; i++) ok += syms[i] != 0;
   /* a null context is rejected with a status, never a crash */

@@ -7,11 +7,48 @@
 #ifndef BGN_L
 #define BGN_L 17  // only selects the default loop shape of the fused routines (pairing.cuh)
 #endif
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../bgn_b200/csrc/kernels.cuh"
 
 namespace {
+// Two lanes of a lane-pair kernel (pairlane.cuh) as two threads that run STRICTLY one at a time: a lane
+// holds the mutex while it computes and gives it up only inside an exchange, where it waits for its
+// partner's value -- the warp shuffle of the CUDA kernel.  The program text is the device's own
+// (`run` with an exchange functor); only the exchange differs.  Bounds travel with the values.
+template <int L>
+struct LanePair {
+  std::mutex m;
+  std::condition_variable cv;
+  uint32_t box[2][2][L];
+  double bnd[2][2];
+  long deposited[2] = {0, 0};
+  void xchg(int s, uint32_t (&other)[L], const uint32_t (&mine)[L], std::unique_lock<std::mutex>& lk) {
+    const long r = deposited[s];
+    for (int j = 0; j < L; j++) box[s][r & 1][j] = mine[j];
+    bnd[s][r & 1] = BGN_GETB(mine);
+    deposited[s] = r + 1;
+    cv.notify_all();
+    cv.wait(lk, [&] { return deposited[1 - s] > r; });
+    for (int j = 0; j < L; j++) other[j] = box[1 - s][r & 1][j];
+    BGN_SETB(other, bnd[1 - s][r & 1]);
+  }
+  template <typename Fn>
+  void run(Fn lane_program) {
+    auto body = [&](int s) {
+      std::unique_lock<std::mutex> lk(m);
+      lane_program(s, [&](uint32_t (&other)[L], const uint32_t (&mine)[L]) { xchg(s, other, mine, lk); });
+      cv.notify_all();
+    };
+    std::thread t1(body, 1);
+    body(0);
+    t1.join();
+  }
+};
+
 template <int L>
 void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
   std::vector<uint32_t> smem(MillerTeam<L>::smem_words(nt) + 8);
@@ -147,6 +184,12 @@ int hs_miller_fixed(int L, const MillerFixedArgs* a, int nt) {
     for (int e = 0; e < a->count; e++) MillerFixed<LL>::run(*a, smem.data(), e % nt, nt, (size_t)e);
   })
 }
+int hs_miller_fixed_pair(int L, const MillerFixedArgs* a) {
+  FOR_L(L, for (int e = 0; e < a->count; e++) {
+    LanePair<LL> lp;
+    lp.run([&](int s, auto xchg) { MillerFixedPair<LL>::run(*a, (size_t)e, s, true, xchg); });
+  })
+}
 int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* lines) {
   FOR_L(L, MillerFixed<LL>::record(px, py, lines))
 }
@@ -171,7 +214,8 @@ void hs_wide_count(uint64_t* out, int reset) {
   out[0] = bgnsim::nmulw;
   out[1] = bgnsim::nredc;
   out[2] = bgnsim::nmulk;
-  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = 0;
+  out[3] = bgnsim::ndot2;
+  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = bgnsim::ndot2 = 0;
 }
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;

@@ -126,7 +126,7 @@ def build(loop: Optional[int] = None, extra: Sequence[str] = (), tag: str = "") 
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         flags = [] if loop is None else ["-DBGN_MILLER_LOOP=%d" % loop, "-DBGN_MILLER_LOOP_A=%d" % loop]
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC"] + flags + list(extra) + ["-o", so, src])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread"] + flags + list(extra) + ["-o", so, src])
     return so
 
 
@@ -280,6 +280,16 @@ class Sim:
         oim = np.zeros_like(ore)
         a = MillerFixedArgs(P32(lines), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), count)
         assert lib().hs_miller_fixed(self.L, C.byref(a), nt) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
+
+    def pair_fixed_pair(self, lines, Epts):
+        """k_miller_fixed_pair: the same pairing, a lane pair per evaluation point (pairlane.cuh)"""
+        count = len(Epts)
+        Ex, Ey, Ei = self.g1_arrays(Epts)
+        ore = np.zeros((count, self.L), dtype=np.uint32)
+        oim = np.zeros_like(ore)
+        a = MillerFixedArgs(P32(lines), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), count)
+        assert lib().hs_miller_fixed_pair(self.L, C.byref(a)) == 0
         return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
     def multpoly(self, c1, d1, c2, d2, count):

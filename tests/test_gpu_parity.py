@@ -184,6 +184,44 @@ def test_make_poly_l2(golden):
     assert e.make_poly_l2_batch(buf(v["in"]), v["d"], v["count"]).tobytes() == unhex(v["out"])
 
 
+@pytest.mark.parametrize("kb", [128, 512, 1024])
+def test_fixed_pairing_lane_pair_equals_one_thread(kb):
+    """e(., P) on a pair of lanes per point (k_miller_fixed_pair, pairlane.cuh) gives the bytes of the
+    one-thread kernel, of the general Miller kernel and of the oracle: odd counts (a warp with a
+    half-used pair and idle pairs), O inputs, level-1 decryption through it."""
+    from bgn_b200 import Engine
+    from oracle import bgn_oracle as O
+    g = load_golden(kb)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    e.set_secret(int(g["q1"], 16), g["msg_space"])
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    P = O.g1_from_bytes(bytes.fromhex(g["P"]), par)
+    rng = random.Random(kb)
+    count = 77 if kb < 1024 else 19
+    xs = np.array([rng.randrange(-40, 40) for _ in range(count)], dtype=np.int64)
+    xs[3] = 0
+    cts = e.encrypt_batch(xs, e.scalars_be([rng.randrange(par.n) for _ in range(count)]))
+    cts[5 * e.elem_bytes: 6 * e.elem_bytes] = 0  # O
+    outs = {}
+    for mode in (1, 0):
+        e.set_option("fixed_pair", mode)
+        outs[mode] = e.make_l2_batch(cts).tobytes()
+        vals, st = e.decrypt_batch(cts, False)
+        assert not st.any() and vals.tolist() == [0 if i == 5 else int(x) for i, x in enumerate(xs)]
+    e.set_option("fixed_lines", 0)
+    general = e.make_l2_batch(cts).tobytes()
+    assert outs[1] == outs[0] == general
+    eb = e.elem_bytes
+    for i in (0, 3, 5, count - 1):
+        pt = O.g1_from_bytes(cts[i * eb:(i + 1) * eb].tobytes(), par)
+        assert outs[1][i * eb:(i + 1) * eb] == O.gt_to_bytes(O.pairing(pt, P, par), par)
+    v = g["make_poly_l2"]
+    e.set_option("fixed_lines", 1)
+    e.set_option("fixed_pair", 1)
+    assert e.make_poly_l2_batch(buf(v["in"]), v["d"], v["count"]).tobytes() == unhex(v["out"])
+    e.close()
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)

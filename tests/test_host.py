@@ -59,7 +59,11 @@ def test_cabi_argument_errors_without_gpu():
     assert lib.bgn_ctx_info(None, None, None, None) == _cabi.BGN_E_BADARG
     assert lib.bgn_encrypt_batch(None, None, None, 1, None) == _cabi.BGN_E_BADARG
     assert lib.bgn_ctx_create(None, 0, ctypes.byref(ctypes.c_void_p())) == _cabi.BGN_E_BADARG
-    assert lib.bgn_last_error(None) == b"null context"
+    # failures without a context are reported through the per-thread string (no stderr, no abort)
+    assert lib.bgn_global_last_error() == b"bgn_ctx_create: null argument or l == 0"
+    assert lib.bgn_last_error(None) == lib.bgn_global_last_error()
+    assert lib.bgn_encrypt_batch(None, None, None, 1, None) == _cabi.BGN_E_BADARG
+    assert lib.bgn_global_last_error() == b"null context"
     lib.bgn_ctx_destroy(None)  # no-op
 
 

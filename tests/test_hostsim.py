@@ -374,6 +374,38 @@ def test_sim_pair_fixed(kb):
 
 
 @pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_pair_fixed_lane_pair(kb):
+    """k_miller_fixed_pair (pairlane.cuh: one pairing on a pair of lanes, squaring / line evaluation /
+    dot-product halves swapped by shuffles) against the golden makeL2 vectors, the one-thread kernel
+    and the oracle, incl. O; the run is also the range proof of its relaxed arithmetic and pins its
+    work model: per point 2 Montgomery products and 1 dot product per lane and step."""
+    import ctypes as C
+    g, par, S, tabs = setup(kb)
+    if "linesP" not in tabs:
+        tabs["linesP"] = S.record_lines(S.P)
+    v = g["make_l2"]
+    pts = g1s(par, v["a"])
+    wide = (C.c_uint64 * 4)()
+    sim.lib().hs_wide_count(wide, 1)
+    sim.lib().hs_mul_count(1)
+    S.range_report()
+    assert S.pair_fixed_pair(tabs["linesP"], pts) == gts(par, v["out"])
+    hi, headroom, unknown, viol = S.range_report()
+    assert viol == 0 and hi <= 16.0, (hi, viol)
+    sim.lib().hs_wide_count(wide, 1)
+    nmul = sim.lib().hs_mul_count(1)
+    from bgn_b200 import workmodel
+    finite = sum(1 for pt in pts if pt is not None)
+    if finite == len(pts):
+        exp_dot, exp_mul = workmodel.miller_fixed_pair_counts(par.p, par.n, par.l)
+        assert (wide[3], nmul) == (exp_dot * len(pts), exp_mul * len(pts)), (wide[3], nmul, exp_dot, exp_mul)
+    if kb < 512:
+        pts = g1s(par, g["g1_add"]["out"])
+        assert S.pair_fixed_pair(tabs["linesP"], pts) == [O.pairing(pt, S.P, par) for pt in pts]
+        assert S.pair_fixed_pair(tabs["linesP"], pts) == S.pair_fixed(tabs["linesP"], pts, nt=3)
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
 def test_sim_inv_gcd(kb):
     """F<L>::inv_gcd (constant-time binary GCD on plain ALU instructions) equals the Fermat inverse
     and the integer inverse, incl. 0 -> 0, 1, p - 1 and a value in [p, 2p)."""
