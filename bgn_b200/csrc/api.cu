@@ -152,6 +152,9 @@ struct bgn_ctx {
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
+  size_t pair_duo_cap = (size_t)-1;  // pairings one wave of k_pair_duo holds (occupancy query, cached)
+  int pair_duo = -1;           // general pairings on two warps each (pairwarp.cuh): -1 = by batch size, 0 = never, 1 = always (BGN_PAIR_DUO)
+  size_t fixed_pair_cap = 0;   // pairings one wave of k_miller_fixed_pair holds (occupancy query, cached)
   int fixed_pair = -1;         // e(., P) on a lane pair per point (pairlane.cuh): -1 = by batch size, 0 = never, 1 = always (BGN_FIXED_PAIR)
   bool dec_lucas = true;       // Decrypt through the Lucas ladder when one giant step suffices (BGN_DEC_LUCAS=0: off)
   // decryption
@@ -541,6 +544,40 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   t.done();
 }
 
+// out[i] = e(A[i], B[i]) with two warps per 32 pairings (pairwarp.cuh); `pairs` warp pairs per block
+void run_pair_duo(bgn_ctx* c, const G1Arr& A, const G1Arr& Bv, size_t count, const GtArr& out) {
+  if (!count) return;
+  PairDuoArgs a;
+  a.Mx = A.x;
+  a.My = A.y;
+  a.Minf = A.inf;
+  a.Ex = Bv.x;
+  a.Ey = Bv.y;
+  a.Einf = Bv.inf;
+  a.out_re = out.re;
+  a.out_im = out.im;
+  a.count = (int)count;
+  const int np = 32;  // one warp pair per block: small batches spread over the SMs pair by pair
+  size_t smem = c->Do->pair_duo_smem_bytes(np) + 16;
+  Timer t(c, "k_pair_duo");
+  CK(c->Do->pair_duo_set_smem(smem));
+  c->Do->pair_duo(cfg(c, nblk(count, np), 2 * np, smem), a);
+  t.done();
+}
+// pairings one wave of k_pair_duo holds (0: the kernel does not fit this key's shared-memory state)
+size_t pair_duo_capacity(bgn_ctx* c) {
+  if (c->pair_duo_cap == (size_t)-1) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    size_t smem = c->Do->pair_duo_smem_bytes(32) + 16;
+    c->pair_duo_cap = 0;
+    if (smem <= 227 * 1024 - 64 && c->Do->pair_duo_set_smem(smem) == cudaSuccess)
+      c->pair_duo_cap = (size_t)sms * std::max(0, c->Do->pair_duo_blocks_per_sm(64, smem)) * 32;
+    cudaGetLastError();
+  }
+  return c->pair_duo_cap;
+}
+
 // lines of the Miller loop of P, recorded once per key (k_miller_record: point arithmetic only)
 int miller_nsteps(const bgn_ctx* c) {
   int n = 0;
@@ -578,11 +615,14 @@ void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out
   a.out_re = out.re;
   a.out_im = out.im;
   a.count = (int)count;
-  // Below kFixedPairMax points one thread per pairing cannot give every scheduler two warps (148 SMs x
-  // 4 schedulers x 64 lanes): split each pairing over a lane pair (pairlane.cuh).  The crossover is
-  // measured (profiles/r02_fixed_pair_ab.json).
-  const size_t kFixedPairMax = (size_t)sms * 256;
-  if (c->fixed_pair > 0 || (c->fixed_pair < 0 && count < kFixedPairMax)) {
+  // Which mapping (measured A/B: profiles/r02_fixedpair_ab_512.json, _1024.json): a lane pair per pairing
+  // (pairlane.cuh, registers only) is the faster one at every batch size -- 1.8x for a single pairing,
+  // 0.77 against 0.53 of the IMAD.WIDE peak at 2^14, 0.91 against 0.78 at 2^17 -- except where the batch
+  // is just over one wave of the pair kernel but still fits ONE wave of the one-thread kernel (148 x 256
+  // threads); there the second, nearly empty wave of the pair kernel costs more than it saves.
+  if (c->fixed_pair_cap == 0) c->fixed_pair_cap = (size_t)sms * std::max(1, c->Do->miller_fixed_pair_blocks_per_sm()) * 32;
+  const bool pair_auto = count <= c->fixed_pair_cap || count > (size_t)sms * 256;
+  if (c->fixed_pair > 0 || (c->fixed_pair < 0 && pair_auto)) {
     Timer t(c, "k_miller_fixed_pair");
     c->Do->miller_fixed_pair(cfg(c, nblk(2 * count, 64), 64, 0), a);
     t.done();
@@ -829,9 +869,9 @@ int guarded(bgn_ctx* c, Fn fn) {
 // them into one IMAD.WIDE), NF FFMA and ND DFMA, each class on its own independent accumulators,
 // interleaved in program order.  Comparing a mix's time with the times of its parts shows which
 // classes share an issue pipe: pipes that co-issue give max(parts), a shared pipe gives sum(parts).
-template <int NW, int NLH, int NF, int ND>
+template <int NW, int NLO, int NHI, int NF, int ND>
 __global__ void __launch_bounds__(256) k_issue_mix(uint32_t* out, int iters, uint32_t seed) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x, a2 = a ^ 0x5555u, b2 = b + 77u;
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x, b2 = b + 77u;
   uint32_t w[16], lo[8], hi[8];
   float f[8], fx = (float)(threadIdx.x & 7) * 1.0e-3f + 1.0f, fy = 0.999f;
   double d[8], dx = (double)(threadIdx.x & 7) * 1.0e-3 + 1.0, dy = 0.999;
@@ -842,18 +882,17 @@ __global__ void __launch_bounds__(256) k_issue_mix(uint32_t* out, int iters, uin
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int rep = 0; rep < 8; rep++) {
-      constexpr int M = NW > NLH ? (NW > NF ? (NW > ND ? NW : ND) : (NF > ND ? NF : ND))
-                                 : (NLH > NF ? (NLH > ND ? NLH : ND) : (NF > ND ? NF : ND));
+      constexpr int M0 = NW > NLO ? NW : NLO, M1 = NHI > NF ? NHI : NF, M2 = M0 > M1 ? M0 : M1, M = M2 > ND ? M2 : ND;
 #pragma unroll
       for (int k = 0; k < M; k++) {
         if (k < NW)
           asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
                        : "+r"(w[2 * (k & 7)]), "+r"(w[2 * (k & 7) + 1])
                        : "r"(a), "r"(b));
-        if (k < NLH) {
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k & 7]) : "r"(a2), "r"(b));
-          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k & 7]) : "r"(a), "r"(b2));
-        }
+        // the accumulator is also the multiplicand, so neither product is loop-invariant (ptxas hoists
+        // an invariant mad.hi out of the loop and leaves only its additions)
+        if (k < NLO) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[k & 7]) : "r"(b), "r"(a));
+        if (k < NHI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(hi[k & 7]) : "r"(b2), "r"(a));
         if (k < NF) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f[k & 7]) : "f"(fx), "f"(fy));
         if (k < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[k & 7]) : "d"(dx), "d"(dy));
       }
@@ -896,6 +935,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* nt = getenv("BGN_NORM_THREADS")) c->norm_threads = std::max(128, atoi(nt));
     if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
     if (const char* fp = getenv("BGN_FIXED_PAIR")) c->fixed_pair = atoi(fp);
+    if (const char* pd = getenv("BGN_PAIR_DUO")) c->pair_duo = atoi(pd);
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -1089,6 +1129,8 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->fixed_lines = value != 0;
   } else if (k == "fixed_pair") {
     c->fixed_pair = value < 0 ? -1 : (value != 0);
+  } else if (k == "pair_duo") {
+    c->pair_duo = value < 0 ? -1 : (value != 0);
   } else {
     c->err = "unknown option " + k;
     return BGN_E_BADARG;
@@ -1366,7 +1408,13 @@ static void pair_common(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t c
     const uint8_t* db = stage_in(c, b, count * 2 * c->B);
     G1Arr Bv = g1_alloc(c, count);
     g1_from_bytes(c, db, count, Bv);
-    run_miller(c, A, 1, Bv, 1, 0, count, 1, R);
+    // a batch that fits one wave of the two-warp kernel leaves the one-thread kernel short of warps
+    // (measured A/B: profiles/r02_pair_duo_ab_*.json)
+    const size_t cap = pair_duo_capacity(c);
+    if (cap && (c->pair_duo > 0 || (c->pair_duo < 0 && count <= cap)))
+      run_pair_duo(c, A, Bv, count, R);
+    else
+      run_miller(c, A, 1, Bv, 1, 0, count, 1, R);
   } else if (c->linesP && c->fixed_lines) {
     run_miller_fixed(c, A, count, R);
   } else {
@@ -1944,10 +1992,12 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, int iters, uin
 }
 
 // mix: 0 WIDE x8 | 1 (LO,HI) x8 | 2 WIDE x8 + (LO,HI) x8 | 3 FFMA x8 | 4 WIDE x8 + FFMA x8 | 5 DFMA x8 |
-//      6 WIDE x8 + DFMA x8 | 7 WIDE x8 + (LO,HI) x4 | 8 WIDE x8 + DFMA x4 | 9 WIDE x4 + DFMA x8
-// per_thread[4] = instructions of each class a thread issues: {IMAD.WIDE, (LO,HI) pairs, FFMA, DFMA}
+//      6 WIDE x8 + DFMA x8 | 7 WIDE x8 + (LO,HI) x4 | 8 WIDE x8 + DFMA x4 | 9 WIDE x4 + DFMA x8 |
+//      10 LO x8 | 11 HI x8 | 12 WIDE x8 + LO x8 | 13 WIDE x8 + HI x8
+// per_thread[5] = instructions of each class a thread issues: {IMAD.WIDE, IMAD.LO, IMAD.HI, FFMA, DFMA}
 int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads, float* ms, double* per_thread) {
   if (!ms || !per_thread || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256 || device < 0) return BGN_E_BADARG;
+  if (mix < 0 || mix > 13) return BGN_E_BADARG;
   std::lock_guard<std::mutex> lk(dev_mu(device));
   if (cudaSetDevice(device) != cudaSuccess) return BGN_E_CUDA;
   uint32_t* d = nullptr;
@@ -1955,24 +2005,28 @@ int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads,
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
-  int nw = 0, nlh = 0, nf = 0, nd = 0;
+  int nw = 0, nlo = 0, nhi = 0, nf = 0, nd = 0;
   auto go = [&](int it) {
     switch (mix) {
-#define BGN_MIX(id, W_, LH_, F_, D_)                                  \
-  case id:                                                            \
-    nw = W_, nlh = LH_, nf = F_, nd = D_;                             \
-    k_issue_mix<W_, LH_, F_, D_><<<blocks, threads>>>(d, it, 12345u); \
+#define BGN_MIX(id, W_, LO_, HI_, F_, D_)                                  \
+  case id:                                                                 \
+    nw = W_, nlo = LO_, nhi = HI_, nf = F_, nd = D_;                       \
+    k_issue_mix<W_, LO_, HI_, F_, D_><<<blocks, threads>>>(d, it, 12345u); \
     break;
-      BGN_MIX(0, 8, 0, 0, 0)
-      BGN_MIX(1, 0, 8, 0, 0)
-      BGN_MIX(2, 8, 8, 0, 0)
-      BGN_MIX(3, 0, 0, 8, 0)
-      BGN_MIX(4, 8, 0, 8, 0)
-      BGN_MIX(5, 0, 0, 0, 8)
-      BGN_MIX(6, 8, 0, 0, 8)
-      BGN_MIX(7, 8, 4, 0, 0)
-      BGN_MIX(8, 8, 0, 0, 4)
-      BGN_MIX(9, 4, 0, 0, 8)
+      BGN_MIX(0, 8, 0, 0, 0, 0)
+      BGN_MIX(1, 0, 8, 8, 0, 0)
+      BGN_MIX(2, 8, 8, 8, 0, 0)
+      BGN_MIX(3, 0, 0, 0, 8, 0)
+      BGN_MIX(4, 8, 0, 0, 8, 0)
+      BGN_MIX(5, 0, 0, 0, 0, 8)
+      BGN_MIX(6, 8, 0, 0, 0, 8)
+      BGN_MIX(7, 8, 4, 4, 0, 0)
+      BGN_MIX(8, 8, 0, 0, 0, 4)
+      BGN_MIX(9, 4, 0, 0, 0, 8)
+      BGN_MIX(10, 0, 8, 0, 0, 0)
+      BGN_MIX(11, 0, 0, 8, 0, 0)
+      BGN_MIX(12, 8, 8, 0, 0, 0)
+      BGN_MIX(13, 8, 0, 8, 0, 0)
 #undef BGN_MIX
       default:
         break;
@@ -1988,10 +2042,10 @@ int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads,
   cudaEventDestroy(b);
   cudaFree(d);
   per_thread[0] = (double)iters * 8 * nw;
-  per_thread[1] = (double)iters * 8 * nlh;
-  per_thread[2] = (double)iters * 8 * nf;
-  per_thread[3] = (double)iters * 8 * nd;
-  if (mix < 0 || mix > 9) return BGN_E_BADARG;
+  per_thread[1] = (double)iters * 8 * nlo;
+  per_thread[2] = (double)iters * 8 * nhi;
+  per_thread[3] = (double)iters * 8 * nf;
+  per_thread[4] = (double)iters * 8 * nd;
   return e == cudaSuccess ? BGN_OK : BGN_E_CUDA;
 }
 

@@ -15,7 +15,23 @@ cudaError_t upload(const FieldConsts* fc, const PairConsts* pc, cudaStream_t s) 
   return cudaMemcpyToSymbolAsync(c_pc, pc, sizeof(PairConsts), 0, cudaMemcpyHostToDevice, s);
 }
 void miller_fixed_pair(LaunchCfg cfg, const MillerFixedArgs& a) { k_miller_fixed_pair<LL><<<CFG>>>(a); }
-const LOpsD ops = {LL, upload, miller_fixed_pair};
+int miller_fixed_pair_blocks_per_sm() {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_miller_fixed_pair<LL>, 64, 0) != cudaSuccess) n = 0;
+  return n;
+}
+size_t pair_duo_smem_bytes(int np) { return MillerDuo<LL>::smem_words(np) * 4; }
+cudaError_t pair_duo_set_smem(size_t smem) {
+  return cudaFuncSetAttribute(k_pair_duo<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+int pair_duo_blocks_per_sm(int threads, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair_duo<LL>, threads, smem) != cudaSuccess) n = 0;
+  return n;
+}
+void pair_duo(LaunchCfg cfg, const PairDuoArgs& a) { k_pair_duo<LL><<<CFG>>>(a); }
+const LOpsD ops = {LL, upload, miller_fixed_pair, miller_fixed_pair_blocks_per_sm, pair_duo_smem_bytes, pair_duo_set_smem,
+                   pair_duo_blocks_per_sm, pair_duo};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

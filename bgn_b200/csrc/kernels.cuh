@@ -10,6 +10,7 @@
 #include "pairing.cuh"
 #include "lucas.cuh"
 #include "pairlane.cuh"
+#include "pairwarp.cuh"
 
 #ifdef BGN_HOSTSIM
 static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -978,6 +979,37 @@ __global__ void __launch_bounds__(64) k_miller_fixed_pair(const __grid_constant_
 #pragma unroll
     for (int j = 0; j < L; j++) other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
   });
+}
+
+// a general pairing on two warps (pairwarp.cuh): even warps advance the Miller points of 32 pairings
+// and publish the line ingredients, odd warps fold the lines into the accumulators one step behind;
+// one named barrier per step and warp pair
+template <int L>
+__global__ void __launch_bounds__(256) k_pair_duo(const __grid_constant__ PairDuoArgs a) {
+  extern __shared__ uint32_t smem_dyn[];
+  const int np = blockDim.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = (warp >> 1) * 32 + lane;
+  MillerDuo<L> T(a, smem_dyn, np, pt, (size_t)blockIdx.x * np + pt);
+  const int bar_id = 1 + (warp >> 1);
+  auto sync = [=] {
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  };
+  if ((warp & 1) == 0) {
+    T.x_init();
+    MillerDuo<L>::for_steps([&](int s, int op) {
+      T.x_step(op, s & 1);
+      sync();
+    });
+  } else {
+    T.f_init();
+    MillerDuo<L>::for_steps([&](int s, int op) {
+      sync();
+      T.f_step(op, s & 1, s == 0);
+    });
+    T.f_finish();
+  }
 }
 
 template <int L>

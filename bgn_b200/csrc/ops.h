@@ -57,6 +57,12 @@ struct LOpsD {
   int L;
   cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
   void (*miller_fixed_pair)(LaunchCfg, const MillerFixedArgs&);
+  int (*miller_fixed_pair_blocks_per_sm)();  // resident 64-thread blocks of k_miller_fixed_pair per SM (register-bound)
+  // general pairing on two warps (pairwarp.cuh); blocks are `pairs` warp pairs = 32 * pairs pairings
+  size_t (*pair_duo_smem_bytes)(int pairings_per_block);
+  cudaError_t (*pair_duo_set_smem)(size_t smem);
+  int (*pair_duo_blocks_per_sm)(int threads, size_t smem);
+  void (*pair_duo)(LaunchCfg, const PairDuoArgs&);
 };
 
 struct LOpsB {

@@ -66,6 +66,16 @@ struct MillerFixedArgs {
   int count;
 };
 
+// General pairing on two warps per 32 pairings (pairwarp.cuh): out[i] = e(M[i], E[i])
+struct PairDuoArgs {
+  const uint32_t *Mx, *My;  // Miller-side points, affine Montgomery [count][L]
+  const uint8_t* Minf;
+  const uint32_t *Ex, *Ey;  // evaluation-side points
+  const uint8_t* Einf;
+  uint32_t *out_re, *out_im;  // [count][L]
+  int count;
+};
+
 struct EncArgs {
   const int64_t* x;       // plaintext scalars (signed, |x| < 2^63)
   const uint8_t* r_be;    // randomness, big-endian, rbytes each (may be null: r = 0)

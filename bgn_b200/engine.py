@@ -293,9 +293,9 @@ def bench_imad_peak(device: int, iters: int, blocks: int, threads: int):
 
 
 def bench_issue_mix(device: int, mix: int, iters: int, blocks: int, threads: int):
-    """-> (ms, [IMAD.WIDE, (IMAD.LO, IMAD.HI) pairs, FFMA, DFMA] instructions per thread)"""
+    """-> (ms, [IMAD.WIDE, IMAD.LO, IMAD.HI, FFMA, DFMA] instructions per thread)"""
     lib = _cabi.load()
-    ms, per = C.c_float(), (C.c_double * 4)()
+    ms, per = C.c_float(), (C.c_double * 5)()
     st = lib.bgn_bench_issue_mix(device, mix, iters, blocks, threads, C.byref(ms), per)
     if st != 0:
         raise BgnError(st, "bgn_bench_issue_mix failed")

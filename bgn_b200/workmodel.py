@@ -123,6 +123,29 @@ def miller_fixed_pair_products(p: int, n: int, l: int) -> int:
     return dots * (3 * L * L + L) + muls * products_per_modmul(L)
 
 
+def pair_duo_counts(p: int, n: int, l: int):
+    """k_pair_duo (pairwarp.cuh), BOTH warps' lanes of one pairing together:
+    -> (fused Montgomery products, double-width products, separate reductions).
+    Doubling step: X 9, F 4 (line at B) + 2 (sqr2, not on the first step); addition step: X 11, F 3;
+    every step one F_p^2 product f * l: 3 double-width products + 2 reductions up to 17 limbs (lazy), 3
+    fused products beyond; final exponentiation of one slot as k_miller_fixed."""
+    L = pick_limbs(p)
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    mm = D * (9 + 4) + (D - 1) * 2 + A * (11 + 3) + final_exp_modmuls(p, l, L, 1, 1) + 1  # + the inversion's check
+    if line_lazy(L):
+        return mm, 3 * (D + A), 2 * (D + A)
+    return mm + 3 * (D + A), 0, 0
+
+
+def pair_duo_products(p: int, n: int, l: int) -> int:
+    """32x32->64 products one k_pair_duo pairing executes (both warps)"""
+    L = pick_limbs(p)
+    mm, mw, rd = pair_duo_counts(p, n, l)
+    return mm * products_per_modmul(L) + mw * L * L + rd * (L * L + L)
+
+
 def canonical_pairing_modmuls(n: int, l: int) -> int:
     """PBC-like unshared schedule, one full pairing."""
     return 23 * n.bit_length() + 18 * bin(n).count("1") - 70 + 4 + 3 + 2 * l.bit_length() + 3 * bin(l).count("1") + 1

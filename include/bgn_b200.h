@@ -81,7 +81,9 @@ const char* bgn_global_last_error(void);
  *   "dec_lucas"    0 | 1         Decrypt through the Lucas ladder when one giant step suffices (default 1)
  *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)
  *   "fixed_pair"   -1 | 0 | 1    e(., P) with one pairing split over a pair of lanes: -1 (default) below the
- *                                measured batch-size crossover, 0 never, 1 always                              */
+ *                                measured batch-size crossover, 0 never, 1 always
+ *   "pair_duo"     -1 | 0 | 1    e(a, b) (bgn_pair_batch) with one pairing split over two warps: -1 (default)
+ *                                for batches within one wave of that kernel, 0 never, 1 always                */
 int bgn_ctx_set_option(bgn_ctx* ctx, const char* name, long value);
 
 /* limbs: 32-bit limbs of the field; coord_bytes: B; scalar_bytes: ceil(bits(n)/8). */
@@ -183,9 +185,10 @@ int bgn_bench_mulmod(bgn_ctx* ctx, int ilp, int iters, int blocks, int threads, 
 int bgn_bench_imad_peak(int device, int iters, int blocks, int threads, float* ms, double* instr_per_thread);
 
 /* Issue-mix microbenchmark on `device`: which instruction classes share the integer-multiply pipe.
- * mix: 0 IMAD.WIDE | 1 IMAD.LO+IMAD.HI pairs | 2 both | 3 FFMA | 4 IMAD.WIDE+FFMA | 5 DFMA |
- *      6 IMAD.WIDE+DFMA | 7..9 other ratios (api.cu).  per_thread[4] receives the instructions of each
- * class one thread issued: {IMAD.WIDE, (LO,HI) pairs, FFMA, DFMA}; *ms the device time. */
+ * mix: 0 IMAD.WIDE | 1 IMAD.LO+IMAD.HI | 2 both | 3 FFMA | 4 IMAD.WIDE+FFMA | 5 DFMA | 6 IMAD.WIDE+DFMA |
+ *      7..9 other ratios | 10 IMAD.LO | 11 IMAD.HI | 12 IMAD.WIDE+IMAD.LO | 13 IMAD.WIDE+IMAD.HI (api.cu).
+ * per_thread[5] receives the instructions of each class one thread issued:
+ * {IMAD.WIDE, IMAD.LO, IMAD.HI, FFMA, DFMA}; *ms the device time. */
 int bgn_bench_issue_mix(int device, int mix, int iters, int blocks, int threads, float* ms, double* per_thread);
 
 #ifdef __cplusplus

@@ -73,6 +73,29 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
     for (auto& t : T) t.finalize();
   }
 }
+// k_pair_duo (pairwarp.cuh): the X warp runs one step AHEAD of the F warp -- the most the one
+// barrier per step allows -- so the run also checks the double buffering of the published values
+template <int L>
+void sim_pair_duo(const PairDuoArgs& a, int np) {
+  std::vector<uint32_t> smem(MillerDuo<L>::smem_words(np) + 8);
+  std::vector<int> ops;
+  MillerDuo<L>::for_steps([&](int, int op) { ops.push_back(op); });
+  const int S = (int)ops.size();
+  for (int b = 0; b * np < a.count; b++) {
+    std::vector<MillerDuo<L>> T;
+    T.reserve(np);
+    for (int pt = 0; pt < np; pt++) T.emplace_back(a, smem.data(), np, pt, (size_t)b * np + pt);
+    for (auto& t : T) t.x_init();
+    for (auto& t : T) t.f_init();
+    for (auto& t : T) t.x_step(ops[0], 0);
+    for (int s = 0; s < S; s++) {
+      if (s + 1 < S)
+        for (auto& t : T) t.x_step(ops[s + 1], (s + 1) & 1);
+      for (auto& t : T) t.f_step(ops[s], s & 1, s == 0);
+    }
+    for (auto& t : T) t.f_finish();
+  }
+}
 }  // namespace
 
 #define FOR_L(L, ...)                          \
@@ -190,6 +213,7 @@ int hs_miller_fixed_pair(int L, const MillerFixedArgs* a) {
     lp.run([&](int s, auto xchg) { MillerFixedPair<LL>::run(*a, (size_t)e, s, true, xchg); });
   })
 }
+int hs_pair_duo(int L, const PairDuoArgs* a, int np) { FOR_L(L, sim_pair_duo<LL>(*a, np)) }
 int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* lines) {
   FOR_L(L, MillerFixed<LL>::record(px, py, lines))
 }

@@ -44,6 +44,11 @@ class MillerFixedArgs(C.Structure):
                 ("count", C.c_int)]
 
 
+class PairDuoArgs(C.Structure):
+    _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
+                ("out_re", u32p), ("out_im", u32p), ("count", C.c_int)]
+
+
 class EncArgs(C.Structure):
     _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p), ("wbitsQ", C.c_int),
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t),
@@ -290,6 +295,17 @@ class Sim:
         oim = np.zeros_like(ore)
         a = MillerFixedArgs(P32(lines), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), count)
         assert lib().hs_miller_fixed_pair(self.L, C.byref(a)) == 0
+        return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
+
+    def pair_duo(self, A, Bp, np_=3):
+        """k_pair_duo: e(A[i], B[i]) on two warps per group of pairings (pairwarp.cuh)"""
+        count = len(A)
+        Mx, My, Mi = self.g1_arrays(A)
+        Ex, Ey, Ei = self.g1_arrays(Bp)
+        ore = np.zeros((count, self.L), dtype=np.uint32)
+        oim = np.zeros_like(ore)
+        a = PairDuoArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), P32(ore), P32(oim), count)
+        assert lib().hs_pair_duo(self.L, C.byref(a), np_) == 0
         return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
     def multpoly(self, c1, d1, c2, d2, count):

@@ -222,6 +222,42 @@ def test_fixed_pairing_lane_pair_equals_one_thread(kb):
     e.close()
 
 
+@pytest.mark.parametrize("kb", [128, 512, 1024])
+def test_general_pairing_two_warps_equals_one_thread(kb):
+    """e(a, b) with a pairing split over two warps (k_pair_duo, pairwarp.cuh) gives the bytes of the
+    one-thread kernel and of the oracle: counts that leave a warp pair partly empty and span several
+    blocks, O on either side, a point paired with itself and with its negative."""
+    from bgn_b200 import Engine
+    from oracle import bgn_oracle as O
+    g = load_golden(kb)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    rng = random.Random(kb + 1)
+    count = 75 if kb < 1024 else 37
+    eb = e.elem_bytes
+    xs = np.array([rng.randrange(-40, 40) for _ in range(count)], dtype=np.int64)
+    a = e.encrypt_batch(xs, e.scalars_be([rng.randrange(par.n) for _ in range(count)]))
+    b = e.encrypt_batch(xs[::-1].copy(), e.scalars_be([rng.randrange(par.n) for _ in range(count)]))
+    a[2 * eb: 3 * eb] = 0                      # O on the Miller side
+    b[4 * eb: 5 * eb] = 0                      # O on the evaluation side
+    b[6 * eb: 7 * eb] = a[6 * eb: 7 * eb]      # e(A, A)
+    b[8 * eb: 9 * eb] = e.g1_neg_batch(a[8 * eb: 9 * eb])  # e(A, -A)
+    outs = {}
+    for mode in (1, 0):
+        e.set_option("pair_duo", mode)
+        outs[mode] = e.pair_batch(a, b).tobytes()
+    assert outs[1] == outs[0]
+    for i in (0, 2, 4, 6, 8, 33, count - 1):
+        pa = O.g1_from_bytes(a[i * eb:(i + 1) * eb].tobytes(), par)
+        pb = O.g1_from_bytes(b[i * eb:(i + 1) * eb].tobytes(), par)
+        assert outs[1][i * eb:(i + 1) * eb] == O.gt_to_bytes(O.pairing(pa, pb, par), par)
+    e.set_option("pair_duo", 1)
+    v = g["pair"]
+    assert e.pair_batch(buf(v["a"]), buf(v["b"])).tobytes() == unhex(v["out"])
+    assert e.pair_batch(buf(v["b"]), buf(v["a"])).tobytes() == unhex(v["out"])
+    e.close()
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)

@@ -98,6 +98,43 @@ def test_sim_pairing(kb):
 
 
 @pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_pair_duo(kb):
+    """k_pair_duo (pairwarp.cuh: point arithmetic on one warp, line evaluation + accumulator on another,
+    double-buffered hand-over) against the golden Mult vectors (incl. O operands) and the one-thread
+    kernel; the X warp is run one step ahead, so a clobbered buffer would show.  Also the range proof
+    of its routines, its variant with the plain (non-lazy) F_p^2 product the 1024-bit field uses, and
+    its work model: 9 / 11 products per doubling / addition on the X side, 4 + 2 / 3 products plus the
+    lazily reduced F_p^2 product on the F side."""
+    import ctypes as C
+    g, par, S, _ = setup(kb)
+    v = g["pair"]
+    A, Bp = g1s(par, v["a"]), g1s(par, v["b"])
+    wide = (C.c_uint64 * 4)()
+    sim.lib().hs_wide_count(wide, 1)
+    sim.lib().hs_mul_count(1)
+    S.range_report()
+    assert S.pair_duo(A, Bp) == gts(par, v["out"])
+    hi, headroom, unknown, viol = S.range_report()
+    assert viol == 0 and unknown == 0 and hi <= 40.0, (hi, unknown, viol)
+    sim.lib().hs_wide_count(wide, 1)
+    nmul = sim.lib().hs_mul_count(1)
+    from bgn_b200 import workmodel
+    live = sum(1 for x, y in zip(A, Bp) if x is not None and y is not None)
+    mm, mw, rd = workmodel.pair_duo_counts(par.p, par.n, par.l)
+    assert (nmul, wide[0], wide[1]) == (live * mm, live * mw, live * rd), (nmul, list(wide), live, mm, mw, rd)
+    if kb < 512:
+        assert S.pair_duo(Bp, A, np_=5) == S.pair(Bp, A)
+        try:
+            sim.use_variant(None, ("-DBGN_LINE_LAZY=0",), "_nolazy")
+            S.activate()
+            assert S.pair_duo(A, Bp) == gts(par, v["out"])
+            _, _, unknown, viol = S.range_report()
+            assert unknown == 0 and viol == 0
+        finally:
+            sim.use_variant(None)
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
 def test_sim_multpoly(kb):
     g, par, S, _ = setup(kb)
     v = g["multpoly"]

@@ -18,8 +18,9 @@ from bgn_b200.engine import bench_issue_mix  # noqa: E402
 SM = 148
 NAMES = {0: "IMAD.WIDE", 1: "IMAD.LO+IMAD.HI", 2: "IMAD.WIDE + (LO,HI) 1:1", 3: "FFMA", 4: "IMAD.WIDE + FFMA 1:1",
          5: "DFMA", 6: "IMAD.WIDE + DFMA 1:1", 7: "IMAD.WIDE + (LO,HI) 2:1", 8: "IMAD.WIDE + DFMA 2:1",
-         9: "IMAD.WIDE + DFMA 1:2"}
-PARTS = {2: (0, 1), 4: (0, 3), 6: (0, 5)}
+         9: "IMAD.WIDE + DFMA 1:2", 10: "IMAD.LO", 11: "IMAD.HI", 12: "IMAD.WIDE + IMAD.LO 1:1",
+         13: "IMAD.WIDE + IMAD.HI 1:1"}
+PARTS = {1: (10, 11), 2: (0, 1), 4: (0, 3), 6: (0, 5), 12: (0, 10), 13: (0, 11)}
 
 
 def sm_clock_mhz():
@@ -34,7 +35,7 @@ def main():
     blocks, threads, iters = SM * 8, 256, 2048
     res = {"config": {"blocks": blocks, "threads": threads, "iters": iters}, "mixes": {}}
     times = {}
-    for mix in range(10):
+    for mix in range(14):
         bench_issue_mix(0, mix, 64, blocks, threads)
         best = None
         for _ in range(3):
@@ -47,10 +48,10 @@ def main():
         clk = ms * 1e-3 * mhz * 1e6
         nthr = blocks * threads
         entry = {"name": NAMES[mix], "ms": ms, "sm_mhz_after": mhz}
-        for cls, cnt in zip(("imad_wide", "imad_lo_hi_pairs", "ffma", "dfma"), per):
+        for cls, cnt in zip(("imad_wide", "imad_lo", "imad_hi", "ffma", "dfma"), per):
             if cnt:
                 entry[cls + "_per_clk_per_sm"] = cnt * nthr / clk / SM
-        prods = per[0] + per[1]
+        prods = per[0] + min(per[1], per[2])  # a (LO, HI) pair is one 32x32->64 product
         if prods:
             entry["products_32x32_per_clk_per_sm"] = prods * nthr / clk / SM
         res["mixes"][str(mix)] = entry
