@@ -10,6 +10,13 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
 
+Beside the headline (config 3, weak scaling) the same line carries, nested where the driver keeps them
+(`config`, `roofline`): config 3 as worded (2^14 pairs in TOTAL split over the ranks: `strong`), configs 2
+and 4 at their stated sizes with a roofline object per dominant kernel (`roofline.ops`), and config 5
+(keyBits=1024 inner product of length 2^16 with the NCCL all-gather + fold inside the timed region:
+`config.inner_product_config5`).  `verified_units` EMults of the TIMED output are recomputed by the CPU
+oracle in the same run.
+
 `value` is measured with inputs resident in HBM (CUDA events on the library's stream around each
 call); `e2e` goes through the same C-ABI call with pinned HOST buffers, so the host<->device copies
 are inside the timed region.  `roofline` is against the integer-multiply (IMAD.WIDE) pipe, which is
@@ -160,12 +167,54 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def load_measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def dram_bytes_per_miller_unit():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_miller<17> launch divided by its units, from
+    the newest `ncu --set full` capture summarised under profiles/ (tools/ncu_summary.py writes the json)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)):
+        if name.endswith("_miller_dram.json"):
+            best = os.path.join(pdir, name)
+    if best:
+        try:
+            with open(best) as f:
+                d = json.load(f)
+            return d["dram_bytes"] / d["units"], os.path.basename(best)
+        except Exception:
+            pass
+    return NCU_DRAM_BYTES_PER_UNIT, "r01_miller_v24_ncu.txt"
+
+
+def verify_emults(g, c1, c2, out, pairs, EB, sample=8, seed=11):
+    """Bit-exact check of `sample` EMults taken from the TIMED batch against the CPU port of the oracle
+    (oracle/cpu_ref.c) run here, on this box, on the very inputs the GPU multiplied: -> (checked, ok)."""
+    import numpy as np
+    from oracle.cpu_ref import CpuRef
+    ref = CpuRef(int(g["p"], 16), int(g["n"], 16), g["l"], threads=min(sample, host_cores()))
+    rng = np.random.default_rng(seed)
+    idx = sorted(set([0, pairs - 1] + [int(x) for x in rng.integers(0, pairs, max(0, sample - 2))]))
+    a = np.concatenate([c1[i * D1 * EB:(i + 1) * D1 * EB].cpu().numpy() for i in idx])
+    b = np.concatenate([c2[i * D2 * EB:(i + 1) * D2 * EB].cpu().numpy() for i in idx])
+    exp = np.asarray(ref.multpoly_batch(a, D1, b, D2, len(idx))).reshape(-1)
+    got = np.concatenate([out[i * (D1 + D2) * EB:(i + 1) * (D1 + D2) * EB].cpu().numpy() for i in idx])
+    return len(idx), bool(exp.tobytes() == got.tobytes())
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from bgn_b200 import Engine, bench_imad_peak, workmodel
+    from bgn_b200.multi import inner_product, shard_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +256,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def all_true(x: bool) -> bool:
+        return sum_over_ranks(0.0 if x else 1.0) == 0.0
+
     g = load_key()
     p, n, l = int(g["p"], 16), int(g["n"], 16), g["l"]
     eng = Engine(p, n, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=local)
@@ -218,11 +270,14 @@ def run_ours(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
 
+    def rand_scalars(count, nbytes=SB):
+        r = torch.randint(0, 256, (count, nbytes), generator=gen, device=dev, dtype=torch.uint8)
+        r[:, 0] &= 0x3F
+        return r.reshape(-1)
+
     def make_batch(d):
         digits = torch.randint(-1, 2, (pairs * d,), generator=gen, device=dev, dtype=torch.int64)
-        r = torch.randint(0, 256, (pairs * d, SB), generator=gen, device=dev, dtype=torch.uint8)
-        r[:, 0] &= 0x3F
-        return eng.encrypt_batch(digits, r.reshape(-1))
+        return eng.encrypt_batch(digits, rand_scalars(pairs * d))
 
     c1, c2 = make_batch(D1), make_batch(D2)
     out = torch.empty(pairs * (D1 + D2) * EB, dtype=torch.uint8, device=dev)
@@ -231,6 +286,7 @@ def run_ours(args):
     # ---- integer-pipe peak, measured live (IMAD.WIDE.U32 microkernel, 8 independent chains/thread)
     ms_peak, ipt = bench_imad_peak(local, 4096, 148 * 8, 256)
     imad_peak = 148 * 8 * 256 * ipt / (ms_peak * 1e-3)  # IMAD.WIDE instructions / s
+    ppm = workmodel.products_per_modmul(L)
 
     eng.timing_enable(True)
 
@@ -259,39 +315,42 @@ def run_ours(args):
     total_pairs = sum_over_ranks(float(pairs)) * args.steps
     value = total_pairs * D1 * D2 / (dev_ms * 1e-3)
 
+    # ---- the timed output is checked HERE, on this box, against the CPU port of the oracle
+    verified_units, verified_ok = 0, True
+    if rank == 0 and not args.no_verify:
+        verified_units, verified_ok = verify_emults(g, c1, c2, out, pairs, EB, sample=args.verify)
+
     # ---- roofline of the dominant kernel (k_miller): executed 32x32->64 products / s vs the pipe
     modmuls_unit = workmodel.miller_unit_modmuls(p, n, l, D1, D2)  # F_p products incl. the lazily reduced ones
-    prod_launch = pairs * workmodel.miller_unit_products(p, n, l, D1, D2)
+    prod_unit = workmodel.miller_unit_products(p, n, l, D1, D2)
     k_avg_s = (k_ms / max(1, k_launches)) * 1e-3
-    achieved = prod_launch / k_avg_s
+    achieved = pairs * prod_unit / k_avg_s
     algo_bytes = pairs * ((D1 + D2) * 2 * L * 4 + (D1 + D2 - 1) * 2 * L * 4)  # SoA in + out of k_miller
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
+    peaks = load_measured_peaks()
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    dram_per_unit, dram_src = dram_bytes_per_miller_unit()
     roofline = {
         "bound": "imad",
         "bound_note": "neither hbm nor tensor: north_star names the 32-bit integer multiply pipe (IMAD) as this path's "
                       "roofline; 50 000 products per byte moved -- the hbm object below shows memory at 0.002 % of its peak",
         "kernel": "k_miller<17>", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
         "unit": "T(32x32->64 products)/s", "frac": achieved / imad_peak,
-        "traffic": NCU_DRAM_BYTES_PER_UNIT * pairs,
-        "traffic_note": "DRAM bytes per launch scaled from the ncu capture of one full wave (profiles/); algorithmic "
-                        "bytes per launch = %d" % algo_bytes,
-        "peak_source": "IMAD.WIDE.U32 microkernel measured in this run (nominal 148 SM x 64/clk x %.3f GHz = %.2f)" % (
-            (clocks.get("sm_max_mhz") or 1965.0) / 1e3, 148 * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12),
-        "fp_products_per_emult": modmuls_unit, "products_per_emult": workmodel.miller_unit_products(p, n, l, D1, D2),
-        "products_per_fused_modmul": workmodel.products_per_modmul(L),
+        "traffic": dram_per_unit * pairs,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per unit from the ncu --set full capture summarised in "
+                        "profiles/%s, times the units of one launch; algorithmic bytes per launch = %d" % (dram_src, algo_bytes),
+        "peak_source": "IMAD.WIDE.U32 microkernel measured in this run (nominal 148 SM x 32/clk x %.3f GHz = %.2f); the "
+                       "issue-mix microbenchmark (profiles/r02_issuemix.json) shows no instruction mix that multiplies "
+                       "faster on this pipe" % ((clocks.get("sm_max_mhz") or 1965.0) / 1e3,
+                                                148 * 32 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12),
+        "fp_products_per_emult": modmuls_unit, "products_per_emult": prod_unit,
+        "products_per_fused_modmul": ppm,
         "kernel_ms": k_ms / max(1, k_launches), "kernel_share_of_step": k_ms / (dev_ms if world == 1 else max(dev_ms, 1e-9)),
         "hbm": {"algorithmic_GBs": algo_bytes / k_avg_s / 1e9, "peak_GBs": hbm_peak,
                 "frac": algo_bytes / k_avg_s / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
 
-    # ---- end to end: pinned host buffers through the same C-ABI call
+    # ---- end to end: pinned host buffers through the same C-ABI call, every step
     h1 = torch.empty_like(c1, device="cpu").pin_memory()
     h2 = torch.empty_like(c2, device="cpu").pin_memory()
     ho = torch.empty_like(out, device="cpu").pin_memory()
@@ -308,7 +367,7 @@ def run_ours(args):
     step_e2e()
     barrier()
     e2e_ms = 0.0
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps
     for _ in range(e2e_steps):
         e2e_ms += step_e2e()
     barrier()
@@ -316,60 +375,125 @@ def run_ours(args):
     e2e_value = sum_over_ranks(float(pairs)) * e2e_steps * D1 * D2 / (e2e_ms * 1e-3)
     same = bool((ho.to(dev) == out).all().item())  # host path and device path give identical bytes
 
-    # ---- the other operations north_star names, measured briefly on the same key (device-resident
-    # inputs, best of 2 calls after one warm-up; tools/opsbench.py has the per-kernel breakdown)
-    def best_ms(fn, reps=2):
+    def best_ms(fn, prefix=None, reps=2):
+        """best device ms of `reps` calls after one warm-up -> (call ms, ms of the kernels named `prefix`)"""
         fn()
         best = None
         for _ in range(reps):
+            eng.timing_reset()
             fn()
             t = eng.timing_last_call()
-            best = t if best is None else min(best, t)
+            k = eng.timing_get(prefix)[0] if prefix else 0.0
+            if best is None or t < best[0]:
+                best = (t, k)
         return best
 
-    n_enc = 1 << 18
-    digits = torch.randint(-1, 2, (n_enc,), generator=gen, device=dev, dtype=torch.int64)
-    rr = torch.randint(0, 256, (n_enc, SB), generator=gen, device=dev, dtype=torch.uint8)
-    rr[:, 0] &= 0x3F
-    rr = rr.reshape(-1)
-    enc_out = torch.empty(n_enc * EB, dtype=torch.uint8, device=dev)
-    enc_ms = best_ms(lambda: eng.encrypt_batch(digits, rr, out=enc_out))
-    add_out = torch.empty((n_enc // 2) * EB, dtype=torch.uint8, device=dev)
-    add_ms = best_ms(lambda: eng.g1_add_batch(enc_out[: (n_enc // 2) * EB], enc_out[(n_enc // 2) * EB:], out=add_out))
+    def op_roofline(kernel, kernel_ms, units, products_per_unit):
+        ach = units * products_per_unit / (kernel_ms * 1e-3)
+        return {"bound": "imad", "kernel": kernel, "kernel_ms": kernel_ms, "units": units,
+                "products_per_unit": products_per_unit, "achieved": ach / 1e12, "peak": imad_peak / 1e12,
+                "unit": "T(32x32->64 products)/s", "frac": ach / imad_peak}
+
+    # ---- config 3 AS WORDED: 2^14 pairs in total, sharded over the ranks (strong scaling)
+    total_strong = 1 << 14
+    lo, hi = shard_range(total_strong, rank, world)
+    mine = min(hi - lo, pairs)
+    o_s = out[: mine * (D1 + D2) * EB]
+    barrier()
+    t_s, k_s = best_ms(lambda: eng.multpoly_batch(c1[: mine * D1 * EB], D1, c2[: mine * D2 * EB], D2, mine, out=o_s),
+                       "k_miller", reps=3)
+    t_s_max = max_over_ranks(t_s)
+    strong = {"pairs_total": int(sum_over_ranks(float(mine))), "pairs_per_gpu": mine, "ms": t_s_max,
+              "pairings_per_s": sum_over_ranks(float(mine)) * D1 * D2 / (t_s_max * 1e-3),
+              "emult_per_s": sum_over_ranks(float(mine)) / (t_s_max * 1e-3),
+              "roofline": op_roofline("k_miller<17>", max_over_ranks(k_s), mine, prod_unit),
+              "note": "BASELINE config 3 as worded: 2^14 pairs in TOTAL split by pair index over the ranks "
+                      "(bgn_b200.multi.shard_range), no collective; best of 3 calls, max over ranks. Below one wave "
+                      "(3404 units per GPU) a rank's k_miller has fewer than two warps per scheduler"}
+
+    # ---- BASELINE configs 2 and 4 at their stated sizes, each with its dominant kernel's roofline
     eng.set_secret(int(g["q1"], 16), 1 << 20)
-    n_dec = 1 << 14
-    l2 = out[: n_dec * EB]  # level-2 coefficient ciphertexts produced by the timed EMult batch
+    q1 = int(g["q1"], 16)
+    n_pt = 1 << 16                      # config 2: 2^16 plaintexts x 11 balanced base-3 digits
+    n_enc = n_pt * D1
+    digits = torch.randint(-1, 2, (n_enc,), generator=gen, device=dev, dtype=torch.int64)
+    rr = rand_scalars(n_enc)
+    enc_out = torch.empty(n_enc * EB, dtype=torch.uint8, device=dev)
+    enc_ms, enc_k = best_ms(lambda: eng.encrypt_batch(digits, rr, out=enc_out), "k_encrypt")
+    half = n_enc // 2                   # config 2: 2^15 pairwise AddPoly = 360 448 coefficient additions
+    add_out = torch.empty(half * EB, dtype=torch.uint8, device=dev)
+    add_ms, add_k = best_ms(lambda: eng.g1_add_batch(enc_out[: half * EB], enc_out[half * EB:], out=add_out), "k_g1_affadd")
+    n_dec = 1 << 14                     # config 4: 2^14 level-2 ciphertexts, T = 2^20, half negative, 1 % zeros
+    av = torch.randint(1, 1 << 10, (n_dec,), generator=gen, device=dev, dtype=torch.int64)
+    bv = torch.randint(-(1 << 10) + 1, 1 << 10, (n_dec,), generator=gen, device=dev, dtype=torch.int64)
+    bv[::100] = 0
+    ca = eng.encrypt_batch(av, rand_scalars(n_dec))
+    cb = eng.encrypt_batch(bv, rand_scalars(n_dec))
+    l2 = torch.empty(n_dec * EB, dtype=torch.uint8, device=dev)
+    pair_ms, pair_k = best_ms(lambda: eng.pair_batch(ca, cb, out=l2), "k_pair_duo")
+    pair_kernel, pair_prod = "k_pair_duo<17>", workmodel.pair_duo_products(p, n, l)
+    if pair_k == 0.0:
+        pair_ms, pair_k = best_ms(lambda: eng.pair_batch(ca, cb, out=l2), "k_miller")
+        pair_kernel, pair_prod = "k_miller<17> (team of 1)", workmodel.miller_unit_products(p, n, l, 1, 1)
     dec = {}
 
     def do_dec():
         dec["v"], dec["s"] = eng.decrypt_batch(l2, True)
 
-    dec_ms = best_ms(do_dec)
+    dec_ms, dec_k = best_ms(do_dec, "k_dec_lucas")
+    dec_ok = bool((dec["v"] == av * bv).all().item()) and not bool(dec["s"].any().item())
     dec1 = {}
 
     def do_dec1():
         dec1["v"], dec1["s"] = eng.decrypt_batch(enc_out[: n_dec * EB], False)
 
-    dec1_ms = best_ms(do_dec1)
+    dec1_ms, dec1_k = best_ms(do_dec1, "k_miller_fixed")
+    dec1_ok = bool((dec1["v"] == digits[:n_dec]).all().item()) and not bool(dec1["s"].any().item())
+    n_bl = 1 << 18
+    bl1_ms, _ = best_ms(lambda: eng.g1_blind_batch(enc_out[: n_bl * EB], rr[: n_bl * SB], out=enc_out.new_empty(n_bl * EB)))
     bl_out = torch.empty(n_dec * EB, dtype=torch.uint8, device=dev)
-    bl1_ms = best_ms(lambda: eng.g1_blind_batch(enc_out, rr, out=enc_out.new_empty(n_enc * EB)))
-    bl2_ms = best_ms(lambda: eng.gt_blind_batch(l2, rr[: n_dec * SB], out=bl_out))
+    bl2_ms, _ = best_ms(lambda: eng.gt_blind_batch(l2, rr[: n_dec * SB], out=bl_out))
     # the HBM-scale variant: 24-bit windows of Q (50 GB table per GPU, ~2 s to build, untimed)
     eng.set_option("enc_window", 24)
-    enc24_ms = best_ms(lambda: eng.encrypt_batch(digits, rr, out=enc_out))
+    enc24_ms, enc24_k = best_ms(lambda: eng.encrypt_batch(digits, rr, out=enc_out), "k_encrypt")
     eng.set_option("enc_window", 16)
-    ops = {"encrypt_coeff_per_s": sum_over_ranks(n_enc / (enc_ms * 1e-3)),
-           "encrypt_coeff_per_s_window24": sum_over_ranks(n_enc / (enc24_ms * 1e-3)),
-           "eadd_coeff_per_s": sum_over_ranks((n_enc // 2) / (add_ms * 1e-3)),
-           "decrypt_l2_per_s": sum_over_ranks(n_dec / (dec_ms * 1e-3)),
-           "decrypt_l1_per_s": sum_over_ranks(n_dec / (dec1_ms * 1e-3)),
-           "decrypt_l1_matches_plaintext": bool((dec1["v"] == digits[:n_dec]).all().item())
-           and not bool(dec1["s"].any().item()),
-           "rerandomize_l1_per_s": sum_over_ranks(n_enc / (bl1_ms * 1e-3)),
-           "rerandomize_l2_per_s": sum_over_ranks(n_dec / (bl2_ms * 1e-3)),
-           "decrypt_all_found": not bool(dec["s"].any().item()),
-           "note": "keyBits=512, per-call device time incl. (de)serialisation kernels; Encrypt: x in {-1,0,1}, "
-                   "512-bit r (16-bit windows of Q unless stated); Decrypt: trace of C^q1 by a Lucas ladder + one table probe over T=2^20 (level 1: pairing with P first); summed over ranks"}
+    fixed_pair_prod = workmodel.miller_fixed_pair_products(p, n, l)
+    ops = {
+        "encrypt": {"config": "BASELINE config 2: 2^16 plaintexts x 11 digits = 720 896 coefficient encryptions, 16-bit windows of Q",
+                    "per_s": sum_over_ranks(n_enc / (enc_ms * 1e-3)), "plaintexts_per_s": sum_over_ranks(n_pt / (enc_ms * 1e-3)),
+                    "ms": max_over_ranks(enc_ms),
+                    "roofline": op_roofline("k_encrypt<17>", enc_k, n_enc, workmodel.encrypt_modmuls(n, SB, 16) * ppm)},
+        "encrypt_window24": {"config": "the same with 24-bit windows (50 GB table)", "per_s": sum_over_ranks(n_enc / (enc24_ms * 1e-3)),
+                             "ms": max_over_ranks(enc24_ms),
+                             "roofline": op_roofline("k_encrypt<17>", enc24_k, n_enc, workmodel.encrypt_modmuls(n, SB, 24) * ppm)},
+        "eadd": {"config": "BASELINE config 2: 2^15 pairwise AddPoly = 360 448 level-1 coefficient additions",
+                 "per_s": sum_over_ranks(half / (add_ms * 1e-3)), "ms": max_over_ranks(add_ms),
+                 "roofline": op_roofline("k_g1_affadd<17>", add_k, half, 6 * ppm),
+                 "roofline_note": "6 products per addition; the shared inversion runs on the ALU pipe (division-step "
+                                  "GCD) and the (de)serialisation kernels around it are HBM-side: this op is not "
+                                  "multiply-bound, the fraction says how far"},
+        "mult_pairs": {"config": "2^14 plain Mult (one pairing each, bgn.go:294-314)", "per_s": sum_over_ranks(n_dec / (pair_ms * 1e-3)),
+                       "ms": max_over_ranks(pair_ms), "roofline": op_roofline(pair_kernel, pair_k, n_dec, pair_prod)},
+        "decrypt_l2": {"config": "BASELINE config 4: 2^14 level-2 ciphertexts, T = 2^20, half negative, 1 % zeros",
+                       "per_s": sum_over_ranks(n_dec / (dec_ms * 1e-3)), "ms": max_over_ranks(dec_ms),
+                       "plaintexts_match": all_true(dec_ok),
+                       "roofline": op_roofline("k_dec_lucas<17>", dec_k, n_dec, workmodel.dec_lucas_modmuls(q1) * ppm)},
+        "decrypt_l1": {"config": "2^14 level-1 ciphertexts (pairing with P on a lane pair, then the ladder)",
+                       "per_s": sum_over_ranks(n_dec / (dec1_ms * 1e-3)), "ms": max_over_ranks(dec1_ms),
+                       "plaintexts_match": all_true(dec1_ok),
+                       "roofline": op_roofline("k_miller_fixed_pair<17>", dec1_k, n_dec, fixed_pair_prod)},
+        "rerandomize_l1_per_s": sum_over_ranks(n_bl / (bl1_ms * 1e-3)),
+        "rerandomize_l2_per_s": sum_over_ranks(n_dec / (bl2_ms * 1e-3)),
+        "note": "keyBits=512; per-call device time incl. (de)serialisation kernels, best of 2 after a warm-up, inputs "
+                "resident in HBM; rates summed over ranks (every rank runs the stated size)"}
+    del enc_out, add_out, digits, rr, flush
+
+    # ---- BASELINE config 5: keyBits=1024 encrypted inner product, length 2^16, d = 8, sharded by index;
+    # per-GPU GT product tree -> NCCL all-gather of the serialised partials -> fold kernel, all inside
+    # the timed region; rank 0 decrypts the 16 result slots and compares with the plaintext result
+    ip = None
+    if not args.no_inner:
+        ip = run_inner_product(args, rank, world, local, dev, barrier, max_over_ranks, sum_over_ranks)
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
@@ -379,12 +503,21 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "key_bits": KEY_BITS, "pairs_per_gpu": pairs, "d1": D1, "d2": D2,
                    "parallelism": "independent pairs per GPU, no collective" if world > 1 else "1 GPU",
                    "l2": "256 MB flush between steps; step working set ~%d MB" % (
-                       (pairs * (2 * (D1 + D2) * (EB + 2 * L * 4))) >> 20)},
+                       (pairs * (2 * (D1 + D2) * (EB + 2 * L * 4))) >> 20),
+                   "strong_scaling_config3": strong, "inner_product_config5": ip},
         "emult_per_s": value / (D1 * D2),
         "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": int(h1.numel() + h2.numel()),
                 "d2h_bytes_per_step": int(ho.numel()), "steps": e2e_steps, "bytes_match_device_path": same},
-        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "wall_s": t_wall, "ops": ops,
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "wall_s": t_wall,
+        "verified_units": verified_units, "verified_ok": verified_ok,
+        "verified_note": "EMults sampled from the timed batch, recomputed on this box by the CPU port of the oracle "
+                         "(121 full pairings each) and compared byte for byte",
     }
+    roofline["ops"] = ops
+    roofline["strong_scaling_config3"] = strong["roofline"]
+    line["strong"] = strong
+    line["inner_product"] = ip
+    line["ops"] = ops
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = host_cores()
         cnt = 48 * cores  # ~12 s on every core (~0.25 core-seconds per EMult at 512 bit)
@@ -394,10 +527,97 @@ def run_ours(args):
             "sample": "%d EMults (121 full pairings each) of the same workload in %.1f s, C port of the oracle "
                       "(oracle/cpu_ref.c), %d threads" % (cnt, el, cores)}
     if rank == 0:
+        if not verified_ok:
+            line["error"] = "timed output differs from the CPU oracle"
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and not verified_ok:
+        sys.exit(3)
+
+
+def run_inner_product(args, rank, world, local, dev, barrier, max_over_ranks, sum_over_ranks):
+    import torch
+    import torch.distributed as dist
+
+    from bgn_b200 import Engine, workmodel
+    from bgn_b200.multi import inner_product, shard_range
+    kb, length, d = 1024, args.inner_length, 8
+    with open(os.path.join(ROOT, "tests", "golden", "kb%d.json" % kb)) as f:
+        g = json.load(f)
+    p, n, l, q1 = int(g["p"], 16), int(g["n"], 16), g["l"], int(g["q1"], 16)
+    eng = Engine(p, n, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=local)
+    SB = eng.scalar_bytes
+    lo, hi = shard_range(length, rank, world)
+    cnt = hi - lo
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5000 + rank)
+    u = torch.randint(-1, 2, (cnt, d), generator=gen, device=dev, dtype=torch.int64)
+    v = torch.randint(-1, 2, (cnt, d), generator=gen, device=dev, dtype=torch.int64)
+
+    def rnd():
+        r = torch.randint(0, 256, (cnt * d, SB), generator=gen, device=dev, dtype=torch.uint8)
+        r[:, 0] &= 0x3F
+        return r.reshape(-1)
+
+    eng.timing_enable(True)
+    cu = eng.encrypt_batch(u.reshape(-1), rnd())
+    cv = eng.encrypt_batch(v.reshape(-1), rnd())
+    enc_ms = eng.timing_last_call()
+    EB = eng.elem_bytes
+    warm = min(cnt, 256)
+    inner_product(eng, cu[: warm * d * EB], d, cv[: warm * d * EB], d, warm)  # warm-up: module load, NCCL channel set-up
+    barrier()
+    eng.timing_reset()
+    tm = {}
+    t0 = time.perf_counter()
+    total = inner_product(eng, cu, d, cv, d, cnt, timings=tm)
+    torch.cuda.synchronize()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    k_ms = eng.timing_get("k_miller")[0]
+    dev_ms = tm["multpoly_ms"] + tm["tree_ms"] + tm["fold_ms"]
+    step_ms = max_over_ranks(dev_ms + tm["allgather_wall_ms"])
+    conv = torch.zeros(2 * d, dtype=torch.int64, device=dev)
+    for i in range(d):
+        for k in range(d):
+            conv[i + k] += (u[:, i] * v[:, k]).sum()
+    if world > 1:
+        dist.all_reduce(conv, op=dist.ReduceOp.SUM)
+    ok, slots = True, []
+    if rank == 0:
+        eng.set_secret(q1, 1 << 20)
+        vals, status = eng.decrypt_batch(total, True)
+        slots = [int(x) for x in vals.cpu()]
+        ok = (not bool(status.any().item())) and slots == [int(x) for x in conv.cpu()]
+    prod_unit = workmodel.miller_unit_products(p, n, l, d, d)
+    from bgn_b200 import bench_imad_peak
+    ms_peak, ipt = bench_imad_peak(local, 2048, 148 * 8, 256)
+    peak = 148 * 8 * 256 * ipt / (ms_peak * 1e-3)
+    miller_ms = max_over_ranks(tm["multpoly_ms"])
+    res = {
+        "config": "BASELINE config 5: keyBits=1024 fixed-point encrypted inner product, length %d, d=%d slots, "
+                  "sharded by index over %d GPU(s)" % (length, d, world),
+        "emult_per_s": length / (step_ms * 1e-3), "pairings_per_s": length * d * d / (step_ms * 1e-3),
+        "ms": step_ms, "wall_ms": max_over_ranks(wall_ms),
+        "ms_max_over_ranks": {"multpoly": miller_ms, "l2_sum_tree": max_over_ranks(tm["tree_ms"]),
+                              "allgather_wall": max_over_ranks(tm["allgather_wall_ms"]),
+                              "fold": max_over_ranks(tm["fold_ms"]), "encrypt_untimed": max_over_ranks(enc_ms)},
+        "collective": "NCCL all_gather_into_tensor of %d serialised GT elements per rank, device to device" % (2 * d)
+                      if world > 1 else "none (1 GPU)",
+        "exchange_bytes_per_rank": tm["exchange_bytes_per_rank"],
+        "exchange_bytes_total": int(sum_over_ranks(float(tm["exchange_bytes_per_rank"]))) if world > 1 else 0,
+        "decrypted_matches_plaintext": bool(ok), "slots": slots,
+        "roofline": {"bound": "imad", "kernel": "k_miller<33>", "kernel_ms": max_over_ranks(k_ms), "units_per_gpu": cnt,
+                     "products_per_unit": prod_unit, "achieved": cnt * prod_unit / (max_over_ranks(k_ms) * 1e-3) / 1e12,
+                     "peak": peak / 1e12, "unit": "T(32x32->64 products)/s",
+                     "frac": cnt * prod_unit / (max_over_ranks(k_ms) * 1e-3) / peak},
+        "limit": "the Miller kernel: tree + all-gather + fold are %.2f %% of the step" % (
+            100.0 * (step_ms - miller_ms) / step_ms),
+    }
+    eng.close()
+    return res
 
 
 def main():
@@ -408,6 +628,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 14)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-inner", action="store_true", help="skip the keyBits=1024 inner product (config 5)")
+    ap.add_argument("--inner-length", type=int, default=1 << 16)
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--verify", type=int, default=8, help="EMults of the timed batch re-computed by the CPU oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -153,6 +153,9 @@ struct bgn_ctx {
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
   size_t pair_duo_cap = (size_t)-1;  // pairings one wave of k_pair_duo holds (occupancy query, cached)
+  int pair_duo_loop = -1;      // products' row loop of k_pair_duo: -1 = the key size's default, 0 / 1 / 2 / 4 (A/B knob)
+  int pair_duo_pairs = 2;      // most warp pairs per block of k_pair_duo (measured: 2 beats 1 and 4 at 2^14 pairings)
+  bool pair_duo_blockbar = true;  // blocks of several pairs synchronise as a whole (lockstep: one instruction stream per role)
   int pair_duo = -1;           // general pairings on two warps each (pairwarp.cuh): -1 = by batch size, 0 = never, 1 = always (BGN_PAIR_DUO)
   size_t fixed_pair_cap = 0;   // pairings one wave of k_miller_fixed_pair holds (occupancy query, cached)
   int fixed_pair = -1;         // e(., P) on a lane pair per point (pairlane.cuh): -1 = by batch size, 0 = never, 1 = always (BGN_FIXED_PAIR)
@@ -544,7 +547,14 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   t.done();
 }
 
-// out[i] = e(A[i], B[i]) with two warps per 32 pairings (pairwarp.cuh); `pairs` warp pairs per block
+// out[i] = e(A[i], B[i]) with two warps per 32 pairings (pairwarp.cuh)
+int pair_duo_variant(bgn_ctx* c, int pairs_per_block) {
+  // measured (profiles/r02_duo_knobs.json): at 17 limbs the 4-rows-per-iteration loop beats the unrolled
+  // products (17.8 against 18.3 ms at 2^14 pairings, 15.0 against 17.9 at 2^12): the two roles run different
+  // code, and the smaller bodies ease the instruction cache
+  int loop = c->pair_duo_loop >= 0 ? c->pair_duo_loop : (c->L == 17 ? 2 : (c->L < 17 ? 0 : 4));
+  return loop + ((c->pair_duo_blockbar && pairs_per_block > 1) ? 8 : 0);
+}
 void run_pair_duo(bgn_ctx* c, const G1Arr& A, const G1Arr& Bv, size_t count, const GtArr& out) {
   if (!count) return;
   PairDuoArgs a;
@@ -557,11 +567,18 @@ void run_pair_duo(bgn_ctx* c, const G1Arr& A, const G1Arr& Bv, size_t count, con
   a.out_re = out.re;
   a.out_im = out.im;
   a.count = (int)count;
-  const int np = 32;  // one warp pair per block: small batches spread over the SMs pair by pair
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  // warp pairs per block: the fewest that keep the batch within one block per SM (small batches are
+  // spread pair by pair), at most pair_duo_pairs
+  int pairs = (int)std::min<size_t>((size_t)c->pair_duo_pairs, std::max<size_t>(1, (count + (size_t)sms * 32 - 1) / ((size_t)sms * 32)));
+  while (pairs > 1 && c->Do->pair_duo_smem_bytes(32 * pairs) + 16 > 227 * 1024 - 64) pairs--;
+  const int np = 32 * pairs;
+  const int variant = pair_duo_variant(c, pairs);
   size_t smem = c->Do->pair_duo_smem_bytes(np) + 16;
   Timer t(c, "k_pair_duo");
-  CK(c->Do->pair_duo_set_smem(smem));
-  c->Do->pair_duo(cfg(c, nblk(count, np), 2 * np, smem), a);
+  CK(c->Do->pair_duo_set_smem(variant, smem));
+  if (!c->Do->pair_duo(variant, cfg(c, nblk(count, np), 2 * np, smem), a)) throw ArgErr{"pair_duo variant not built for this key size"};
   t.done();
 }
 // pairings one wave of k_pair_duo holds (0: the kernel does not fit this key's shared-memory state)
@@ -569,10 +586,13 @@ size_t pair_duo_capacity(bgn_ctx* c) {
   if (c->pair_duo_cap == (size_t)-1) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    size_t smem = c->Do->pair_duo_smem_bytes(32) + 16;
+    int pairs = c->pair_duo_pairs;
+    while (pairs > 1 && c->Do->pair_duo_smem_bytes(32 * pairs) + 16 > 227 * 1024 - 64) pairs--;
+    size_t smem = c->Do->pair_duo_smem_bytes(32 * pairs) + 16;
+    const int variant = pair_duo_variant(c, pairs);
     c->pair_duo_cap = 0;
-    if (smem <= 227 * 1024 - 64 && c->Do->pair_duo_set_smem(smem) == cudaSuccess)
-      c->pair_duo_cap = (size_t)sms * std::max(0, c->Do->pair_duo_blocks_per_sm(64, smem)) * 32;
+    if (smem <= 227 * 1024 - 64 && c->Do->pair_duo_set_smem(variant, smem) == cudaSuccess)
+      c->pair_duo_cap = (size_t)sms * std::max(0, c->Do->pair_duo_blocks_per_sm(variant, 64 * pairs, smem)) * 32 * pairs;
     cudaGetLastError();
   }
   return c->pair_duo_cap;
@@ -1131,6 +1151,14 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->fixed_pair = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo") {
     c->pair_duo = value < 0 ? -1 : (value != 0);
+  } else if (k == "pair_duo_loop") {
+    c->pair_duo_loop = (int)value;
+    c->pair_duo_cap = (size_t)-1;
+  } else if (k == "pair_duo_pairs") {
+    c->pair_duo_pairs = (int)std::max<long>(1, std::min<long>(4, value));
+    c->pair_duo_cap = (size_t)-1;
+  } else if (k == "pair_duo_blockbar") {
+    c->pair_duo_blockbar = value != 0;
   } else {
     c->err = "unknown option " + k;
     return BGN_E_BADARG;

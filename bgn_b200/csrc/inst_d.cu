@@ -21,15 +21,47 @@ int miller_fixed_pair_blocks_per_sm() {
   return n;
 }
 size_t pair_duo_smem_bytes(int np) { return MillerDuo<LL>::smem_words(np) * 4; }
-cudaError_t pair_duo_set_smem(size_t smem) {
-  return cudaFuncSetAttribute(k_pair_duo<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// the variants compiled in: every limb count has its default loop shape; the 512-bit field also carries
+// the A/B candidates (tools/mapping_ab.py --which general)
+#if BGN_L == 17
+#define BGN_DUO_VARIANTS(X) X(0) X(1) X(2) X(4)
+#elif BGN_L <= 17
+#define BGN_DUO_VARIANTS(X) X(0)
+#else
+#define BGN_DUO_VARIANTS(X) X(4) X(2)
+#endif
+template <typename Fn>
+bool duo_dispatch(int variant, Fn fn) {
+  const bool blockbar = (variant & 8) != 0;
+  switch (variant & 7) {
+#define BGN_DUO_CASE(U)                            \
+  case U:                                          \
+    if (blockbar)                                  \
+      fn(k_pair_duo<LL, U, true>);                 \
+    else                                           \
+      fn(k_pair_duo<LL, U, false>);                \
+    return true;
+    BGN_DUO_VARIANTS(BGN_DUO_CASE)
+#undef BGN_DUO_CASE
+    default:
+      return false;
+  }
 }
-int pair_duo_blocks_per_sm(int threads, size_t smem) {
+cudaError_t pair_duo_set_smem(int variant, size_t smem) {
+  cudaError_t e = cudaErrorInvalidValue;
+  duo_dispatch(variant, [&](auto k) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+  return e;
+}
+int pair_duo_blocks_per_sm(int variant, int threads, size_t smem) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair_duo<LL>, threads, smem) != cudaSuccess) n = 0;
+  duo_dispatch(variant, [&](auto k) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) n = 0;
+  });
   return n;
 }
-void pair_duo(LaunchCfg cfg, const PairDuoArgs& a) { k_pair_duo<LL><<<CFG>>>(a); }
+bool pair_duo(int variant, LaunchCfg cfg, const PairDuoArgs& a) {
+  return duo_dispatch(variant, [&](auto k) { k<<<CFG>>>(a); });
+}
 const LOpsD ops = {LL, upload, miller_fixed_pair, miller_fixed_pair_blocks_per_sm, pair_duo_smem_bytes, pair_duo_set_smem,
                    pair_duo_blocks_per_sm, pair_duo};
 }  // namespace

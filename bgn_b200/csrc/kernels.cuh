@@ -983,28 +983,30 @@ __global__ void __launch_bounds__(64) k_miller_fixed_pair(const __grid_constant_
 
 // a general pairing on two warps (pairwarp.cuh): even warps advance the Miller points of 32 pairings
 // and publish the line ingredients, odd warps fold the lines into the accumulators one step behind;
-// one named barrier per step and warp pair
-template <int L>
+// one barrier per step.  BLOCKBAR: the barrier spans the block, so all its warp pairs stay in lockstep
+// and share one instruction stream per role (otherwise each pair has its own named barrier).
+template <int L, int U, bool BLOCKBAR>
 __global__ void __launch_bounds__(256) k_pair_duo(const __grid_constant__ PairDuoArgs a) {
   extern __shared__ uint32_t smem_dyn[];
+  typedef MillerDuo<L, U> T_;
   const int np = blockDim.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pt = (warp >> 1) * 32 + lane;
-  MillerDuo<L> T(a, smem_dyn, np, pt, (size_t)blockIdx.x * np + pt);
-  const int bar_id = 1 + (warp >> 1);
+  T_ T(a, smem_dyn, np, pt, (size_t)blockIdx.x * np + pt);
+  const int bar_id = BLOCKBAR ? 0 : 1 + (warp >> 1), bar_n = BLOCKBAR ? (int)blockDim.x : 64;
   auto sync = [=] {
     __syncwarp();
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
   };
   if ((warp & 1) == 0) {
     T.x_init();
-    MillerDuo<L>::for_steps([&](int s, int op) {
+    T_::for_steps([&](int s, int op) {
       T.x_step(op, s & 1);
       sync();
     });
   } else {
     T.f_init();
-    MillerDuo<L>::for_steps([&](int s, int op) {
+    T_::for_steps([&](int s, int op) {
       sync();
       T.f_step(op, s & 1, s == 0);
     });

@@ -59,10 +59,12 @@ struct LOpsD {
   void (*miller_fixed_pair)(LaunchCfg, const MillerFixedArgs&);
   int (*miller_fixed_pair_blocks_per_sm)();  // resident 64-thread blocks of k_miller_fixed_pair per SM (register-bound)
   // general pairing on two warps (pairwarp.cuh); blocks are `pairs` warp pairs = 32 * pairs pairings
+  // variant = loop shape of the products (0 unrolled, 1 / 2 / 4 = 2U rows per iteration; only the
+  // shipped one and the A/B candidates are instantiated) + 8 if the barrier spans the whole block
   size_t (*pair_duo_smem_bytes)(int pairings_per_block);
-  cudaError_t (*pair_duo_set_smem)(size_t smem);
-  int (*pair_duo_blocks_per_sm)(int threads, size_t smem);
-  void (*pair_duo)(LaunchCfg, const PairDuoArgs&);
+  cudaError_t (*pair_duo_set_smem)(int variant, size_t smem);
+  int (*pair_duo_blocks_per_sm)(int variant, int threads, size_t smem);
+  bool (*pair_duo)(int variant, LaunchCfg, const PairDuoArgs&);  // false: variant not instantiated
 };
 
 struct LOpsB {

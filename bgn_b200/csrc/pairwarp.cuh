@@ -188,10 +188,14 @@ struct MDuo : MF<L, U, 1> {
   }
 };
 
-template <int L>
+// U: the products' row loop (fused.cuh), 0 = fully unrolled.  Which one ships is measured
+// (tools/mapping_ab.py --duo-loop): the two warps of a pair run DIFFERENT straight-line code, so the
+// unrolled routines (9.5 KB per product at L = 17) put twice the pressure on the instruction cache
+// that the one-thread kernel's lockstep blocks do.
+template <int L, int U = BGN_MILLER_LOOP_A>
 struct MillerDuo {
   typedef F<L> FF;
-  typedef MDuo<L, BGN_MILLER_LOOP_A> MA;
+  typedef MDuo<L, U> MA;
   // shared-memory slots per pairing, [slot][pairing of the block][L]: the X warp's point, two buffers
   // of published values, the F warp's accumulator and evaluation point
   enum { S_X = 0, S_Y = 1, S_Z = 2, S_PUB = 3, NPUB = 5, S_FR = 13, S_FI = 14, S_EX = 15, S_EY = 16, NSLOT = 17 };

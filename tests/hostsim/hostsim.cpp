@@ -79,7 +79,7 @@ template <int L>
 void sim_pair_duo(const PairDuoArgs& a, int np) {
   std::vector<uint32_t> smem(MillerDuo<L>::smem_words(np) + 8);
   std::vector<int> ops;
-  MillerDuo<L>::for_steps([&](int, int op) { ops.push_back(op); });
+  MillerDuo<L>::for_steps([&](int, int op) { ops.push_back(op); });  // (default loop shape of this build)
   const int S = (int)ops.size();
   for (int b = 0; b * np < a.count; b++) {
     std::vector<MillerDuo<L>> T;

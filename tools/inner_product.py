@@ -66,7 +66,7 @@ def main():
     t_mult = eng.timing_last_call()
     part = eng.l2_sum_reduce(prod, cnt, 2 * d)
     t_red = eng.timing_last_call()
-    total = fold_l2_sum(part.cpu().numpy(), 2 * d, eng.l2_sum_reduce)
+    total = fold_l2_sum(part, 2 * d, eng.l2_sum_reduce)  # device to device: NCCL all-gather + fold kernel
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
 
