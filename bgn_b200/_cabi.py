@@ -52,6 +52,18 @@ SIGNATURES = {
                                            C.c_size_t, u8p]),
     "bgn_evalpoly_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_int, C.c_uint32, C.c_size_t, u8p]),
     "bgn_make_poly_l2_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, C.c_size_t, u8p]),
+    "bgn_buf_import": (C.c_int, [C.c_void_p, C.c_int, u8p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bgn_buf_export": (C.c_int, [C.c_void_p, C.c_void_p, u8p]),
+    "bgn_buf_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "bgn_buf_free": (None, [C.c_void_p]),
+    "bgn_encrypt_h": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bgn_g1_add_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "bgn_gt_mul_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "bgn_pair_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bgn_multpoly_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                 C.POINTER(C.c_void_p)]),
+    "bgn_l2_sum_reduce_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bgn_decrypt_h": (C.c_int, [C.c_void_p, C.c_void_p, u8p, u8p]),
     "bgn_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "bgn_timing_reset": (C.c_int, [C.c_void_p]),
     "bgn_timing_get": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -1213,6 +1213,57 @@ int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t 
   });
 }
 
+// R = A + B / A - B / O - B (A a single O element when bcast1) on device arrays; arena: scratch only
+static void g1_add_core(bgn_ctx* c, const G1Arr& A, const G1Arr& Bv, size_t count, int subtract, int bcast1, const G1Arr& R) {
+  if (c->affine_add) {
+    // affine + affine -> affine with one binary-GCD inversion per thread (types.h: G1AffAddArgs)
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    G1AffAddArgs aa;
+    aa.x1 = A.x;
+    aa.y1 = A.y;
+    aa.inf1 = A.inf;
+    aa.x2 = Bv.x;
+    aa.y2 = Bv.y;
+    aa.inf2 = Bv.inf;
+    aa.bcast1 = bcast1;
+    aa.subtract = subtract;
+    aa.ox = R.x;
+    aa.oy = R.y;
+    aa.oinf = R.inf;
+    aa.scratch = scratch;
+    aa.count = count;
+    aa.G = (int)shared_inversion_threads(c, count);
+    Timer t(c, "k_g1_affadd");
+    c->Bo->g1_affadd(cfg(c, nblk(aa.G, 128), 128, 0), aa);
+    t.done();
+    return;
+  }
+  JacArr j = jac_alloc(c, count);
+  uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+  G1AddArgs ga;
+  ga.x1 = A.x;
+  ga.y1 = A.y;
+  ga.inf1 = A.inf;
+  ga.N1 = A.N;
+  ga.x2 = Bv.x;
+  ga.y2 = Bv.y;
+  ga.inf2 = Bv.inf;
+  ga.N2 = Bv.N;
+  ga.bcast1 = bcast1;
+  ga.subtract = subtract;
+  ga.X = j.X;
+  ga.Y = j.Y;
+  ga.Z = j.Z;
+  ga.count = count;
+  ga.N = j.N;
+  {
+    Timer t(c, "k_g1_add");
+    c->Bo->g1_add(cfg(c, nblk(count, 128), 128, 0), ga);
+    t.done();
+  }
+  normalize_soa(c, j, count, scratch, R);
+}
+
 static int g1_binop(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, int subtract,
                     int neg_only) {
   return guarded(c, [&] {
@@ -1232,55 +1283,7 @@ static int g1_binop(bgn_ctx* c, const uint8_t* a, const uint8_t* b, size_t count
     }
     const uint8_t* db = stage_in(c, b, count * 2 * c->B);
     g1_from_bytes(c, db, count, Bv);
-    if (c->affine_add) {
-      // affine + affine -> affine with one binary-GCD inversion per thread (types.h: G1AffAddArgs)
-      uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
-      G1AffAddArgs aa;
-      aa.x1 = A.x;
-      aa.y1 = A.y;
-      aa.inf1 = A.inf;
-      aa.x2 = Bv.x;
-      aa.y2 = Bv.y;
-      aa.inf2 = Bv.inf;
-      aa.bcast1 = neg_only;
-      aa.subtract = subtract;
-      aa.ox = R.x;
-      aa.oy = R.y;
-      aa.oinf = R.inf;
-      aa.scratch = scratch;
-      aa.count = count;
-      aa.G = (int)shared_inversion_threads(c, count);
-      Timer t(c, "k_g1_affadd");
-      c->Bo->g1_affadd(cfg(c, nblk(aa.G, 128), 128, 0), aa);
-      t.done();
-      g1_to_bytes(c, R, count, ob.dev);
-      commit_out(c, ob);
-      return;
-    }
-    JacArr j = jac_alloc(c, count);
-    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
-    G1AddArgs ga;
-    ga.x1 = A.x;
-    ga.y1 = A.y;
-    ga.inf1 = A.inf;
-    ga.N1 = A.N;
-    ga.x2 = Bv.x;
-    ga.y2 = Bv.y;
-    ga.inf2 = Bv.inf;
-    ga.N2 = Bv.N;
-    ga.bcast1 = neg_only;
-    ga.subtract = subtract;
-    ga.X = j.X;
-    ga.Y = j.Y;
-    ga.Z = j.Z;
-    ga.count = count;
-    ga.N = j.N;
-    {
-      Timer t(c, "k_g1_add");
-      c->Bo->g1_add(cfg(c, nblk(count, 128), 128, 0), ga);
-      t.done();
-    }
-    normalize_soa(c, j, count, scratch, R);
+    g1_add_core(c, A, Bv, count, subtract, neg_only, R);
     g1_to_bytes(c, R, count, ob.dev);
     commit_out(c, ob);
   });
@@ -1840,6 +1843,74 @@ int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t
   });
 }
 
+// level-2 elements A (count) -> plaintexts: Lucas ladder + one table probe, or C^q1 + giant steps
+static void decrypt_core(bgn_ctx* c, const GtArr& A, size_t count, int64_t* d_out, uint8_t* d_status) {
+  if (c->bs_giant == 1 && c->dec_lucas) {
+    // the whole message space is in the baby-step table: Lucas ladder on the trace, a pair of
+    // lanes per ciphertext, search by real part (lucas.cuh)
+    DecLucasArgs da;
+    da.re = A.re;
+    da.im = A.im;
+    da.count = count;
+    da.elems = c->bs_elems;
+    da.slots = c->bs_slots;
+    da.hmask = c->bs_hmask;
+    da.S = c->bs_S;
+    da.mmax = c->bs_mmax;
+    da.out = d_out;
+    da.status = d_status;
+    Timer t(c, "k_dec_lucas");
+    c->Co->dec_lucas(cfg(c, nblk(2 * count, 64), 64, 0), da);
+    t.done();
+    return;
+  }
+  GtArr R = gt_alloc(c, count);
+  GtPowArgs pa;
+  pa.re = A.re;
+  pa.im = A.im;
+  pa.Nin = A.N;
+  pa.e_be = nullptr;
+  pa.ebytes = 0;
+  pa.mode = 1;
+  pa.ore = R.re;
+  pa.oim = R.im;
+  pa.count = count;
+  pa.N = R.N;
+  {
+    Timer t(c, "k_gt_pow");
+    c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
+    t.done();
+  }
+  BsgsLookupArgs la;
+  la.re = R.re;
+  la.im = R.im;
+  la.Nin = R.N;
+  la.count = count;
+  la.elems = c->bs_elems;
+  la.slots = c->bs_slots;
+  la.hmask = c->bs_hmask;
+  la.S = c->bs_S;
+  la.ginv = c->bs_ginv;
+  la.giant_steps = c->bs_giant;
+  la.mmax = c->bs_mmax;
+  la.out = d_out;
+  la.status = d_status;
+  {
+    Timer t(c, "k_bsgs_lookup");
+    c->A->bsgs_lookup(cfg(c, nblk(count, 128), 128, 0), la);
+    t.done();
+  }
+}
+// e(C[i], P) for level-1 elements (line table of P when enabled)
+static void make_l2_core(bgn_ctx* c, const G1Arr& C1, size_t count, const GtArr& out) {
+  if (c->linesP && c->fixed_lines) {
+    run_miller_fixed(c, C1, count, out);
+  } else {
+    G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
+    run_miller(c, C1, 1, Pv, 1, 1, count, 1, out);
+  }
+}
+
 int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status) {
   if (c && !c->has_secret) {
     c->err = "DL tables not computed!";
@@ -1855,76 +1926,277 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
     const uint8_t* di = stage_in(c, in, count * 2 * c->B);
     OutBuf oo = stage_out(c, out, count * 8);
     OutBuf os = stage_out(c, status, count);
-    GtArr A = gt_alloc(c, count), R = gt_alloc(c, count);
+    GtArr A = gt_alloc(c, count);
     if (is_l2) {
       gt_from_bytes(c, di, count, A);
     } else {
       // level 1: e(C, P)^q1 = e(P,P)^(q1 m); same m as the reference's G1 table search (bgn.go:222-223)
       G1Arr C1 = g1_alloc(c, count);
       g1_from_bytes(c, di, count, C1);
-      if (c->linesP && c->fixed_lines) {
-        run_miller_fixed(c, C1, count, A);
-      } else {
-        G1Arr Pv{c->dPx, c->dPy, c->dPinf, 1};
-        run_miller(c, C1, 1, Pv, 1, 1, count, 1, A);
-      }
+      make_l2_core(c, C1, count, A);
     }
-    if (c->bs_giant == 1 && c->dec_lucas) {
-      // the whole message space is in the baby-step table: Lucas ladder on the trace, a pair of
-      // lanes per ciphertext, search by real part (lucas.cuh)
-      DecLucasArgs da;
-      da.re = A.re;
-      da.im = A.im;
-      da.count = count;
-      da.elems = c->bs_elems;
-      da.slots = c->bs_slots;
-      da.hmask = c->bs_hmask;
-      da.S = c->bs_S;
-      da.mmax = c->bs_mmax;
-      da.out = reinterpret_cast<int64_t*>(oo.dev);
-      da.status = os.dev;
-      Timer t(c, "k_dec_lucas");
-      c->Co->dec_lucas(cfg(c, nblk(2 * count, 64), 64, 0), da);
+    decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
+    commit_out(c, oo);
+    commit_out(c, os);
+  });
+}
+
+// ---------------------------------------------------------------- device-resident batches
+// A bgn_buf is a batch of group elements kept on the device in the kernels' own form (Montgomery limbs,
+// [count][L] per coordinate, G1 with its infinity flags).  Chained operations -- Encrypt -> EAdd -> EMult
+// -> L2 sum -> Decrypt -- then run kernel to kernel: the byte format, its Montgomery conversion and the
+// on-curve check (k_g1_from_bytes alone costs as much as the addition it feeds) are paid once at the edge.
+}  // extern "C"  (the struct and helpers below are C++)
+
+struct bgn_buf {
+  bgn_ctx* owner = nullptr;
+  int kind = 0;  // BGN_KIND_G1 / BGN_KIND_GT
+  size_t count = 0, cap = 0;
+  uint32_t *a = nullptr, *b = nullptr;  // x, y  /  re, im
+  uint8_t* inf = nullptr;               // G1 only
+};
+
+namespace {
+void buf_release(bgn_buf* h) {
+  if (!h) return;
+  cudaFree(h->a);
+  cudaFree(h->inf);
+  delete h;
+}
+// *out: reused when it belongs to this context, has the kind and is large enough; else (re)allocated
+bgn_buf* buf_prepare(bgn_ctx* c, bgn_buf** out, int kind, size_t count) {
+  if (!out) throw ArgErr{"null output handle"};
+  bgn_buf* h = *out;
+  if (h && (h->owner != c || h->kind != kind || h->cap < count)) {
+    if (h->owner != c) throw ArgErr{"output handle belongs to another context"};
+    buf_release(h);
+    h = nullptr;
+    *out = nullptr;
+  }
+  if (!h) {
+    h = new bgn_buf();
+    h->owner = c;
+    h->kind = kind;
+    h->cap = std::max<size_t>(count, 1);
+    size_t words = h->cap * (size_t)c->L;
+    cudaError_t e = cudaMalloc(&h->a, 2 * words * 4);
+    if (e == cudaSuccess && kind == BGN_KIND_G1) e = cudaMalloc(&h->inf, h->cap);
+    if (e != cudaSuccess) {
+      buf_release(h);
+      cudaGetLastError();
+      throw CudaErr{std::string("cudaMalloc (handle): ") + cudaGetErrorString(e)};
+    }
+    h->b = h->a + words;
+    *out = h;
+  }
+  h->count = count;
+  return h;
+}
+const bgn_buf* buf_check(bgn_ctx* c, const bgn_buf* h, int kind, const char* what) {
+  if (!h) throw ArgErr{std::string("null handle: ") + what};
+  if (h->owner != c) throw ArgErr{std::string("handle of another context: ") + what};
+  if (h->kind != kind) throw ArgErr{std::string("handle holds the other group: ") + what};
+  return h;
+}
+G1Arr as_g1(const bgn_buf* h) { return G1Arr{h->a, h->b, h->inf, h->count}; }
+GtArr as_gt(const bgn_buf* h) { return GtArr{h->a, h->b, h->count}; }
+}  // namespace
+
+extern "C" {
+int bgn_buf_import(bgn_ctx* c, int kind, const uint8_t* bytes, size_t count, bgn_buf** out) {
+  return guarded(c, [&] {
+    if (kind != BGN_KIND_G1 && kind != BGN_KIND_GT) throw ArgErr{"kind must be BGN_KIND_G1 or BGN_KIND_GT"};
+    if (count && !bytes) throw ArgErr{"null buffer"};
+    check_count(count);
+    bgn_buf* h = buf_prepare(c, out, kind, count);
+    if (!count) return;
+    arena_reserve(c, io_bytes(c, count) + 4096);
+    const uint8_t* d = stage_in(c, bytes, count * 2 * c->B);
+    if (kind == BGN_KIND_G1)
+      g1_from_bytes(c, d, count, as_g1(h));
+    else
+      gt_from_bytes(c, d, count, as_gt(h));
+  });
+}
+int bgn_buf_export(bgn_ctx* c, const bgn_buf* h, uint8_t* bytes_out) {
+  return guarded(c, [&] {
+    if (!h || h->owner != c) throw ArgErr{"bad handle"};
+    if (!h->count) return;
+    if (!bytes_out) throw ArgErr{"null buffer"};
+    arena_reserve(c, io_bytes(c, h->count) + 4096);
+    OutBuf ob = stage_out(c, bytes_out, h->count * 2 * c->B);
+    if (h->kind == BGN_KIND_G1)
+      g1_to_bytes(c, as_g1(h), h->count, ob.dev);
+    else
+      gt_to_bytes(c, as_gt(h), h->count, ob.dev);
+    commit_out(c, ob);
+  });
+}
+int bgn_buf_info(const bgn_buf* h, int* kind, size_t* count) {
+  if (!h) return BGN_E_BADARG;
+  if (kind) *kind = h->kind;
+  if (count) *count = h->count;
+  return BGN_OK;
+}
+void bgn_buf_free(bgn_buf* h) {
+  if (!h) return;
+  bgn_ctx* c = h->owner;
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  buf_release(h);
+}
+
+int bgn_encrypt_h(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t count, bgn_buf** out) {
+  return guarded(c, [&] {
+    if (count && !x) throw ArgErr{"null buffer"};
+    check_count(count);
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_G1, count);
+    if (!count) return;
+    arena_reserve(c, pad256(count * 8) + pad256(count * c->nbytes) + jac_bytes(c, count) + pad256(count * c->L * 4) + 4096);
+    const int64_t* dx = reinterpret_cast<const int64_t*>(stage_in(c, x, count * 8));
+    const uint8_t* dr = r_be ? stage_in(c, r_be, count * c->nbytes) : nullptr;
+    JacArr j = jac_alloc(c, count);
+    uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
+    EncArgs ea;
+    ea.x = dx;
+    ea.r_be = dr;
+    ea.rbytes = c->nbytes;
+    if (dr) ensure_tabQw(c);
+    ea.tabP = c->tabP;
+    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
+    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
+    ea.X = j.X;
+    ea.Y = j.Y;
+    ea.Z = j.Z;
+    ea.count = count;
+    ea.N = count;
+    ea.bx = ea.by = nullptr;
+    ea.binf = nullptr;
+    {
+      Timer t(c, "k_encrypt");
+      c->Bo->encrypt(cfg(c, nblk(count, 128), 128, 0), ea);
       t.done();
-      commit_out(c, oo);
-      commit_out(c, os);
+    }
+    normalize_soa(c, j, count, scratch, as_g1(h));
+  });
+}
+
+int bgn_g1_add_h(bgn_ctx* c, const bgn_buf* a, const bgn_buf* b, int subtract, bgn_buf** out) {
+  return guarded(c, [&] {
+    buf_check(c, a, BGN_KIND_G1, "a");
+    buf_check(c, b, BGN_KIND_G1, "b");
+    if (a->count != b->count) throw ArgErr{"operands differ in count"};
+    if (out && (*out == a || *out == b)) throw ArgErr{"the output handle must not be an operand"};
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_G1, a->count);
+    if (!a->count) return;
+    arena_reserve(c, jac_bytes(c, a->count) + 2 * pad256(a->count * c->L * 4) + 8192);
+    g1_add_core(c, as_g1(a), as_g1(b), a->count, subtract ? 1 : 0, 0, as_g1(h));
+  });
+}
+
+int bgn_gt_mul_h(bgn_ctx* c, const bgn_buf* a, const bgn_buf* b, int divide, bgn_buf** out) {
+  return guarded(c, [&] {
+    buf_check(c, a, BGN_KIND_GT, "a");
+    buf_check(c, b, BGN_KIND_GT, "b");
+    if (a->count != b->count) throw ArgErr{"operands differ in count"};
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_GT, a->count);
+    if (!a->count) return;
+    GtBinArgs ga;
+    ga.are = a->a;
+    ga.aim = a->b;
+    ga.Na = a->count;
+    ga.bre = b->a;
+    ga.bim = b->b;
+    ga.Nb = b->count;
+    ga.conj_b = divide ? 1 : 0;
+    ga.ore = h->a;
+    ga.oim = h->b;
+    ga.count = a->count;
+    ga.N = h->count;
+    Timer t(c, "k_gt_mul");
+    c->A->gt_mul(cfg(c, nblk(a->count, 128), 128, 0), ga);
+    t.done();
+  });
+}
+
+int bgn_pair_h(bgn_ctx* c, const bgn_buf* a, const bgn_buf* b, bgn_buf** out) {
+  return guarded(c, [&] {
+    buf_check(c, a, BGN_KIND_G1, "a");
+    if (b) buf_check(c, b, BGN_KIND_G1, "b");
+    if (b && a->count != b->count) throw ArgErr{"operands differ in count"};
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_GT, a->count);
+    if (!a->count) return;
+    if (!b) ensure_linesP(c);
+    arena_reserve(c, miller_scratch(c, a->count, 1) + 8192);
+    if (!b) {
+      make_l2_core(c, as_g1(a), a->count, as_gt(h));  // makeL2: e(a, P)
       return;
     }
-    GtPowArgs pa;
-    pa.re = A.re;
-    pa.im = A.im;
-    pa.Nin = A.N;
-    pa.e_be = nullptr;
-    pa.ebytes = 0;
-    pa.mode = 1;
-    pa.ore = R.re;
-    pa.oim = R.im;
-    pa.count = count;
-    pa.N = R.N;
-    {
-      Timer t(c, "k_gt_pow");
-      c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
+    const size_t cap = pair_duo_capacity(c);
+    if (cap && (c->pair_duo > 0 || (c->pair_duo < 0 && a->count <= cap)))
+      run_pair_duo(c, as_g1(a), as_g1(b), a->count, as_gt(h));
+    else
+      run_miller(c, as_g1(a), 1, as_g1(b), 1, 0, a->count, 1, as_gt(h));
+  });
+}
+
+int bgn_multpoly_h(bgn_ctx* c, const bgn_buf* c1, size_t d1, const bgn_buf* c2, size_t d2, size_t count, bgn_buf** out) {
+  return guarded(c, [&] {
+    buf_check(c, c1, BGN_KIND_G1, "c1");
+    buf_check(c, c2, BGN_KIND_G1, "c2");
+    if (!d1 || !d2 || d1 > 128 || d2 > 128) throw ArgErr{"bad slot count"};
+    if (c1->count != count * d1 || c2->count != count * d2) throw ArgErr{"handle sizes do not match count x slots"};
+    check_count(count * (d1 + d2));
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_GT, count * (d1 + d2));
+    if (!count) return;
+    arena_reserve(c, miller_scratch(c, count, (int)std::max(d1, d2)) + 8192);
+    if (d1 <= d2)
+      run_miller(c, as_g1(c1), (int)d1, as_g1(c2), (int)d2, 0, count, (int)(d1 + d2), as_gt(h));
+    else
+      run_miller(c, as_g1(c2), (int)d2, as_g1(c1), (int)d1, 0, count, (int)(d1 + d2), as_gt(h));
+  });
+}
+
+int bgn_l2_sum_reduce_h(bgn_ctx* c, const bgn_buf* in, size_t nterms, size_t ncoeff, bgn_buf** out) {
+  return guarded(c, [&] {
+    buf_check(c, in, BGN_KIND_GT, "in");
+    if (!ncoeff || ncoeff > (1u << 20) || in->count != nterms * ncoeff) throw ArgErr{"handle size does not match nterms x ncoeff"};
+    if (out && *out == in) throw ArgErr{"the output handle must not be the operand"};
+    bgn_buf* h = buf_prepare(c, out, BGN_KIND_GT, ncoeff);
+    arena_reserve(c, 3 * gt_bytes(c, nterms * ncoeff / 8 + ncoeff + 64) + 65536);
+    GtArr R;
+    if (nterms == 0) {
+      R = gt_alloc(c, ncoeff);
+      Timer t(c, "k_gt_reduce");
+      c->A->gt_reduce(cfg(c, nblk(ncoeff, 128), 128, 0), R.re, R.im, R.N, 0, (int)ncoeff, 1, R.re, R.im, R.N);
       t.done();
+    } else {
+      R = reduce_tree(c, as_gt(in), nterms, ncoeff);
     }
-    BsgsLookupArgs la;
-    la.re = R.re;
-    la.im = R.im;
-    la.Nin = R.N;
-    la.count = count;
-    la.elems = c->bs_elems;
-    la.slots = c->bs_slots;
-    la.hmask = c->bs_hmask;
-    la.S = c->bs_S;
-    la.ginv = c->bs_ginv;
-    la.giant_steps = c->bs_giant;
-    la.mmax = c->bs_mmax;
-    la.out = reinterpret_cast<int64_t*>(oo.dev);
-    la.status = os.dev;
-    {
-      Timer t(c, "k_bsgs_lookup");
-      c->A->bsgs_lookup(cfg(c, nblk(count, 128), 128, 0), la);
-      t.done();
-    }
+    CK(cudaMemcpyAsync(h->a, R.re, ncoeff * c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(h->b, R.im, ncoeff * c->L * 4, cudaMemcpyDeviceToDevice, c->stream));
+  });
+}
+
+int bgn_decrypt_h(bgn_ctx* c, const bgn_buf* in, int64_t* out, uint8_t* status) {
+  if (c && !c->has_secret) {
+    c->err = "DL tables not computed!";
+    return BGN_E_NOTSETUP;
+  }
+  return guarded(c, [&] {
+    if (!in || in->owner != c) throw ArgErr{"bad handle"};
+    const size_t count = in->count;
+    if (!count) return;
+    if (!out || !status) throw ArgErr{"null buffer"};
+    const bool l2 = in->kind == BGN_KIND_GT;
+    if (!l2) ensure_linesP(c);
+    arena_reserve(c, 3 * gt_bytes(c, count) + pad256(count * 8) + pad256(count) + miller_scratch(c, count, 1) + 8192);
+    OutBuf oo = stage_out(c, out, count * 8);
+    OutBuf os = stage_out(c, status, count);
+    GtArr A = l2 ? as_gt(in) : gt_alloc(c, count);
+    if (!l2) make_l2_core(c, as_g1(in), count, A);
+    decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
     commit_out(c, oo);
     commit_out(c, os);
   });

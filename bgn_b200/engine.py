@@ -48,6 +48,44 @@ def _as_buf(x):
     return a.ctypes.data, a.nbytes, a, False
 
 
+class DeviceBatch:
+    """A batch of group elements resident on the engine's GPU in the kernels' own form (bgn_buf,
+    include/bgn_b200.h): what the `*_h` entry points consume and produce.  `kind`: 1 = G1 (level 1),
+    2 = GT (level 2)."""
+
+    def __init__(self, engine: "Engine", handle: C.c_void_p):
+        self.engine, self._h = engine, handle
+
+    @property
+    def kind(self) -> int:
+        k, n = C.c_int(), C.c_size_t()
+        self.engine._lib.bgn_buf_info(self._h, C.byref(k), C.byref(n))
+        return k.value
+
+    def __len__(self) -> int:
+        k, n = C.c_int(), C.c_size_t()
+        self.engine._lib.bgn_buf_info(self._h, C.byref(k), C.byref(n))
+        return n.value
+
+    def to_bytes(self, out=None):
+        """Element.Bytes() of every element (PBC format); `out` may be a CUDA tensor"""
+        o = out if out is not None else np.empty(len(self) * self.engine.elem_bytes, dtype=np.uint8)
+        self.engine._check(self.engine._lib.bgn_buf_export(self.engine._ctx, self._h, _as_buf(o)[0]))
+        return o
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            self.engine._lib.bgn_buf_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.engine._ctx.value:
+                self.free()
+        except Exception:
+            pass
+
+
 class Engine:
     """One BGN key resident on one GPU (bgn_ctx)."""
 
@@ -256,6 +294,66 @@ class Engine:
             status = np.empty(count, dtype=np.uint8)
         self._check(self._lib.bgn_decrypt_batch(self._ctx, pc, 1 if is_l2 else 0, count, _as_buf(vals)[0],
                                                 _as_buf(status)[0]))
+        return vals, status
+
+    # ------------------------------------------------------------------ device-resident batches
+    def _new_out(self, out: Optional[DeviceBatch]) -> C.c_void_p:
+        return out._h if out is not None else C.c_void_p()
+
+    def _wrap(self, h: C.c_void_p, out: Optional[DeviceBatch]) -> DeviceBatch:
+        if out is not None:
+            out._h = h
+            return out
+        return DeviceBatch(self, h)
+
+    def import_batch(self, kind: int, data, out: Optional[DeviceBatch] = None) -> DeviceBatch:
+        """bytes (PBC format, host or CUDA) -> DeviceBatch; kind 1 = G1 (curve check applies), 2 = GT"""
+        pd, nd, kd, cd = _as_buf(data)
+        h = self._new_out(out)
+        self._check(self._lib.bgn_buf_import(self._ctx, kind, pd, self._count(nd), C.byref(h)))
+        return self._wrap(h, out)
+
+    def encrypt_h(self, x, r_be=None, out: Optional[DeviceBatch] = None) -> DeviceBatch:
+        if not _is_torch(x):
+            x = np.ascontiguousarray(x, dtype=np.int64)
+        px, nx, kx, cx = _as_buf(x)
+        pr, nr, kr, cr = _as_buf(r_be)
+        h = self._new_out(out)
+        self._check(self._lib.bgn_encrypt_h(self._ctx, px, pr, nx // 8, C.byref(h)))
+        return self._wrap(h, out)
+
+    def g1_add_h(self, a: DeviceBatch, b: DeviceBatch, subtract: bool = False, out: Optional[DeviceBatch] = None):
+        h = self._new_out(out)
+        self._check(self._lib.bgn_g1_add_h(self._ctx, a._h, b._h, 1 if subtract else 0, C.byref(h)))
+        return self._wrap(h, out)
+
+    def gt_mul_h(self, a: DeviceBatch, b: DeviceBatch, divide: bool = False, out: Optional[DeviceBatch] = None):
+        h = self._new_out(out)
+        self._check(self._lib.bgn_gt_mul_h(self._ctx, a._h, b._h, 1 if divide else 0, C.byref(h)))
+        return self._wrap(h, out)
+
+    def pair_h(self, a: DeviceBatch, b: Optional[DeviceBatch] = None, out: Optional[DeviceBatch] = None):
+        """e(a[i], b[i]); b = None: makeL2, e(a[i], P)"""
+        h = self._new_out(out)
+        self._check(self._lib.bgn_pair_h(self._ctx, a._h, b._h if b is not None else None, C.byref(h)))
+        return self._wrap(h, out)
+
+    def multpoly_h(self, c1: DeviceBatch, d1: int, c2: DeviceBatch, d2: int, count: int, out: Optional[DeviceBatch] = None):
+        h = self._new_out(out)
+        self._check(self._lib.bgn_multpoly_h(self._ctx, c1._h, d1, c2._h, d2, count, C.byref(h)))
+        return self._wrap(h, out)
+
+    def l2_sum_reduce_h(self, terms: DeviceBatch, nterms: int, ncoeff: int, out: Optional[DeviceBatch] = None):
+        h = self._new_out(out)
+        self._check(self._lib.bgn_l2_sum_reduce_h(self._ctx, terms._h, nterms, ncoeff, C.byref(h)))
+        return self._wrap(h, out)
+
+    def decrypt_h(self, cts: DeviceBatch):
+        """-> (int64 values, uint8 status) as numpy arrays; the level is the batch's kind"""
+        count = len(cts)
+        vals = np.empty(count, dtype=np.int64)
+        status = np.empty(count, dtype=np.uint8)
+        self._check(self._lib.bgn_decrypt_h(self._ctx, cts._h, _as_buf(vals)[0], _as_buf(status)[0]))
         return vals, status
 
     # ------------------------------------------------------------------ instrumentation

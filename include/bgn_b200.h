@@ -167,6 +167,30 @@ int bgn_evalpoly_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, int is_l2, uin
  * out: count*(d+1) GT elements, out[u][i] = e(in[u][i], P), out[u][d] = identity. */
 int bgn_make_poly_l2_batch(bgn_ctx* ctx, const uint8_t* in, size_t d, size_t count, uint8_t* out);
 
+/* ---- device-resident batches: chained operations without the byte format in between.
+ * A bgn_buf holds `count` elements of one group on the context's device in the kernels' own form.  The
+ * byte entry points above convert, and for G1 check the curve equation, on every call -- for a level-1
+ * addition that costs as much as the addition; a pipeline Encrypt -> EAdd -> EMult -> L2 sum -> Decrypt on
+ * handles runs kernel to kernel and meets the PBC byte format only at bgn_buf_import / bgn_buf_export.
+ * Same results as the byte forms, bit for bit.  Output handles: pass the address of a NULL handle to have
+ * one allocated, or of an earlier result to reuse its memory (it is reallocated if too small); an output
+ * must not alias an operand unless stated.  Handles belong to their context; free them before it. */
+typedef struct bgn_buf bgn_buf;
+enum { BGN_KIND_G1 = 1, BGN_KIND_GT = 2 };
+int bgn_buf_import(bgn_ctx* ctx, int kind, const uint8_t* bytes, size_t count, bgn_buf** out); /* Element.SetBytes */
+int bgn_buf_export(bgn_ctx* ctx, const bgn_buf* buf, uint8_t* bytes_out);                      /* Element.Bytes */
+int bgn_buf_info(const bgn_buf* buf, int* kind, size_t* count);
+void bgn_buf_free(bgn_buf* buf);
+/* bgn_encrypt_batch / g1_add|sub / gt_mul|div / pair (b = NULL: makeL2, e(a, P)) / multpoly / l2_sum_reduce /
+ * decrypt (level taken from the handle's kind) on handles */
+int bgn_encrypt_h(bgn_ctx* ctx, const int64_t* x, const uint8_t* r_be, size_t count, bgn_buf** out);
+int bgn_g1_add_h(bgn_ctx* ctx, const bgn_buf* a, const bgn_buf* b, int subtract, bgn_buf** out);
+int bgn_gt_mul_h(bgn_ctx* ctx, const bgn_buf* a, const bgn_buf* b, int divide, bgn_buf** out);
+int bgn_pair_h(bgn_ctx* ctx, const bgn_buf* a, const bgn_buf* b, bgn_buf** out);
+int bgn_multpoly_h(bgn_ctx* ctx, const bgn_buf* c1, size_t d1, const bgn_buf* c2, size_t d2, size_t count, bgn_buf** out);
+int bgn_l2_sum_reduce_h(bgn_ctx* ctx, const bgn_buf* in, size_t nterms, size_t ncoeff, bgn_buf** out);
+int bgn_decrypt_h(bgn_ctx* ctx, const bgn_buf* in, int64_t* out, uint8_t* status);
+
 /* ---- instrumentation (bench.py) ---- */
 /* When enabled, every kernel launch is bracketed by CUDA events on the context's
  * stream; bgn_timing_get returns the accumulated device time and launch count of

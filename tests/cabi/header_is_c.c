@@ -19,7 +19,10 @@ int main(void) {
       (fn)bgn_evalpoly_batch,      (fn)bgn_make_poly_l2_batch, (fn)bgn_timing_enable,
       (fn)bgn_timing_reset,        (fn)bgn_timing_get,         (fn)bgn_timing_last_call,
       (fn)bgn_bench_mulmod,        (fn)bgn_bench_imad_peak,    (fn)bgn_global_last_error,
-      (fn)bgn_bench_issue_mix};
+      (fn)bgn_bench_issue_mix,     (fn)bgn_buf_import,         (fn)bgn_buf_export,
+      (fn)bgn_buf_info,            (fn)bgn_buf_free,           (fn)bgn_encrypt_h,
+      (fn)bgn_g1_add_h,            (fn)bgn_gt_mul_h,           (fn)bgn_pair_h,
+      (fn)bgn_multpoly_h,          (fn)bgn_l2_sum_reduce_h,    (fn)bgn_decrypt_h};
   unsigned n = (unsigned)(sizeof(syms) / sizeof(syms[0])), ok = 0, i;
   for (i = 0; i < n; i++) ok += syms[i] != 0;
   /* a null context is rejected with a status, never a crash */

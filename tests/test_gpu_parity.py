@@ -258,6 +258,69 @@ def test_general_pairing_two_warps_equals_one_thread(kb):
     e.close()
 
 
+@pytest.mark.parametrize("kb", [128, 512])
+def test_device_resident_handles_chain(kb):
+    """Encrypt -> EAdd -> EMult (MultPoly) -> L2 sum -> Decrypt on device-resident handles (bgn_buf,
+    `*_h` entry points) gives the bytes of the byte-format entry points at every stage, decrypts to the
+    plaintext result, and launches no (de)serialisation kernel between the two edges."""
+    from bgn_b200 import Engine
+    g = load_golden(kb)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    e.set_secret(int(g["q1"], 16), g["msg_space"])
+    rng = random.Random(kb + 5)
+    n = int(g["n"], 16)
+    count, d = 9, 3
+    xa = np.array([rng.randrange(-1, 2) for _ in range(count * d)], dtype=np.int64)
+    xb = np.array([rng.randrange(-1, 2) for _ in range(count * d)], dtype=np.int64)
+    xc = np.array([rng.randrange(-1, 2) for _ in range(count * d)], dtype=np.int64)
+    ra, rb, rc = (e.scalars_be([rng.randrange(n) for _ in range(count * d)]) for _ in range(3))
+    # byte path
+    A, B_, C_ = e.encrypt_batch(xa, ra), e.encrypt_batch(xb, rb), e.encrypt_batch(xc, rc)
+    S = e.g1_add_batch(A, B_)
+    Dif = e.g1_sub_batch(A, B_)
+    Pr = e.multpoly_batch(S, d, C_, d, count)
+    Tot = e.l2_sum_reduce(Pr, count, 2 * d)
+    vals, st = e.decrypt_batch(Tot, True)
+    # handle path
+    e.timing_enable(True)
+    e.timing_reset()
+    hA, hB, hC = e.encrypt_h(xa, ra), e.encrypt_h(xb, rb), e.encrypt_h(xc, rc)
+    hS = e.g1_add_h(hA, hB)
+    hD = e.g1_add_h(hA, hB, subtract=True)
+    hP = e.multpoly_h(hS, d, hC, d, count)
+    hT = e.l2_sum_reduce_h(hP, count, 2 * d)
+    hv, hs = e.decrypt_h(hT)
+    for k in ("k_g1_from_bytes", "k_g1_to_bytes", "k_fp2_from_bytes", "k_fp2_to_bytes"):
+        assert e.timing_get(k)[1] == 0, k + " ran inside the handle chain"
+    assert (len(hS), hS.kind, len(hP), hP.kind, len(hT)) == (count * d, 1, count * 2 * d, 2, 2 * d)
+    assert hA.to_bytes().tobytes() == A.tobytes() and hS.to_bytes().tobytes() == S.tobytes()
+    assert hD.to_bytes().tobytes() == Dif.tobytes()
+    assert hP.to_bytes().tobytes() == Pr.tobytes() and hT.to_bytes().tobytes() == Tot.tobytes()
+    assert hv.tolist() == vals.tolist() and not hs.any() and not st.any()
+    plain = np.sum([np.convolve((xa + xb)[u * d:(u + 1) * d], xc[u * d:(u + 1) * d]) for u in range(count)], axis=0)
+    assert hv.tolist() == plain.tolist() + [0]
+    # import / export round trip, level-1 decrypt and plain pairings on handles, output reuse
+    imp = e.import_batch(1, S)
+    assert imp.to_bytes().tobytes() == S.tobytes()
+    v1, s1 = e.decrypt_h(imp)
+    assert not s1.any() and v1.tolist() == (xa + xb).tolist()
+    hM = e.pair_h(hA, hB)
+    assert hM.to_bytes().tobytes() == e.pair_batch(A, B_).tobytes()
+    assert e.pair_h(hA).to_bytes().tobytes() == e.make_l2_batch(A).tobytes()
+    assert e.gt_mul_h(hM, hM).to_bytes().tobytes() == e.gt_mul_batch(hM.to_bytes(), hM.to_bytes()).tobytes()
+    one = b"\x00" * (e.coord_bytes - 1) + b"\x01" + b"\x00" * e.coord_bytes
+    assert e.gt_mul_h(hM, hM, divide=True).to_bytes().tobytes() == one * (count * d)
+    reuse = e.g1_add_h(hA, hB, out=hD)
+    assert reuse is hD and hD.to_bytes().tobytes() == S.tobytes()
+    with pytest.raises(Exception):
+        e.g1_add_h(hA, hM)  # wrong group
+    with pytest.raises(Exception):
+        e.g1_add_h(hA, hB, out=hA)  # output aliases an operand
+    for h in (hA, hB, hC, hS, hD, hP, hT, imp, hM):
+        h.free()
+    e.close()
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)
