@@ -8,7 +8,7 @@ HAVE      := $(foreach l,$(LIMBS),-DBGN_HAVE_L$(l))
 SRC       := bgn_b200/csrc
 OBJ       := build
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h) include/bgn_b200.h
-OBJS      := $(OBJ)/api.o $(foreach l,$(LIMBS),$(OBJ)/inst_a_$(l).o $(OBJ)/inst_b_$(l).o $(OBJ)/inst_c_$(l).o $(OBJ)/inst_d_$(l).o)
+OBJS      := $(OBJ)/api.o $(foreach l,$(LIMBS),$(OBJ)/inst_a_$(l).o $(OBJ)/inst_b_$(l).o $(OBJ)/inst_c_$(l).o $(OBJ)/inst_d_$(l).o $(OBJ)/inst_e_$(l).o)
 LIB       := bgn_b200/libbgn_b200.so
 
 all: $(LIB)
@@ -28,6 +28,10 @@ $(OBJ)/inst_c_%.o: $(SRC)/inst_c.cu $(HDRS)
 $(OBJ)/inst_d_%.o: $(SRC)/inst_d.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -DBGN_L=$* -c $< -o $@ 2> $(OBJ)/inst_d_$*.log || (tail -30 $(OBJ)/inst_d_$*.log; false)
+
+$(OBJ)/inst_e_%.o: $(SRC)/inst_e.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DBGN_L=$* -c $< -o $@ 2> $(OBJ)/inst_e_$*.log || (tail -30 $(OBJ)/inst_e_$*.log; false)
 
 # api.o depends on WHICH limb counts are linked in: re-made whenever LIMBS changes
 $(OBJ)/limbs.stamp: FORCE

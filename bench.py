@@ -633,6 +633,80 @@ def run_inner_product(args, rank, world, local, dev, barrier, max_over_ranks, su
     return res
 
 
+def run_single_process(args):
+    """ONE process driving `--gpus` contexts, one host thread each (the shape of a Go integration: one
+    goroutine per device around the cgo calls).  Same workload and timing as the headline arm; the
+    threads meet at a barrier before and after the timed steps and the slowest thread's device time
+    counts.  Compare `value` with the torchrun arm's (one process per GPU) at the same N."""
+    import threading
+
+    import torch
+
+    from bgn_b200 import Engine
+    n = args.gpus
+    g = load_key()
+    p, nn, l = int(g["p"], 16), int(g["n"], 16), g["l"]
+    pairs = args.pairs
+    res = [None] * n
+    errs = []
+    bar = threading.Barrier(n)
+
+    def work(i):
+        try:
+            dev = torch.device("cuda", i)
+            eng = Engine(p, nn, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=i)
+            EB, SB = eng.elem_bytes, eng.scalar_bytes
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(1234 + i)
+
+            def make_batch(d):
+                digits = torch.randint(-1, 2, (pairs * d,), generator=gen, device=dev, dtype=torch.int64)
+                r = torch.randint(0, 256, (pairs * d, SB), generator=gen, device=dev, dtype=torch.uint8)
+                r[:, 0] &= 0x3F
+                return eng.encrypt_batch(digits, r.reshape(-1))
+
+            c1, c2 = make_batch(D1), make_batch(D2)
+            out = torch.empty(pairs * (D1 + D2) * EB, dtype=torch.uint8, device=dev)
+            eng.timing_enable(True)
+            for _ in range(args.warmup):
+                eng.multpoly_batch(c1, D1, c2, D2, pairs, out=out)
+            torch.cuda.synchronize(dev)
+            bar.wait()
+            t0 = time.perf_counter()
+            ms = 0.0
+            for _ in range(args.steps):
+                eng.multpoly_batch(c1, D1, c2, D2, pairs, out=out)
+                ms += eng.timing_last_call()
+            torch.cuda.synchronize(dev)
+            bar.wait()
+            res[i] = (ms, time.perf_counter() - t0)
+            eng.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+            try:
+                bar.abort()
+            except Exception:
+                pass
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        print(json.dumps({"impl": "single-process", "error": errs}), flush=True)
+        sys.exit(2)
+    dev_ms = max(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    value = n * pairs * args.steps * D1 * D2 / (dev_ms * 1e-3)
+    print(json.dumps({
+        "impl": "single-process", "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "wall_s": wall,
+        "value_by_wall_clock": n * pairs * args.steps * D1 * D2 / wall, "higher_is_better": True, "scaling": "weak",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "parallelism": "one process, one host thread and one bgn_ctx per GPU, no collective"},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -641,6 +715,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 14)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process, one host thread + context per GPU (instead of torchrun's process per GPU)")
     ap.add_argument("--no-inner", action="store_true", help="skip the keyBits=1024 inner product (config 5)")
     ap.add_argument("--inner-length", type=int, default=1 << 16)
     ap.add_argument("--no-verify", action="store_true")
@@ -648,6 +724,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_ours(args)
 

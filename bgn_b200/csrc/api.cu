@@ -136,6 +136,7 @@ struct bgn_ctx {
   const LOpsB* Bo = nullptr;
   const LOpsC* Co = nullptr;
   const LOpsD* Do = nullptr;
+  const LOpsE* Eo = nullptr;
   FieldConsts fc;
   PairConsts pc;
   cudaStream_t stream = nullptr;
@@ -153,6 +154,8 @@ struct bgn_ctx {
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
   size_t pair_duo_cap = (size_t)-1;  // pairings one wave of k_pair_duo holds (occupancy query, cached)
+  int miller_split = -1;       // MultPoly below one wave on the split team kernel (teamsplit.cuh): -1 = by the time model, 0 = never, 1 = always (BGN_MILLER_SPLIT)
+  double split_floor = 0.45, split_full = 0.65;  // time of a split wave in full k_miller waves: latency floor, full wave
   int pair_duo_loop = -1;      // products' row loop of k_pair_duo: -1 = the key size's default, 0 / 1 / 2 / 4 (A/B knob)
   int pair_duo_pairs = 2;      // most warp pairs per block of k_pair_duo (measured: 2 beats 1 and 4 at 2^14 pairings)
   bool pair_duo_blockbar = true;  // blocks of several pairs synchronise as a whole (lockstep: one instruction stream per role)
@@ -208,6 +211,7 @@ void activate(bgn_ctx* c) {
     CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
     CK(c->Co->upload(&c->fc, &c->pc, c->stream));
     CK(c->Do->upload(&c->fc, &c->pc, c->stream));
+    CK(c->Eo->upload(&c->fc, &c->pc, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     g_active[c->device] = c;
   }
@@ -217,6 +221,7 @@ void reupload_pc(bgn_ctx* c) {
   CK(c->Bo->upload(&c->fc, &c->pc, c->stream));
   CK(c->Co->upload(&c->fc, &c->pc, c->stream));
   CK(c->Do->upload(&c->fc, &c->pc, c->stream));
+  CK(c->Eo->upload(&c->fc, &c->pc, c->stream));
   CK(cudaStreamSynchronize(c->stream));
 }
 
@@ -449,6 +454,62 @@ size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
   return pad256(((count + upb - 1) / upb + 160) * pb) + 256;  // + one block per SM: small batches are spread out
 }
 
+// ---- the split team kernel (teamsplit.cuh): two threads per output-slot pair, for sub-wave batches
+struct SplitGeom {
+  int tpb = 0;       // teams (units) per block at most
+  size_t cap = 0;    // units one wave holds
+};
+SplitGeom miller_split_geom(bgn_ctx* c, int dM, int dE) {
+  SplitGeom g;
+  if (!c->Eo->miller_split || dM < 2 || 2 * dE > 384) return g;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int tpb = 384 / (2 * dE);
+  while (tpb > 0) {
+    int nt = (tpb * 2 * dE + 31) / 32 * 32;
+    if (c->Eo->miller_split_smem_bytes(nt, tpb * dE) + 16 <= 227 * 1024 - 64) break;
+    tpb--;
+  }
+  g.tpb = tpb;
+  g.cap = (size_t)sms * tpb;
+  return g;
+}
+// one launch: `count` units spread over the SMs, at most g.tpb per block
+void launch_miller_split(bgn_ctx* c, const SplitGeom& g, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast,
+                         size_t count, int out_slots, const GtArr& out) {
+  if (!count) return;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int tpb = (int)std::min<size_t>((size_t)g.tpb, std::max<size_t>(1, (count + sms - 1) / sms));
+  int nt = (tpb * 2 * dE + 31) / 32 * 32;
+  size_t smem = c->Eo->miller_split_smem_bytes(nt, tpb * dE) + 16;
+  MillerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Mx = M.x;
+  a.My = M.y;
+  a.Minf = M.inf;
+  a.NM = (int)M.N;
+  a.Ex = E.x;
+  a.Ey = E.y;
+  a.Einf = E.inf;
+  a.NE = (int)E.N;
+  a.e_bcast = e_bcast;
+  a.priv = nullptr;
+  a.out_re = out.re;
+  a.out_im = out.im;
+  a.NOUT = (int)out.N;
+  a.dM = dM;
+  a.dE = dE;
+  a.out_slots = out_slots;
+  a.count = (int)count;
+  a.teams_per_group = tpb;
+  a.group_threads = nt;
+  Timer t(c, "k_miller_split");
+  CK(c->Eo->miller_split_set_smem(smem));
+  c->Eo->miller_split(cfg(c, (count + tpb - 1) / tpb, nt, smem), a);
+  t.done();
+}
+
 // the Miller team kernel; dM <= dE
 void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int e_bcast, size_t count, int out_slots,
                 const GtArr& out, bool is_tail = false) {
@@ -492,6 +553,46 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
       GT_ = 128;
     }
     smem = c->A->miller_smem_bytes(groups * GT_) + 16;
+  }
+  // Sub-wave work -- a whole batch below one wave, or the remainder after the full waves -- goes to the
+  // split kernel (two threads per output-slot pair: 0.6 of the dependent chain per Miller step) when it
+  // fits ONE wave of that kernel; several balanced split waves replace a nearly empty last wave pair.
+  // Policy constants measured: profiles/r02_split_ab.json.
+  if (groups == 1 && !is_tail && !c->A->miller_fixed_threads() && c->miller_split != 0) {
+    SplitGeom g = miller_split_geom(c, dM, dE);
+    const size_t cap_std = (size_t)sms * tpg;
+    if (g.cap) {
+      auto g1_off = [&](const G1Arr& a, size_t n) { return G1Arr{a.x + n * c->L, a.y + n * c->L, a.inf + n, a.N - n}; };
+      auto gt_off = [&](size_t units) { return GtArr{out.re + units * out_slots * c->L, out.im + units * out_slots * c->L, out.N - units * out_slots}; };
+      const size_t full = count / cap_std, rem = count % cap_std;
+      // time model in units of one full wave of k_miller: a split wave of n units costs
+      // max(kSplitFloor, kSplitFull * n / cap_split)
+      auto t_split = [&](size_t n) { return std::max(c->split_floor, c->split_full * (double)n / (double)g.cap); };
+      auto t_std_rem = [&](size_t n) { return n == 0 ? 0.0 : (n * 2 <= cap_std ? 0.75 : 1.0); };
+      const double t_a = (double)full + t_std_rem(rem);                                       // all standard
+      const double t_b = rem && rem <= g.cap ? (double)full + t_split(rem) : 1e30;            // full waves + split remainder
+      const size_t kw = (count + g.cap - 1) / g.cap;
+      const double t_c = (double)kw * t_split((count + kw - 1) / kw);                          // balanced split waves
+      int choice = 0;
+      if (c->miller_split > 0) choice = (count <= g.cap || !full) ? 2 : 1;
+      else if (t_b < t_a && t_b <= t_c) choice = 1;
+      else if (t_c < t_a) choice = 2;
+      if (choice == 1 && rem && rem <= g.cap) {
+        if (full) run_miller(c, M, dM, E, dE, e_bcast, full * cap_std, out_slots, out, true);
+        launch_miller_split(c, g, g1_off(M, full * cap_std * dM), dM, e_bcast ? E : g1_off(E, full * cap_std * dE), dE, e_bcast, rem,
+                            out_slots, gt_off(full * cap_std));
+        return;
+      }
+      if (choice == 2) {
+        size_t done = 0;
+        for (size_t w = 0; w < kw; w++) {
+          size_t n = (count - done + (kw - w) - 1) / (kw - w);
+          launch_miller_split(c, g, g1_off(M, done * dM), dM, e_bcast ? E : g1_off(E, done * dE), dE, e_bcast, n, out_slots, gt_off(done));
+          done += n;
+        }
+        return;
+      }
+    }
   }
   // A batch smaller than one full wave: use the fewest warps per scheduler that still fit the batch
   // in one wave, in blocks of whole scheduler rounds (128 threads = one warp on each of the four
@@ -808,6 +909,7 @@ void ctx_free(bgn_ctx* c) {
     c->Bo->upload(&c->fc, &c->pc, c->stream);
     c->Co->upload(&c->fc, &c->pc, c->stream);
     if (c->Do) c->Do->upload(&c->fc, &c->pc, c->stream);
+    if (c->Eo) c->Eo->upload(&c->fc, &c->pc, c->stream);
     cudaStreamSynchronize(c->stream);
   }
   cudaFree(c->dPx);
@@ -956,6 +1058,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* fl = getenv("BGN_FIXED_LINES")) c->fixed_lines = atoi(fl) != 0;
     if (const char* fp = getenv("BGN_FIXED_PAIR")) c->fixed_pair = atoi(fp);
     if (const char* pd = getenv("BGN_PAIR_DUO")) c->pair_duo = atoi(pd);
+    if (const char* ms = getenv("BGN_MILLER_SPLIT")) c->miller_split = atoi(ms);
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -974,6 +1077,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     c->Bo = bgn_opsB_##n();  \
     c->Co = bgn_opsC_##n();  \
     c->Do = bgn_opsD_##n();  \
+    c->Eo = bgn_opsE_##n();  \
     break;
 #ifdef BGN_HAVE_L3
       BGN_PICK(3)
@@ -994,7 +1098,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
       default:
         break;
     }
-    if (!c->A || !c->Bo || !c->Co || !c->Do) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
+    if (!c->A || !c->Bo || !c->Co || !c->Do || !c->Eo) throw ArgErr{"this build of libbgn_b200 does not instantiate the limb count this key needs"};
     c->B = (pbits + 7) / 8;
     Big p(p0.begin(), p0.begin() + L);
     Big n = big_from_be(prm->n_be, prm->n_len, BGN_MAXL);
@@ -1151,6 +1255,8 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->fixed_pair = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo") {
     c->pair_duo = value < 0 ? -1 : (value != 0);
+  } else if (k == "miller_split") {
+    c->miller_split = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo_loop") {
     c->pair_duo_loop = (int)value;
     c->pair_duo_cap = (size_t)-1;

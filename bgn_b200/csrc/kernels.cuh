@@ -11,6 +11,7 @@
 #include "lucas.cuh"
 #include "pairlane.cuh"
 #include "pairwarp.cuh"
+#include "teamsplit.cuh"
 
 #ifdef BGN_HOSTSIM
 static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -959,6 +960,14 @@ __global__ void __launch_bounds__(256, 1) k_miller(const __grid_constant__ Mille
     }
   }
   T.run([=] { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory"); });
+}
+
+// the team kernel with two threads per output-slot pair (teamsplit.cuh): batches below one wave
+template <int L>
+__global__ void __launch_bounds__(384) k_miller_split(const __grid_constant__ MillerArgs a) {
+  extern __shared__ uint32_t smem_dyn[];
+  MillerSplit<L> T(a, smem_dyn, threadIdx.x, blockIdx.x, blockDim.x);
+  T.run([] { __syncthreads(); });
 }
 
 // fixed-first-argument pairing: one thread per evaluation point, no barriers

@@ -67,6 +67,17 @@ struct LOpsD {
   bool (*pair_duo)(int variant, LaunchCfg, const PairDuoArgs&);  // false: variant not instantiated
 };
 
+// inst_e.cu: the team kernel with two threads per output-slot pair (teamsplit.cuh).  It runs 12 warps per
+// SM, which caps it at 168 registers; ptxas applies a unit's tightest cap to the device functions its
+// kernels share, so it lives alone (in inst_d.cu it cost k_miller_fixed_pair 80 bytes of spills).
+struct LOpsE {
+  int L;
+  cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
+  size_t (*miller_split_smem_bytes)(int nt, int ncol);  // null above 17 limbs
+  cudaError_t (*miller_split_set_smem)(size_t smem);
+  void (*miller_split)(LaunchCfg, const MillerArgs&);
+};
+
 struct LOpsB {
   int L;
   cudaError_t (*upload)(const FieldConsts*, const PairConsts*, cudaStream_t);
@@ -92,7 +103,8 @@ struct LOpsB {
   extern "C" const LOpsA* bgn_opsA_##L(); \
   extern "C" const LOpsB* bgn_opsB_##L(); \
   extern "C" const LOpsC* bgn_opsC_##L(); \
-  extern "C" const LOpsD* bgn_opsD_##L();
+  extern "C" const LOpsD* bgn_opsD_##L(); \
+  extern "C" const LOpsE* bgn_opsE_##L();
 BGN_DECL_OPS(3)
 BGN_DECL_OPS(5)
 BGN_DECL_OPS(9)

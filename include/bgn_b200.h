@@ -82,6 +82,9 @@ const char* bgn_global_last_error(void);
  *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)
  *   "fixed_pair"   -1 | 0 | 1    e(., P) with one pairing split over a pair of lanes: -1 (default) below the
  *                                measured batch-size crossover, 0 never, 1 always
+ *   "miller_split" -1 | 0 | 1    MultPoly work below one wave (a small batch, or the remainder after the full waves) on
+ *                                the team kernel with two threads per output-slot pair: -1 (default) where the
+ *                                measured time model says it is faster, 0 never, 1 always
  *   "pair_duo"     -1 | 0 | 1    e(a, b) (bgn_pair_batch) with one pairing split over two warps: -1 (default)
  *                                for batches within one wave of that kernel, 0 never, 1 always                */
 int bgn_ctx_set_option(bgn_ctx* ctx, const char* name, long value);

@@ -73,6 +73,28 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
     for (auto& t : T) t.finalize();
   }
 }
+// k_miller_split (teamsplit.cuh): the same phase schedule as sim_miller, 2 dE threads per team
+template <int L>
+void sim_miller_split(const MillerArgs& a, int nblocks, int nt) {
+  std::vector<uint32_t> smem(MillerSplit<L>::smem_words(nt, a.teams_per_group * a.dE) + 8);
+  for (int b = 0; b < nblocks; b++) {
+    std::vector<MillerSplit<L>> T;
+    T.reserve(nt);
+    for (int tid = 0; tid < nt; tid++) T.emplace_back(a, smem.data(), tid, b, nt);
+    for (auto& t : T) t.init();
+    int n = c_pc.naf_len;
+    for (int idx = 1; idx < n; idx++) {
+      for (auto& t : T) t.phaseA(MOP_DBL, idx == 1);
+      for (auto& t : T) t.phaseB();
+      int d = c_pc.naf[idx];
+      if (d != 0 && idx != n - 1) {
+        for (auto& t : T) t.phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
+        for (auto& t : T) t.phaseB();
+      }
+    }
+    for (auto& t : T) t.finalize();
+  }
+}
 // k_pair_duo (pairwarp.cuh): the X warp runs one step AHEAD of the F warp -- the most the one
 // barrier per step allows -- so the run also checks the double buffering of the published values
 template <int L>
@@ -145,6 +167,7 @@ void hs_track_array(const uint32_t* a, size_t count, int L, double bound) {
   for (size_t e = 0; e < count; e++) bgnsim::setb(a + e * L, bound);
 }
 int hs_miller(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller<LL>(*a, nblocks, nt)) }
+int hs_miller_split(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller_split<LL>(*a, nblocks, nt)) }
 int hs_encrypt(int L, const EncArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) encrypt_body<LL>(*a, e)) }
 int hs_normalize(int L, const NormArgs* a) { FOR_L(L, for (size_t g = 0; g < (size_t)a->G; g++) normalize_body<LL>(*a, g)) }
 int hs_g1_add(int L, const G1AddArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) g1_add_body<LL>(*a, e)) }

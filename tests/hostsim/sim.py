@@ -267,6 +267,25 @@ class Sim:
         assert lib().hs_miller(self.L, C.byref(a), nblocks, nt) == 0
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
 
+    def miller_split(self, M, dM, E, dE, count, out_slots, teams_per_block=2):
+        """k_miller_split (teamsplit.cuh): two threads per output-slot pair"""
+        Mx, My, Mi = self.g1_arrays(M)
+        Ex, Ey, Ei = self.g1_arrays(E)
+        nout = count * out_slots
+        ore = np.zeros((nout, self.L), dtype=np.uint32)
+        oim = np.zeros((nout, self.L), dtype=np.uint32)
+        nt = teams_per_block * 2 * dE + 3  # a few idle threads: exercises the inactive path
+        a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
+                       Ex.shape[0], nout, 0, dM, dE, out_slots, count, teams_per_block, nt, 0)
+        nblocks = (count + teams_per_block - 1) // teams_per_block
+        assert lib().hs_miller_split(self.L, C.byref(a), nblocks, nt) == 0
+        return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
+
+    def multpoly_split(self, c1, d1, c2, d2, count, **kw):
+        if d1 <= d2:
+            return self.miller_split(c1, d1, c2, d2, count, d1 + d2, **kw)
+        return self.miller_split(c2, d2, c1, d1, count, d1 + d2, **kw)
+
     def record_lines(self, base):
         """api.cu: ensure_linesP -- k_miller_record"""
         nsteps = lib().hs_miller_nsteps(self.L)

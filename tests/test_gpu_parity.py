@@ -321,6 +321,43 @@ def test_device_resident_handles_chain(kb):
     e.close()
 
 
+@pytest.mark.parametrize("kb,count,d1,d2", [(512, 40, 11, 11), (512, 33, 3, 7), (256, 50, 5, 4), (128, 300, 2, 2),
+                                            (128, 20, 6, 11), (64, 1500, 3, 3)])
+def test_multpoly_split_team_kernel_equals_team_kernel(kb, count, d1, d2):
+    """MultPoly on the split team kernel (k_miller_split, teamsplit.cuh: two threads per output-slot pair)
+    gives the bytes of the team kernel and of the automatic policy, with O coefficients sprinkled in;
+    one product is also checked against the oracle."""
+    from bgn_b200 import Engine
+    from oracle import bgn_oracle as O
+    g = load_golden(kb)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    rng = random.Random(kb + count)
+    eb = e.elem_bytes
+    x1 = np.array([rng.randrange(-1, 2) for _ in range(count * d1)], dtype=np.int64)
+    x2 = np.array([rng.randrange(-1, 2) for _ in range(count * d2)], dtype=np.int64)
+    c1 = e.encrypt_batch(x1, e.scalars_be([rng.randrange(par.n) for _ in range(count * d1)]))
+    c2 = e.encrypt_batch(x2, e.scalars_be([rng.randrange(par.n) for _ in range(count * d2)]))
+    c1[eb: 2 * eb] = 0
+    c2[(d2 + 1) * eb: (d2 + 2) * eb] = 0
+    outs = {}
+    e.timing_enable(True)
+    for mode in (0, 1, -1):
+        e.set_option("miller_split", mode)
+        e.timing_reset()
+        outs[mode] = e.multpoly_batch(c1, d1, c2, d2, count).tobytes()
+        if mode == 1:
+            assert e.timing_get("k_miller_split")[1] >= 1, "the split kernel did not run"
+    assert outs[1] == outs[0] == outs[-1]
+    pk = O.PublicKey(par, O.g1_from_bytes(bytes.fromhex(g["P"]), par), O.g1_from_bytes(bytes.fromhex(g["Q"]), par), 0)
+    u = count - 1
+    A = [O.Ciphertext(O.g1_from_bytes(c1[(u * d1 + i) * eb:(u * d1 + i + 1) * eb].tobytes(), par), False) for i in range(d1)]
+    Bq = [O.Ciphertext(O.g1_from_bytes(c2[(u * d2 + i) * eb:(u * d2 + i + 1) * eb].tobytes(), par), False) for i in range(d2)]
+    exp = O.mult_poly(pk, O.PolyCiphertext(A, d1, 0, False), O.PolyCiphertext(Bq, d2, 0, False))
+    assert outs[1][u * (d1 + d2) * eb:] == O.poly_ct_bytes(pk, exp)
+    e.close()
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)

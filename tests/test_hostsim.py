@@ -146,6 +146,27 @@ def test_sim_multpoly(kb):
 
 
 @pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_multpoly_split(kb):
+    """k_miller_split (teamsplit.cuh: two threads per output-slot pair, partial accumulators multiplied
+    before the final exponentiation, shared memory laid out per column) against the golden MultPoly
+    vectors and the team kernel on other shapes (d1 != d2, d1 = 2, several units per block, O
+    coefficients); the run is the range proof of the split schedule."""
+    g, par, S, _ = setup(kb)
+    v = g["multpoly"]
+    c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+    S.range_report()
+    assert S.multpoly_split(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+    hi, headroom, unknown, viol = S.range_report()
+    assert viol == 0 and unknown == 0 and hi <= 40.0, (hi, unknown, viol)
+    if kb < 512:
+        assert S.multpoly_split(c2, v["d2"], c1, v["d1"], 1) == S.multpoly(c2, v["d2"], c1, v["d1"], 1)
+        assert S.multpoly_split(c1 * 3, v["d1"], c2 * 3, v["d2"], 3) == gts(par, v["out"]) * 3
+        assert S.multpoly_split(c1[:2] * 3, 2, c2 * 3, v["d2"], 3, teams_per_block=1) == S.multpoly(c1[:2] * 3, 2, c2 * 3, v["d2"], 3)
+        sq = c2[: v["d2"]]
+        assert S.multpoly_split(sq, v["d2"], sq, v["d2"], 1) == S.multpoly(sq, v["d2"], sq, v["d2"], 1)
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
 def test_sim_gt_ops(kb):
     g, par, S, _ = setup(kb)
     v = g["gt_mul"]
