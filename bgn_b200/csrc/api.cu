@@ -155,7 +155,6 @@ struct bgn_ctx {
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
   size_t pair_duo_cap = (size_t)-1;  // pairings one wave of k_pair_duo holds (occupancy query, cached)
   int miller_split = -1;       // MultPoly below one wave on the split team kernel (teamsplit.cuh): -1 = by the time model, 0 = never, 1 = always (BGN_MILLER_SPLIT)
-  double split_floor = 0.45, split_full = 0.65;  // time of a split wave in full k_miller waves: latency floor, full wave
   int pair_duo_loop = -1;      // products' row loop of k_pair_duo: -1 = the key size's default, 0 / 1 / 2 / 4 (A/B knob)
   int pair_duo_pairs = 2;      // most warp pairs per block of k_pair_duo (measured: 2 beats 1 and 4 at 2^14 pairings)
   bool pair_duo_blockbar = true;  // blocks of several pairs synchronise as a whole (lockstep: one instruction stream per role)
@@ -461,12 +460,12 @@ struct SplitGeom {
 };
 SplitGeom miller_split_geom(bgn_ctx* c, int dM, int dE) {
   SplitGeom g;
-  if (!c->Eo->miller_split || dM < 2 || 2 * dE > 384) return g;
+  if (!c->Eo->miller_split || dM < 2 || dE > 192) return g;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  int tpb = 384 / (2 * dE);
+  int tpb = 192 / dE;  // each half of a block (one thread role) is at most 6 warps
   while (tpb > 0) {
-    int nt = (tpb * 2 * dE + 31) / 32 * 32;
+    int nt = 2 * ((tpb * dE + 31) / 32 * 32);
     if (c->Eo->miller_split_smem_bytes(nt, tpb * dE) + 16 <= 227 * 1024 - 64) break;
     tpb--;
   }
@@ -481,7 +480,7 @@ void launch_miller_split(bgn_ctx* c, const SplitGeom& g, const G1Arr& M, int dM,
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int tpb = (int)std::min<size_t>((size_t)g.tpb, std::max<size_t>(1, (count + sms - 1) / sms));
-  int nt = (tpb * 2 * dE + 31) / 32 * 32;
+  int nt = 2 * ((tpb * dE + 31) / 32 * 32);  // two halves of whole warps: one thread role per warp
   size_t smem = c->Eo->miller_split_smem_bytes(nt, tpb * dE) + 16;
   MillerArgs a;
   memset(&a, 0, sizeof(a));
@@ -565,11 +564,15 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
       auto g1_off = [&](const G1Arr& a, size_t n) { return G1Arr{a.x + n * c->L, a.y + n * c->L, a.inf + n, a.N - n}; };
       auto gt_off = [&](size_t units) { return GtArr{out.re + units * out_slots * c->L, out.im + units * out_slots * c->L, out.N - units * out_slots}; };
       const size_t full = count / cap_std, rem = count % cap_std;
-      // time model in units of one full wave of k_miller: a split wave of n units costs
-      // max(kSplitFloor, kSplitFull * n / cap_split)
-      auto t_split = [&](size_t n) { return std::max(c->split_floor, c->split_full * (double)n / (double)g.cap); };
-      auto t_std_rem = [&](size_t n) { return n == 0 ? 0.0 : (n * 2 <= cap_std ? 0.75 : 1.0); };
-      const double t_a = (double)full + t_std_rem(rem);                                       // all standard
+      // Time model in units of one full wave of k_miller (measured at 11 x 11 slots, 17 limbs:
+      // profiles/r02_split_ab_v2.json).  A split wave's time steps with the warps each thread role
+      // occupies per SM: <= 2 (one per scheduler pair) 0.49, <= 4: 0.60, <= 6 (full): 0.81.  The team
+      // kernel: a batch within half a wave (one warp per scheduler) 0.76, anything else whole waves.
+      auto t_split = [&](size_t n) {
+        const size_t u = (n + sms - 1) / sms, w = (u * (size_t)dE + 31) / 32;
+        return w <= 2 ? 0.49 : (w <= 4 ? 0.60 : 0.81);
+      };
+      const double t_a = count > cap_std ? (double)((count + cap_std - 1) / cap_std) : (count * 2 <= cap_std ? 0.76 : 1.0);
       const double t_b = rem && rem <= g.cap ? (double)full + t_split(rem) : 1e30;            // full waves + split remainder
       const size_t kw = (count + g.cap - 1) / g.cap;
       const double t_c = (double)kw * t_split((count + kw - 1) / kw);                          // balanced split waves

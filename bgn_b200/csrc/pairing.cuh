@@ -53,6 +53,14 @@
 #ifndef BGN_MILLER_LOOP_A
 #define BGN_MILLER_LOOP_A (BGN_L <= 17 ? 0 : 4)
 #endif
+// Phase B of the TEAM kernel (line_mul: three quarters of its work).  Round 2, measured at 33 limbs on a
+// full wave of 8 x 8 products (profiles/r02_ab1024_unroll.txt): 8-row loop in both phases 0.813 of the
+// IMAD.WIDE peak, everything unrolled 0.831, phase B unrolled and phase A looped 0.850 -- the five
+// unrolled products of line_mul (175 KB) are walked by all warps of the block in lockstep, the twelve
+// of dbl_line would not stay cached.  Up to 17 limbs this is BGN_MILLER_LOOP (unrolled) as before.
+#ifndef BGN_TEAM_LOOP_B
+#define BGN_TEAM_LOOP_B (BGN_L <= 17 ? BGN_MILLER_LOOP : 0)
+#endif
 
 BGN_CONST PairConsts c_pc;
 
@@ -105,7 +113,7 @@ struct MillerTeam {
   static constexpr bool GP = BGN_MILLER_GP != 0;
   static constexpr int NT = BGN_MILLER_NT;
   static constexpr int ES = GP ? NT : 1;          // element stride of every slot
-  typedef MF<L, BGN_MILLER_LOOP, ES> M;      // phase B
+  typedef MF<L, BGN_TEAM_LOOP_B, ES> M;      // phase B
   typedef MF<L, BGN_MILLER_LOOP_A, ES> MA;   // phase A
   // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
   // the line it publishes, its evaluation point.  The loop's routines are fused (fused.cuh) and

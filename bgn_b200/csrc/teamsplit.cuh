@@ -39,20 +39,24 @@ struct MillerSplit {
   int t, h, team, unit, col, base_col, ptid;  // ptid: the partner thread (t, 1 - h)
   bool active;
 
-  // a block is teams_per_group teams of 2 dE threads (blockDim >= that, rounded up to whole warps)
+  // A block is teams_per_group teams.  Its first blockDim / 2 threads are the (t, 0) halves of all teams,
+  // the second blockDim / 2 the (t, 1) halves (each half padded to whole warps): a warp then holds threads
+  // of ONE role, so the Miller-point warps (dbl_line / madd_line) and the squaring warps of phase A run side
+  // by side.  With both halves of a team in one warp the two roles diverge and serialise -- measured: 72 ms
+  // against 54 ms for a batch of 692 products (profiles/r02_split_ab_v1.json against _v2).
   BGN_DEV MillerSplit(const MillerArgs& a_, uint32_t* smem_, int tid_, int bid_, int nt_)
       : a(a_), smem(smem_), nt(nt_), tid(tid_) {
-    const int TS = 2 * a.dE;
+    const int half = nt >> 1;
     ncol = a.teams_per_group * a.dE;
-    team = tid / TS;
-    const int ltid = tid - team * TS;
-    h = ltid / a.dE;
-    t = ltid - h * a.dE;
+    h = tid >= half ? 1 : 0;
+    const int r = tid - h * half;
+    team = r / a.dE;
+    t = r - team * a.dE;
     unit = bid_ * a.teams_per_group + team;
     active = team < a.teams_per_group && unit < a.count;
     base_col = team * a.dE;
     col = base_col + t;
-    ptid = team * TS + (1 - h) * a.dE + t;
+    ptid = (1 - h) * half + r;
   }
   static BGN_HD size_t smem_words(int nt, int ncol) {
     return ((size_t)NA * nt + (size_t)NC * ncol) * L + (2 * (size_t)ncol + 3) / 4;

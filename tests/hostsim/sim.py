@@ -274,7 +274,7 @@ class Sim:
         nout = count * out_slots
         ore = np.zeros((nout, self.L), dtype=np.uint32)
         oim = np.zeros((nout, self.L), dtype=np.uint32)
-        nt = teams_per_block * 2 * dE + 3  # a few idle threads: exercises the inactive path
+        nt = 2 * (teams_per_block * dE + 2)  # two halves (one role each) with idle threads: the inactive path
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 0, dM, dE, out_slots, count, teams_per_block, nt, 0)
         nblocks = (count + teams_per_block - 1) // teams_per_block
