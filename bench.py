@@ -470,21 +470,21 @@ def run_ours(args):
         "encrypt": {"config": "BASELINE config 2: 2^16 plaintexts x 11 digits = 720 896 coefficient encryptions, 16-bit windows of Q",
                     "per_s": sum_over_ranks(n_enc / (enc_ms * 1e-3)), "plaintexts_per_s": sum_over_ranks(n_pt / (enc_ms * 1e-3)),
                     "ms": max_over_ranks(enc_ms),
-                    "roofline": op_roofline("k_encrypt<17>", enc_k, n_enc, workmodel.encrypt_modmuls(n, SB, 16) * ppm)},
+                    "roofline": op_roofline("k_encrypt<17>", enc_k, n_enc, workmodel.encrypt_products(n, SB, 16, L))},
         "encrypt_window24": {"config": "the same with 24-bit windows (50 GB table)", "per_s": sum_over_ranks(n_enc / (enc24_ms * 1e-3)),
                              "ms": max_over_ranks(enc24_ms),
-                             "roofline": op_roofline("k_encrypt<17>", enc24_k, n_enc, workmodel.encrypt_modmuls(n, SB, 24) * ppm)},
+                             "roofline": op_roofline("k_encrypt<17>", enc24_k, n_enc, workmodel.encrypt_products(n, SB, 24, L))},
         "eadd": {"config": "BASELINE config 2: 2^15 pairwise AddPoly = 360 448 level-1 coefficient additions",
                  "per_s": sum_over_ranks(half / (add_ms * 1e-3)), "ms": max_over_ranks(add_ms),
-                 "roofline": op_roofline("k_g1_affadd<17>", add_k, half, 6 * ppm),
-                 "roofline_note": "6 products per addition; the shared inversion runs on the ALU pipe (division-step "
+                 "roofline": op_roofline("k_g1_affadd<17>", add_k, half, workmodel.affadd_products(L)),
+                 "roofline_note": "5 products and 1 squaring per addition; the shared inversion runs on the ALU pipe (division-step "
                                   "GCD) and the (de)serialisation kernels around it are HBM-side: this op is not "
                                   "multiply-bound, the fraction says how far"},
         "eadd_handles": {"config": "the same 360 448 additions on device-resident handles (bgn_g1_add_h): the byte format, its "
                                    "Montgomery conversion and the curve check are paid once at import, not per operation",
                          "per_s": sum_over_ranks(half / (addh_ms * 1e-3)), "ms": max_over_ranks(addh_ms),
                          "bytes_equal_byte_path": all_true(addh_same),
-                         "roofline": op_roofline("k_g1_affadd<17>", addh_k, half, 6 * ppm)},
+                         "roofline": op_roofline("k_g1_affadd<17>", addh_k, half, workmodel.affadd_products(L))},
         "mult_pairs": {"config": "2^14 plain Mult (one pairing each, bgn.go:294-314)", "per_s": sum_over_ranks(n_dec / (pair_ms * 1e-3)),
                        "ms": max_over_ranks(pair_ms), "roofline": op_roofline(pair_kernel, pair_k, n_dec, pair_prod)},
         "decrypt_l2": {"config": "BASELINE config 4: 2^14 level-2 ciphertexts, T = 2^20, half negative, 1 % zeros",

@@ -36,6 +36,7 @@ static thread_local uint32_t cc = 0;
 static uint64_t nmul = 0;  // Montgomery products executed (work model check, tests only)
 static uint64_t nmulw = 0, nredc = 0;  // double-width products / separate reductions executed
 static uint64_t nmulk = 0;             // of which Karatsuba products (counted apart from nmulw)
+static uint64_t nsqrw = 0;             // dedicated double-width squarings (L (L + 1) / 2 products each)
 static uint64_t ndot2 = 0;             // one-pass dot products a0 b0 + a1 b1 (3L^2 + L products each)
 static uint64_t safegcd_fallbacks = 0;  // F<L>::inv_gcd<SAFE>: times the verified fast inversion fell back
 // Range tracker (tests only): every element written by the arithmetic below carries an upper
@@ -705,7 +706,82 @@ struct Fp {
     addc(r[L - 1], A[L - 1], B[L]);
   }
 
-  BGN_DEV static void sqr(uint32_t (&r)[L], const uint32_t (&a)[L]) { mul(r, a, a); }
+  // ---- dedicated squaring (round 2): r = a^2 / R mod p with L (L + 1) / 2 products for the square
+  // (every cross product a_i a_j, i < j, once, against the doubled operand 2a; the L squares a_i^2 lead
+  // the even chains) plus the L^2 + L of one Montgomery reduction: 459 instead of 595 at L = 17.  The
+  // double-width square is accumulated in two arrays as in the product rows -- XE holds the pairs
+  // aligned at even limb positions, XO those at odd positions (XO[k] is position k + 1) -- so every
+  // (mad.lo.cc, madc.hi.cc) pair still fuses into one IMAD.WIDE.  Row i touches positions 2i and up
+  // only; its carry-out lands on a limb no earlier row has used for more than a carry.
+  // Requires 2a < R (a < 128 p); r < a^2 / R + p.
+  template <int I>
+  BGN_DEV static void sq_row(uint32_t (&XE)[2 * L + 2], uint32_t (&XO)[2 * L + 2], const uint32_t (&a)[L],
+                             const uint32_t (&a2)[L]) {
+    const uint32_t s = a[I];
+    // even chain: a_I^2 at position 2I, then a_I * (2 a_j) for j = I + 2, I + 4, ...
+    mad_wide_cc(XE[2 * I], XE[2 * I + 1], a[I], s);
+    BGN_UNROLL
+    for (int j = I + 2; j < L; j += 2) madc_wide_cc(XE[I + j], XE[I + j + 1], a2[j], s);
+    {
+      constexpr int JL = I + 2 * ((L - 1 - I) / 2);  // last j of the even chain
+      addc(XE[I + JL + 2], XE[I + JL + 2], 0);
+    }
+    // odd chain: a_I * (2 a_j) for j = I + 1, I + 3, ...: position I + j is odd, XO index I + j - 1
+    if (I + 1 < L) {
+      // the first limb of 2 * (a >> 32 (I + 1)) is a_{I+1} << 1 WITHOUT the bit a_I shifts out (that bit
+      // belongs to the doubling of the part at and below limb I, which this row does not multiply)
+      mad_wide_cc(XO[2 * I], XO[2 * I + 1], a[I + 1 < L ? I + 1 : 0] << 1, s);
+      BGN_UNROLL
+      for (int j = I + 3; j < L; j += 2) madc_wide_cc(XO[I + j - 1], XO[I + j], a2[j], s);
+      constexpr int JL = I + 1 + 2 * ((L - 2 - I) / 2 < 0 ? 0 : (L - 2 - I) / 2);  // last j of the odd chain
+      addc(XO[I + JL + 1], XO[I + JL + 1], 0);
+    }
+  }
+  template <int I, bool END = (I >= L)>
+  struct SqRows {
+    BGN_DEV static void run(uint32_t (&XE)[2 * L + 2], uint32_t (&XO)[2 * L + 2], const uint32_t (&a)[L],
+                            const uint32_t (&a2)[L]) {
+      sq_row<I>(XE, XO, a, a2);
+      SqRows<I + 1>::run(XE, XO, a, a2);
+    }
+  };
+  template <int I>
+  struct SqRows<I, true> {
+    BGN_DEV static void run(uint32_t (&)[2 * L + 2], uint32_t (&)[2 * L + 2], const uint32_t (&)[L], const uint32_t (&)[L]) {}
+  };
+  // T = a^2 (double width)
+  BGN_DEV static void sqrw(uint32_t (&T)[2 * L], const uint32_t (&a)[L]) {
+    uint32_t XE[2 * L + 2], XO[2 * L + 2], a2[L];
+#ifdef BGN_HOSTSIM
+    {
+      double A = BGN_GETB(a);
+      BGN_CHECK(2.0 * A <= bgnsim::headroom, "squaring operand too large");
+      bgnsim::setw(T, A * A, 0.0);
+      bgnsim::nsqrw++;
+    }
+#endif
+    BGN_UNROLL
+    for (int j = 0; j < 2 * L + 2; j++) XE[j] = 0, XO[j] = 0;
+    BGN_UNROLL
+    for (int j = L - 1; j > 0; j--) a2[j] = (a[j] << 1) | (a[j - 1] >> 31);
+    a2[0] = a[0] << 1;
+    SqRows<0>::run(XE, XO, a, a2);
+    // T = XE + (XO << 32)
+    T[0] = XE[0];
+    add_cc(T[1], XE[1], XO[0]);
+    BGN_UNROLL
+    for (int j = 2; j < 2 * L - 1; j++) addc_cc(T[j], XE[j], XO[j - 1]);
+    addc(T[2 * L - 1], XE[2 * L - 1], XO[2 * L - 2]);
+  }
+  BGN_DEV static void sqr(uint32_t (&r)[L], const uint32_t (&a)[L]) {
+#ifdef BGN_NO_DEDICATED_SQR
+    mul(r, a, a);
+#else
+    uint32_t T[2 * L];
+    sqrw(T, a);
+    redc(r, T);
+#endif
+  }
 
   // r = a + b, kept in [0,2p)
   BGN_DEV static void add(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {

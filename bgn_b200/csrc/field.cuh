@@ -74,7 +74,14 @@ struct F {
     P::mul(z, x, y);
     st<L>(r, z);
   }
-  BGN_DEV static void sqr(E r, const uint32_t* a) { mul(r, a, a); }
+  // r = a^2 through the dedicated squaring (arith.cuh: Fp::sqr): 3 of the 11 products of a mixed addition,
+  // 6 of the 9 of a doubling, so Encrypt / MultConst / the table builds execute ~8 % / ~15 % fewer products
+  BGN_DEVNI static void sqr(E r, const uint32_t* a) {
+    uint32_t x[L], z[L];
+    ld<L>(x, a);
+    P::sqr(z, x);
+    st<L>(r, z);
+  }
   // measured alternatives (tools/primbench.py modes 10, 22): multiplier streamed from memory / two
   // interleaved products per call
   BGN_DEVNI static void mul_stream(E r, const uint32_t* a, const uint32_t* b) {

@@ -94,7 +94,7 @@ struct MillerFixedPair {
   BGN_DEV static void fe_sq(uint32_t (&t)[L], const State& st, int s) {
     uint32_t x[L];
     LU::sel(x, s == 0, st.f0, st.f1);
-    P::mul(t, x, x);
+    P::mul(t, x, x);  // (once per pairing: the dedicated squaring's two double-width arrays would cost this kernel spills)
   }
   // stage 2 (after the exchange: u = f0^2, v = f1^2 in both lanes): both lanes form N = u + v, invert it
   // (verified division-step GCD, ALU pipe) and scale their coordinate of conj(f)^2 = (u - v) - 2 f0 f1 i.

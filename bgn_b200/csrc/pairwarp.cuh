@@ -32,6 +32,17 @@ struct MDuo : MF<L, U, 1> {
   typedef uint32_t R[L];
   using B::dbl;
   using B::mulm;
+  // the dedicated squaring also with looped products (fused.cuh: sqrm uses it only when U == 0): the
+  // X warp's doubling is 6 squarings of 9 products and the X warp is the critical path; measured by A/B
+#ifndef BGN_DUO_SQR
+#define BGN_DUO_SQR 1
+#endif
+  BGN_DEV static void sqrm(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* mem) {
+    if (BGN_DUO_SQR && L <= 17)
+      P::sqr(r, a);
+    else
+      mulm(r, a, mem);
+  }
 
   // ---- X warp.  (X, Y, Z) <- 2 (X, Y, Z), 9 products; publishes M = 3 XX + ZZ^2, ZZ, Z3 = 2 Y Z,
   // the old X and 2 YY.   in: X, Y, Z < 9p.   out: X, Y < 6p, Z < 3p; oM < 6p, oZZ < 2p, oZ3 < 3p,
@@ -40,14 +51,14 @@ struct MDuo : MF<L, U, 1> {
     R x, w, xx, yy, zz, m, s;
     ld<L>(x, X);
     st<L>(oX, x);
-    mulm(xx, x, X);            // XX
+    sqrm(xx, x, X);            // XX
     ld<L>(w, Y);
-    mulm(yy, w, Y);            // YY
+    sqrm(yy, w, Y);            // YY
     dbl(w, w);                 // 2Y
     ld<L>(s, Z);
-    mulm(zz, s, Z);            // ZZ
+    sqrm(zz, s, Z);            // ZZ
     st<L>(oZZ, zz);
-    mulm(m, zz, oZZ);          // ZZ^2
+    sqrm(m, zz, oZZ);          // ZZ^2
     P::addn(m, m, xx);
     dbl(xx, xx);
     P::addn(m, m, xx);         // M = 3 XX + ZZ^2
@@ -59,8 +70,8 @@ struct MDuo : MF<L, U, 1> {
     st<L>(oYY2, yy);
     dbl(x, x);                 // 2X
     mulm(s, x, oYY2);          // S = 2X * 2YY
-    mulm(zz, yy, oYY2);        // 4 YY^2
-    mulm(xx, m, oM);           // M^2
+    sqrm(zz, yy, oYY2);        // 4 YY^2
+    sqrm(xx, m, oM);           // M^2
     dbl(w, s);
     P::subk(xx, xx, w, c_fc.p4, 4);  // X3 = M^2 - 2S
     st<L>(X, xx);
@@ -80,7 +91,7 @@ struct MDuo : MF<L, U, 1> {
     ld<L>(ya, yA);
     if (negate) P::negk(ya, ya, c_fc.p2, 2);
     ld<L>(z, Z);
-    mulm(w, z, Z);             // ZZ
+    sqrm(w, z, Z);             // ZZ
     st<L>(t0, w);
     mulm(h, xa, t0);           // U2 = xA ZZ
     ld<L>(w, X);
@@ -97,12 +108,12 @@ struct MDuo : MF<L, U, 1> {
     mulm(v, z, t0);            // Z3 = Z * 2H
     st<L>(Z, v);
     st<L>(oZ3, v);
-    mulm(v, w, t0);            // I = (2H)^2
+    sqrm(v, w, t0);            // I = (2H)^2
     ld<L>(z, X);               // z <- X
     st<L>(t1, v);
     mulm(w, h, t1);            // J = H I
     mulm(v, z, t1);            // V = X I
-    mulm(c, r, oR);            // r^2
+    sqrm(c, r, oR);            // r^2
     dbl(z, v);
     P::addn(z, z, w);          // J + 2V
     P::subk(c, c, z, c_fc.p4, 4);    // X3 = r^2 - J - 2V

@@ -15,6 +15,17 @@ def products_per_modmul(L: int) -> int:
     return 2 * L * L + L
 
 
+def products_per_sqr(L: int) -> int:
+    """the dedicated squaring (arith.cuh: Fp::sqr): L (L + 1) / 2 for the square + L^2 + L for its reduction"""
+    return L * (L + 1) // 2 + L * L + L
+
+
+def fused_sqr(L: int) -> bool:
+    """fused.cuh MF::SQR: the fused routines square with Fp::sqr where their products are unrolled (up to
+    17 limbs); the looped variants of the 1024-bit field keep the product"""
+    return L <= 17
+
+
 def pick_limbs(p: int) -> int:
     for L in (3, 5, 9, 17, 33):
         if 32 * L >= p.bit_length() + 8:
@@ -57,21 +68,35 @@ def line_lazy(L: int) -> bool:
     return L <= 17
 
 
+def miller_unit_squarings(p: int, n: int, l: int, dM: int, dE: int) -> int:
+    """of miller_unit_modmuls, how many are dedicated squarings: 6 of dbl_line's 12 (XX, YY, ZZ, ZZ^2,
+    (2YY)^2, M^2), 3 of madd_line's 13 (ZZ, (2H)^2, r^2), 2 of fe_prepare's 3 per output slot"""
+    L = pick_limbs(p)
+    if not fused_sqr(L):
+        return 0
+    naf = naf_digits(n)
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    return D * dM * 6 + A * dM * 3 + (dM + dE - 1) * 2
+
+
 def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int) -> int:
     """32x32->64 products one unit of k_miller executes.  Every F_p product is a fused
     multiply-and-reduce of 2L^2 + L, except that the lazy-reduction line_mul (fused.cuh) spends
-    2 (2L^2 + L) + 3 L^2 + 2 (L^2 + L) on its 5 multiplications and 4 reductions."""
+    2 (2L^2 + L) + 3 L^2 + 2 (L^2 + L) on its 5 multiplications and 4 reductions, and that the
+    squarings (round 2) cost L (L + 1) / 2 + L^2 + L."""
     L = pick_limbs(p)
     mm = miller_unit_modmuls(p, n, l, dM, dE)
+    nsq = miller_unit_squarings(p, n, l, dM, dE)
+    full, sq = products_per_modmul(L), products_per_sqr(L)
     if not line_lazy(L):
-        return mm * products_per_modmul(L)
+        return (mm - nsq) * full + nsq * sq
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     lines = (D + A) * dM * dE
-    full = products_per_modmul(L)
     lazy = 2 * full + 3 * L * L + 2 * (L * L + L)
-    return (mm - 5 * lines) * full + lines * lazy
+    return (mm - 5 * lines - nsq) * full + lines * lazy + nsq * sq
 
 
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
@@ -97,7 +122,8 @@ def miller_fixed_products(p: int, n: int, l: int) -> int:
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     full = products_per_modmul(L)
     line = (2 * full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 5 * full
-    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1)) * full
+    nsq = 2 if fused_sqr(L) else 0  # fe_prepare: f0^2, f1^2
+    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1) - nsq) * full + nsq * products_per_sqr(L)
 
 
 def miller_fixed_pair_counts(p: int, n: int, l: int):
@@ -123,27 +149,35 @@ def miller_fixed_pair_products(p: int, n: int, l: int) -> int:
     return dots * (3 * L * L + L) + muls * products_per_modmul(L)
 
 
-def pair_duo_counts(p: int, n: int, l: int):
+def duo_loop_default(L: int) -> int:
+    """api.cu: pair_duo_variant -- the shipped loop shape of k_pair_duo's products"""
+    return 2 if L == 17 else (0 if L < 17 else 4)
+
+
+def pair_duo_counts(p: int, n: int, l: int, loop: int = None):
     """k_pair_duo (pairwarp.cuh), BOTH warps' lanes of one pairing together:
-    -> (fused Montgomery products, double-width products, separate reductions).
-    Doubling step: X 9, F 4 (line at B) + 2 (sqr2, not on the first step); addition step: X 11, F 3;
-    every step one F_p^2 product f * l: 3 double-width products + 2 reductions up to 17 limbs (lazy), 3
-    fused products beyond; final exponentiation of one slot as k_miller_fixed."""
+    -> (fused Montgomery products, double-width products, separate reductions, dedicated squarings).
+    Doubling step: X 9 (6 of them squarings up to 17 limbs), F 4 (line at B) + 2 (sqr2, not on the first
+    step); addition step: X 11 (3 squarings), F 3; every step one F_p^2 product f * l: 3 double-width
+    products + 2 reductions up to 17 limbs (lazy), 3 fused products beyond; final exponentiation of one slot
+    as k_miller_fixed (its two squarings dedicated only with unrolled products, loop == 0)."""
     L = pick_limbs(p)
+    loop = duo_loop_default(L) if loop is None else loop
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     mm = D * (9 + 4) + (D - 1) * 2 + A * (11 + 3) + final_exp_modmuls(p, l, L, 1, 1) + 1  # + the inversion's check
+    nsq = (D * 6 + A * 3 if L <= 17 else 0) + (2 if loop == 0 else 0)
     if line_lazy(L):
-        return mm, 3 * (D + A), 2 * (D + A)
-    return mm + 3 * (D + A), 0, 0
+        return mm - nsq, 3 * (D + A), 2 * (D + A), nsq
+    return mm - nsq + 3 * (D + A), 0, 0, nsq
 
 
-def pair_duo_products(p: int, n: int, l: int) -> int:
+def pair_duo_products(p: int, n: int, l: int, loop: int = None) -> int:
     """32x32->64 products one k_pair_duo pairing executes (both warps)"""
     L = pick_limbs(p)
-    mm, mw, rd = pair_duo_counts(p, n, l)
-    return mm * products_per_modmul(L) + mw * L * L + rd * (L * L + L)
+    mm, mw, rd, nsq = pair_duo_counts(p, n, l, loop)
+    return mm * products_per_modmul(L) + mw * L * L + rd * (L * L + L) + nsq * products_per_sqr(L)
 
 
 def canonical_pairing_modmuls(n: int, l: int) -> int:
@@ -165,6 +199,21 @@ def dec_lucas_modmuls(e: int) -> int:
     if e == 0:
         return 0
     return 2 * (e.bit_length() - 1) + 2 * 3 + 2
+
+
+def madd_products(L: int) -> int:
+    """one complete mixed addition (curve.cuh: G::madd): 8 products and 3 dedicated squarings"""
+    return 8 * products_per_modmul(L) + 3 * products_per_sqr(L)
+
+
+def affadd_products(L: int) -> int:
+    """one affine addition with a shared inversion (k_g1_affadd): 5 products and 1 squaring (the slope's)"""
+    return 5 * products_per_modmul(L) + products_per_sqr(L)
+
+
+def encrypt_products(n: int, rbytes: int, window_bits: int, L: int, p_x_nonzero: float = 2.0 / 3.0) -> float:
+    """k_encrypt, EXPECTED 32x32->64 products per coefficient (see encrypt_modmuls for the addition count)"""
+    return encrypt_modmuls(n, rbytes, window_bits, p_x_nonzero) / 11.0 * madd_products(L)
 
 
 def encrypt_modmuls(n: int, rbytes: int, window_bits: int = 8, p_x_nonzero: float = 2.0 / 3.0) -> float:

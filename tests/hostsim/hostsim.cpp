@@ -262,12 +262,24 @@ void hs_wide_count(uint64_t* out, int reset) {
   out[1] = bgnsim::nredc;
   out[2] = bgnsim::nmulk;
   out[3] = bgnsim::ndot2;
-  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = bgnsim::ndot2 = 0;
+  out[4] = bgnsim::nsqrw;
+  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = bgnsim::ndot2 = bgnsim::nsqrw = 0;
 }
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;
   if (reset) bgnsim::nmul = 0;
   return v;
+}
+// r[i] = a[i]^2 through the dedicated squaring and through the product: both must agree limb for limb
+int hs_fp_sqr(int L, uint32_t* r_sqr, uint32_t* r_mul, const uint32_t* a, size_t count) {
+  FOR_L(L, for (size_t i = 0; i < count; i++) {
+    uint32_t x[LL], y[LL], z[LL];
+    ld<LL>(x, a + i * LL);
+    Fp<LL>::sqr(y, x);
+    Fp<LL>::mul(z, x, x);
+    st<LL>(r_sqr + i * LL, y);
+    st<LL>(r_mul + i * LL, z);
+  })
 }
 int hs_fp_inv(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, Loc<LL> t; F<LL>::inv(r, a, t.v())) }
 int hs_fp_inv_gcd(int L, uint32_t* r, const uint32_t* a) { FOR_L(L, F<LL>::inv_gcd(r, a)) }

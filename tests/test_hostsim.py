@@ -109,7 +109,7 @@ def test_sim_pair_duo(kb):
     g, par, S, _ = setup(kb)
     v = g["pair"]
     A, Bp = g1s(par, v["a"]), g1s(par, v["b"])
-    wide = (C.c_uint64 * 4)()
+    wide = (C.c_uint64 * 8)()
     sim.lib().hs_wide_count(wide, 1)
     sim.lib().hs_mul_count(1)
     S.range_report()
@@ -120,8 +120,9 @@ def test_sim_pair_duo(kb):
     nmul = sim.lib().hs_mul_count(1)
     from bgn_b200 import workmodel
     live = sum(1 for x, y in zip(A, Bp) if x is not None and y is not None)
-    mm, mw, rd = workmodel.pair_duo_counts(par.p, par.n, par.l)
-    assert (nmul, wide[0], wide[1]) == (live * mm, live * mw, live * rd), (nmul, list(wide), live, mm, mw, rd)
+    mm, mw, rd, nsq = workmodel.pair_duo_counts(par.p, par.n, par.l, loop=0)  # the simulator's build: unrolled products
+    assert (nmul, wide[0], wide[1] - wide[4], wide[4]) == (live * mm, live * mw, live * rd, live * nsq), (
+        nmul, list(wide), live, mm, mw, rd, nsq)
     if kb < 512:
         assert S.pair_duo(Bp, A, np_=5) == S.pair(Bp, A)
         try:
@@ -253,14 +254,15 @@ def test_work_model_matches_executed_products(kb):
     ctypes = __import__("ctypes")
     lib.hs_mul_count.restype = ctypes.c_uint64
     lib.hs_mul_count(1)
-    wide = (ctypes.c_uint64 * 3)()
+    wide = (ctypes.c_uint64 * 8)()
     lib.hs_wide_count(wide, 1)
     S.miller(c1, v["d1"], c2, v["d2"], 1, v["d1"] + v["d2"], teams_per_block=1)
     fused = lib.hs_mul_count(1)  # multiply-and-reduce products (2L^2 + L each)
     lib.hs_wide_count(wide, 1)   # double-width multiplications (L^2) and separate reductions (L^2 + L)
     L = S.L
-    executed = fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L)
+    executed = fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[4] * (L * (L + 1) // 2)
     assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
+    assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"]) > 0
     assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
 
@@ -443,7 +445,7 @@ def test_sim_pair_fixed_lane_pair(kb):
         tabs["linesP"] = S.record_lines(S.P)
     v = g["make_l2"]
     pts = g1s(par, v["a"])
-    wide = (C.c_uint64 * 4)()
+    wide = (C.c_uint64 * 8)()
     sim.lib().hs_wide_count(wide, 1)
     sim.lib().hs_mul_count(1)
     S.range_report()
@@ -456,11 +458,46 @@ def test_sim_pair_fixed_lane_pair(kb):
     finite = sum(1 for pt in pts if pt is not None)
     if finite == len(pts):
         exp_dot, exp_mul = workmodel.miller_fixed_pair_counts(par.p, par.n, par.l)
-        assert (wide[3], nmul) == (exp_dot * len(pts), exp_mul * len(pts)), (wide[3], nmul, exp_dot, exp_mul)
+        assert (wide[3], nmul, wide[4]) == (exp_dot * len(pts), exp_mul * len(pts), 0), (list(wide), nmul)
     if kb < 512:
         pts = g1s(par, g["g1_add"]["out"])
         assert S.pair_fixed_pair(tabs["linesP"], pts) == [O.pairing(pt, S.P, par) for pt in pts]
         assert S.pair_fixed_pair(tabs["linesP"], pts) == S.pair_fixed(tabs["linesP"], pts, nt=3)
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_dedicated_squaring(kb):
+    """Fp::sqr (L (L + 1) / 2 products + one Montgomery reduction: cross products against the doubled
+    operand, squares leading the even chains) equals Fp::mul(a, a) LIMB FOR LIMB -- same Montgomery
+    quotient, same representative -- on random values, on limbs with their top bits set (the bit the
+    doubling carries from limb i into limb i + 1 must not enter row i), and on relaxed operands up to
+    64 p."""
+    import ctypes as C
+    import random
+    import numpy as np
+    g, par, S, _ = setup(kb)
+    rng = random.Random(kb + 5)
+    p, L = par.p, S.L
+    vals = [0, 1, p - 1, p - 2, (1 << (32 * L - 9)) - 1]
+    vals += [rng.randrange(p) for _ in range(200 if kb < 512 else 40)]
+    vals += [sum((0x80000000 | rng.getrandbits(31)) << (32 * j) for j in range(L)) % p for _ in range(50 if kb < 512 else 10)]
+    vals += [sum(0xFFFFFFFF << (32 * j) for j in range(L)) % p, sum(0x80000000 << (32 * j) for j in range(L)) % p]
+    a = S.soa(vals, mont=False)
+    relaxed = [v + k * p for v, k in zip(vals[:40], [rng.randrange(64) for _ in range(40)])]
+    b = np.zeros((len(relaxed), L), dtype=np.uint32)
+    for e, v in enumerate(relaxed):
+        for j in range(L):
+            b[e, j] = (v >> (32 * j)) & 0xFFFFFFFF
+    sim.lib().hs_track_array(sim.P32(b), C.c_size_t(len(relaxed)), L, C.c_double(64.0))
+    Rinv = pow(1 << (32 * L), -1, p)
+    for arr, src in ((a, vals), (b, relaxed)):
+        r1, r2 = np.zeros_like(arr), np.zeros_like(arr)
+        assert sim.lib().hs_fp_sqr(L, sim.P32(r1), sim.P32(r2), sim.P32(arr), C.c_size_t(len(src))) == 0
+        assert (r1 == r2).all(), "dedicated squaring and product differ"
+        got = [sum(int(r1[e, j]) << (32 * j) for j in range(L)) for e in range(len(src))]
+        assert all(gv % p == v * v * Rinv % p for gv, v in zip(got, src))
+    _, _, _, viol = S.range_report()
+    assert viol == 0
 
 
 @pytest.mark.parametrize("kb", SIM_KB)

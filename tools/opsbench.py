@@ -54,10 +54,10 @@ def main():
             if best is None or t < best:
                 best = t
                 kern = {k: eng.timing_get(k)[0] for k in
-                        ("k_encrypt", "k_normalize", "k_g1_add", "k_g1_mulvar", "k_gt_pow", "k_bsgs_lookup", "k_miller", "k_miller_fixed",
+                        ("k_encrypt", "k_normalize", "k_g1_add", "k_g1_mulvar", "k_gt_pow", "k_bsgs_lookup", "k_miller", "k_miller_fixed", "k_pair_duo", "k_miller_split",
                          "k_dec_lucas", "k_gt_blind", "k_g1_affadd", "k_g1_polyconv", "k_gt_polyconv", "k_gt_mul",
                          "k_g1_from_bytes", "k_g1_to_bytes", "k_fp2_from_bytes", "k_fp2_to_bytes")}
-        kern["k_miller"] -= kern["k_miller_fixed"]  # timing_get matches by prefix
+        kern["k_miller"] -= kern["k_miller_fixed"] + kern["k_miller_split"]  # timing_get matches by prefix
         return best, {k: v for k, v in kern.items() if v > 1e-9}
 
     def entry(name, units, unit_name, ms_call, kern, modmuls_per_unit=None, dominant=None):
@@ -76,7 +76,7 @@ def main():
     r = r.reshape(-1)
     out = torch.empty(cnt * EB, dtype=torch.uint8, device=dev)
     t, k = timed(lambda: eng.encrypt_batch(digits, r, out=out))
-    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_modmuls(n, SB, args.enc_window), "k_encrypt")
+    entry("encrypt", cnt, "coefficient encryptions", t, k, workmodel.encrypt_products(n, SB, args.enc_window, L) / ppm, "k_encrypt")
     res["ops"]["encrypt"]["window_bits"] = args.enc_window
     res["ops"]["encrypt"]["plaintexts_per_s"] = args.plaintexts / (t * 1e-3)
 
@@ -113,8 +113,11 @@ def main():
     ca = eng.encrypt_batch(av, rr.reshape(-1))
     cb = eng.encrypt_batch(bv, rr.flip(0).reshape(-1))
     t, k = timed(lambda: eng.pair_batch(ca, cb))
-    entry("pair_single", nd, "pairings (unshared, one team of 1)", t, k,
-          workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
+    if "k_pair_duo" in k:
+        entry("pair_single", nd, "pairings (two warps per 32 pairings)", t, k, workmodel.pair_duo_products(p, n, l) / ppm, "k_pair_duo")
+    else:
+        entry("pair_single", nd, "pairings (unshared, one team of 1)", t, k,
+              workmodel.miller_unit_products(p, n, l, 1, 1) / ppm, "k_miller")
     l2 = eng.pair_batch(ca, cb)
     # the same kernels on a batch that gives every scheduler two warps (2^17 pairings)
     rep = (1 << 17) // nd
@@ -145,7 +148,7 @@ def main():
     dl1 = eng.encrypt_batch(torch.randint(-1000, 1000, (nd,), generator=gen, device=dev, dtype=torch.int64),
                             rr.reshape(-1))
     t, k = timed(lambda: eng.decrypt_batch(dl1, False))
-    entry("decrypt_l1", nd, "decryptions of level-1 ciphertexts", t, k, workmodel.miller_fixed_products(p, n, l) / ppm,
+    entry("decrypt_l1", nd, "decryptions of level-1 ciphertexts", t, k, workmodel.miller_fixed_pair_products(p, n, l) / ppm,
           "k_miller_fixed")
     # ---- larger decrypt batch (the kernel's rate once every scheduler holds two warps)
     big = 1 << 18
@@ -163,8 +166,8 @@ def main():
     ob = torch.empty(nb * EB, dtype=torch.uint8, device=dev)
     src1 = out[: nb * EB] if nb <= cnt else out.repeat((nb + cnt - 1) // cnt)[: nb * EB]
     t, k = timed(lambda: eng.g1_blind_batch(src1, rb, out=ob))
-    entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k, workmodel.encrypt_modmuls(n, SB, args.enc_window, 0.0) + 11,
-          "k_encrypt")
+    entry("blind_l1", nb, "level-1 re-randomisations (+ r*Q)", t, k,
+          (workmodel.encrypt_products(n, SB, args.enc_window, L, 0.0) + workmodel.madd_products(L)) / ppm, "k_encrypt")
     l2b = l2.repeat(nb // nd)
     t, k = timed(lambda: eng.gt_blind_batch(l2b, rb, out=ob))
     entry("blind_l2", nb, "level-2 re-randomisations (* e(Q,Q)^r)", t, k, 3 * SB * 255.0 / 256.0, "k_gt_blind")
