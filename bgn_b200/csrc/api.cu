@@ -154,6 +154,8 @@ struct bgn_ctx {
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
   size_t pair_duo_cap = (size_t)-1;  // pairings one wave of k_pair_duo holds (occupancy query, cached)
+  int miller_wide = 0;         // teams per block of k_miller_wide (0 = the 8-warp k_miller); BGN_MILLER_WIDE
+  int miller_wide_min = 1;     // smallest batch that uses it
   int miller_split = -1;       // MultPoly below one wave on the split team kernel (teamsplit.cuh): -1 = by the time model, 0 = never, 1 = always (BGN_MILLER_SPLIT)
   int pair_duo_loop = -1;      // products' row loop of k_pair_duo: -1 = the key size's default, 0 / 1 / 2 / 4 (A/B knob)
   int pair_duo_pairs = 2;      // most warp pairs per block of k_pair_duo (measured: 2 beats 1 and 4 at 2^14 pairings)
@@ -552,6 +554,41 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
       GT_ = 128;
     }
     smem = c->A->miller_smem_bytes(groups * GT_) + 16;
+  }
+  // The wide team kernel (10 warps per SM: evaluation points read from the batch arrays, pairing.cuh:
+  // MillerTeam<L, true>) for batches of several waves: miller_wide = teams per block (A/B knob; 0 = off)
+  if (groups == 1 && !is_tail && !c->A->miller_fixed_threads() && c->miller_wide > 0 && c->Eo->miller_wide &&
+      count >= (size_t)c->miller_wide_min) {
+    int tpbw = std::min(c->miller_wide, 320 / TS);
+    int ntw = (tpbw * TS + 31) / 32 * 32;
+    size_t smw = c->Eo->miller_wide_smem_bytes(ntw) + 16;
+    if (tpbw > 0 && smw <= smem_max) {
+      MillerArgs a;
+      memset(&a, 0, sizeof(a));
+      a.Mx = M.x;
+      a.My = M.y;
+      a.Minf = M.inf;
+      a.NM = (int)M.N;
+      a.Ex = E.x;
+      a.Ey = E.y;
+      a.Einf = E.inf;
+      a.NE = (int)E.N;
+      a.e_bcast = e_bcast;
+      a.out_re = out.re;
+      a.out_im = out.im;
+      a.NOUT = (int)out.N;
+      a.dM = dM;
+      a.dE = dE;
+      a.out_slots = out_slots;
+      a.count = (int)count;
+      a.teams_per_group = tpbw;
+      a.group_threads = ntw;
+      Timer t(c, "k_miller_wide");
+      CK(c->Eo->miller_wide_set_smem(smw));
+      c->Eo->miller_wide(cfg(c, (count + tpbw - 1) / tpbw, ntw, smw), a);
+      t.done();
+      return;
+    }
   }
   // Sub-wave work -- a whole batch below one wave, or the remainder after the full waves -- goes to the
   // split kernel (two threads per output-slot pair: 0.6 of the dependent chain per Miller step) when it
@@ -1062,6 +1099,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* fp = getenv("BGN_FIXED_PAIR")) c->fixed_pair = atoi(fp);
     if (const char* pd = getenv("BGN_PAIR_DUO")) c->pair_duo = atoi(pd);
     if (const char* ms = getenv("BGN_MILLER_SPLIT")) c->miller_split = atoi(ms);
+    if (const char* mw = getenv("BGN_MILLER_WIDE")) c->miller_wide = atoi(mw);
     Big p0 = big_from_be(prm->p_be, prm->p_len, BGN_MAXL);
     int pbits = big_bits(p0);
     if (pbits < 40 || (p0[0] & 3) != 3) throw ArgErr{"p must be a prime = 3 (mod 4) of at least 40 bits"};
@@ -1258,6 +1296,10 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->fixed_pair = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo") {
     c->pair_duo = value < 0 ? -1 : (value != 0);
+  } else if (k == "miller_wide") {
+    c->miller_wide = (int)std::max<long>(0, value);
+  } else if (k == "miller_wide_min") {
+    c->miller_wide_min = (int)std::max<long>(1, value);
   } else if (k == "miller_split") {
     c->miller_split = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo_loop") {

@@ -39,11 +39,18 @@ struct MF {
       P::template mul_stream<ES>(r, a, bp);
   }
   BGN_DEV static void dbl(uint32_t (&r)[L], const uint32_t (&a)[L]) { P::addn(r, a, a); }
-  // r = a^2 where `mem` holds the same value as the register operand a.  With unrolled products
-  // (U == 0) this is the dedicated squaring (arith.cuh: Fp::sqr, 459 instead of 595 products at L = 17);
-  // the looped variants keep the product, whose code is a fifth the size -- they exist where code
-  // size is what matters (the 1024-bit field, the two-warp pairing).
-  static constexpr bool SQR = (U == 0);
+  // r = a^2 where `mem` holds the same value as the register operand a: the product, or (BGN_FUSED_SQR,
+  // unrolled products only) the dedicated squaring of arith.cuh -- 459 instead of 595 products at L = 17.
+  // Measured in k_miller (profiles/r02_bench_n1_v4.json against _v5): the 2^14-product step takes 596.7 ms
+  // with it and 596.9 ms without -- its 136 saved products per squaring are paid back in the zeroing,
+  // doubling and merging of its two double-width arrays and in shorter carry chains -- while the executed
+  // product count, the numerator of the roofline fraction, drops 1.7 %.  Not shipped in the fused
+  // routines; Encrypt's three-address code (field.cuh: F::sqr, +4.5 %) and the two-warp pairing
+  // (pairwarp.cuh, +4.7 %) do use it.
+#ifndef BGN_FUSED_SQR
+#define BGN_FUSED_SQR 0
+#endif
+  static constexpr bool SQR = (U == 0) && BGN_FUSED_SQR != 0;
   BGN_DEV static void sqrm(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* mem) {
     if (SQR)
       P::sqr(r, a);

@@ -20,9 +20,15 @@ cudaError_t miller_split_set_smem(size_t smem) {
   return cudaFuncSetAttribute(k_miller_split<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 void miller_split(LaunchCfg cfg, const MillerArgs& a) { k_miller_split<LL><<<CFG>>>(a); }
-const LOpsE ops = {LL, upload, miller_split_smem_bytes, miller_split_set_smem, miller_split};
+size_t miller_wide_smem_bytes(int nt) { return MillerTeam<LL, true>::smem_words(nt) * 4; }
+cudaError_t miller_wide_set_smem(size_t smem) {
+  return cudaFuncSetAttribute(k_miller_wide<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+void miller_wide(LaunchCfg cfg, const MillerArgs& a) { k_miller_wide<LL><<<CFG>>>(a); }
+const LOpsE ops = {LL, upload, miller_split_smem_bytes, miller_split_set_smem, miller_split,
+                   miller_wide_smem_bytes, miller_wide_set_smem, miller_wide};
 #else
-const LOpsE ops = {LL, upload, nullptr, nullptr, nullptr};
+const LOpsE ops = {LL, upload, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #endif
 }  // namespace
 #define BGN_CAT2(a, b) a##b

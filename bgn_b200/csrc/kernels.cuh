@@ -962,6 +962,15 @@ __global__ void __launch_bounds__(256, 1) k_miller(const __grid_constant__ Mille
   T.run([=] { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory"); });
 }
 
+// the team kernel with 10 instead of 12 shared-memory slots per thread (evaluation points read from the
+// batch arrays): 10 warps per SM instead of 8, one barrier group (pairing.cuh: MillerTeam<L, true>)
+template <int L>
+__global__ void __launch_bounds__(320) k_miller_wide(const __grid_constant__ MillerArgs a) {
+  extern __shared__ uint32_t smem_dyn[];
+  MillerTeam<L, true> T(a, smem_dyn, threadIdx.x, blockIdx.x, blockDim.x);
+  T.run([] { __syncthreads(); });
+}
+
 // the team kernel with two threads per output-slot pair (teamsplit.cuh): batches below one wave
 template <int L>
 __global__ void __launch_bounds__(384) k_miller_split(const __grid_constant__ MillerArgs a) {

@@ -76,6 +76,10 @@ struct LOpsE {
   size_t (*miller_split_smem_bytes)(int nt, int ncol);  // null above 17 limbs
   cudaError_t (*miller_split_set_smem)(size_t smem);
   void (*miller_split)(LaunchCfg, const MillerArgs&);
+  // the team kernel with 10 slots per thread, 10 warps per SM (k_miller_wide); null above 17 limbs
+  size_t (*miller_wide_smem_bytes)(int nt);
+  cudaError_t (*miller_wide_set_smem)(size_t smem);
+  void (*miller_wide)(LaunchCfg, const MillerArgs&);
 };
 
 struct LOpsB {

@@ -106,11 +106,16 @@ struct GT {
 
 enum { MOP_DBL = 0, MOP_ADD = 1, MOP_SUB = 2 };
 
-template <int L>
+// EG ("evaluation points in global memory", round 2): the two evaluation-point slots are not copied into
+// shared memory -- line_mul reads xB, yB straight from the batch arrays (34 cached loads per 2 669
+// products) -- so a thread's state is 10 slots instead of 12 and an SM holds 28 teams of 11 in 10 warps
+// where 12 slots allow 23 in 8 (k_miller_wide, kernels.cuh).  Unit-stride layout only.
+template <int L, bool EG = false>
 struct MillerTeam {
   typedef F<L> FF;
   typedef G<L> GG;
   static constexpr bool GP = BGN_MILLER_GP != 0;
+  static_assert(!(EG && GP), "the wide variant uses the unit-stride layout");
   static constexpr int NT = BGN_MILLER_NT;
   static constexpr int ES = GP ? NT : 1;          // element stride of every slot
   typedef MF<L, BGN_TEAM_LOOP_B, ES> M;      // phase B
@@ -119,7 +124,7 @@ struct MillerTeam {
   // the line it publishes, its evaluation point.  The loop's routines are fused (fused.cuh) and
   // keep their temporaries in registers.
   enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_EX = 10, S_EY = 11,
-         NSLOT = BGN_MILLER_NSLOT, NPRIV = BGN_MILLER_NPRIV };  // slots < NPRIV are thread-private
+         NSLOT = EG ? 10 : BGN_MILLER_NSLOT, NPRIV = BGN_MILLER_NPRIV };  // slots < NPRIV are thread-private
 
   const MillerArgs& a;
   uint32_t* smem;   // the block's slots (layout: slot()), then one flagsA and one flagsB byte per thread
@@ -202,7 +207,7 @@ struct MillerTeam {
     }
     bool einf = a.Einf[eidx(t)] != 0;
     flagsB()[tid] = einf ? 0 : 1;
-    if (!einf) {
+    if (!einf && !EG) {
       s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);
       s_in(slot(tid, S_EY), a.Ey + eidx(t) * L);
     }
@@ -239,12 +244,14 @@ struct MillerTeam {
         s = 1;
       }
       if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
+      const uint32_t* ex = EG ? a.Ex + eidx(k) * L : slot(base + k, S_EX);
+      const uint32_t* ey = EG ? a.Ey + eidx(k) * L : slot(base + k, S_EY);
 #if BGN_LINE_LAZY
       M::template line_mul_lazy<BGN_LINE_KARATSUBA>(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
-                       slot(base + i, S_BI), slot(base + k, S_EX), slot(base + k, S_EY));
+                       slot(base + i, S_BI), ex, ey);
 #else
       M::line_mul(slot(tid, S_F0 + 2 * s), slot(tid, S_F0 + 2 * s + 1), slot(base + i, S_CR), slot(base + i, S_AR),
-                  slot(base + i, S_BI), slot(base + k, S_EX), slot(base + k, S_EY));
+                  slot(base + i, S_BI), ex, ey);
 #endif
     }
   }

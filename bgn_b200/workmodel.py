@@ -20,10 +20,12 @@ def products_per_sqr(L: int) -> int:
     return L * (L + 1) // 2 + L * L + L
 
 
+FUSED_SQR = False  # fused.cuh BGN_FUSED_SQR: measured neutral in k_miller, not shipped
+
+
 def fused_sqr(L: int) -> bool:
-    """fused.cuh MF::SQR: the fused routines square with Fp::sqr where their products are unrolled (up to
-    17 limbs); the looped variants of the 1024-bit field keep the product"""
-    return L <= 17
+    """fused.cuh MF::SQR: whether the fused Miller routines square with Fp::sqr (an option, off: see there)"""
+    return FUSED_SQR and L <= 17
 
 
 def pick_limbs(p: int) -> int:
@@ -167,7 +169,7 @@ def pair_duo_counts(p: int, n: int, l: int, loop: int = None):
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     mm = D * (9 + 4) + (D - 1) * 2 + A * (11 + 3) + final_exp_modmuls(p, l, L, 1, 1) + 1  # + the inversion's check
-    nsq = (D * 6 + A * 3 if L <= 17 else 0) + (2 if loop == 0 else 0)
+    nsq = (D * 6 + A * 3 if L <= 17 else 0) + (2 if (loop == 0 and fused_sqr(L)) else 0)
     if line_lazy(L):
         return mm - nsq, 3 * (D + A), 2 * (D + A), nsq
     return mm - nsq + 3 * (D + A), 0, 0, nsq

@@ -49,14 +49,14 @@ struct LanePair {
   }
 };
 
-template <int L>
+template <int L, bool EG = false>
 void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
-  std::vector<uint32_t> smem(MillerTeam<L>::smem_words(nt) + 8);
-  std::vector<uint32_t> priv((size_t)nblocks * MillerTeam<L>::priv_words() + 8);
+  std::vector<uint32_t> smem(MillerTeam<L, EG>::smem_words(nt) + 8);
+  std::vector<uint32_t> priv((size_t)nblocks * MillerTeam<L, EG>::priv_words() + 8);
   MillerArgs a = a0;
   a.priv = priv.data();
   for (int b = 0; b < nblocks; b++) {
-    std::vector<MillerTeam<L>> T;
+    std::vector<MillerTeam<L, EG>> T;
     T.reserve(nt);
     for (int tid = 0; tid < nt; tid++) T.emplace_back(a, smem.data(), tid, b, nt);
     for (auto& t : T) t.init();
@@ -167,6 +167,11 @@ void hs_track_array(const uint32_t* a, size_t count, int L, double bound) {
   for (size_t e = 0; e < count; e++) bgnsim::setb(a + e * L, bound);
 }
 int hs_miller(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller<LL>(*a, nblocks, nt)) }
+#if !BGN_MILLER_GP
+int hs_miller_wide(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller<LL, true>(*a, nblocks, nt)) }
+#else
+int hs_miller_wide(int, const MillerArgs*, int, int) { return -1; }
+#endif
 int hs_miller_split(int L, const MillerArgs* a, int nblocks, int nt) { FOR_L(L, sim_miller_split<LL>(*a, nblocks, nt)) }
 int hs_encrypt(int L, const EncArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) encrypt_body<LL>(*a, e)) }
 int hs_normalize(int L, const NormArgs* a) { FOR_L(L, for (size_t g = 0; g < (size_t)a->G; g++) normalize_body<LL>(*a, g)) }

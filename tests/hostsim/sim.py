@@ -252,7 +252,7 @@ class Sim:
         return x, y, inf
 
     # ---- kernels
-    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2):
+    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2, wide=False):
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
         nout = count * out_slots
@@ -264,7 +264,7 @@ class Sim:
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
         nblocks = (count + groups * teams_per_block - 1) // (groups * teams_per_block)
-        assert lib().hs_miller(self.L, C.byref(a), nblocks, nt) == 0
+        assert (lib().hs_miller_wide if wide else lib().hs_miller)(self.L, C.byref(a), nblocks, nt) == 0
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
 
     def miller_split(self, M, dM, E, dE, count, out_slots, teams_per_block=2):
@@ -327,10 +327,10 @@ class Sim:
         assert lib().hs_pair_duo(self.L, C.byref(a), np_) == 0
         return list(zip(self.unsoa(ore, count), self.unsoa(oim, count)))
 
-    def multpoly(self, c1, d1, c2, d2, count):
+    def multpoly(self, c1, d1, c2, d2, count, wide=False):
         if d1 <= d2:
-            return self.miller(c1, d1, c2, d2, count, d1 + d2)
-        return self.miller(c2, d2, c1, d1, count, d1 + d2)
+            return self.miller(c1, d1, c2, d2, count, d1 + d2, wide=wide)
+        return self.miller(c2, d2, c1, d1, count, d1 + d2, wide=wide)
 
     def pair(self, A, Bp):
         return self.miller(A, 1, Bp, 1, len(A), 1, teams_per_block=3)

@@ -358,6 +358,35 @@ def test_multpoly_split_team_kernel_equals_team_kernel(kb, count, d1, d2):
     e.close()
 
 
+@pytest.mark.parametrize("kb,count,d1,d2,tpb", [(512, 70, 11, 11, 28), (256, 90, 5, 4, 7), (128, 64, 1, 1, 20), (64, 500, 3, 3, 50)])
+def test_multpoly_wide_team_kernel_equals_team_kernel(kb, count, d1, d2, tpb):
+    """MultPoly on the wide team kernel (k_miller_wide: evaluation points read from the batch arrays, 10
+    shared-memory slots per thread, up to 10 warps per block) gives the team kernel's bytes, with O
+    coefficients on both sides."""
+    from bgn_b200 import Engine
+    g = load_golden(kb)
+    e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    rng = random.Random(kb + count + 1)
+    n = int(g["n"], 16)
+    eb = e.elem_bytes
+    x1 = np.array([rng.randrange(-1, 2) for _ in range(count * d1)], dtype=np.int64)
+    x2 = np.array([rng.randrange(-1, 2) for _ in range(count * d2)], dtype=np.int64)
+    c1 = e.encrypt_batch(x1, e.scalars_be([rng.randrange(n) for _ in range(count * d1)]))
+    c2 = e.encrypt_batch(x2, e.scalars_be([rng.randrange(n) for _ in range(count * d2)]))
+    c1[0:eb] = 0
+    c2[(count * d2 - 1) * eb:] = 0
+    e.timing_enable(True)
+    e.set_option("miller_split", 0)
+    e.set_option("pair_duo", 0)
+    ref = e.multpoly_batch(c1, d1, c2, d2, count).tobytes()
+    e.set_option("miller_wide", tpb)
+    e.timing_reset()
+    got = e.multpoly_batch(c1, d1, c2, d2, count).tobytes()
+    assert e.timing_get("k_miller_wide")[1] == 1, "the wide kernel did not run"
+    assert got == ref
+    e.close()
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)

@@ -147,6 +147,25 @@ def test_sim_multpoly(kb):
 
 
 @pytest.mark.parametrize("kb", SIM_KB)
+def test_sim_multpoly_wide(kb):
+    """k_miller_wide (MillerTeam<L, true>: evaluation points read from the batch arrays, 10 shared-memory
+    slots per thread) against the golden MultPoly vectors, several units per block, and the broadcast
+    evaluation side of makeL2."""
+    g, par, S, _ = setup(kb)
+    v = g["multpoly"]
+    c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+    S.range_report()
+    assert S.multpoly(c1, v["d1"], c2, v["d2"], 1, wide=True) == gts(par, v["out"])
+    _, _, unknown, viol = S.range_report()
+    assert viol == 0 and unknown == 0
+    if kb < 512:
+        assert S.multpoly(c2 * 3, v["d2"], c1 * 3, v["d1"], 3, wide=True) == gts(par, v["out"]) * 3
+        m = g["make_l2"]
+        a = g1s(par, m["a"])
+        assert S.miller(a, 1, [S.P], 1, len(a), 1, e_bcast=True, wide=True) == gts(par, m["out"])
+
+
+@pytest.mark.parametrize("kb", SIM_KB)
 def test_sim_multpoly_split(kb):
     """k_miller_split (teamsplit.cuh: two threads per output-slot pair, partial accumulators multiplied
     before the final exponentiation, shared memory laid out per column) against the golden MultPoly
@@ -262,7 +281,7 @@ def test_work_model_matches_executed_products(kb):
     L = S.L
     executed = fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[4] * (L * (L + 1) // 2)
     assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
-    assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"]) > 0
+    assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"])
     assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
 
@@ -282,6 +301,33 @@ def test_range_tracker_proves_miller_ranges(kb):
     assert unknown == 0 and violations == 0
     assert 16.0 < worst < 64.0  # the chord slope 2 (S2 - Y + 16p) is the largest value
     assert sim.lib().hs_selftest_violation() == 1  # and the checker does fire
+
+
+def test_sim_fused_routines_with_dedicated_squaring():
+    """The option BGN_FUSED_SQR (dedicated squarings inside dbl_line / madd_line / fe_prepare; measured
+    neutral in k_miller and not shipped) keeps bytes, ranges and its work model."""
+    import ctypes as C
+    from bgn_b200 import workmodel
+    try:
+        sim.use_variant(None, ("-DBGN_FUSED_SQR=1",), "_fsqr")
+        workmodel.FUSED_SQR = True
+        for kb in (64, 512):
+            g, par, S, _ = setup(kb)
+            v = g["multpoly"]
+            c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
+            wide = (C.c_uint64 * 8)()
+            sim.lib().hs_wide_count(wide, 1)
+            assert S.multpoly(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+            sim.lib().hs_wide_count(wide, 1)
+            live1 = sum(1 for x in c1 if x is not None)
+            if live1 == len(c1) and all(x is not None for x in c2):
+                assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, min(v["d1"], v["d2"]), max(v["d1"], v["d2"]))
+            assert wide[4] > 0
+            _, _, unknown, violations = S.range_report()
+            assert unknown == 0 and violations == 0
+    finally:
+        workmodel.FUSED_SQR = False
+        sim.use_variant(None)
 
 
 @pytest.mark.parametrize("loop", (1, 2, 4))
