@@ -500,6 +500,44 @@ struct Fp {
     BGN_UNROLL
     for (int j = 0; j < L; j++) T[L + j] = hi[j];
   }
+  // Two independent double-width products with their rows interleaved in program order (ILP 2): the carry
+  // chains of one fill the dependency gaps of the other (A/B candidate for line_mul_lazy; fused.cuh)
+  template <int ES = 1>
+  BGN_DEV static void mulw2(uint32_t (&T0)[2 * L], const uint32_t (&a0)[L], const uint32_t* b0, uint32_t (&T1)[2 * L],
+                            const uint32_t (&a1)[L], const uint32_t* b1) {
+    uint32_t X0[W], Y0[W], X1[W], Y1[W];
+#ifdef BGN_HOSTSIM
+    {
+      double A = BGN_GETB(a0), B = BGN_GETB(b0), C = BGN_GETB(a1), D = BGN_GETB(b1);
+      BGN_CHECK(A <= bgnsim::headroom && B <= bgnsim::headroom && C <= bgnsim::headroom && D <= bgnsim::headroom,
+                "wide product operand too large");
+      bgnsim::setw(T0, A * B, 0.0);
+      bgnsim::setw(T1, C * D, 0.0);
+      bgnsim::nmulw += 2;
+    }
+#endif
+    T0[0] = mrow<true>(X0, Y0, a0, b0[0]);
+    T1[0] = mrow<true>(X1, Y1, a1, b1[0]);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      T0[i] = mrow<false>(Y0, X0, a0, b0[i * ES]);
+      T1[i] = mrow<false>(Y1, X1, a1, b1[i * ES]);
+      T0[i + 1] = mrow<false>(X0, Y0, a0, b0[(i + 1) * ES]);
+      T1[i + 1] = mrow<false>(X1, Y1, a1, b1[(i + 1) * ES]);
+    }
+    uint32_t h0[L], h1[L];
+    if ((L & 1) == 0) {
+      T0[L - 1] = mrow<false>(Y0, X0, a0, b0[(L - 1) * ES]);
+      T1[L - 1] = mrow<false>(Y1, X1, a1, b1[(L - 1) * ES]);
+      merge(h0, X0, Y0);
+      merge(h1, X1, Y1);
+    } else {
+      merge(h0, Y0, X0);
+      merge(h1, Y1, X1);
+    }
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) T0[L + j] = h0[j], T1[L + j] = h1[j];
+  }
   // plain integer product T[2L] = a * b of two L-limb numbers held in registers (no field
   // semantics, no range bookkeeping): the building block of the Karatsuba product below
   BGN_DEV static void mulw_raw(uint32_t (&T)[2 * L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {

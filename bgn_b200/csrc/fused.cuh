@@ -136,6 +136,33 @@ struct MF {
     st<L, ES>(fim, b);
   }
 
+  // A/B candidate (tools/primbench.py mode 83): line_mul_lazy with the two independent double-width
+  // products f0 l0 and f1 l1 interleaved row by row (Fp::mulw2), and the two evaluation products likewise
+  BGN_DEVNI static void line_mul_lazy_il(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
+                                         const uint32_t* xB, const uint32_t* yB) {
+    R a, b, c, l0, l1;
+    uint32_t T0[2 * L], T1[2 * L], S[2 * L];
+    ld<L, ES>(a, xB);
+    ld<L, ES>(b, yB);
+    P::mul_pair(l0, a, aR, l1, b, bI);  // aR xB | bI yB
+    ld<L, ES>(a, cR);
+    P::addn(l0, l0, a);       // l0 = cR + aR xB
+    P::template mulw2<ES>(T0, l0, fre, T1, l1, fim);   // f0 l0 | f1 l1
+    P::addw(S, T0, T1);
+    P::subw_k(T0, T0, T1, c_fc.p, 1);
+    P::redc(a, T0);
+    ld<L, ES>(b, fre);
+    ld<L, ES>(c, fim);
+    P::addn(b, b, c);
+    st<L, ES>(fre, b);            // f0 + f1
+    P::addn(l0, l0, l1);
+    P::template mulw<ES>(T1, l0, fre);   // (f0 + f1)(l0 + l1)
+    P::subw(T1, T1, S);
+    st<L, ES>(fre, a);
+    P::redc(b, T1);
+    st<L, ES>(fim, b);
+  }
+
   // f <- f^2 = (f0 + f1)(f0 - f1) + 2 f0 f1 i, 2 products.  in: < 8p.  out: < 4p.
   BGN_DEVNI static void sqr2(E fre, E fim) {
     R a, b, s, d, m;

@@ -1113,6 +1113,8 @@ __global__ void __launch_bounds__(256, 1) k_prim_bench(uint32_t* io, size_t N, i
       MF<L, 0>::template line_mul_lazy<1>(slot(0), slot(1), slot(7), slot(8), slot(9), slot(4), slot(5));
     } else if (mode == 82) {  // + Karatsuba on all five multiplications
       MF<L, 0>::template line_mul_lazy<2>(slot(0), slot(1), slot(7), slot(8), slot(9), slot(4), slot(5));
+    } else if (mode == 83) {  // lazy reduction with the independent products interleaved (ILP 2)
+      MF<L, 0>::line_mul_lazy_il(slot(0), slot(1), slot(7), slot(8), slot(9), slot(4), slot(5));
 #endif
     } else {
       G<L>::dbl_line(slot(4), slot(5), slot(6), slot(7), slot(8), slot(9), slot(10), slot(11), slot(12));

@@ -12,7 +12,7 @@ peak = 148 * 8 * 256 * ipt / (ms * 1e-3)
 MM = {1: 1, 10: 1, 11: 5, 12: 2, 13: 12, 20: 1, 22: 2}
 for base in (30, 40, 50, 60, 70):
     MM.update({base: 5, base + 2: 2, base + 3: 12, base + 4: 13})
-MM[80] = MM[81] = MM[82] = 5  # lazy line_mul: counted as 5 modmuls = one line_mul, so frac compares line_mul rates
+MM[80] = MM[81] = MM[82] = MM[83] = 5  # lazy line_mul: counted as 5 modmuls = one line_mul, so frac compares line_mul rates
 MODES = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 20, 11, 70, 50, 60, 40, 73, 53, 63, 43, 72, 42, 74, 44]
 for mode in MODES:
     for threads in (128, 256):
