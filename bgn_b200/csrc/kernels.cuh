@@ -1016,20 +1016,29 @@ __global__ void __launch_bounds__(256) k_pair_duo(const __grid_constant__ PairDu
     __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
   };
-  if ((warp & 1) == 0) {
+  // Iteration s: the X warps compute step s while the F warps consume step s - 1; then ONE barrier, at
+  // one call site for both roles (every thread executes the same sequence of barrier instructions:
+  // compute-sanitizer synccheck is clean).  Step s publishes into buffer s & 1, which the F warps
+  // finished reading before the previous barrier.
+  const bool is_x = (warp & 1) == 0;
+  if (is_x)
     T.x_init();
-    T_::for_steps([&](int s, int op) {
-      T.x_step(op, s & 1);
-      sync();
-    });
-  } else {
+  else
     T.f_init();
-    T_::for_steps([&](int s, int op) {
-      sync();
-      T.f_step(op, s & 1, s == 0);
-    });
-    T.f_finish();
-  }
+  int prev_op = -1, s = 0;
+  auto iter = [&](int op_x) {
+    if (is_x) {
+      if (op_x >= 0) T.x_step(op_x, s & 1);
+    } else if (prev_op >= 0) {
+      T.f_step(prev_op, (s - 1) & 1, s == 1);
+    }
+    sync();
+    prev_op = op_x;
+    s++;
+  };
+  T_::for_steps([&](int, int op) { iter(op); });
+  iter(-1);
+  if (!is_x) T.f_finish();
 }
 
 template <int L>
