@@ -181,13 +181,76 @@ def make(kb: int, small: bool) -> dict:
         out["evalpoly_" + name] = {"d": dd, "count": pcount, "base": pk.poly_base,
                                    "in": [enc_el(c) for ct in cts for c in ct.coefficients],
                                    "out": [enc_el(O.eval_poly(pk, ct)) for ct in cts]}
+    if not small:
+        out["nondet_poly"] = nondet_poly_section(pk, kb)
     return out
 
 
+def nondet_poly_section(pk, kb: int) -> dict:
+    """Round 2: the polynomial operations on a Deterministic=false key.  Every newCryptoRandom(pk.N) draw
+    of the reference's control flow (poly.go:45-55, 97-118, 140-152, 191-204 -> bgn.go:260-269, 279-288,
+    302-311, 421-432, 466-474, 488-495) is taken from the recorded stream `draws`, in sequential program
+    order; the fixture records the stream, the inputs and each operation's output bytes and draw count."""
+    par, p, n = pk.params, pk.params.p, pk.params.n
+    nd = O.PublicKey(par, pk.P, pk.Q, pk.msg_space, deterministic=False, poly_base=pk.poly_base,
+                     fp_scale_base=pk.fp_scale_base, fp_precision=pk.fp_precision)
+    rng = random.Random(SEEDS[kb] ^ 0xD3A5)
+    g1b = lambda P: hx(O.g1_to_bytes(P, par))  # noqa: E731
+
+    def enc(coeffs):
+        cs = []
+        for x in coeffs:
+            c = O.encrypt_with_randomness(nd, abs(x), rng.randrange(n)).C
+            cs.append(O.Ciphertext(O.g1_neg(c, p) if x < 0 else c, False))
+        return O.PolyCiphertext(cs, len(coeffs), 0, False)
+
+    a, b = enc([1, -1, 1]), enc([0, 1])
+    draws = [rng.randrange(n) for _ in range(64)]
+    ops = {}
+
+    def run(name, fn):
+        it = iter(draws)
+        used = [0]
+
+        def src():
+            used[0] += 1
+            return next(it)
+
+        nd.rand_source = src
+        res = fn()
+        nd.rand_source = None
+        if isinstance(res, O.Ciphertext):
+            ops[name] = {"draws_used": used[0], "L2": res.L2, "out": [hx(O.ct_bytes(nd, res))]}
+        else:
+            ops[name] = {"draws_used": used[0], "L2": res.L2, "degree": res.degree, "scale_factor": res.scale_factor,
+                         "out": [hx(O.ct_bytes(nd, c)) for c in res.coefficients]}
+        return res
+
+    m = run("mult_poly", lambda: O.mult_poly(nd, a, b))
+    run("add_poly", lambda: O.add_poly(nd, a, b))
+    run("sub_poly", lambda: O.sub_poly(nd, a, b))
+    run("neg_poly", lambda: O.neg_poly(nd, a))
+    run("neg_poly_l2", lambda: O.neg_poly(nd, m))
+    run("mult_const_poly_neg2", lambda: O.mult_const_poly(nd, a, -2.0))
+    run("make_poly_l2", lambda: O.make_poly_l2(nd, b))
+    run("add_poly_mixed_levels", lambda: O.add_poly(nd, m, b))
+    run("eval_poly", lambda: O.eval_poly(nd, a))
+    return {"a": [g1b(c.C) for c in a.coefficients], "b": [g1b(c.C) for c in b.coefficients],
+            "draws": [hex(x) for x in draws], "ops": ops}
+
+
 if __name__ == "__main__":
+    only_new = "--only-new" in sys.argv  # add the sections an existing fixture lacks, keep the rest byte for byte
     for kb in (64, 128, 256, 512, 1024):
-        d = make(kb, small=(kb == 1024))
         path = os.path.join(HERE, "kb%d.json" % kb)
+        if only_new and os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f)
+            if "nondet_poly" not in d and kb != 1024:
+                pk, _ = O.keygen(kb, MSG_SPACE[kb], seed=SEEDS[kb])
+                d["nondet_poly"] = nondet_poly_section(pk, kb)
+        else:
+            d = make(kb, small=(kb == 1024))
         with open(path, "w") as f:
             json.dump(d, f, indent=1)
         print("wrote", path, os.path.getsize(path), "bytes")

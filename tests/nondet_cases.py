@@ -143,3 +143,49 @@ def run_poly_cases(pk0: PublicKey, opk: O.PublicKey, sk=None, osk=None, values=(
             assert sk.DecryptPoly(x, pk).Coefficients == sk.DecryptPoly(y, pk).Coefficients
     x, y = pk.MultPolyBatch(bi, bt), pk.MultPolyBatch(bi, bt)
     assert raw(x.data) != raw(y.data)
+
+
+def run_golden_section(pk0: PublicKey, g: dict):
+    """The mirror on a Deterministic=false key, replaying the fixture's recorded randomness stream, against the
+    committed bytes of tests/golden/kb*.json["nondet_poly"] (made by the oracle's literal poly.go control
+    flow, tests/golden/make_golden.py) -- including how many draws every operation consumes."""
+    from bgn_b200.bgn import Ciphertext, PolyCiphertext
+    v = g["nondet_poly"]
+    pk = PublicKey(pk0.engine.p, pk0.N, pk0.engine.l, pk0.P, pk0.Q, pk0.MsgSpace, Deterministic=False, engine=pk0.engine)
+    draws = [int(x, 16) for x in v["draws"]]
+
+    def poly(hexes, l2=False):
+        return PolyCiphertext([Ciphertext(bytes.fromhex(h), l2) for h in hexes], len(hexes), 0, l2)
+
+    a, b = poly(v["a"]), poly(v["b"])
+    res = {}
+
+    def check(name, fn):
+        used = [0]
+        it = iter(draws)
+
+        def src():
+            used[0] += 1
+            return next(it)
+
+        pk.rand_source = src
+        out = fn()
+        exp = v["ops"][name]
+        assert used[0] == exp["draws_used"], (name, used[0], exp["draws_used"])
+        if isinstance(out, Ciphertext):
+            assert (out.C.hex(), out.L2) == (exp["out"][0], exp["L2"]), name
+        else:
+            assert (out.Degree, out.ScaleFactor, out.L2) == (exp["degree"], exp["scale_factor"], exp["L2"]), name
+            assert [c.C.hex() for c in out.Coefficients] == exp["out"], name
+        res[name] = out
+        return out
+
+    m = check("mult_poly", lambda: pk.MultPoly(a, b))
+    check("add_poly", lambda: pk.AddPoly(a, b))
+    check("sub_poly", lambda: pk.SubPoly(a, b))
+    check("neg_poly", lambda: pk.NegPoly(a))
+    check("neg_poly_l2", lambda: pk.NegPoly(m))
+    check("mult_const_poly_neg2", lambda: pk.MultConstPoly(a, -2.0))
+    check("make_poly_l2", lambda: pk.MakePolyL2(b))
+    check("add_poly_mixed_levels", lambda: pk.AddPoly(m, b))
+    check("eval_poly", lambda: pk.EvalPoly(a))

@@ -594,6 +594,18 @@ def test_mirror_api_nondeterministic_poly_ops(kb):
     pk.engine.close()
 
 
+@pytest.mark.parametrize("kb", [64, 128, 256, 512])
+def test_mirror_api_nondeterministic_poly_golden(kb):
+    """the committed non-deterministic polynomial fixtures (tests/golden/kb*.json["nondet_poly"]: oracle's
+    literal poly.go control flow on a recorded randomness stream) through the mirror on the CUDA engine"""
+    from bgn_b200 import PublicKey
+    from nondet_cases import run_golden_section
+    g = load_golden(kb)
+    pk = PublicKey.FromPBCParams(g["pbc_params"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), g["msg_space"])
+    run_golden_section(pk, g)
+    pk.engine.close()
+
+
 def test_mirror_wire_roundtrip():
     """bgn_test.go:37-85 (TestMarshalUnmarshal*): ciphertext -> gob envelope -> ciphertext keeps the
     element, level, Degree and ScaleFactor, on both levels; malformed element bytes follow

@@ -149,6 +149,18 @@ def test_nondeterministic_poly_ops_match_oracle(keys):
     run_poly_cases(pk, opk, sk, osk)
 
 
+@pytest.mark.parametrize("kb", [64, 128])
+def test_nondeterministic_poly_ops_match_golden(kb):
+    """the committed non-deterministic fixtures (tests/golden/kb*.json["nondet_poly"]) through the mirror on
+    the oracle-backed stand-in engine"""
+    from nondet_cases import run_golden_section
+    g = load_golden(kb)
+    p, n, l = int(g["p"], 16), int(g["n"], 16), g["l"]
+    P, Q = bytes.fromhex(g["P"]), bytes.fromhex(g["Q"])
+    pk = PublicKey(p, n, l, P, Q, g["msg_space"], engine=FakeEngine(p, n, l, P, Q))
+    run_golden_section(pk, g)
+
+
 def test_secret_key_mismatch_is_an_error(keys):
     pk, sk, _, _ = keys
     with pytest.raises(ValueError, match="not the one installed"):

@@ -198,3 +198,23 @@ def test_work_model_formula():
     par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
     m = O.canonical_modmuls_per_pairing(par)
     assert 15000 < m < 18000 and O.products_per_modmul(17) == 595
+
+
+@pytest.mark.parametrize("kb", [64, 128])
+def test_nondet_poly_golden_section_is_reproducible(kb):
+    """the oracle's literal poly.go control flow on the recorded randomness stream reproduces the committed
+    non-deterministic fixtures (pins the oracle, and the draw order, against accidental change)"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    from conftest import load_golden
+    g = load_golden(kb)
+    pk, _ = O.keygen(kb, mg.MSG_SPACE[kb], seed=mg.SEEDS[kb])
+    assert mg.nondet_poly_section(pk, kb) == g["nondet_poly"]
+    ops = g["nondet_poly"]["ops"]
+    # MultPoly 3 x 2: two draws per coefficient pairing; its unused top slot is the GT identity
+    assert ops["mult_poly"]["draws_used"] == 2 * 3 * 2 and ops["add_poly"]["draws_used"] == 2 and ops["neg_poly"]["draws_used"] == 3
+    cb = g["coord_bytes"]
+    assert ops["mult_poly"]["out"][-1] == (b"\x00" * (cb - 1) + b"\x01" + b"\x00" * cb).hex()
