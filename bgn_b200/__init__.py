@@ -5,7 +5,7 @@ operation runs in hand-written sm_100a CUDA behind the C-ABI of
 include/bgn_b200.h (bgn_b200/libbgn_b200.so).  No CPU fallback exists: using a
 compute entry point without the built CUDA library raises.
 """
-from .engine import BgnError, DeviceBatch, Engine, bench_imad_peak  # noqa: F401
+from .engine import BgnError, DeviceBatch, Engine, EngineGroup, bench_imad_peak  # noqa: F401
 from .bgn import (Ciphertext, DLError, PolyCiphertext, PolyCiphertextBatch, PublicKey, SecretKey)  # noqa: F401
 from .gadgets import DecryptionProof, NewDecryptionProof, ProofOfPlaintextKnowledge  # noqa: F401
 from .keygen import NewKeyGen  # noqa: F401

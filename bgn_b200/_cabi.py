@@ -64,6 +64,18 @@ SIGNATURES = {
                                  C.POINTER(C.c_void_p)]),
     "bgn_l2_sum_reduce_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "bgn_decrypt_h": (C.c_int, [C.c_void_p, C.c_void_p, u8p, u8p]),
+    "bgn_group_create": (C.c_int, [C.POINTER(bgn_params), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "bgn_group_destroy": (None, [C.c_void_p]),
+    "bgn_group_size": (C.c_int, [C.c_void_p]),
+    "bgn_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "bgn_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "bgn_group_set_secret": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32]),
+    "bgn_group_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
+    "bgn_group_encrypt_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),
+    "bgn_group_g1_add_batch": (C.c_int, [C.c_void_p, u8p, u8p, C.c_size_t, u8p]),
+    "bgn_group_multpoly_batch": (C.c_int, [C.c_void_p, u8p, C.c_size_t, u8p, C.c_size_t, C.c_size_t, u8p]),
+    "bgn_group_decrypt_batch": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_size_t, u8p, u8p]),
+    "bgn_group_inner_product": (C.c_int, [C.c_void_p, u8p, C.c_size_t, u8p, C.c_size_t, C.c_size_t, u8p]),
     "bgn_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "bgn_timing_reset": (C.c_int, [C.c_void_p]),
     "bgn_timing_get": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -2353,6 +2353,168 @@ int bgn_decrypt_h(bgn_ctx* c, const bgn_buf* in, int64_t* out, uint8_t* status) 
   });
 }
 
+// ---------------------------------------------------------------- several GPUs behind one handle
+// SURVEY.md 8(b) proposed bgn_ctx_create(params, ndev, devs): "multi-GPU is driven inside one call by
+// per-device host threads".  A bgn_group is that: one context per listed device, and batch entry points
+// that cut the batch into contiguous shards (the reference's independent units, poly.go:15, 37, 140-141),
+// run every shard on its device from its own host thread, and -- for the one operation with a cross-unit
+// dependency, the L2 sum behind an inner product -- fold the per-device partial products on device 0.
+// Buffers are HOST pointers (a device pointer belongs to one GPU).
+}  // extern "C"
+
+#include <thread>
+
+struct bgn_group {
+  std::vector<bgn_ctx*> ctx;
+  std::string err;
+};
+
+namespace {
+// shard [lo, hi) of `count` units for member g of n: sizes differ by at most one
+void group_shard(size_t count, size_t g, size_t n, size_t* lo, size_t* hi) {
+  size_t base = count / n, rem = count % n;
+  *lo = g * base + std::min(g, rem);
+  *hi = *lo + base + (g < rem ? 1 : 0);
+}
+// run fn(g, ctx) on every member from its own thread; the first failing status wins
+template <typename Fn>
+int group_run(bgn_group* grp, Fn fn) {
+  if (!grp || grp->ctx.empty()) return BGN_E_BADARG;
+  const size_t n = grp->ctx.size();
+  std::vector<int> st(n, BGN_OK);
+  try {
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (size_t g = 1; g < n; g++) th.emplace_back([&, g] { st[g] = fn(g, grp->ctx[g]); });
+    st[0] = fn(0, grp->ctx[0]);
+    for (auto& t : th) t.join();
+  } catch (...) {
+    grp->err = "could not start the per-device host threads";
+    return BGN_E_NOMEM;
+  }
+  for (size_t g = 0; g < n; g++)
+    if (st[g] != BGN_OK) {
+      grp->err = "device " + std::to_string(grp->ctx[g]->device) + ": " + grp->ctx[g]->err;
+      return st[g];
+    }
+  return BGN_OK;
+}
+}  // namespace
+
+extern "C" {
+int bgn_group_create(const bgn_params* prm, int ndev, const int* devs, bgn_group** out) {
+  g_last_error.clear();
+  if (!out || ndev < 1 || ndev > kMaxDevices || !devs) {
+    g_last_error = "bgn_group_create: bad argument";
+    return BGN_E_BADARG;
+  }
+  *out = nullptr;
+  bgn_group* grp = nullptr;
+  try {
+    grp = new bgn_group();
+  } catch (...) {
+    return BGN_E_NOMEM;
+  }
+  // contexts are built one after the other: table construction is seconds at most, and the per-thread
+  // error string of a failed bgn_ctx_create stays readable on this thread
+  for (int i = 0; i < ndev; i++) {
+    bgn_ctx* c = nullptr;
+    int st = bgn_ctx_create(prm, devs[i], &c);
+    if (st != BGN_OK) {
+      for (bgn_ctx* d : grp->ctx) bgn_ctx_destroy(d);
+      delete grp;
+      return st;
+    }
+    try {
+      grp->ctx.push_back(c);
+    } catch (...) {
+      bgn_ctx_destroy(c);
+      for (bgn_ctx* d : grp->ctx) bgn_ctx_destroy(d);
+      delete grp;
+      return BGN_E_NOMEM;
+    }
+  }
+  *out = grp;
+  return BGN_OK;
+}
+void bgn_group_destroy(bgn_group* grp) {
+  if (!grp) return;
+  for (bgn_ctx* c : grp->ctx) bgn_ctx_destroy(c);
+  delete grp;
+}
+int bgn_group_size(const bgn_group* grp) { return grp ? (int)grp->ctx.size() : 0; }
+bgn_ctx* bgn_group_ctx(bgn_group* grp, int i) {
+  return (grp && i >= 0 && (size_t)i < grp->ctx.size()) ? grp->ctx[(size_t)i] : nullptr;
+}
+const char* bgn_group_last_error(const bgn_group* grp) { return grp ? grp->err.c_str() : g_last_error.c_str(); }
+
+int bgn_group_set_secret(bgn_group* grp, const uint8_t* q1_be, size_t q1_len, uint64_t msg_space, uint32_t baby_steps) {
+  return group_run(grp, [&](size_t, bgn_ctx* c) { return bgn_ctx_set_secret(c, q1_be, q1_len, msg_space, baby_steps); });
+}
+int bgn_group_set_option(bgn_group* grp, const char* name, long value) {
+  return group_run(grp, [&](size_t, bgn_ctx* c) { return bgn_ctx_set_option(c, name, value); });
+}
+
+int bgn_group_encrypt_batch(bgn_group* grp, const int64_t* x, const uint8_t* r_be, size_t count, uint8_t* out) {
+  return group_run(grp, [&](size_t g, bgn_ctx* c) {
+    size_t lo, hi;
+    group_shard(count, g, grp->ctx.size(), &lo, &hi);
+    return bgn_encrypt_batch(c, x + lo, r_be ? r_be + lo * c->nbytes : nullptr, hi - lo, out + lo * 2 * c->B);
+  });
+}
+int bgn_group_g1_add_batch(bgn_group* grp, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out) {
+  return group_run(grp, [&](size_t g, bgn_ctx* c) {
+    size_t lo, hi;
+    group_shard(count, g, grp->ctx.size(), &lo, &hi);
+    const size_t eb = 2 * (size_t)c->B;
+    return bgn_g1_add_batch(c, a + lo * eb, b + lo * eb, hi - lo, out + lo * eb);
+  });
+}
+int bgn_group_multpoly_batch(bgn_group* grp, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                             uint8_t* out) {
+  return group_run(grp, [&](size_t g, bgn_ctx* c) {
+    size_t lo, hi;
+    group_shard(count, g, grp->ctx.size(), &lo, &hi);
+    const size_t eb = 2 * (size_t)c->B;
+    return bgn_multpoly_batch(c, c1 + lo * d1 * eb, d1, c2 + lo * d2 * eb, d2, hi - lo, out + lo * (d1 + d2) * eb);
+  });
+}
+int bgn_group_decrypt_batch(bgn_group* grp, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status) {
+  return group_run(grp, [&](size_t g, bgn_ctx* c) {
+    size_t lo, hi;
+    group_shard(count, g, grp->ctx.size(), &lo, &hi);
+    return bgn_decrypt_batch(c, in + lo * 2 * (size_t)c->B, is_l2, hi - lo, out + lo, status + lo);
+  });
+}
+// sum_i c1[i] * c2[i] as ONE polynomial ciphertext of d1 + d2 level-2 slots (BASELINE config 5): every device
+// multiplies its shard (MultPoly) and reduces it to one partial (GT product tree); the partials -- d1 + d2
+// elements per device -- are folded on device 0.
+int bgn_group_inner_product(bgn_group* grp, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                            uint8_t* out) {
+  if (!grp || grp->ctx.empty() || !out) return BGN_E_BADARG;
+  const size_t n = grp->ctx.size(), nc = d1 + d2, eb = 2 * (size_t)grp->ctx[0]->B;
+  std::vector<uint8_t> parts, prod;
+  try {
+    parts.resize(n * nc * eb);
+    prod.resize(count * nc * eb);
+  } catch (...) {
+    grp->err = "host allocation failed";
+    return BGN_E_NOMEM;
+  }
+  int st = group_run(grp, [&](size_t g, bgn_ctx* c) {
+    size_t lo, hi;
+    group_shard(count, g, n, &lo, &hi);
+    uint8_t* pr = prod.data() + lo * nc * eb;
+    int s1 = (hi > lo) ? bgn_multpoly_batch(c, c1 + lo * d1 * eb, d1, c2 + lo * d2 * eb, d2, hi - lo, pr) : BGN_OK;
+    if (s1 != BGN_OK) return s1;
+    return bgn_l2_sum_reduce(c, hi > lo ? pr : nullptr, hi - lo, nc, parts.data() + g * nc * eb);
+  });
+  if (st != BGN_OK) return st;
+  st = bgn_l2_sum_reduce(grp->ctx[0], parts.data(), n, nc, out);
+  if (st != BGN_OK) grp->err = grp->ctx[0]->err;
+  return st;
+}
+
 // ---------------------------------------------------------------- instrumentation
 int bgn_timing_enable(bgn_ctx* c, int on) {
   if (!c) return BGN_E_BADARG;

@@ -380,6 +380,98 @@ class Engine:
         return ms.value
 
 
+class EngineGroup:
+    """One key on SEVERAL GPUs behind one handle (bgn_group, include/bgn_b200.h): every batch call is cut
+    into contiguous shards, one per listed device, each run from its own host thread inside the library.
+    Buffers are host arrays.  `devices` may repeat an ordinal (its contexts take turns)."""
+
+    def __init__(self, p: int, n: int, l: int, P_bytes: bytes, Q_bytes: bytes, devices: Sequence[int]):
+        self._lib = _cabi.load()
+        self._grp = C.c_void_p()
+        pb = p.to_bytes((p.bit_length() + 7) // 8, "big")
+        nb = n.to_bytes((n.bit_length() + 7) // 8, "big")
+        prm = _cabi.bgn_params(pb, len(pb), nb, len(nb), l, bytes(P_bytes), bytes(Q_bytes))
+        devs = (C.c_int * len(devices))(*devices)
+        st = self._lib.bgn_group_create(C.byref(prm), len(devices), devs, C.byref(self._grp))
+        if st != 0:
+            self._grp = C.c_void_p()
+            raise BgnError(st, self._lib.bgn_global_last_error().decode() or "bgn_group_create failed")
+        L, B, nbytes = C.c_int(), C.c_int(), C.c_int()
+        self._lib.bgn_ctx_info(self._lib.bgn_group_ctx(self._grp, 0), C.byref(L), C.byref(B), C.byref(nbytes))
+        self.limbs, self.coord_bytes, self.scalar_bytes = L.value, B.value, nbytes.value
+        self.elem_bytes = 2 * B.value
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_grp", None) is not None and self._grp.value:
+            self._lib.bgn_group_destroy(self._grp)
+            self._grp = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != 0:
+            raise BgnError(st, self._lib.bgn_group_last_error(self._grp).decode())
+
+    @staticmethod
+    def _host(x, dtype=np.uint8):
+        if _is_torch(x):
+            assert not x.is_cuda, "group calls take host buffers (a device pointer belongs to one GPU)"
+            return x
+        return np.ascontiguousarray(x, dtype=dtype)
+
+    def scalars_be(self, ks: Sequence[int], width: Optional[int] = None) -> np.ndarray:
+        width = width or self.scalar_bytes
+        return np.frombuffer(b"".join(int(k).to_bytes(width, "big") for k in ks), dtype=np.uint8).copy()
+
+    def set_secret(self, q1: int, msg_space: int, baby_steps: int = 0):
+        qb = q1.to_bytes((q1.bit_length() + 7) // 8, "big")
+        self._check(self._lib.bgn_group_set_secret(self._grp, qb, len(qb), msg_space, baby_steps))
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.bgn_group_set_option(self._grp, name.encode(), int(value)))
+
+    def encrypt_batch(self, x, r_be=None, out=None):
+        x = self._host(x, np.int64)
+        count = _as_buf(x)[1] // 8
+        r = None if r_be is None else self._host(r_be)
+        o = out if out is not None else np.empty(count * self.elem_bytes, dtype=np.uint8)
+        self._check(self._lib.bgn_group_encrypt_batch(self._grp, _as_buf(x)[0], _as_buf(r)[0], count, _as_buf(o)[0]))
+        return o
+
+    def g1_add_batch(self, a, b, out=None):
+        a, b = self._host(a), self._host(b)
+        na = _as_buf(a)[1]
+        o = out if out is not None else np.empty(na, dtype=np.uint8)
+        self._check(self._lib.bgn_group_g1_add_batch(self._grp, _as_buf(a)[0], _as_buf(b)[0], na // self.elem_bytes, _as_buf(o)[0]))
+        return o
+
+    def multpoly_batch(self, c1, d1: int, c2, d2: int, count: int, out=None):
+        c1, c2 = self._host(c1), self._host(c2)
+        o = out if out is not None else np.empty(count * (d1 + d2) * self.elem_bytes, dtype=np.uint8)
+        self._check(self._lib.bgn_group_multpoly_batch(self._grp, _as_buf(c1)[0], d1, _as_buf(c2)[0], d2, count, _as_buf(o)[0]))
+        return o
+
+    def inner_product(self, c1, d1: int, c2, d2: int, count: int):
+        c1, c2 = self._host(c1), self._host(c2)
+        o = np.empty((d1 + d2) * self.elem_bytes, dtype=np.uint8)
+        self._check(self._lib.bgn_group_inner_product(self._grp, _as_buf(c1)[0], d1, _as_buf(c2)[0], d2, count, _as_buf(o)[0]))
+        return o
+
+    def decrypt_batch(self, cts, is_l2: bool):
+        cts = self._host(cts)
+        count = _as_buf(cts)[1] // self.elem_bytes
+        vals = np.empty(count, dtype=np.int64)
+        status = np.empty(count, dtype=np.uint8)
+        self._check(self._lib.bgn_group_decrypt_batch(self._grp, _as_buf(cts)[0], 1 if is_l2 else 0, count,
+                                                      _as_buf(vals)[0], _as_buf(status)[0]))
+        return vals, status
+
+
 def bench_imad_peak(device: int, iters: int, blocks: int, threads: int):
     """-> (ms, IMAD.WIDE instructions per thread)"""
     lib = _cabi.load()

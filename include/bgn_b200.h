@@ -194,6 +194,30 @@ int bgn_multpoly_h(bgn_ctx* ctx, const bgn_buf* c1, size_t d1, const bgn_buf* c2
 int bgn_l2_sum_reduce_h(bgn_ctx* ctx, const bgn_buf* in, size_t nterms, size_t ncoeff, bgn_buf** out);
 int bgn_decrypt_h(bgn_ctx* ctx, const bgn_buf* in, int64_t* out, uint8_t* status);
 
+/* ---- several GPUs behind one handle ("multi-GPU is driven inside one call by per-device host
+ * threads").  A bgn_group owns one context per listed device (a device may be listed more than once: its contexts
+ * then take turns); every batch call cuts the batch into contiguous shards -- the reference's independent units
+ * (poly.go:15, 37, 140-141) -- and runs each shard on its device from its own host thread.  Buffers are HOST
+ * pointers.  Results are identical to the single-context calls.  Per-member access (options, handles, timing):
+ * bgn_group_ctx(grp, i). */
+typedef struct bgn_group bgn_group;
+int bgn_group_create(const bgn_params* prm, int ndev, const int* devs, bgn_group** out);
+void bgn_group_destroy(bgn_group* grp);
+int bgn_group_size(const bgn_group* grp);
+bgn_ctx* bgn_group_ctx(bgn_group* grp, int i);
+const char* bgn_group_last_error(const bgn_group* grp);
+int bgn_group_set_secret(bgn_group* grp, const uint8_t* q1_be, size_t q1_len, uint64_t msg_space, uint32_t baby_steps);
+int bgn_group_set_option(bgn_group* grp, const char* name, long value);
+int bgn_group_encrypt_batch(bgn_group* grp, const int64_t* x, const uint8_t* r_be, size_t count, uint8_t* out);
+int bgn_group_g1_add_batch(bgn_group* grp, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out);
+int bgn_group_multpoly_batch(bgn_group* grp, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                             uint8_t* out);
+int bgn_group_decrypt_batch(bgn_group* grp, const uint8_t* in, int is_l2, size_t count, int64_t* out, uint8_t* status);
+/* sum_i c1[i] * c2[i] as one polynomial ciphertext of d1 + d2 level-2 slots (AddPoly folded over MultPoly,
+ * poly.go:123-156, 191-204): per-device MultPoly + GT product tree, partials folded on the first device. */
+int bgn_group_inner_product(bgn_group* grp, const uint8_t* c1, size_t d1, const uint8_t* c2, size_t d2, size_t count,
+                            uint8_t* out);
+
 /* ---- instrumentation (bench.py) ---- */
 /* When enabled, every kernel launch is bracketed by CUDA events on the context's
  * stream; bgn_timing_get returns the accumulated device time and launch count of

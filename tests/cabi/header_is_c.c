@@ -22,7 +22,11 @@ int main(void) {
       (fn)bgn_bench_issue_mix,     (fn)bgn_buf_import,         (fn)bgn_buf_export,
       (fn)bgn_buf_info,            (fn)bgn_buf_free,           (fn)bgn_encrypt_h,
       (fn)bgn_g1_add_h,            (fn)bgn_gt_mul_h,           (fn)bgn_pair_h,
-      (fn)bgn_multpoly_h,          (fn)bgn_l2_sum_reduce_h,    (fn)bgn_decrypt_h};
+      (fn)bgn_multpoly_h,          (fn)bgn_l2_sum_reduce_h,    (fn)bgn_decrypt_h,
+      (fn)bgn_group_create,        (fn)bgn_group_destroy,      (fn)bgn_group_size,
+      (fn)bgn_group_ctx,           (fn)bgn_group_last_error,   (fn)bgn_group_set_secret,
+      (fn)bgn_group_set_option,    (fn)bgn_group_encrypt_batch, (fn)bgn_group_g1_add_batch,
+      (fn)bgn_group_multpoly_batch, (fn)bgn_group_decrypt_batch, (fn)bgn_group_inner_product};
   unsigned n = (unsigned)(sizeof(syms) / sizeof(syms[0])), ok = 0, i;
   for (i = 0; i < n; i++) ok += syms[i] != 0;
   /* a null context is rejected with a status, never a crash */

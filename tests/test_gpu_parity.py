@@ -387,6 +387,50 @@ def test_multpoly_wide_team_kernel_equals_team_kernel(kb, count, d1, d2, tpb):
     e.close()
 
 
+@pytest.mark.parametrize("kb", [128, 512])
+def test_group_of_contexts_equals_single_context(kb):
+    """bgn_group (several GPUs behind one handle, one host thread per device inside each call): every GPU of the
+    box when there are several, and in any case three contexts taking turns on device 0 -- an uneven split
+    with an empty shard (2 units over 3 members).  Sharded Encrypt / EAdd / MultPoly / Decrypt give the
+    single-context bytes; the inner product equals MultPoly + L2 sum on one context and decrypts to the
+    plaintext result."""
+    import torch
+    from bgn_b200 import Engine, EngineGroup
+    g = load_golden(kb)
+    key = (int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+    one = Engine(*key)
+    one.set_secret(int(g["q1"], 16), g["msg_space"])
+    rng = random.Random(kb + 9)
+    n = key[1]
+    layouts = [[0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        layouts.append(list(range(torch.cuda.device_count())))
+    for devs in layouts:
+        grp = EngineGroup(*key, devices=devs)
+        grp.set_secret(int(g["q1"], 16), g["msg_space"])
+        for count, d in ((2, 3), (29, 3)):
+            xa = np.array([rng.randrange(-1, 2) for _ in range(count * d)], dtype=np.int64)
+            xb = np.array([rng.randrange(-1, 2) for _ in range(count * d)], dtype=np.int64)
+            ra = one.scalars_be([rng.randrange(n) for _ in range(count * d)])
+            rb = one.scalars_be([rng.randrange(n) for _ in range(count * d)])
+            A, Bq = grp.encrypt_batch(xa, ra), grp.encrypt_batch(xb, rb)
+            assert A.tobytes() == one.encrypt_batch(xa, ra).tobytes() and Bq.tobytes() == one.encrypt_batch(xb, rb).tobytes()
+            assert grp.g1_add_batch(A, Bq).tobytes() == one.g1_add_batch(A, Bq).tobytes()
+            prod = grp.multpoly_batch(A, d, Bq, d, count)
+            assert prod.tobytes() == one.multpoly_batch(A, d, Bq, d, count).tobytes()
+            total = grp.inner_product(A, d, Bq, d, count)
+            assert total.tobytes() == one.l2_sum_reduce(prod, count, 2 * d).tobytes()
+            vals, st = grp.decrypt_batch(total, True)
+            plain = np.sum([np.convolve(xa[u * d:(u + 1) * d], xb[u * d:(u + 1) * d]) for u in range(count)], axis=0)
+            assert not st.any() and vals.tolist() == plain.tolist() + [0]
+            v1, s1 = grp.decrypt_batch(A, False)
+            assert not s1.any() and v1.tolist() == xa.tolist()
+        grp.close()
+    one.close()
+    with pytest.raises(Exception):
+        EngineGroup(*key, devices=[0, 99])
+
+
 def test_empty_batches(golden):
     e = engine_for(golden)
     z = np.zeros(0, dtype=np.uint8)

@@ -10,7 +10,7 @@ tail -6 $O/r2e_pytest.log
 tail -3 $O/r2e_bench_n2.err
 ( time timeout 600 python bench.py --single-process --gpus 2 --steps 3 --warmup 3 ) > $O/r2e_bench_sp2.json 2> $O/r2e_bench_sp2.err
 tail -3 $O/r2e_bench_sp2.err
-( time timeout 600 python bench.py --single-process --gpus 1 --steps 3 --warmup 3 ) > $O/r2e_bench_sp1.json 2>> $O/r2e_bench_sp2.err
+
 python - <<PY
 import json
 d=json.loads(open("$O/r2e_bench_n2.json").read().strip().splitlines()[0])
