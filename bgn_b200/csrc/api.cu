@@ -149,7 +149,8 @@ struct bgn_ctx {
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
-  int enc_window = 16;         // 16; 8 stays with the small table, 24 builds the 50 GB one (BGN_ENC_WINDOW)
+  int enc_window = 0;          // window bits of Q's table: 0 = widest of 16/18/20 within enc_table_max; 8 | 16 | 18 | 20 | 22 | 24 (BGN_ENC_WINDOW)
+  size_t enc_table_max = (size_t)4 << 30;  // bound of the automatic choice (option enc_table_max_mb)
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
@@ -807,7 +808,27 @@ void check_count(size_t count) {
   if (count > ((size_t)1 << 27)) throw ArgErr{"batch too large (max 2^27 elements per call)"};
 }
 
-// builds a 255-entry-per-window table for the base point (bx, by) (device, Montgomery, N = 1)
+// Table of nwin windows of hb bits for the base point (bx, by) (device, Montgomery, N = 1): entry (w, d),
+// d = 1 .. 2^hb - 1, is d * 2^(hb w) * base, affine x || y.  The caller provides the temporaries: Jacobian
+// and affine arrays of nwin points for the window bases, a Jacobian array of nwin (2^hb - 1) points and
+// as many field elements of scratch.
+void build_table_with(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* tab, const JacArr& jb,
+                      const G1Arr& ab, const JacArr& je, uint32_t* scratch) {
+  size_t nent = (size_t)nwin * (((size_t)1 << hb) - 1);
+  {
+    Timer t(c, "k_tab_bases");
+    c->Bo->tab_bases(cfg(c, 1, 32, 0), bx, by, nwin, hb, jb.X, jb.Y, jb.Z, jb.N);
+    t.done();
+  }
+  normalize_soa(c, jb, nwin, scratch, ab);
+  {
+    Timer t(c, "k_tab_fill");
+    c->Bo->tab_fill(cfg(c, nblk(nwin, 32), 32, 0), ab.x, ab.y, ab.inf, ab.N, nwin, hb, je.X, je.Y, je.Z, je.N);
+    t.done();
+  }
+  normalize(c, je, nent, scratch, tab, tab + c->L, 2 * (size_t)c->L, 1, nullptr);
+}
+// the 255-entry-per-window tables of P and Q built with the key (temporaries from the arena)
 void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* tab) {
   size_t nent = (size_t)nwin * 255;
   arena_reset(c);
@@ -816,63 +837,77 @@ void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, u
   G1Arr ab = g1_alloc(c, nwin);
   JacArr je = jac_alloc(c, nent);
   uint32_t* scratch = arena_get<uint32_t>(c, nent * c->L);
-  {
-    Timer t(c, "k_tab_bases");
-    c->Bo->tab_bases(cfg(c, 1, 32, 0), bx, by, nwin, jb.X, jb.Y, jb.Z, jb.N);
-    t.done();
-  }
-  normalize_soa(c, jb, nwin, scratch, ab);
-  {
-    Timer t(c, "k_tab_fill");
-    c->Bo->tab_fill(cfg(c, nblk(nwin, 32), 32, 0), ab.x, ab.y, ab.inf, ab.N, nwin, je.X, je.Y, je.Z, je.N);
-    t.done();
-  }
-  normalize(c, je, nent, scratch, tab, tab + c->L, 2 * (size_t)c->L, 1, nullptr);
+  build_table_with(c, bx, by, nwin, 8, tab, jb, ab, je, scratch);
   finish(c);
 }
 
-// Wide-window table of Q for Encrypt, sized for HBM rather than shared memory: windows of 16 bits
-// (ceil(nbytes/2) x 65535 affine points: 285 MB at 512-bit keys, 1.1 GB at 1024; half the additions
-// of the 8-bit table) or, on request, of 24 bits (ceil(nbytes/3) x (2^24 - 1) points: 50 GB at 512
-// bit, a third of the additions).  Built once from the 8-bit table, in chunks whose temporaries are
-// released again.  A 24-bit table that does not fit the free memory falls back to 16 bits.
+// Wide-window table of Q for Encrypt, sized for HBM rather than shared memory: ceil(8 nbytes / w) windows of
+// w bits, 2^w - 1 affine points each.  At 512-bit keys: w = 16: 285 MB, 32 additions per encryption;
+// w = 20: 3.7 GB, 26; w = 22: 13.7 GB, 24; w = 24: 50 GB, 22.  A window is built as nsub windows of hb
+// bits (16 = 2 x 8, 18 = 2 x 9, 20 = 2 x 10, 22 = 2 x 11, 24 = 3 x 8) from a narrow table -- the 8-bit
+// table of the key, or a temporary one -- in chunks whose temporaries are released again.  enc_window = 0
+// (the default) takes the widest of 16 / 18 / 20 bits whose table stays within enc_table_max bytes
+// (4 GiB); a table that does not fit the free memory falls back to 16 bits.
+size_t tabQw_bytes(const bgn_ctx* c, int bits) {
+  return (size_t)((8 * c->nbytes + bits - 1) / bits) * (((size_t)1 << bits) - 1) * 2 * (size_t)c->L * 4;
+}
+int enc_window_auto(const bgn_ctx* c) {
+  for (int bits = 20; bits > 16; bits -= 2)
+    if (tabQw_bytes(c, bits) <= c->enc_table_max) return bits;
+  return 16;
+}
 void ensure_tabQw(bgn_ctx* c) {
   if (c->tabQw || c->enc_window == 8) return;
-  int wbits = c->enc_window;
+  int wbits = c->enc_window ? c->enc_window : enc_window_auto(c);
   size_t ew = (size_t)c->L * 4;
-  auto table_bytes = [&](int bits) {
-    int wb = bits / 8;
-    return (size_t)((c->nbytes + wb - 1) / wb) * (((size_t)1 << bits) - 1) * 2 * ew;
-  };
   const size_t chunk_max = (size_t)1 << 22;
-  if (wbits == 24) {
+  if (wbits > 16) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    if (table_bytes(24) + chunk_max * 4 * ew + ((size_t)16 << 30) > free_b) wbits = 16;
+    // leave room for the callers' batches next to the table (a quarter of it, at least 1 GiB, at most 16)
+    size_t room = std::min<size_t>((size_t)16 << 30, std::max<size_t>((size_t)1 << 30, tabQw_bytes(c, wbits) / 4));
+    if (tabQw_bytes(c, wbits) + chunk_max * 4 * ew + room > free_b) wbits = 16;
   }
-  const int wb = wbits / 8;
+  const int nsub = wbits % 8 == 0 ? wbits / 8 : 2;
+  const int hb = wbits / nsub;
+  const int nwin = (8 * c->nbytes + wbits - 1) / wbits;
   const size_t ents = ((size_t)1 << wbits) - 1;
-  const size_t nent = (size_t)((c->nbytes + wb - 1) / wb) * ents;
+  const size_t nent = (size_t)nwin * ents;
   const size_t chunk = std::min(nent, chunk_max);
-  uint32_t *tab = nullptr, *tmp = nullptr;
-  CK(cudaMalloc(&tab, nent * 2 * ew));
-  cudaError_t e = cudaMalloc(&tmp, chunk * 4 * ew);
-  if (e != cudaSuccess) {
-    cudaFree(tab);
-    CK(e);
-  }
-  JacArr j;
-  j.X = tmp;
-  j.Y = tmp + chunk * c->L;
-  j.Z = tmp + 2 * chunk * c->L;
-  j.N = chunk;
-  uint32_t* scratch = tmp + 3 * chunk * c->L;
+  uint32_t *tab = nullptr, *tmp = nullptr, *narrow = nullptr;
   try {
+    CK(cudaMalloc(&tab, nent * 2 * ew));
+    CK(cudaMalloc(&tmp, chunk * 4 * ew));
+    const uint32_t* tabh = c->tabQ;
+    int nwin_h = c->nbytes;
+    if (hb != 8) {
+      // temporary narrow table: nwin * nsub windows of hb bits
+      nwin_h = nwin * nsub;
+      const size_t nent_h = (size_t)nwin_h * (((size_t)1 << hb) - 1);
+      const size_t words = (6 * nent_h + 5 * (size_t)nwin_h) * c->L;
+      CK(cudaMalloc(&narrow, words * 4 + pad256(nwin_h) + 256));
+      uint32_t* w = narrow + 2 * nent_h * c->L;
+      JacArr je{w, w + nent_h * c->L, w + 2 * nent_h * c->L, nent_h};
+      w += 3 * nent_h * c->L;
+      uint32_t* scratch = w;
+      w += nent_h * c->L;
+      JacArr jb{w, w + (size_t)nwin_h * c->L, w + 2 * (size_t)nwin_h * c->L, (size_t)nwin_h};
+      w += 3 * (size_t)nwin_h * c->L;
+      G1Arr ab{w, w + (size_t)nwin_h * c->L, reinterpret_cast<uint8_t*>(w + 2 * (size_t)nwin_h * c->L), (size_t)nwin_h};
+      build_table_with(c, c->dQx, c->dQy, nwin_h, hb, narrow, jb, ab, je, scratch);
+      tabh = narrow;
+    }
+    JacArr j;
+    j.X = tmp;
+    j.Y = tmp + chunk * c->L;
+    j.Z = tmp + 2 * chunk * c->L;
+    j.N = chunk;
+    uint32_t* scratch = tmp + 3 * chunk * c->L;
     for (size_t first = 0; first < nent; first += chunk) {
       size_t cnt = std::min(chunk, nent - first);
       {
         Timer t(c, "k_tabw_fill");
-        c->Bo->tabw_fill(cfg(c, nblk(cnt, 128), 128, 0), c->tabQ, c->nbytes, wb, j.X, j.Y, j.Z, first, cnt);
+        c->Bo->tabw_fill(cfg(c, nblk(cnt, 128), 128, 0), tabh, nwin_h, nsub, hb, j.X, j.Y, j.Z, first, cnt);
         t.done();
       }
       uint32_t* dst = tab + first * 2 * c->L;
@@ -882,9 +917,11 @@ void ensure_tabQw(bgn_ctx* c) {
   } catch (...) {
     cudaFree(tab);
     cudaFree(tmp);
+    cudaFree(narrow);
     throw;
   }
   CK(cudaFree(tmp));
+  if (narrow) CK(cudaFree(narrow));
   c->tabQw = tab;
   c->tabQw_bits = wbits;
 }
@@ -1090,7 +1127,10 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     if (const char* sk = getenv("BGN_MILLER_SKEW")) c->miller_skew = atoi(sk);  // tuning knob (cycles)
     if (const char* gr = getenv("BGN_MILLER_GROUPS")) c->miller_groups = atoi(gr);
     if (const char* tl = getenv("BGN_MILLER_TAIL")) c->miller_tail = atoi(tl);
-    if (const char* ew = getenv("BGN_ENC_WINDOW")) c->enc_window = atoi(ew) == 8 ? 8 : (atoi(ew) == 24 ? 24 : 16);
+    if (const char* ew = getenv("BGN_ENC_WINDOW")) {
+      int w = atoi(ew);
+      c->enc_window = (w == 8 || (w >= 16 && w <= 24 && w % 2 == 0)) ? w : 0;
+    }
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
     if (const char* af = getenv("BGN_AFFINE_ADD")) c->affine_add = atoi(af) != 0;
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
@@ -1276,11 +1316,11 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
   std::lock_guard<std::mutex> lk(dev_mu(c->device));
   std::string k(name);
   if (k == "enc_window") {
-    if (value != 8 && value != 16 && value != 24) {
-      c->err = "enc_window must be 8, 16 or 24";
+    if (value != 0 && value != 8 && !(value >= 16 && value <= 24 && value % 2 == 0)) {
+      c->err = "enc_window must be 0 (automatic), 8, 16, 18, 20, 22 or 24";
       return BGN_E_BADARG;
     }
-    if (c->enc_window != (int)value || (c->tabQw && c->tabQw_bits != (int)value)) {
+    if (c->enc_window != (int)value) {
       cudaSetDevice(c->device);
       if (c->stream) cudaStreamSynchronize(c->stream);
       cudaFree(c->tabQw);
@@ -1288,6 +1328,15 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
       c->tabQw_bits = 0;
     }
     c->enc_window = (int)value;
+  } else if (k == "enc_table_max_mb") {
+    c->enc_table_max = (size_t)std::max<long>(0, value) << 20;
+    if (c->enc_window == 0 && c->tabQw) {
+      cudaSetDevice(c->device);
+      if (c->stream) cudaStreamSynchronize(c->stream);
+      cudaFree(c->tabQw);
+      c->tabQw = nullptr;
+      c->tabQw_bits = 0;
+    }
   } else if (k == "dec_lucas") {
     c->dec_lucas = value != 0;
   } else if (k == "fixed_lines") {

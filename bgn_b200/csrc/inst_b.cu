@@ -25,17 +25,17 @@ void encrypt(LaunchCfg cfg, const EncArgs& a) { k_encrypt<LL><<<CFG>>>(a); }
 void normalize(LaunchCfg cfg, const NormArgs& a) { k_normalize<LL><<<CFG>>>(a); }
 void g1_add(LaunchCfg cfg, const G1AddArgs& a) { k_g1_add<LL><<<CFG>>>(a); }
 void g1_mulvar(LaunchCfg cfg, const G1MulArgs& a) { k_g1_mulvar<LL><<<CFG>>>(a); }
-void tab_bases(LaunchCfg cfg, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
-               size_t N) {
-  k_tab_bases<LL><<<CFG>>>(bx, by, nwin, X, Y, Z, N);
+void tab_bases(LaunchCfg cfg, const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* X, uint32_t* Y,
+               uint32_t* Z, size_t N) {
+  k_tab_bases<LL><<<CFG>>>(bx, by, nwin, hb, X, Y, Z, N);
 }
-void tab_fill(LaunchCfg cfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
+void tab_fill(LaunchCfg cfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, int hb,
               uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
-  k_tab_fill<LL><<<CFG>>>(ax, ay, ainf, Nb, nwin, X, Y, Z, N);
+  k_tab_fill<LL><<<CFG>>>(ax, ay, ainf, Nb, nwin, hb, X, Y, Z, N);
 }
-void tabw_fill(LaunchCfg cfg, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
-               size_t nent) {
-  k_tabw_fill<LL><<<CFG>>>(tab8, nwin8, wb, X, Y, Z, first, nent);
+void tabw_fill(LaunchCfg cfg, const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+               size_t first, size_t nent) {
+  k_tabw_fill<LL><<<CFG>>>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent);
 }
 void g1_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_g1_polyconv<LL><<<CFG>>>(a); }
 void g1_affadd(LaunchCfg cfg, const G1AffAddArgs& a) { k_g1_affadd<LL><<<CFG>>>(a); }

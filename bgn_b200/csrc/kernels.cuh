@@ -159,18 +159,20 @@ BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
     FF::set_one(Z.v());
   }
   if (a.r_be) {
-    // fixed-base windows of wbitsQ = 8, 16 or 24 bits: one complete mixed addition per non-zero
-    // window digit.  The wide tables (2^16 - 1 or 2^24 - 1 points per window: 285 MB / 50 GB at 512
-    // bit) live in HBM and each lookup is one 8L-byte read at a random address.
+    // fixed-base windows of wbitsQ bits (8 .. 24, any width): one complete mixed addition per non-zero
+    // window digit.  The wide tables (2^wbitsQ - 1 points per window: 285 MB at 16 bits, 3.7 GB at 20,
+    // 50 GB at 24 for 512-bit keys) live in HBM and each lookup is one 8L-byte read at a random address.
     const uint8_t* r = a.r_be + e * a.rbytes;
-    const int wb = a.wbitsQ >> 3;
-    const size_t ents = ((size_t)1 << a.wbitsQ) - 1;
-    const int nw = (a.rbytes + wb - 1) / wb;
+    const int wbits = a.wbitsQ;
+    const size_t ents = ((size_t)1 << wbits) - 1;
+    const int nw = (8 * a.rbytes + wbits - 1) / wbits;
     for (int win = 0; win < nw; win++) {
-      int lo = a.rbytes - 1 - wb * win;
-      uint32_t d = r[lo];
-      for (int k = 1; k < wb; k++)
-        if (lo - k >= 0) d |= (uint32_t)r[lo - k] << (8 * k);
+      const int bit = win * wbits;            // offset of the digit from the least significant bit of r
+      const int lo = a.rbytes - 1 - (bit >> 3);
+      uint32_t v = r[lo];                     // four bytes cover 7 + 24 bits
+      for (int k = 1; k < 4; k++)
+        if (lo - k >= 0) v |= (uint32_t)r[lo - k] << (8 * k);
+      const uint32_t d = (v >> (bit & 7)) & (uint32_t)ents;
       if (d) {
         const uint32_t* ent = a.tabQ + ((size_t)win * ents + (d - 1)) * 2 * L;
         G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
@@ -376,10 +378,10 @@ BGN_DEV void g1_mulvar_body(const G1MulArgs& a, size_t e) {
 }
 
 // table construction -----------------------------------------------------
-// bases[win] = 2^(8 win) * Base in Jacobian coordinates (single thread: 8*nwin doublings)
+// bases[win] = 2^(hb win) * Base in Jacobian coordinates (single thread: hb*nwin doublings)
 template <int L>
-BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
-                            size_t N, size_t g) {
+BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* X, uint32_t* Y,
+                            uint32_t* Z, size_t N, size_t g) {
   typedef F<L> FF;
   if (g != 0) return;
   Loc<L> x, y, z, t0, t1, t2, t3;
@@ -390,42 +392,45 @@ BGN_DEV void tab_bases_body(const uint32_t* bx, const uint32_t* by, int nwin, ui
     FF::copy(X + (size_t)(win) * L, x.v());
     FF::copy(Y + (size_t)(win) * L, y.v());
     FF::copy(Z + (size_t)(win) * L, z.v());
-    for (int i = 0; i < 8; i++) G<L>::dbl(x.v(), y.v(), z.v(), t0.v(), t1.v(), t2.v(), t3.v());
+    for (int i = 0; i < hb; i++) G<L>::dbl(x.v(), y.v(), z.v(), t0.v(), t1.v(), t2.v(), t3.v());
   }
 }
-// entries (win, d), d = 1..255, by repeated addition of the affine base of the window
+// entries (win, d), d = 1 .. 2^hb - 1, by repeated addition of the affine base of the window
 template <int L>
-BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
+BGN_DEV void tab_fill_body(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, int hb,
                            uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N, size_t g) {
   typedef F<L> FF;
   int win = (int)g;
   if (g >= (size_t)nwin) return;
+  const int ents = (1 << hb) - 1;
   Loc<L> x, y, z, t0, t1, t2, t3;
   FF::set_zero(x.v());
   FF::set_zero(y.v());
   FF::set_zero(z.v());
-  for (int d = 1; d <= 255; d++) {
+  for (int d = 1; d <= ents; d++) {
     if (!ainf[win])
       G<L>::madd(x.v(), y.v(), z.v(), (ax + (size_t)(win) * L), (ay + (size_t)(win) * L), false, t0.v(), t1.v(), t2.v(),
                  t3.v());
-    size_t o = (size_t)win * 255 + (d - 1);
+    size_t o = (size_t)win * ents + (d - 1);
     FF::copy(X + (size_t)(o) * L, x.v());
     FF::copy(Y + (size_t)(o) * L, y.v());
     FF::copy(Z + (size_t)(o) * L, z.v());
   }
 }
 
-// Wide-window table from the 8-bit one: entry (w, d) of a table with windows of wb bytes is the sum
-// of the 8-bit entries of d's bytes, T8[wb w + k][byte k of d] (wb - 1 complete mixed additions per
-// entry, all entries in parallel; Jacobian out).  `first` is the global index of this launch's first
-// entry (the 24-bit table is built in chunks).  A window that reaches past the scalar's top byte
-// leaves the entries with a non-zero byte there as O; they are never addressed.
+// Wide-window table from a narrow one: a window of nsub * hb bits is nsub windows of hb bits, so entry
+// (w, d) is the sum of the narrow entries of d's hb-bit digits, Th[nsub w + k][digit k of d] (nsub - 1
+// complete mixed additions per entry, all entries in parallel; Jacobian out).  `first` is the global
+// index of this launch's first entry (large tables are built in chunks).  The narrow table has nwin_h
+// windows; a wide window that reaches past them leaves the entries with a non-zero digit there as O:
+// they lie beyond the scalar's top bit and are never addressed.
 template <int L>
-BGN_DEV void tabw_fill_body(const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+BGN_DEV void tabw_fill_body(const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
                             size_t first, size_t nent, size_t id) {
   typedef F<L> FF;
   if (id >= nent) return;
-  const size_t ents = ((size_t)1 << (8 * wb)) - 1;
+  const size_t ents = ((size_t)1 << (hb * nsub)) - 1;
+  const uint32_t mask = (1u << hb) - 1u;
   const size_t gidx = first + id;
   const int w = (int)(gidx / ents);
   const uint32_t d = (uint32_t)(gidx % ents) + 1;
@@ -434,13 +439,13 @@ BGN_DEV void tabw_fill_body(const uint32_t* tab8, int nwin8, int wb, uint32_t* X
   FF::set_zero(y.v());
   FF::set_zero(z.v());
   bool valid = true;
-  for (int k = 0; k < wb; k++)
-    if (((d >> (8 * k)) & 255u) && w * wb + k >= nwin8) valid = false;
+  for (int k = 0; k < nsub; k++)
+    if (((d >> (hb * k)) & mask) && w * nsub + k >= nwin_h) valid = false;
   if (valid) {
-    for (int k = 0; k < wb; k++) {
-      uint32_t byte = (d >> (8 * k)) & 255u;
-      if (byte) {
-        const uint32_t* ent = tab8 + ((size_t)(w * wb + k) * 255 + (byte - 1)) * 2 * L;
+    for (int k = 0; k < nsub; k++) {
+      uint32_t dig = (d >> (hb * k)) & mask;
+      if (dig) {
+        const uint32_t* ent = tabh + ((size_t)(w * nsub + k) * mask + (dig - 1)) * 2 * L;
         G<L>::madd(x.v(), y.v(), z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
       }
     }
@@ -927,19 +932,19 @@ __global__ void k_fp2_to_bytes(const uint32_t* re, const uint32_t* im, size_t N,
   stage_bytes_out(out + first * 2 * B, smem_io, n * 2 * B);
 }
 template <int L>
-__global__ void k_tab_bases(const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
-                            size_t N) {
-  tab_bases_body<L>(bx, by, nwin, X, Y, Z, N, BGN_GID(size_t));
+__global__ void k_tab_bases(const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* X, uint32_t* Y,
+                            uint32_t* Z, size_t N) {
+  tab_bases_body<L>(bx, by, nwin, hb, X, Y, Z, N, BGN_GID(size_t));
 }
 template <int L>
-__global__ void k_tab_fill(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
+__global__ void k_tab_fill(const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, int hb,
                            uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
-  tab_fill_body<L>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, BGN_GID(size_t));
+  tab_fill_body<L>(ax, ay, ainf, Nb, nwin, hb, X, Y, Z, N, BGN_GID(size_t));
 }
 template <int L>
-__global__ void __launch_bounds__(128) k_tabw_fill(const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y,
-                                                   uint32_t* Z, size_t first, size_t nent) {
-  tabw_fill_body<L>(tab8, nwin8, wb, X, Y, Z, first, nent, BGN_GID(size_t));
+__global__ void __launch_bounds__(128) k_tabw_fill(const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X,
+                                                   uint32_t* Y, uint32_t* Z, size_t first, size_t nent) {
+  tabw_fill_body<L>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent, BGN_GID(size_t));
 }
 template <int L>
 __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms,

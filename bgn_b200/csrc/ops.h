@@ -93,12 +93,12 @@ struct LOpsB {
   void (*normalize)(LaunchCfg, const NormArgs&);
   void (*g1_add)(LaunchCfg, const G1AddArgs&);
   void (*g1_mulvar)(LaunchCfg, const G1MulArgs&);
-  void (*tab_bases)(LaunchCfg, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z,
-                    size_t N);
-  void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin,
+  void (*tab_bases)(LaunchCfg, const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* X, uint32_t* Y,
+                    uint32_t* Z, size_t N);
+  void (*tab_fill)(LaunchCfg, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, int hb,
                    uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
-  void (*tabw_fill)(LaunchCfg, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
-                    size_t nent);
+  void (*tabw_fill)(LaunchCfg, const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                    size_t first, size_t nent);
   void (*g1_polyconv)(LaunchCfg, const PolyConvArgs&);
   void (*g1_affadd)(LaunchCfg, const G1AffAddArgs&);
 };

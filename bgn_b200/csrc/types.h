@@ -81,8 +81,8 @@ struct EncArgs {
   const uint8_t* r_be;    // randomness, big-endian, rbytes each (may be null: r = 0)
   int rbytes;
   const uint32_t* tabP;   // 8 windows
-  const uint32_t* tabQ;   // rbytes windows of 8 bits, or ceil(rbytes/2) windows of 16 bits
-  int wbitsQ;             // 8 or 16: window width of tabQ (entries per window = 2^wbitsQ - 1)
+  const uint32_t* tabQ;   // ceil(8 rbytes / wbitsQ) windows of wbitsQ bits
+  int wbitsQ;             // 8 .. 24: window width of tabQ (entries per window = 2^wbitsQ - 1)
   uint32_t *X, *Y, *Z;    // Jacobian out, [N][L]
   size_t count, N;
   // optional starting point per element (affine, [count][L] + infinity flags): out = base + r*Q,

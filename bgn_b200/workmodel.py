@@ -213,6 +213,19 @@ def affadd_products(L: int) -> int:
     return 5 * products_per_modmul(L) + products_per_sqr(L)
 
 
+def enc_table_bytes(rbytes: int, window_bits: int, L: int) -> int:
+    """bytes of the fixed-base table of Q with windows of window_bits (api.cu: tabQw_bytes)"""
+    return ((8 * rbytes + window_bits - 1) // window_bits) * ((1 << window_bits) - 1) * 2 * L * 4
+
+
+def enc_window_auto(rbytes: int, L: int, table_max: int = 4 << 30) -> int:
+    """the window width `enc_window = 0` picks (api.cu: enc_window_auto): widest of 20 / 18 / 16 bits within table_max"""
+    for bits in (20, 18):
+        if enc_table_bytes(rbytes, bits, L) <= table_max:
+            return bits
+    return 16
+
+
 def encrypt_products(n: int, rbytes: int, window_bits: int, L: int, p_x_nonzero: float = 2.0 / 3.0) -> float:
     """k_encrypt, EXPECTED 32x32->64 products per coefficient (see encrypt_modmuls for the addition count)"""
     return encrypt_modmuls(n, rbytes, window_bits, p_x_nonzero) / 11.0 * madd_products(L)

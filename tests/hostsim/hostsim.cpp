@@ -191,16 +191,17 @@ int hs_bsgs_build(int L, const BsgsBuildArgs* a) {
 int hs_bsgs_lookup(int L, const BsgsLookupArgs* a) {
   FOR_L(L, for (size_t e = 0; e < a->count; e++) bsgs_lookup_body<LL>(*a, e))
 }
-int hs_tab_bases(int L, const uint32_t* bx, const uint32_t* by, int nwin, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N) {
-  FOR_L(L, tab_bases_body<LL>(bx, by, nwin, X, Y, Z, N, 0))
+int hs_tab_bases(int L, const uint32_t* bx, const uint32_t* by, int nwin, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                 size_t N) {
+  FOR_L(L, tab_bases_body<LL>(bx, by, nwin, hb, X, Y, Z, N, 0))
 }
-int hs_tab_fill(int L, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, uint32_t* X,
+int hs_tab_fill(int L, const uint32_t* ax, const uint32_t* ay, const uint8_t* ainf, size_t Nb, int nwin, int hb, uint32_t* X,
                 uint32_t* Y, uint32_t* Z, size_t N) {
-  FOR_L(L, for (int w = 0; w < nwin; w++) tab_fill_body<LL>(ax, ay, ainf, Nb, nwin, X, Y, Z, N, w))
+  FOR_L(L, for (int w = 0; w < nwin; w++) tab_fill_body<LL>(ax, ay, ainf, Nb, nwin, hb, X, Y, Z, N, w))
 }
-int hs_tabw_fill(int L, const uint32_t* tab8, int nwin8, int wb, uint32_t* X, uint32_t* Y, uint32_t* Z, size_t first,
-                 size_t nent) {
-  FOR_L(L, for (size_t id = 0; id < nent; id++) tabw_fill_body<LL>(tab8, nwin8, wb, X, Y, Z, first, nent, id))
+int hs_tabw_fill(int L, const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
+                 size_t first, size_t nent) {
+  FOR_L(L, for (size_t id = 0; id < nent; id++) tabw_fill_body<LL>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent, id))
 }
 int hs_g1_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf, size_t N) {
   FOR_L(L, for (size_t e = 0; e < count; e++) g1_from_bytes_body<LL>(in, B, count, x, y, inf, N, e))

@@ -347,20 +347,21 @@ class Sim:
         xs, ys = self.unsoa(ox, count), self.unsoa(oy, count)
         return [None if inf[e] else (xs[e], ys[e]) for e in range(count)]
 
-    def build_table(self, base, nwin):
+    def build_table(self, base, nwin, hb=8):
+        """k_tab_bases + k_tab_fill + k_normalize (api.cu: build_table_with): nwin windows of hb bits"""
         L = self.L
         bx, by = self.soa([base[0]]), self.soa([base[1]])
         X = np.zeros((nwin, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
-        assert lib().hs_tab_bases(L, P32(bx), P32(by), nwin, P32(X), P32(Y), P32(Z), nwin) == 0
+        assert lib().hs_tab_bases(L, P32(bx), P32(by), nwin, hb, P32(X), P32(Y), P32(Z), nwin) == 0
         bases = self.normalize(X, Y, Z, nwin)
         ax, ay, ainf = self.g1_arrays(bases)
-        nent = nwin * 255
+        nent = nwin * ((1 << hb) - 1)
         X = np.zeros((nent, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
-        assert lib().hs_tab_fill(L, P32(ax), P32(ay), P8(ainf), nwin, nwin, P32(X), P32(Y), P32(Z), nent) == 0
+        assert lib().hs_tab_fill(L, P32(ax), P32(ay), P8(ainf), nwin, nwin, hb, P32(X), P32(Y), P32(Z), nent) == 0
         tab = np.zeros(nent * 2 * L, dtype=np.uint32)
         scratch = np.zeros_like(X)
         a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), nent, nent, 7, P32(tab), P32(tab[L:]), 2 * L, 1, None)
@@ -368,17 +369,21 @@ class Sim:
         return tab
 
     def build_table16(self, tab8, nwin8):
-        """k_tabw_fill + k_normalize: 16-bit windows from the 8-bit table (api.cu: ensure_tabQw), built in
-        two chunks the way the 24-bit table is"""
+        """16-bit windows from the 8-bit table of the key"""
+        return self.build_table_wide(tab8, nwin8, (nwin8 + 1) // 2, 2, 8)
+
+    def build_table_wide(self, tabh, nwin_h, nwin, nsub, hb):
+        """k_tabw_fill + k_normalize: nwin windows of nsub * hb bits from a table of nwin_h windows of hb bits
+        (api.cu: ensure_tabQw), built in two chunks the way the large tables are"""
         L = self.L
-        nent = ((nwin8 + 1) // 2) * 65535
+        nent = nwin * ((1 << (nsub * hb)) - 1)
         X = np.zeros((nent, L), dtype=np.uint32)
         Y = np.zeros_like(X)
         Z = np.zeros_like(X)
         half = nent // 2 + 3
-        assert lib().hs_tabw_fill(L, P32(tab8), nwin8, 2, P32(X), P32(Y), P32(Z), C.c_size_t(0), C.c_size_t(half)) == 0
-        assert lib().hs_tabw_fill(L, P32(tab8), nwin8, 2, P32(X[half:]), P32(Y[half:]), P32(Z[half:]), C.c_size_t(half),
-                                  C.c_size_t(nent - half)) == 0
+        assert lib().hs_tabw_fill(L, P32(tabh), nwin_h, nsub, hb, P32(X), P32(Y), P32(Z), C.c_size_t(0), C.c_size_t(half)) == 0
+        assert lib().hs_tabw_fill(L, P32(tabh), nwin_h, nsub, hb, P32(X[half:]), P32(Y[half:]), P32(Z[half:]),
+                                  C.c_size_t(half), C.c_size_t(nent - half)) == 0
         tab = np.zeros(nent * 2 * L, dtype=np.uint32)
         scratch = np.zeros_like(X)
         a = NormArgs(P32(X), P32(Y), P32(Z), P32(scratch), nent, nent, 64, P32(tab), P32(tab[L:]), 2 * L, 1, None)

@@ -884,36 +884,41 @@ def test_full_size_decrypt_l2():
     e2.close()
 
 
-def test_encrypt_window_24():
-    """The HBM-scale 24-bit fixed-base windows of Q (enc_window = 24; 4 GB at keyBits=128) give the
-    golden bytes, and on a random batch the same bytes as the default 16-bit table, incl. scalars with
-    zero top bytes (windows that reach past the scalar's top byte)."""
+def test_encrypt_windows():
+    """The HBM-scale fixed-base windows of Q (enc_window = 16 .. 24 bits; 18, 20 and 22 are built from a temporary
+    narrow table of 9-, 10- and 11-bit windows, 24 from the key's 8-bit table: 4 GB at keyBits=128) give the golden
+    bytes, and on a random batch the same bytes as the 8-bit table built with the context, incl. scalars with
+    zero top bytes (windows that reach past the scalar's top bit)."""
     from bgn_b200 import BgnError, Engine
     g = load_golden(128)
-    e24 = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
-    e24.set_option("enc_window", 24)
+    ew = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
     with pytest.raises(BgnError):
-        e24.set_option("enc_window", 12)
+        ew.set_option("enc_window", 12)
     with pytest.raises(BgnError):
-        e24.set_option("no_such_knob", 1)
-    v = g["encrypt"]
-    out = e24.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(e24, v["r"], e24.scalar_bytes))
-    assert out.tobytes() == unhex(v["out"])
-    v = g["g1_blind"]
-    assert e24.g1_blind_batch(buf(v["a"]), scal(e24, v["r"], e24.scalar_bytes)).tobytes() == unhex(v["out"])
+        ew.set_option("enc_window", 19)
+    with pytest.raises(BgnError):
+        ew.set_option("no_such_knob", 1)
     rng = np.random.default_rng(24)
     cnt = 4096
     x = rng.integers(-1, 2, cnt)
-    r = rng.integers(0, 256, (cnt, e24.scalar_bytes), dtype=np.uint8)
+    r = rng.integers(0, 256, (cnt, ew.scalar_bytes), dtype=np.uint8)
     r[:, 0] &= 0x3F
     r[::5, :4] = 0
     r[::7] = 0
-    e16 = engine_for(g)
-    exp = e16.encrypt_batch(x, r.reshape(-1)).tobytes()
-    assert e24.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
-    e24.set_option("enc_window", 8)  # drops the wide table: the 8-bit windows built with the context
-    assert e24.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
-    e24.close()
+    ew.set_option("enc_window", 8)  # no wide table: the 8-bit windows built with the context
+    exp = ew.encrypt_batch(x, r.reshape(-1)).tobytes()
+    for bits in (0, 16, 18, 20, 22, 24):  # 0: the automatic choice (20 bits at this key size)
+        ew.set_option("enc_window", bits)
+        v = g["encrypt"]
+        out = ew.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(ew, v["r"], ew.scalar_bytes))
+        assert out.tobytes() == unhex(v["out"]), bits
+        v = g["g1_blind"]
+        assert ew.g1_blind_batch(buf(v["a"]), scal(ew, v["r"], ew.scalar_bytes)).tobytes() == unhex(v["out"]), bits
+        assert ew.encrypt_batch(x, r.reshape(-1)).tobytes() == exp, bits
+    ew.set_option("enc_table_max_mb", 1)  # the automatic choice under a table bound: back to 16 bits
+    ew.set_option("enc_window", 0)
+    assert ew.encrypt_batch(x, r.reshape(-1)).tobytes() == exp
+    ew.close()
 
 
 def test_two_contexts_two_threads_same_device():

@@ -67,6 +67,15 @@ def test_sim_encrypt(kb):
             return O.g1_neg(c, par.p) if x < 0 else c
 
         assert S.encrypt(v["x"], small, tabs["P"], tabs["Q16"], wbitsQ=16) == [enc(x, r) for x, r in zip(v["x"], small)]
+        # windows that are not whole bytes (api.cu: ensure_tabQw builds 18 = 2 x 9, 20 = 2 x 10, 22 = 2 x 11 this
+        # way): 10 = 2 x 5 and 9 = 3 x 3 bits from a temporary narrow table, digits straddling byte boundaries
+        for nsub, hb in ((2, 5), (3, 3)):
+            wbits = nsub * hb
+            nwin = (8 * S.nbytes + wbits - 1) // wbits
+            narrow = S.build_table(S.Q, nwin * nsub, hb)
+            wide = S.build_table_wide(narrow, nwin * nsub, nwin, nsub, hb)
+            assert S.encrypt(v["x"], [int(r, 16) for r in v["r"]], tabs["P"], wide, wbitsQ=wbits) == g1s(par, v["out"])
+            assert S.encrypt(v["x"], small, tabs["P"], wide, wbitsQ=wbits) == [enc(x, r) for x, r in zip(v["x"], small)]
     got = S.encrypt(v["x"][:k], None, tabs["P"], tabs["Q"])  # EncryptDeterministic
     exp = [O.g1_mul(x, S.P, par.p) for x in v["x"][:k]]
     assert got == exp

@@ -27,13 +27,15 @@ def main():
     ap.add_argument("--key-bits", type=int, default=512)
     ap.add_argument("--emults", type=int, default=0, help="also time MultPoly of this many pairs")
     ap.add_argument("--d", type=int, default=D, help="coefficient slots per polynomial for --emults")
-    ap.add_argument("--enc-window", type=int, default=16, help="fixed-base window of Q: 8, 16 or 24 bits")
+    ap.add_argument("--enc-window", type=int, default=0, help="fixed-base window of Q: 0 (the default choice), 8, 16 .. 24 bits")
     args = ap.parse_args()
     with open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "kb%d.json" % args.key_bits)) as f:
         g = json.load(f)
     p, n, l, q1 = int(g["p"], 16), int(g["n"], 16), g["l"], int(g["q1"], 16)
     eng = Engine(p, n, l, bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]), device=0)
     eng.set_option("enc_window", args.enc_window)
+    if args.enc_window == 0:
+        args.enc_window = workmodel.enc_window_auto(eng.scalar_bytes, eng.limbs)
     L, EB, SB = eng.limbs, eng.elem_bytes, eng.scalar_bytes
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev)
