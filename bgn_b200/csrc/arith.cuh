@@ -399,6 +399,38 @@ struct Fp {
     }
   }
 
+  // The dot product with both multipliers streamed from memory (limb i at bp[i * ES]), as mul_stream does for
+  // the product: the multiplicands a0, a1 stay in registers.  Used by the Miller loop's line evaluation at a
+  // normalised point (fused.cuh: line_mul_n): cR * (1/yB) + aR * (xB/yB) in one pass.
+  template <int ES = 1>
+  BGN_DEV static void dot2_stream(uint32_t (&r)[L], const uint32_t (&a0)[L], const uint32_t* b0, const uint32_t (&a1)[L],
+                                  const uint32_t* b1) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    {
+      double A0 = BGN_GETB(a0), B0 = BGN_GETB(b0), A1 = BGN_GETB(a1), B1 = BGN_GETB(b1);
+      BGN_CHECK(2.0 * (A0 + A1 + 1.0) <= bgnsim::headroom, "dot product multiplicands too large");
+      BGN_CHECK(B0 <= bgnsim::headroom && B1 <= bgnsim::headroom, "dot product multiplier too large");
+      BGN_SETB(r, (A0 * B0 + A1 * B1) / bgnsim::headroom + 1.0);
+      bgnsim::ndot2++;
+    }
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row2<true>(X, Y, a0, b0[0], a1, b1[0], pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      row2<false>(Y, X, a0, b0[i * ES], a1, b1[i * ES], pm, np0);
+      row2<false>(X, Y, a0, b0[(i + 1) * ES], a1, b1[(i + 1) * ES], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row2<false>(Y, X, a0, b0[(L - 1) * ES], a1, b1[(L - 1) * ES], pm, np0);
+      merge(r, X, Y);
+    } else {
+      merge(r, Y, X);
+    }
+  }
+
   // Same product as mul_stream with the rows in a NON-unrolled loop of 2U rows per iteration (the
   // accumulators swap roles every row and move down one register pair every two rows, which a
   // loop pays for with ~2L register moves per iteration; unrolled code renames for free): 1 + 2U

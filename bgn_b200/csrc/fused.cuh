@@ -136,6 +136,72 @@ struct MF {
     st<L, ES>(fim, b);
   }
 
+  // ---- the line at a NORMALISED evaluation point (round 2).  F_p factors of a line value die in the
+  // final exponentiation, so the line may be divided by yB: with uB = xB / yB and vB = 1 / yB (one
+  // inversion per evaluation point, before the loop: MillerTeam::init)
+  //     l / yB = (cR vB + aR uB) + bI i
+  // -- the imaginary part is the line coefficient itself, and the real part is ONE dot product
+  // (arith.cuh: dot2_stream, 3L^2 + L) where the plain form spends two products (4L^2 + 2L):
+  // 8L^2 + 3L = 2363 products per line at L = 17 against 2669 (line_mul_lazy_n), 9L^2 + 4L against
+  // 10L^2 + 5L without lazy reduction (line_mul_n).  yB != 0: the only point of the curve with y = 0 is
+  // (0, 0), which the byte format reads as O.
+  // in: f.re, f.im < 8p; cR < 8p; aR < 64p; bI < 8p; uB, vB < 2p.   out: as line_mul / line_mul_lazy.
+  BGN_DEVNI static void line_mul_n(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
+                                   const uint32_t* uB, const uint32_t* vB) {
+    R a, l0, l1, t, u, v;
+    ld<L, ES>(a, vB);
+    ld<L, ES>(v, uB);
+    P::template dot2_stream<ES>(l0, a, cR, v, aR);  // l0 = cR vB + aR uB
+    ld<L, ES>(l1, bI);                              // l1 = bI
+    mulm(t, l0, fre);    // f0 l0
+    mulm(u, l1, fim);    // f1 l1
+    ld<L, ES>(a, fre);
+    ld<L, ES>(v, fim);
+    P::addn(a, a, v);
+    st<L, ES>(fre, a);       // f0 + f1 (f0 itself is dead)
+    P::addn(l0, l0, l1);
+    mulm(v, l0, fre);    // (f0 + f1)(l0 + l1)
+    P::subk(a, t, u, c_fc.p2, 2);
+    st<L, ES>(fre, a);       // f0 l0 - f1 l1
+    P::addn(t, t, u);
+    P::subk(v, v, t, c_fc.p4, 4);
+    st<L, ES>(fim, v);       // f0 l1 + f1 l0
+  }
+  template <int KM>
+  BGN_DEVNI static void line_mul_lazy_n(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,
+                                        const uint32_t* uB, const uint32_t* vB) {
+    R a, b, c, l0, l1;
+    uint32_t T0[2 * L], T1[2 * L], S[2 * L];
+    ld<L, ES>(a, vB);
+    ld<L, ES>(b, uB);
+    P::template dot2_stream<ES>(l0, a, cR, b, aR);  // l0 = cR vB + aR uB
+    ld<L, ES>(l1, bI);                              // l1 = bI
+    mulwk<KM>(T0, l0, fre);   // f0 l0
+    mulwk<KM>(T1, l1, fim);   // f1 l1
+    P::addw(S, T0, T1);
+    P::subw_k(T0, T0, T1, c_fc.p, 1);
+    P::redc(a, T0);           // re; stays in registers while the f.re slot feeds the last product
+    ld<L, ES>(b, fre);
+    ld<L, ES>(c, fim);
+    P::addn(b, b, c);
+    st<L, ES>(fre, b);            // f0 + f1
+    P::addn(l0, l0, l1);
+    mulwk<KM>(T1, l0, fre);   // (f0 + f1)(l0 + l1)
+    P::subw(T1, T1, S);       // = f0 l1 + f1 l0 >= 0
+    st<L, ES>(fre, a);
+    P::redc(b, T1);
+    st<L, ES>(fim, b);
+  }
+  // (xB, yB) -> (uB, vB) = (xB / yB, 1 / yB) in place: the inversion is the binary GCD of arith.cuh on the
+  // ALU pipe (F::inv_gcd), once per evaluation point and pairing batch.  in: canonical.  out: < 2p.
+  BGN_DEVNI static void eval_normalise(E xB, E yB) {
+    F<L>::template inv_gcd<true, ES>(yB, yB);
+    R x, y;
+    ld<L, ES>(x, xB);
+    mulm(y, x, yB);
+    st<L, ES>(xB, y);
+  }
+
   // A/B candidate (tools/primbench.py mode 83): line_mul_lazy with the two independent double-width
   // products f0 l0 and f1 l1 interleaved row by row (Fp::mulw2), and the two evaluation products likewise
   BGN_DEVNI static void line_mul_lazy_il(E fre, E fim, const uint32_t* cR, const uint32_t* aR, const uint32_t* bI,

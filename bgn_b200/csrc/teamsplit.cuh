@@ -91,6 +91,7 @@ struct MillerSplit {
     if (!einf) {
       FF::copy(cslot(col, C_EX), a.Ex + e * L);
       FF::copy(cslot(col, C_EY), a.Ey + e * L);
+      if (BGN_EVAL_NORM) MA::eval_normalise(cslot(col, C_EX), cslot(col, C_EY));  // (x / y, 1 / y): fused.cuh line_mul_n
     }
   }
 
@@ -131,13 +132,19 @@ struct MillerSplit {
         s = 1;
       }
       if (!flagsA()[base_col + i] || !flagsB()[base_col + k]) continue;
+      E fr = acc(tid, A_F0 + 2 * s), fi = acc(tid, A_F0 + 2 * s + 1);
+      const uint32_t *cR = cslot(base_col + i, C_CR), *aR = cslot(base_col + i, C_AR), *bI = cslot(base_col + i, C_BI);
+      const uint32_t *ex = cslot(base_col + k, C_EX), *ey = cslot(base_col + k, C_EY);
 #if BGN_LINE_LAZY
-      M::template line_mul_lazy<BGN_LINE_KARATSUBA>(acc(tid, A_F0 + 2 * s), acc(tid, A_F0 + 2 * s + 1), cslot(base_col + i, C_CR),
-                                                    cslot(base_col + i, C_AR), cslot(base_col + i, C_BI),
-                                                    cslot(base_col + k, C_EX), cslot(base_col + k, C_EY));
+      if (BGN_EVAL_NORM)
+        M::template line_mul_lazy_n<BGN_LINE_KARATSUBA>(fr, fi, cR, aR, bI, ex, ey);
+      else
+        M::template line_mul_lazy<BGN_LINE_KARATSUBA>(fr, fi, cR, aR, bI, ex, ey);
 #else
-      M::line_mul(acc(tid, A_F0 + 2 * s), acc(tid, A_F0 + 2 * s + 1), cslot(base_col + i, C_CR), cslot(base_col + i, C_AR),
-                  cslot(base_col + i, C_BI), cslot(base_col + k, C_EX), cslot(base_col + k, C_EY));
+      if (BGN_EVAL_NORM)
+        M::line_mul_n(fr, fi, cR, aR, bI, ex, ey);
+      else
+        M::line_mul(fr, fi, cR, aR, bI, ex, ey);
 #endif
     }
   }

@@ -82,23 +82,42 @@ def miller_unit_squarings(p: int, n: int, l: int, dM: int, dE: int) -> int:
     return D * dM * 6 + A * dM * 3 + (dM + dE - 1) * 2
 
 
-def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int) -> int:
+EVAL_NORM = True  # pairing.cuh BGN_EVAL_NORM: evaluation points normalised to (x / y, 1 / y) before the loop
+
+
+def line_products(L: int, eval_norm: bool = None) -> int:
+    """32x32->64 products of ONE line folded into an accumulator in the team kernels (fused.cuh).
+    Plain form: two evaluation products and an F_p^2 product -- 5 (2L^2 + L), or with lazy reduction
+    (up to 17 limbs) 2 (2L^2 + L) + 3 L^2 + 2 (L^2 + L).  At a normalised evaluation point (round 2) the
+    evaluation is one dot product of 3L^2 + L: 9L^2 + 4L, or 8L^2 + 3L with lazy reduction."""
+    eval_norm = EVAL_NORM if eval_norm is None else eval_norm
+    full = products_per_modmul(L)
+    ev = (3 * L * L + L) if eval_norm else 2 * full
+    return ev + (3 * L * L + 2 * (L * L + L) if line_lazy(L) else 3 * full)
+
+
+def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bool = None) -> int:
     """32x32->64 products one unit of k_miller executes.  Every F_p product is a fused
-    multiply-and-reduce of 2L^2 + L, except that the lazy-reduction line_mul (fused.cuh) spends
-    2 (2L^2 + L) + 3 L^2 + 2 (L^2 + L) on its 5 multiplications and 4 reductions, and that the
-    squarings (round 2) cost L (L + 1) / 2 + L^2 + L."""
+    multiply-and-reduce of 2L^2 + L, except the lines (line_products), the squarings where the
+    dedicated routine is used (L (L + 1) / 2 + L^2 + L), and -- with normalised evaluation points --
+    one inversion (its two products of glue) and one product per evaluation point before the loop."""
+    eval_norm = EVAL_NORM if eval_norm is None else eval_norm
     L = pick_limbs(p)
     mm = miller_unit_modmuls(p, n, l, dM, dE)
     nsq = miller_unit_squarings(p, n, l, dM, dE)
     full, sq = products_per_modmul(L), products_per_sqr(L)
-    if not line_lazy(L):
-        return (mm - nsq) * full + nsq * sq
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     lines = (D + A) * dM * dE
-    lazy = 2 * full + 3 * L * L + 2 * (L * L + L)
-    return (mm - 5 * lines - nsq) * full + lines * lazy + nsq * sq
+    prep = dE * (GCD_INV_MODMULS + 1) if eval_norm else 0
+    return (mm - 5 * lines - nsq + prep) * full + lines * line_products(L, eval_norm) + nsq * sq
+
+
+def miller_unit_lines(n: int, dM: int, dE: int) -> int:
+    """lines folded into accumulators by one unit of k_miller: one per (Miller point, evaluation point) and step"""
+    naf = naf_digits(n)
+    return (len(naf) - 1 + sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)) * dM * dE
 
 
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:

@@ -288,8 +288,10 @@ def test_work_model_matches_executed_products(kb):
     fused = lib.hs_mul_count(1)  # multiply-and-reduce products (2L^2 + L each)
     lib.hs_wide_count(wide, 1)   # double-width multiplications (L^2) and separate reductions (L^2 + L)
     L = S.L
-    executed = fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[4] * (L * (L + 1) // 2)
+    executed = (fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[3] * (3 * L * L + L)
+                + wide[4] * (L * (L + 1) // 2))
     assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
+    assert wide[3] == (workmodel.miller_unit_lines(par.n, v["d1"], v["d2"]) if workmodel.EVAL_NORM else 0)
     assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"])
     assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
