@@ -751,16 +751,28 @@ int miller_nsteps(const bgn_ctx* c) {
 }
 void ensure_linesP(bgn_ctx* c) {
   if (c->linesP || !c->fixed_lines) return;
-  uint32_t* tab = nullptr;
-  CK(cudaMalloc(&tab, (size_t)miller_nsteps(c) * 3 * c->L * 4));
+  const size_t words = (size_t)miller_nsteps(c) * 2 * c->L;
+  uint32_t *tab = nullptr, *scratch = nullptr;
+  int ok = 0;
   try {
+    CK(cudaMalloc(&tab, words * 4));
+    CK(cudaMalloc(&scratch, words * 4 + 256));
+    int* dok = reinterpret_cast<int*>(scratch + words);
     Timer t(c, "k_miller_record");
-    c->Co->miller_record(cfg(c, 1, 32, 0), c->dPx, c->dPy, tab);
+    c->Co->miller_record(cfg(c, 1, 32, 0), c->dPx, c->dPy, tab, scratch, dok);
     t.done();
+    CK(cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     finish(c);
   } catch (...) {
     cudaFree(tab);
+    cudaFree(scratch);
     throw;
+  }
+  cudaFree(scratch);
+  if (!ok) {  // P is not a point of odd order: no normalised table; e(., P) goes through the general kernel
+    cudaFree(tab);
+    c->fixed_lines = false;
+    return;
   }
   c->linesP = tab;
 }

@@ -192,6 +192,60 @@ struct MF {
     P::redc(b, T1);
     st<L, ES>(fim, b);
   }
+  // ---- the line of a RECORDED table (fixed first pairing argument: MillerFixed, pairing.cuh).  The table is
+  // normalised once per key, every line divided by its third coefficient (cRn = cR / bI, aRn = aR / bI):
+  //     l / bI = (cRn + aRn xB) + yB i
+  // one product for the real part, none for the imaginary part: 7L^2 + 3L = 2074 products per line at
+  // L = 17 with lazy reduction (line_mul_lazy_f), 4 (2L^2 + L) without (line_mul_f).
+  // in: f.re, f.im < 8p; cRn, aRn < 2p; xB, yB < 8p.   out: as line_mul / line_mul_lazy.
+  BGN_DEVNI static void line_mul_f(E fre, E fim, const uint32_t* cRn, const uint32_t* aRn, const uint32_t* xB,
+                                   const uint32_t* yB) {
+    R a, l0, l1, t, u, v;
+    ld<L, ES>(a, xB);
+    mulm(l0, a, aRn);
+    ld<L, ES>(a, cRn);
+    P::addn(l0, l0, a);  // l0 = cRn + aRn xB
+    ld<L, ES>(l1, yB);   // l1 = yB
+    mulm(t, l0, fre);    // f0 l0
+    mulm(u, l1, fim);    // f1 l1
+    ld<L, ES>(a, fre);
+    ld<L, ES>(v, fim);
+    P::addn(a, a, v);
+    st<L, ES>(fre, a);       // f0 + f1 (f0 itself is dead)
+    P::addn(l0, l0, l1);
+    mulm(v, l0, fre);    // (f0 + f1)(l0 + l1)
+    P::subk(a, t, u, c_fc.p2, 2);
+    st<L, ES>(fre, a);       // f0 l0 - f1 l1
+    P::addn(t, t, u);
+    P::subk(v, v, t, c_fc.p4, 4);
+    st<L, ES>(fim, v);       // f0 l1 + f1 l0
+  }
+  template <int KM>
+  BGN_DEVNI static void line_mul_lazy_f(E fre, E fim, const uint32_t* cRn, const uint32_t* aRn, const uint32_t* xB,
+                                        const uint32_t* yB) {
+    R a, b, c, l0, l1;
+    uint32_t T0[2 * L], T1[2 * L], S[2 * L];
+    ld<L, ES>(a, xB);
+    mulm(l0, a, aRn);
+    ld<L, ES>(a, cRn);
+    P::addn(l0, l0, a);       // l0 = cRn + aRn xB
+    ld<L, ES>(l1, yB);        // l1 = yB
+    mulwk<KM>(T0, l0, fre);   // f0 l0
+    mulwk<KM>(T1, l1, fim);   // f1 l1
+    P::addw(S, T0, T1);
+    P::subw_k(T0, T0, T1, c_fc.p, 1);
+    P::redc(a, T0);
+    ld<L, ES>(b, fre);
+    ld<L, ES>(c, fim);
+    P::addn(b, b, c);
+    st<L, ES>(fre, b);            // f0 + f1
+    P::addn(l0, l0, l1);
+    mulwk<KM>(T1, l0, fre);   // (f0 + f1)(l0 + l1)
+    P::subw(T1, T1, S);       // = f0 l1 + f1 l0 >= 0
+    st<L, ES>(fre, a);
+    P::redc(b, T1);
+    st<L, ES>(fim, b);
+  }
   // (xB, yB) -> (uB, vB) = (xB / yB, 1 / yB) in place: the inversion is the binary GCD of arith.cuh on the
   // ALU pipe (F::inv_gcd), once per evaluation point and pairing batch.  in: canonical.  out: < 2p.
   BGN_DEVNI static void eval_normalise(E xB, E yB) {

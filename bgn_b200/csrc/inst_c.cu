@@ -29,8 +29,8 @@ cudaError_t miller_fixed_set_smem(size_t smem) {
 }
 size_t miller_fixed_smem_bytes(int nt) { return MillerFixed<LL>::smem_words(nt) * 4; }
 void miller_fixed(LaunchCfg cfg, const MillerFixedArgs& a) { k_miller_fixed<LL><<<CFG>>>(a); }
-void miller_record(LaunchCfg cfg, const uint32_t* px, const uint32_t* py, uint32_t* lines) {
-  k_miller_record<LL><<<CFG>>>(px, py, lines);
+void miller_record(LaunchCfg cfg, const uint32_t* px, const uint32_t* py, uint32_t* lines, uint32_t* scratch, int* ok) {
+  k_miller_record<LL><<<CFG>>>(px, py, lines, scratch, ok);
 }
 const LOpsC ops = {LL,          upload,    gt_blind,
                    gt_tab_bases, gt_tab_fill, gt_polyconv,

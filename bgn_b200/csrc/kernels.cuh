@@ -1047,8 +1047,9 @@ __global__ void __launch_bounds__(256) k_pair_duo(const __grid_constant__ PairDu
 }
 
 template <int L>
-__global__ void __launch_bounds__(32) k_miller_record(const uint32_t* px, const uint32_t* py, uint32_t* lines) {
-  if (BGN_GID(size_t) == 0) MillerFixed<L>::record(px, py, lines);
+__global__ void __launch_bounds__(32) k_miller_record(const uint32_t* px, const uint32_t* py, uint32_t* lines,
+                                                      uint32_t* scratch, int* ok) {
+  if (BGN_GID(size_t) == 0) MillerFixed<L>::record(px, py, lines, scratch, ok);
 }
 
 // Register-resident Montgomery products: `iters` dependent modmuls per thread on

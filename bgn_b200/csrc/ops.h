@@ -48,7 +48,7 @@ struct LOpsC {
   cudaError_t (*miller_fixed_set_smem)(size_t smem);
   size_t (*miller_fixed_smem_bytes)(int nt);
   void (*miller_fixed)(LaunchCfg, const MillerFixedArgs&);
-  void (*miller_record)(LaunchCfg, const uint32_t* px, const uint32_t* py, uint32_t* lines);
+  void (*miller_record)(LaunchCfg, const uint32_t* px, const uint32_t* py, uint32_t* lines, uint32_t* scratch, int* ok);
 };
 
 // inst_d.cu: kernels that split one item over a pair of lanes (pairlane.cuh), added in round 2 for

@@ -371,20 +371,31 @@ struct MillerFixed {
     return n;
   }
 
-  // The line table of the affine point (px, py): the Miller loop's point arithmetic alone, one
-  // thread, [step][cR, aR, bI][L] (same step order as MillerTeam::run).
-  BGN_DEV static void record(const uint32_t* px, const uint32_t* py, uint32_t* lines) {
+  // The line table of the affine point (px, py): the Miller loop's point arithmetic alone, one thread, in
+  // the step order of MillerTeam::run, every line (cR, aR, bI) NORMALISED by its third coefficient:
+  // lines[step] = [cR / bI | aR / bI] -- F_p factors of a line value die in the final exponentiation, and
+  // the line at (xB, yB) becomes (cRn + aRn xB) + yB i (fused.cuh: line_mul_f).  The divisions share one
+  // inversion (Montgomery's trick over all steps); scratch holds [step][bI | prefix product].  *ok = 0 if
+  // some bI is zero -- only possible when (px, py) is not a point of odd order -- and the table is then
+  // unusable (api.cu falls back to the general kernel).
+  BGN_DEV static void record(const uint32_t* px, const uint32_t* py, uint32_t* lines, uint32_t* scratch, int* ok) {
     typedef F<L> FF;
-    Loc<L> X, Y, Z, cR, aR, bI;
+    Loc<L> X, Y, Z, cR, aR, bI, acc, t;
     FF::copy(X.v(), px);
     FF::copy(Y.v(), py);
     FF::copy(Z.v(), c_fc.one);
+    FF::copy(acc.v(), c_fc.one);
     const int n = c_pc.naf_len;
+    int ns = 0;
     auto emit = [&]() {
-      FF::copy(lines, cR.v());
-      FF::copy(lines + L, aR.v());
-      FF::copy(lines + 2 * L, bI.v());
-      lines += 3 * L;
+      uint32_t* ln = lines + (size_t)ns * 2 * L;
+      uint32_t* sc = scratch + (size_t)ns * 2 * L;
+      FF::copy(ln, cR.v());
+      FF::copy(ln + L, aR.v());
+      FF::copy(sc, bI.v());
+      FF::copy(sc + L, acc.v());
+      FF::mul(acc.v(), acc.v(), bI.v());
+      ns++;
     };
     for (int idx = 1; idx < n; idx++) {
       MA::dbl_line(X.v(), Y.v(), Z.v(), cR.v(), aR.v(), bI.v());
@@ -394,6 +405,17 @@ struct MillerFixed {
         MA::madd_line(X.v(), Y.v(), Z.v(), px, py, d < 0, cR.v(), aR.v(), bI.v());
         emit();
       }
+    }
+    *ok = FF::is_zero(acc.v()) ? 0 : 1;
+    if (!*ok) return;
+    FF::template inv_gcd<true>(acc.v(), acc.v());
+    for (int k = ns - 1; k >= 0; k--) {
+      uint32_t* ln = lines + (size_t)k * 2 * L;
+      uint32_t* sc = scratch + (size_t)k * 2 * L;
+      FF::mul(t.v(), acc.v(), sc + L);    // 1 / bI_k
+      FF::mul(acc.v(), acc.v(), sc);      // drop bI_k from the running inverse
+      FF::mul(ln, ln, t.v());
+      FF::mul(ln + L, ln + L, t.v());
     }
   }
 
@@ -415,11 +437,11 @@ struct MillerFixed {
     const int n = c_pc.naf_len;
     auto fold = [&]() {
 #if BGN_LINE_LAZY
-      M::template line_mul_lazy<BGN_LINE_KARATSUBA>(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+      M::template line_mul_lazy_f<BGN_LINE_KARATSUBA>(fr, fi, ln, ln + L, ex, ey);
 #else
-      M::line_mul(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+      M::line_mul_f(fr, fi, ln, ln + L, ex, ey);
 #endif
-      ln += 3 * L;
+      ln += 2 * L;
     };
     BGN_UNROLL1
     for (int idx = 1; idx < n; idx++) {

@@ -11,16 +11,20 @@
 // register-resident; nothing lives in shared or local memory.
 //
 //   e(C, P) through the recorded line table of P (MillerFixedPair; replaces k_miller_fixed below a
-//   batch-size threshold chosen by measurement, api.cu: run_miller_fixed).  Per Miller step, with
-//   the line (cR, aR, bI) of the table and the evaluation point (xB, yB):
+//   batch-size threshold chosen by measurement, api.cu: run_miller_fixed).  The table's lines are
+//   normalised by their third coefficient (pairing.cuh: MillerFixed::record), so the line of step k at
+//   the evaluation point (xB, yB) is l = (cRn_k + aRn_k xB) + yB i: only its real part costs a product,
+//   and it does not depend on the accumulator -- the two lanes evaluate the lines of TWO consecutive
+//   steps in one round:
 //
 //                       lane 0                              lane 1
+//     lines (every      l0_k = cRn_k + aRn_k xB            l0_k+1 = cRn_k+1 + aRn_k+1 xB      1 product each
+//      other step)
 //     f^2            (f0 + f1)(f0 - f1)                   2 f0 f1                  1 product each
-//     line           l0 = cR + aR xB                      l1 = bI yB               1 product each
-//     f * l          re = f0 l0 + (-f1) l1                im = f0 l1 + f1 l0       1 dot product each
+//     f * l          re = f0 l0 + (-f1) yB                im = f0 yB + f1 l0       1 dot product each
 //
-//   2 (2L^2 + L) + (3L^2 + L) = 2074 products per lane and doubling step at L = 17 against the
-//   3859 one thread spends (fused.cuh: sqr2 + line_mul_lazy), three shuffle exchanges per step.
+//   1.5 (2L^2 + L) + (3L^2 + L) = 1776 products per lane and doubling step at L = 17 against the
+//   3264 one thread spends (fused.cuh: sqr2 + line_mul_lazy_f), 2.5 shuffle exchanges per step.
 //   The dot product (arith.cuh: Fp::dot2) accumulates both multiplicands row by row into one CIOS
 //   window, so the F_p^2 product needs no double-width temporaries.
 //
@@ -36,16 +40,18 @@ struct MillerFixedPair {
   typedef Lucas<L> LU;
   struct State {
     uint32_t f0[L], f1[L];  // accumulator, both coordinates in both lanes (relaxed range, below 4p)
-    uint32_t e[L];          // lane 0: xB, lane 1: yB
+    uint32_t ex[L], ey[L];  // the evaluation point, in both lanes
   };
 
   BGN_DEV static void init(State& st, const uint32_t* ex, const uint32_t* ey, int s, bool active) {
     if (active) {
-      ld<L>(st.e, s == 0 ? ex : ey);
+      ld<L>(st.ex, ex);
+      ld<L>(st.ey, ey);
     } else {
-      BGN_SETB(st.e, 0.0);
+      BGN_SETB(st.ex, 0.0);
+      BGN_SETB(st.ey, 0.0);
       BGN_UNROLL
-      for (int j = 0; j < L; j++) st.e[j] = 0;
+      for (int j = 0; j < L; j++) st.ex[j] = st.ey[j] = 0;
     }
     ld<L>(st.f0, c_fc.one);
     BGN_SETB(st.f1, 0.0);
@@ -63,16 +69,11 @@ struct MillerFixedPair {
     P::addn(d, t, t);
     LU::sel(t, s == 0, t, d);  // lane 1 holds 2 f0 f1
   }
-  // this lane's coordinate of the line (cR, aR, bI) at the evaluation point: lane 0 cR + aR xB,
-  // lane 1 bI yB.  ln points at the step's [cR | aR | bI] in the table.  out: < 8p.
-  BGN_DEV static void eval_half(uint32_t (&t)[L], const State& st, const uint32_t* ln, int s) {
-    uint32_t c[L], z[L];
-    P::mul_stream(t, st.e, ln + (s == 0 ? L : 2 * L));
+  // real part of the normalised line ln = [cRn | aRn] at the evaluation point: cRn + aRn xB.  out: < 4p.
+  BGN_DEV static void eval_line(uint32_t (&t)[L], const State& st, const uint32_t* ln) {
+    uint32_t c[L];
+    P::mul_stream(t, st.ex, ln + L);
     ld<L>(c, ln);
-    BGN_SETB(z, 0.0);
-    BGN_UNROLL
-    for (int j = 0; j < L; j++) z[j] = 0;
-    LU::sel(c, s == 0, c, z);
     P::addn(t, t, c);
   }
   // this lane's coordinate of f * (l0 + l1 i), `mine` being the coordinate of l this lane evaluated:
@@ -153,7 +154,10 @@ struct MillerFixedPair {
     init(st, a.Ex + ee * L, a.Ey + ee * L, s, active && !inf);
     const uint32_t* ln = a.lines;
     const int n = c_pc.naf_len;
-    uint32_t mine[L], other[L], lm[L], lo[L];
+    int left = 0;  // lines still to fold
+    for (int idx = 1; idx < n; idx++) left += (c_pc.naf[idx] != 0 && idx != n - 1) ? 2 : 1;
+    uint32_t mine[L], other[L], lm[L], lo[L], cur[L], nxt[L];
+    bool have = false;  // nxt holds the real part of the next line (uniform over the batch: one key)
     BGN_UNROLL1
     for (int idx = 1; idx < n; idx++) {
       const int folds = (c_pc.naf[idx] != 0 && idx != n - 1) ? 2 : 1;
@@ -164,12 +168,24 @@ struct MillerFixedPair {
       }
       BGN_UNROLL1
       for (int k = 0; k < folds; k++) {
-        eval_half(lm, st, ln, s);
-        xchg(lo, lm);
+        if (!have) {  // lane 0 evaluates this line, lane 1 the next one (the last line: both this one)
+          eval_line(lm, st, ln + (left > 1 ? s : 0) * 2 * L);
+          xchg(lo, lm);
+          LU::sel(cur, s == 0, lm, lo);
+          LU::sel(nxt, s == 0, lo, lm);
+          have = left > 1;
+        } else {
+          LU::sel(cur, true, nxt, nxt);
+          have = false;
+        }
+        // l = cur + yB i: lane 0 multiplies by (cur, yB), lane 1 by (yB, cur)
+        LU::sel(lm, s == 0, cur, st.ey);
+        LU::sel(lo, s == 0, st.ey, cur);
         mul_half(mine, st, lm, lo, s);
         xchg(other, mine);
         update(st, mine, other, s);
-        ln += 3 * L;
+        ln += 2 * L;
+        left--;
       }
     }
     fe_sq(mine, st, s);

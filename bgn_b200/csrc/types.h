@@ -59,7 +59,7 @@ struct MillerArgs {
 // squares its accumulator and folds in the line evaluated at its own point: 2 + 5 products per
 // step instead of 12..13 + 2 + 5, no inter-thread traffic, no barriers.
 struct MillerFixedArgs {
-  const uint32_t* lines;  // [nsteps][3][L]
+  const uint32_t* lines;  // [nsteps][2][L]: cR / bI, aR / bI of every line (pairing.cuh: MillerFixed::record)
   const uint32_t *Ex, *Ey;  // evaluation points, affine Montgomery [count][L]
   const uint8_t* Einf;
   uint32_t *out_re, *out_im;  // [count][L]

@@ -134,15 +134,16 @@ def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
 
 
 def miller_fixed_products(p: int, n: int, l: int) -> int:
-    """32x32->64 products of one k_miller_fixed thread (pairing with the recorded line table of a
-    fixed first argument): per step one line_mul (lazy up to 17 limbs) and, on doubling steps after
-    the first, one sqr2; then the final exponentiation of one slot."""
+    """32x32->64 products of one k_miller_fixed thread (pairing with the recorded, normalised line table
+    of a fixed first argument): per step one line (fused.cuh: line_mul_lazy_f up to 17 limbs -- one
+    evaluation product, three double-width products, two reductions -- else line_mul_f, 4 products) and,
+    on doubling steps after the first, one sqr2; then the final exponentiation of one slot."""
     L = pick_limbs(p)
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     full = products_per_modmul(L)
-    line = (2 * full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 5 * full
+    line = (full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 4 * full
     nsq = 2 if fused_sqr(L) else 0  # fe_prepare: f0^2, f1^2
     return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1) - nsq) * full + nsq * products_per_sqr(L)
 
@@ -150,15 +151,16 @@ def miller_fixed_products(p: int, n: int, l: int) -> int:
 def miller_fixed_pair_counts(p: int, n: int, l: int):
     """k_miller_fixed_pair (pairlane.cuh), BOTH lanes of one pairing together:
     -> (dot products, plain Montgomery products incl. the inversion's glue).
-    Per step a line evaluation half and a dot-product half per lane, a squaring half per lane on
-    doubling steps after the first; final exponentiation: f0^2 | f1^2, f0 f1 and the scaling in both
-    lanes, the verified inversion (3 products) in both lanes, then g^l."""
+    Per step a dot-product half per lane, per TWO steps one line evaluation per lane (the table is
+    normalised: only the real part of a line costs a product, and the lanes evaluate two consecutive lines
+    at once), a squaring half per lane on doubling steps after the first; final exponentiation: f0^2 | f1^2,
+    f0 f1 and the scaling in both lanes, the verified inversion (3 products) in both lanes, then g^l."""
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     lb, lw = l.bit_length() - 1, bin(l).count("1") - 1
     dots = 2 * (D + A) + 2 * lw
-    muls = 2 * (D + A) + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
+    muls = 2 * ((D + A + 1) // 2) + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
     return dots, muls
 
 

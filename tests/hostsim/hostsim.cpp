@@ -243,8 +243,8 @@ int hs_miller_fixed_pair(int L, const MillerFixedArgs* a) {
   })
 }
 int hs_pair_duo(int L, const PairDuoArgs* a, int np) { FOR_L(L, sim_pair_duo<LL>(*a, np)) }
-int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* lines) {
-  FOR_L(L, MillerFixed<LL>::record(px, py, lines))
+int hs_miller_record(int L, const uint32_t* px, const uint32_t* py, uint32_t* lines, uint32_t* scratch, int* ok) {
+  FOR_L(L, MillerFixed<LL>::record(px, py, lines, scratch, ok))
 }
 int hs_miller_nsteps(int L) { FOR_L(L, return MillerFixed<LL>::nsteps(c_pc)) }
 int hs_gt_pow_pair(int L, const GtPowArgs* a) { FOR_L(L, for (size_t e = 0; e < a->count; e++) gt_pow_pair_sim<LL>(*a, e)) }

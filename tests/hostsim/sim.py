@@ -291,10 +291,12 @@ class Sim:
         nsteps = lib().hs_miller_nsteps(self.L)
         ns = naf_digits(self.par.n)
         assert nsteps == sum(1 + (1 if (ns[i] != 0 and i != len(ns) - 1) else 0) for i in range(1, len(ns)))
-        lines = np.zeros(nsteps * 3 * self.L, dtype=np.uint32)
+        lines = np.zeros(nsteps * 2 * self.L, dtype=np.uint32)  # [step][cR / bI | aR / bI]
+        scratch = np.zeros_like(lines)
+        ok = C.c_int(0)
         bx, by = self.soa([base[0]]), self.soa([base[1]])
-        assert lib().hs_miller_record(self.L, P32(bx), P32(by), P32(lines)) == 0
-        return lines
+        assert lib().hs_miller_record(self.L, P32(bx), P32(by), P32(lines), P32(scratch), C.byref(ok)) == 0
+        return lines if ok.value else None
 
     def pair_fixed(self, lines, Epts, nt=4):
         """k_miller_fixed: e(E[i], base) through the recorded line table"""
