@@ -144,13 +144,16 @@ struct bgn_ctx {
   uint32_t *dPx = nullptr, *dPy = nullptr, *dQx = nullptr, *dQy = nullptr;
   uint8_t *dPinf = nullptr, *dQinf = nullptr;
   uint32_t *tabP = nullptr, *tabQ = nullptr;
+  uint32_t* tabPe = nullptr;   // tabP as twisted Edwards points (u | v | u v), 3L words per entry (curve.cuh: Ed)
+  bool enc_edwards = true;     // Encrypt sums table points in Edwards form (option enc_edwards; cleared if P or Q has even order)
+  bool tabQw_edw = false;      // tabQw holds Edwards points
   uint32_t* tabQw = nullptr;   // 16- or 24-bit windows of Q, built on the first randomised encryption
   int tabQw_bits = 0;
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
   int enc_window = 0;          // window bits of Q's table: 0 = widest of 16/18/20 within enc_table_max; 8 | 16 | 18 | 20 | 22 | 24 (BGN_ENC_WINDOW)
-  size_t enc_table_max = (size_t)4 << 30;  // bound of the automatic choice (option enc_table_max_mb)
+  size_t enc_table_max = (size_t)6 << 30;  // bound of the automatic choice (option enc_table_max_mb)
   int norm_per_thread = 8;     // lower bound of elements per inversion in k_normalize (BGN_NORM_PER_THREAD)
   int norm_threads = 148 * 256;  // threads k_normalize aims at (BGN_NORM_THREADS)
   bool affine_add = true;      // EAdd / ESub / Neg in affine coordinates with shared inversions (BGN_AFFINE_ADD=0: Jacobian + normalise)
@@ -861,7 +864,24 @@ void build_table(bgn_ctx* c, const uint32_t* bx, const uint32_t* by, int nwin, u
 // (the default) takes the widest of 16 / 18 / 20 bits whose table stays within enc_table_max bytes
 // (4 GiB); a table that does not fit the free memory falls back to 16 bits.
 size_t tabQw_bytes(const bgn_ctx* c, int bits) {
-  return (size_t)((8 * c->nbytes + bits - 1) / bits) * (((size_t)1 << bits) - 1) * 2 * (size_t)c->L * 4;
+  const size_t per_entry = (c->enc_edwards && c->tabPe ? 3 : 2) * (size_t)c->L * 4;
+  return (size_t)((8 * c->nbytes + bits - 1) / bits) * (((size_t)1 << bits) - 1) * per_entry;
+}
+// Weierstrass table (x || y per entry) -> Edwards table (u || v || u v); returns false if some finite entry
+// has no Edwards image (the base point is not of odd order)
+bool table_to_edwards(bgn_ctx* c, const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, int* dbad, size_t count) {
+  if (!count) return true;
+  CK(cudaMemsetAsync(dbad, 0, sizeof(int), c->stream));
+  size_t G = shared_inversion_threads(c, count);
+  {
+    Timer t(c, "k_tab_edwards");
+    c->Bo->tab_edwards(cfg(c, nblk(G, 128), 128, 0), tabw, tabe, scratch, count, (int)G, dbad);
+    t.done();
+  }
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  finish(c);
+  return bad == 0;
 }
 int enc_window_auto(const bgn_ctx* c) {
   for (int bits = 20; bits > 16; bits -= 2)
@@ -871,6 +891,7 @@ int enc_window_auto(const bgn_ctx* c) {
 void ensure_tabQw(bgn_ctx* c) {
   if (c->tabQw || c->enc_window == 8) return;
   int wbits = c->enc_window ? c->enc_window : enc_window_auto(c);
+  const bool edw = c->enc_edwards && c->tabPe;
   size_t ew = (size_t)c->L * 4;
   const size_t chunk_max = (size_t)1 << 22;
   if (wbits > 16) {
@@ -878,7 +899,7 @@ void ensure_tabQw(bgn_ctx* c) {
     CK(cudaMemGetInfo(&free_b, &total_b));
     // leave room for the callers' batches next to the table (a quarter of it, at least 1 GiB, at most 16)
     size_t room = std::min<size_t>((size_t)16 << 30, std::max<size_t>((size_t)1 << 30, tabQw_bytes(c, wbits) / 4));
-    if (tabQw_bytes(c, wbits) + chunk_max * 4 * ew + room > free_b) wbits = 16;
+    if (tabQw_bytes(c, wbits) + chunk_max * 6 * ew + room > free_b) wbits = 16;
   }
   const int nsub = wbits % 8 == 0 ? wbits / 8 : 2;
   const int hb = wbits / nsub;
@@ -887,9 +908,10 @@ void ensure_tabQw(bgn_ctx* c) {
   const size_t nent = (size_t)nwin * ents;
   const size_t chunk = std::min(nent, chunk_max);
   uint32_t *tab = nullptr, *tmp = nullptr, *narrow = nullptr;
+  bool ok = true;
   try {
-    CK(cudaMalloc(&tab, nent * 2 * ew));
-    CK(cudaMalloc(&tmp, chunk * 4 * ew));
+    CK(cudaMalloc(&tab, nent * (edw ? 3 : 2) * ew));
+    CK(cudaMalloc(&tmp, chunk * (edw ? 6 : 4) * ew + 256));
     const uint32_t* tabh = c->tabQ;
     int nwin_h = c->nbytes;
     if (hb != 8) {
@@ -915,15 +937,22 @@ void ensure_tabQw(bgn_ctx* c) {
     j.Z = tmp + 2 * chunk * c->L;
     j.N = chunk;
     uint32_t* scratch = tmp + 3 * chunk * c->L;
-    for (size_t first = 0; first < nent; first += chunk) {
+    uint32_t* aff = tmp + 4 * chunk * c->L;                       // Edwards build: the chunk's affine points
+    int* dbad = reinterpret_cast<int*>(tmp + (edw ? 6 : 4) * chunk * c->L);
+    for (size_t first = 0; first < nent && ok; first += chunk) {
       size_t cnt = std::min(chunk, nent - first);
       {
         Timer t(c, "k_tabw_fill");
         c->Bo->tabw_fill(cfg(c, nblk(cnt, 128), 128, 0), tabh, nwin_h, nsub, hb, j.X, j.Y, j.Z, first, cnt);
         t.done();
       }
-      uint32_t* dst = tab + first * 2 * c->L;
-      normalize(c, j, cnt, scratch, dst, dst + c->L, 2 * (size_t)c->L, 1, nullptr);
+      if (edw) {
+        normalize(c, j, cnt, scratch, aff, aff + c->L, 2 * (size_t)c->L, 1, nullptr);
+        ok = table_to_edwards(c, aff, tab + first * 3 * c->L, scratch, dbad, cnt);
+      } else {
+        uint32_t* dst = tab + first * 2 * c->L;
+        normalize(c, j, cnt, scratch, dst, dst + c->L, 2 * (size_t)c->L, 1, nullptr);
+      }
     }
     finish(c);
   } catch (...) {
@@ -934,8 +963,25 @@ void ensure_tabQw(bgn_ctx* c) {
   }
   CK(cudaFree(tmp));
   if (narrow) CK(cudaFree(narrow));
+  if (!ok) {  // Q is not of odd order: stay with Weierstrass tables
+    cudaFree(tab);
+    c->enc_edwards = false;
+    ensure_tabQw(c);
+    return;
+  }
   c->tabQw = tab;
   c->tabQw_bits = wbits;
+  c->tabQw_edw = edw;
+}
+// tables, window width and form for one Encrypt / re-randomisation launch
+void enc_tables(bgn_ctx* c, EncArgs& ea, bool randomised) {
+  if (randomised) ensure_tabQw(c);
+  const bool wide = randomised && c->tabQw;
+  const bool edw = wide ? c->tabQw_edw : (!randomised && c->enc_edwards && c->tabPe);
+  ea.tabP = edw ? c->tabPe : c->tabP;
+  ea.tabQ = wide ? c->tabQw : c->tabQ;
+  ea.wbitsQ = wide ? c->tabQw_bits : 8;
+  ea.edw = edw ? 1 : 0;
 }
 
 // Fixed-base table of E = e(Q,Q) for the level-2 re-randomisation `* e(Q,Q)^r` (bgn.go:283-287,
@@ -1004,6 +1050,7 @@ void ctx_free(bgn_ctx* c) {
   cudaFree(c->dPx);
   cudaFree(c->dPinf);
   cudaFree(c->tabP);
+  cudaFree(c->tabPe);
   cudaFree(c->tabQ);
   cudaFree(c->tabQw);
   cudaFree(c->tabE);
@@ -1143,6 +1190,7 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
       int w = atoi(ew);
       c->enc_window = (w == 8 || (w >= 16 && w <= 24 && w % 2 == 0)) ? w : 0;
     }
+    if (const char* ee = getenv("BGN_ENC_EDWARDS")) c->enc_edwards = atoi(ee) != 0;
     if (const char* dl = getenv("BGN_DEC_LUCAS")) c->dec_lucas = atoi(dl) != 0;
     if (const char* af = getenv("BGN_AFFINE_ADD")) c->affine_add = atoi(af) != 0;
     if (const char* np = getenv("BGN_NORM_PER_THREAD")) c->norm_per_thread = std::max(1, atoi(np));
@@ -1287,6 +1335,25 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     CK(cudaMalloc(&c->tabQ, tabQ_words * 4));
     build_table(c, c->dPx, c->dPy, 8, c->tabP);
     build_table(c, c->dQx, c->dQy, c->nbytes, c->tabQ);
+    if (c->enc_edwards) {  // P's table in Edwards form (Q's wide table is built on the first randomised encryption)
+      const size_t nP = (size_t)8 * 255;
+      uint32_t* scr = nullptr;
+      CK(cudaMalloc(&c->tabPe, nP * 3 * L * 4));
+      CK(cudaMalloc(&scr, nP * L * 4 + 256));
+      bool ok = false;
+      try {
+        ok = table_to_edwards(c, c->tabP, c->tabPe, scr, reinterpret_cast<int*>(scr + nP * L), nP);
+      } catch (...) {
+        cudaFree(scr);
+        throw;
+      }
+      cudaFree(scr);
+      if (!ok) {
+        cudaFree(c->tabPe);
+        c->tabPe = nullptr;
+        c->enc_edwards = false;
+      }
+    }
     *out = c;
     return BGN_OK;
   } catch (const CudaErr& e) {
@@ -1340,6 +1407,16 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
       c->tabQw_bits = 0;
     }
     c->enc_window = (int)value;
+  } else if (k == "enc_edwards") {
+    const bool on = value != 0 && c->tabPe != nullptr;
+    if (on != c->enc_edwards) {
+      cudaSetDevice(c->device);
+      if (c->stream) cudaStreamSynchronize(c->stream);
+      cudaFree(c->tabQw);
+      c->tabQw = nullptr;
+      c->tabQw_bits = 0;
+    }
+    c->enc_edwards = on;
   } else if (k == "enc_table_max_mb") {
     c->enc_table_max = (size_t)std::max<long>(0, value) << 20;
     if (c->enc_window == 0 && c->tabQw) {
@@ -1403,10 +1480,7 @@ int bgn_encrypt_batch(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t 
     ea.x = dx;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
-    if (dr) ensure_tabQw(c);
-    ea.tabP = c->tabP;
-    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
-    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
+    enc_tables(c, ea, dr != nullptr);
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;
@@ -1765,14 +1839,11 @@ int bgn_g1_blind_batch(bgn_ctx* c, const uint8_t* a, const uint8_t* r_be, size_t
     g1_from_bytes(c, da, count, A);
     JacArr j = jac_alloc(c, count);
     uint32_t* scratch = arena_get<uint32_t>(c, count * c->L);
-    ensure_tabQw(c);
     EncArgs ea;
     ea.x = nullptr;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
-    ea.tabP = c->tabP;
-    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
-    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
+    enc_tables(c, ea, true);
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;
@@ -2274,10 +2345,7 @@ int bgn_encrypt_h(bgn_ctx* c, const int64_t* x, const uint8_t* r_be, size_t coun
     ea.x = dx;
     ea.r_be = dr;
     ea.rbytes = c->nbytes;
-    if (dr) ensure_tabQw(c);
-    ea.tabP = c->tabP;
-    ea.tabQ = c->tabQw ? c->tabQw : c->tabQ;
-    ea.wbitsQ = c->tabQw ? c->tabQw_bits : 8;
+    enc_tables(c, ea, dr != nullptr);
     ea.X = j.X;
     ea.Y = j.Y;
     ea.Z = j.Z;

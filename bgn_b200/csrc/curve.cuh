@@ -173,3 +173,69 @@ struct G {
     return FF::equal(t0, t1);
   }
 };
+
+// ---------------------------------------------------------------------------------------------------
+// The same group in twisted Edwards form, for the fixed-base sums of Encrypt (round 2).
+//
+// y^2 = x^3 + x is the Montgomery curve B y^2 = x^3 + A x^2 + x with A = 0, B = 1, hence birationally
+// equivalent to the twisted Edwards curve  a u^2 + v^2 = 1 + d u^2 v^2  with a = (A + 2) / B = 2,
+// d = (A - 2) / B = -2  through  (u, v) = (x / y, (x - 1) / (x + 1)),  x = (1 + v) / (1 - v), y = x / u;
+// O <-> (0, 1).  The map is a group isomorphism away from the points of order dividing 4; G1 has odd
+// order n, and on points of odd order the unified addition law below has no exceptional cases (they
+// all involve a point of even order), so it needs no branches for P + P, P - P or the identity.
+//
+// Extended coordinates (U : V : Z : T), u = U / Z, v = V / Z, T = U V / Z, and a table point given
+// affinely as (u2, v2, t2 = u2 v2) [Hisil-Wong-Carter-Dawson 2008, unified mixed addition]:
+//     A = U u2, B = V v2, C = d T t2, E = (U + V)(u2 + v2) - A - B, F = Z - C, G = Z + C, H = B - a A,
+//     U3 = E F, V3 = G H, T3 = E H, Z3 = F G
+// 8 products where the complete mixed Jacobian addition of G<L>::madd spends 8 products + 3 squarings
+// and two zero tests.  a A = 2A and d T t2 = -2 T t2 are additions.
+// libpbc has no such form; the results leave this file as Jacobian Weierstrass points (to_jac), so
+// the bytes Encrypt returns are the ones curve.c produces (bgn.go:340-353).
+template <int L>
+struct Ed {
+  typedef F<L> FF;
+  // (U, V, Z, T) <- (U, V, Z, T) + (ent[0..L), ent[L..2L), t = ent[2L..3L)).  t0..t3 scratch.
+  BGN_DEVNI static void madd(E U, E V, E Z, E T, const uint32_t* ent, E t0, E t1, E t2, E t3) {
+    const uint32_t *u2 = ent, *v2 = ent + L, *tt = ent + 2 * L;
+    FF::mul(t0, U, u2);    // A
+    FF::mul(t1, V, v2);    // B
+    FF::mul(t2, T, tt);
+    FF::add(t2, t2, t2);   // -C = 2 T t2
+    FF::add(t3, U, V);
+    FF::add(T, u2, v2);
+    FF::mul(t3, t3, T);
+    FF::sub(t3, t3, t0);
+    FF::sub(t3, t3, t1);   // E
+    FF::add(U, Z, t2);     // F = Z - C
+    FF::sub(V, Z, t2);     // G = Z + C
+    FF::add(t0, t0, t0);
+    FF::sub(t1, t1, t0);   // H = B - 2A
+    FF::mul(Z, U, V);      // Z3 = F G
+    FF::mul(T, t3, t1);    // T3 = E H
+    FF::mul(U, t3, U);     // U3 = E F
+    FF::mul(V, V, t1);     // V3 = G H
+  }
+  // first term of a sum: the table point itself
+  BGN_DEVNI static void set(E U, E V, E Z, E T, const uint32_t* ent) {
+    FF::copy(U, ent);
+    FF::copy(V, ent + L);
+    FF::set_one(Z);
+    FF::copy(T, ent + 2 * L);
+  }
+  // Jacobian Weierstrass (X, Y, Zj) of the extended point (U, V, Z, .): with D = (Z - V) U,
+  // x = (Z + V) U / D, y = (Z + V) Z / D, so Zj = D, X = (Z + V) U D, Y = (Z + V) Z D^2.  6 products.
+  // The identity (U = 0, V = Z) gives Zj = 0 = O.  U, V, Z are overwritten with the result.
+  BGN_DEVNI static void to_jac(E U, E V, E Z, E t0, E t1, E t2) {
+    FF::sub(t0, Z, V);
+    FF::add(t1, Z, V);
+    FF::mul(t0, t0, U);    // D
+    FF::mul(t2, t1, U);    // (Z + V) U
+    FF::mul(t1, t1, Z);    // (Z + V) Z
+    FF::mul(U, t2, t0);    // X
+    FF::sqr(t2, t0);       // D^2
+    FF::mul(V, t1, t2);    // Y
+    FF::copy(Z, t0);       // Zj
+  }
+};
+

@@ -37,10 +37,13 @@ void tabw_fill(LaunchCfg cfg, const uint32_t* tabh, int nwin_h, int nsub, int hb
                size_t first, size_t nent) {
   k_tabw_fill<LL><<<CFG>>>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent);
 }
+void tab_edwards(LaunchCfg cfg, const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, size_t count, int G, int* bad) {
+  k_tab_edwards<LL><<<CFG>>>(tabw, tabe, scratch, count, G, bad);
+}
 void g1_polyconv(LaunchCfg cfg, const PolyConvArgs& a) { k_g1_polyconv<LL><<<CFG>>>(a); }
 void g1_affadd(LaunchCfg cfg, const G1AffAddArgs& a) { k_g1_affadd<LL><<<CFG>>>(a); }
 const LOpsB ops = {LL,     upload,    g1_from_bytes, g1_to_bytes, encrypt,    normalize,
-                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tabw_fill,  g1_polyconv, g1_affadd};
+                   g1_add, g1_mulvar, tab_bases,     tab_fill,    tabw_fill,  tab_edwards, g1_polyconv, g1_affadd};
 }  // namespace
 #define BGN_CAT2(a, b) a##b
 #define BGN_CAT(a, b) BGN_CAT2(a, b)

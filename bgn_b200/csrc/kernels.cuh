@@ -146,47 +146,87 @@ BGN_DEV void fp2_to_bytes_body(const uint32_t* re, const uint32_t* im, size_t N,
 // Montgomery, AoS: tab[(win*255 + d-1) * 2L + {0..L-1: x, L..2L-1: y}].
 // C = x*P + r*Q  (EncryptWithRandomness, bgn.go:340-353), x < 0: C = -(|x|*P + r*Q); Jacobian out.
 template <int L>
+BGN_DEV uint32_t enc_digit(const uint8_t* r, int rbytes, int win, int wbits) {
+  const int bit = win * wbits;            // offset of the digit from the least significant bit of r
+  const int lo = rbytes - 1 - (bit >> 3);
+  uint32_t v = r[lo];                     // four bytes cover 7 + 24 bits
+  for (int k = 1; k < 4; k++)
+    if (lo - k >= 0) v |= (uint32_t)r[lo - k] << (8 * k);
+  return (v >> (bit & 7)) & ((1u << wbits) - 1u);
+}
+template <int L>
 BGN_DEV void encrypt_body(const EncArgs& a, size_t e) {
   typedef F<L> FF;
   if (e >= a.count) return;
   Loc<L> X, Y, Z, t0, t1, t2, t3;
-  FF::set_zero(X.v());
-  FF::set_zero(Y.v());
-  FF::set_zero(Z.v());
-  if (a.bx && !a.binf[e]) {  // re-randomisation: start from the ciphertext instead of O
-    FF::copy(X.v(), a.bx + e * L);
-    FF::copy(Y.v(), a.by + e * L);
-    FF::set_one(Z.v());
-  }
-  if (a.r_be) {
-    // fixed-base windows of wbitsQ bits (8 .. 24, any width): one complete mixed addition per non-zero
-    // window digit.  The wide tables (2^wbitsQ - 1 points per window: 285 MB at 16 bits, 3.7 GB at 20,
-    // 50 GB at 24 for 512-bit keys) live in HBM and each lookup is one 8L-byte read at a random address.
-    const uint8_t* r = a.r_be + e * a.rbytes;
-    const int wbits = a.wbitsQ;
-    const size_t ents = ((size_t)1 << wbits) - 1;
-    const int nw = (8 * a.rbytes + wbits - 1) / wbits;
+  int64_t xs = a.x ? a.x[e] : 0;
+  bool neg = xs < 0;
+  uint64_t xm = neg ? (uint64_t)(-(xs + 1)) + 1u : (uint64_t)xs;
+  // fixed-base windows of wbitsQ bits (8 .. 24, any width): one table point added per non-zero window digit
+  // of r, plus one per non-zero byte of |x|.  The wide tables (2^wbitsQ - 1 points per window: 285 MB at 16
+  // bits, 3.7 GB at 20, 50 GB at 24 for 512-bit keys and Weierstrass points) live in HBM and each lookup is
+  // one read of an entry at a random address.
+  const int wbits = a.wbitsQ;
+  const size_t ents = ((size_t)1 << wbits) - 1;
+  const int nw = a.r_be ? (8 * a.rbytes + wbits - 1) / wbits : 0;
+  const uint8_t* r = a.r_be ? a.r_be + e * a.rbytes : nullptr;
+  if (a.edw) {
+    // twisted Edwards form (curve.cuh: Ed): 8 products per table point, no special cases; the sum is
+    // converted to Jacobian Weierstrass coordinates (6 products) before the starting point, if any, is added
+    Loc<L> T;
+    bool started = false;
     for (int win = 0; win < nw; win++) {
-      const int bit = win * wbits;            // offset of the digit from the least significant bit of r
-      const int lo = a.rbytes - 1 - (bit >> 3);
-      uint32_t v = r[lo];                     // four bytes cover 7 + 24 bits
-      for (int k = 1; k < 4; k++)
-        if (lo - k >= 0) v |= (uint32_t)r[lo - k] << (8 * k);
-      const uint32_t d = (v >> (bit & 7)) & (uint32_t)ents;
+      const uint32_t d = enc_digit<L>(r, a.rbytes, win, wbits);
+      if (!d) continue;
+      const uint32_t* ent = a.tabQ + ((size_t)win * ents + (d - 1)) * 3 * L;
+      if (started)
+        Ed<L>::madd(X.v(), Y.v(), Z.v(), T.v(), ent, t0.v(), t1.v(), t2.v(), t3.v());
+      else
+        Ed<L>::set(X.v(), Y.v(), Z.v(), T.v(), ent);
+      started = true;
+    }
+    for (int win = 0; win < 8; win++) {
+      const uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
+      if (!d) continue;
+      const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 3 * L;
+      if (started)
+        Ed<L>::madd(X.v(), Y.v(), Z.v(), T.v(), ent, t0.v(), t1.v(), t2.v(), t3.v());
+      else
+        Ed<L>::set(X.v(), Y.v(), Z.v(), T.v(), ent);
+      started = true;
+    }
+    if (started) {
+      Ed<L>::to_jac(X.v(), Y.v(), Z.v(), t0.v(), t1.v(), t2.v());
+    } else {
+      FF::set_zero(X.v());
+      FF::set_zero(Y.v());
+      FF::set_zero(Z.v());
+    }
+    if (a.bx && !a.binf[e])  // re-randomisation: the ciphertext + r*Q
+      G<L>::madd(X.v(), Y.v(), Z.v(), a.bx + e * L, a.by + e * L, false, t0.v(), t1.v(), t2.v(), t3.v());
+  } else {
+    FF::set_zero(X.v());
+    FF::set_zero(Y.v());
+    FF::set_zero(Z.v());
+    if (a.bx && !a.binf[e]) {  // re-randomisation: start from the ciphertext instead of O
+      FF::copy(X.v(), a.bx + e * L);
+      FF::copy(Y.v(), a.by + e * L);
+      FF::set_one(Z.v());
+    }
+    // Weierstrass tables: one complete mixed Jacobian addition per table point
+    for (int win = 0; win < nw; win++) {
+      const uint32_t d = enc_digit<L>(r, a.rbytes, win, wbits);
       if (d) {
         const uint32_t* ent = a.tabQ + ((size_t)win * ents + (d - 1)) * 2 * L;
         G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
       }
     }
-  }
-  int64_t xs = a.x ? a.x[e] : 0;
-  bool neg = xs < 0;
-  uint64_t xm = neg ? (uint64_t)(-(xs + 1)) + 1u : (uint64_t)xs;
-  for (int win = 0; win < 8; win++) {
-    uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
-    if (d) {
-      const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
-      G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+    for (int win = 0; win < 8; win++) {
+      uint32_t d = (uint32_t)(xm >> (8 * win)) & 255u;
+      if (d) {
+        const uint32_t* ent = a.tabP + ((size_t)win * 255 + (d - 1)) * 2 * L;
+        G<L>::madd(X.v(), Y.v(), Z.v(), ent, ent + L, false, t0.v(), t1.v(), t2.v(), t3.v());
+      }
     }
   }
   // negative plaintext: -(|x|*P + r*Q), the Sub(encryptZero(), Encrypt(|c|)) of poly.go:17-21
@@ -453,6 +493,60 @@ BGN_DEV void tabw_fill_body(const uint32_t* tabh, int nwin_h, int nsub, int hb, 
   FF::copy(X + id * L, x.v());
   FF::copy(Y + id * L, y.v());
   FF::copy(Z + id * L, z.v());
+}
+
+// Weierstrass table -> twisted Edwards table (curve.cuh: Ed): entry (x, y) -> (u, v, u v) with u = x / y,
+// v = (x - 1) / (x + 1); `count` entries, AoS x || y in, u || v || t out.  Thread g converts the entries
+// g, g + G, ... with one inversion (Montgomery's trick on y (x + 1)).  All-zero entries (O: windows beyond
+// the scalar's top bit, never addressed) are written as zeros.  A finite entry with y (x + 1) = 0 is a point
+// of order 2 or 4 -- the base point is not of odd order -- and raises *bad: the caller then keeps the
+// Weierstrass tables.
+template <int L>
+BGN_DEV void tab_edwards_body(const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, size_t count, int G_,
+                              int* bad, size_t g) {
+  typedef F<L> FF;
+  if (g >= (size_t)G_ || g >= count) return;
+  Loc<L> acc, den, one, t, u, v;
+  FF::set_one(acc.v());
+  FF::set_one(one.v());
+  auto skip = [&](size_t e) {  // den(e) into `den`; true where the entry takes no part in the shared inversion
+    const uint32_t* x = tabw + e * 2 * L;
+    FF::add(t.v(), x, one.v());
+    FF::mul(den.v(), t.v(), x + L);
+    if (!FF::is_zero(den.v())) return false;
+    if (!(FF::is_zero(x) && FF::is_zero(x + L))) *bad = 1;
+    return true;
+  };
+  for (size_t e = g; e < count; e += G_) {
+    if (skip(e)) continue;
+    FF::copy(scratch + e * L, acc.v());
+    FF::mul(acc.v(), acc.v(), den.v());
+  }
+  FF::inv_gcd_fast(acc.v(), acc.v());
+  const size_t last = ((count - 1 - g) / G_) * G_ + g;
+  for (size_t e = last;; e -= G_) {
+    const uint32_t* x = tabw + e * 2 * L;
+    uint32_t* o = tabe + e * 3 * L;
+    if (skip(e)) {
+      FF::set_zero(o);
+      FF::set_zero(o + L);
+      FF::set_zero(o + 2 * L);
+    } else {
+      FF::mul(t.v(), acc.v(), scratch + e * L);   // 1 / (y (x + 1))
+      FF::mul(acc.v(), acc.v(), den.v());
+      FF::add(u.v(), x, one.v());
+      FF::mul(u.v(), u.v(), t.v());               // 1 / y
+      FF::mul(u.v(), u.v(), x);                   // u = x / y
+      FF::mul(v.v(), t.v(), x + L);               // 1 / (x + 1)
+      FF::sub(t.v(), x, one.v());
+      FF::mul(v.v(), v.v(), t.v());               // v = (x - 1) / (x + 1)
+      FF::mul(t.v(), u.v(), v.v());
+      FF::canon(o, u.v());
+      FF::canon(o + L, v.v());
+      FF::canon(o + 2 * L, t.v());
+    }
+    if (e < (size_t)G_) break;
+  }
 }
 
 // ------------------------------------------------------------ GT kernels
@@ -945,6 +1039,11 @@ template <int L>
 __global__ void __launch_bounds__(128) k_tabw_fill(const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X,
                                                    uint32_t* Y, uint32_t* Z, size_t first, size_t nent) {
   tabw_fill_body<L>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent, BGN_GID(size_t));
+}
+template <int L>
+__global__ void __launch_bounds__(128) k_tab_edwards(const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, size_t count,
+                                                     int G_, int* bad) {
+  tab_edwards_body<L>(tabw, tabe, scratch, count, G_, bad, BGN_GID(size_t));
 }
 template <int L>
 __global__ void __launch_bounds__(128) k_gt_reduce(const uint32_t* re, const uint32_t* im, size_t Nin, size_t nterms,

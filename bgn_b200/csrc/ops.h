@@ -99,6 +99,7 @@ struct LOpsB {
                    uint32_t* X, uint32_t* Y, uint32_t* Z, size_t N);
   void (*tabw_fill)(LaunchCfg, const uint32_t* tabh, int nwin_h, int nsub, int hb, uint32_t* X, uint32_t* Y, uint32_t* Z,
                     size_t first, size_t nent);
+  void (*tab_edwards)(LaunchCfg, const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, size_t count, int G, int* bad);
   void (*g1_polyconv)(LaunchCfg, const PolyConvArgs&);
   void (*g1_affadd)(LaunchCfg, const G1AffAddArgs&);
 };

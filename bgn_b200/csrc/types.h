@@ -89,6 +89,9 @@ struct EncArgs {
   // the re-randomisation of the non-deterministic mode (bgn.go:264-268, 491-495).  x may then be null.
   const uint32_t *bx, *by;
   const uint8_t* binf;
+  // edw != 0: tabP and tabQ hold twisted Edwards points, 3L words per entry (u | v | u v) (curve.cuh: Ed);
+  // the sum is formed in extended coordinates and converted to Jacobian before the starting point is added
+  int edw;
 };
 
 struct NormArgs {

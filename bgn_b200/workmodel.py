@@ -234,12 +234,17 @@ def affadd_products(L: int) -> int:
     return 5 * products_per_modmul(L) + products_per_sqr(L)
 
 
-def enc_table_bytes(rbytes: int, window_bits: int, L: int) -> int:
-    """bytes of the fixed-base table of Q with windows of window_bits (api.cu: tabQw_bytes)"""
-    return ((8 * rbytes + window_bits - 1) // window_bits) * ((1 << window_bits) - 1) * 2 * L * 4
+ENC_EDWARDS = True  # api.cu enc_edwards: Encrypt's tables hold twisted Edwards points (curve.cuh: Ed)
 
 
-def enc_window_auto(rbytes: int, L: int, table_max: int = 4 << 30) -> int:
+def enc_table_bytes(rbytes: int, window_bits: int, L: int, edwards: bool = None) -> int:
+    """bytes of the fixed-base table of Q with windows of window_bits (api.cu: tabQw_bytes): two field
+    elements per entry, three (u, v, u v) in Edwards form"""
+    edwards = ENC_EDWARDS if edwards is None else edwards
+    return ((8 * rbytes + window_bits - 1) // window_bits) * ((1 << window_bits) - 1) * (3 if edwards else 2) * L * 4
+
+
+def enc_window_auto(rbytes: int, L: int, table_max: int = 6 << 30) -> int:
     """the window width `enc_window = 0` picks (api.cu: enc_window_auto): widest of 20 / 18 / 16 bits within table_max"""
     for bits in (20, 18):
         if enc_table_bytes(rbytes, bits, L) <= table_max:
@@ -247,15 +252,28 @@ def enc_window_auto(rbytes: int, L: int, table_max: int = 4 << 30) -> int:
     return 16
 
 
-def encrypt_products(n: int, rbytes: int, window_bits: int, L: int, p_x_nonzero: float = 2.0 / 3.0) -> float:
-    """k_encrypt, EXPECTED 32x32->64 products per coefficient (see encrypt_modmuls for the addition count)"""
-    return encrypt_modmuls(n, rbytes, window_bits, p_x_nonzero) / 11.0 * madd_products(L)
-
-
-def encrypt_modmuls(n: int, rbytes: int, window_bits: int = 8, p_x_nonzero: float = 2.0 / 3.0) -> float:
-    """k_encrypt, EXPECTED products per coefficient for uniform r: one complete mixed addition (11
-    products; the first one into O is a copy) per non-zero window digit of r, plus one for a non-zero
-    plaintext digit.  Jacobian -> affine (k_normalize) is accounted separately."""
+def encrypt_additions(rbytes: int, window_bits: int, p_x_nonzero: float = 2.0 / 3.0) -> float:
+    """k_encrypt, EXPECTED table points per coefficient for uniform r: one per non-zero window digit of r,
+    plus one for a non-zero plaintext digit"""
     windows = (8 * rbytes + window_bits - 1) // window_bits
-    adds = windows * (1.0 - 2.0 ** -window_bits) + p_x_nonzero
-    return max(0.0, adds - 1.0) * 11
+    return windows * (1.0 - 2.0 ** -window_bits) + p_x_nonzero
+
+
+def encrypt_products(n: int, rbytes: int, window_bits: int, L: int, p_x_nonzero: float = 2.0 / 3.0,
+                     edwards: bool = None) -> float:
+    """k_encrypt, EXPECTED 32x32->64 products per coefficient.  The first table point is a copy.  Edwards
+    form (the default): 8 products per further point and the conversion to Jacobian coordinates (5 products
+    and a squaring); Weierstrass tables: one complete mixed addition (8 products, 3 squarings) per further
+    point.  Jacobian -> affine (k_normalize) is accounted separately."""
+    edwards = ENC_EDWARDS if edwards is None else edwards
+    adds = max(0.0, encrypt_additions(rbytes, window_bits, p_x_nonzero) - 1.0)
+    if edwards:
+        return (8 * adds + 5) * products_per_modmul(L) + products_per_sqr(L)
+    return adds * madd_products(L)
+
+
+def encrypt_modmuls(n: int, rbytes: int, window_bits: int = 8, p_x_nonzero: float = 2.0 / 3.0, edwards: bool = None) -> float:
+    """the same as a count of F_p products (squarings counted as products)"""
+    edwards = ENC_EDWARDS if edwards is None else edwards
+    adds = max(0.0, encrypt_additions(rbytes, window_bits, p_x_nonzero) - 1.0)
+    return 8 * adds + 6 if edwards else 11 * adds

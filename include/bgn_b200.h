@@ -76,12 +76,16 @@ const char* bgn_global_last_error(void);
  *   "enc_window"   0 | 8 | 16 | 18 | 20 | 22 | 24
  *                                fixed-base window of Q for Encrypt / level-1 re-randomisation, in bits.  0 (default):
  *                                the widest of 16 / 18 / 20 whose table stays within "enc_table_max_mb" (20 bits,
- *                                3.7 GB, at 512-bit keys; 18 bits, 3.9 GB, at 1024).  16: 285 MB at 512-bit keys;
- *                                22: 13.7 GB; 24: 50 GB, a third fewer additions than 16 (+42 % Encrypt
+ *                                5.6 GB, at 512-bit keys; 18 bits, 5.9 GB, at 1024).  16: 428 MB at 512-bit keys;
+ *                                22: 20.5 GB; 24: 75 GB, a third fewer additions than 16 (+42 % Encrypt
  *                                throughput), ~2 s to build -- for long-lived contexts.  A table that does not fit
  *                                the free device memory falls back to 16 bits.  The table is (re)built on the next
  *                                randomised encryption.
- *   "enc_table_max_mb"           bound of the automatic choice in MiB (default 4096)
+ *   "enc_table_max_mb"           bound of the automatic choice in MiB (default 6144)
+ *   "enc_edwards"  0 | 1         Encrypt sums its table points in twisted Edwards form (8 products per point
+ *                                instead of 11; tables hold 3 field elements per point instead of 2).
+ *                                Default 1; 0 keeps Weierstrass tables.  Off by itself for a key whose P or Q
+ *                                is not of odd order.
  *   "dec_lucas"    0 | 1         Decrypt through the Lucas ladder when one giant step suffices (default 1)
  *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)
  *   "fixed_pair"   -1 | 0 | 1    e(., P) with one pairing split over a pair of lanes: -1 (default) below the

@@ -203,6 +203,9 @@ int hs_tabw_fill(int L, const uint32_t* tabh, int nwin_h, int nsub, int hb, uint
                  size_t first, size_t nent) {
   FOR_L(L, for (size_t id = 0; id < nent; id++) tabw_fill_body<LL>(tabh, nwin_h, nsub, hb, X, Y, Z, first, nent, id))
 }
+int hs_tab_edwards(int L, const uint32_t* tabw, uint32_t* tabe, uint32_t* scratch, size_t count, int G, int* bad) {
+  FOR_L(L, for (int g = 0; g < G; g++) tab_edwards_body<LL>(tabw, tabe, scratch, count, G, bad, (size_t)g))
+}
 int hs_g1_from_bytes(int L, const uint8_t* in, int B, size_t count, uint32_t* x, uint32_t* y, uint8_t* inf, size_t N) {
   FOR_L(L, for (size_t e = 0; e < count; e++) g1_from_bytes_body<LL>(in, B, count, x, y, inf, N, e))
 }

@@ -52,7 +52,7 @@ class PairDuoArgs(C.Structure):
 class EncArgs(C.Structure):
     _fields_ = [("x", C.POINTER(C.c_int64)), ("r_be", u8p), ("rbytes", C.c_int), ("tabP", u32p), ("tabQ", u32p), ("wbitsQ", C.c_int),
                 ("X", u32p), ("Y", u32p), ("Z", u32p), ("count", C.c_size_t), ("N", C.c_size_t),
-                ("bx", u32p), ("by", u32p), ("binf", u8p)]
+                ("bx", u32p), ("by", u32p), ("binf", u8p), ("edw", C.c_int)]
 
 
 class GtBlindArgs(C.Structure):
@@ -392,8 +392,20 @@ class Sim:
         assert lib().hs_normalize(L, C.byref(a)) == 0
         return tab
 
-    def encrypt(self, xs, rs, tabP, tabQ, wbitsQ=8, base=None):
-        """base: optional list of starting points (bgn_g1_blind_batch: base + r*Q; xs then None)"""
+    def table_to_edwards(self, tabw, G=5):
+        """k_tab_edwards (api.cu: table_to_edwards): x || y entries -> u || v || u v entries, or None if an
+        entry has no Edwards image"""
+        L = self.L
+        count = len(tabw) // (2 * L)
+        tabe = np.zeros(count * 3 * L, dtype=np.uint32)
+        scratch = np.zeros(count * L, dtype=np.uint32)
+        bad = C.c_int(0)
+        assert lib().hs_tab_edwards(L, P32(tabw), P32(tabe), P32(scratch), C.c_size_t(count), G, C.byref(bad)) == 0
+        return None if bad.value else tabe
+
+    def encrypt(self, xs, rs, tabP, tabQ, wbitsQ=8, base=None, edw=False):
+        """base: optional list of starting points (bgn_g1_blind_batch: base + r*Q; xs then None);
+        edw: the tables hold twisted Edwards points (table_to_edwards)"""
         count = len(rs) if xs is None else len(xs)
         x = np.array(xs if xs is not None else [0], dtype=np.int64)
         bx = by = binf = None
@@ -409,7 +421,7 @@ class Sim:
             rbuf = np.frombuffer(b"".join(int(r).to_bytes(self.nbytes, "big") for r in rs), dtype=np.uint8).copy()
             rp = P8(rbuf)
         a = EncArgs(x.ctypes.data_as(C.POINTER(C.c_int64)) if xs is not None else None, rp, self.nbytes, P32(tabP),
-                    P32(tabQ), wbitsQ, P32(X), P32(Y), P32(Z), count, count, bx, by, binf)
+                    P32(tabQ), wbitsQ, P32(X), P32(Y), P32(Z), count, count, bx, by, binf, 1 if edw else 0)
         assert lib().hs_encrypt(self.L, C.byref(a)) == 0
         return self.normalize(X, Y, Z, count)
 

@@ -907,14 +907,24 @@ def test_encrypt_windows():
     r[::7] = 0
     ew.set_option("enc_window", 8)  # no wide table: the 8-bit windows built with the context
     exp = ew.encrypt_batch(x, r.reshape(-1)).tobytes()
-    for bits in (0, 16, 18, 20, 22, 24):  # 0: the automatic choice (20 bits at this key size)
-        ew.set_option("enc_window", bits)
-        v = g["encrypt"]
-        out = ew.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(ew, v["r"], ew.scalar_bytes))
-        assert out.tobytes() == unhex(v["out"]), bits
-        v = g["g1_blind"]
-        assert ew.g1_blind_batch(buf(v["a"]), scal(ew, v["r"], ew.scalar_bytes)).tobytes() == unhex(v["out"]), bits
-        assert ew.encrypt_batch(x, r.reshape(-1)).tobytes() == exp, bits
+    # tables in twisted Edwards form (the default; curve.cuh: Ed) and in Weierstrass form
+    for edw, widths in ((1, (0, 16, 18, 20, 22, 24)), (0, (0, 16, 20, 24))):  # 0: the automatic choice (20 bits here)
+        ew.set_option("enc_edwards", edw)
+        for bits in widths:
+            ew.set_option("enc_window", bits)
+            v = g["encrypt"]
+            out = ew.encrypt_batch(np.array(v["x"], dtype=np.int64), scal(ew, v["r"], ew.scalar_bytes))
+            assert out.tobytes() == unhex(v["out"]), (edw, bits)
+            v = g["g1_blind"]
+            assert ew.g1_blind_batch(buf(v["a"]), scal(ew, v["r"], ew.scalar_bytes)).tobytes() == unhex(v["out"]), (edw, bits)
+            assert ew.encrypt_batch(x, r.reshape(-1)).tobytes() == exp, (edw, bits)
+    ew.set_option("enc_edwards", 1)
+    # plaintext-only sums (EncryptDeterministic: P's Edwards table alone), incl. x = 0 and large |x|
+    xd = np.array([0, 1, -1, 2, 255, 256, -65537, (1 << 62) + 12345, -(1 << 62)], dtype=np.int64)
+    got = ew.encrypt_batch(xd, None).tobytes()
+    ew.set_option("enc_edwards", 0)
+    assert ew.encrypt_batch(xd, None).tobytes() == got
+    ew.set_option("enc_edwards", 1)
     ew.set_option("enc_table_max_mb", 1)  # the automatic choice under a table bound: back to 16 bits
     ew.set_option("enc_window", 0)
     assert ew.encrypt_batch(x, r.reshape(-1)).tobytes() == exp

@@ -79,6 +79,41 @@ def test_sim_encrypt(kb):
     got = S.encrypt(v["x"][:k], None, tabs["P"], tabs["Q"])  # EncryptDeterministic
     exp = [O.g1_mul(x, S.P, par.p) for x in v["x"][:k]]
     assert got == exp
+    # the same sums with the tables in twisted Edwards form (curve.cuh: Ed; what the GPU path uses by default)
+    if "Pe" not in tabs:
+        tabs["Pe"] = S.table_to_edwards(tabs["P"])
+        tabs["Qe"] = S.table_to_edwards(tabs["Q"])
+    S.range_report()
+    got = S.encrypt(v["x"][:k], [int(r, 16) for r in v["r"][:k]], tabs["Pe"], tabs["Qe"], edw=True)
+    assert got == g1s(par, v["out"][:k])
+    assert S.encrypt(v["x"][:k], None, tabs["Pe"], tabs["Qe"], edw=True) == exp
+    _, _, unknown, violations = S.range_report()
+    assert unknown == 0 and violations == 0
+    if kb == 64:
+        # degenerate sums: r = 0 and x = 0 (the identity), r*Q = -(x*P)-like cancellations are covered by the
+        # re-randomisation below: base + r*Q with base = -(r*Q) gives O, base = r*Q doubles
+        rq = [O.g1_mul(int(r, 16), S.Q, par.p) for r in v["r"][:4]]
+        rs = [int(r, 16) for r in v["r"][:4]]
+        base = [O.g1_neg(rq[0], par.p), rq[1], None, rq[3]]
+        exp_b = [O.g1_add(b, q, par.p) if b is not None else q for b, q in zip(base, rq)]
+        assert S.encrypt(None, rs, tabs["Pe"], tabs["Qe"], base=base, edw=True) == exp_b
+        assert S.encrypt([0, 0], [0, 0], tabs["Pe"], tabs["Qe"], edw=True) == [None, None]
+        assert S.encrypt([5, -5], [0, 0], tabs["Pe"], tabs["Qe"], edw=True) == [O.g1_mul(5, S.P, par.p), O.g1_neg(O.g1_mul(5, S.P, par.p), par.p)]
+        q16e = S.table_to_edwards(tabs["Q16"])
+        assert S.encrypt(v["x"], [int(r, 16) for r in v["r"]], tabs["Pe"], q16e, wbitsQ=16, edw=True) == g1s(par, v["out"])
+        assert S.encrypt(v["x"], small, tabs["Pe"], q16e, wbitsQ=16, edw=True) == [enc(x, r) for x, r in zip(v["x"], small)]
+        # an all-zero entry is O (an unused slot), not an error; a finite point without an Edwards image --
+        # (-1, sqrt(-2)) has order 4 -- raises the flag (api.cu then keeps the Weierstrass tables)
+        import numpy as np
+        t2 = np.zeros(2 * 2 * S.L, dtype=np.uint32)
+        t2[2 * S.L:] = tabs["P"][: 2 * S.L]
+        assert S.table_to_edwards(t2) is not None
+        assert par.p % 8 == 3
+        y4 = pow(par.p - 2, (par.p + 1) // 4, par.p)
+        assert y4 * y4 % par.p == par.p - 2
+        t2[: S.L] = S.soa([par.p - 1]).ravel()
+        t2[S.L: 2 * S.L] = S.soa([y4]).ravel()
+        assert S.table_to_edwards(t2) is None
 
 
 @pytest.mark.parametrize("kb", SIM_KB)

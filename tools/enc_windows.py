@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Encrypt (BASELINE config 2: 720 896 coefficient encryptions, keyBits = 512) against the window width of Q's
-fixed-base table: 16 / 18 / 20 / 22 / 24 bits (285 MB .. 50 GB).  Table build time, kernel time, IMAD fraction,
-and the same at keyBits = 1024 for 16 / 18 / 20.  One JSON object."""
+fixed-base table -- 16 / 18 / 20 / 22 / 24 bits -- and the form of its points: twisted Edwards (the default:
+8 products per table point) or Weierstrass (complete mixed Jacobian addition: 8 products + 3 squarings).  Table
+size and build time, kernel time, IMAD fraction, and the same at keyBits = 1024 for 16 / 18 / 20.  One JSON object."""
 import json
 import os
 import sys
@@ -33,7 +34,8 @@ def main():
         out = torch.empty(cnt * EB, dtype=torch.uint8, device=dev)
         eng.timing_enable(True)
         ref = None
-        for bits in widths:
+        for edw, bits in [(e, b) for e in (1, 0) for b in widths]:
+            eng.set_option("enc_edwards", edw)
             eng.set_option("enc_window", bits)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -50,11 +52,12 @@ def main():
                     best = (t, k)
             if ref is None:
                 ref = out.clone()
-            row = {"key_bits": kb, "window_bits": bits, "table_GB": workmodel.enc_table_bytes(SB, bits, L) / 1e9,
+            row = {"key_bits": kb, "edwards": bool(edw), "window_bits": bits,
+                   "table_GB": workmodel.enc_table_bytes(SB, bits, L, bool(edw)) / 1e9,
                    "table_build_s": build_s, "encryptions": cnt, "call_ms": best[0], "k_encrypt_ms": best[1],
                    "per_s": cnt / (best[0] * 1e-3),
-                   "imad_frac": cnt * workmodel.encrypt_products(n, SB, bits, L) / (best[1] * 1e-3) / peak,
-                   "bytes_equal_16bit": bool((out == ref).all().item())}
+                   "imad_frac": cnt * workmodel.encrypt_products(n, SB, bits, L, edwards=bool(edw)) / (best[1] * 1e-3) / peak,
+                   "bytes_equal_first_row": bool((out == ref).all().item())}
             res["rows"].append(row)
             print(json.dumps(row), file=sys.stderr, flush=True)
         eng.close()
