@@ -1335,6 +1335,49 @@ int bgn_ctx_create(const bgn_params* prm, int device, bgn_ctx** out) {
     CK(cudaMalloc(&c->tabQ, tabQ_words * 4));
     build_table(c, c->dPx, c->dPy, 8, c->tabP);
     build_table(c, c->dQx, c->dQy, c->nbytes, c->tabQ);
+    if (c->enc_edwards) {
+      // The Edwards form's unified addition has no exceptional cases on points of ODD order only: check
+      // n P = n Q = O (n is odd).  Every key NewKeyGen makes passes (bgn.go:112-119); other generators keep
+      // the Weierstrass tables and their complete addition.
+      uint8_t* dn = nullptr;
+      CK(cudaMalloc(&dn, pad256(prm->n_len) + 6 * (size_t)L * 4));
+      bool odd = true;
+      try {
+        uint32_t* jz = reinterpret_cast<uint32_t*>(dn + pad256(prm->n_len));
+        CK(cudaMemcpyAsync(dn, prm->n_be, prm->n_len, cudaMemcpyHostToDevice, c->stream));
+        for (int w = 0; w < 2; w++) {
+          G1MulArgs ma;
+          ma.x = w ? c->dQx : c->dPx;
+          ma.y = w ? c->dQy : c->dPy;
+          ma.inf = w ? c->dQinf : c->dPinf;
+          ma.Nin = 1;
+          ma.k_be = dn;
+          ma.kbytes = (int)prm->n_len;
+          ma.X = jz;
+          ma.Y = jz + L;
+          ma.Z = jz + 2 * L + w * L;  // Z of P's multiple, then Z of Q's
+          ma.count = 1;
+          ma.N = 1;
+          c->Bo->g1_mulvar(cfg(c, 1, 32, 0), ma);
+        }
+        std::vector<uint32_t> z(2 * (size_t)L);
+        CK(cudaMemcpyAsync(z.data(), jz + 2 * L, 2 * (size_t)L * 4, cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        for (int w = 0; w < 2; w++) {
+          bool zero = true, is_p = true;
+          for (int i = 0; i < L; i++) {
+            zero = zero && z[(size_t)w * L + i] == 0;
+            is_p = is_p && z[(size_t)w * L + i] == p[i];
+          }
+          odd = odd && (zero || is_p);
+        }
+      } catch (...) {
+        cudaFree(dn);
+        throw;
+      }
+      cudaFree(dn);
+      if (!odd) c->enc_edwards = false;
+    }
     if (c->enc_edwards) {  // P's table in Edwards form (Q's wide table is built on the first randomised encryption)
       const size_t nP = (size_t)8 * 255;
       uint32_t* scr = nullptr;

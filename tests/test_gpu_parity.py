@@ -471,6 +471,33 @@ def test_off_curve_input_becomes_O(golden):
     assert out.tobytes() == bytes.fromhex(v["b"][0])
 
 
+def test_generators_of_even_order_keep_the_complete_addition():
+    """A context whose Q is not of odd order (Q + the point of order 2: on the curve, so it is accepted) must not
+    use the Edwards form, whose unified addition is only free of exceptional cases on odd-order points: Encrypt
+    and the re-randomisation still equal the oracle's x*P + r*Q computed with the complete affine law."""
+    from bgn_b200 import Engine
+    from oracle import bgn_oracle as O
+    g = load_golden(128)
+    par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+    P = O.g1_from_bytes(bytes.fromhex(g["P"]), par)
+    Q = O.g1_from_bytes(bytes.fromhex(g["Q"]), par)
+    Q2 = O.g1_add(Q, (0, 0), par.p)
+    assert Q2 is not None and O.g1_mul(par.n, Q2, par.p) == (0, 0)
+    e = Engine(par.p, par.n, par.l, bytes.fromhex(g["P"]), O.g1_to_bytes(Q2, par))
+    rng = random.Random(77)
+    xs = [rng.randrange(-2, 3) for _ in range(12)]
+    rs = [rng.randrange(par.n) for _ in range(12)]
+    rs[0], rs[1], rs[2] = 0, 1, 2
+    exp = b""
+    for x, r in zip(xs, rs):
+        c = O.g1_add(O.g1_mul(abs(x), P, par.p), O.g1_mul(r, Q2, par.p), par.p)
+        exp += O.g1_to_bytes(O.g1_neg(c, par.p) if x < 0 else c, par)
+    for bits in (0, 16, 8):
+        e.set_option("enc_window", bits)
+        assert e.encrypt_batch(np.array(xs, dtype=np.int64), e.scalars_be(rs, e.scalar_bytes)).tobytes() == exp, bits
+    e.close()
+
+
 # ---------------------------------------------------------------- seeded random parity vs the oracle
 @pytest.mark.parametrize("kb", [128, 512])
 def test_random_vs_oracle(kb):
