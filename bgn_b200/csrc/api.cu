@@ -151,6 +151,8 @@ struct bgn_ctx {
   int tabQw_bits = 0;
   uint32_t* tabE = nullptr;    // 8-bit windows of e(Q,Q) in GT, built on the first level-2 re-randomisation
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
+  uint32_t* linesPq = nullptr; // line table of q1*P, built with the secret: level-1 Decrypt is e(C, q1 P) = e(C, P)^q1
+  bool dec_pair_q1 = true;     // level-1 Decrypt through linesPq (option dec_pair_q1)
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
   int enc_window = 0;          // window bits of Q's table: 0 = widest of 16/18/20 within enc_table_max; 8 | 16 | 18 | 20 | 22 | 24 (BGN_ENC_WINDOW)
   size_t enc_table_max = (size_t)6 << 30;  // bound of the automatic choice (option enc_table_max_mb)
@@ -752,8 +754,8 @@ int miller_nsteps(const bgn_ctx* c) {
   }
   return n;
 }
-void ensure_linesP(bgn_ctx* c) {
-  if (c->linesP || !c->fixed_lines) return;
+// normalised line table of the affine point (px, py) (device, Montgomery); nullptr if it has none
+uint32_t* record_lines(bgn_ctx* c, const uint32_t* px, const uint32_t* py) {
   const size_t words = (size_t)miller_nsteps(c) * 2 * c->L;
   uint32_t *tab = nullptr, *scratch = nullptr;
   int ok = 0;
@@ -762,7 +764,7 @@ void ensure_linesP(bgn_ctx* c) {
     CK(cudaMalloc(&scratch, words * 4 + 256));
     int* dok = reinterpret_cast<int*>(scratch + words);
     Timer t(c, "k_miller_record");
-    c->Co->miller_record(cfg(c, 1, 32, 0), c->dPx, c->dPy, tab, scratch, dok);
+    c->Co->miller_record(cfg(c, 1, 32, 0), px, py, tab, scratch, dok);
     t.done();
     CK(cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     finish(c);
@@ -772,20 +774,25 @@ void ensure_linesP(bgn_ctx* c) {
     throw;
   }
   cudaFree(scratch);
-  if (!ok) {  // P is not a point of odd order: no normalised table; e(., P) goes through the general kernel
+  if (!ok) {
     cudaFree(tab);
-    c->fixed_lines = false;
-    return;
+    return nullptr;
   }
-  c->linesP = tab;
+  return tab;
+}
+void ensure_linesP(bgn_ctx* c) {
+  if (c->linesP || !c->fixed_lines) return;
+  c->linesP = record_lines(c, c->dPx, c->dPy);
+  // P is not a point of odd order: no normalised table; e(., P) goes through the general kernel
+  if (!c->linesP) c->fixed_lines = false;
 }
 // out[i] = e(E[i], P) through the line table
-void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out) {
+void run_miller_fixed(bgn_ctx* c, const G1Arr& E, size_t count, const GtArr& out, const uint32_t* lines = nullptr) {
   if (!count) return;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   MillerFixedArgs a;
-  a.lines = c->linesP;
+  a.lines = lines ? lines : c->linesP;
   a.Ex = E.x;
   a.Ey = E.y;
   a.Einf = E.inf;
@@ -1055,6 +1062,7 @@ void ctx_free(bgn_ctx* c) {
   cudaFree(c->tabQw);
   cudaFree(c->tabE);
   cudaFree(c->linesP);
+  cudaFree(c->linesPq);
   cudaFree(c->bs_elems);
   cudaFree(c->bs_slots);
   cudaFree(c->bs_ginv);
@@ -1473,6 +1481,8 @@ int bgn_ctx_set_option(bgn_ctx* c, const char* name, long value) {
     c->dec_lucas = value != 0;
   } else if (k == "fixed_lines") {
     c->fixed_lines = value != 0;
+  } else if (k == "dec_pair_q1") {
+    c->dec_pair_q1 = value != 0;  // takes effect for tables built by the next bgn_ctx_set_secret; 0 also stops using one
   } else if (k == "fixed_pair") {
     c->fixed_pair = value < 0 ? -1 : (value != 0);
   } else if (k == "pair_duo") {
@@ -2165,10 +2175,69 @@ int bgn_ctx_set_secret(bgn_ctx* c, const uint8_t* q1_be, size_t q1_len, uint64_t
     c->bs_hmask = (uint32_t)(hs - 1);
     c->bs_mmax = mmax;
     c->bs_giant = (uint32_t)((mmax + S - 1) / S);
+    // Level-1 Decrypt needs e(C, P)^q1 = e(C, q1 P): with the line table of q1*P the exponentiation is part of
+    // the pairing.  (The reference forms gsk = P^q1 too, bgn.go:222; its table search then runs in G1.)
+    cudaFree(c->linesPq);
+    c->linesPq = nullptr;
+    if (c->fixed_lines && c->dec_pair_q1) {
+      uint32_t* tmp = nullptr;  // k_be | Jacobian (3L) | scratch (L) | affine x, y (2L) | flag
+      const size_t kb = pad256(q1_len);
+      CK(cudaMalloc(&tmp, kb + 6 * (size_t)c->L * 4 + 256));
+      try {
+        uint8_t* dk = reinterpret_cast<uint8_t*>(tmp);
+        uint32_t* w = reinterpret_cast<uint32_t*>(dk + kb);
+        JacArr j{w, w + c->L, w + 2 * c->L, 1};
+        uint32_t* scr = w + 3 * c->L;
+        G1Arr gq{w + 4 * c->L, w + 5 * c->L, reinterpret_cast<uint8_t*>(w + 6 * c->L), 1};
+        CK(cudaMemcpyAsync(dk, q1_be, q1_len, cudaMemcpyHostToDevice, c->stream));
+        G1MulArgs ma;
+        ma.x = c->dPx;
+        ma.y = c->dPy;
+        ma.inf = c->dPinf;
+        ma.Nin = 1;
+        ma.k_be = dk;
+        ma.kbytes = (int)q1_len;
+        ma.X = j.X;
+        ma.Y = j.Y;
+        ma.Z = j.Z;
+        ma.count = 1;
+        ma.N = 1;
+        c->Bo->g1_mulvar(cfg(c, 1, 32, 0), ma);
+        normalize_soa(c, j, 1, scr, gq);
+        uint8_t isinf = 1;
+        CK(cudaMemcpyAsync(&isinf, gq.inf, 1, cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        if (!isinf) c->linesPq = record_lines(c, gq.x, gq.y);
+      } catch (...) {
+        cudaFree(tmp);
+        throw;
+      }
+      cudaFree(tmp);
+    }
     c->has_secret = true;
   });
 }
 
+// R = C^q1 (count elements) -> plaintexts by the baby-step table and the giant steps (gsbs.go:54-106)
+static void lookup_core(bgn_ctx* c, const GtArr& R, size_t count, int64_t* d_out, uint8_t* d_status) {
+  BsgsLookupArgs la;
+  la.re = R.re;
+  la.im = R.im;
+  la.Nin = R.N;
+  la.count = count;
+  la.elems = c->bs_elems;
+  la.slots = c->bs_slots;
+  la.hmask = c->bs_hmask;
+  la.S = c->bs_S;
+  la.ginv = c->bs_ginv;
+  la.giant_steps = c->bs_giant;
+  la.mmax = c->bs_mmax;
+  la.out = d_out;
+  la.status = d_status;
+  Timer t(c, "k_bsgs_lookup");
+  c->A->bsgs_lookup(cfg(c, nblk(count, 128), 128, 0), la);
+  t.done();
+}
 // level-2 elements A (count) -> plaintexts: Lucas ladder + one table probe, or C^q1 + giant steps
 static void decrypt_core(bgn_ctx* c, const GtArr& A, size_t count, int64_t* d_out, uint8_t* d_status) {
   if (c->bs_giant == 1 && c->dec_lucas) {
@@ -2207,25 +2276,19 @@ static void decrypt_core(bgn_ctx* c, const GtArr& A, size_t count, int64_t* d_ou
     c->A->gt_pow(cfg(c, nblk(count, 128), 128, 0), pa);
     t.done();
   }
-  BsgsLookupArgs la;
-  la.re = R.re;
-  la.im = R.im;
-  la.Nin = R.N;
-  la.count = count;
-  la.elems = c->bs_elems;
-  la.slots = c->bs_slots;
-  la.hmask = c->bs_hmask;
-  la.S = c->bs_S;
-  la.ginv = c->bs_ginv;
-  la.giant_steps = c->bs_giant;
-  la.mmax = c->bs_mmax;
-  la.out = d_out;
-  la.status = d_status;
-  {
-    Timer t(c, "k_bsgs_lookup");
-    c->A->bsgs_lookup(cfg(c, nblk(count, 128), 128, 0), la);
-    t.done();
+  lookup_core(c, R, count, d_out, d_status);
+}
+// level-1 elements -> plaintexts: e(C, q1 P) through the line table of q1*P and the table search, or
+// e(C, P) and the level-2 path
+static void make_l2_core(bgn_ctx* c, const G1Arr& C1, size_t count, const GtArr& out);
+static void decrypt_l1_core(bgn_ctx* c, const G1Arr& C1, size_t count, const GtArr& A, int64_t* d_out, uint8_t* d_status) {
+  if (c->linesPq && c->fixed_lines && c->dec_pair_q1) {
+    run_miller_fixed(c, C1, count, A, c->linesPq);
+    lookup_core(c, A, count, d_out, d_status);
+    return;
   }
+  make_l2_core(c, C1, count, A);
+  decrypt_core(c, A, count, d_out, d_status);
 }
 // e(C[i], P) for level-1 elements (line table of P when enabled)
 static void make_l2_core(bgn_ctx* c, const G1Arr& C1, size_t count, const GtArr& out) {
@@ -2259,9 +2322,9 @@ int bgn_decrypt_batch(bgn_ctx* c, const uint8_t* in, int is_l2, size_t count, in
       // level 1: e(C, P)^q1 = e(P,P)^(q1 m); same m as the reference's G1 table search (bgn.go:222-223)
       G1Arr C1 = g1_alloc(c, count);
       g1_from_bytes(c, di, count, C1);
-      make_l2_core(c, C1, count, A);
+      decrypt_l1_core(c, C1, count, A, reinterpret_cast<int64_t*>(oo.dev), os.dev);
     }
-    decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
+    if (is_l2) decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
     commit_out(c, oo);
     commit_out(c, os);
   });
@@ -2518,8 +2581,10 @@ int bgn_decrypt_h(bgn_ctx* c, const bgn_buf* in, int64_t* out, uint8_t* status) 
     OutBuf oo = stage_out(c, out, count * 8);
     OutBuf os = stage_out(c, status, count);
     GtArr A = l2 ? as_gt(in) : gt_alloc(c, count);
-    if (!l2) make_l2_core(c, as_g1(in), count, A);
-    decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
+    if (l2)
+      decrypt_core(c, A, count, reinterpret_cast<int64_t*>(oo.dev), os.dev);
+    else
+      decrypt_l1_core(c, as_g1(in), count, A, reinterpret_cast<int64_t*>(oo.dev), os.dev);
     commit_out(c, oo);
     commit_out(c, os);
   });

@@ -152,6 +152,42 @@ def test_decrypt_l1(golden):
     assert [int(x) for x in vals] == v["out"]
 
 
+def test_decrypt_l1_both_routes():
+    """Level-1 Decrypt as one pairing e(C, q1 P) with the line table of q1*P (the default) and as e(C, P) followed by
+    the exponentiation give the same plaintexts and statuses: golden vectors, a random batch with negative values,
+    zeros, O and out-of-range plaintexts, byte form and handle form."""
+    from bgn_b200 import Engine
+    g = load_golden(128)
+    v = g["decrypt_l1"]
+    rng = np.random.default_rng(5)
+    T = g["msg_space"]
+    x = rng.integers(-T, T + 1, 600)
+    x[:4] = [0, T, -T, 4 * T * T]  # the last one is out of range: status 1
+    res = []
+    for route in (1, 0):
+        e = Engine(int(g["p"], 16), int(g["n"], 16), g["l"], bytes.fromhex(g["P"]), bytes.fromhex(g["Q"]))
+        e.set_option("dec_pair_q1", route)
+        e.set_secret(int(g["q1"], 16), T)
+        vals, st = e.decrypt_batch(buf(v["in"]), False)
+        assert list(st) == v["status"] and [int(t) for t in vals] == v["out"], route
+        r = rng.integers(0, 256, (len(x), e.scalar_bytes), dtype=np.uint8) if route else r
+        r[:, 0] &= 0x3F
+        ct = e.encrypt_batch(x, r.reshape(-1))
+        ct[5 * e.elem_bytes: 6 * e.elem_bytes] = 0  # O decrypts to 0
+        vals, st = e.decrypt_batch(ct, False)
+        h = e.import_batch(1, ct)
+        vh, sh = e.decrypt_h(h)
+        assert (np.asarray(vh) == np.asarray(vals)).all() and (np.asarray(sh) == np.asarray(st)).all()
+        h.free()
+        res.append((np.asarray(vals).copy(), np.asarray(st).copy()))
+        ok = np.asarray(st) == 0
+        exp = x.copy()
+        exp[5] = 0
+        assert (np.asarray(vals)[ok] == exp[ok]).all() and not ok[3] and ok[:3].all() and ok[4:].all(), route
+        e.close()
+    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
+
+
 # ---------------------------------------------------------------- SURVEY.md 8(f1): non-deterministic mode
 def test_g1_blind(golden):
     e, v = engine_for(golden), golden["g1_blind"]
