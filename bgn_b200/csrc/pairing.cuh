@@ -214,6 +214,10 @@ struct MillerTeam {
       }
     }
     bool einf = a.Einf[eidx(t)] != 0;
+    // A finite evaluation point with y = 0 is the point of order 2, (0, 0); every line value at it lies in F_p, so
+    // its pairings are 1 -- what skipping it like O yields, and what keeps 1 / y out of the normalisation.  (The
+    // byte format already reads (0, 0) as O; only a handle can carry it.)
+    if (NORM && !einf && FF::is_zero(a.Ey + eidx(t) * L)) einf = true;
     flagsB()[tid] = einf ? 0 : 1;
     if (!einf && !EG) {
       s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);

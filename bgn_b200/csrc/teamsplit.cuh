@@ -87,6 +87,7 @@ struct MillerSplit {
     }
     size_t e = a.e_bcast ? (size_t)t : (size_t)unit * a.dE + t;
     bool einf = a.Einf[e] != 0;
+    if (BGN_EVAL_NORM && !einf && FF::is_zero(a.Ey + e * L)) einf = true;  // (0, 0): pairings are 1 (pairing.cuh: init)
     flagsB()[col] = einf ? 0 : 1;
     if (!einf) {
       FF::copy(cslot(col, C_EX), a.Ex + e * L);

@@ -188,6 +188,23 @@ def test_sim_multpoly(kb):
     assert S.multpoly(c2, v["d2"], c1, v["d1"], 1) == gts(par, v["out"])
     if kb < 512:  # three units, ragged last block
         assert S.multpoly(c1 * 3, v["d1"], c2 * 3, v["d2"], 3) == gts(par, v["out"]) * 3
+        # the point of order 2, (0, 0), as a coefficient on the evaluation side (only a handle can carry it: the
+        # byte format reads it as O): its pairings are 1, as the oracle's Miller loop finds -- every line value
+        # at it lies in F_p -- and the evaluation points must not be normalised by 1 / y = 1 / 0
+        d1, d2 = v["d1"], v["d2"]
+        a1, a2 = list(c1), list(c2)
+        (a2 if d1 <= d2 else a1)[0] = (0, 0)  # the polynomial with fewer slots takes the Miller side
+        exp = []
+        for j in range(d1 + d2):
+            acc = (1, 0)
+            for i in range(d1):
+                k = j - i
+                if 0 <= k < d2 and a1[i] is not None and a2[k] is not None:
+                    mp, ep = (a1[i], a2[k]) if d1 <= d2 else (a2[k], a1[i])
+                    acc = O.fp2_mul(acc, O.pairing(mp, ep, par), par.p)
+            exp.append(acc)
+        assert S.multpoly(a1, d1, a2, d2, 1) == exp
+        assert S.multpoly_split(a1, d1, a2, d2, 1) == exp
 
 
 @pytest.mark.parametrize("kb", SIM_KB)
