@@ -968,6 +968,7 @@ def test_encrypt_windows():
     r[:, 0] &= 0x3F
     r[::5, :4] = 0
     r[::7] = 0
+    r[3::11] = 255  # r = 2^(8 bytes) - 1 >= n: every window at its last entry, the top window past the bits of n
     ew.set_option("enc_window", 8)  # no wide table: the 8-bit windows built with the context
     exp = ew.encrypt_batch(x, r.reshape(-1)).tobytes()
     # tables in twisted Edwards form (the default; curve.cuh: Ed) and in Weierstrass form
