@@ -788,10 +788,11 @@ def test_batch_poly_helpers_match_mirror():
 # ---------------------------------------------------------------- mid-size parity vs the C port of the oracle
 @pytest.mark.parametrize("kb,count,d1,d2", [(512, 48, 11, 11), (512, 64, 3, 7), (1024, 6, 8, 8), (256, 200, 5, 4),
                                             (256, 9, 1, 7), (256, 7, 40, 5), (128, 5, 32, 32), (64, 3, 128, 128),
-                                            (512, 300, 1, 1)])
+                                            (512, 300, 1, 1), (512, 24, 13, 13)])
 def test_multpoly_vs_cpu_ref(kb, count, d1, d2):
-    """Encrypt + EMult at BASELINE.json's shapes (d = 11 at 512 bit, d = 8 at 1024 bit) on sizes the
-    multi-threaded C oracle finishes in seconds; includes zero digits with r = 0 (O coefficients)."""
+    """Encrypt + EMult at BASELINE.json's shapes (d = 11 at 512 bit, d = 8 at 1024 bit) and at the shape of the
+    reference's own BenchmarkMultPoly (plaintext 100.1 -> 13 slots -> 169 pairings, poly_test.go:55-66) on sizes
+    the multi-threaded C oracle finishes in seconds; includes zero digits with r = 0 (O coefficients)."""
     import os
     from oracle.cpu_ref import CpuRef
     g = load_golden(kb)
