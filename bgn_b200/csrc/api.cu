@@ -456,7 +456,11 @@ void normalize_soa(bgn_ctx* c, const JacArr& j, size_t count, uint32_t* scratch,
 size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
   size_t pb = c->A->miller_priv_bytes();
   int fixed = c->A->miller_fixed_threads();
-  if (!pb || !fixed || !count || dE <= 0 || dE > fixed) return 0;
+  if (!count || dE <= 0) return 0;
+  // unit-stride layout: x^2 / y of every evaluation point for the parabola steps (MillerArgs::evw); a batch
+  // may be served by up to three launches (full waves, remainder), each with its own padded slice
+  if (!pb || !fixed) return pad256(count * (size_t)dE * c->L * 4) + 1024;
+  if (dE > fixed) return 0;
   size_t upb = (size_t)(fixed / dE);
   return pad256(((count + upb - 1) / upb + 160) * pb) + 256;  // + one block per SM: small batches are spread out
 }
@@ -608,12 +612,12 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
       auto gt_off = [&](size_t units) { return GtArr{out.re + units * out_slots * c->L, out.im + units * out_slots * c->L, out.N - units * out_slots}; };
       const size_t full = count / cap_std, rem = count % cap_std;
       // Time model in units of one full wave of k_miller (measured at 11 x 11 slots, 17 limbs:
-      // profiles/r02_split_ab_v2.json).  A split wave's time steps with the warps each thread role
-      // occupies per SM: <= 2 (one per scheduler pair) 0.49, <= 4: 0.60, <= 6 (full): 0.81.  The team
+      // profiles/r02_split_ab_v4.json).  A split wave's time steps with the warps each thread role
+      // occupies per SM: <= 2 (one per scheduler pair) 0.57, <= 4: 0.68, <= 6 (full): 0.92.  The team
       // kernel: a batch within half a wave (one warp per scheduler) 0.76, anything else whole waves.
       auto t_split = [&](size_t n) {
         const size_t u = (n + sms - 1) / sms, w = (u * (size_t)dE + 31) / 32;
-        return w <= 2 ? 0.49 : (w <= 4 ? 0.60 : 0.81);
+        return w <= 2 ? 0.57 : (w <= 4 ? 0.68 : 0.92);
       };
       const double t_a = count > cap_std ? (double)((count + cap_std - 1) / cap_std) : (count * 2 <= cap_std ? 0.76 : 1.0);
       const double t_b = rem && rem <= g.cap ? (double)full + t_split(rem) : 1e30;            // full waves + split remainder
@@ -688,6 +692,7 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.teams_per_group = tpg;
   a.group_threads = GT_;
   a.skew_cycles = c->miller_skew;
+  a.evw = c->A->miller_fixed_threads() ? nullptr : arena_get<uint32_t>(c, (e_bcast ? (size_t)dE : count * (size_t)dE) * c->L);
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
   c->A->miller(cfg(c, nblocks, nt, smem), a);

@@ -37,6 +37,7 @@ static uint64_t nmul = 0;  // Montgomery products executed (work model check, te
 static uint64_t nmulw = 0, nredc = 0;  // double-width products / separate reductions executed
 static uint64_t nmulk = 0;             // of which Karatsuba products (counted apart from nmulw)
 static uint64_t nsqrw = 0;             // dedicated double-width squarings (L (L + 1) / 2 products each)
+static uint64_t ndot3 = 0;             // one-pass three-term dot products (4L^2 + L products each)
 static uint64_t ndot2 = 0;             // one-pass dot products a0 b0 + a1 b1 (3L^2 + L products each)
 static uint64_t safegcd_fallbacks = 0;  // F<L>::inv_gcd<SAFE>: times the verified fast inversion fell back
 // Range tracker (tests only): every element written by the arithmetic below carries an upper
@@ -425,6 +426,90 @@ struct Fp {
     }
     if ((L & 1) == 0) {
       row2<false>(Y, X, a0, b0[(L - 1) * ES], a1, b1[(L - 1) * ES], pm, np0);
+      merge(r, X, Y);
+    } else {
+      merge(r, Y, X);
+    }
+  }
+
+  // ---- three-term dot product r = (a0*b0 + a1*b1 + a2*b2) / R mod p in one CIOS pass: 4L^2 + L products.
+  // Multiplicands in registers, multipliers streamed from memory.  Used by the Miller loop's parabola step
+  // (fused.cuh: para_mul): s (x^2/y) + c1 (x/y) + c0 (1/y) at a normalised evaluation point.
+  // Requires a0 + a1 + a2 + p < R / 2 (window head-room).
+  template <bool FIRST>
+  BGN_DEV static void row3(uint32_t (&X)[W], uint32_t (&Y)[W], const uint32_t (&a0)[L], uint32_t s0,
+                           const uint32_t (&a1)[L], uint32_t s1, const uint32_t (&a2)[L], uint32_t s2,
+                           const uint32_t* __restrict__ pm, uint32_t np0) {
+    if (FIRST) {
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) mul_wide(Y[2 * k], Y[2 * k + 1], a0[2 * k + 1], s0);
+      Y[W - 2] = 0;
+      Y[W - 1] = 0;
+      BGN_UNROLL
+      for (int k = 0; k < KE; k++) mul_wide(X[2 * k], X[2 * k + 1], a0[2 * k], s0);
+      if (2 * KE < W) {
+        X[W - 2] = 0;
+        X[W - 1] = 0;
+      }
+    } else {
+      add_cc(X[0], X[0], Y[1]);
+      BGN_UNROLL
+      for (int k = 0; k < KO; k++) madc_wide_cc3(Y[2 * k], Y[2 * k + 1], a0[2 * k + 1], s0, Y[2 * k + 2], Y[2 * k + 3]);
+      addc(Y[W - 2], 0, 0);
+      Y[W - 1] = 0;
+      mad_wide_cc(X[0], X[1], a0[0], s0);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a0[2 * k], s0);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+    BGN_UNROLL
+    for (int t = 0; t < 2; t++) {
+      const uint32_t (&a)[L] = t == 0 ? a1 : a2;
+      const uint32_t s = t == 0 ? s1 : s2;
+      if (KO > 0) {
+        mad_wide_cc(Y[0], Y[1], a[1], s);
+        BGN_UNROLL
+        for (int k = 1; k < KO; k++) madc_wide_cc(Y[2 * k], Y[2 * k + 1], a[2 * k + 1], s);
+        addc(Y[W - 2], Y[W - 2], 0);
+      }
+      mad_wide_cc(X[0], X[1], a[0], s);
+      BGN_UNROLL
+      for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], a[2 * k], s);
+      if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+    }
+    uint32_t m = X[0] * np0;
+    mad_wide_cc(Y[0], Y[1], pm[1], m);
+    BGN_UNROLL
+    for (int k = 1; k < KO; k++) madc_wide_cc(Y[2 * k], Y[2 * k + 1], pm[2 * k + 1], m);
+    addc(Y[W - 2], Y[W - 2], 0);
+    mad_wide_cc(X[0], X[1], pm[0], m);
+    BGN_UNROLL
+    for (int k = 1; k < KE; k++) madc_wide_cc(X[2 * k], X[2 * k + 1], pm[2 * k], m);
+    if (2 * KE < W) addc(X[2 * KE], X[2 * KE], 0);
+  }
+  template <int ES = 1>
+  BGN_DEV static void dot3_stream(uint32_t (&r)[L], const uint32_t (&a0)[L], const uint32_t* b0, const uint32_t (&a1)[L],
+                                  const uint32_t* b1, const uint32_t (&a2)[L], const uint32_t* b2) {
+    uint32_t X[W], Y[W];
+#ifdef BGN_HOSTSIM
+    {
+      double A0 = BGN_GETB(a0), B0 = BGN_GETB(b0), A1 = BGN_GETB(a1), B1 = BGN_GETB(b1), A2 = BGN_GETB(a2), B2 = BGN_GETB(b2);
+      BGN_CHECK(2.0 * (A0 + A1 + A2 + 1.0) <= bgnsim::headroom, "dot product multiplicands too large");
+      BGN_CHECK(B0 <= bgnsim::headroom && B1 <= bgnsim::headroom && B2 <= bgnsim::headroom, "dot product multiplier too large");
+      BGN_SETB(r, (A0 * B0 + A1 * B1 + A2 * B2) / bgnsim::headroom + 1.0);
+      bgnsim::ndot3++;
+    }
+#endif
+    const uint32_t* pm = c_fc.p;
+    const uint32_t np0 = c_fc.np0;
+    row3<true>(X, Y, a0, b0[0], a1, b1[0], a2, b2[0], pm, np0);
+    BGN_UNROLL
+    for (int i = 1; i + 1 < L; i += 2) {
+      row3<false>(Y, X, a0, b0[i * ES], a1, b1[i * ES], a2, b2[i * ES], pm, np0);
+      row3<false>(X, Y, a0, b0[(i + 1) * ES], a1, b1[(i + 1) * ES], a2, b2[(i + 1) * ES], pm, np0);
+    }
+    if ((L & 1) == 0) {
+      row3<false>(Y, X, a0, b0[(L - 1) * ES], a1, b1[(L - 1) * ES], a2, b2[(L - 1) * ES], pm, np0);
       merge(r, X, Y);
     } else {
       merge(r, Y, X);

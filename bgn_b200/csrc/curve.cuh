@@ -114,6 +114,79 @@ struct G {
     FF::sub(Y, t0, t2);
   }
 
+  // ---- the doubling-and-addition step of the Miller loop as ONE step (round 2):
+  //     T <- (T + A) + T = 2T + A,   A = (xA, +-yA) affine,
+  // and the PARABOLA through T (twice), A and -(2T + A) (Eisentraeger-Lauter-Montgomery): the tangent at T and
+  // the chord through 2T and A multiply to parabola x vertical, and the vertical lies in F_p at the distorted
+  // evaluation points, so f <- f^2 * parabola replaces f <- f^2 * tangent * chord -- one F_p^2 product per
+  // evaluation point instead of two.  With R = T + A (slope l1), S = R + T (slope l2):
+  //     g(x, y) = (x - xT)(x + xT + xR + l1 l2) - (l1 + l2)(y - yT)
+  // In Jacobian coordinates, T = (X, Y, Z):  ZZ = Z^2, H = xA ZZ - X, N1 = yA Z^3 - Y, ZR = Z H,
+  //     U = X H^2, W = Y H^3 (T on R's Z), XR = N1^2 - H^3 - 2U, YR = N1 (U - XR) - W;
+  // S by the co-Z addition: H2 = XR - U, N2 = YR - W, A2 = H2^2, B2 = U A2, C2 = XR A2,
+  //     XS = N2^2 - B2 - C2, YS = N2 (B2 - XS) - W (C2 - B2), ZS = ZR H2;
+  // and with An = XR H2 + N1 N2, Sn = N1 H2 + N2, Dn = ZR ZS the parabola scaled by Dn^2, at phi(B) = (-xB, i yB):
+  //     g Dn^2 = [cs xB^2 + c1 xB + c0] + [ci yB] i,
+  //     cs = Dn^2, c1 = -An Dn, c0 = H2 (Sn W - U (U H2 + An)), ci = -Sn Dn ZR.
+  // 11 + 7 + 12 = 30 products where dbl_line + madd_line spend 25; three-address code (its share of the loop is
+  // small; the evaluation side is where the step pays: fused.cuh para_mul).  No special cases, as madd_line.
+  // X, Y, Z are replaced by S; cs, c1, c0, ci receive the coefficients; t0..t7 scratch.
+  BGN_DEV static void dadd_para(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E cs, E c1, E c0,
+                                E ci, E t0, E t1, E t2, E t3, E t4, E t5, E t6, E t7) {
+    FF::sqr(t0, Z);            // ZZ
+    FF::mul(t1, xA, t0);
+    FF::sub(t1, t1, X);        // H
+    FF::mul(t0, Z, t0);        // Z^3
+    FF::mul(t0, yA, t0);
+    if (negate) FF::neg(t0, t0);
+    FF::sub(t0, t0, Y);        // N1
+    FF::mul(Z, Z, t1);         // ZR
+    FF::sqr(t2, t1);           // H^2
+    FF::mul(t3, t1, t2);       // H^3
+    FF::mul(t2, X, t2);        // U
+    FF::mul(t4, Y, t3);        // W
+    FF::sqr(X, t0);
+    FF::sub(X, X, t3);
+    FF::sub(X, X, t2);
+    FF::sub(X, X, t2);         // XR
+    FF::sub(t3, t2, X);
+    FF::mul(Y, t0, t3);
+    FF::sub(Y, Y, t4);         // YR
+    FF::sub(t1, X, t2);        // H2
+    FF::sub(t3, Y, t4);        // N2
+    FF::mul(t5, X, t1);        // XR H2
+    FF::mul(t6, t0, t3);       // N1 N2
+    FF::add(t5, t5, t6);       // An
+    FF::mul(t6, t0, t1);
+    FF::add(t6, t6, t3);       // Sn                         (N1 is dead: t0 free)
+    FF::sqr(t0, t1);           // A2
+    FF::mul(t7, t2, t0);       // B2
+    FF::mul(t0, X, t0);        // C2                         (XR is dead)
+    FF::sqr(X, t3);
+    FF::sub(X, X, t7);
+    FF::sub(X, X, t0);         // XS
+    FF::sub(t0, t0, t7);       // C2 - B2
+    FF::sub(t7, t7, X);        // B2 - XS
+    FF::mul(Y, t3, t7);
+    FF::mul(t0, t4, t0);
+    FF::sub(Y, Y, t0);         // YS                         (N2 is dead: t3 free)
+    FF::mul(t3, Z, t1);        // ZS = ZR H2
+    FF::mul(t7, Z, t3);        // Dn = ZR ZS
+    FF::mul(ci, t6, t7);
+    FF::mul(ci, ci, Z);
+    FF::neg(ci, ci);           // ci = -Sn Dn ZR
+    FF::copy(Z, t3);           // Z <- ZS
+    FF::sqr(cs, t7);           // cs = Dn^2
+    FF::mul(c1, t5, t7);
+    FF::neg(c1, c1);           // c1 = -An Dn
+    FF::mul(t0, t2, t1);       // U H2
+    FF::add(t0, t0, t5);       // U H2 + An
+    FF::mul(t0, t2, t0);       // U (U H2 + An)
+    FF::mul(c0, t6, t4);       // Sn W
+    FF::sub(c0, c0, t0);
+    FF::mul(c0, t1, c0);       // c0 = H2 (Sn W - U (U H2 + An))
+  }
+
   // Complete mixed addition P <- P + (xA, sgn*yA) for scalar multiplication and EAdd: handles
   // P == O, P == A (doubling) and P == -A (-> O).  11 products on the common path.
   BGN_DEVNI static void madd(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E t0, E t1, E t2, E t3) {

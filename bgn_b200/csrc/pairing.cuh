@@ -69,6 +69,14 @@
 #define BGN_EVAL_NORM 1
 #endif
 
+// A NAF digit != 0 as ONE doubling-and-addition step whose tangent and chord are merged into a parabola
+// (curve.cuh: G::dadd_para, fused.cuh: para_mul): one F_p^2 product per evaluation point on those steps instead
+// of two.  Team kernel with the unit-stride layout (up to 17 limbs); needs BGN_EVAL_NORM.  0 restores the two
+// separate steps (A/B).
+#ifndef BGN_PARABOLA
+#define BGN_PARABOLA (BGN_L <= 17 && !BGN_MILLER_GP && BGN_EVAL_NORM ? 1 : 0)
+#endif
+
 BGN_CONST PairConsts c_pc;
 
 template <int L>
@@ -126,13 +134,15 @@ struct MillerTeam {
   static constexpr int NT = BGN_MILLER_NT;
   static constexpr int ES = GP ? NT : 1;          // element stride of every slot
   static constexpr bool NORM = !EG && BGN_EVAL_NORM != 0;  // slots S_EX, S_EY hold (x / y, 1 / y)
+  static constexpr bool PARA = NORM && !GP && BGN_PARABOLA != 0;  // doubling-and-addition steps use the parabola
   typedef MF<L, BGN_TEAM_LOOP_B, ES> M;      // phase B
   typedef MF<L, BGN_MILLER_LOOP_A, ES> MA;   // phase A
   // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
   // the line it publishes, its evaluation point.  The loop's routines are fused (fused.cuh) and
   // keep their temporaries in registers.
-  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_EX = 10, S_EY = 11,
-         NSLOT = EG ? 10 : BGN_MILLER_NSLOT, NPRIV = BGN_MILLER_NPRIV };  // slots < NPRIV are thread-private
+  // (PARA: a 13th slot for the parabola's fourth coefficient; its x^2 / y values live in a global array)
+  enum { S_F0 = 0, S_F1 = 2, S_X = 4, S_Y = 5, S_Z = 6, S_CR = 7, S_AR = 8, S_BI = 9, S_EX = 10, S_EY = 11, S_C3 = 12,
+         NSLOT = EG ? 10 : (PARA ? 13 : BGN_MILLER_NSLOT), NPRIV = BGN_MILLER_NPRIV };  // slots < NPRIV are thread-private
 
   const MillerArgs& a;
   uint32_t* smem;   // the block's slots (layout: slot()), then one flagsA and one flagsB byte per thread
@@ -223,6 +233,49 @@ struct MillerTeam {
       s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);
       s_in(slot(tid, S_EY), a.Ey + eidx(t) * L);
       if (NORM) MA::eval_normalise(slot(tid, S_EX), slot(tid, S_EY));
+      if (PARA) FF::mul(a.evw + eidx(t) * L, a.Ex + eidx(t) * L, slot(tid, S_EX));  // x^2 / y = x * (x / y)
+    }
+  }
+
+  // phase A of a doubling-and-addition step: square own accumulators, replace own Miller point T by 2T +- A and
+  // publish the parabola (slots S_CR, S_AR, S_BI, S_C3 = cs, c1, c0, ci)
+  BGN_DEV void phaseA_dadd(int op) {
+    if (!active) return;
+    MA::sqr2(slot(tid, S_F0), slot(tid, S_F0 + 1));
+    if (t + a.dE < a.dM + a.dE - 1) MA::sqr2(slot(tid, S_F1), slot(tid, S_F1 + 1));
+    if (t < a.dM && flagsA()[tid]) {
+      Loc<L> t0, t1, t2, t3, t4, t5, t6, t7;
+      size_t idx = (size_t)unit * a.dM + t;
+      MA::norm1(slot(tid, S_X));
+      MA::norm1(slot(tid, S_Y));
+      MA::norm1(slot(tid, S_Z));
+      GG::dadd_para(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
+                    slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), slot(tid, S_C3), t0.v(), t1.v(), t2.v(), t3.v(),
+                    t4.v(), t5.v(), t6.v(), t7.v());
+    }
+  }
+  // phase B of such a step: fold parabola_i(B_k) into the slot i+k
+  BGN_DEV void phaseB_para() {
+    if (!active) return;
+    int TS = a.dE;
+    int base = tid - t;
+    for (int i = 0; i < a.dM; i++) {
+      int k = t - i;
+      int s = 0;
+      if (k < 0) {
+        k += TS;
+        s = 1;
+      }
+      if (!flagsA()[base + i] || !flagsB()[base + k]) continue;
+      E fr = slot(tid, S_F0 + 2 * s), fi = slot(tid, S_F0 + 2 * s + 1);
+      const uint32_t *cs = slot(base + i, S_CR), *c1 = slot(base + i, S_AR), *c0 = slot(base + i, S_BI),
+                     *ci = slot(base + i, S_C3);
+      const uint32_t *eu = slot(base + k, S_EX), *ev = slot(base + k, S_EY), *ew = a.evw + eidx(k) * L;
+#if BGN_LINE_LAZY
+      M::template para_mul_lazy<BGN_LINE_KARATSUBA>(fr, fi, cs, c1, c0, ci, eu, ev, ew);
+#else
+      M::para_mul(fr, fi, cs, c1, c0, ci, eu, ev, ew);
+#endif
     }
   }
 
@@ -337,12 +390,20 @@ struct MillerTeam {
     sync();
     int n = c_pc.naf_len;
     for (int idx = 1; idx < n; idx++) {
+      int d = c_pc.naf[idx];
+      const bool add = d != 0 && idx != n - 1;
+      if (PARA && add) {  // never the first step: a NAF has no two adjacent non-zero digits
+        phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
+        sync();
+        phaseB_para();
+        sync();
+        continue;
+      }
       phaseA(MOP_DBL, idx == 1);
       sync();
       phaseB();
       sync();
-      int d = c_pc.naf[idx];
-      if (d != 0 && idx != n - 1) {
+      if (add) {
         phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
         sync();
         phaseB();

@@ -51,6 +51,9 @@ struct MillerArgs {
   int teams_per_group;  // whole teams in one barrier group
   int group_threads;    // threads per barrier group (128 on the GPU); blockDim = groups * group_threads
   int skew_cycles;      // start-up delay of odd groups (decorrelates the two warps of a scheduler)
+  // global scratch of the parabola steps (pairing.cuh: BGN_PARABOLA): x^2 / y of every evaluation point,
+  // [count * dE][L] ([dE][L] with e_bcast); written by the kernel's init, read in its phase B
+  uint32_t* evw;
 };
 
 // Pairing with a FIXED first argument (makeL2: e(C, P) = e(P, C), bgn.go:316-321; level-1 decrypt;

@@ -96,28 +96,65 @@ def line_products(L: int, eval_norm: bool = None) -> int:
     return ev + (3 * L * L + 2 * (L * L + L) if line_lazy(L) else 3 * full)
 
 
-def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bool = None) -> int:
+PARABOLA = True  # pairing.cuh BGN_PARABOLA (unit-stride layout, up to 17 limbs): digit != 0 -> one parabola step
+
+
+def parabola_on(L: int, eval_norm: bool = None, parabola: bool = None) -> bool:
+    eval_norm = EVAL_NORM if eval_norm is None else eval_norm
+    parabola = PARABOLA if parabola is None else parabola
+    return bool(parabola and eval_norm and L <= 17)
+
+
+def para_products(L: int) -> int:
+    """one parabola folded into an accumulator (fused.cuh: para_mul_lazy / para_mul): a three-term dot product
+    (4L^2 + L) and an F_p^2 product (3 L^2 + 2 (L^2 + L) lazily reduced, else 3 (2L^2 + L))"""
+    full = products_per_modmul(L)
+    return (4 * L * L + L) + (3 * L * L + 2 * (L * L + L) if line_lazy(L) else 3 * full)
+
+
+DADD_MULS, DADD_SQRS = 24, 6  # curve.cuh G::dadd_para (three-address code: its squarings are dedicated ones)
+
+
+def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bool = None, parabola: bool = None) -> int:
     """32x32->64 products one unit of k_miller executes.  Every F_p product is a fused
     multiply-and-reduce of 2L^2 + L, except the lines (line_products), the squarings where the
     dedicated routine is used (L (L + 1) / 2 + L^2 + L), and -- with normalised evaluation points --
-    one inversion (its two products of glue) and one product per evaluation point before the loop."""
+    one inversion (its two products of glue) and one product per evaluation point before the loop.
+    With the parabola step a NAF digit != 0 costs dM dadd_para (24 products, 6 squarings) and dM dE
+    para_products instead of a doubling and an addition step with dM dE lines each; the x^2 / y of the
+    evaluation points is one more product each before the loop."""
     eval_norm = EVAL_NORM if eval_norm is None else eval_norm
     L = pick_limbs(p)
-    mm = miller_unit_modmuls(p, n, l, dM, dE)
-    nsq = miller_unit_squarings(p, n, l, dM, dE)
     full, sq = products_per_modmul(L), products_per_sqr(L)
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
-    lines = (D + A) * dM * dE
+    nslots = dM + dE - 1
+    fe = final_exp_modmuls(p, l, L, nslots, dE)
     prep = dE * (GCD_INV_MODMULS + 1) if eval_norm else 0
+    nsq = miller_unit_squarings(p, n, l, dM, dE)   # dedicated squarings inside the fused routines (FUSED_SQR)
+    if parabola_on(L, eval_norm, parabola):
+        plain = (D - A) * dM * 12 + (D - 1) * nslots * 2 + fe + prep + dE   # fused products outside lines / parabolas
+        return ((plain - nsq + A * dM * DADD_MULS) * full + (nsq + A * dM * DADD_SQRS) * sq
+                + (D - A) * dM * dE * line_products(L, eval_norm) + A * dM * dE * para_products(L))
+    mm = miller_unit_modmuls(p, n, l, dM, dE)
+    lines = (D + A) * dM * dE
     return (mm - 5 * lines - nsq + prep) * full + lines * line_products(L, eval_norm) + nsq * sq
 
 
-def miller_unit_lines(n: int, dM: int, dE: int) -> int:
-    """lines folded into accumulators by one unit of k_miller: one per (Miller point, evaluation point) and step"""
+def miller_unit_lines(n: int, dM: int, dE: int, L: int = 17) -> int:
+    """lines folded into accumulators by one unit of k_miller: one per (Miller point, evaluation point) and step;
+    with the parabola step only the steps whose digit is zero have lines"""
     naf = naf_digits(n)
-    return (len(naf) - 1 + sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)) * dM * dE
+    D = len(naf) - 1
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    return ((D - A) if parabola_on(L) else (D + A)) * dM * dE
+
+
+def miller_unit_parabolas(n: int, dM: int, dE: int, L: int = 17) -> int:
+    naf = naf_digits(n)
+    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    return A * dM * dE if parabola_on(L) else 0
 
 
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:

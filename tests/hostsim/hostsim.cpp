@@ -55,6 +55,8 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
   std::vector<uint32_t> priv((size_t)nblocks * MillerTeam<L, EG>::priv_words() + 8);
   MillerArgs a = a0;
   a.priv = priv.data();
+  std::vector<uint32_t> evw((size_t)(a.e_bcast ? a.dE : a.count * a.dE) * L + 8);
+  a.evw = evw.data();
   for (int b = 0; b < nblocks; b++) {
     std::vector<MillerTeam<L, EG>> T;
     T.reserve(nt);
@@ -62,9 +64,14 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
     for (auto& t : T) t.init();
     int n = c_pc.naf_len;
     for (int idx = 1; idx < n; idx++) {
+      int d = c_pc.naf[idx];
+      if (MillerTeam<L, EG>::PARA && d != 0 && idx != n - 1) {
+        for (auto& t : T) t.phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
+        for (auto& t : T) t.phaseB_para();
+        continue;
+      }
       for (auto& t : T) t.phaseA(MOP_DBL, idx == 1);
       for (auto& t : T) t.phaseB();
-      int d = c_pc.naf[idx];
       if (d != 0 && idx != n - 1) {
         for (auto& t : T) t.phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
         for (auto& t : T) t.phaseB();
@@ -272,7 +279,8 @@ void hs_wide_count(uint64_t* out, int reset) {
   out[2] = bgnsim::nmulk;
   out[3] = bgnsim::ndot2;
   out[4] = bgnsim::nsqrw;
-  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = bgnsim::ndot2 = bgnsim::nsqrw = 0;
+  out[5] = bgnsim::ndot3;
+  if (reset) bgnsim::nmulw = bgnsim::nredc = bgnsim::nmulk = bgnsim::ndot2 = bgnsim::nsqrw = bgnsim::ndot3 = 0;
 }
 uint64_t hs_mul_count(int reset) {
   uint64_t v = bgnsim::nmul;

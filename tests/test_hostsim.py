@@ -341,10 +341,13 @@ def test_work_model_matches_executed_products(kb):
     lib.hs_wide_count(wide, 1)   # double-width multiplications (L^2) and separate reductions (L^2 + L)
     L = S.L
     executed = (fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[3] * (3 * L * L + L)
-                + wide[4] * (L * (L + 1) // 2))
+                + wide[4] * (L * (L + 1) // 2) + wide[5] * (4 * L * L + L))
     assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
-    assert wide[3] == (workmodel.miller_unit_lines(par.n, v["d1"], v["d2"]) if workmodel.EVAL_NORM else 0)
-    assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"])
+    assert wide[3] == (workmodel.miller_unit_lines(par.n, v["d1"], v["d2"], L) if workmodel.EVAL_NORM else 0)
+    assert wide[5] == workmodel.miller_unit_parabolas(par.n, v["d1"], v["d2"], L)
+    naf = workmodel.naf_digits(par.n)
+    adds = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0) if workmodel.parabola_on(L) else 0
+    assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"]) + adds * v["d1"] * workmodel.DADD_SQRS
     assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
 
@@ -362,7 +365,7 @@ def test_range_tracker_proves_miller_ranges(kb):
     worst, headroom, unknown, violations = S.range_report()
     assert headroom == 256.0
     assert unknown == 0 and violations == 0
-    assert 16.0 < worst < 64.0  # the chord slope 2 (S2 - Y + 16p) is the largest value
+    assert 8.0 < worst < 64.0  # (with the parabola step the team kernel no longer forms the chord slope 2 (S2 - Y + 16p))
     assert sim.lib().hs_selftest_violation() == 1  # and the checker does fire
 
 
