@@ -457,12 +457,13 @@ size_t miller_scratch(bgn_ctx* c, size_t count, int dE) {
   size_t pb = c->A->miller_priv_bytes();
   int fixed = c->A->miller_fixed_threads();
   if (!count || dE <= 0) return 0;
-  // unit-stride layout: x^2 / y of every evaluation point for the parabola steps (MillerArgs::evw); a batch
-  // may be served by up to three launches (full waves, remainder), each with its own padded slice
-  if (!pb || !fixed) return pad256(count * (size_t)dE * c->L * 4) + 1024;
+  // x^2 / y of every evaluation point for the parabola steps (MillerArgs::evw); a batch may be served by up to
+  // three launches (full waves, remainder), each with its own padded slice
+  const size_t evw = pad256(count * (size_t)dE * c->L * 4) + 1024;
+  if (!pb || !fixed) return evw;
   if (dE > fixed) return 0;
   size_t upb = (size_t)(fixed / dE);
-  return pad256(((count + upb - 1) / upb + 160) * pb) + 256;  // + one block per SM: small batches are spread out
+  return evw + pad256(((count + upb - 1) / upb + 160) * pb) + 256;  // + one block per SM: small batches are spread out
 }
 
 // ---- the split team kernel (teamsplit.cuh): two threads per output-slot pair, for sub-wave batches
@@ -692,7 +693,7 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.teams_per_group = tpg;
   a.group_threads = GT_;
   a.skew_cycles = c->miller_skew;
-  a.evw = c->A->miller_fixed_threads() ? nullptr : arena_get<uint32_t>(c, (e_bcast ? (size_t)dE : count * (size_t)dE) * c->L);
+  a.evw = arena_get<uint32_t>(c, (e_bcast ? (size_t)dE : count * (size_t)dE) * c->L);
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
   c->A->miller(cfg(c, nblocks, nt, smem), a);

@@ -301,7 +301,14 @@ struct MF {
     P::redc(b, T1);
     st<L, ES>(fim, b);
   }
-  // bring one slot back to [0, 2p) (entry of the three-address parabola step).  in: < 16p.
+  // dst (unit stride, e.g. a global array) <- a (unit stride) * b (slot)
+  BGN_DEVNI static void mul_to_unit(uint32_t* dst, const uint32_t* a, const uint32_t* b) {
+    R x, y;
+    ld<L, 1>(x, a);
+    mulm(y, x, b);
+    st<L, 1>(dst, y);
+  }
+  // bring one slot back to [0, 2p) (entry of the three-address parabola step).  in: < 8p.
   BGN_DEVNI static void norm1(E s) {
     R a;
     ld<L, ES>(a, s);

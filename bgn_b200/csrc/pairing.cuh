@@ -71,10 +71,9 @@
 
 // A NAF digit != 0 as ONE doubling-and-addition step whose tangent and chord are merged into a parabola
 // (curve.cuh: G::dadd_para, fused.cuh: para_mul): one F_p^2 product per evaluation point on those steps instead
-// of two.  Team kernel with the unit-stride layout (up to 17 limbs); needs BGN_EVAL_NORM.  0 restores the two
-// separate steps (A/B).
+// of two.  Team kernel, both layouts; needs BGN_EVAL_NORM.  0 restores the two separate steps (A/B).
 #ifndef BGN_PARABOLA
-#define BGN_PARABOLA (BGN_L <= 17 && !BGN_MILLER_GP && BGN_EVAL_NORM ? 1 : 0)
+#define BGN_PARABOLA (BGN_EVAL_NORM ? 1 : 0)
 #endif
 
 BGN_CONST PairConsts c_pc;
@@ -134,7 +133,7 @@ struct MillerTeam {
   static constexpr int NT = BGN_MILLER_NT;
   static constexpr int ES = GP ? NT : 1;          // element stride of every slot
   static constexpr bool NORM = !EG && BGN_EVAL_NORM != 0;  // slots S_EX, S_EY hold (x / y, 1 / y)
-  static constexpr bool PARA = NORM && !GP && BGN_PARABOLA != 0;  // doubling-and-addition steps use the parabola
+  static constexpr bool PARA = NORM && BGN_PARABOLA != 0;  // doubling-and-addition steps use the parabola
   typedef MF<L, BGN_TEAM_LOOP_B, ES> M;      // phase B
   typedef MF<L, BGN_MILLER_LOOP_A, ES> MA;   // phase A
   // element slots per thread in shared memory: two GT accumulators, the thread's Miller point,
@@ -233,7 +232,7 @@ struct MillerTeam {
       s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);
       s_in(slot(tid, S_EY), a.Ey + eidx(t) * L);
       if (NORM) MA::eval_normalise(slot(tid, S_EX), slot(tid, S_EY));
-      if (PARA) FF::mul(a.evw + eidx(t) * L, a.Ex + eidx(t) * L, slot(tid, S_EX));  // x^2 / y = x * (x / y)
+      if (PARA) MA::mul_to_unit(a.evw + eidx(t) * L, a.Ex + eidx(t) * L, slot(tid, S_EX));  // x^2 / y = x * (x / y)
     }
   }
 
@@ -249,9 +248,26 @@ struct MillerTeam {
       MA::norm1(slot(tid, S_X));
       MA::norm1(slot(tid, S_Y));
       MA::norm1(slot(tid, S_Z));
-      GG::dadd_para(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
-                    slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), slot(tid, S_C3), t0.v(), t1.v(), t2.v(), t3.v(),
-                    t4.v(), t5.v(), t6.v(), t7.v());
+      if (GP) {
+        // interleaved layout: the three-address step works on unit-stride copies
+        Loc<L> X, Y, Z, cs, c1, c0, ci;
+        s_out(X.v(), slot(tid, S_X));
+        s_out(Y.v(), slot(tid, S_Y));
+        s_out(Z.v(), slot(tid, S_Z));
+        GG::dadd_para(X.v(), Y.v(), Z.v(), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB, cs.v(), c1.v(), c0.v(), ci.v(),
+                      t0.v(), t1.v(), t2.v(), t3.v(), t4.v(), t5.v(), t6.v(), t7.v());
+        s_in(slot(tid, S_X), X.v());
+        s_in(slot(tid, S_Y), Y.v());
+        s_in(slot(tid, S_Z), Z.v());
+        s_in(slot(tid, S_CR), cs.v());
+        s_in(slot(tid, S_AR), c1.v());
+        s_in(slot(tid, S_BI), c0.v());
+        s_in(slot(tid, S_C3), ci.v());
+      } else {
+        GG::dadd_para(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
+                      slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), slot(tid, S_C3), t0.v(), t1.v(), t2.v(), t3.v(),
+                      t4.v(), t5.v(), t6.v(), t7.v());
+      }
     }
   }
   // phase B of such a step: fold parabola_i(B_k) into the slot i+k

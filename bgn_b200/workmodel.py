@@ -96,13 +96,13 @@ def line_products(L: int, eval_norm: bool = None) -> int:
     return ev + (3 * L * L + 2 * (L * L + L) if line_lazy(L) else 3 * full)
 
 
-PARABOLA = True  # pairing.cuh BGN_PARABOLA (unit-stride layout, up to 17 limbs): digit != 0 -> one parabola step
+PARABOLA = True  # pairing.cuh BGN_PARABOLA: a NAF digit != 0 is one parabola step
 
 
 def parabola_on(L: int, eval_norm: bool = None, parabola: bool = None) -> bool:
     eval_norm = EVAL_NORM if eval_norm is None else eval_norm
     parabola = PARABOLA if parabola is None else parabola
-    return bool(parabola and eval_norm and L <= 17)
+    return bool(parabola and eval_norm)
 
 
 def para_products(L: int) -> int:
