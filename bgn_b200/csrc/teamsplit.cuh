@@ -30,8 +30,10 @@ struct MillerSplit {
   typedef F<L> FF;
   typedef MF<L, BGN_MILLER_LOOP, 1> M;     // phase B
   typedef MF<L, BGN_MILLER_LOOP_A, 1> MA;  // phase A
+  static constexpr bool PARA = BGN_EVAL_NORM != 0 && BGN_PARABOLA != 0;  // pairing.cuh: doubling-and-addition steps
   enum { A_F0 = 0, A_F1 = 2, NA = 4,                                   // per thread: two partial accumulators
-         C_X = 0, C_Y = 1, C_Z = 2, C_CR = 3, C_AR = 4, C_BI = 5, C_EX = 6, C_EY = 7, NC = 8 };  // per column
+         C_X = 0, C_Y = 1, C_Z = 2, C_CR = 3, C_AR = 4, C_BI = 5, C_EX = 6, C_EY = 7, C_C3 = 8,
+         NC = PARA ? 9 : 8 };  // per column (PARA: the parabola's fourth coefficient)
 
   const MillerArgs& a;
   uint32_t* smem;
@@ -93,6 +95,7 @@ struct MillerSplit {
       FF::copy(cslot(col, C_EX), a.Ex + e * L);
       FF::copy(cslot(col, C_EY), a.Ey + e * L);
       if (BGN_EVAL_NORM) MA::eval_normalise(cslot(col, C_EX), cslot(col, C_EY));  // (x / y, 1 / y): fused.cuh line_mul_n
+      if (PARA) MA::mul_to_unit(a.evw + e * L, a.Ex + e * L, cslot(col, C_EX));         // x^2 / y
     }
   }
 
@@ -117,6 +120,58 @@ struct MillerSplit {
         MA::madd_line(cslot(col, C_X), cslot(col, C_Y), cslot(col, C_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
                       cslot(col, C_CR), cslot(col, C_AR), cslot(col, C_BI));
       }
+    }
+  }
+
+  // a doubling-and-addition step (pairing.cuh: MillerTeam::phaseA_dadd / phaseB_para) with the same split:
+  // (t, 1) squares the four partial accumulators of column t, (t, 0) replaces Miller point t by 2T +- A and
+  // publishes the parabola; then each half folds its share of the parabolas
+  BGN_DEV void phaseA_dadd(int op) {
+    if (!active) return;
+    if (h == 1) {
+      MA::sqr2(acc(tid, A_F0), acc(tid, A_F0 + 1));
+      MA::sqr2(acc(ptid, A_F0), acc(ptid, A_F0 + 1));
+      if (owns2()) {
+        MA::sqr2(acc(tid, A_F1), acc(tid, A_F1 + 1));
+        MA::sqr2(acc(ptid, A_F1), acc(ptid, A_F1 + 1));
+      }
+      return;
+    }
+    if (t < a.dM && flagsA()[col]) {
+      Loc<L> t0, t1, t2, t3, t4, t5, t6, t7;
+      size_t idx = (size_t)unit * a.dM + t;
+      MA::norm1(cslot(col, C_X));
+      MA::norm1(cslot(col, C_Y));
+      MA::norm1(cslot(col, C_Z));
+      G<L>::dadd_para(cslot(col, C_X), cslot(col, C_Y), cslot(col, C_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
+                      cslot(col, C_CR), cslot(col, C_AR), cslot(col, C_BI), cslot(col, C_C3), t0.v(), t1.v(), t2.v(),
+                      t3.v(), t4.v(), t5.v(), t6.v(), t7.v());
+    }
+  }
+  BGN_DEV void phaseB_para() {
+    if (!active) return;
+    const int TS = a.dE;
+    const int mid = (a.dM + 1) / 2;
+    // the half that advanced the Miller point (30 products against 8 squarings) folds the smaller share
+    const int i0 = h ? a.dM - mid : 0, i1 = h ? a.dM : a.dM - mid;
+    for (int i = i0; i < i1; i++) {
+      int k = t - i;
+      int s = 0;
+      if (k < 0) {
+        k += TS;
+        s = 1;
+      }
+      if (!flagsA()[base_col + i] || !flagsB()[base_col + k]) continue;
+      E fr = acc(tid, A_F0 + 2 * s), fi = acc(tid, A_F0 + 2 * s + 1);
+      const size_t e = a.e_bcast ? (size_t)k : (size_t)unit * a.dE + k;
+#if BGN_LINE_LAZY
+      M::template para_mul_lazy<BGN_LINE_KARATSUBA>(fr, fi, cslot(base_col + i, C_CR), cslot(base_col + i, C_AR),
+                                                    cslot(base_col + i, C_BI), cslot(base_col + i, C_C3),
+                                                    cslot(base_col + k, C_EX), cslot(base_col + k, C_EY), a.evw + e * L);
+#else
+      M::para_mul(fr, fi, cslot(base_col + i, C_CR), cslot(base_col + i, C_AR), cslot(base_col + i, C_BI),
+                  cslot(base_col + i, C_C3), cslot(base_col + k, C_EX), cslot(base_col + k, C_EY), a.evw + e * L);
+#endif
     }
   }
 
@@ -204,11 +259,18 @@ struct MillerSplit {
     sync();
     int n = c_pc.naf_len;
     for (int idx = 1; idx < n; idx++) {
+      int d = c_pc.naf[idx];
+      if (PARA && a.para && d != 0 && idx != n - 1) {
+        phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
+        sync();
+        phaseB_para();
+        sync();
+        continue;
+      }
       phaseA(MOP_DBL, idx == 1);
       sync();
       phaseB();
       sync();
-      int d = c_pc.naf[idx];
       if (d != 0 && idx != n - 1) {
         phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
         sync();

@@ -54,6 +54,7 @@ struct MillerArgs {
   // global scratch of the parabola steps (pairing.cuh: BGN_PARABOLA): x^2 / y of every evaluation point,
   // [count * dE][L] ([dE][L] with e_bcast); written by the kernel's init, read in its phase B
   uint32_t* evw;
+  int para;  // k_miller_split only: use the parabola steps (api.cu: launch_miller_split chooses by block geometry)
 };
 
 // Pairing with a FIXED first argument (makeL2: e(C, P) = e(P, C), bgn.go:316-321; level-1 decrypt;

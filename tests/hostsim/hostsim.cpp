@@ -82,8 +82,11 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
 }
 // k_miller_split (teamsplit.cuh): the same phase schedule as sim_miller, 2 dE threads per team
 template <int L>
-void sim_miller_split(const MillerArgs& a, int nblocks, int nt) {
+void sim_miller_split(const MillerArgs& a0, int nblocks, int nt) {
+  MillerArgs a = a0;
   std::vector<uint32_t> smem(MillerSplit<L>::smem_words(nt, a.teams_per_group * a.dE) + 8);
+  std::vector<uint32_t> evw((size_t)(a.e_bcast ? a.dE : a.count * a.dE) * L + 8);
+  a.evw = evw.data();
   for (int b = 0; b < nblocks; b++) {
     std::vector<MillerSplit<L>> T;
     T.reserve(nt);
@@ -91,9 +94,14 @@ void sim_miller_split(const MillerArgs& a, int nblocks, int nt) {
     for (auto& t : T) t.init();
     int n = c_pc.naf_len;
     for (int idx = 1; idx < n; idx++) {
+      int d = c_pc.naf[idx];
+      if (MillerSplit<L>::PARA && a.para && d != 0 && idx != n - 1) {
+        for (auto& t : T) t.phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
+        for (auto& t : T) t.phaseB_para();
+        continue;
+      }
       for (auto& t : T) t.phaseA(MOP_DBL, idx == 1);
       for (auto& t : T) t.phaseB();
-      int d = c_pc.naf[idx];
       if (d != 0 && idx != n - 1) {
         for (auto& t : T) t.phaseA(d > 0 ? MOP_ADD : MOP_SUB, false);
         for (auto& t : T) t.phaseB();

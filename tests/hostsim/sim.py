@@ -36,7 +36,7 @@ class MillerArgs(C.Structure):
     _fields_ = [("Mx", u32p), ("My", u32p), ("Minf", u8p), ("Ex", u32p), ("Ey", u32p), ("Einf", u8p),
                 ("priv", u32p), ("out_re", u32p), ("out_im", u32p), ("NM", C.c_int), ("NE", C.c_int), ("NOUT", C.c_int),
                 ("e_bcast", C.c_int), ("dM", C.c_int), ("dE", C.c_int), ("out_slots", C.c_int), ("count", C.c_int),
-                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int), ("evw", u32p)]
+                ("teams_per_group", C.c_int), ("group_threads", C.c_int), ("skew_cycles", C.c_int), ("evw", u32p), ("para", C.c_int)]
 
 
 class MillerFixedArgs(C.Structure):
@@ -260,14 +260,14 @@ class Sim:
         oim = np.zeros((nout, self.L), dtype=np.uint32)
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
-                       teams_per_block * dE + 1, 0, None)  # one idle thread per group: exercises the inactive path
+                       teams_per_block * dE + 1, 0, None, 1)  # one idle thread per group: exercises the inactive path
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
         nblocks = (count + groups * teams_per_block - 1) // (groups * teams_per_block)
         assert (lib().hs_miller_wide if wide else lib().hs_miller)(self.L, C.byref(a), nblocks, nt) == 0
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))
 
-    def miller_split(self, M, dM, E, dE, count, out_slots, teams_per_block=2):
+    def miller_split(self, M, dM, E, dE, count, out_slots, teams_per_block=2, para=1):
         """k_miller_split (teamsplit.cuh): two threads per output-slot pair"""
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
@@ -276,7 +276,7 @@ class Sim:
         oim = np.zeros((nout, self.L), dtype=np.uint32)
         nt = 2 * (teams_per_block * dE + 2)  # two halves (one role each) with idle threads: the inactive path
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
-                       Ex.shape[0], nout, 0, dM, dE, out_slots, count, teams_per_block, nt, 0, None)
+                       Ex.shape[0], nout, 0, dM, dE, out_slots, count, teams_per_block, nt, 0, None, para)
         nblocks = (count + teams_per_block - 1) // teams_per_block
         assert lib().hs_miller_split(self.L, C.byref(a), nblocks, nt) == 0
         return list(zip(self.unsoa(ore, nout), self.unsoa(oim, nout)))

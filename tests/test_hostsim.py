@@ -237,6 +237,7 @@ def test_sim_multpoly_split(kb):
     c1, c2 = g1s(par, v["c1"]), g1s(par, v["c2"])
     S.range_report()
     assert S.multpoly_split(c1, v["d1"], c2, v["d2"], 1) == gts(par, v["out"])
+    assert S.multpoly_split(c1, v["d1"], c2, v["d2"], 1, para=0) == gts(par, v["out"])  # separate doubling / addition steps
     hi, headroom, unknown, viol = S.range_report()
     assert viol == 0 and unknown == 0 and hi <= 40.0, (hi, unknown, viol)
     if kb < 512:
