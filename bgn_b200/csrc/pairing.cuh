@@ -452,51 +452,75 @@ struct MillerFixed {
     return n;
   }
 
-  // The line table of the affine point (px, py): the Miller loop's point arithmetic alone, one thread, in
-  // the step order of MillerTeam::run, every line (cR, aR, bI) NORMALISED by its third coefficient:
-  // lines[step] = [cR / bI | aR / bI] -- F_p factors of a line value die in the final exponentiation, and
-  // the line at (xB, yB) becomes (cRn + aRn xB) + yB i (fused.cuh: line_mul_f).  The divisions share one
-  // inversion (Montgomery's trick over all steps); scratch holds [step][bI | prefix product].  *ok = 0 if
-  // some bI is zero -- only possible when (px, py) is not a point of odd order -- and the table is then
-  // unusable (api.cu falls back to the general kernel).
+  // a NAF digit != 0 below the top one is ONE doubling-and-addition step with a parabola entry (BGN_PARABOLA)
+  static constexpr bool PARA = BGN_PARABOLA != 0;
+  static BGN_HD bool is_dadd(const PairConsts& pc, int idx) { return PARA && pc.naf[idx] != 0 && idx != pc.naf_len - 1; }
+
+  // The table of the affine point (px, py): the Miller loop's point arithmetic alone, one thread, in the step
+  // order of MillerTeam::run, every entry NORMALISED by its imaginary coefficient -- F_p factors of a line
+  // value die in the final exponentiation:
+  //     doubling step            [cR / bI | aR / bI]             line at (xB, yB): (cRn + aRn xB) + yB i
+  //     doubling-and-addition    [cs / ci | c1 / ci | c0 / ci]   parabola: ((csn xB + c1n) xB + c0n) + yB i
+  // (without BGN_PARABOLA: a doubling and an addition entry of two elements each).  The divisions share one
+  // inversion (Montgomery's trick over all steps); scratch holds [step][denominator | prefix product].  *ok = 0
+  // if some denominator is zero -- only possible when (px, py) is not a point of odd order -- and the table is
+  // then unusable (api.cu falls back to the general kernel).  At most nsteps() * 2 elements either way.
   BGN_DEV static void record(const uint32_t* px, const uint32_t* py, uint32_t* lines, uint32_t* scratch, int* ok) {
     typedef F<L> FF;
-    Loc<L> X, Y, Z, cR, aR, bI, acc, t;
+    Loc<L> X, Y, Z, cR, aR, bI, c3, acc, t;
+    Loc<L> t0, t1, t2, t3, t4, t5, t6, t7;
     FF::copy(X.v(), px);
     FF::copy(Y.v(), py);
     FF::copy(Z.v(), c_fc.one);
     FF::copy(acc.v(), c_fc.one);
     const int n = c_pc.naf_len;
     int ns = 0;
-    auto emit = [&]() {
-      uint32_t* ln = lines + (size_t)ns * 2 * L;
+    uint32_t* ln = lines;
+    auto emit = [&](int nnum, const uint32_t* den) {  // numerators cR, aR[, bI]; denominator den
       uint32_t* sc = scratch + (size_t)ns * 2 * L;
       FF::copy(ln, cR.v());
       FF::copy(ln + L, aR.v());
-      FF::copy(sc, bI.v());
+      if (nnum == 3) FF::copy(ln + 2 * L, bI.v());
+      ln += (size_t)nnum * L;
+      FF::copy(sc, den);
       FF::copy(sc + L, acc.v());
-      FF::mul(acc.v(), acc.v(), bI.v());
+      FF::mul(acc.v(), acc.v(), den);
       ns++;
     };
     for (int idx = 1; idx < n; idx++) {
-      MA::dbl_line(X.v(), Y.v(), Z.v(), cR.v(), aR.v(), bI.v());
-      emit();
       int d = c_pc.naf[idx];
+      if (is_dadd(c_pc, idx)) {
+        MA::norm1(X.v());
+        MA::norm1(Y.v());
+        MA::norm1(Z.v());
+        G<L>::dadd_para(X.v(), Y.v(), Z.v(), px, py, d < 0, cR.v(), aR.v(), bI.v(), c3.v(), t0.v(), t1.v(), t2.v(), t3.v(),
+                        t4.v(), t5.v(), t6.v(), t7.v());
+        emit(3, c3.v());
+        continue;
+      }
+      MA::dbl_line(X.v(), Y.v(), Z.v(), cR.v(), aR.v(), bI.v());
+      emit(2, bI.v());
       if (d != 0 && idx != n - 1) {
         MA::madd_line(X.v(), Y.v(), Z.v(), px, py, d < 0, cR.v(), aR.v(), bI.v());
-        emit();
+        emit(2, bI.v());
       }
     }
     *ok = FF::is_zero(acc.v()) ? 0 : 1;
     if (!*ok) return;
     FF::template inv_gcd<true>(acc.v(), acc.v());
-    for (int k = ns - 1; k >= 0; k--) {
-      uint32_t* ln = lines + (size_t)k * 2 * L;
-      uint32_t* sc = scratch + (size_t)k * 2 * L;
-      FF::mul(t.v(), acc.v(), sc + L);    // 1 / bI_k
-      FF::mul(acc.v(), acc.v(), sc);      // drop bI_k from the running inverse
-      FF::mul(ln, ln, t.v());
-      FF::mul(ln + L, ln + L, t.v());
+    // backwards over the entries: the same walk, from the last step
+    int k = ns - 1;
+    for (int idx = n - 1; idx >= 1; idx--) {
+      int d = c_pc.naf[idx];
+      const int entries = is_dadd(c_pc, idx) ? 1 : ((d != 0 && idx != n - 1) ? 2 : 1);
+      for (int q = 0; q < entries; q++, k--) {
+        const int nnum = is_dadd(c_pc, idx) ? 3 : 2;
+        ln -= (size_t)nnum * L;
+        uint32_t* sc = scratch + (size_t)k * 2 * L;
+        FF::mul(t.v(), acc.v(), sc + L);    // 1 / den_k
+        FF::mul(acc.v(), acc.v(), sc);      // drop den_k from the running inverse
+        for (int j = 0; j < nnum; j++) FF::mul(ln + (size_t)j * L, ln + (size_t)j * L, t.v());
+      }
     }
   }
 
@@ -527,6 +551,15 @@ struct MillerFixed {
     BGN_UNROLL1
     for (int idx = 1; idx < n; idx++) {
       if (idx != 1) MA::sqr2(fr, fi);
+      if (is_dadd(c_pc, idx)) {
+#if BGN_LINE_LAZY
+        M::template para_mul_lazy_f<BGN_LINE_KARATSUBA>(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+#else
+        M::para_mul_f(fr, fi, ln, ln + L, ln + 2 * L, ex, ey);
+#endif
+        ln += 3 * L;
+        continue;
+      }
       fold();
       if (c_pc.naf[idx] != 0 && idx != n - 1) fold();
     }

@@ -41,6 +41,7 @@ struct MillerFixedPair {
   struct State {
     uint32_t f0[L], f1[L];  // accumulator, both coordinates in both lanes (relaxed range, below 4p)
     uint32_t ex[L], ey[L];  // the evaluation point, in both lanes
+    uint32_t e2[L];         // lane 0: xB^2, lane 1: xB (the multiplicand of this lane's half of a parabola's real part)
   };
 
   BGN_DEV static void init(State& st, const uint32_t* ex, const uint32_t* ey, int s, bool active) {
@@ -57,6 +58,11 @@ struct MillerFixedPair {
     BGN_SETB(st.f1, 0.0);
     BGN_UNROLL
     for (int j = 0; j < L; j++) st.f1[j] = 0;
+    if (MillerFixed<L>::PARA) {
+      uint32_t sq[L];
+      P::mul(sq, st.ex, st.ex);
+      LU::sel(st.e2, s == 0, sq, st.ex);
+    }
   }
   // this lane's half of f^2.  in: f < 4p.  out: < 3p.
   BGN_DEV static void sqr_half(uint32_t (&t)[L], const State& st, int s) {
@@ -74,6 +80,18 @@ struct MillerFixedPair {
     uint32_t c[L];
     P::mul_stream(t, st.ex, ln + L);
     ld<L>(c, ln);
+    P::addn(t, t, c);
+  }
+  // this lane's half of the real part of the normalised parabola ln = [csn | c1n | c0n] at the evaluation
+  // point: lane 0 csn xB^2 + c0n, lane 1 c1n xB; the sum of the halves is the real part.  out: < 4p.
+  BGN_DEV static void eval_para_half(uint32_t (&t)[L], const State& st, const uint32_t* ln, int s) {
+    uint32_t c[L], z[L];
+    P::mul_stream(t, st.e2, ln + (s == 0 ? 0 : L));
+    ld<L>(c, ln + 2 * L);
+    BGN_SETB(z, 0.0);
+    BGN_UNROLL
+    for (int j = 0; j < L; j++) z[j] = 0;
+    LU::sel(c, s == 0, c, z);
     P::addn(t, t, c);
   }
   // this lane's coordinate of f * (l0 + l1 i), `mine` being the coordinate of l this lane evaluated:
@@ -166,14 +184,29 @@ struct MillerFixedPair {
         xchg(other, mine);
         update(st, mine, other, s);
       }
+      if (MillerFixed<L>::is_dadd(c_pc, idx)) {
+        // doubling-and-addition step: one parabola entry, its real part evaluated in halves by the two lanes
+        eval_para_half(lm, st, ln, s);
+        xchg(lo, lm);
+        P::addn(cur, lm, lo);
+        LU::sel(lm, s == 0, cur, st.ey);
+        LU::sel(lo, s == 0, st.ey, cur);
+        mul_half(mine, st, lm, lo, s);
+        xchg(other, mine);
+        update(st, mine, other, s);
+        ln += 3 * L;
+        left -= 2;
+        continue;
+      }
       BGN_UNROLL1
       for (int k = 0; k < folds; k++) {
-        if (!have) {  // lane 0 evaluates this line, lane 1 the next one (the last line: both this one)
-          eval_line(lm, st, ln + (left > 1 ? s : 0) * 2 * L);
+        if (!have) {  // lane 0 evaluates this line, lane 1 the next entry if that is a line too
+          const bool pair = MillerFixed<L>::PARA ? (idx + 1 < n && !MillerFixed<L>::is_dadd(c_pc, idx + 1)) : left > 1;
+          eval_line(lm, st, ln + (pair ? s : 0) * 2 * L);
           xchg(lo, lm);
           LU::sel(cur, s == 0, lm, lo);
           LU::sel(nxt, s == 0, lo, lm);
-          have = left > 1;
+          have = pair;
         } else {
           LU::sel(cur, true, nxt, nxt);
           have = false;

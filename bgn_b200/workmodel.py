@@ -170,34 +170,55 @@ def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:
     return D * per_dbl + (D - 1) * nslots * 2 + A * per_add + final_exp_modmuls(p, l, L, nslots, dE)
 
 
-def miller_fixed_products(p: int, n: int, l: int) -> int:
-    """32x32->64 products of one k_miller_fixed thread (pairing with the recorded, normalised line table
-    of a fixed first argument): per step one line (fused.cuh: line_mul_lazy_f up to 17 limbs -- one
-    evaluation product, three double-width products, two reductions -- else line_mul_f, 4 products) and,
-    on doubling steps after the first, one sqr2; then the final exponentiation of one slot."""
+def miller_fixed_products(p: int, n: int, l: int, parabola: bool = None) -> int:
+    """32x32->64 products of one k_miller_fixed thread (pairing with the recorded, normalised table of a
+    fixed first argument): per doubling step one line (fused.cuh: line_mul_lazy_f up to 17 limbs -- one
+    evaluation product, three double-width products, two reductions -- else line_mul_f, 4 products); per
+    doubling-and-addition step one parabola (para_mul_lazy_f: two evaluation products; without the parabola
+    step: two lines); on every step after the first one sqr2; then the final exponentiation of one slot."""
+    parabola = PARABOLA if parabola is None else parabola
     L = pick_limbs(p)
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
     full = products_per_modmul(L)
-    line = (full + 3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 4 * full
+    fp2 = (3 * L * L + 2 * (L * L + L)) if line_lazy(L) else 3 * full
     nsq = 2 if fused_sqr(L) else 0  # fe_prepare: f0^2, f1^2
-    return (D + A) * line + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1) - nsq) * full + nsq * products_per_sqr(L)
+    folds = (D - A) * (full + fp2) + A * (2 * full + fp2) if parabola else (D + A) * (full + fp2)
+    return folds + ((D - 1) * 2 + final_exp_modmuls(p, l, L, 1, 1) - nsq) * full + nsq * products_per_sqr(L)
 
 
-def miller_fixed_pair_counts(p: int, n: int, l: int):
+def miller_fixed_pair_counts(p: int, n: int, l: int, parabola: bool = None):
     """k_miller_fixed_pair (pairlane.cuh), BOTH lanes of one pairing together:
     -> (dot products, plain Montgomery products incl. the inversion's glue).
-    Per step a dot-product half per lane, per TWO steps one line evaluation per lane (the table is
-    normalised: only the real part of a line costs a product, and the lanes evaluate two consecutive lines
-    at once), a squaring half per lane on doubling steps after the first; final exponentiation: f0^2 | f1^2,
-    f0 f1 and the scaling in both lanes, the verified inversion (3 products) in both lanes, then g^l."""
+    Per table entry a dot-product half per lane; a line's real part costs one product and the lanes evaluate
+    two consecutive line entries at once; a parabola's real part is one product per lane (csn xB^2 | c1n xB;
+    xB^2 is one more product per lane before the loop); a squaring half per lane on every step after the
+    first; final exponentiation: f0^2 | f1^2, f0 f1 and the scaling in both lanes, the verified inversion
+    (3 products) in both lanes, then g^l."""
+    parabola = PARABOLA if parabola is None else parabola
     naf = naf_digits(n)
-    D = len(naf) - 1
-    A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
+    N = len(naf)
+    D = N - 1
+    A = sum(1 for i in range(1, N - 1) if naf[i] != 0)
     lb, lw = l.bit_length() - 1, bin(l).count("1") - 1
-    dots = 2 * (D + A) + 2 * lw
-    muls = 2 * ((D + A + 1) // 2) + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
+    if not parabola:
+        dots = 2 * (D + A) + 2 * lw
+        muls = 2 * ((D + A + 1) // 2) + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
+        return dots, muls
+    is_dadd = lambda i: naf[i] != 0 and i != N - 1
+    rounds, have = 0, False
+    for idx in range(1, N):
+        if is_dadd(idx):
+            rounds += 1
+            continue
+        if not have:
+            rounds += 1
+            have = idx + 1 < N and not is_dadd(idx + 1)
+        else:
+            have = False
+    dots = 2 * D + 2 * lw
+    muls = 2 * rounds + 2 + 2 * (D - 1) + 2 * (1 + 1 + 1 + 3) + 2 * lb
     return dots, muls
 
 
