@@ -703,7 +703,7 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
   a.group_threads = GT_;
   a.skew_cycles = c->miller_skew;
   a.evw = arena_get<uint32_t>(c, (e_bcast ? (size_t)dE : count * (size_t)dE) * c->L);
-  a.para = 1;
+  a.para = dE >= 3 ? 1 : 0;
   Timer t(c, "k_miller");
   CK(c->A->miller_set_smem(smem));
   c->A->miller(cfg(c, nblocks, nt, smem), a);

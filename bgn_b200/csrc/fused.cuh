@@ -523,6 +523,92 @@ struct MF {
     st<L, ES>(Y, w);               // Y3 = r (V - X3) - 2 Y J
   }
 
+  // ---- the doubling-and-addition step T <- (T + A) + T with its parabola (curve.cuh: G::dadd_para has the
+  // formulas), fused: 22 products, 6 squarings and one dot product, every product (register) x (memory), the
+  // seven slots X, Y, Z, cs, c1, c0, ci doubling as the multipliers' storage in an order that never overwrites
+  // a value still to be read.
+  // in: X, Y, Z < 9p; xA, yA < 2p.   out: X, Y < 9p, Z < 3p; cs, c1, c0, ci < 8p.
+  BGN_DEVNI static void dadd_para(E X, E Y, E Z, const uint32_t* xA, const uint32_t* yA, bool negate, E cs, E c1, E c0,
+                                  E ci) {
+    R a, b, h, n1, zr, u, w, xr, n2, an, sn, t;
+    ld<L, ES>(a, Z);
+    sqrm(b, a, Z);               // ZZ
+    st<L, ES>(cs, b);
+    mulm(t, a, cs);              // Z^3
+    st<L, ES>(c1, t);
+    ld<L, 1>(a, xA);
+    mulm(h, a, cs);              // xA ZZ
+    ld<L, ES>(b, X);
+    P::subk(h, h, b, c_fc.p16, 16);  // H = xA ZZ - X
+    ld<L, 1>(a, yA);
+    if (negate) P::negk(a, a, c_fc.p2, 2);
+    mulm(n1, a, c1);             // yA Z^3
+    ld<L, ES>(a, Y);
+    P::subk(n1, n1, a, c_fc.p16, 16);  // N1
+    mulm(zr, h, Z);              // ZR = Z H
+    st<L, ES>(c0, h);
+    sqrm(a, h, c0);              // H^2
+    st<L, ES>(ci, a);
+    mulm(t, h, ci);              // H^3
+    mulm(u, b, ci);              // U = X H^2   (b still holds X)
+    st<L, ES>(c1, t);            // H^3 (Z^3 is dead)
+    ld<L, ES>(a, Y);
+    mulm(w, a, c1);              // W = Y H^3
+    st<L, ES>(cs, n1);           // N1 (ZZ is dead)
+    sqrm(xr, n1, cs);            // N1^2
+    P::subk(xr, xr, t, c_fc.p4, 4);
+    dbl(a, u);
+    P::subk(xr, xr, a, c_fc.p8, 8);    // XR = N1^2 - H^3 - 2U
+    P::subk(a, u, xr, c_fc.p16, 16);   // U - XR
+    mulm(t, a, cs);              // N1 (U - XR)
+    P::subk(t, t, w, c_fc.p4, 4);      // YR
+    P::subk(h, xr, u, c_fc.p4, 4);     // H2 = XR - U   (H is dead)
+    P::subk(n2, t, w, c_fc.p4, 4);     // N2 = YR - W
+    st<L, ES>(c0, h);            // H2
+    st<L, ES>(ci, n2);           // N2
+    P::template dot2_stream<ES>(an, xr, c0, n1, ci);   // An = XR H2 + N1 N2
+    mulm(sn, n1, c0);            // N1 H2
+    P::addn(sn, sn, n2);         // Sn
+    sqrm(a, h, c0);              // A2 = H2^2
+    st<L, ES>(c1, a);            // A2 (H^3 is dead)
+    mulm(b, u, c1);              // B2 = U A2
+    mulm(t, xr, c1);             // C2 = XR A2
+    sqrm(a, n2, ci);             // N2^2
+    P::subk(a, a, b, c_fc.p4, 4);
+    P::subk(a, a, t, c_fc.p4, 4);      // XS
+    st<L, ES>(X, a);
+    P::subk(t, t, b, c_fc.p4, 4);      // C2 - B2
+    st<L, ES>(c1, t);
+    P::subk(b, b, a, c_fc.p16, 16);    // B2 - XS
+    mulm(a, b, ci);              // N2 (B2 - XS)
+    mulm(t, w, c1);              // W (C2 - B2)
+    P::subk(a, a, t, c_fc.p4, 4);      // YS
+    st<L, ES>(Y, a);
+    mulm(t, zr, c0);             // ZS = ZR H2
+    st<L, ES>(Z, t);
+    mulm(a, zr, Z);              // Dn = ZR ZS
+    st<L, ES>(ci, a);            // Dn (N2 is dead)
+    sqrm(n2, a, ci);             // cs = Dn^2            (kept in registers until its slot is free)
+    mulm(b, an, ci);             // An Dn
+    P::negk(b, b, c_fc.p4, 4);   // c1 = -An Dn
+    mulm(t, sn, ci);             // Sn Dn
+    st<L, ES>(c1, zr);           // ZR (C2 - B2 is dead)
+    mulm(a, t, c1);              // Sn Dn ZR
+    P::negk(a, a, c_fc.p4, 4);   // ci = -Sn Dn ZR
+    st<L, ES>(ci, a);
+    st<L, ES>(cs, w);            // W (N1 is dead)
+    mulm(t, sn, cs);             // Sn W
+    mulm(a, u, c0);              // U H2
+    P::addn(a, a, an);           // U H2 + An
+    st<L, ES>(c1, a);
+    mulm(zr, u, c1);             // U (U H2 + An)
+    P::subk(t, t, zr, c_fc.p4, 4);
+    mulm(a, t, c0);              // c0 = H2 (Sn W - U (U H2 + An))
+    st<L, ES>(c0, a);
+    st<L, ES>(c1, b);
+    st<L, ES>(cs, n2);
+  }
+
   // ---- final exponentiation f^((p^2-1)/n) = (conj(f)/f)^l = (conj(f)^2 / N(f))^l, fused.
   // Step 1: f <- conj(f)^2 = (f0^2 - f1^2) - 2 f0 f1 i and nrm <- N(f) = f0^2 + f1^2.  3 products.
   // in: f < 8p.  out: f.re < 4p, f.im < 4p, nrm < 4p.

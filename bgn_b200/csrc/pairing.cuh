@@ -243,31 +243,9 @@ struct MillerTeam {
     MA::sqr2(slot(tid, S_F0), slot(tid, S_F0 + 1));
     if (t + a.dE < a.dM + a.dE - 1) MA::sqr2(slot(tid, S_F1), slot(tid, S_F1 + 1));
     if (t < a.dM && flagsA()[tid]) {
-      Loc<L> t0, t1, t2, t3, t4, t5, t6, t7;
       size_t idx = (size_t)unit * a.dM + t;
-      MA::norm1(slot(tid, S_X));
-      MA::norm1(slot(tid, S_Y));
-      MA::norm1(slot(tid, S_Z));
-      if (GP) {
-        // interleaved layout: the three-address step works on unit-stride copies
-        Loc<L> X, Y, Z, cs, c1, c0, ci;
-        s_out(X.v(), slot(tid, S_X));
-        s_out(Y.v(), slot(tid, S_Y));
-        s_out(Z.v(), slot(tid, S_Z));
-        GG::dadd_para(X.v(), Y.v(), Z.v(), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB, cs.v(), c1.v(), c0.v(), ci.v(),
-                      t0.v(), t1.v(), t2.v(), t3.v(), t4.v(), t5.v(), t6.v(), t7.v());
-        s_in(slot(tid, S_X), X.v());
-        s_in(slot(tid, S_Y), Y.v());
-        s_in(slot(tid, S_Z), Z.v());
-        s_in(slot(tid, S_CR), cs.v());
-        s_in(slot(tid, S_AR), c1.v());
-        s_in(slot(tid, S_BI), c0.v());
-        s_in(slot(tid, S_C3), ci.v());
-      } else {
-        GG::dadd_para(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
-                      slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), slot(tid, S_C3), t0.v(), t1.v(), t2.v(), t3.v(),
-                      t4.v(), t5.v(), t6.v(), t7.v());
-      }
+      MA::dadd_para(slot(tid, S_X), slot(tid, S_Y), slot(tid, S_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
+                    slot(tid, S_CR), slot(tid, S_AR), slot(tid, S_BI), slot(tid, S_C3));
     }
   }
   // phase B of such a step: fold parabola_i(B_k) into the slot i+k
@@ -408,7 +386,7 @@ struct MillerTeam {
     for (int idx = 1; idx < n; idx++) {
       int d = c_pc.naf[idx];
       const bool add = d != 0 && idx != n - 1;
-      if (PARA && add) {  // never the first step: a NAF has no two adjacent non-zero digits
+      if (PARA && a.para && add) {  // never the first step: a NAF has no two adjacent non-zero digits
         phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
         sync();
         phaseB_para();

@@ -138,14 +138,9 @@ struct MillerSplit {
       return;
     }
     if (t < a.dM && flagsA()[col]) {
-      Loc<L> t0, t1, t2, t3, t4, t5, t6, t7;
       size_t idx = (size_t)unit * a.dM + t;
-      MA::norm1(cslot(col, C_X));
-      MA::norm1(cslot(col, C_Y));
-      MA::norm1(cslot(col, C_Z));
-      G<L>::dadd_para(cslot(col, C_X), cslot(col, C_Y), cslot(col, C_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
-                      cslot(col, C_CR), cslot(col, C_AR), cslot(col, C_BI), cslot(col, C_C3), t0.v(), t1.v(), t2.v(),
-                      t3.v(), t4.v(), t5.v(), t6.v(), t7.v());
+      MA::dadd_para(cslot(col, C_X), cslot(col, C_Y), cslot(col, C_Z), a.Mx + idx * L, a.My + idx * L, op == MOP_SUB,
+                    cslot(col, C_CR), cslot(col, C_AR), cslot(col, C_BI), cslot(col, C_C3));
     }
   }
   BGN_DEV void phaseB_para() {

@@ -54,7 +54,8 @@ struct MillerArgs {
   // global scratch of the parabola steps (pairing.cuh: BGN_PARABOLA): x^2 / y of every evaluation point,
   // [count * dE][L] ([dE][L] with e_bcast); written by the kernel's init, read in its phase B
   uint32_t* evw;
-  int para;  // k_miller_split only: use the parabola steps (api.cu: launch_miller_split chooses by block geometry)
+  int para;  // use the parabola steps: k_miller when a Miller point serves >= 3 evaluation points (below that the
+             // 5 extra products of the merged step outweigh the saved F_p^2 products), k_miller_split by block geometry
 };
 
 // Pairing with a FIXED first argument (makeL2: e(C, P) = e(P, C), bgn.go:316-321; level-1 decrypt;

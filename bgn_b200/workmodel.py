@@ -97,12 +97,14 @@ def line_products(L: int, eval_norm: bool = None) -> int:
 
 
 PARABOLA = True  # pairing.cuh BGN_PARABOLA: a NAF digit != 0 is one parabola step
+BGN_PARABOLA_BUILD = True  # the library is built with BGN_PARABOLA (MillerTeam::init forms x^2 / y)
 
 
-def parabola_on(L: int, eval_norm: bool = None, parabola: bool = None) -> bool:
+def parabola_on(L: int, eval_norm: bool = None, parabola: bool = None, dE: int = 11) -> bool:
+    """api.cu run_miller: the team kernel merges doubling and addition where a Miller point serves >= 3 evaluation points"""
     eval_norm = EVAL_NORM if eval_norm is None else eval_norm
     parabola = PARABOLA if parabola is None else parabola
-    return bool(parabola and eval_norm)
+    return bool(parabola and eval_norm and dE >= 3)
 
 
 def para_products(L: int) -> int:
@@ -112,7 +114,7 @@ def para_products(L: int) -> int:
     return (4 * L * L + L) + (3 * L * L + 2 * (L * L + L) if line_lazy(L) else 3 * full)
 
 
-DADD_MULS, DADD_SQRS = 24, 6  # curve.cuh G::dadd_para (three-address code: its squarings are dedicated ones)
+DADD_MULS, DADD_SQRS, DADD_DOT2 = 28, 0, 1  # fused.cuh MF::dadd_para: 22 products + 6 squarings (as products) + one dot product
 
 
 def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bool = None, parabola: bool = None) -> int:
@@ -120,7 +122,7 @@ def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bo
     multiply-and-reduce of 2L^2 + L, except the lines (line_products), the squarings where the
     dedicated routine is used (L (L + 1) / 2 + L^2 + L), and -- with normalised evaluation points --
     one inversion (its two products of glue) and one product per evaluation point before the loop.
-    With the parabola step a NAF digit != 0 costs dM dadd_para (24 products, 6 squarings) and dM dE
+    With the parabola step a NAF digit != 0 costs dM dadd_para (28 products and a dot product) and dM dE
     para_products instead of a doubling and an addition step with dM dE lines each; the x^2 / y of the
     evaluation points is one more product each before the loop."""
     eval_norm = EVAL_NORM if eval_norm is None else eval_norm
@@ -132,10 +134,12 @@ def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bo
     nslots = dM + dE - 1
     fe = final_exp_modmuls(p, l, L, nslots, dE)
     prep = dE * (GCD_INV_MODMULS + 1) if eval_norm else 0
+    if eval_norm and BGN_PARABOLA_BUILD:
+        prep += dE   # x^2 / y of every evaluation point is formed whether or not the launch uses it
     nsq = miller_unit_squarings(p, n, l, dM, dE)   # dedicated squarings inside the fused routines (FUSED_SQR)
-    if parabola_on(L, eval_norm, parabola):
-        plain = (D - A) * dM * 12 + (D - 1) * nslots * 2 + fe + prep + dE   # fused products outside lines / parabolas
-        return ((plain - nsq + A * dM * DADD_MULS) * full + (nsq + A * dM * DADD_SQRS) * sq
+    if parabola_on(L, eval_norm, parabola, dE):
+        plain = (D - A) * dM * 12 + (D - 1) * nslots * 2 + fe + prep   # fused products outside lines / parabolas
+        return ((plain - nsq + A * dM * DADD_MULS) * full + (nsq + A * dM * DADD_SQRS) * sq + A * dM * DADD_DOT2 * (3 * L * L + L)
                 + (D - A) * dM * dE * line_products(L, eval_norm) + A * dM * dE * para_products(L))
     mm = miller_unit_modmuls(p, n, l, dM, dE)
     lines = (D + A) * dM * dE
@@ -148,13 +152,13 @@ def miller_unit_lines(n: int, dM: int, dE: int, L: int = 17) -> int:
     naf = naf_digits(n)
     D = len(naf) - 1
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
-    return ((D - A) if parabola_on(L) else (D + A)) * dM * dE
+    return ((D - A) if parabola_on(L, dE=dE) else (D + A)) * dM * dE
 
 
 def miller_unit_parabolas(n: int, dM: int, dE: int, L: int = 17) -> int:
     naf = naf_digits(n)
     A = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0)
-    return A * dM * dE if parabola_on(L) else 0
+    return A * dM * dE if parabola_on(L, dE=dE) else 0
 
 
 def miller_unit_modmuls(p: int, n: int, l: int, dM: int, dE: int) -> int:

@@ -65,7 +65,7 @@ void sim_miller(const MillerArgs& a0, int nblocks, int nt) {
     int n = c_pc.naf_len;
     for (int idx = 1; idx < n; idx++) {
       int d = c_pc.naf[idx];
-      if (MillerTeam<L, EG>::PARA && d != 0 && idx != n - 1) {
+      if (MillerTeam<L, EG>::PARA && a.para && d != 0 && idx != n - 1) {
         for (auto& t : T) t.phaseA_dadd(d > 0 ? MOP_ADD : MOP_SUB);
         for (auto& t : T) t.phaseB_para();
         continue;

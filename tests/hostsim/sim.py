@@ -252,7 +252,7 @@ class Sim:
         return x, y, inf
 
     # ---- kernels
-    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2, wide=False):
+    def miller(self, M, dM, E, dE, count, out_slots, e_bcast=False, teams_per_block=2, wide=False, para=None):
         Mx, My, Mi = self.g1_arrays(M)
         Ex, Ey, Ei = self.g1_arrays(E)
         nout = count * out_slots
@@ -260,7 +260,7 @@ class Sim:
         oim = np.zeros((nout, self.L), dtype=np.uint32)
         a = MillerArgs(P32(Mx), P32(My), P8(Mi), P32(Ex), P32(Ey), P8(Ei), None, P32(ore), P32(oim), Mx.shape[0],
                        Ex.shape[0], nout, 1 if e_bcast else 0, dM, dE, out_slots, count, teams_per_block,
-                       teams_per_block * dE + 1, 0, None, 1)  # one idle thread per group: exercises the inactive path
+                       teams_per_block * dE + 1, 0, None, (1 if dE >= 3 else 0) if para is None else para)  # (one idle thread per group)
         groups = 2 if count > teams_per_block else 1
         nt = groups * (teams_per_block * dE + 1)
         nblocks = (count + groups * teams_per_block - 1) // (groups * teams_per_block)

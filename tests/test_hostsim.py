@@ -344,10 +344,10 @@ def test_work_model_matches_executed_products(kb):
     executed = (fused * (2 * L * L + L) + wide[0] * L * L + wide[1] * (L * L + L) + wide[3] * (3 * L * L + L)
                 + wide[4] * (L * (L + 1) // 2) + wide[5] * (4 * L * L + L))
     assert executed == workmodel.miller_unit_products(par.p, par.n, par.l, v["d1"], v["d2"])
-    assert wide[3] == (workmodel.miller_unit_lines(par.n, v["d1"], v["d2"], L) if workmodel.EVAL_NORM else 0)
-    assert wide[5] == workmodel.miller_unit_parabolas(par.n, v["d1"], v["d2"], L)
     naf = workmodel.naf_digits(par.n)
-    adds = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0) if workmodel.parabola_on(L) else 0
+    adds = sum(1 for i in range(1, len(naf) - 1) if naf[i] != 0) if workmodel.parabola_on(L, dE=v["d2"]) else 0
+    assert wide[3] == (workmodel.miller_unit_lines(par.n, v["d1"], v["d2"], L) if workmodel.EVAL_NORM else 0) + adds * v["d1"] * workmodel.DADD_DOT2
+    assert wide[5] == workmodel.miller_unit_parabolas(par.n, v["d1"], v["d2"], L)
     assert wide[4] == workmodel.miller_unit_squarings(par.p, par.n, par.l, v["d1"], v["d2"]) + adds * v["d1"] * workmodel.DADD_SQRS
     assert (wide[0] > 0) == workmodel.line_lazy(L)
     assert workmodel.pick_limbs(par.p) == S.L
