@@ -153,7 +153,7 @@ struct bgn_ctx {
   uint32_t* linesP = nullptr;  // line table of the Miller loop of P (MillerFixedArgs::lines), built on first use
   uint32_t* linesPq = nullptr; // line table of q1*P, built with the secret: level-1 Decrypt is e(C, q1 P) = e(C, P)^q1
   bool dec_pair_q1 = true;     // level-1 Decrypt through linesPq (option dec_pair_q1)
-  int split_para = -1;         // k_miller_split with parabola steps: -1 by block geometry, 0 never, 1 always (option split_para)
+  int split_para = -1;         // k_miller_split with parabola steps: -1 / 1 on (default), 0 off (option split_para)
   bool fixed_lines = true;     // e(., P) through the line table (BGN_FIXED_LINES=0: the general kernel)
   int enc_window = 0;          // window bits of Q's table: 0 = widest of 16/18/20 within enc_table_max; 8 | 16 | 18 | 20 | 22 | 24 (BGN_ENC_WINDOW)
   size_t enc_table_max = (size_t)6 << 30;  // bound of the automatic choice (option enc_table_max_mb)
@@ -518,12 +518,9 @@ void launch_miller_split(bgn_ctx* c, const SplitGeom& g, const G1Arr& M, int dM,
   a.teams_per_group = tpb;
   a.group_threads = nt;
   a.evw = arena_get<uint32_t>(c, (e_bcast ? (size_t)dE : count * (size_t)dE) * c->L);
-  // The parabola step loads the Miller-point half of a thread pair with 30 three-address products against the
-  // other half's 8 squarings; with 3 or 5 warps per role the four schedulers hold the roles unevenly and the
-  // separate steps are faster (measured, profiles/r02_split_ab_v5.json: 1024 units 69.6 against 66.3 ms, 2048
-  // units 95.2 against 89.5 ms; 1, 2, 4 and 6 warps per role gain 0 - 12 %).
-  const int wpr = (tpb * dE + 31) / 32;
-  a.para = c->split_para >= 0 ? c->split_para : ((wpr == 3 || wpr == 5) ? 0 : 1);
+  // parabola steps: faster at every block geometry since the merged step is a fused routine (measured,
+  // profiles/r02_split_para_ab.json: 1 - 6 warps per role gain 4 - 11 %); split_para = 0 is the A/B switch
+  a.para = c->split_para >= 0 ? c->split_para : 1;
   Timer t(c, "k_miller_split");
   CK(c->Eo->miller_split_set_smem(smem));
   c->Eo->miller_split(cfg(c, (count + tpb - 1) / tpb, nt, smem), a);
@@ -621,12 +618,12 @@ void run_miller(bgn_ctx* c, const G1Arr& M, int dM, const G1Arr& E, int dE, int 
       auto gt_off = [&](size_t units) { return GtArr{out.re + units * out_slots * c->L, out.im + units * out_slots * c->L, out.N - units * out_slots}; };
       const size_t full = count / cap_std, rem = count % cap_std;
       // Time model in units of one full wave of k_miller (measured at 11 x 11 slots, 17 limbs:
-      // profiles/r02_split_ab_v5.json).  A split wave's time depends on the warps each thread role
-      // occupies per SM: 1: 0.50, 2: 0.58, 3: 0.68, 4: 0.60, 5: 0.92, 6 (full): 0.87.  The team
+      // profiles/r02_split_para_ab.json, r02_split_ab_v7.json).  A split wave's time depends on the warps each
+      // thread role occupies per SM: 1 - 2: 0.56, 3 - 4: 0.63, 5: 0.90, 6 (full): 0.84.  The team
       // kernel: a batch within half a wave (one warp per scheduler) 0.76, anything else whole waves.
       auto t_split = [&](size_t n) {
         const size_t u = (n + sms - 1) / sms, w = (u * (size_t)dE + 31) / 32;
-        static const double tw[7] = {0.50, 0.50, 0.58, 0.68, 0.60, 0.92, 0.87};
+        static const double tw[7] = {0.56, 0.56, 0.56, 0.63, 0.63, 0.90, 0.84};
         return tw[std::min<size_t>(w, 6)];
       };
       const double t_a = count > cap_std ? (double)((count + cap_std - 1) / cap_std) : (count * 2 <= cap_std ? 0.76 : 1.0);
