@@ -88,6 +88,7 @@ const char* bgn_global_last_error(void);
  *                                is not of odd order.
  *   "dec_lucas"    0 | 1         Decrypt through the Lucas ladder when one giant step suffices (default 1)
  *   "fixed_lines"  0 | 1         e(., P) through the recorded line table (default 1)
+ *   "split_para"   -1 | 0 | 1    the sub-wave MultPoly kernel with merged doubling-and-addition steps (default on; 0: A/B)
  *   "dec_pair_q1"  0 | 1         level-1 Decrypt as ONE pairing e(C, q1 P) through a line table of q1*P built by
  *                                bgn_ctx_set_secret (default 1), instead of e(C, P) followed by the exponentiation
  *   "fixed_pair"   -1 | 0 | 1    e(., P) with one pairing split over a pair of lanes: -1 (default) below the

@@ -418,11 +418,13 @@ def test_sim_miller_loop_variants(loop):
 @pytest.mark.parametrize("flags,tag", [(("-DBGN_MILLER_GP=1", "-DBGN_MILLER_NT=32", "-DBGN_LINE_LAZY=0"), "_gp"),
                                        (("-DBGN_MILLER_GP=1", "-DBGN_MILLER_NT=32"), "_gplazy"),
                                        (("-DBGN_LINE_KARATSUBA=2",), "_kara"),
-                                       (("-DBGN_EVAL_NORM=0",), "_plainlines")])
+                                       (("-DBGN_EVAL_NORM=0",), "_plainlines"),
+                                       (("-DBGN_PARABOLA=0",), "_noparabola")])
 def test_sim_miller_layout_and_multiplier_variants(flags, tag):
     """Build variants of the Miller kernel: the thread-interleaved layout with the private slots in
     global memory (what the 1024-bit field ships with), the Karatsuba multiplier (measured, not
-    shipped) and the plain line form (evaluation points not normalised: the A/B switch of DESIGN 2.4)
+    shipped), the plain line form (evaluation points not normalised: the A/B switch of DESIGN 2.4) and the
+    separate doubling / addition steps (no parabola: the A/B switch of DESIGN 2.5)
     produce the same bytes and stay within the proven ranges."""
     try:
         sim.use_variant(None, flags, tag)
