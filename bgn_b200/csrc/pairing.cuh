@@ -14,7 +14,10 @@
 //    evaluated at its B_k into the <= 2 output slots it owns, so the f^2
 //    squarings and the final exponentiation happen once per OUTPUT slot
 //    (d1+d2-1 of them), not once per pairing (d1*d2);
-//  * a plain pairing batch is the same program with TS = 1.
+//  * a plain pairing batch is the same program with TS = 1;
+//  * (round 2) line values are scaled by F_p factors that the final exponentiation removes -- evaluation points
+//    normalised to (x / y, 1 / y), BGN_EVAL_NORM -- and a NAF digit != 0 is ONE doubling-and-addition step whose
+//    tangent and chord are merged into a parabola, BGN_PARABOLA.
 #pragma once
 #include "curve.cuh"
 #include "fused.cuh"

@@ -25,6 +25,10 @@
 //
 //   1.5 (2L^2 + L) + (3L^2 + L) = 1776 products per lane and doubling step at L = 17 against the
 //   3264 one thread spends (fused.cuh: sqr2 + line_mul_lazy_f), 2.5 shuffle exchanges per step.
+//   A doubling-and-addition step is ONE table entry, a parabola [csn | c1n | c0n] (pairing.cuh:
+//   MillerFixed::record): lane 0 forms csn xB^2 + c0n, lane 1 c1n xB, their sum is the real part, the
+//   imaginary part is yB -- 2 (2L^2 + L) + (3L^2 + L) per lane where a doubling step followed by an
+//   addition step cost 2 (2L^2 + L) + 2 (3L^2 + L).
 //   The dot product (arith.cuh: Fp::dot2) accumulates both multiplicands row by row into one CIOS
 //   window, so the F_p^2 product needs no double-width temporaries.
 //

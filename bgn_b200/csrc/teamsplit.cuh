@@ -20,6 +20,9 @@
 // (team, t) -- 16 dE slots per team where the uniform layout of pairing.cuh would take 24 dE -- so an
 // SM holds 14 teams of 22 threads (10 warps) where k_miller holds 23 teams of 11.
 //
+// A NAF digit != 0 is one merged doubling-and-addition step with a parabola (pairing.cuh: BGN_PARABOLA), split the
+// same way: (t, 0) runs fused.cuh dadd_para while (t, 1) squares, then each half folds its share of the parabolas.
+//
 // Same results, bit for bit: the product of the two partial Miller values is the Miller value.
 // Unit-stride layout only (up to 17 limbs); the 1024-bit field keeps k_miller.
 #pragma once
