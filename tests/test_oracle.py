@@ -218,3 +218,27 @@ def test_nondet_poly_golden_section_is_reproducible(kb):
     assert ops["mult_poly"]["draws_used"] == 2 * 3 * 2 and ops["add_poly"]["draws_used"] == 2 and ops["neg_poly"]["draws_used"] == 3
     cb = g["coord_bytes"]
     assert ops["mult_poly"]["out"][-1] == (b"\x00" * (cb - 1) + b"\x01" + b"\x00" * cb).hex()
+
+
+def test_parabola_step_identity():
+    """the Miller loop with merged doubling-and-addition steps (ELM parabola in Jacobian coordinates,
+    normalised evaluation point) gives the oracle's pairing value -- the arithmetic the device routines
+    curve.cuh G::dadd_para / fused.cuh MF::dadd_para and para_mul implement, in plain integers."""
+    import importlib.util
+    import os
+    import random
+    spec = importlib.util.spec_from_file_location(
+        "parabola_proto", os.path.join(os.path.dirname(__file__), "..", "tools", "_proto", "parabola.py"))
+    proto = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(proto)
+    from conftest import load_golden
+    from oracle import bgn_oracle as O
+    for kb in (64, 128):
+        g = load_golden(kb)
+        par = O.A1Params(int(g["p"], 16), int(g["n"], 16), g["l"])
+        P = O.g1_from_bytes(bytes.fromhex(g["P"]), par)
+        rng = random.Random(kb)
+        for _ in range(3):
+            A = O.g1_mul(rng.randrange(1, par.n), P, par.p)
+            B = O.g1_mul(rng.randrange(1, par.n), P, par.p)
+            assert O.final_exp(proto.miller_parabola(A, B, par), par) == O.pairing(A, B, par)
