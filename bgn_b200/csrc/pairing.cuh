@@ -235,7 +235,7 @@ struct MillerTeam {
       s_in(slot(tid, S_EX), a.Ex + eidx(t) * L);
       s_in(slot(tid, S_EY), a.Ey + eidx(t) * L);
       if (NORM) MA::eval_normalise(slot(tid, S_EX), slot(tid, S_EY));
-      if (PARA) MA::mul_to_unit(a.evw + eidx(t) * L, a.Ex + eidx(t) * L, slot(tid, S_EX));  // x^2 / y = x * (x / y)
+      if (PARA && a.para) MA::mul_to_unit(a.evw + eidx(t) * L, a.Ex + eidx(t) * L, slot(tid, S_EX));  // x^2 / y = x * (x / y)
     }
   }
 

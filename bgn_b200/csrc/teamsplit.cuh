@@ -98,7 +98,7 @@ struct MillerSplit {
       FF::copy(cslot(col, C_EX), a.Ex + e * L);
       FF::copy(cslot(col, C_EY), a.Ey + e * L);
       if (BGN_EVAL_NORM) MA::eval_normalise(cslot(col, C_EX), cslot(col, C_EY));  // (x / y, 1 / y): fused.cuh line_mul_n
-      if (PARA) MA::mul_to_unit(a.evw + e * L, a.Ex + e * L, cslot(col, C_EX));         // x^2 / y
+      if (PARA && a.para) MA::mul_to_unit(a.evw + e * L, a.Ex + e * L, cslot(col, C_EX));  // x^2 / y
     }
   }
 

@@ -97,7 +97,6 @@ def line_products(L: int, eval_norm: bool = None) -> int:
 
 
 PARABOLA = True  # pairing.cuh BGN_PARABOLA: a NAF digit != 0 is one parabola step
-BGN_PARABOLA_BUILD = True  # the library is built with BGN_PARABOLA (MillerTeam::init forms x^2 / y)
 
 
 def parabola_on(L: int, eval_norm: bool = None, parabola: bool = None, dE: int = 11) -> bool:
@@ -134,8 +133,8 @@ def miller_unit_products(p: int, n: int, l: int, dM: int, dE: int, eval_norm: bo
     nslots = dM + dE - 1
     fe = final_exp_modmuls(p, l, L, nslots, dE)
     prep = dE * (GCD_INV_MODMULS + 1) if eval_norm else 0
-    if eval_norm and BGN_PARABOLA_BUILD:
-        prep += dE   # x^2 / y of every evaluation point is formed whether or not the launch uses it
+    if parabola_on(L, eval_norm, parabola, dE):
+        prep += dE   # x^2 / y of every evaluation point
     nsq = miller_unit_squarings(p, n, l, dM, dE)   # dedicated squarings inside the fused routines (FUSED_SQR)
     if parabola_on(L, eval_norm, parabola, dE):
         plain = (D - A) * dM * 12 + (D - 1) * nslots * 2 + fe + prep   # fused products outside lines / parabolas
